@@ -1,0 +1,243 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on seeded weights.
+
+Runs only in the build container (needs /root/reference, which is absent on the GPU box).
+The reference's `ASRModel` (tiny_audio/asr_modeling.py:47) is constructed offline through the four
+loader seams SURVEY.md Appendix A verified (no network / no checkpoints): its GLM-ASR encoder,
+Qwen3 LM and MLP projector receive the weights of `oracle.path_oracle.init_weights(cfg, seed)`, then
+`ASRModel.forward` + autograd + `torch.optim.AdamW` + `clip_grad_norm_` run exactly as
+scripts/train.py / HF Trainer would drive them (fp32, sdpa attention, dropout 0).
+
+Each fixture stores the config, the seeds, and sub-sampled reference outputs (everything is small;
+weights and inputs are regenerated from the seeds by the tests).
+
+usage:  python oracle/make_golden.py [--only NAME]
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import os
+import sys
+import time
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import path_oracle as po  # noqa: E402
+
+REF = "/root/reference"
+
+
+def load_reference():
+    """Import the reference's tiny_audio submodules under the alias `ref_tiny_audio` (the repo
+    ships its own `tiny_audio` shim, so the names must not collide).  The package __init__ is NOT
+    executed (it would pull diarization etc.)."""
+    pkg = types.ModuleType("ref_tiny_audio")
+    pkg.__path__ = [os.path.join(REF, "tiny_audio")]
+    sys.modules["ref_tiny_audio"] = pkg
+    mods = {}
+    for name in ("asr_config", "projectors", "asr_modeling", "asr_processing"):
+        spec = importlib.util.spec_from_file_location(
+            f"ref_tiny_audio.{name}", os.path.join(REF, "tiny_audio", f"{name}.py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"ref_tiny_audio.{name}"] = m
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods
+
+
+class StubTok:
+    """Attributes ASRModel reads from the tokenizer (asr_modeling.py:163-168, 305-342)."""
+    pad_token = "<|finetune_right_pad_id|>"
+    eos_token = "<|im_end|>"
+    padding_side = "right"
+    chat_template = ""
+    additional_special_tokens = ["<audio>"]
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.pad_token_id = min(151643, cfg.vocab - 2)
+        self.eos_token_id = po.IM_END % (cfg.vocab - 1) if po.IM_END >= cfg.vocab - 1 else po.IM_END
+        self.bos_token_id = None
+
+    def convert_tokens_to_ids(self, t):
+        return {"<audio>": self.cfg.audio_token_id, "<|im_end|>": self.eos_token_id,
+                "<|endoftext|>": self.pad_token_id}.get(t)
+
+    def get_vocab(self):
+        return {"<audio>": self.cfg.audio_token_id}
+
+    def __len__(self):
+        return self.cfg.vocab
+
+
+def build_reference_model(cfg: po.PathConfig, W, mods):
+    from transformers import GlmAsrEncoderConfig, Qwen3Config, Qwen3ForCausalLM, WhisperFeatureExtractor
+    from transformers.models.glmasr.modeling_glmasr import GlmAsrEncoder
+
+    ASRModel = mods["asr_modeling"].ASRModel
+    ASRConfig = mods["asr_config"].ASRConfig
+    enc_cfg = GlmAsrEncoderConfig(hidden_size=cfg.enc_dim, intermediate_size=cfg.enc_ffn,
+                                  num_hidden_layers=cfg.enc_layers, num_attention_heads=cfg.enc_heads,
+                                  num_key_value_heads=cfg.enc_heads, num_mel_bins=cfg.n_mels)
+    txt_cfg = Qwen3Config(hidden_size=cfg.lm_dim, intermediate_size=cfg.lm_ffn, num_hidden_layers=cfg.lm_layers,
+                          num_attention_heads=cfg.lm_heads, num_key_value_heads=cfg.lm_kv_heads,
+                          head_dim=cfg.lm_head_dim, vocab_size=cfg.vocab, rms_norm_eps=cfg.lm_eps,
+                          tie_word_embeddings=True, max_position_embeddings=40960,
+                          rope_parameters={"rope_theta": cfg.lm_rope_theta, "rope_type": "default"})
+
+    def _enc(cls, config, dtype):
+        m = GlmAsrEncoder._from_config(enc_cfg, attn_implementation=config.attn_implementation).to(dtype)
+        missing = m.load_state_dict(W["encoder"], strict=True)
+        m.requires_grad_(False)
+        m.eval()
+        return m
+
+    def _lm(cls, config, dtype):
+        m = Qwen3ForCausalLM._from_config(txt_cfg, attn_implementation=config.attn_implementation).to(dtype)
+        m.load_state_dict(W["lm"], strict=True)
+        m.tie_weights()
+        m.requires_grad_(False)
+        m.train(False)
+        return m
+
+    tok = StubTok(cfg)
+
+    def _tok(self, config):
+        self.tokenizer = tok
+        self.audio_token_id = cfg.audio_token_id
+
+    ASRModel._load_audio_encoder = classmethod(_enc)
+    ASRModel._load_language_model = classmethod(_lm)
+    ASRModel._init_tokenizer = _tok
+    ASRModel._create_feature_extractor = lambda self, config: WhisperFeatureExtractor(feature_size=cfg.n_mels)
+    acfg = ASRConfig(audio_config=enc_cfg, text_config=txt_cfg, model_dtype="float32", attn_implementation="sdpa",
+                     projector_type="mlp", projector_pool_stride=cfg.proj_k, projector_hidden_dim=cfg.proj_hidden,
+                     audio_token_dropout=0.0)
+    model = ASRModel(acfg)
+    model.projector.load_state_dict(W["projector"], strict=True)
+    return model
+
+
+def sub(t: torch.Tensor, n: int = 4096) -> np.ndarray:
+    """Deterministic strided sub-sample of a tensor (flattened)."""
+    f = t.detach().reshape(-1)
+    step = max(1, f.numel() // n)
+    return f[::step][:n].float().numpy().copy()
+
+
+CASES = {
+    # name: (cfg kwargs or 'full', batch, clip_s, pad_s, response_len, seed)
+    "small_b2_2s":   (dict(), 2, 2.0, None, 16, 11),
+    "small_b2_1s_pad30": (dict(), 2, 1.0, 30.0, 8, 12),     # reference behaviour through train.py: pad to 30 s
+    "small_b3_ragged": (dict(enc_layers=1, lm_layers=1), 3, 1.5, None, 8, 13),
+    "h2048_b2_2s":   (dict(proj_hidden=2048, enc_layers=1, lm_layers=1), 2, 2.0, None, 8, 14),
+    "full_b1_4s":    ("full", 1, 4.0, None, 32, 21),
+}
+
+
+def run_case(name, mods, outdir):
+    spec, B, clip_s, pad_s, R, seed = CASES[name]
+    cfg = po.FULL if spec == "full" else po.small_config(**spec)
+    torch.manual_seed(0)
+    t0 = time.time()
+    W = po.init_weights(cfg, seed=seed)
+    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s)
+    if name == "small_b3_ragged":
+        # ragged text: right-pad labels/ids of samples 1,2 and shrink their audio counts
+        ids, labels, am = batch["input_ids"].clone(), batch["labels"].clone(), batch["attention_mask"].clone()
+        pad_id = StubTok(cfg).pad_token_id
+        for b, cut in ((1, 3), (2, 5)):
+            ids[b, -cut:] = pad_id
+            labels[b, -cut:] = -100
+            am[b, -cut:] = 0
+        batch.update(input_ids=ids, labels=labels, attention_mask=am)
+    model = build_reference_model(cfg, W, mods)
+    model.train()
+
+    # reference feature extraction (HF WhisperFeatureExtractor through the collator's call, train.py:327-333)
+    fe = model.feature_extractor
+    L = int(batch["sample_lengths"][0])
+    audio = [batch["waveform"][b, :L].numpy() for b in range(B)]
+    pad_mode = "max_length" if pad_s == 30.0 else "longest"
+    feats = fe(audio, sampling_rate=16000, padding=pad_mode, return_attention_mask=True, return_tensors="pt")
+    mel_ref = feats.input_features
+    mask_ref = feats.attention_mask
+
+    ref_batch = dict(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"], labels=batch["labels"],
+                     input_features=mel_ref, audio_attention_mask=mask_ref,
+                     audio_token_counts=batch["audio_token_counts"])
+    n_items = int((batch["labels"] != -100).sum())
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.999),
+                            eps=1e-8, weight_decay=0.0)
+    out = model(**ref_batch, num_items_in_batch=torch.tensor(n_items))
+    loss = out.loss
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.projector.named_parameters()}
+    gnorm = torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+    opt.step()
+    new_params = {k: p.detach().clone() for k, p in model.projector.named_parameters()}
+
+    with torch.no_grad():
+        enc_out = model.audio_tower(input_features=mel_ref).last_hidden_state
+        model.projector.load_state_dict(W["projector"])
+        proj_out = model.projector(enc_out)
+        out_mean = model(**ref_batch)       # per-micro-batch mean path (loss_utils.py:35-36)
+
+    # ---- oracle vs reference (sanity; the test suite re-checks from the fixture) ----
+    ob = dict(batch)
+    ob["input_features"] = mel_ref
+    res = po.train_step(W, ob, cfg, lr=1e-3, max_grad_norm=1.0, num_items_in_batch=n_items)
+    mel_or = po.log_mel(batch["waveform"], cfg)
+    print(f"[{name}] ref loss {float(loss):.6f} oracle {float(res['loss']):.6f}  "
+          f"mel maxdiff {float((mel_or - mel_ref).abs().max()):.2e}  "
+          f"gnorm ref {float(gnorm):.6f} oracle {float(res['grad_norm']):.6f}  ({time.time()-t0:.1f}s)")
+
+    logits = out.logits.detach()
+    lab_pos = (torch.nn.functional.pad(batch["labels"], (0, 1), value=-100)[:, 1:] != -100)
+    fx = {
+        "cfg_json": np.array(str(cfg.to_dict())),
+        "seed": np.array(seed), "batch": np.array(B), "clip_s": np.array(clip_s),
+        "pad_s": np.array(pad_s if pad_s else 0.0), "response_len": np.array(R),
+        "input_ids": batch["input_ids"].numpy(), "labels": batch["labels"].numpy(),
+        "attention_mask": batch["attention_mask"].numpy(),
+        "audio_token_counts": batch["audio_token_counts"].numpy(),
+        "mel_mask": mask_ref.numpy().astype(np.int32),
+        "mel_shape": np.array(mel_ref.shape), "mel_sub": sub(mel_ref, 8192),
+        "mel_max": np.array(float(mel_ref.max())), "mel_mean": np.array(float(mel_ref.double().mean())),
+        "enc_shape": np.array(enc_out.shape), "enc_sub": sub(enc_out, 8192),
+        "proj_shape": np.array(proj_out.shape), "proj_sub": sub(proj_out, 8192),
+        "loss": np.array(float(loss)), "loss_mean_path": np.array(float(out_mean.loss)),
+        "num_items": np.array(n_items),
+        "logits_shape": np.array(logits.shape),
+        "logits_lab_sub": sub(logits[lab_pos], 8192),
+        "logits_argmax": logits.argmax(-1).numpy().astype(np.int64),
+        "grad_norm": np.array(float(gnorm)),
+    }
+    for k in grads:
+        fx["grad_sub." + k] = sub(grads[k], 4096)
+        fx["grad_l2." + k] = np.array(float(grads[k].norm()))
+        fx["new_param_sub." + k] = sub(new_params[k], 4096)
+    np.savez_compressed(os.path.join(outdir, name + ".npz"), **fx)
+    del model
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    mods = load_reference()
+    outdir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(outdir, exist_ok=True)
+    for name in CASES:
+        if args.only and name != args.only:
+            continue
+        run_case(name, mods, outdir)
+
+
+if __name__ == "__main__":
+    main()
