@@ -1,0 +1,215 @@
+/* tinyaudio_b200.h -- C ABI of libtinyaudio_b200.so (sm_100a).
+ *
+ * Drop-in boundary for tiny-audio's training hot path.  The reference is pure Python and has no FFI of its own;
+ * its boundary is the Python plugin surface (ASRModel / ASRProcessor / PROJECTOR_CLASSES).
+ * Each entry point below replaces the arithmetic behind one reference call site (cited as file:line;
+ * "HF:" = the transformers package the reference calls into).  The Python host side in tiny_audio_b200/ binds
+ * these with ctypes and keeps the reference's class / method names.
+ *
+ * Conventions
+ *   - every function returns 0 on success, negative on error; ta_last_error_string() gives the message
+ *   - all pointers are DEVICE pointers unless stated; the caller (PyTorch) owns every buffer
+ *   - no allocation, no host synchronisation, no retained pointers; launches go to `stream` (cudaStream_t)
+ *   - bf16 = __nv_bfloat16 storage; "ld*" = leading dimension in ELEMENTS
+ */
+#ifndef TINYAUDIO_B200_H
+#define TINYAUDIO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* ta_last_error_string(void);
+int ta_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM  C[M,N] = epilogue(A[M,K] . B[N,K]^T), bf16 in, fp32 accumulate (tcgen05 + TMEM + TMA)
+ * replaces every nn.Linear on the path: HF:models/glmasr/modeling_glmasr.py:198-206,223,228-239;
+ * HF:models/qwen3/modeling_qwen3.py:81-83,263-291,505; tiny_audio/projectors.py:66-71
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+    TA_EPI_BF16 = 0,       /* out bf16 = acc + bias                                              */
+    TA_EPI_BF16_GELU = 1,  /* out bf16 = gelu_erf(bf16(acc + bias))                              */
+    TA_EPI_BF16_RESID = 2, /* out bf16 = resid_bf16 + bf16(acc + bias)                           */
+    TA_EPI_F32_RESID = 3,  /* out f32  = resid_f32 + bf16(acc + bias)                            */
+    TA_EPI_F32 = 4,        /* out f32  = alpha * acc                                             */
+    TA_EPI_SWIGLU = 5,     /* B rows interleaved [64 gate | 64 up]: out bf16 [M,N/2] = silu(g)*u; out2 = (g,u) stash */
+    TA_EPI_SWIGLU_BWD = 6  /* acc = d(h) [M,N]; aux = (g,u) stash [M,2N]; out bf16 [M,2N] = (d gate | d up)          */
+};
+
+typedef struct ta_gemm_epilogue {
+    void* out;
+    long long ldo;
+    const float* bias;  /* [N] fp32 or NULL */
+    const void* resid;  /* RESID modes */
+    long long ldr;      /* 0 -> ldo */
+    void* out2;         /* SWIGLU: optional (gate, up) stash [M,N] bf16 */
+    long long ldo2;
+    const void* aux;    /* SWIGLU_BWD: the stash */
+    long long ldaux;
+    float alpha;        /* F32 mode scale; 0 -> 1 */
+} ta_gemm_epilogue;
+
+int ta_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epilogue_mode,
+                 const ta_gemm_epilogue* epilogue, void* stream);
+int ta_gemm_set_tile_n(int bn); /* 0 = auto, 128, 256 (testing / tuning) */
+
+
+/* ------------------------------------------------------------------------------------------------
+ * a1. log-mel front end  (replaces WhisperFeatureExtractor._torch_extract_fbank_features,
+ *     HF:models/whisper/feature_extraction_whisper.py:135-164; mel bank :95-103)
+ *   wave (B, L) fp32 zero-padded clips; T = L / 160 frames.  workspace: ta_logmel_workspace_floats().
+ *   out_f32 (B,128,T) fp32 "input_features" (optional); out_conv1_im2col bf16 [B*T, 384] (optional):
+ *   row (b,t) = [mel(t-1) | mel(t) | mel(t+1)], the A operand of conv1 (k=3, pad=1) as a GEMM.
+ * ---------------------------------------------------------------------------------------------- */
+int ta_logmel_workspace_floats(int B, int L, long long* n_floats);
+int ta_logmel_fwd(const float* wave, long long ld_wave, int B, int L, float* workspace, float* out_f32,
+                  void* out_conv1_im2col_bf16, void* stream);
+/* features computed by the reference's CPU collator (scripts/train.py:327-333) -> conv1 operand */
+int ta_mel_to_conv1_im2col(const float* mel /*(B,128,T)*/, int B, int T, void* out_conv1_im2col_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * attention (flash, fp32 softmax).  q/k/v/o are [B, S, heads, head_dim] views with arbitrary row strides
+ * (elements between consecutive tokens), so they can point into fused qkv buffers.
+ *   encoder: HF:models/glmasr/modeling_glmasr.py:208-221 (non-causal, no mask, 20 x 64)
+ *   decoder: HF:models/qwen3/modeling_qwen3.py:273-291 + HF:integrations/sdpa_attention.py (causal GQA 16/8 x 128)
+ * lse: [B, Hq, S] fp32 (natural log), optional in forward.
+ * backward: dsum_ws [B,Hq,S] fp32 scratch; dq_acc [B,S,Hq*hd] fp32 (zeroed inside); dk/dv bf16.
+ * ---------------------------------------------------------------------------------------------- */
+int ta_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int Hq, int Hkv,
+                int head_dim, long long q_rs, long long k_rs, long long v_rs, long long o_rs, int causal, float scale,
+                void* stream);
+int ta_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                float* dsum_ws, float* dq_acc, void* dk, void* dv, int B, int S, int Hq, int Hkv, int head_dim,
+                long long q_rs, long long k_rs, long long v_rs, long long o_rs, long long do_rs, long long dq_rs,
+                long long dk_rs, long long dv_rs, int causal, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * HBM-bound building blocks (exported for unit parity tests; the engines below call them internally)
+ * ---------------------------------------------------------------------------------------------- */
+int ta_im2col_k3(const void* x /*bf16 [B,T,C]*/, void* out /*bf16 [B*T2, 3C]*/, int B, int T, int C, int stride, void* stream);
+int ta_layernorm_bf16(const void* x, const float* w, const float* b, void* y, long long rows, int D, float eps, void* stream);
+int ta_rmsnorm_f32(const float* x, const float* w, void* y_bf16, const int* row_index, long long rows, int D, float eps, void* stream);
+int ta_rmsnorm_f32_bwd(const void* dy_bf16, const float* x, const float* w, float* dx, const int* row_index, long long rows,
+                       int D, float eps, int accumulate, void* stream);
+int ta_enc_rope(void* qkv, const float* cos_t, const float* sin_t, long long rows, int S, int H, int hd, int rot_dim, void* stream);
+int ta_lm_qknorm_rope_fwd(const void* qkv, void* qk, const float* q_norm_w, const float* k_norm_w, const float* cos_t,
+                          const float* sin_t, long long M, int S, int Hq, int Hkv, float eps, void* stream);
+int ta_lm_qknorm_rope_bwd(const void* qkv, const float* dq, const void* dk, const void* dv, void* dqkv, const float* q_norm_w,
+                          const float* k_norm_w, const float* cos_t, const float* sin_t, long long M, int S, int Hq, int Hkv,
+                          float eps, void* stream);
+int ta_proj_norm_fwd(const void* x_bf16, const float* w, void* y, long long rows, int D, float eps, int gelu, void* stream);
+int ta_proj_norm_bwd(const void* x_bf16, const float* w, const void* dy, int dy_is_f32, void* dx_bf16, float* dw, long long rows,
+                     int D, float eps, int gelu, void* stream);
+/* tiny_audio/asr_modeling.py:27-44 (_gather_audio_embeds) + :511-515 (masked_scatter): exact index semantics */
+int ta_audio_index(const long long* input_ids, const long long* token_counts, int* src_row, int B, int S, int n_a,
+                   long long audio_token_id, void* stream);
+int ta_embed_scatter(const long long* input_ids, const int* src_row, const float* embed_table, const float* audio_embeds,
+                     float* inputs_embeds, long long n_tok, int D, long long vocab, void* stream);
+int ta_audio_grad_gather(const int* src_row, const float* d_inputs_embeds, float* d_audio_embeds, long long n_tok, int D, void* stream);
+/* HF:loss/loss_utils.py:28-67 on the labelled rows only; loss_sum += sum_rows(CE) * inv_items; logits <- d(logits) */
+int ta_ce_fwd_bwd(void* logits_bf16, long long ld, const int* targets, long long rows, int V, int Vpad, float inv_items,
+                  float* loss_sum, float* row_loss, int write_grad, void* stream);
+int ta_transpose_bf16(const void* in, void* out, int R, int C, long long ld_in, long long ld_out, void* stream);
+int ta_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+/* tiny_audio/projectors.py:79-87 (_frame_stack): row j <- frames k*j .. k*j+k-1, feature-major per frame */
+int ta_frame_stack(const void* x /*bf16 [B,S,D]*/, void* out /*bf16 [B,n,k*D]*/, int B, int S, int n, int k, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a12. optimiser: clip_grad_norm_(1.0) + torch.optim.AdamW(fused) (configs/training/production.yaml:5-9)
+ *   per step: zero *gnorm_sq, ta_grad_sumsq() per tensor (after the DDP all-reduce), ta_adamw_clip_step() per tensor
+ * ---------------------------------------------------------------------------------------------- */
+int ta_grad_sumsq(const float* g, long long n, float* gnorm_sq, void* stream);
+int ta_adamw_clip_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int step, float max_grad_norm, const float* gnorm_sq, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a3. GLM-ASR encoder forward (frozen, no grad): GlmAsrEncoder.forward, HF:models/glmasr/modeling_glmasr.py:316-330
+ *   weights are bf16 for GEMM operands, fp32 for biases / LayerNorm; `layers` is a HOST array of
+ *   n_layers * TA_ENC_PTRS_PER_LAYER device pointers in the order of the enum below.
+ * ---------------------------------------------------------------------------------------------- */
+enum { TA_ENC_LN1_W = 0, TA_ENC_LN1_B, TA_ENC_WQKV, TA_ENC_BQKV, TA_ENC_WO, TA_ENC_BO, TA_ENC_LN2_W, TA_ENC_LN2_B,
+       TA_ENC_W1, TA_ENC_B1, TA_ENC_W2, TA_ENC_B2, TA_ENC_PTRS_PER_LAYER };
+typedef struct ta_encoder_weights {
+    int n_layers, dim, ffn, heads, head_dim, rot_dim, n_mels, max_pos;
+    float ln_eps;
+    const void* conv1_w;   /* bf16 [dim, 3*n_mels], K index = tap*n_mels + c */
+    const float* conv1_b;
+    const void* conv2_w;   /* bf16 [dim, 3*dim],    K index = tap*dim + c    */
+    const float* conv2_b;
+    const float* lnf_w;
+    const float* lnf_b;
+    const float* rope_cos; /* [max_pos, rot_dim/2] (values already rounded to bf16, as the reference's cos.to(x.dtype)) */
+    const float* rope_sin;
+    const void* const* layers;
+} ta_encoder_weights;
+int ta_encoder_workspace_bytes(const ta_encoder_weights* w, int B, int T, long long* bytes);
+int ta_encoder_forward(const ta_encoder_weights* w, const void* conv1_im2col_bf16 /*[B*T, 3*n_mels]*/, int B, int T,
+                       void* workspace, long long workspace_bytes, void* out_bf16 /*[B*S_e, dim]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a5. MLP projector forward / backward: MLPAudioProjector.forward, tiny_audio/projectors.py:57-71 (+ autograd)
+ *   x_stacked: bf16 [M, k*enc_dim] (frame-stacked encoder output).  Stash tensors are caller-owned.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ta_mlp_projector_weights {
+    int in_dim, hidden, out_dim;
+    float eps;
+    const void* w1;        /* bf16 [hidden, in_dim]  */
+    const float* norm_w;   /* fp32 [hidden]          */
+    const void* w2;        /* bf16 [out_dim, hidden] */
+    const void* w2_t;      /* bf16 [hidden, out_dim] (backward only) */
+    const float* norm2_w;  /* fp32 [out_dim]         */
+} ta_mlp_projector_weights;
+int ta_mlp_projector_forward(const ta_mlp_projector_weights* w, const void* x_stacked, long long M, void* y1 /*bf16 [M,hidden]*/,
+                             void* a1 /*bf16 [M,hidden]*/, void* y2 /*bf16 [M,out]*/, float* out /*fp32 [M,out]*/, void* stream);
+int ta_mlp_projector_backward_workspace_bytes(const ta_mlp_projector_weights* w, long long M, long long* bytes);
+int ta_mlp_projector_backward(const ta_mlp_projector_weights* w, const void* x_stacked, long long M, const void* y1, const void* a1,
+                              const void* y2, const float* d_out /*fp32 [M,out]*/, void* workspace, long long workspace_bytes,
+                              float* d_w1 /*fp32 [hidden,in]*/, float* d_norm_w /*accumulated*/, float* d_w2, float* d_norm2_w,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a8-a10. Qwen3 forward + CE + backward-to-inputs (frozen LM, dgrad only):
+ *   Qwen3ForCausalLM.forward(inputs_embeds, labels) HF:models/qwen3/modeling_qwen3.py:458-517, ForCausalLMLoss
+ *   HF:loss/loss_utils.py:45-67, autograd backward HF:trainer.py:1935.  lm_head is evaluated on the labelled rows.
+ * ---------------------------------------------------------------------------------------------- */
+enum { TA_LM_LN1_W = 0, TA_LM_WQKV, TA_LM_WQKV_T, TA_LM_QNORM_W, TA_LM_KNORM_W, TA_LM_WO, TA_LM_WO_T, TA_LM_LN2_W,
+       TA_LM_WGU, TA_LM_WGU_T, TA_LM_WD, TA_LM_WD_T, TA_LM_PTRS_PER_LAYER };
+typedef struct ta_lm_weights {
+    int n_layers, dim, ffn, n_q_heads, n_kv_heads, head_dim, max_pos;
+    long long vocab, vocab_pad;
+    float eps;
+    const float* embed_f32;     /* [vocab, dim]  (embedding lookup stays fp32 under autocast)            */
+    const void* embed_bf16;     /* [vocab_pad, dim] bf16, rows >= vocab are zero (tied lm_head)          */
+    const void* embed_bf16_t;   /* [dim, vocab_pad] bf16 (dgrad operand)                                  */
+    const float* final_norm_w;
+    const float* rope_cos;      /* [max_pos, head_dim/2] fp32 */
+    const float* rope_sin;
+    const void* const* layers;  /* HOST array, n_layers * TA_LM_PTRS_PER_LAYER device pointers:
+                                   WQKV  bf16 [(Hq+2Hkv)*hd, dim]   WQKV_T bf16 [dim, (Hq+2Hkv)*hd]
+                                   WO    bf16 [dim, Hq*hd]          WO_T   bf16 [Hq*hd, dim]
+                                   WGU   bf16 [2*ffn, dim] rows interleaved in 64-blocks (gate, up)   WGU_T bf16 [dim, 2*ffn]
+                                   WD    bf16 [dim, ffn]            WD_T   bf16 [ffn, dim] */
+} ta_lm_weights;
+typedef struct ta_lm_step_args {
+    int B, S, n_labelled, with_backward;
+    const float* inputs_embeds;   /* [B*S, dim] fp32 */
+    const int* label_rows;        /* [n_labelled] flat token index whose hidden state predicts label_targets[i] */
+    const int* label_targets;     /* [n_labelled] */
+    float inv_num_items;          /* 1 / num_items_in_batch */
+    float* loss;                  /* device scalar, accumulated into (caller zeroes) */
+    float* row_loss;              /* optional [n_labelled] */
+    float* d_inputs_embeds;       /* [B*S, dim] fp32 out (with_backward) */
+    void* workspace;
+    long long workspace_bytes;
+} ta_lm_step_args;
+int ta_lm_workspace_bytes(const ta_lm_weights* w, int B, int S, int n_labelled, int with_backward, long long* bytes);
+int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args* a, void* stream);
+/* full-vocabulary logits for given rows (eval / generate):  logits bf16 [n_rows, vocab_pad] */
+int ta_lm_hidden_to_logits(const ta_lm_weights* w, const float* hidden_f32 /*[B*S, dim] pre-final-norm*/, const int* rows,
+                           int n_rows, void* normed_ws /*bf16 [n_rows, dim]*/, void* logits_bf16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

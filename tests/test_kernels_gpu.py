@@ -1,0 +1,405 @@
+"""Unit parity of each CUDA kernel against a plain torch fp32 statement of the same op (-m gpu)."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from tiny_audio_b200 import lib as L  # noqa: E402
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def max_err(a, b):
+    return float((a.float() - b.float()).abs().max())
+
+
+def rnd(*shape, scale=1.0, dtype=BF16, seed=0, dev="cuda"):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dev).to(dtype)
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 512, 192), (1000, 1280, 1280), (77, 256, 1000), (4096, 3840, 1280)])
+def test_gemm_plain(cuda, M, N, K, bn):
+    lib = L.load()
+    L.check(lib.ta_gemm_set_tile_n(bn))
+    try:
+        a, b = rnd(M, K, seed=1), rnd(N, K, seed=2)
+        bias = rnd(N, dtype=F32, seed=3)
+        out = L.gemm(a, b, epi=L.EPI_BF16, bias=bias)
+        ref = a.float() @ b.float().t() + bias
+        torch.cuda.synchronize()
+        e = rel_err(out, ref)
+        print(f"gemm bn={bn} {M}x{N}x{K} rel_err {e:.3e}")
+        assert e < 5e-3
+        out32 = L.gemm(a, b, epi=L.EPI_F32, alpha=0.5)
+        assert rel_err(out32, 0.5 * (a.float() @ b.float().t())) < 1e-4
+    finally:
+        L.check(lib.ta_gemm_set_tile_n(0))
+
+
+def test_gemm_epilogues(cuda):
+    M, N, K = 520, 512, 256
+    a, b = rnd(M, K, seed=1, scale=0.5), rnd(N, K, seed=2, scale=0.1)
+    bias = rnd(N, dtype=F32, seed=3)
+    acc = a.float() @ b.float().t()
+    out = L.gemm(a, b, epi=L.EPI_BF16_GELU, bias=bias)
+    ref = F.gelu((acc + bias).to(BF16).float())
+    assert rel_err(out, ref) < 5e-3
+    r16 = rnd(M, N, seed=4)
+    out = L.gemm(a, b, epi=L.EPI_BF16_RESID, bias=bias, resid=r16)
+    assert rel_err(out, r16.float() + (acc + bias).to(BF16).float()) < 5e-3
+    r32 = rnd(M, N, dtype=F32, seed=5)
+    out = L.gemm(a, b, epi=L.EPI_F32_RESID, resid=r32)
+    assert out.dtype == F32 and rel_err(out, r32 + acc.to(BF16).float()) < 2e-3
+    # in-place residual (out aliases resid), as the encoder uses it
+    r16b = r16.clone()
+    L.gemm(a, b, epi=L.EPI_BF16_RESID, bias=bias, resid=r16b, out=r16b)
+    assert rel_err(r16b, r16.float() + (acc + bias).to(BF16).float()) < 5e-3
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_swiglu_fwd_bwd(cuda, bn):
+    lib = L.load()
+    L.check(lib.ta_gemm_set_tile_n(bn))
+    try:
+        M, D, Fd = 300, 256, 512
+        x = rnd(M, D, seed=1)
+        wg, wu = rnd(Fd, D, seed=2, scale=0.08), rnd(Fd, D, seed=3, scale=0.08)
+        wgu = torch.cat([wg.view(Fd // 64, 1, 64, D), wu.view(Fd // 64, 1, 64, D)], 1).reshape(2 * Fd, D).contiguous()
+        gu = torch.empty(M, 2 * Fd, device="cuda", dtype=BF16)
+        h = L.gemm(x, wgu, epi=L.EPI_SWIGLU, out2=gu)
+        g = (x.float() @ wg.float().t()).to(BF16).float()
+        u = (x.float() @ wu.float().t()).to(BF16).float()
+        href = F.silu(g).to(BF16).float() * u
+        assert h.shape == (M, Fd) and rel_err(h, href) < 6e-3
+        gu_v = gu.view(M, Fd // 64, 2, 64)
+        assert rel_err(gu_v[:, :, 0].reshape(M, Fd), g) < 1e-5 and rel_err(gu_v[:, :, 1].reshape(M, Fd), u) < 1e-5
+        # backward: dh = dy @ Wd  (Wd [D2, Fd]);  B operand = Wd^T [Fd, D2]
+        D2 = 128
+        dy = rnd(M, D2, seed=5)
+        wd_t = rnd(Fd, D2, seed=6, scale=0.1)
+        dgu = L.gemm(dy, wd_t, epi=L.EPI_SWIGLU_BWD, aux=gu)
+        dh = (dy.float() @ wd_t.float().t()).to(BF16).float()
+        gg = g.clone().requires_grad_(True)
+        uu = u.clone().requires_grad_(True)
+        (F.silu(gg) * uu * dh).sum().backward()
+        dgu_v = dgu.view(M, Fd // 64, 2, 64)
+        e1, e2 = rel_err(dgu_v[:, :, 0].reshape(M, Fd), gg.grad), rel_err(dgu_v[:, :, 1].reshape(M, Fd), uu.grad)
+        print("swiglu bwd rel err", e1, e2)
+        assert e1 < 1e-2 and e2 < 1e-2
+    finally:
+        L.check(lib.ta_gemm_set_tile_n(0))
+
+
+# ------------------------------------------------------------------ attention
+def ref_attn(q, k, v, causal, scale):
+    B, S, Hq, hd = q.shape
+    Hkv = k.shape[2]
+    qf, kf, vf = (t.float().transpose(1, 2) for t in (q, k, v))
+    kf = kf.repeat_interleave(Hq // Hkv, 1)
+    vf = vf.repeat_interleave(Hq // Hkv, 1)
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    if causal:
+        s = s.masked_fill(~torch.ones(S, S, dtype=torch.bool, device=q.device).tril(), float("-inf"))
+    lse = torch.logsumexp(s, -1)
+    return (torch.softmax(s, -1) @ vf).transpose(1, 2), lse
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv,hd,causal", [(2, 200, 4, 4, 64, False), (1, 1500, 20, 20, 64, False),
+                                                   (2, 77, 4, 2, 128, True), (3, 464, 16, 8, 128, True)])
+def test_attn_fwd(cuda, B, S, Hq, Hkv, hd, causal):
+    lib = L.load()
+    W = (Hq + 2 * Hkv) * hd
+    qkv = rnd(B, S, W, seed=7)
+    q = qkv[..., : Hq * hd].view(B, S, Hq, hd)
+    k = qkv[..., Hq * hd:(Hq + Hkv) * hd].view(B, S, Hkv, hd)
+    v = qkv[..., (Hq + Hkv) * hd:].view(B, S, Hkv, hd)
+    o = torch.empty(B, S, Hq * hd, device="cuda", dtype=BF16)
+    lse = torch.empty(B, Hq, S, device="cuda", dtype=F32)
+    scale = hd ** -0.5
+    L.check(lib.ta_attn_fwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), L.ptr(lse), B, S, Hq, Hkv, hd, W, W, W, Hq * hd,
+                            int(causal), scale, L.stream_ptr()))
+    oref, lref = ref_attn(q, k, v, causal, scale)
+    torch.cuda.synchronize()
+    e = rel_err(o.view(B, S, Hq, hd), oref)
+    print(f"attn fwd S={S} hd={hd} causal={causal}: rel {e:.3e}  lse max err {max_err(lse, lref):.3e}")
+    assert e < 1e-2 and max_err(lse, lref) < 2e-3
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv", [(2, 77, 4, 2), (2, 464, 16, 8), (1, 130, 2, 2)])
+def test_attn_bwd(cuda, B, S, Hq, Hkv):
+    lib = L.load()
+    hd = 128
+    scale = hd ** -0.5
+    q, k, v = rnd(B, S, Hq, hd, seed=1), rnd(B, S, Hkv, hd, seed=2), rnd(B, S, Hkv, hd, seed=3)
+    do = rnd(B, S, Hq, hd, seed=4)
+    o = torch.empty(B, S, Hq * hd, device="cuda", dtype=BF16)
+    lse = torch.empty(B, Hq, S, device="cuda", dtype=F32)
+    L.check(lib.ta_attn_fwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), L.ptr(lse), B, S, Hq, Hkv, hd, Hq * hd, Hkv * hd, Hkv * hd,
+                            Hq * hd, 1, scale, L.stream_ptr()))
+    dsum = torch.empty(B, Hq, S, device="cuda", dtype=F32)
+    dq = torch.empty(B, S, Hq * hd, device="cuda", dtype=F32)
+    dk = torch.empty(B, S, Hkv * hd, device="cuda", dtype=BF16)
+    dv = torch.empty_like(dk)
+    L.check(lib.ta_attn_bwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), L.ptr(do), L.ptr(lse), L.ptr(dsum), L.ptr(dq), L.ptr(dk),
+                            L.ptr(dv), B, S, Hq, Hkv, hd, Hq * hd, Hkv * hd, Hkv * hd, Hq * hd, Hq * hd, Hq * hd, Hkv * hd,
+                            Hkv * hd, 1, scale, L.stream_ptr()))
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    oref, _ = ref_attn(qf, kf, vf, True, scale)
+    (oref * do.float()).sum().backward()
+    torch.cuda.synchronize()
+    e = [rel_err(dq.view_as(q), qf.grad), rel_err(dk.view_as(k), kf.grad), rel_err(dv.view_as(v), vf.grad)]
+    print(f"attn bwd S={S}: rel dq {e[0]:.3e} dk {e[1]:.3e} dv {e[2]:.3e}")
+    assert max(e) < 2e-2
+
+
+# ------------------------------------------------------------------ log-mel
+def torch_logmel(wave):
+    from transformers import WhisperFeatureExtractor
+    fe = WhisperFeatureExtractor(feature_size=128)
+    return torch.from_numpy(fe._torch_extract_fbank_features(wave.cpu().numpy(), "cpu"))
+
+
+@pytest.mark.parametrize("B,L", [(2, 16000), (3, 48000 + 37), (1, 480000)])
+def test_logmel(cuda, B, L):
+    lib = L_ = L.load()
+    g = torch.Generator().manual_seed(5)
+    wave = (0.1 * torch.randn(B, L, generator=g)).float()
+    wave[-1, L // 2:] = 0.0                                   # a zero-padded clip
+    wd = wave.cuda()
+    n = C.c_longlong()
+    L.check(lib.ta_logmel_workspace_floats(B, L, C.byref(n)))
+    ws = torch.empty(n.value, device="cuda", dtype=F32)
+    T = L // 160
+    out = torch.empty(B, 128, T, device="cuda", dtype=F32)
+    im2 = torch.empty(B * T, 384, device="cuda", dtype=BF16)
+    L.check(lib.ta_logmel_fwd(L.ptr(wd), wd.stride(0), B, L, L.ptr(ws), L.ptr(out), L.ptr(im2), L.stream_ptr()))
+    ref = torch_logmel(wave)
+    torch.cuda.synchronize()
+    assert ref.shape == out.shape
+    e = max_err(out.cpu(), ref)
+    print(f"logmel B={B} L={L}: max abs err {e:.3e}")
+    assert e < 2e-4, "fp32 direct DFT vs torch.stft FFT: tolerance 2e-4 on the (x+4)/4 scale"
+    # im2col = [mel(t-1) | mel(t) | mel(t+1)] in bf16
+    m = out.transpose(1, 2).to(BF16)                          # [B, T, 128]
+    z = torch.zeros(B, 1, 128, device="cuda", dtype=BF16)
+    expect = torch.cat([torch.cat([z, m[:, :-1]], 1), m, torch.cat([m[:, 1:], z], 1)], -1).reshape(B * T, 384)
+    assert torch.equal(im2, expect)
+    im2b = torch.empty_like(im2)
+    L.check(lib.ta_mel_to_conv1_im2col(L.ptr(out), B, T, L.ptr(im2b), L.stream_ptr()))
+    assert torch.equal(im2b, expect)
+
+
+# ------------------------------------------------------------------ elementwise
+def test_layernorm_rmsnorm(cuda):
+    lib = L.load()
+    rows, D = 1000, 1280
+    x = rnd(rows, D, seed=1)
+    w, b = rnd(D, dtype=F32, seed=2) + 1, rnd(D, dtype=F32, seed=3)
+    y = torch.empty_like(x)
+    L.check(lib.ta_layernorm_bf16(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), rows, D, 1e-5, L.stream_ptr()))
+    assert rel_err(y, F.layer_norm(x.float(), (D,), w, b, 1e-5)) < 4e-3
+    D = 1024
+    xf = rnd(rows, D, dtype=F32, seed=4)
+    w = rnd(D, dtype=F32, seed=5) + 1
+    y = torch.empty(rows, D, device="cuda", dtype=BF16)
+    L.check(lib.ta_rmsnorm_f32(L.ptr(xf), L.ptr(w), L.ptr(y), None, rows, D, 1e-6, L.stream_ptr()))
+    ref = w * xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)
+    assert rel_err(y, ref) < 4e-3
+    # gather variant + backward
+    idx = torch.tensor([5, 17, 999, 0], device="cuda", dtype=torch.int32)
+    y2 = torch.empty(4, D, device="cuda", dtype=BF16)
+    L.check(lib.ta_rmsnorm_f32(L.ptr(xf), L.ptr(w), L.ptr(y2), L.ptr(idx), 4, D, 1e-6, L.stream_ptr()))
+    assert rel_err(y2, ref[idx.long()]) < 4e-3
+    dy = rnd(rows, D, seed=6)
+    dres = rnd(rows, D, dtype=F32, seed=7)
+    dx = dres.clone()
+    L.check(lib.ta_rmsnorm_f32_bwd(L.ptr(dy), L.ptr(xf), L.ptr(w), L.ptr(dx), None, rows, D, 1e-6, 1, L.stream_ptr()))
+    xr = xf.clone().requires_grad_(True)
+    (w * xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6) * dy.float()).sum().backward()
+    assert rel_err(dx, dres + xr.grad) < 1e-4
+
+
+def test_enc_rope_and_qknorm(cuda):
+    lib = L.load()
+    B, S, H, hd, rd = 2, 50, 20, 64, 32
+    qkv = rnd(B * S, 3 * H * hd, seed=1)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, rd, 2).float() / rd))
+    fr = torch.arange(S).float()[:, None] * inv[None]
+    cos, sin = fr.cos().cuda().contiguous(), fr.sin().cuda().contiguous()
+    ref = qkv.float().view(B, S, 3, H, hd).clone()
+    for part in (0, 1):
+        x = ref[:, :, part]
+        x1, x2 = x[..., : rd // 2].clone(), x[..., rd // 2: rd].clone()
+        c, s = cos[None, :, None, :], sin[None, :, None, :]
+        x[..., : rd // 2] = x1 * c - x2 * s
+        x[..., rd // 2: rd] = x2 * c + x1 * s
+    L.check(lib.ta_enc_rope(L.ptr(qkv), L.ptr(cos), L.ptr(sin), B * S, S, H, hd, rd, L.stream_ptr()))
+    assert rel_err(qkv.view(B, S, 3, H, hd), ref) < 4e-3
+
+    # Qwen3 q/k norm + rope fwd/bwd
+    Hq, Hkv, hd = 4, 2, 128
+    M = B * S
+    raw = rnd(M, (Hq + 2 * Hkv) * hd, seed=2)
+    qw, kw = rnd(hd, dtype=F32, seed=3) * 0.1 + 1, rnd(hd, dtype=F32, seed=4) * 0.1 + 1
+    inv = 1.0 / (1e6 ** (torch.arange(0, hd, 2).float() / hd))
+    fr = torch.arange(S).float()[:, None] * inv[None]
+    cos, sin = fr.cos().cuda().contiguous(), fr.sin().cuda().contiguous()
+    qk = torch.empty(M, (Hq + Hkv) * hd, device="cuda", dtype=BF16)
+    L.check(lib.ta_lm_qknorm_rope_fwd(L.ptr(raw), L.ptr(qk), L.ptr(qw), L.ptr(kw), L.ptr(cos), L.ptr(sin), M, S, Hq, Hkv, 1e-6,
+                                      L.stream_ptr()))
+
+    def fwd(rawf):
+        x = rawf.view(B, S, Hq + 2 * Hkv, hd)[:, :, : Hq + Hkv]
+        w = torch.cat([qw[None].expand(Hq, hd), kw[None].expand(Hkv, hd)], 0)
+        n = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+        c = torch.cat([cos, cos], -1)[None, :, None, :]
+        s = torch.cat([sin, sin], -1)[None, :, None, :]
+        rot = torch.cat([-n[..., hd // 2:], n[..., : hd // 2]], -1)
+        return n * c + rot * s
+
+    rawf = raw.float().clone().requires_grad_(True)
+    y = fwd(rawf)
+    assert rel_err(qk.view(B, S, Hq + Hkv, hd), y) < 6e-3
+    dq = rnd(M, Hq * hd, dtype=F32, seed=5)
+    dk = rnd(M, Hkv * hd, seed=6)
+    dv = rnd(M, Hkv * hd, seed=7)
+    dqkv = torch.empty_like(raw)
+    L.check(lib.ta_lm_qknorm_rope_bwd(L.ptr(raw), L.ptr(dq), L.ptr(dk), L.ptr(dv), L.ptr(dqkv), L.ptr(qw), L.ptr(kw), L.ptr(cos),
+                                      L.ptr(sin), M, S, Hq, Hkv, 1e-6, L.stream_ptr()))
+    gy = torch.cat([dq.view(B, S, Hq, hd), dk.float().view(B, S, Hkv, hd)], 2)
+    (y * gy).sum().backward()
+    gref = rawf.grad.view(B, S, Hq + 2 * Hkv, hd).clone()
+    gref[:, :, Hq + Hkv:] = dv.float().view(B, S, Hkv, hd)
+    assert rel_err(dqkv.view(B, S, Hq + 2 * Hkv, hd), gref) < 8e-3
+
+
+def test_projector_norms(cuda):
+    lib = L.load()
+    for D, gelu in ((1024, 1), (2048, 1), (1024, 0)):
+        rows = 333
+        x = rnd(rows, D, seed=1, scale=2.0)
+        w = rnd(D, dtype=F32, seed=2) * 0.1 + 1
+        y = torch.empty(rows, D, device="cuda", dtype=BF16 if gelu else F32)
+        L.check(lib.ta_proj_norm_fwd(L.ptr(x), L.ptr(w), L.ptr(y), rows, D, 1e-6, gelu, L.stream_ptr()))
+        xr = x.float().clone().requires_grad_(True)
+        n = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6)
+        wr = w.clone().requires_grad_(True)
+        z = wr * n
+        ref = F.gelu(z) if gelu else z
+        assert rel_err(y, ref) < 6e-3
+        dy = rnd(rows, D, seed=3, dtype=BF16 if gelu else F32)
+        dx = torch.empty(rows, D, device="cuda", dtype=BF16)
+        dw = torch.zeros(D, device="cuda", dtype=F32)
+        L.check(lib.ta_proj_norm_bwd(L.ptr(x), L.ptr(w), L.ptr(dy), 0 if gelu else 1, L.ptr(dx), L.ptr(dw), rows, D, 1e-6, gelu,
+                                     L.stream_ptr()))
+        (ref * dy.float()).sum().backward()
+        e1, e2 = rel_err(dx, xr.grad), rel_err(dw, wr.grad)
+        print(f"proj norm bwd D={D} gelu={gelu}: dx {e1:.3e} dw {e2:.3e}")
+        assert e1 < 1e-2 and e2 < 1e-2
+
+
+def test_scatter_ce_misc(cuda):
+    lib = L.load()
+    B, S, n_a, D, V = 3, 40, 6, 1024, 1000
+    AUD = 999
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, V - 1, (B, S), generator=g)
+    counts = torch.tensor([6, 4, 8])          # sample 2 asks for more rows than the projector produced -> zero rows
+    for b, c in enumerate(counts.tolist()):
+        ids[b, 2:2 + c] = AUD
+    table = rnd(V, D, dtype=F32, seed=4)
+    audio = rnd(B, n_a, D, dtype=F32, seed=5)
+    # reference semantics (tiny_audio/asr_modeling.py:27-44 + masked_scatter)
+    rows = []
+    for b in range(B):
+        c = int(counts[b])
+        t = audio[b, : min(c, n_a)]
+        if c > n_a:
+            t = torch.cat([t, torch.zeros(c - n_a, D, device="cuda")])
+        rows.append(t)
+    packed = torch.cat(rows)
+    ref = table[ids.cuda()].clone()
+    ref.view(-1, D)[(ids.view(-1) == AUD).nonzero().squeeze(-1).cuda()] = packed
+    src = torch.empty(B * S, device="cuda", dtype=torch.int32)
+    emb = torch.empty(B * S, D, device="cuda", dtype=F32)
+    idd, cd = ids.cuda(), counts.cuda()
+    L.check(lib.ta_audio_index(L.ptr(idd), L.ptr(cd), L.ptr(src), B, S, n_a, AUD, L.stream_ptr()))
+    L.check(lib.ta_embed_scatter(L.ptr(idd), L.ptr(src), L.ptr(table), L.ptr(audio), L.ptr(emb), B * S, D, V, L.stream_ptr()))
+    assert torch.equal(emb.view(B, S, D), ref), "embed + <audio> scatter must be bit-exact"
+    demb = rnd(B * S, D, dtype=F32, seed=6)
+    dau = torch.zeros(B * n_a, D, device="cuda", dtype=F32)
+    L.check(lib.ta_audio_grad_gather(L.ptr(src), L.ptr(demb), L.ptr(dau), B * S, D, L.stream_ptr()))
+    a2 = audio.clone().requires_grad_(True)
+    rows = [a2[b, : min(int(counts[b]), n_a)] for b in range(B)]
+    rows[2] = torch.cat([rows[2], torch.zeros(2, D, device="cuda")])
+    e2 = table[idd].clone()
+    e2.view(-1, D)[(idd.view(-1) == AUD).nonzero().squeeze(-1)] = torch.cat(rows)
+    (e2.view(-1, D) * demb).sum().backward()
+    assert torch.equal(dau.view(B, n_a, D), a2.grad)
+
+    # cross entropy on bf16 logits with a padded vocabulary
+    R, V, Vp = 50, 5003, 5120
+    logits = rnd(R, Vp, seed=7, scale=3.0)
+    tg = torch.randint(0, V, (R,), generator=g).to(torch.int32).cuda()
+    ref_l = logits[:, :V].float().clone().requires_grad_(True)
+    loss_ref = F.cross_entropy(ref_l, tg.long(), reduction="sum") / 37.0
+    loss_ref.backward()
+    loss = torch.zeros(1, device="cuda", dtype=F32)
+    rl = torch.empty(R, device="cuda", dtype=F32)
+    lg = logits.clone()
+    L.check(lib.ta_ce_fwd_bwd(L.ptr(lg), Vp, L.ptr(tg), R, V, Vp, 1.0 / 37.0, L.ptr(loss), L.ptr(rl), 1, L.stream_ptr()))
+    assert abs(float(loss) - float(loss_ref)) < 1e-4 * abs(float(loss_ref))
+    assert rel_err(lg[:, :V], ref_l.grad) < 6e-3 and float(lg[:, V:].abs().max()) == 0.0
+
+    # transpose / cast / frame-stack (indices exact)
+    x = rnd(70, 200, seed=8)
+    xt = torch.zeros(200, 72, device="cuda", dtype=BF16)
+    L.check(lib.ta_transpose_bf16(L.ptr(x), L.ptr(xt), 70, 200, 200, 72, L.stream_ptr()))
+    assert torch.equal(xt[:, :70], x.t())
+    xf = rnd(1001, dtype=F32, seed=9)
+    xb = torch.empty(1001, device="cuda", dtype=BF16)
+    L.check(lib.ta_cast_f32_bf16(L.ptr(xf), L.ptr(xb), 1001, L.stream_ptr()))
+    assert torch.equal(xb, xf.to(BF16))
+    e = rnd(2, 50, 1280, seed=10)
+    n = (50 - 4) // 4 + 1
+    st = torch.empty(2, n, 4 * 1280, device="cuda", dtype=BF16)
+    L.check(lib.ta_frame_stack(L.ptr(e), L.ptr(st), 2, 50, n, 4, 1280, L.stream_ptr()))
+    assert torch.equal(st, e[:, : n * 4].reshape(2, n, 4 * 1280))
+    y = rnd(10, 1280, 3, seed=11)   # conv2 im2col
+    xx = rnd(2, 21, 1280, seed=12)
+    T2 = (21 + 2 - 3) // 2 + 1
+    out = torch.empty(2 * T2, 3 * 1280, device="cuda", dtype=BF16)
+    L.check(lib.ta_im2col_k3(L.ptr(xx), L.ptr(out), 2, 21, 1280, 2, L.stream_ptr()))
+    xp = F.pad(xx, (0, 0, 1, 1))
+    exp = torch.stack([xp[:, 2 * t: 2 * t + 3].reshape(2, -1) for t in range(T2)], 1).reshape(2 * T2, -1)
+    assert torch.equal(out, exp)
+
+
+def test_adamw_clip(cuda):
+    from tiny_audio_b200.engine import FusedClipAdamW
+    g = torch.Generator().manual_seed(1)
+    ps = [torch.randn(1000, 37, generator=g).cuda(), torch.randn(513, generator=g).cuda()]
+    ref = [p.clone().requires_grad_(True) for p in ps]
+    opt_ref = torch.optim.AdamW(ref, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    opt = FusedClipAdamW(ps, lr=1e-2, weight_decay=0.05, max_grad_norm=1.0)
+    for step in range(3):
+        grads = [torch.randn(p.shape, generator=g).cuda() * (3.0 if step == 0 else 0.01) for p in ps]
+        for r, gr in zip(ref, grads):
+            r.grad = gr.clone()
+        torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        opt_ref.step()
+        opt.step(grads)
+        for p, r in zip(ps, ref):
+            assert max_err(p, r) < 2e-6

@@ -1,0 +1,129 @@
+"""Whole-path parity on the GPU: CUDA hot path vs the CPU oracle (and the reference's golden fixtures) on the
+same seeded weights / inputs.  Tolerances are for the production recipe (bf16 GEMM operands, fp32 accumulate)
+against the fp32 oracle and are written next to each assert."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import path_oracle as po  # noqa: E402  (checker only)
+from tiny_audio_b200.engine import FusedClipAdamW, HotPath, PathDims  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def sub(t, n=4096):
+    f = t.detach().reshape(-1)
+    step = max(1, f.numel() // n)
+    return f[::step][:n].float().cpu().numpy()
+
+
+def build(cfg, seed):
+    W = po.init_weights(cfg, seed=seed)
+    hp = HotPath(PathDims.from_any(cfg.to_dict()), W["encoder"], W["lm"], "cuda")
+    return W, hp
+
+
+def run_step(hp, W, batch, n_items, use_wave=True):
+    params = {k: v.clone().cuda().contiguous() for k, v in W["projector"].items()}
+    grads = {k: torch.zeros_like(v) for k, v in params.items()}
+    kw = dict(waveform=batch["waveform"].cuda()) if use_wave else dict(input_features=po.log_mel(batch["waveform"]).cuda())
+    loss, parts = hp.forward_backward(input_ids=batch["input_ids"].cuda(), labels_cpu=batch["labels"], proj_params=params,
+                                      audio_token_counts=batch["audio_token_counts"].cuda(), num_items_in_batch=n_items,
+                                      grads=grads, return_parts=True, **kw)
+    torch.cuda.synchronize()
+    return loss, parts, params, grads
+
+
+@pytest.mark.parametrize("name", ["small_b2_2s", "small_b3_ragged", "h2048_b2_2s", "small_b2_1s_pad30"])
+def test_small_configs_vs_oracle_and_golden(cuda, name):
+    from oracle.make_golden import CASES
+    spec, B, clip_s, pad_s, R, seed = CASES[name]
+    cfg = po.small_config(**spec)
+    fx = np.load(os.path.join(GOLD, name + ".npz"))
+    W, hp = build(cfg, seed)
+    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s)
+    batch["input_ids"] = torch.from_numpy(fx["input_ids"])
+    batch["labels"] = torch.from_numpy(fx["labels"])
+    n_items = int(fx["num_items"])
+    loss, parts, params, grads = run_step(hp, W, batch, n_items)
+
+    # oracle on the CPU (fp32)
+    ob = dict(batch)
+    res = po.train_step(W, ob, cfg, lr=1e-3, max_grad_norm=1.0, num_items_in_batch=n_items)
+    _, _, oparts = po.model_forward(W, ob, cfg, n_items, return_parts=True)
+
+    e_mel = float((parts["mel"].cpu() - oparts["mel"]).abs().max())
+    e_enc = rel(parts["encoder_out"], oparts["encoder_out"])
+    e_proj = rel(parts["projector_out"], oparts["projector_out"])
+    d_loss = abs(float(loss) - float(res["loss"]))
+    d_gold = abs(float(loss) - float(fx["loss"]))
+    print(f"[{name}] mel {e_mel:.2e} enc {e_enc:.3e} proj {e_proj:.3e} loss {float(loss):.5f} "
+          f"(oracle {float(res['loss']):.5f}, golden {float(fx['loss']):.5f})")
+    assert e_mel < 2e-4                     # fp32 DFT vs fp32 FFT on the (x+4)/4 scale
+    assert e_enc < 3e-2                     # bf16 encoder (2 layers) vs fp32
+    assert e_proj < 3e-2
+    assert d_loss < 5e-3 and d_gold < 5e-3  # CE (mean over labelled tokens), bf16 recipe vs fp32
+    for k in grads:
+        e = rel(grads[k], res["grads"][k])
+        eg = float(np.linalg.norm(sub(grads[k]) - fx["grad_sub." + k]) / (np.linalg.norm(fx["grad_sub." + k]) + 1e-12))
+        print(f"   grad {k}: rel vs oracle {e:.3e}, vs golden sub-sample {eg:.3e}")
+        assert e < 6e-2 and eg < 8e-2       # the reference's own bf16-vs-fp32 grad error is 2.4e-2
+    # frame-stack indices: the stacked operand must equal the oracle's gather of the encoder output exactly
+    xs, n_a = hp.frame_stack(parts["encoder_out"])
+    idx = po.frame_stack_indices(parts["encoder_out"].shape[1], cfg.proj_k, cfg.enc_dim)
+    e = parts["encoder_out"].cpu()
+    gathered = e[:, torch.from_numpy(idx[..., 0]), torch.from_numpy(idx[..., 1])]
+    assert torch.equal(xs.view(e.shape[0], n_a, -1).cpu(), gathered)
+
+    # optimiser step (clip 1.0 + AdamW) against the oracle's update
+    names = list(params)
+    opt = FusedClipAdamW([params[k] for k in names], lr=1e-3, max_grad_norm=1.0)
+    opt.step([grads[k] for k in names])
+    torch.cuda.synchronize()
+    gn = float(opt.grad_norm())
+    assert abs(gn - float(res["grad_norm"])) < 5e-2 * float(res["grad_norm"])
+    for k in names:
+        # first AdamW step moves every element by ~lr*sign(g): compare the update direction where |g| is not tiny
+        upd = (params[k].cpu() - W["projector"][k])
+        ref_upd = res["params"][k] - W["projector"][k]
+        big = res["grads"][k].abs() > 1e-3 * res["grads"][k].abs().max()
+        agree = float((torch.sign(upd[big]) == torch.sign(ref_upd[big])).float().mean())
+        assert agree > 0.98, f"{k}: update sign agreement {agree}"
+
+
+def test_mel_features_path_matches_waveform_path(cuda):
+    cfg = po.small_config(enc_layers=1, lm_layers=1)
+    W, hp = build(cfg, 3)
+    batch = po.synthetic_batch(cfg, 2, 1.0, seed=3, response_len=8)
+    n = int((batch["labels"] != -100).sum())
+    l1, _, _, g1 = run_step(hp, W, batch, n, use_wave=True)
+    l2, _, _, g2 = run_step(hp, W, batch, n, use_wave=False)
+    assert abs(float(l1) - float(l2)) < 2e-3
+    for k in g1:
+        assert rel(g1[k], g2[k]) < 2e-2
+
+
+def test_linearity_in_num_items_and_determinism(cuda):
+    """size-independent properties: loss and grads scale as 1/num_items; two identical runs agree bit-for-bit
+    except for the fp32 atomics in dQ / norm-weight grads (tolerance 1e-5 rel)."""
+    cfg = po.small_config(enc_layers=1, lm_layers=2)
+    W, hp = build(cfg, 5)
+    batch = po.synthetic_batch(cfg, 2, 1.0, seed=5, response_len=8)
+    n = int((batch["labels"] != -100).sum())
+    l1, _, _, g1 = run_step(hp, W, batch, n)
+    l2, _, _, g2 = run_step(hp, W, batch, 2 * n)
+    l3, _, _, g3 = run_step(hp, W, batch, n)
+    assert abs(float(l1) - 2 * float(l2)) < 1e-5 * abs(float(l1))
+    for k in g1:
+        assert rel(g2[k] * 2, g1[k]) < 2e-2     # dlogits are rounded to bf16 after the 1/num_items scale
+        assert rel(g3[k], g1[k]) < 1e-4
+    assert abs(float(l1) - float(l3)) < 1e-6 * abs(float(l1))

@@ -1,0 +1,349 @@
+// Host-side orchestration of the three towers of the path: all launches go to the caller's stream, no host
+// synchronisation, no allocation (workspaces come from the caller).  This is the native "runtime" of the hot path:
+// one C call per tower instead of ~2000 Python->ctypes launches per step.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tinyaudio_b200.h"
+
+namespace {
+
+struct Carver {
+    uint8_t* base;
+    long long off = 0, cap;
+    Carver(void* p, long long c) : base(reinterpret_cast<uint8_t*>(p)), cap(c) {}
+    template <typename T>
+    T* take(long long n_elems) {
+        off = (off + 255) & ~255LL;
+        T* p = reinterpret_cast<T*>(base ? base + off : nullptr);
+        off += n_elems * (long long)sizeof(T);
+        return p;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+inline int gemm(const void* A, long long lda, const void* B, long long ldb, long long M, int N, int K, int epi, void* out,
+                long long ldo, const float* bias, const void* resid, void* out2, long long ldo2, const void* aux,
+                long long ldaux, cudaStream_t st, float alpha = 1.0f) {
+    if (M == 0) return 0;
+    ta_gemm_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.out = out; e.ldo = ldo; e.bias = bias; e.resid = resid; e.ldr = ldo; e.out2 = out2; e.ldo2 = ldo2; e.aux = aux;
+    e.ldaux = ldaux; e.alpha = alpha;
+    return ta_gemm_bf16(A, lda, B, ldb, (int)M, N, K, epi, &e, st);
+}
+#define RUN(x)            \
+    do {                  \
+        int _rc = (x);    \
+        if (_rc) return _rc; \
+    } while (0)
+
+inline int enc_out_len(int T) { return (T + 2 - 3) / 2 + 1; }
+
+}  // namespace
+
+// =============================================================================================================
+// encoder
+// =============================================================================================================
+static long long enc_carve(const ta_encoder_weights* w, int B, int T, void* ws, long long cap, bf16** x, bf16** h, bf16** qkv,
+                           bf16** f) {
+    const long long S = enc_out_len(T), M = (long long)B * S, M1 = (long long)B * T;
+    const long long D = w->dim, F = w->ffn;
+    Carver c(ws, cap);
+    *x = c.take<bf16>(M * D);
+    *h = c.take<bf16>(M * D);
+    // qkv doubles as the conv2 im2col buffer [M, 3D]; f doubles as the conv1 output [M1, D]
+    *qkv = c.take<bf16>(M * 3 * D);
+    const long long f_elems = (M * F > M1 * D) ? M * F : M1 * D;
+    *f = c.take<bf16>(f_elems);
+    return c.off;
+}
+
+TA_API int ta_encoder_workspace_bytes(const ta_encoder_weights* w, int B, int T, long long* bytes) {
+    TA_REQUIRE(w && bytes, "null");
+    bf16 *a, *b, *c, *d;
+    *bytes = enc_carve(w, B, T, nullptr, 0, &a, &b, &c, &d) + 256;
+    return 0;
+}
+
+TA_API int ta_encoder_forward(const ta_encoder_weights* w, const void* conv1_im2col, int B, int T, void* workspace,
+                              long long workspace_bytes, void* out, void* stream) {
+    TA_REQUIRE(w && conv1_im2col && workspace && out, "ta_encoder_forward: null pointer");
+    TA_REQUIRE(w->head_dim == 64 && w->heads * w->head_dim == w->dim, "encoder: head_dim must be 64 and heads*64 == dim");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int S = enc_out_len(T);
+    TA_REQUIRE(S <= w->max_pos, "encoder: %d frames exceed the rotary table (%d)", S, w->max_pos);
+    const long long M = (long long)B * S, M1 = (long long)B * T;
+    const int D = w->dim, F = w->ffn;
+    bf16 *x, *h, *qkv, *f;
+    const long long need = enc_carve(w, B, T, workspace, workspace_bytes, &x, &h, &qkv, &f);
+    TA_REQUIRE(need <= workspace_bytes, "encoder workspace too small: need %lld, have %lld", need, workspace_bytes);
+    if (M == 0) return 0;
+
+    // conv1 (k3, s1, p1) + GELU as a GEMM over the im2col rows; conv2 (k3, s2, p1) + GELU likewise
+    bf16* c1 = f;
+    RUN(gemm(conv1_im2col, 3 * w->n_mels, w->conv1_w, 3 * w->n_mels, M1, D, 3 * w->n_mels, TA_EPI_BF16_GELU, c1, D, w->conv1_b,
+             nullptr, nullptr, 0, nullptr, 0, st));
+    bf16* im2 = qkv;
+    RUN(k_im2col_k3(c1, im2, B, T, D, 2, st));
+    RUN(gemm(im2, 3 * D, w->conv2_w, 3 * D, M, D, 3 * D, TA_EPI_BF16_GELU, x, D, w->conv2_b, nullptr, nullptr, 0, nullptr, 0, st));
+
+    const float scale = 1.0f / sqrtf((float)w->head_dim);
+    for (int l = 0; l < w->n_layers; ++l) {
+        const void* const* L = w->layers + (long long)l * TA_ENC_PTRS_PER_LAYER;
+        RUN(k_layernorm_bf16(x, (const float*)L[TA_ENC_LN1_W], (const float*)L[TA_ENC_LN1_B], h, M, D, w->ln_eps, st));
+        RUN(gemm(h, D, L[TA_ENC_WQKV], D, M, 3 * D, D, TA_EPI_BF16, qkv, 3 * D, (const float*)L[TA_ENC_BQKV], nullptr, nullptr, 0,
+                 nullptr, 0, st));
+        RUN(k_enc_rope(qkv, w->rope_cos, w->rope_sin, M, S, w->heads, w->head_dim, w->rot_dim, st));
+        RUN(ta_attn_fwd(qkv, qkv + D, qkv + 2 * D, h, nullptr, B, S, w->heads, w->heads, w->head_dim, 3 * D, 3 * D, 3 * D, D, 0,
+                        scale, st));
+        RUN(gemm(h, D, L[TA_ENC_WO], D, M, D, D, TA_EPI_BF16_RESID, x, D, (const float*)L[TA_ENC_BO], x, nullptr, 0, nullptr, 0, st));
+        RUN(k_layernorm_bf16(x, (const float*)L[TA_ENC_LN2_W], (const float*)L[TA_ENC_LN2_B], h, M, D, w->ln_eps, st));
+        RUN(gemm(h, D, L[TA_ENC_W1], D, M, F, D, TA_EPI_BF16_GELU, f, F, (const float*)L[TA_ENC_B1], nullptr, nullptr, 0, nullptr, 0, st));
+        RUN(gemm(f, F, L[TA_ENC_W2], F, M, D, F, TA_EPI_BF16_RESID, x, D, (const float*)L[TA_ENC_B2], x, nullptr, 0, nullptr, 0, st));
+    }
+    RUN(k_layernorm_bf16(x, w->lnf_w, w->lnf_b, reinterpret_cast<bf16*>(out), M, D, w->ln_eps, st));
+    return 0;
+}
+
+// =============================================================================================================
+// MLP projector
+// =============================================================================================================
+TA_API int ta_mlp_projector_forward(const ta_mlp_projector_weights* w, const void* x_stacked, long long M, void* y1, void* a1,
+                                    void* y2, float* out, void* stream) {
+    TA_REQUIRE(w && x_stacked && y1 && a1 && y2 && out, "ta_mlp_projector_forward: null pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (M == 0) return 0;
+    RUN(gemm(x_stacked, w->in_dim, w->w1, w->in_dim, M, w->hidden, w->in_dim, TA_EPI_BF16, y1, w->hidden, nullptr, nullptr, nullptr,
+             0, nullptr, 0, st));
+    RUN(k_proj_norm_fwd((const bf16*)y1, w->norm_w, a1, M, w->hidden, w->eps, 1, st));
+    RUN(gemm(a1, w->hidden, w->w2, w->hidden, M, w->out_dim, w->hidden, TA_EPI_BF16, y2, w->out_dim, nullptr, nullptr, nullptr, 0,
+             nullptr, 0, st));
+    RUN(k_proj_norm_fwd((const bf16*)y2, w->norm2_w, out, M, w->out_dim, w->eps, 0, st));
+    return 0;
+}
+
+static long long proj_bwd_carve(const ta_mlp_projector_weights* w, long long M, void* ws, long long cap, bf16** dy2, bf16** da1,
+                                bf16** tA, bf16** tB, long long* Mp) {
+    *Mp = (M + 7) / 8 * 8;
+    Carver c(ws, cap);
+    *dy2 = c.take<bf16>(M * w->out_dim);
+    *da1 = c.take<bf16>(M * w->hidden);
+    const long long amax = (w->out_dim > w->hidden) ? w->out_dim : w->hidden;
+    const long long bmax = (w->hidden > w->in_dim) ? w->hidden : w->in_dim;
+    *tA = c.take<bf16>(amax * *Mp);
+    *tB = c.take<bf16>(bmax * *Mp);
+    return c.off;
+}
+
+TA_API int ta_mlp_projector_backward_workspace_bytes(const ta_mlp_projector_weights* w, long long M, long long* bytes) {
+    TA_REQUIRE(w && bytes, "null");
+    bf16 *a, *b, *c, *d;
+    long long mp;
+    *bytes = proj_bwd_carve(w, M, nullptr, 0, &a, &b, &c, &d, &mp) + 256;
+    return 0;
+}
+
+TA_API int ta_mlp_projector_backward(const ta_mlp_projector_weights* w, const void* x_stacked, long long M, const void* y1,
+                                     const void* a1, const void* y2, const float* d_out, void* workspace, long long workspace_bytes,
+                                     float* d_w1, float* d_norm_w, float* d_w2, float* d_norm2_w, void* stream) {
+    TA_REQUIRE(w && x_stacked && y1 && a1 && y2 && d_out && workspace && d_w1 && d_norm_w && d_w2 && d_norm2_w && w->w2_t,
+               "ta_mlp_projector_backward: null pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (M == 0) return 0;
+    TA_REQUIRE(M < (1LL << 31), "projector backward: too many rows");
+    bf16 *dy2, *da1, *tA, *tB;
+    long long Mp;
+    const long long need = proj_bwd_carve(w, M, workspace, workspace_bytes, &dy2, &da1, &tA, &tB, &Mp);
+    TA_REQUIRE(need <= workspace_bytes, "projector backward workspace too small: need %lld, have %lld", need, workspace_bytes);
+    const int H = w->hidden, O = w->out_dim, I = w->in_dim;
+    // norm_2 backward -> d(y2) (bf16), d(norm_2.weight)
+    RUN(k_proj_norm_bwd((const bf16*)y2, w->norm2_w, d_out, 1, dy2, d_norm2_w, M, O, w->eps, 0, st));
+    // wgrad linear_2: dW2[O,H] = dy2^T . a1      (contraction over the M rows)
+    RUN(k_transpose_bf16(dy2, tA, (int)M, O, O, Mp, st));
+    RUN(k_transpose_bf16((const bf16*)a1, tB, (int)M, H, H, Mp, st));
+    RUN(gemm(tA, Mp, tB, Mp, O, H, (int)M, TA_EPI_F32, d_w2, H, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+    // dgrad linear_2: d(a1)[M,H] = dy2 . W2
+    RUN(gemm(dy2, O, w->w2_t, O, M, H, O, TA_EPI_BF16, da1, H, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+    // GELU + norm backward (in place: d(a1) -> d(y1)), d(norm.weight)
+    RUN(k_proj_norm_bwd((const bf16*)y1, w->norm_w, da1, 0, da1, d_norm_w, M, H, w->eps, 1, st));
+    // wgrad linear_1: dW1[H,I] = dy1^T . x_stacked
+    RUN(k_transpose_bf16(da1, tA, (int)M, H, H, Mp, st));
+    RUN(k_transpose_bf16((const bf16*)x_stacked, tB, (int)M, I, I, Mp, st));
+    RUN(gemm(tA, Mp, tB, Mp, H, I, (int)M, TA_EPI_F32, d_w1, I, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+    return 0;
+}
+
+// =============================================================================================================
+// Qwen3: forward + CE + backward to inputs_embeds
+// =============================================================================================================
+namespace {
+struct LmBufs {
+    // per-layer stash (index by layer when with_backward, else all layers alias slot 0)
+    float* resid;      // [L+1][M, D] : resid[l] = input of layer l (l >= 1), resid[L] = final hidden
+    float* resid_mid;  // [L][M, D]
+    bf16* qkv;         // [L][M, QKV]
+    bf16* qk;          // [L][M, QK]
+    bf16* att;         // [L][M, Hq*hd]
+    float* lse;        // [L][B*Hq*S]
+    bf16* gu;          // [L][M, 2F]
+    // scratch
+    bf16* xn;          // [M, D]
+    bf16* h;           // [M, F]
+    bf16* hl;          // [n_lab, D]
+    bf16* logits;      // [n_lab, Vpad]
+    bf16* dhl;         // [n_lab, D]
+    float* dx;         // aliases d_inputs_embeds
+    bf16* dxb;         // [M, D]
+    bf16* big;         // [M, max(2F, QKV)]
+    bf16* dxn;         // [M, D]
+    bf16* datt;        // [M, Hq*hd]
+    float* dq;         // [M, Hq*hd]
+    bf16* dk;          // [M, Hkv*hd]
+    bf16* dv;          // [M, Hkv*hd]
+    float* dsum;       // [B*Hq*S]
+    long long stride_layers;   // 1 if with_backward else 0
+};
+
+long long lm_carve(const ta_lm_weights* w, int B, int S, int n_lab, int with_bwd, void* ws, long long cap, LmBufs* b) {
+    const long long M = (long long)B * S, D = w->dim, F = w->ffn;
+    const long long QD = (long long)w->n_q_heads * w->head_dim, KD = (long long)w->n_kv_heads * w->head_dim;
+    const long long QKV = QD + 2 * KD, QK = QD + KD;
+    const long long L = with_bwd ? w->n_layers : 1;
+    Carver c(ws, cap);
+    b->stride_layers = with_bwd ? 1 : 0;
+    b->resid = c.take<float>((with_bwd ? (w->n_layers + 1) : 2) * M * D);
+    b->resid_mid = c.take<float>(L * M * D);
+    b->qkv = c.take<bf16>(L * M * QKV);
+    b->qk = c.take<bf16>(L * M * QK);
+    b->att = c.take<bf16>(L * M * QD);
+    b->lse = c.take<float>(L * (long long)B * w->n_q_heads * S);
+    b->gu = c.take<bf16>(L * M * 2 * F);
+    b->xn = c.take<bf16>(M * D);
+    b->h = c.take<bf16>(M * F);
+    b->hl = c.take<bf16>((long long)n_lab * D);
+    b->logits = c.take<bf16>((long long)n_lab * w->vocab_pad);
+    b->dhl = c.take<bf16>((long long)n_lab * D);
+    if (with_bwd) {
+        b->dxb = c.take<bf16>(M * D);
+        const long long bigw = (2 * F > QKV) ? 2 * F : QKV;
+        b->big = c.take<bf16>(M * bigw);
+        b->dxn = c.take<bf16>(M * D);
+        b->datt = c.take<bf16>(M * QD);
+        b->dq = c.take<float>(M * QD);
+        b->dk = c.take<bf16>(M * KD);
+        b->dv = c.take<bf16>(M * KD);
+        b->dsum = c.take<float>((long long)B * w->n_q_heads * S);
+    }
+    return c.off;
+}
+}  // namespace
+
+TA_API int ta_lm_workspace_bytes(const ta_lm_weights* w, int B, int S, int n_labelled, int with_backward, long long* bytes) {
+    TA_REQUIRE(w && bytes, "null");
+    LmBufs b;
+    *bytes = lm_carve(w, B, S, n_labelled, with_backward, nullptr, 0, &b) + 256;
+    return 0;
+}
+
+TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args* a, void* stream) {
+    TA_REQUIRE(w && a && a->inputs_embeds && a->workspace && a->loss, "ta_lm_forward_backward: null pointer");
+    TA_REQUIRE(w->head_dim == 128, "Qwen3 path: head_dim must be 128");
+    TA_REQUIRE(a->S <= w->max_pos, "sequence length %d exceeds the rotary table (%d)", a->S, w->max_pos);
+    TA_REQUIRE(!a->with_backward || a->d_inputs_embeds, "with_backward needs d_inputs_embeds");
+    TA_REQUIRE(a->n_labelled == 0 || (a->label_rows && a->label_targets), "label rows / targets missing");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int B = a->B, S = a->S, nl = a->n_labelled;
+    const long long M = (long long)B * S;
+    const int D = w->dim, F = w->ffn, Hq = w->n_q_heads, Hkv = w->n_kv_heads, hd = w->head_dim;
+    const int QD = Hq * hd, KD = Hkv * hd, QKV = QD + 2 * KD, QK = QD + KD;
+    const int Lyr = w->n_layers;
+    LmBufs b;
+    const long long need = lm_carve(w, B, S, nl, a->with_backward, a->workspace, a->workspace_bytes, &b);
+    TA_REQUIRE(need <= a->workspace_bytes, "LM workspace too small: need %lld, have %lld", need, a->workspace_bytes);
+    if (M == 0) return 0;
+    const long long sl = b.stride_layers;
+    const float scale = 1.0f / sqrtf((float)hd);
+    const long long lse_n = (long long)B * Hq * S;
+
+    // ------------------------------ forward ------------------------------
+    const float* x_in = a->inputs_embeds;
+    for (int l = 0; l < Lyr; ++l) {
+        const void* const* Lw = w->layers + (long long)l * TA_LM_PTRS_PER_LAYER;
+        bf16* qkv = b.qkv + sl * l * M * QKV;
+        bf16* qk = b.qk + sl * l * M * QK;
+        bf16* att = b.att + sl * l * M * QD;
+        float* lse = b.lse + sl * l * lse_n;
+        float* x_mid = b.resid_mid + sl * l * M * D;
+        bf16* gu = b.gu + sl * l * M * 2 * F;
+        float* x_out = b.resid + (a->with_backward ? (long long)(l + 1) : (long long)((l + 1) & 1)) * M * D;
+
+        RUN(k_rmsnorm_f32(x_in, (const float*)Lw[TA_LM_LN1_W], b.xn, nullptr, M, D, w->eps, st));
+        RUN(gemm(b.xn, D, Lw[TA_LM_WQKV], D, M, QKV, D, TA_EPI_BF16, qkv, QKV, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+        RUN(k_lm_qknorm_rope_fwd(qkv, qk, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W], w->rope_cos, w->rope_sin,
+                                 M, S, Hq, Hkv, w->eps, st));
+        RUN(ta_attn_fwd(qk, qk + QD, qkv + QK, att, lse, B, S, Hq, Hkv, hd, QK, QK, QKV, QD, 1, scale, st));
+        RUN(gemm(att, QD, Lw[TA_LM_WO], QD, M, D, QD, TA_EPI_F32_RESID, x_mid, D, nullptr, x_in, nullptr, 0, nullptr, 0, st));
+        RUN(k_rmsnorm_f32(x_mid, (const float*)Lw[TA_LM_LN2_W], b.xn, nullptr, M, D, w->eps, st));
+        RUN(gemm(b.xn, D, Lw[TA_LM_WGU], D, M, 2 * F, D, TA_EPI_SWIGLU, b.h, F, nullptr, nullptr, gu, 2 * F, nullptr, 0, st));
+        RUN(gemm(b.h, F, Lw[TA_LM_WD], F, M, D, F, TA_EPI_F32_RESID, x_out, D, nullptr, x_mid, nullptr, 0, nullptr, 0, st));
+        x_in = x_out;
+    }
+    const float* x_final = x_in;
+
+    // ------------------------------ head: final norm on the labelled rows, lm_head, CE ------------------------------
+    if (nl > 0) {
+        RUN(k_rmsnorm_f32(x_final, w->final_norm_w, b.hl, a->label_rows, nl, D, w->eps, st));
+        RUN(gemm(b.hl, D, w->embed_bf16, D, nl, (int)w->vocab_pad, D, TA_EPI_BF16, b.logits, w->vocab_pad, nullptr, nullptr, nullptr,
+                 0, nullptr, 0, st));
+        RUN(k_ce_fwd_bwd(b.logits, w->vocab_pad, a->label_targets, nl, (int)w->vocab, (int)w->vocab_pad, a->inv_num_items, a->loss,
+                         a->row_loss, a->with_backward, st));
+    }
+    if (!a->with_backward) return 0;
+
+    // ------------------------------ backward ------------------------------
+    float* dx = a->d_inputs_embeds;
+    TA_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * M * D, st));
+    if (nl > 0) {
+        // d(normed hidden) = d(logits) . E     [nl, D]
+        RUN(gemm(b.logits, w->vocab_pad, w->embed_bf16_t, w->vocab_pad, nl, D, (int)w->vocab_pad, TA_EPI_BF16, b.dhl, D, nullptr,
+                 nullptr, nullptr, 0, nullptr, 0, st));
+        RUN(k_rmsnorm_f32_bwd(b.dhl, x_final, w->final_norm_w, dx, a->label_rows, nl, D, w->eps, 0, st));
+    }
+    for (int l = Lyr - 1; l >= 0; --l) {
+        const void* const* Lw = w->layers + (long long)l * TA_LM_PTRS_PER_LAYER;
+        const bf16* qkv = b.qkv + (long long)l * M * QKV;
+        const bf16* qk = b.qk + (long long)l * M * QK;
+        const bf16* att = b.att + (long long)l * M * QD;
+        const float* lse = b.lse + (long long)l * lse_n;
+        const float* x_mid = b.resid_mid + (long long)l * M * D;
+        const bf16* gu = b.gu + (long long)l * M * 2 * F;
+        const float* x_l = (l == 0) ? a->inputs_embeds : (b.resid + (long long)l * M * D);
+
+        // MLP branch
+        RUN(k_cast_f32_bf16(dx, b.dxb, M * D, st));
+        RUN(gemm(b.dxb, D, Lw[TA_LM_WD_T], D, M, F, D, TA_EPI_SWIGLU_BWD, b.big, 2 * F, nullptr, nullptr, nullptr, 0, gu, 2 * F, st));
+        RUN(gemm(b.big, 2 * F, Lw[TA_LM_WGU_T], 2 * F, M, D, 2 * F, TA_EPI_BF16, b.dxn, D, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+        RUN(k_rmsnorm_f32_bwd(b.dxn, x_mid, (const float*)Lw[TA_LM_LN2_W], dx, nullptr, M, D, w->eps, 1, st));
+        // attention branch
+        RUN(k_cast_f32_bf16(dx, b.dxb, M * D, st));
+        RUN(gemm(b.dxb, D, Lw[TA_LM_WO_T], D, M, QD, D, TA_EPI_BF16, b.datt, QD, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+        RUN(ta_attn_bwd(qk, qk + QD, qkv + QK, att, b.datt, lse, b.dsum, b.dq, b.dk, b.dv, B, S, Hq, Hkv, hd, QK, QK, QKV, QD, QD, QD,
+                        KD, KD, 1, scale, st));
+        RUN(k_lm_qknorm_rope_bwd(qkv, b.dq, b.dk, b.dv, b.big, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W],
+                                 w->rope_cos, w->rope_sin, M, S, Hq, Hkv, w->eps, st));
+        RUN(gemm(b.big, QKV, Lw[TA_LM_WQKV_T], QKV, M, D, QKV, TA_EPI_BF16, b.dxn, D, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+        RUN(k_rmsnorm_f32_bwd(b.dxn, x_l, (const float*)Lw[TA_LM_LN1_W], dx, nullptr, M, D, w->eps, 1, st));
+    }
+    return 0;
+}
+
+TA_API int ta_lm_hidden_to_logits(const ta_lm_weights* w, const float* hidden, const int* rows, int n_rows, void* normed_ws,
+                                  void* logits, void* stream) {
+    TA_REQUIRE(w && hidden && normed_ws && logits, "ta_lm_hidden_to_logits: null pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n_rows == 0) return 0;
+    RUN(k_rmsnorm_f32(hidden, w->final_norm_w, (bf16*)normed_ws, rows, n_rows, w->dim, w->eps, st));
+    RUN(gemm(normed_ws, w->dim, w->embed_bf16, w->dim, n_rows, (int)w->vocab_pad, w->dim, TA_EPI_BF16, logits, w->vocab_pad, nullptr,
+             nullptr, nullptr, 0, nullptr, 0, st));
+    return 0;
+}

@@ -1,0 +1,458 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = epilogue( A[M,K] . B[N,K]^T )
+//
+//   A, B : bf16, K-major (row-major with K contiguous), leading dims in elements (multiples of 8)
+//   accumulate fp32 in TMEM, persistent CTAs (one per SM), warp-specialised:
+//     warp 0 : TMA producer (one elected lane)      smem ring of STAGES x {A 128x64, B BNx64}, SWIZZLE_128B
+//     warp 1 : MMA issuer  (one lane)               tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16
+//     warp 2 : TMEM allocator (2 x BN columns: double-buffered accumulator)
+//     warps 4-7 : epilogue (tcgen05.ld 32x32b, fused bias / GELU / residual / SwiGLU / SwiGLU-backward)
+//
+// Every linear layer of the path (GLM-ASR encoder, projector, Qwen3 fwd + dgrad, lm_head) goes through this file.
+// Reference call sites replaced: HF:models/glmasr/modeling_glmasr.py:198-206,223,228-239 ; HF:models/qwen3/
+// modeling_qwen3.py:81-83,263-291,505 ; tiny_audio/projectors.py:66-71.
+#include "common.cuh"
+#include "tinyaudio_b200.h"
+
+#include <mutex>
+#include <unordered_map>
+#include <cstdarg>
+
+// ----------------------------------------------------------------------------------------------
+// error string (shared by all translation units)
+// ----------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "ok";
+void ta_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+TA_API const char* ta_last_error_string(void) { return g_err; }
+TA_API int ta_version(void) { return 100; }
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct Cfg {
+    static constexpr int STAGES = (BN == 128) ? 6 : 4;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct EpiArgs {
+    void* out;
+    long long ldo;
+    const float* bias;
+    const void* resid;
+    long long ldr;
+    void* out2;
+    long long ldo2;
+    const bf16* aux;
+    long long ldaux;
+    float alpha;
+};
+
+__device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32]) {
+    uint4* p = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        p[i] = u;
+    }
+}
+__device__ __forceinline__ void load_bf16x32(const bf16* src, float (&v)[32]) {
+    const uint4* p = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u = p[i];
+        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        v[8 * i + 0] = a.x; v[8 * i + 1] = a.y; v[8 * i + 2] = b.x; v[8 * i + 3] = b.y;
+        v[8 * i + 4] = c.x; v[8 * i + 5] = c.y; v[8 * i + 6] = d.x; v[8 * i + 7] = d.y;
+    }
+}
+__device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32]) {
+    float4* p = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void load_f32x32(const float* src, float (&v)[32]) {
+    const float4* p = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float4 f = p[i];
+        v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+    }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+            EpiArgs ep) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + C::STAGES * C::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + C::STAGES;
+    uint64_t* tfull = bars + 2 * C::STAGES;
+    uint64_t* tempty = bars + 2 * C::STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_n = N / BN;
+    const int tiles_m = (M + BM - 1) / BM;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                    tma_load_2d(smA + stage * C::A_BYTES, &tmA, &full[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(smB + stage * C::B_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(smA + stage * C::A_BYTES);
+                    const uint32_t b0 = smem_u32(smB + stage * C::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ad = umma_desc_sw128_kmajor(a0 + k * UMMA_K * 2);
+                        const uint64_t bd = umma_desc_sw128_kmajor(b0 + k * UMMA_K * 2);
+                        umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[as]);
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;   // TMEM lane quadrant this warp may touch
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const long long row = (long long)m_blk * BM + q * 32 + lane;
+            const bool row_ok = row < M;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+
+            if constexpr (EPI == TA_EPI_SWIGLU) {
+                // tile columns come in 128-wide groups: [64 gate | 64 up] (weights interleaved by the host)
+#pragma unroll 1
+                for (int sb = 0; sb < BN / 128; ++sb) {
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t rg[32], ru[32];
+                        tmem_ld_32x32(taddr + sb * 128 + c * 32, rg);
+                        tmem_ld_32x32(taddr + sb * 128 + 64 + c * 32, ru);
+                        tmem_ld_wait();
+                        __syncwarp();
+                        if (row_ok) {
+                            float g[32], u[32], h[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                g[i] = bf16_round(__uint_as_float(rg[i]));
+                                u[i] = bf16_round(__uint_as_float(ru[i]));
+                                const float s = bf16_round(g[i] * sigmoidf_(g[i]));   // act_fn output is bf16 under autocast
+                                h[i] = s * u[i];
+                            }
+                            const long long col_gu = (long long)n_blk * BN + sb * 128 + c * 32;
+                            const long long col_h = ((long long)n_blk * BN + sb * 128) / 2 + c * 32;
+                            store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col_h, h);
+                            if (ep.out2) {
+                                bf16* gu = reinterpret_cast<bf16*>(ep.out2) + row * ep.ldo2 + col_gu;
+                                store_bf16x32(gu, g);
+                                store_bf16x32(gu + 64, u);
+                            }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    __syncwarp();
+                    if (row_ok) {
+                    const long long col = (long long)n_blk * BN + c * 32;
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    if constexpr (EPI != TA_EPI_F32 && EPI != TA_EPI_SWIGLU_BWD) {
+                        if (ep.bias) {
+                            float b[32];
+                            load_f32x32(ep.bias + col, b);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] += b[i];
+                        }
+                    }
+                    if constexpr (EPI == TA_EPI_BF16) {
+                        store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
+                    } else if constexpr (EPI == TA_EPI_BF16_GELU) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(bf16_round(v[i]));
+                        store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
+                    } else if constexpr (EPI == TA_EPI_BF16_RESID) {
+                        float rs[32];
+                        load_bf16x32(reinterpret_cast<const bf16*>(ep.resid) + row * ep.ldr + col, rs);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = rs[i] + bf16_round(v[i]);
+                        store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
+                    } else if constexpr (EPI == TA_EPI_F32_RESID) {
+                        float rs[32];
+                        load_f32x32(reinterpret_cast<const float*>(ep.resid) + row * ep.ldr + col, rs);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = rs[i] + bf16_round(v[i]);
+                        store_f32x32(reinterpret_cast<float*>(ep.out) + row * ep.ldo + col, v);
+                    } else if constexpr (EPI == TA_EPI_F32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= ep.alpha;
+                        store_f32x32(reinterpret_cast<float*>(ep.out) + row * ep.ldo + col, v);
+                    } else if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
+                        // v = d(h) for h columns [col, col+32); the stash holds (gate, up) interleaved in 64-blocks
+                        const long long jb = col / 64, jo = col % 64;
+                        const bf16* gu = ep.aux + row * ep.ldaux + jb * 128 + jo;
+                        float g[32], u[32], dg[32], du[32];
+                        load_bf16x32(gu, g);
+                        load_bf16x32(gu + 64, u);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float dh = bf16_round(v[i]);
+                            const float sg = sigmoidf_(g[i]);
+                            const float silu = bf16_round(g[i] * sg);
+                            du[i] = dh * silu;
+                            dg[i] = dh * u[i] * (sg * (1.0f + g[i] * (1.0f - sg)));
+                        }
+                        bf16* o = reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + jb * 128 + jo;
+                        store_bf16x32(o, dg);
+                        store_bf16x32(o + 64, du);
+                    }
+                    }   // row_ok
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// ----------------------------------------------------------------------------------------------
+// host: tensor maps
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    long long rows, cols, ld;
+    int box_rows;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.ptr);
+        h ^= std::hash<long long>()(k.rows * 1315423911LL + k.cols) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+        h ^= std::hash<long long>()(k.ld * 31 + k.box_rows) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+        return h;
+    }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 2-D bf16 row-major [rows, cols] (ld elements), box = {64 cols, box_rows}, SWIZZLE_128B, zero fill out of bounds
+int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    MapKey key{ptr, rows, cols, ld, box_rows};
+    {
+        std::lock_guard<std::mutex> g(g_map_mu);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) {
+            *out = it->second;
+            return 0;
+        }
+    }
+    EncodeTiledFn fn = get_encode_fn();
+    TA_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    TA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand pointer must be 16-byte aligned");
+    TA_REQUIRE((ld * 2) % 16 == 0, "GEMM operand leading dimension must be a multiple of 8 elements (got %lld)", ld);
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows,
+               cols, ld);
+    std::lock_guard<std::mutex> g(g_map_mu);
+    if (g_maps.size() > 8192) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return 0;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int BN, int EPI>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiArgs& ep, cudaStream_t st) {
+    using C = Cfg<BN>;
+    auto kern = gemm_kernel<BN, EPI>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int tiles = ((M + BM - 1) / BM) * (N / BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, M, N, K, ep);
+    TA_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int BN>
+int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiArgs& ep,
+                 cudaStream_t st) {
+    switch (epi) {
+        case TA_EPI_BF16: return launch<BN, TA_EPI_BF16>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_BF16_GELU: return launch<BN, TA_EPI_BF16_GELU>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_BF16_RESID: return launch<BN, TA_EPI_BF16_RESID>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_F32_RESID: return launch<BN, TA_EPI_F32_RESID>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_F32: return launch<BN, TA_EPI_F32>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_SWIGLU: return launch<BN, TA_EPI_SWIGLU>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_SWIGLU_BWD: return launch<BN, TA_EPI_SWIGLU_BWD>(ta, tb, M, N, K, ep, st);
+        default: ta_set_error("unknown epilogue mode %d", epi); return -1;
+    }
+}
+
+int g_force_bn = 0;
+
+}  // namespace
+
+TA_API int ta_gemm_set_tile_n(int bn) {
+    if (bn != 0 && bn != 128 && bn != 256) {
+        ta_set_error("tile N must be 0 (auto), 128 or 256");
+        return -1;
+    }
+    g_force_bn = bn;
+    return 0;
+}
+
+TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epi,
+                        const ta_gemm_epilogue* e, void* stream) {
+    TA_REQUIRE(A && B && e && e->out, "ta_gemm_bf16: null pointer");
+    TA_REQUIRE(M > 0 && N > 0 && K > 0, "ta_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+    TA_REQUIRE(N % 128 == 0, "ta_gemm_bf16: N=%d must be a multiple of 128", N);
+    TA_REQUIRE(K % 8 == 0, "ta_gemm_bf16: K=%d must be a multiple of 8", K);
+    if (epi == TA_EPI_BF16_RESID || epi == TA_EPI_F32_RESID) TA_REQUIRE(e->resid, "residual epilogue needs resid");
+    if (epi == TA_EPI_SWIGLU_BWD) TA_REQUIRE(e->aux && N % 64 == 0, "swiglu-bwd epilogue needs aux stash");
+    int bn = g_force_bn ? g_force_bn : ((N % 256 == 0) ? 256 : 128);
+    if (N % bn != 0) bn = 128;
+    EpiArgs ep;
+    ep.out = e->out; ep.ldo = e->ldo; ep.bias = e->bias; ep.resid = e->resid; ep.ldr = e->ldr ? e->ldr : e->ldo;
+    ep.out2 = e->out2; ep.ldo2 = e->ldo2; ep.aux = reinterpret_cast<const bf16*>(e->aux); ep.ldaux = e->ldaux;
+    ep.alpha = e->alpha == 0.0f ? 1.0f : e->alpha;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, A, M, K, lda, BM);
+    if (rc) return rc;
+    rc = make_map(&tb, B, N, K, ldb, bn);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (bn == 256) return dispatch_epi<256>(epi, ta, tb, M, N, K, ep, st);
+    return dispatch_epi<128>(epi, ta, tb, M, N, K, ep, st);
+}

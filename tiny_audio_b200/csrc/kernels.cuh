@@ -1,0 +1,29 @@
+// Internal launcher declarations shared between translation units (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+int k_im2col_k3(const bf16* x, bf16* out, int B, int T, int C, int stride, cudaStream_t st);
+int k_layernorm_bf16(const bf16* x, const float* w, const float* b, bf16* y, long long rows, int D, float eps, cudaStream_t st);
+int k_rmsnorm_f32(const float* x, const float* w, bf16* y, const int* row_index, long long rows, int D, float eps, cudaStream_t st);
+int k_rmsnorm_f32_bwd(const bf16* dy, const float* x, const float* w, float* dx, const int* row_index, long long rows, int D,
+                      float eps, int accumulate, cudaStream_t st);
+int k_enc_rope(bf16* qkv, const float* cosT, const float* sinT, long long rows, int S, int H, int hd, int rd, cudaStream_t st);
+int k_lm_qknorm_rope_fwd(const bf16* qkv, bf16* qk, const float* qw, const float* kw, const float* cosT, const float* sinT,
+                         long long M, int S, int Hq, int Hkv, float eps, cudaStream_t st);
+int k_lm_qknorm_rope_bwd(const bf16* qkv, const float* dq, const bf16* dk, const bf16* dv, bf16* dqkv, const float* qw,
+                         const float* kw, const float* cosT, const float* sinT, long long M, int S, int Hq, int Hkv, float eps,
+                         cudaStream_t st);
+int k_proj_norm_fwd(const bf16* x, const float* w, void* y, long long rows, int D, float eps, int gelu, cudaStream_t st);
+int k_proj_norm_bwd(const bf16* x, const float* w, const void* dy, int dy_is_f32, bf16* dx, float* dw, long long rows, int D,
+                    float eps, int gelu, cudaStream_t st);
+int k_audio_index(const long long* ids, const long long* counts, int* src_row, int B, int S, int n_a, long long audio_id,
+                  cudaStream_t st);
+int k_embed_scatter(const long long* ids, const int* src_row, const float* table, const float* audio, float* out,
+                    long long n_tok, int D, long long vocab, cudaStream_t st);
+int k_audio_grad_gather(const int* src_row, const float* d_emb, float* d_audio, long long n_tok, int D, cudaStream_t st);
+int k_ce_fwd_bwd(bf16* logits, long long ld, const int* targets, long long rows, int V, int Vpad, float inv_items,
+                 float* loss_sum, float* row_loss, int write_grad, cudaStream_t st);
+int k_transpose_bf16(const bf16* in, bf16* out, int R, int C, long long ld_in, long long ld_out, cudaStream_t st);
+int k_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t st);
+int k_frame_stack(const bf16* x, bf16* out, int B, int S, int n, int k, int D, cudaStream_t st);
+int k_sumsq(const float* g, long long n, float* out, cudaStream_t st);

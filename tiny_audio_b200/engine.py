@@ -1,0 +1,417 @@
+"""Host-side driver of the B200 hot path: packs the frozen towers' weights into the layouts the CUDA
+kernels want, owns the workspaces, and runs one fused forward+backward of
+
+    waveform / mel -> GLM-ASR encoder -> MLP projector -> <audio> scatter -> Qwen3 -> CE -> d(projector params)
+
+through libtinyaudio_b200.so.  PyTorch supplies device memory and the stream, nothing else.
+
+Numerics recipe = the reference's production recipe (fp32 master weights + bf16 autocast,
+configs/training/production.yaml:49): bf16 GEMM operands with fp32 accumulation, fp32 LayerNorm /
+RMSNorm / softmax / CE, fp32 residual stream in the decoder, bf16 residual stream in the encoder
+(conv output is bf16 under autocast), fp32 embedding lookup.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import lib as L
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+@dataclass
+class PathDims:
+    """Dimensions of the path (mirrors oracle.path_oracle.PathConfig; kept separate so the product
+    never imports the oracle)."""
+    n_mels: int = 128
+    hop: int = 160
+    enc_dim: int = 1280
+    enc_ffn: int = 5120
+    enc_layers: int = 32
+    enc_heads: int = 20
+    enc_rope_theta: float = 10000.0
+    enc_partial_rotary: float = 0.5
+    enc_ln_eps: float = 1e-5
+    enc_max_pos: int = 1500
+    proj_k: int = 4
+    proj_hidden: int = 1024
+    proj_eps: float = 1e-6
+    lm_dim: int = 1024
+    lm_ffn: int = 3072
+    lm_layers: int = 28
+    lm_heads: int = 16
+    lm_kv_heads: int = 8
+    lm_head_dim: int = 128
+    lm_rope_theta: float = 1e6
+    lm_eps: float = 1e-6
+    lm_max_pos: int = 4096
+    vocab: int = 151936
+    audio_token_id: int = 151669
+
+    @classmethod
+    def from_any(cls, cfg) -> "PathDims":
+        d = cfg if isinstance(cfg, dict) else {k: getattr(cfg, k) for k in cls.__dataclass_fields__ if hasattr(cfg, k)}
+        return cls(**{k: v for k, v in d.items() if k in cls.__dataclass_fields__})
+
+
+def _rope_tables(n_pos: int, dim: int, theta: float, device, round_bf16: bool):
+    inv = 1.0 / (theta ** (torch.arange(0, dim, 2, dtype=torch.int64).float() / dim))
+    fr = torch.arange(n_pos).float()[:, None] * inv[None, :]
+    cos, sin = fr.cos(), fr.sin()
+    if round_bf16:       # the encoder's cos/sin are cast to the activation dtype (bf16 under autocast)
+        cos, sin = cos.to(BF16).float(), sin.to(BF16).float()
+    return cos.contiguous().to(device), sin.contiguous().to(device)
+
+
+class PackedEncoder:
+    """GLM-ASR encoder weights in kernel layout (state_dict names = HF GlmAsrEncoder)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], dims: PathDims, device):
+        d = dims
+        D = d.enc_dim
+        self.dims = d
+        self.keep = []
+
+        def dev(t, dtype):
+            t = t.detach().to(device=device, dtype=dtype).contiguous()
+            self.keep.append(t)
+            return t
+
+        self.conv1_w = dev(sd["conv1.weight"].permute(0, 2, 1).reshape(D, 3 * d.n_mels), BF16)
+        self.conv1_b = dev(sd["conv1.bias"], F32)
+        self.conv2_w = dev(sd["conv2.weight"].permute(0, 2, 1).reshape(D, 3 * D), BF16)
+        self.conv2_b = dev(sd["conv2.bias"], F32)
+        self.lnf_w, self.lnf_b = dev(sd["norm.weight"], F32), dev(sd["norm.bias"], F32)
+        rot = int((D // d.enc_heads) * d.enc_partial_rotary)
+        self.rope_cos, self.rope_sin = _rope_tables(d.enc_max_pos, rot, d.enc_rope_theta, device, True)
+        ptrs = []
+        for i in range(d.enc_layers):
+            p = f"layers.{i}."
+            wq, wk, wv = (sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv")
+            bq, bv = sd[p + "self_attn.q_proj.bias"], sd[p + "self_attn.v_proj.bias"]
+            layer = [None] * L.ENC_PTRS_PER_LAYER
+            layer[L.ENC_LN1_W] = dev(sd[p + "input_layernorm.weight"], F32)
+            layer[L.ENC_LN1_B] = dev(sd[p + "input_layernorm.bias"], F32)
+            layer[L.ENC_WQKV] = dev(torch.cat([wq, wk, wv], 0), BF16)
+            layer[L.ENC_BQKV] = dev(torch.cat([bq.float().cpu(), torch.zeros(D), bv.float().cpu()], 0), F32)
+            layer[L.ENC_WO] = dev(sd[p + "self_attn.o_proj.weight"], BF16)
+            layer[L.ENC_BO] = dev(sd[p + "self_attn.o_proj.bias"], F32)
+            layer[L.ENC_LN2_W] = dev(sd[p + "post_attention_layernorm.weight"], F32)
+            layer[L.ENC_LN2_B] = dev(sd[p + "post_attention_layernorm.bias"], F32)
+            layer[L.ENC_W1] = dev(sd[p + "mlp.fc1.weight"], BF16)
+            layer[L.ENC_B1] = dev(sd[p + "mlp.fc1.bias"], F32)
+            layer[L.ENC_W2] = dev(sd[p + "mlp.fc2.weight"], BF16)
+            layer[L.ENC_B2] = dev(sd[p + "mlp.fc2.bias"], F32)
+            ptrs.extend(layer)
+        self.table = L.pointer_table(ptrs)
+        self.c = L.EncoderWeights(d.enc_layers, D, d.enc_ffn, d.enc_heads, D // d.enc_heads, rot, d.n_mels, d.enc_max_pos,
+                                  d.enc_ln_eps, L.ptr(self.conv1_w), L.ptr(self.conv1_b), L.ptr(self.conv2_w),
+                                  L.ptr(self.conv2_b), L.ptr(self.lnf_w), L.ptr(self.lnf_b), L.ptr(self.rope_cos),
+                                  L.ptr(self.rope_sin), C.cast(self.table, C.POINTER(L.P)))
+
+
+class PackedLM:
+    """Qwen3 weights in kernel layout (state_dict names = HF Qwen3ForCausalLM)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], dims: PathDims, device):
+        d = dims
+        self.dims = d
+        self.keep = []
+
+        def dev(t, dtype):
+            t = t.detach().to(device=device, dtype=dtype).contiguous()
+            self.keep.append(t)
+            return t
+
+        V, D, F = d.vocab, d.lm_dim, d.lm_ffn
+        self.vocab_pad = _round_up(V, 128)
+        emb = sd["model.embed_tokens.weight"]
+        assert emb.shape[0] == V, f"embedding rows {emb.shape[0]} != vocab {V}"
+        self.embed_f32 = dev(emb, F32)
+        eb = torch.zeros(self.vocab_pad, D, dtype=BF16, device=device)
+        eb[:V] = self.embed_f32.to(BF16)            # tied lm_head (autocast casts the fp32 table to bf16)
+        self.embed_bf16 = eb
+        self.embed_bf16_t = eb.t().contiguous()
+        self.final_norm_w = dev(sd["model.norm.weight"], F32)
+        self.rope_cos, self.rope_sin = _rope_tables(d.lm_max_pos, d.lm_head_dim, d.lm_rope_theta, device, False)
+        assert F % 64 == 0
+        ptrs = []
+        for i in range(d.lm_layers):
+            p = f"model.layers.{i}."
+            wq, wk, wv = (sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv")
+            wqkv = dev(torch.cat([wq, wk, wv], 0), BF16)
+            wo = dev(sd[p + "self_attn.o_proj.weight"], BF16)
+            g = sd[p + "mlp.gate_proj.weight"].reshape(F // 64, 1, 64, D)
+            u = sd[p + "mlp.up_proj.weight"].reshape(F // 64, 1, 64, D)
+            wgu = dev(torch.cat([g, u], 1).reshape(2 * F, D), BF16)    # 64-row blocks: gate, up, gate, up ...
+            wd = dev(sd[p + "mlp.down_proj.weight"], BF16)
+            layer = [None] * L.LM_PTRS_PER_LAYER
+            layer[L.LM_LN1_W] = dev(sd[p + "input_layernorm.weight"], F32)
+            layer[L.LM_WQKV] = wqkv
+            layer[L.LM_WQKV_T] = dev(wqkv.t(), BF16)
+            layer[L.LM_QNORM_W] = dev(sd[p + "self_attn.q_norm.weight"], F32)
+            layer[L.LM_KNORM_W] = dev(sd[p + "self_attn.k_norm.weight"], F32)
+            layer[L.LM_WO] = wo
+            layer[L.LM_WO_T] = dev(wo.t(), BF16)
+            layer[L.LM_LN2_W] = dev(sd[p + "post_attention_layernorm.weight"], F32)
+            layer[L.LM_WGU] = wgu
+            layer[L.LM_WGU_T] = dev(wgu.t(), BF16)
+            layer[L.LM_WD] = wd
+            layer[L.LM_WD_T] = dev(wd.t(), BF16)
+            ptrs.extend(layer)
+        self.table = L.pointer_table(ptrs)
+        self.c = L.LmWeights(d.lm_layers, D, F, d.lm_heads, d.lm_kv_heads, d.lm_head_dim, d.lm_max_pos, V, self.vocab_pad,
+                             d.lm_eps, L.ptr(self.embed_f32), L.ptr(self.embed_bf16), L.ptr(self.embed_bf16_t),
+                             L.ptr(self.final_norm_w), L.ptr(self.rope_cos), L.ptr(self.rope_sin),
+                             C.cast(self.table, C.POINTER(L.P)))
+
+
+class _Workspaces:
+    """Grow-only device scratch keyed by name (allocated through torch's caching allocator)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, nbytes: int) -> torch.Tensor:
+        b = self.bufs.get(name)
+        if b is None or b.numel() < nbytes:
+            self.bufs[name] = b = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return b
+
+    def typed(self, name: str, shape, dtype) -> torch.Tensor:
+        n = int(math.prod(shape))
+        b = self.get(name, n * torch.empty((), dtype=dtype).element_size())
+        return b[: n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+
+
+def label_rows_and_targets(labels_cpu: torch.Tensor):
+    """Shift-by-one on the host (HF:loss/loss_utils.py:56-59): position p predicts labels[p+1].
+    Returns flat row indices (int32) and targets (int32) of the non-ignored positions."""
+    B, S = labels_cpu.shape
+    shift = torch.full_like(labels_cpu, -100)
+    shift[:, :-1] = labels_cpu[:, 1:]
+    flat = shift.reshape(-1)
+    rows = (flat != -100).nonzero().squeeze(-1)
+    return rows.to(torch.int32), flat[rows].to(torch.int32)
+
+
+class HotPath:
+    """One GPU's replica of the frozen towers + the per-step driver."""
+
+    def __init__(self, dims: PathDims, enc_sd, lm_sd, device="cuda"):
+        self.lib = L.load()
+        self.dims = dims
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.TinyAudioB200Error("HotPath needs a CUDA device (no CPU fallback)")
+        self.enc = PackedEncoder(enc_sd, dims, self.device)
+        self.lm = PackedLM(lm_sd, dims, self.device)
+        self.ws = _Workspaces(self.device)
+        self.launches = 0
+
+    # ------------------------------------------------------------------ front end + encoder
+    def logmel(self, wave: torch.Tensor, want_f32: bool = False):
+        """wave (B, L) fp32 CUDA -> (conv1 im2col bf16 [B*T, 3*n_mels], optional fp32 (B,128,T))."""
+        L.require_cuda(wave)
+        assert wave.dtype == F32 and wave.dim() == 2 and wave.stride(1) == 1
+        B, Ls = wave.shape
+        T = Ls // self.dims.hop
+        n = C.c_longlong()
+        L.check(self.lib.ta_logmel_workspace_floats(B, Ls, C.byref(n)))
+        ws = self.ws.typed("logmel", (n.value,), F32)
+        im2 = self.ws.typed("conv1_im2col", (B * T, 3 * self.dims.n_mels), BF16)
+        out = torch.empty(B, self.dims.n_mels, T, device=self.device, dtype=F32) if want_f32 else None
+        L.check(self.lib.ta_logmel_fwd(L.ptr(wave), wave.stride(0), B, Ls, L.ptr(ws), L.ptr(out), L.ptr(im2), L.stream_ptr()))
+        return im2, out, T
+
+    def mel_to_im2col(self, mel: torch.Tensor):
+        L.require_cuda(mel)
+        mel = mel.to(F32).contiguous()
+        B, nm, T = mel.shape
+        assert nm == self.dims.n_mels
+        im2 = self.ws.typed("conv1_im2col", (B * T, 3 * nm), BF16)
+        L.check(self.lib.ta_mel_to_conv1_im2col(L.ptr(mel), B, T, L.ptr(im2), L.stream_ptr()))
+        return im2, T
+
+    def encode(self, im2col: torch.Tensor, B: int, T: int) -> torch.Tensor:
+        """-> encoder last_hidden_state, bf16 [B, S_e, enc_dim]."""
+        S = (T + 2 - 3) // 2 + 1
+        n = C.c_longlong()
+        L.check(self.lib.ta_encoder_workspace_bytes(C.byref(self.enc.c), B, T, C.byref(n)))
+        ws = self.ws.get("encoder", n.value)
+        out = self.ws.typed("enc_out", (B, S, self.dims.enc_dim), BF16)
+        L.check(self.lib.ta_encoder_forward(C.byref(self.enc.c), L.ptr(im2col), B, T, L.ptr(ws), n.value, L.ptr(out),
+                                            L.stream_ptr()))
+        return out
+
+    # ------------------------------------------------------------------ projector
+    def _proj_struct(self, params: Dict[str, torch.Tensor], need_t: bool):
+        d = self.dims
+        H = params["linear_1.weight"].shape[0]
+        w1 = self.ws.typed("proj_w1", (H, d.proj_k * d.enc_dim), BF16)
+        w2 = self.ws.typed("proj_w2", (d.lm_dim, H), BF16)
+        st = L.stream_ptr()
+        p1, p2 = params["linear_1.weight"], params["linear_2.weight"]
+        L.check(self.lib.ta_cast_f32_bf16(L.ptr(p1), L.ptr(w1), p1.numel(), st))
+        L.check(self.lib.ta_cast_f32_bf16(L.ptr(p2), L.ptr(w2), p2.numel(), st))
+        w2t = None
+        if need_t:
+            w2t = self.ws.typed("proj_w2t", (H, d.lm_dim), BF16)
+            L.check(self.lib.ta_transpose_bf16(L.ptr(w2), L.ptr(w2t), d.lm_dim, H, H, d.lm_dim, st))
+        n1, n2 = params["norm.weight"], params["norm_2.weight"]
+        self._proj_keep = (w1, w2, w2t, n1, n2)
+        return L.MlpProjectorWeights(d.proj_k * d.enc_dim, H, d.lm_dim, d.proj_eps, L.ptr(w1), L.ptr(n1), L.ptr(w2),
+                                     L.ptr(w2t), L.ptr(n2)), H
+
+    def frame_stack(self, enc_out: torch.Tensor):
+        B, S, D = enc_out.shape
+        k = self.dims.proj_k
+        n = (S - k) // k + 1
+        if n * k == S:
+            return enc_out.view(B * n, k * D), n          # free view (tiny_audio/projectors.py:87)
+        out = self.ws.typed("stacked", (B * n, k * D), BF16)
+        L.check(self.lib.ta_frame_stack(L.ptr(enc_out), L.ptr(out), B, S, n, k, D, L.stream_ptr()))
+        return out, n
+
+    def projector_forward(self, x_stacked: torch.Tensor, params, need_bwd: bool):
+        for k in ("linear_1.weight", "norm.weight", "linear_2.weight", "norm_2.weight"):
+            t = params[k]
+            L.require_cuda(t)
+            assert t.dtype == F32 and t.is_contiguous(), f"projector param {k} must be contiguous fp32"
+        pw, H = self._proj_struct(params, need_bwd)
+        M = x_stacked.shape[0]
+        d = self.dims
+        y1 = self.ws.typed("proj_y1", (M, H), BF16)
+        a1 = self.ws.typed("proj_a1", (M, H), BF16)
+        y2 = self.ws.typed("proj_y2", (M, d.lm_dim), BF16)
+        out = self.ws.typed("proj_out", (M, d.lm_dim), F32)
+        L.check(self.lib.ta_mlp_projector_forward(C.byref(pw), L.ptr(x_stacked), M, L.ptr(y1), L.ptr(a1), L.ptr(y2), L.ptr(out),
+                                                  L.stream_ptr()))
+        return out, (pw, x_stacked, M, y1, a1, y2, H)
+
+    def projector_backward(self, stash, d_out: torch.Tensor, grads: Dict[str, torch.Tensor]):
+        pw, x_stacked, M, y1, a1, y2, H = stash
+        n = C.c_longlong()
+        L.check(self.lib.ta_mlp_projector_backward_workspace_bytes(C.byref(pw), M, C.byref(n)))
+        ws = self.ws.get("proj_bwd", n.value)
+        grads["norm.weight"].zero_()
+        grads["norm_2.weight"].zero_()
+        L.check(self.lib.ta_mlp_projector_backward(C.byref(pw), L.ptr(x_stacked), M, L.ptr(y1), L.ptr(a1), L.ptr(y2), L.ptr(d_out),
+                                                   L.ptr(ws), n.value, L.ptr(grads["linear_1.weight"]), L.ptr(grads["norm.weight"]),
+                                                   L.ptr(grads["linear_2.weight"]), L.ptr(grads["norm_2.weight"]), L.stream_ptr()))
+
+    # ------------------------------------------------------------------ embed + scatter
+    def embed_scatter(self, input_ids: torch.Tensor, counts: torch.Tensor, audio: torch.Tensor, n_a: int):
+        B, S = input_ids.shape
+        d = self.dims
+        src = self.ws.typed("src_row", (B * S,), torch.int32)
+        emb = self.ws.typed("inputs_embeds", (B * S, d.lm_dim), F32)
+        st = L.stream_ptr()
+        L.check(self.lib.ta_audio_index(L.ptr(input_ids), L.ptr(counts), L.ptr(src), B, S, n_a, d.audio_token_id, st))
+        L.check(self.lib.ta_embed_scatter(L.ptr(input_ids), L.ptr(src), L.ptr(self.lm.embed_f32), L.ptr(audio), L.ptr(emb),
+                                          B * S, d.lm_dim, d.vocab, st))
+        return emb, src
+
+    # ------------------------------------------------------------------ decoder + loss (+ backward to inputs_embeds)
+    def lm_step(self, emb: torch.Tensor, B: int, S: int, rows: torch.Tensor, targets: torch.Tensor, inv_items: float,
+                with_backward: bool, want_row_loss: bool = False):
+        d = self.dims
+        nl = int(rows.numel())
+        n = C.c_longlong()
+        L.check(self.lib.ta_lm_workspace_bytes(C.byref(self.lm.c), B, S, nl, int(with_backward), C.byref(n)))
+        ws = self.ws.get("lm", n.value)
+        loss = torch.zeros(1, device=self.device, dtype=F32)
+        demb = self.ws.typed("d_inputs_embeds", (B * S, d.lm_dim), F32) if with_backward else None
+        row_loss = torch.empty(nl, device=self.device, dtype=F32) if want_row_loss else None
+        args = L.LmStepArgs(B, S, nl, int(with_backward), L.ptr(emb), L.ptr(rows), L.ptr(targets), inv_items, L.ptr(loss),
+                            L.ptr(row_loss), L.ptr(demb), L.ptr(ws), n.value)
+        L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
+        return loss, demb, row_loss
+
+    # ------------------------------------------------------------------ the whole step
+    def forward_backward(self, *, input_ids: torch.Tensor, labels_cpu: Optional[torch.Tensor], proj_params,
+                         waveform: Optional[torch.Tensor] = None, input_features: Optional[torch.Tensor] = None,
+                         audio_token_counts: Optional[torch.Tensor] = None, num_items_in_batch: Optional[float] = None,
+                         grads: Optional[Dict[str, torch.Tensor]] = None, return_parts: bool = False):
+        """Returns (loss [1] fp32 device tensor, parts).  When `grads` is given (fp32 tensors shaped like the projector
+        params) the backward runs and fills them with d(loss)/d(param)."""
+        d = self.dims
+        B, S = input_ids.shape
+        parts = {}
+        if waveform is not None:
+            im2, mel_f32, T = self.logmel(waveform, want_f32=return_parts)
+            if return_parts:
+                parts["mel"] = mel_f32
+        else:
+            im2, T = self.mel_to_im2col(input_features)
+        enc = self.encode(im2, B, T)
+        xs, n_a = self.frame_stack(enc)
+        with_bwd = grads is not None
+        audio, stash = self.projector_forward(xs, proj_params, with_bwd)
+        if audio_token_counts is None:
+            audio_token_counts = (input_ids == d.audio_token_id).sum(-1)
+        counts = audio_token_counts.to(device=self.device, dtype=torch.int64).contiguous()
+        ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
+        emb, src = self.embed_scatter(ids, counts, audio, n_a)
+        if labels_cpu is not None:
+            rows, targets = label_rows_and_targets(labels_cpu)
+            n_items = float(rows.numel()) if num_items_in_batch is None else float(num_items_in_batch)
+            rows_d = rows.to(self.device, non_blocking=True)
+            tg_d = targets.to(self.device, non_blocking=True)
+        else:
+            rows_d = torch.empty(0, dtype=torch.int32, device=self.device)
+            tg_d = rows_d
+            n_items = 1.0
+        inv = 1.0 / max(n_items, 1.0)
+        loss, demb, _ = self.lm_step(emb, B, S, rows_d, tg_d, inv, with_bwd)
+        if with_bwd:
+            d_audio = self.ws.typed("d_audio", (B * n_a, d.lm_dim), F32)
+            d_audio.zero_()
+            L.check(self.lib.ta_audio_grad_gather(L.ptr(src), L.ptr(demb), L.ptr(d_audio), B * S, d.lm_dim, L.stream_ptr()))
+            self.projector_backward(stash, d_audio, grads)
+        if return_parts:
+            parts.update(encoder_out=enc, projector_out=audio.view(B, n_a, d.lm_dim), inputs_embeds=emb.view(B, S, d.lm_dim))
+        return loss, parts
+
+
+class FusedClipAdamW:
+    """clip_grad_norm_(max_norm) + AdamW over a list of fp32 tensors, all on device, no host sync
+    (replaces HF Trainer's clip + torch.optim.AdamW(fused=True); configs/training/production.yaml:5-9)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
+                 no_decay=()):
+        self.lib = L.load()
+        self.params = list(params)
+        self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.no_decay = set(id(p) for p in no_decay)
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.step_count = 0
+        self.gnorm_sq = torch.zeros(1, device=self.params[0].device, dtype=F32)
+
+    def step(self, grads, lr: Optional[float] = None):
+        st = L.stream_ptr()
+        self.step_count += 1
+        self.gnorm_sq.zero_()
+        for g in grads:
+            L.check(self.lib.ta_grad_sumsq(L.ptr(g), g.numel(), L.ptr(self.gnorm_sq), st))
+        lr = self.lr if lr is None else lr
+        for p, g, m, v in zip(self.params, grads, self.m, self.v):
+            wd = 0.0 if id(p) in self.no_decay else self.wd
+            L.check(self.lib.ta_adamw_clip_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, self.betas[0],
+                                                self.betas[1], self.eps, wd, self.step_count, self.max_norm,
+                                                L.ptr(self.gnorm_sq), st))
+
+    def grad_norm(self) -> torch.Tensor:
+        return self.gnorm_sq.sqrt()

@@ -1,0 +1,180 @@
+"""ctypes binding of libtinyaudio_b200.so (include/tinyaudio_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, an exception is raised.
+PyTorch is used only for device memory and streams; every function takes raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtinyaudio_b200.so")
+
+c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+P = c_void_p
+
+# epilogue modes (enum in the header)
+EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESID, EPI_F32_RESID, EPI_F32, EPI_SWIGLU, EPI_SWIGLU_BWD = range(7)
+ENC_PTRS_PER_LAYER = 12
+LM_PTRS_PER_LAYER = 12
+(ENC_LN1_W, ENC_LN1_B, ENC_WQKV, ENC_BQKV, ENC_WO, ENC_BO, ENC_LN2_W, ENC_LN2_B, ENC_W1, ENC_B1, ENC_W2, ENC_B2) = range(12)
+(LM_LN1_W, LM_WQKV, LM_WQKV_T, LM_QNORM_W, LM_KNORM_W, LM_WO, LM_WO_T, LM_LN2_W, LM_WGU, LM_WGU_T, LM_WD, LM_WD_T) = range(12)
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [("out", P), ("ldo", c_ll), ("bias", P), ("resid", P), ("ldr", c_ll), ("out2", P), ("ldo2", c_ll),
+                ("aux", P), ("ldaux", c_ll), ("alpha", c_float)]
+
+
+class EncoderWeights(C.Structure):
+    _fields_ = [("n_layers", c_int), ("dim", c_int), ("ffn", c_int), ("heads", c_int), ("head_dim", c_int),
+                ("rot_dim", c_int), ("n_mels", c_int), ("max_pos", c_int), ("ln_eps", c_float),
+                ("conv1_w", P), ("conv1_b", P), ("conv2_w", P), ("conv2_b", P), ("lnf_w", P), ("lnf_b", P),
+                ("rope_cos", P), ("rope_sin", P), ("layers", C.POINTER(P))]
+
+
+class MlpProjectorWeights(C.Structure):
+    _fields_ = [("in_dim", c_int), ("hidden", c_int), ("out_dim", c_int), ("eps", c_float),
+                ("w1", P), ("norm_w", P), ("w2", P), ("w2_t", P), ("norm2_w", P)]
+
+
+class LmWeights(C.Structure):
+    _fields_ = [("n_layers", c_int), ("dim", c_int), ("ffn", c_int), ("n_q_heads", c_int), ("n_kv_heads", c_int),
+                ("head_dim", c_int), ("max_pos", c_int), ("vocab", c_ll), ("vocab_pad", c_ll), ("eps", c_float),
+                ("embed_f32", P), ("embed_bf16", P), ("embed_bf16_t", P), ("final_norm_w", P),
+                ("rope_cos", P), ("rope_sin", P), ("layers", C.POINTER(P))]
+
+
+class LmStepArgs(C.Structure):
+    _fields_ = [("B", c_int), ("S", c_int), ("n_labelled", c_int), ("with_backward", c_int),
+                ("inputs_embeds", P), ("label_rows", P), ("label_targets", P), ("inv_num_items", c_float),
+                ("loss", P), ("row_loss", P), ("d_inputs_embeds", P), ("workspace", P), ("workspace_bytes", c_ll)]
+
+
+_SIGS = {
+    "ta_version": ([], c_int),
+    "ta_gemm_bf16": ([P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, C.POINTER(GemmEpilogue), P], c_int),
+    "ta_gemm_set_tile_n": ([c_int], c_int),
+    "ta_logmel_workspace_floats": ([c_int, c_int, C.POINTER(c_ll)], c_int),
+    "ta_logmel_fwd": ([P, c_ll, c_int, c_int, P, P, P, P], c_int),
+    "ta_mel_to_conv1_im2col": ([P, c_int, c_int, P, P], c_int),
+    "ta_attn_fwd": ([P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_int, c_float, P], c_int),
+    "ta_attn_bwd": ([P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
+                     c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_int, c_float, P], c_int),
+    "ta_im2col_k3": ([P, P, c_int, c_int, c_int, c_int, P], c_int),
+    "ta_layernorm_bf16": ([P, P, P, P, c_ll, c_int, c_float, P], c_int),
+    "ta_rmsnorm_f32": ([P, P, P, P, c_ll, c_int, c_float, P], c_int),
+    "ta_rmsnorm_f32_bwd": ([P, P, P, P, P, c_ll, c_int, c_float, c_int, P], c_int),
+    "ta_enc_rope": ([P, P, P, c_ll, c_int, c_int, c_int, c_int, P], c_int),
+    "ta_lm_qknorm_rope_fwd": ([P, P, P, P, P, P, c_ll, c_int, c_int, c_int, c_float, P], c_int),
+    "ta_lm_qknorm_rope_bwd": ([P, P, P, P, P, P, P, P, P, c_ll, c_int, c_int, c_int, c_float, P], c_int),
+    "ta_proj_norm_fwd": ([P, P, P, c_ll, c_int, c_float, c_int, P], c_int),
+    "ta_proj_norm_bwd": ([P, P, P, c_int, P, P, c_ll, c_int, c_float, c_int, P], c_int),
+    "ta_audio_index": ([P, P, P, c_int, c_int, c_int, c_ll, P], c_int),
+    "ta_embed_scatter": ([P, P, P, P, P, c_ll, c_int, c_ll, P], c_int),
+    "ta_audio_grad_gather": ([P, P, P, c_ll, c_int, P], c_int),
+    "ta_ce_fwd_bwd": ([P, c_ll, P, c_ll, c_int, c_int, c_float, P, P, c_int, P], c_int),
+    "ta_transpose_bf16": ([P, P, c_int, c_int, c_ll, c_ll, P], c_int),
+    "ta_cast_f32_bf16": ([P, P, c_ll, P], c_int),
+    "ta_frame_stack": ([P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "ta_grad_sumsq": ([P, c_ll, P, P], c_int),
+    "ta_adamw_clip_step": ([P, P, P, P, c_ll, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P, P], c_int),
+    "ta_encoder_workspace_bytes": ([C.POINTER(EncoderWeights), c_int, c_int, C.POINTER(c_ll)], c_int),
+    "ta_encoder_forward": ([C.POINTER(EncoderWeights), P, c_int, c_int, P, c_ll, P, P], c_int),
+    "ta_mlp_projector_forward": ([C.POINTER(MlpProjectorWeights), P, c_ll, P, P, P, P, P], c_int),
+    "ta_mlp_projector_backward_workspace_bytes": ([C.POINTER(MlpProjectorWeights), c_ll, C.POINTER(c_ll)], c_int),
+    "ta_mlp_projector_backward": ([C.POINTER(MlpProjectorWeights), P, c_ll, P, P, P, P, P, c_ll, P, P, P, P, P], c_int),
+    "ta_lm_workspace_bytes": ([C.POINTER(LmWeights), c_int, c_int, c_int, c_int, C.POINTER(c_ll)], c_int),
+    "ta_lm_forward_backward": ([C.POINTER(LmWeights), C.POINTER(LmStepArgs), P], c_int),
+    "ta_lm_hidden_to_logits": ([C.POINTER(LmWeights), P, P, c_int, P, P, P], c_int),
+}
+
+EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["ta_last_error_string"])
+
+_lib = None
+
+
+class TinyAudioB200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built -- there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TinyAudioB200Error(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C tiny_audio_b200/csrc`).  tiny_audio_b200 has no CPU / PyTorch fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.ta_last_error_string.argtypes = []
+    lib.ta_last_error_string.restype = C.c_char_p
+    for name, (args, res) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().ta_last_error_string().decode("utf-8", "replace")
+        raise TinyAudioB200Error(f"libtinyaudio_b200 error {rc}: {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise TinyAudioB200Error("tiny_audio_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+# --------------------------------------------------------------------------------------------------
+# thin, typed convenience wrappers used by the host modules and the unit tests
+# --------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, *, epi: int = EPI_BF16, out: Optional[torch.Tensor] = None,
+         bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
+         aux: Optional[torch.Tensor] = None, alpha: float = 1.0, k: Optional[int] = None) -> torch.Tensor:
+    """out = epilogue(a @ b.T);  a [M,K] bf16, b [N,K] bf16 (both row-major, K contiguous)."""
+    lib = load()
+    require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.stride(-1) == 1 and b.stride(-1) == 1
+    M, K = a.shape[0], (k if k is not None else a.shape[1])
+    N = b.shape[0]
+    if out is None:
+        if epi == EPI_SWIGLU:
+            out = torch.empty(M, N // 2, device=a.device, dtype=torch.bfloat16)
+        elif epi == EPI_SWIGLU_BWD:
+            out = torch.empty(M, 2 * N, device=a.device, dtype=torch.bfloat16)
+        elif epi in (EPI_F32, EPI_F32_RESID):
+            out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+        else:
+            out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    e = GemmEpilogue(ptr(out), out.stride(0), ptr(bias), ptr(resid), resid.stride(0) if resid is not None else 0,
+                     ptr(out2), out2.stride(0) if out2 is not None else 0, ptr(aux),
+                     aux.stride(0) if aux is not None else 0, alpha)
+    check(lib.ta_gemm_bf16(ptr(a), a.stride(0), ptr(b), b.stride(0), M, N, K, epi, C.byref(e), stream_ptr()))
+    return out
+
+
+def pointer_table(tensors) -> "C.Array":
+    arr = (P * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
