@@ -21,6 +21,7 @@ extern "C" {
 
 const char* ta_last_error_string(void);
 int ta_version(void);
+unsigned long long ta_launch_count(void); /* kernels launched by the library so far (host-side counter) */
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM  C[M,N] = epilogue(A[M,K] . B[N,K]^T), bf16 in, fp32 accumulate (tcgen05 + TMEM + TMA)

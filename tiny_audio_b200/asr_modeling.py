@@ -1,0 +1,336 @@
+"""ASRModel -- drop-in for the reference's `tiny_audio/asr_modeling.py:47` on the training hot path.
+
+Same constructor seams, attribute names and call surface as the reference (so `scripts/train.py` drives it
+unchanged: SURVEY.md section 8b), but `forward` does not run the HF modules: the frozen GLM-ASR encoder, the
+projector, the frozen Qwen3 decoder, the CE loss and the whole backward into the projector parameters run as
+hand-written sm_100a kernels behind libtinyaudio_b200.so (tiny_audio_b200/engine.py).  The HF modules are kept
+only as the owners of the fp32 master weights (`audio_tower`, `language_model`) -- for `.to()`, `state_dict`
+naming, and weight loading -- and are never called on the hot path.
+
+No CPU fallback: a forward with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from transformers import PreTrainedModel
+from transformers.generation import GenerationMixin
+from transformers.modeling_outputs import CausalLMOutputWithPast
+
+from . import lib as L
+from .asr_config import ASRConfig, compute_encoder_output_length
+from .engine import HotPath, PathDims
+from .projectors import PROJECTOR_CLASSES
+
+_PROJ_KEYS = ("linear_1.weight", "norm.weight", "linear_2.weight", "norm_2.weight")
+
+
+def _gather_audio_embeds(audio_embeds: torch.Tensor, token_counts: torch.Tensor) -> torch.Tensor:
+    """Reference helper (asr_modeling.py:27-44) restated with plain indexing: first `token_counts[i]` rows of each
+    sample, zero rows when a count exceeds the available length.  The CUDA path implements the same index
+    semantics inside `ta_audio_index` / `ta_embed_scatter`; this function exists for API parity and tests."""
+    _, n, _ = audio_embeds.shape
+    need = int(token_counts.max()) if token_counts.numel() else 0
+    if need > n:
+        audio_embeds = torch.nn.functional.pad(audio_embeds, (0, 0, 0, need - n))
+        n = need
+    keep = torch.arange(n, device=audio_embeds.device)[None, :] < token_counts[:, None]
+    return audio_embeds[keep]
+
+
+class _FusedPathLoss(torch.autograd.Function):
+    """loss = CE(Qwen3(scatter(projector(encoder(audio))))) with d(loss)/d(projector params) computed in the
+    same pass; backward only rescales the stored gradients by the incoming scalar."""
+
+    @staticmethod
+    def forward(ctx, w1, n1, w2, n2, model, call):
+        hot: HotPath = model._hot_path()
+        params = {k: p.detach().float().contiguous() for k, p in zip(_PROJ_KEYS, (w1, n1, w2, n2))}
+        need = any(ctx.needs_input_grad[:4])
+        grads = {k: torch.empty_like(v) for k, v in params.items()} if need else None
+        loss, _ = hot.forward_backward(proj_params=params, grads=grads, **call)
+        ctx.grads = grads
+        ctx.dtypes = (w1.dtype, n1.dtype, w2.dtype, n2.dtype)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        if ctx.grads is None:
+            return (None,) * 6
+        outs = tuple((ctx.grads[k] * gout).to(dt) for k, dt in zip(_PROJ_KEYS, ctx.dtypes))
+        return outs + (None, None)
+
+
+class ASRModel(PreTrainedModel, GenerationMixin):
+    """Audio encoder (frozen) + projector (trainable) + causal LM (frozen): the reference's composition."""
+
+    config_class = ASRConfig
+    base_model_prefix = "model"
+    main_input_name = "input_features"
+    _supports_flash_attn_2 = True
+    supports_gradient_checkpointing = True
+    _is_loading_from_pretrained: bool = False
+
+    TRANSCRIBE_PROMPT = "Transcribe the speech to text"
+
+    # ------------------------------------------------------------------ construction (same seams as the reference)
+    def __init__(self, config: ASRConfig, **kwargs) -> None:
+        super().__init__(config)
+        self.system_prompt = config.system_prompt
+        dtype = getattr(torch, config.model_dtype)
+        self.audio_tower = self._load_audio_encoder(config, dtype)
+        self.language_model = self._load_language_model(config, dtype)
+        self._init_tokenizer(config)
+
+        gc = self.language_model.generation_config
+        self.generation_config = gc
+        for name in ("max_new_tokens", "min_new_tokens", "num_beams", "do_sample", "temperature", "top_p", "top_k",
+                     "use_cache", "length_penalty", "repetition_penalty", "no_repeat_ngram_size"):
+            setattr(gc, name, getattr(config, name))
+        eos = [self.tokenizer.convert_tokens_to_ids(t) for t in ("<|im_end|>", "<|endoftext|>")]
+        gc.eos_token_id = [t for t in eos if t is not None]
+        gc.pad_token_id = self.tokenizer.pad_token_id
+
+        self.feature_extractor = self._create_feature_extractor(config)
+        self.projector = self._create_projector(config, dtype)
+        if getattr(config, "use_lora", False) and not getattr(type(self), "_is_loading_from_pretrained", False):
+            self._setup_lora(config)
+        if getattr(config, "freeze_projector", False):
+            self.projector.requires_grad_(False)
+        self._no_split_modules = getattr(self.language_model, "_no_split_modules", [])
+        self._hot: Optional[HotPath] = None
+        self._hot_key = None
+
+    def _create_feature_extractor(self, config: ASRConfig):
+        from transformers import AutoFeatureExtractor
+        fe = AutoFeatureExtractor.from_pretrained(config.audio_model_id)
+        if "whisper" not in config.audio_model_id.lower():
+            fe.padding = False
+        return fe
+
+    @classmethod
+    def _load_audio_encoder(cls, config: ASRConfig, dtype: torch.dtype) -> nn.Module:
+        kw = dict(attn_implementation=config.attn_implementation, low_cpu_mem_usage=True, dtype=dtype)
+        name = config.audio_model_id.lower()
+        if "glm" in name:
+            from transformers import AutoModelForSeq2SeqLM
+            full = AutoModelForSeq2SeqLM.from_pretrained(config.audio_model_id, trust_remote_code=True, **kw)
+            enc = full.audio_tower
+            full.language_model = None
+            full.multi_modal_projector = None
+            del full
+        else:
+            raise NotImplementedError("tiny_audio_b200's hot path is built for the GLM-ASR encoder "
+                                      f"(audio_model_id={config.audio_model_id!r}); see DESIGN.md")
+        enc.requires_grad_(False)
+        enc.eval()
+        return enc
+
+    @classmethod
+    def _load_language_model(cls, config: ASRConfig, dtype: torch.dtype) -> PreTrainedModel:
+        from transformers import AutoModelForCausalLM
+        lm = AutoModelForCausalLM.from_pretrained(config.text_model_id, attn_implementation=config.attn_implementation,
+                                                  trust_remote_code=True, low_cpu_mem_usage=True, dtype=dtype)
+        lm.config.use_cache = getattr(config, "use_cache", True)
+        if getattr(config, "freeze_language_model", True):
+            lm.requires_grad_(False)
+            lm.train(False)
+        else:
+            raise NotImplementedError("freeze_language_model=False (full decoder fine-tuning) is a 'next' row "
+                                      "(SURVEY.md section 8f rank 3) and not built yet")
+        return lm
+
+    def _create_projector(self, config: ASRConfig, dtype: torch.dtype) -> nn.Module:
+        if config.encoder_dim is None:
+            ec = self.audio_tower.config
+            config.encoder_dim = getattr(ec, "hidden_size", None) or getattr(ec, "d_model", None)
+        if config.llm_dim is None:
+            dc = self.language_model.config
+            config.llm_dim = getattr(dc, "hidden_size", None) or getattr(dc, "d_model", None)
+        if config.encoder_dim is None or config.llm_dim is None:
+            raise ValueError("could not infer encoder_dim / llm_dim; set them in the config")
+        kind = getattr(config, "projector_type", "mlp")
+        if kind not in PROJECTOR_CLASSES:
+            raise ValueError(f"Unknown projector_type: {kind}. Valid options: {list(PROJECTOR_CLASSES.keys())}")
+        proj = PROJECTOR_CLASSES[kind](config)
+        device = next(self.language_model.parameters()).device
+        return proj.to(device=device, dtype=dtype)
+
+    def _setup_lora(self, config: ASRConfig):
+        raise NotImplementedError("use_lora=True (BASELINE config 5) is a 'next' row and not built in this round")
+
+    def _init_tokenizer(self, config: ASRConfig):
+        from transformers import AutoTokenizer
+        tok = AutoTokenizer.from_pretrained(config.text_model_id, trust_remote_code=True)
+        if tok.pad_token is None or tok.pad_token_id == tok.eos_token_id:
+            if "<|finetune_right_pad_id|>" in tok.get_vocab():
+                tok.pad_token = "<|finetune_right_pad_id|>"
+            elif tok.pad_token is None:
+                tok.pad_token = tok.eos_token
+        special = list(getattr(tok, "additional_special_tokens", None) or [])
+        if "<audio>" not in special:
+            tok.add_special_tokens({"additional_special_tokens": special + ["<audio>"]})
+            self.language_model.resize_token_embeddings(len(tok), mean_resizing=True)
+        tok.padding_side = "right"
+        self.tokenizer = tok
+        self.audio_token_id = tok.convert_tokens_to_ids("<audio>")
+        for cfg in (self.config.text_config, self.language_model.config, getattr(self, "generation_config", None)):
+            if cfg is not None:
+                cfg.pad_token_id, cfg.eos_token_id, cfg.bos_token_id = tok.pad_token_id, tok.eos_token_id, tok.bos_token_id
+
+    # ------------------------------------------------------------------ bookkeeping the Trainer relies on
+    def train(self, mode: bool = True):
+        super().train(mode)
+        self.audio_tower.train(False)
+        if getattr(self.config, "freeze_language_model", True):
+            self.language_model.train(False)
+        return self
+
+    def _set_gradient_checkpointing(self, enable: bool = True, gradient_checkpointing_func=None):
+        # activations of the decoder live in one preallocated workspace (engine.cu); there is nothing to checkpoint
+        return None
+
+    def get_input_embeddings(self):
+        return self.language_model.get_input_embeddings()
+
+    def set_input_embeddings(self, value):
+        self.language_model.set_input_embeddings(value)
+        self._hot = None
+
+    def get_output_embeddings(self):
+        return self.language_model.get_output_embeddings()
+
+    def set_output_embeddings(self, value):
+        self.language_model.set_output_embeddings(value)
+        self._hot = None
+
+    def get_processor(self):
+        from .asr_processing import ASRProcessor
+        return ASRProcessor(feature_extractor=self.feature_extractor, tokenizer=self.tokenizer, projector=self.projector,
+                            encoder_conv_layers=self.config.encoder_conv_layers)
+
+    def state_dict(self, *args, **kwargs):
+        """Trainable weights only (projector), reference key names (`projector.linear_1.weight`, ...)."""
+        return {f"projector.{k}": v for k, v in self.projector.state_dict().items()}
+
+    def _compute_encoder_output_lengths(self, audio_attention_mask: torch.Tensor) -> torch.Tensor:
+        return compute_encoder_output_length(audio_attention_mask.sum(dim=-1), self.config.encoder_conv_layers)
+
+    def _get_num_audio_tokens(self, audio_attention_mask: torch.Tensor) -> int:
+        n = int(self._compute_encoder_output_lengths(audio_attention_mask).max().item())
+        return int(self.projector.get_output_length(n))
+
+    # ------------------------------------------------------------------ the B200 hot path
+    def path_dims(self) -> PathDims:
+        ec, tc = self.audio_tower.config, self.language_model.config
+        rope_e = getattr(ec, "rope_parameters", None) or {}
+        rope_t = getattr(tc, "rope_parameters", None) or {}
+        emb = self.language_model.get_input_embeddings().weight
+        hidden = getattr(self.config, "projector_hidden_dim", None) or tc.hidden_size
+        return PathDims(
+            n_mels=ec.num_mel_bins, enc_dim=ec.hidden_size, enc_ffn=ec.intermediate_size, enc_layers=ec.num_hidden_layers,
+            enc_heads=ec.num_attention_heads, enc_rope_theta=float(rope_e.get("rope_theta", 10000.0)),
+            enc_partial_rotary=float(rope_e.get("partial_rotary_factor", getattr(ec, "partial_rotary_factor", 0.5))),
+            enc_max_pos=max(int(getattr(ec, "max_position_embeddings", 1500)), 1500),
+            proj_k=self.config.projector_pool_stride, proj_hidden=hidden,
+            lm_dim=tc.hidden_size, lm_ffn=tc.intermediate_size, lm_layers=tc.num_hidden_layers,
+            lm_heads=tc.num_attention_heads, lm_kv_heads=tc.num_key_value_heads,
+            lm_head_dim=getattr(tc, "head_dim", None) or tc.hidden_size // tc.num_attention_heads,
+            lm_rope_theta=float(rope_t.get("rope_theta", getattr(tc, "rope_theta", 1e6))), lm_eps=tc.rms_norm_eps,
+            vocab=emb.shape[0], audio_token_id=int(self.audio_token_id))
+
+    def _hot_path(self) -> HotPath:
+        dev = next(self.projector.parameters()).device
+        if dev.type != "cuda":
+            raise L.TinyAudioB200Error("ASRModel.forward needs the model on a CUDA device (no CPU fallback)")
+        key = (dev.index, self.language_model.get_input_embeddings().weight.data_ptr())
+        if self._hot is None or self._hot_key != key:
+            with torch.no_grad():
+                self._hot = HotPath(self.path_dims(), self.audio_tower.state_dict(), self.language_model.state_dict(), dev)
+            self._hot_key = key
+        return self._hot
+
+    def _encode_audio(self, audio_features: torch.Tensor, expected_token_counts: torch.Tensor) -> torch.Tensor:
+        """Reference signature (asr_modeling.py:434-456): packed audio embeddings (sum(counts), llm_dim)."""
+        hot = self._hot_path()
+        B = audio_features.shape[0]
+        if audio_features.dim() == 2:
+            im2, _, T = hot.logmel(audio_features.float().contiguous())
+        else:
+            im2, T = hot.mel_to_im2col(audio_features)
+        enc = hot.encode(im2, B, T).clone()
+        enc = self._maybe_drop_audio_tokens(enc)
+        audio = self.projector(enc)
+        return _gather_audio_embeds(audio, expected_token_counts.to(device=audio.device, dtype=torch.long))
+
+    def _maybe_drop_audio_tokens(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        p = float(getattr(self.config, "audio_token_dropout", 0.0))
+        if not self.training or p <= 0.0:
+            return hidden_states
+        keep = torch.bernoulli(torch.full(hidden_states.shape[:-1], 1.0 - p, device=hidden_states.device,
+                                          dtype=hidden_states.dtype)).unsqueeze(-1)
+        return hidden_states * keep
+
+    def forward(self, input_ids: Optional[torch.Tensor] = None, input_features: Optional[torch.Tensor] = None,
+                audio_attention_mask: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None, past_key_values=None, inputs_embeds: Optional[torch.Tensor] = None,
+                labels: Optional[torch.Tensor] = None, use_cache: Optional[bool] = None,
+                cache_position: Optional[torch.Tensor] = None, audio_token_counts: Optional[torch.Tensor] = None,
+                **kwargs) -> CausalLMOutputWithPast:
+        """Training / scoring forward.  `input_features` is either the reference's (B, n_mels, T) log-mel tensor or,
+        on the fast path, the zero-padded 16 kHz waveform (B, L) -- the log-mel then runs on the GPU (ta_logmel_fwd).
+        `labels` may live on the host (no device->host sync) or on the device (one sync to build the row list)."""
+        if input_ids is None or input_features is None:
+            raise NotImplementedError("the B200 hot path covers audio+text batches (input_ids and input_features); "
+                                      "text-only / cached decoding is a 'next' row (DESIGN.md)")
+        if past_key_values is not None or inputs_embeds is not None:
+            raise NotImplementedError("past_key_values / inputs_embeds are not supported on the training hot path")
+        hot = self._hot_path()
+        dev = hot.device
+        feats = input_features.to(dev, non_blocking=True)
+        call = dict(input_ids=input_ids.to(dev, non_blocking=True),
+                    labels_cpu=(labels.cpu() if labels is not None else None),
+                    audio_token_counts=(audio_token_counts.to(dev, non_blocking=True) if audio_token_counts is not None else None))
+        if feats.dim() == 2:
+            call["waveform"] = feats.float().contiguous()
+        else:
+            call["input_features"] = feats
+        nib = kwargs.get("num_items_in_batch")
+        if nib is not None:
+            call["num_items_in_batch"] = float(nib)
+        p = float(getattr(self.config, "audio_token_dropout", 0.0))
+        if self.training and p > 0.0:
+            call["frame_keep_prob"] = 1.0 - p
+        pr = self.projector
+        loss = _FusedPathLoss.apply(pr.linear_1.weight, pr.norm.weight, pr.linear_2.weight, pr.norm_2.weight, self, call)
+        if labels is None:
+            loss = None
+        return CausalLMOutputWithPast(loss=loss, logits=None)
+
+    # ------------------------------------------------------------------ persistence (projector-only, reference layout)
+    def save_pretrained(self, save_directory, **kwargs):
+        from safetensors.torch import save_file
+        out = Path(save_directory)
+        out.mkdir(parents=True, exist_ok=True)
+        self.config.save_pretrained(out)
+        save_file({k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}, str(out / "model.safetensors"))
+        for obj in (getattr(self, "tokenizer", None), getattr(self, "feature_extractor", None)):
+            if obj is not None and hasattr(obj, "save_pretrained"):
+                obj.save_pretrained(out)
+        (out / "tiny_audio_b200.json").write_text(json.dumps({"format": "projector-only", "keys": list(self.state_dict())}))
+
+    def load_projector(self, path: str):
+        from safetensors.torch import load_file
+        sd = load_file(str(Path(path) / "model.safetensors"))
+        self.projector.load_state_dict({k[len("projector."):]: v for k, v in sd.items() if k.startswith("projector.")})
+
+
+try:
+    import transformers
+    transformers.AutoModel.register(ASRConfig, ASRModel, exist_ok=True)
+except Exception:   # registration is a convenience, never a requirement of the hot path
+    pass

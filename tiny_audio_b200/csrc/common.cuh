@@ -30,7 +30,12 @@ void ta_set_error(const char* fmt, ...);
             return -1;                                                                       \
         }                                                                                    \
     } while (0)
-#define TA_LAUNCH_CHECK() TA_CHECK_CUDA(cudaGetLastError())
+extern unsigned long long g_ta_launches;   // kernels launched by this library (bench.py reports it as gpu_launches)
+#define TA_LAUNCH_CHECK()                          \
+    do {                                           \
+        ++g_ta_launches;                           \
+        TA_CHECK_CUDA(cudaGetLastError());         \
+    } while (0)
 
 typedef __nv_bfloat16 bf16;
 

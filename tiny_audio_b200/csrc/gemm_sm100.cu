@@ -29,6 +29,8 @@ void ta_set_error(const char* fmt, ...) {
 }
 TA_API const char* ta_last_error_string(void) { return g_err; }
 TA_API int ta_version(void) { return 100; }
+unsigned long long g_ta_launches = 0;
+TA_API unsigned long long ta_launch_count(void) { return g_ta_launches; }
 
 namespace {
 
@@ -438,7 +440,6 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
     TA_REQUIRE(A && B && e && e->out, "ta_gemm_bf16: null pointer");
     TA_REQUIRE(M > 0 && N > 0 && K > 0, "ta_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
     TA_REQUIRE(N % 128 == 0, "ta_gemm_bf16: N=%d must be a multiple of 128", N);
-    TA_REQUIRE(K % 8 == 0, "ta_gemm_bf16: K=%d must be a multiple of 8", K);
     if (epi == TA_EPI_BF16_RESID || epi == TA_EPI_F32_RESID) TA_REQUIRE(e->resid, "residual epilogue needs resid");
     if (epi == TA_EPI_SWIGLU_BWD) TA_REQUIRE(e->aux && N % 64 == 0, "swiglu-bwd epilogue needs aux stash");
     int bn = g_force_bn ? g_force_bn : ((N % 256 == 0) ? 256 : 128);

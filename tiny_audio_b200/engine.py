@@ -343,7 +343,8 @@ class HotPath:
     def forward_backward(self, *, input_ids: torch.Tensor, labels_cpu: Optional[torch.Tensor], proj_params,
                          waveform: Optional[torch.Tensor] = None, input_features: Optional[torch.Tensor] = None,
                          audio_token_counts: Optional[torch.Tensor] = None, num_items_in_batch: Optional[float] = None,
-                         grads: Optional[Dict[str, torch.Tensor]] = None, return_parts: bool = False):
+                         grads: Optional[Dict[str, torch.Tensor]] = None, return_parts: bool = False,
+                         frame_keep_prob: Optional[float] = None):
         """Returns (loss [1] fp32 device tensor, parts).  When `grads` is given (fp32 tensors shaped like the projector
         params) the backward runs and fills them with d(loss)/d(param)."""
         d = self.dims
@@ -356,6 +357,11 @@ class HotPath:
         else:
             im2, T = self.mel_to_im2col(input_features)
         enc = self.encode(im2, B, T)
+        if frame_keep_prob is not None and frame_keep_prob < 1.0:
+            # audio_token_dropout (asr_modeling.py:458-479): whole-frame Bernoulli zero mask, no rescale.  The mask is
+            # drawn with torch's generator exactly as the reference does; parity runs use p = 0.
+            keep = torch.bernoulli(torch.full(enc.shape[:-1], float(frame_keep_prob), device=self.device, dtype=F32))
+            enc.mul_(keep.unsqueeze(-1).to(enc.dtype))
         xs, n_a = self.frame_stack(enc)
         with_bwd = grads is not None
         audio, stash = self.projector_forward(xs, proj_params, with_bwd)

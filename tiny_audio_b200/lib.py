@@ -57,6 +57,7 @@ class LmStepArgs(C.Structure):
 
 _SIGS = {
     "ta_version": ([], c_int),
+    "ta_launch_count": ([], C.c_ulonglong),
     "ta_gemm_bf16": ([P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, C.POINTER(GemmEpilogue), P], c_int),
     "ta_gemm_set_tile_n": ([c_int], c_int),
     "ta_logmel_workspace_floats": ([c_int, c_int, C.POINTER(c_ll)], c_int),
