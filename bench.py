@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- train audio-seconds/sec of the tiny-audio hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm   (torchrun for N > 1, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the oracle port of the reference's own
+                                                           PyTorch fp32 path on the box's host cores (rank 0 only)
+
+One "step" = one full train step on one batch of synthetic 16 kHz clips:
+  log-mel -> GLM-ASR encoder (32 L) -> MLP projector -> <audio> scatter -> Qwen3-0.6B (28 L) -> CE
+  -> backward to the projector -> [NCCL all-reduce of the flat projector gradient] -> clip(1.0) + AdamW.
+Full-size architecture, random-initialised weights (no checkpoints offline), bf16 tensor-core GEMMs with fp32
+accumulation = the reference's production recipe (fp32 masters + bf16 autocast).
+
+`value`  : device-resident inputs, HotPath driver.            `e2e`: public API (ASRModel(**batch) -> loss.backward()
+-> optimizer.step()) with pinned HOST buffers, H2D of the waveform / ids and D2H of the loss inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train_audio_seconds_per_second"
+UNIT = "audio-s/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU (weak scaling)")
+    ap.add_argument("--clip-seconds", type=float, default=30.0)
+    ap.add_argument("--response-len", type=int, default=64)
+    ap.add_argument("--proj-hidden", type=int, default=2048, help="projector hidden dim (2048 = the ~12 M variant)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's PyTorch fp32 path on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference(args, steps: int, warmup: int, batch: int):
+    from oracle import path_oracle as po   # the one place bench.py executes oracle/ : as the timed CPU baseline
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = po.PathConfig(proj_hidden=args.proj_hidden)
+    W = po.init_weights(cfg, seed=1)
+    b = po.synthetic_batch(cfg, batch, args.clip_seconds, seed=0, response_len=args.response_len)
+    n_items = int((b["labels"] != -100).sum())
+    state = None
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = po.train_step(W, b, cfg, lr=1e-3, max_grad_norm=1.0, state=state, num_items_in_batch=n_items)
+        state = res["state"]
+        W["projector"] = res["params"]
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1000.0 * sum(times) / len(times)
+    return {"value": batch * args.clip_seconds / (ms / 1000.0), "ms_per_step": ms, "cores": torch.get_num_threads(),
+            "sample": f"B={batch} x {args.clip_seconds:g}s clip(s), full-size model, fp32, {steps} step(s) after {warmup} warm-up",
+            "loss": float(res["loss"])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(args, max(1, args.steps), max(0, min(args.warmup, 1)), args.cpu_sample_batch)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    return {"workload": f"tiny-audio train step: MLP projector (hidden {args.proj_hidden}), GLM-ASR encoder 32L + Qwen3-0.6B 28L, "
+                        f"batch {args.batch}/GPU x {args.clip_seconds:g} s 16 kHz clips, response {args.response_len} tokens",
+            "global_batch": args.batch * n_gpus, "clip_seconds": args.clip_seconds, "parallelism": f"dp{n_gpus}",
+            "padding": "longest (equal-length clips)", "audio_token_dropout": 0.0, "grad_accum": 1,
+            "l2_policy": "per-step inputs+activations (>1 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from tiny_audio_b200 import lib as L
+    from tiny_audio_b200.engine import PathDims
+    from tiny_audio_b200.optim import ClipAdamW
+    from tiny_audio_b200.synthetic import build_offline_model, synthetic_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+
+    dims = PathDims(proj_hidden=args.proj_hidden)
+    model = build_offline_model(dims, device=dev, seed=1234)
+    model.train()
+    hot = model._hot_path()
+    # the HF modules only own the fp32 master copies; free them (the packed bf16 copies in `hot` are what runs)
+    names = [n for n, _ in model.projector.named_parameters()]
+    params = [p for _, p in model.projector.named_parameters()]
+    opt = ClipAdamW(params, lr=1e-3, max_grad_norm=1.0)
+
+    B = args.batch
+    host = synthetic_batch(dims, B, args.clip_seconds, seed=100 + rank, response_len=args.response_len, pin=True)
+    n_lab_local = int((host["labels"] != -100).sum())
+    n_items_global = n_lab_local * world            # equal-length synthetic batches: arithmetic, no collective needed
+    d_wave = host["input_features"].to(dev)
+    d_ids = host["input_ids"].to(dev)
+    d_cnt = host["audio_token_counts"].to(dev)
+    labels_cpu = host["labels"]
+    pmap = {n: p.data for n, p in zip(names, params)}
+    gmap = {n: p.grad for n, p in zip(names, params)}
+
+    def step_resident():
+        loss, _ = hot.forward_backward(input_ids=d_ids, labels_cpu=labels_cpu, proj_params=pmap, waveform=d_wave,
+                                       audio_token_counts=d_cnt, num_items_in_batch=n_items_global, grads=gmap)
+        opt.step()
+        return loss
+
+    def step_e2e():
+        opt.zero_grad()
+        out = model(input_ids=host["input_ids"], input_features=host["input_features"], labels=host["labels"],
+                    attention_mask=host["attention_mask"], audio_token_counts=host["audio_token_counts"],
+                    num_items_in_batch=n_items_global)
+        out.loss.backward()
+        opt.step()
+        return float(out.loss)          # device -> host read of the step's loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            last = fn()
+        barrier()
+        if sampler:
+            sampler.start()
+        c0 = lib.ta_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            last = fn()
+        e1.record()
+        barrier()
+        c1 = lib.ta_launch_count()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t) / steps, (c1 - c0) // max(steps, 1), clocks, last
+
+    W = max(args.warmup, 3)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_step, launches, clocks, last_loss = timed(step_resident, args.steps, W, sampler)
+    audio_s = B * world * args.clip_seconds
+    value = audio_s / (ms_step / 1000.0)
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e2e, _, _, _ = timed(step_e2e, args.steps, 2)
+        h2d = sum(host[k].numel() * host[k].element_size() for k in ("input_features", "input_ids", "audio_token_counts"))
+        e2e = {"value": audio_s / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4}
+
+    # ---- roofline of the dominant kernel: the tcgen05 GEMM, timed alone on its largest shape of the step ----
+    roof = None
+    if rank == 0:
+        pk, how = peaks()
+        S_e = int(args.clip_seconds * 16000) // 160 // 2
+        M, N, K = B * S_e, dims.enc_ffn, dims.enc_dim          # encoder fc1 (+bias+GELU): 32 launches / step
+        a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.03
+        bias = torch.zeros(N, device=dev, dtype=torch.float32)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            L.gemm(a, w, epi=L.EPI_BF16_GELU, bias=bias, out=out)
+        torch.cuda.synchronize()
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            L.gemm(a, w, epi=L.EPI_BF16_GELU, bias=bias, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / reps / 1000.0
+        ach = 2.0 * M * N * K / t / 1e12
+        peak = pk["bf16_tflops"]
+        roof = {"bound": "tensor", "kernel": f"gemm_kernel<256,BF16_GELU> M={M} N={N} K={K} (encoder fc1)", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": f"{how} burst (kernel timed alone)",
+                "traffic": None, "step_tflops": 116.0e9 * audio_s / (ms_step / 1000.0) / 1e12 / world,
+                "step_frac_of_sustained": 116.0e9 * audio_s / (ms_step / 1000.0) / 1e12 / world / pk["bf16_tflops_sustained"]}
+        del a, w, out
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del model
+        r = cpu_reference(args, 1, 1, args.cpu_sample_batch)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "loss": float(last_loss)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,127 @@
+"""Host-side logic of the drop-in surface + the C-ABI export check (no GPU compute).  The integer cases restate the
+reference's own unit tests (file:line given per test)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from tiny_audio_b200 import lib as L
+    handle = L.load()
+    header = open(os.path.join(ROOT, "include", "tinyaudio_b200.h")).read()
+    declared = set(re.findall(r"\b(ta_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    for sym in sorted(declared):
+        assert hasattr(handle, sym), f"{sym} declared in include/tinyaudio_b200.h but not exported"
+    assert set(L.EXPORTED_SYMBOLS) <= declared | {"ta_last_error_string"}
+    assert handle.ta_version() >= 100
+    assert isinstance(handle.ta_last_error_string(), bytes)
+
+
+def test_no_cpu_fallback():
+    from tiny_audio_b200 import lib as L
+    from tiny_audio_b200.projectors import MLPAudioProjector
+
+    class Cfg:
+        encoder_dim, llm_dim, projector_pool_stride, projector_hidden_dim = 256, 512, 4, None
+    with pytest.raises(L.TinyAudioB200Error):
+        MLPAudioProjector(Cfg())(torch.randn(2, 100, 256))
+    a = torch.zeros(128, 64, dtype=torch.bfloat16)
+    with pytest.raises(L.TinyAudioB200Error):
+        L.gemm(a, a)
+
+
+def test_conv_length_formula():
+    # reference tests/test_asr_processing.py:29-45, tests/test_asr_config.py:150-175
+    from tiny_audio_b200.asr_config import compute_encoder_output_length as f
+    assert f(100) == 50 and f(1) == 1 and f(3000) == 1500
+    assert torch.equal(f(torch.tensor([3000, 1500])), torch.tensor([1500, 750]))
+    assert f(100, [(1, 3, 1)]) == 100
+
+
+def test_projector_contract():
+    # reference tests/test_projectors.py:58-77, 225-238
+    from tiny_audio_b200.projectors import PROJECTOR_CLASSES, MLPAudioProjector
+
+    class Cfg:
+        encoder_dim, llm_dim, projector_pool_stride, projector_hidden_dim = 256, 512, 4, None
+    p = MLPAudioProjector(Cfg())
+    assert set(PROJECTOR_CLASSES) == {"mlp", "mosa", "moe", "qformer"}
+    assert p.get_output_length(100) == 25 and p.get_output_length(1500) == 375 and p.get_output_length(50) == 12
+    assert torch.equal(p.get_output_length(torch.tensor([100, 50])), torch.tensor([25, 12]))
+    assert [k for k, _ in p.named_parameters()] == ["linear_1.weight", "norm.weight", "linear_2.weight", "norm_2.weight"]
+    assert p.linear_1.weight.shape == (512, 1024) and p.linear_2.weight.shape == (512, 512)
+    with pytest.raises(NotImplementedError):
+        PROJECTOR_CLASSES["qformer"](Cfg())
+
+
+def test_gather_audio_embeds_semantics():
+    # reference tests/test_encode_audio_gather.py:27-58: == per-sample slice + cat, zero rows when count > len
+    from tiny_audio_b200.asr_modeling import _gather_audio_embeds
+    x = torch.randn(3, 5, 4)
+    counts = torch.tensor([5, 0, 7])
+    out = _gather_audio_embeds(x, counts)
+    exp = torch.cat([x[0, :5], x[2, :5], torch.zeros(2, 4)])
+    assert torch.equal(out, exp)
+
+
+def test_waveform_feature_extractor_mask_arithmetic():
+    # HF:models/whisper/feature_extraction_whisper.py:328-337 ; reference tests/test_asr_processing.py:212-233
+    from transformers import WhisperFeatureExtractor as HFExtractor
+    from tiny_audio_b200.asr_processing import WhisperFeatureExtractor
+    rng = np.random.default_rng(0)
+    clips = [rng.standard_normal(n).astype(np.float32) for n in (16000, 12345, 8000)]
+    ours = WhisperFeatureExtractor()
+    ref = HFExtractor(feature_size=128)
+    for pad in ("longest", "max_length"):
+        a = ours(clips, sampling_rate=16000, padding=pad, return_attention_mask=True, return_tensors="pt")
+        b = ref(clips, sampling_rate=16000, padding=pad, return_attention_mask=True, return_tensors="pt")
+        assert torch.equal(a["attention_mask"].long(), b["attention_mask"].long())
+        assert a["input_features"].shape[1] // 160 == b["input_features"].shape[2]
+    assert type(ours).__name__ == "WhisperFeatureExtractor"     # scripts/train.py:260-264 keys the padding mode on it
+
+
+def test_label_rows_shift():
+    from tiny_audio_b200.engine import label_rows_and_targets
+    labels = torch.tensor([[-100, -100, 5, 6, -100], [-100, 7, -100, -100, 8]])
+    rows, tg = label_rows_and_targets(labels)
+    assert rows.tolist() == [1, 2, 5, 8] and tg.tolist() == [5, 6, 7, 8]
+
+
+def test_asr_config_defaults_and_model_surface():
+    from transformers import GlmAsrEncoderConfig, Qwen3Config
+    from tiny_audio_b200.asr_config import ASRConfig
+    c = ASRConfig(audio_config=GlmAsrEncoderConfig(), text_config=Qwen3Config(hidden_size=1024))
+    assert c.projector_type == "mlp" and c.projector_pool_stride == 4 and c.num_beams == 1 and c.max_new_tokens == 128
+    assert c.use_cache is True and c.lora_rank == 8 and c.lora_alpha == 32 and c.freeze_language_model is True
+    assert c.encoder_conv_layers == [(1, 3, 1), (1, 3, 2)] and len(c.lora_target_modules) == 7
+    assert c.model_type == "asr_model" and c.auto_map["AutoModel"] == "asr_modeling.ASRModel"
+
+    from tiny_audio_b200.engine import PathDims
+    from tiny_audio_b200.synthetic import build_offline_model, synthetic_batch
+    d = PathDims(enc_layers=1, lm_layers=1, vocab=5003, audio_token_id=5002)
+    m = build_offline_model(d, device="cpu")
+    assert list(m.state_dict()) == ["projector.linear_1.weight", "projector.norm.weight", "projector.linear_2.weight",
+                                    "projector.norm_2.weight"]                      # reference tests/test_asr_modeling.py:96-117
+    assert [n for n, p in m.named_parameters() if p.requires_grad] == list(m.state_dict())
+    m.train()
+    assert not m.audio_tower.training and not m.language_model.training and m.projector.training   # asr_modeling.py:344-357
+    assert m.main_input_name == "input_features" and m.base_model_prefix == "model"
+    b = synthetic_batch(d, 2, 1.0)
+    assert int((b["input_ids"] == d.audio_token_id).sum(-1)[0]) == 12 == int(b["audio_token_counts"][0])
+    p = m.get_processor()
+    assert p.audio_token_id == 5002
+
+
+def test_tiny_audio_import_shim():
+    import tiny_audio.asr_config as a
+    import tiny_audio.asr_modeling as b
+    import tiny_audio.projectors as c
+    import tiny_audio_b200.asr_modeling as real
+    assert b.ASRModel is real.ASRModel and hasattr(a, "ASRConfig") and "mlp" in c.PROJECTOR_CLASSES

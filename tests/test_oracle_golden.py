@@ -1,0 +1,80 @@
+"""The oracle against the fixtures generated from the UNMODIFIED reference (oracle/make_golden.py): this is what
+pins the oracle.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import path_oracle as po
+from oracle.make_golden import CASES, sub
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load_case(name):
+    spec, B, clip_s, pad_s, R, seed = CASES[name]
+    cfg = po.FULL if spec == "full" else po.small_config(**spec)
+    fx = np.load(os.path.join(GOLD, name + ".npz"))
+    W = po.init_weights(cfg, seed=seed)
+    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s)
+    batch["input_ids"] = torch.from_numpy(fx["input_ids"])
+    batch["labels"] = torch.from_numpy(fx["labels"])
+    batch["attention_mask"] = torch.from_numpy(fx["attention_mask"])
+    return cfg, fx, W, batch
+
+
+@pytest.mark.parametrize("name", ["small_b2_2s", "small_b3_ragged", "h2048_b2_2s", "small_b2_1s_pad30"])
+def test_oracle_matches_reference_fixture(name):
+    torch.set_num_threads(os.cpu_count())
+    cfg, fx, W, batch = load_case(name)
+    n_items = int(fx["num_items"])
+    # log-mel + frame mask (a1)
+    mel = po.log_mel(batch["waveform"], cfg)
+    assert tuple(mel.shape) == tuple(fx["mel_shape"])
+    assert np.abs(sub(mel, 8192) - fx["mel_sub"]).max() < 1e-5
+    L = int(batch["sample_lengths"][0])
+    mask = po.mel_attention_mask(batch["sample_lengths"], batch["waveform"].shape[1])
+    assert np.array_equal(mask.numpy(), fx["mel_mask"])
+    assert int(mask[0].sum()) == L // 160
+    # token-count arithmetic (a2) -- integers, exact
+    n_a = po.projector_output_length(po.encoder_output_length(L // 160), cfg.proj_k)
+    assert np.array_equal(fx["audio_token_counts"], np.full(len(fx["audio_token_counts"]), n_a))
+    # forward pieces + loss + grads + optimiser (a3-a12)
+    res = po.train_step(W, batch, cfg, lr=1e-3, max_grad_norm=1.0, num_items_in_batch=n_items)
+    loss_mean, logits, parts = po.model_forward(W, batch, cfg, None, return_parts=True)
+    assert tuple(parts["encoder_out"].shape) == tuple(fx["enc_shape"])
+    assert np.abs(sub(parts["encoder_out"], 8192) - fx["enc_sub"]).max() < 2e-4
+    assert np.abs(sub(parts["projector_out"], 8192) - fx["proj_sub"]).max() < 2e-4
+    assert abs(float(res["loss"]) - float(fx["loss"])) < 2e-5
+    assert abs(float(loss_mean) - float(fx["loss_mean_path"])) < 2e-5
+    lab_pos = torch.nn.functional.pad(batch["labels"], (0, 1), value=-100)[:, 1:] != -100
+    assert np.abs(sub(logits[lab_pos], 8192) - fx["logits_lab_sub"]).max() < 2e-4
+    # greedy ids: identical wherever the reference's top-1 margin exceeds fp32 noise
+    top2 = logits.topk(2, -1).values
+    sure = (top2[..., 0] - top2[..., 1]) > 1e-4
+    assert np.array_equal(logits.argmax(-1)[sure].numpy(), fx["logits_argmax"][sure.numpy()])
+    for k, g in res["grads"].items():
+        ref = fx["grad_sub." + k]
+        assert np.abs(sub(g) - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7
+        # torch's fp32 CPU .norm() of a 5M-element tensor carries ~4e-4 relative error (the oracle sums in fp32 pairwise)
+        assert abs(float(g.norm()) - float(fx["grad_l2." + k])) < 1e-3 * float(fx["grad_l2." + k])
+        assert np.abs(sub(res["params"][k]) - fx["new_param_sub." + k]).max() < 2e-5
+    assert abs(float(res["grad_norm"]) - float(fx["grad_norm"])) < 1e-3 * float(fx["grad_norm"])
+
+
+def test_oracle_full_size_fixture():
+    """Full-depth (32 + 28 layers) model, 1 x 4 s clip: loss and logits against the reference."""
+    torch.set_num_threads(os.cpu_count())
+    cfg, fx, W, batch = load_case("full_b1_4s")
+    loss, logits = po.model_forward(W, batch, cfg, int(fx["num_items"]))
+    assert abs(float(loss) - float(fx["loss"])) < 5e-5
+    lab_pos = torch.nn.functional.pad(batch["labels"], (0, 1), value=-100)[:, 1:] != -100
+    assert np.abs(sub(logits[lab_pos], 8192) - fx["logits_lab_sub"]).max() < 5e-4
+
+
+def test_mel_filter_bank_matches_hf():
+    from transformers.audio_utils import mel_filter_bank
+    ref = mel_filter_bank(201, 128, 0.0, 8000.0, 16000, norm="slaney", mel_scale="slaney")
+    assert np.abs(po.mel_filter_bank() - ref).max() < 1e-12
+    assert (np.abs(ref) > 0).sum(0).max() <= 16      # the CUDA kernel's per-filter tap budget (logmel.cu MAXW)

@@ -1,0 +1,80 @@
+"""torch.optim-compatible front for the fused clip + AdamW kernels, with the data-parallel gradient all-reduce.
+
+Replaces, on the hot path, HF Trainer's `clip_grad_norm_(1.0)` + `torch.optim.AdamW(fused=True)`
+(configs/training/production.yaml:5-9) and the DDP bucket all-reduce accelerate would add under torchrun
+(the reference itself has no distributed code).  All trainable parameters' gradients live in ONE
+flat fp32 buffer (`param.grad` are views of it), so a step is:
+
+    [NCCL all_reduce(flat_grad, SUM)]  ->  ta_grad_sumsq  ->  ta_adamw_clip_step        (no host sync)
+
+The loss is normalised by the GLOBAL number of label tokens (num_items_in_batch), so SUM over ranks yields the
+gradient of the global token-mean CE -- the same quantity HF Trainer produces with
+average_tokens_across_devices (HF:trainer.py:2141-2143, 2013-2018).
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+
+from . import lib as L
+
+
+class ClipAdamW(torch.optim.Optimizer):
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, max_grad_norm: float = 1.0, process_group=None):
+        params = [p for p in params if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.lib = L.load()
+        self.max_grad_norm = max_grad_norm
+        self.process_group = process_group
+        self._params = params
+        for p in params:
+            L.require_cuda(p)
+            assert p.dtype == torch.float32 and p.is_contiguous(), "ClipAdamW needs contiguous fp32 parameters"
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.step_count = 0
+        off = 0
+        self._slices = []
+        for p in params:
+            k = p.numel()
+            p.grad = self.flat_grad[off: off + k].view_as(p)      # autograd accumulates in place into the flat buffer
+            self._slices.append((off, k))
+            off += k
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.flat_grad.zero_()
+        for p, (off, k) in zip(self._params, self._slices):
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                p.grad = self.flat_grad[off: off + k].view_as(p)
+
+    def grad_norm(self) -> torch.Tensor:
+        return self.gnorm_sq.sqrt()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for p, (off, k) in zip(self._params, self._slices):       # a fresh .grad tensor (not our view) is folded in
+            if p.grad is not None and p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                self.flat_grad[off: off + k].copy_(p.grad.reshape(-1))
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and \
+                torch.distributed.get_world_size(self.process_group) > 1:
+            torch.distributed.all_reduce(self.flat_grad, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
+        st = L.stream_ptr()
+        self.step_count += 1
+        self.gnorm_sq.zero_()
+        L.check(self.lib.ta_grad_sumsq(L.ptr(self.flat_grad), self.flat_grad.numel(), L.ptr(self.gnorm_sq), st))
+        g = self.param_groups[0]
+        for group in self.param_groups:
+            for p in group["params"]:
+                i = next(j for j, q in enumerate(self._params) if q is p)
+                off, k = self._slices[i]
+                L.check(self.lib.ta_adamw_clip_step(
+                    L.ptr(p), L.ptr(self.flat_grad[off: off + k]), L.ptr(self.m[off: off + k]), L.ptr(self.v[off: off + k]), k,
+                    group["lr"], group["betas"][0], group["betas"][1], group["eps"], group["weight_decay"], self.step_count,
+                    self.max_grad_norm, L.ptr(self.gnorm_sq), st))
+        return None
