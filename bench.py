@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--cpu-threads", type=int, default=32)
     return ap.parse_args()
 
 
@@ -108,7 +109,9 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 def cpu_reference(args, steps: int, warmup: int, batch: int):
     from oracle import path_oracle as po   # the one place bench.py executes oracle/ : as the timed CPU baseline
-    torch.set_num_threads(os.cpu_count() or 1)
+    # intra-op threads: all cores up to 32 -- beyond that torch's CPU kernels get SLOWER on this workload (measured:
+    # 128 threads -> 0.10 audio-s/s vs 8 threads -> 3.3 audio-s/s for the same step)
+    torch.set_num_threads(min(os.cpu_count() or 1, args.cpu_threads))
     cfg = po.PathConfig(proj_hidden=args.proj_hidden)
     W = po.init_weights(cfg, seed=1)
     b = po.synthetic_batch(cfg, batch, args.clip_seconds, seed=0, response_len=args.response_len)

@@ -54,6 +54,7 @@ typedef struct ta_gemm_epilogue {
 int ta_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epilogue_mode,
                  const ta_gemm_epilogue* epilogue, void* stream);
 int ta_gemm_set_tile_n(int bn); /* 0 = auto, 128, 256 (testing / tuning) */
+int ta_gemm_set_cta_pair(int on); /* 1: CTA-pair kernel (tcgen05 cta_group::2, 256 x N tiles); 0: 1-CTA kernel */
 
 
 /* ------------------------------------------------------------------------------------------------
@@ -80,6 +81,7 @@ int ta_mel_to_conv1_im2col(const float* mel /*(B,128,T)*/, int B, int T, void* o
 int ta_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int Hq, int Hkv,
                 int head_dim, long long q_rs, long long k_rs, long long v_rs, long long o_rs, int causal, float scale,
                 void* stream);
+int ta_attn_set_tc(int on); /* 1 (default): encoder-shape forward runs on tcgen05 (attn_tc.cu); 0: mma.sync kernel */
 int ta_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                 float* dsum_ws, float* dq_acc, void* dk, void* dv, int B, int S, int Hq, int Hkv, int head_dim,
                 long long q_rs, long long k_rs, long long v_rs, long long o_rs, long long do_rs, long long dq_rs,

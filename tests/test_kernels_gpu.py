@@ -11,6 +11,7 @@ pytestmark = pytest.mark.gpu
 from tiny_audio_b200 import lib as L  # noqa: E402
 
 BF16, F32 = torch.bfloat16, torch.float32
+DEFAULT_PAIR = 1   # library default GEMM kernel (set to 1 once the CTA-pair kernel is the default)
 
 
 def rel_err(a, b):
@@ -28,11 +29,13 @@ def rnd(*shape, scale=1.0, dtype=BF16, seed=0, dev="cuda"):
 
 
 # ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("bn", [128, 256])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 512, 192), (1000, 1280, 1280), (77, 256, 1000), (4096, 3840, 1280)])
-def test_gemm_plain(cuda, M, N, K, bn):
+def test_gemm_plain(cuda, M, N, K, bn, pair):
     lib = L.load()
     L.check(lib.ta_gemm_set_tile_n(bn))
+    L.check(lib.ta_gemm_set_cta_pair(pair))
     try:
         a, b = rnd(M, K, seed=1), rnd(N, K, seed=2)
         bias = rnd(N, dtype=F32, seed=3)
@@ -46,9 +49,12 @@ def test_gemm_plain(cuda, M, N, K, bn):
         assert rel_err(out32, 0.5 * (a.float() @ b.float().t())) < 1e-4
     finally:
         L.check(lib.ta_gemm_set_tile_n(0))
+        L.check(lib.ta_gemm_set_cta_pair(DEFAULT_PAIR))
 
 
-def test_gemm_epilogues(cuda):
+@pytest.mark.parametrize("pair", [0, 1])
+def test_gemm_epilogues(cuda, pair):
+    L.check(L.load().ta_gemm_set_cta_pair(pair))
     M, N, K = 520, 512, 256
     a, b = rnd(M, K, seed=1, scale=0.5), rnd(N, K, seed=2, scale=0.1)
     bias = rnd(N, dtype=F32, seed=3)
@@ -66,12 +72,15 @@ def test_gemm_epilogues(cuda):
     r16b = r16.clone()
     L.gemm(a, b, epi=L.EPI_BF16_RESID, bias=bias, resid=r16b, out=r16b)
     assert rel_err(r16b, r16.float() + (acc + bias).to(BF16).float()) < 5e-3
+    L.check(L.load().ta_gemm_set_cta_pair(DEFAULT_PAIR))
 
 
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("bn", [128, 256])
-def test_gemm_swiglu_fwd_bwd(cuda, bn):
+def test_gemm_swiglu_fwd_bwd(cuda, bn, pair):
     lib = L.load()
     L.check(lib.ta_gemm_set_tile_n(bn))
+    L.check(lib.ta_gemm_set_cta_pair(pair))
     try:
         M, D, Fd = 300, 256, 512
         x = rnd(M, D, seed=1)
@@ -100,6 +109,7 @@ def test_gemm_swiglu_fwd_bwd(cuda, bn):
         assert e1 < 1e-2 and e2 < 1e-2
     finally:
         L.check(lib.ta_gemm_set_tile_n(0))
+        L.check(lib.ta_gemm_set_cta_pair(DEFAULT_PAIR))
 
 
 # ------------------------------------------------------------------ attention
@@ -116,10 +126,12 @@ def ref_attn(q, k, v, causal, scale):
     return (torch.softmax(s, -1) @ vf).transpose(1, 2), lse
 
 
-@pytest.mark.parametrize("B,S,Hq,Hkv,hd,causal", [(2, 200, 4, 4, 64, False), (1, 1500, 20, 20, 64, False),
+@pytest.mark.parametrize("tc", [1, 0])
+@pytest.mark.parametrize("B,S,Hq,Hkv,hd,causal", [(2, 200, 4, 4, 64, False), (1, 1500, 20, 20, 64, False), (3, 128, 2, 2, 64, False),
                                                    (2, 77, 4, 2, 128, True), (3, 464, 16, 8, 128, True)])
-def test_attn_fwd(cuda, B, S, Hq, Hkv, hd, causal):
+def test_attn_fwd(cuda, B, S, Hq, Hkv, hd, causal, tc):
     lib = L.load()
+    L.check(lib.ta_attn_set_tc(tc))
     W = (Hq + 2 * Hkv) * hd
     qkv = rnd(B, S, W, seed=7)
     q = qkv[..., : Hq * hd].view(B, S, Hq, hd)
@@ -134,6 +146,7 @@ def test_attn_fwd(cuda, B, S, Hq, Hkv, hd, causal):
     torch.cuda.synchronize()
     e = rel_err(o.view(B, S, Hq, hd), oref)
     print(f"attn fwd S={S} hd={hd} causal={causal}: rel {e:.3e}  lse max err {max_err(lse, lref):.3e}")
+    L.check(lib.ta_attn_set_tc(1))
     assert e < 1e-2 and max_err(lse, lref) < 2e-3
 
 

@@ -6,6 +6,7 @@
 // forward has a tcgen05 successor (attn_tc.cu, when enabled); this file stays as its parity reference and as
 // the decoder forward/backward.
 #include "common.cuh"
+#include "kernels.cuh"
 #include "tinyaudio_b200.h"
 
 namespace {
@@ -459,6 +460,12 @@ TA_API int ta_attn_fwd(const void* q, const void* k, const void* v, void* o, flo
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bf16 *Q = (const bf16*)q, *K = (const bf16*)k, *V = (const bf16*)v;
     bf16* O = (bf16*)o;
+    {   // tcgen05 kernel for the encoder shape (attn_tc.cu); other shapes stay on the mma.sync kernels below
+        int handled = 0;
+        const int rc = k_attn_tc_fwd(Q, K, V, O, lse, B, S, Hq, Hkv, head_dim, q_rs, k_rs, v_rs, o_rs, causal, scale, st, &handled);
+        if (rc) return rc;
+        if (handled) return 0;
+    }
     if (head_dim == 64 && !causal) return launch_fwd<64, false>(Q, K, V, O, lse, B, S, Hq, Hkv, q_rs, k_rs, v_rs, o_rs, scale, st);
     if (head_dim == 64 && causal) return launch_fwd<64, true>(Q, K, V, O, lse, B, S, Hq, Hkv, q_rs, k_rs, v_rs, o_rs, scale, st);
     if (head_dim == 128 && causal) return launch_fwd<128, true>(Q, K, V, O, lse, B, S, Hq, Hkv, q_rs, k_rs, v_rs, o_rs, scale, st);

@@ -1,0 +1,312 @@
+// tcgen05 flash-attention forward for the GLM-ASR encoder shape: head_dim 64, non-causal, no mask, S <= 1500
+// (HF:models/glmasr/modeling_glmasr.py:208-221).  Successor of attn_fwd_kernel<64,false> in attn_mma.cu, which tops
+// out at the legacy mma.sync rate (~0.5 PFLOP/s on B200; profiles/r01_*): here both GEMMs of the attention run on
+// the 5th-gen tensor cores with TMEM accumulators, so the kernel is bound by the exp2 rate of the SFUs instead.
+//
+// One CTA = one (batch, head, 128-query tile); two CTAs are resident per SM so that one CTA's softmax overlaps the
+// other's MMAs.  Roles:  warp 0 TMA producer (Q once; K_j / V_j through a 3-slot ring of 16 KB tiles),
+//                        warp 1 MMA issuer   (S_j = Q K_j^T -> TMEM[0,128);  O += P_j V_j -> TMEM[128,192)),
+//                        warp 2 TMEM allocator,  warps 4-7 softmax (thread = query row = TMEM lane).
+// Softmax keeps a lazily updated reference max (rescale O only when the row max grows by > 2^8, the FA-4 trick),
+// reads S twice from TMEM (max pass, exp pass) to stay under 128 registers, and writes P as bf16 into shared memory
+// in the K-major SWIZZLE_128B layout the A-operand descriptor expects.  V is consumed as an MN-major B operand
+// straight from its row-major [kv][64] TMA tile.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tinyaudio_b200.h"
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int BQ = 128, BKV = 128;
+constexpr int TILE_BYTES = 128 * 64 * 2;   // every smem tile here is 128 rows x 128 B
+constexpr int KV_SLOTS = 3;
+constexpr int ATT_THREADS = 256;
+constexpr int SMEM_ATT = TILE_BYTES * (1 + KV_SLOTS + 2) + 256 + 1024;
+constexpr int TMEM_COLS_ATT = 256;
+constexpr uint32_t S_COL = 0, O_COL = 128;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// MN-major SWIZZLE_128B operand (rows = K index, 64 bf16 = 128 B of the MN index per row; 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int H,
+                   long long o_rs, float scale_log2) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    uint8_t* sQ = smem;
+    uint8_t* sKV = smem + TILE_BYTES;
+    uint8_t* sP = smem + TILE_BYTES * (1 + KV_SLOTS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TILE_BYTES * (1 + KV_SLOTS + 2));
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = bars + 1 + KV_SLOTS;
+    uint64_t* s_full = bars + 1 + 2 * KV_SLOTS;
+    uint64_t* s_empty = s_full + 1;
+    uint64_t* p_full = s_full + 2;
+    uint64_t* pv_done = s_full + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qt * BQ;
+    const int n_kv = (S + BKV - 1) / BKV;
+    const int row_base = b * S;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < KV_SLOTS; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 4);
+        mbar_init(p_full, 4);
+        mbar_init(pv_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<TMEM_COLS_ATT>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            tma_load_2d(sQ, &tmQ, q_full, h * HD, row_base + q0);
+            for (int i = 0; i < 2 * n_kv; ++i) {
+                const int slot = i % KV_SLOTS;
+                const uint32_t ph = (uint32_t)(i / KV_SLOTS) & 1u;
+                mbar_wait(&kv_empty[slot], ph ^ 1);
+                mbar_arrive_expect_tx(&kv_full[slot], TILE_BYTES);
+                const int j = i >> 1;
+                tma_load_2d(sKV + slot * TILE_BYTES, (i & 1) ? &tmV : &tmK, &kv_full[slot], h * HD, row_base + j * BKV);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
+            constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
+            const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+            auto issue_s = [&](int j) {
+                const int i = 2 * j, slot = i % KV_SLOTS;
+                mbar_wait(&kv_full[slot], (uint32_t)(i / KV_SLOTS) & 1u);
+                mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sKV + slot * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_f16(tmem_base + S_COL, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(k_addr + k * 32),
+                             idesc_s, k != 0 ? 1u : 0u);
+                umma_commit(s_full);
+                umma_commit(&kv_empty[slot]);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) issue_s(j + 1);
+                const int i = 2 * j + 1, slot = i % KV_SLOTS;
+                mbar_wait(p_full, (uint32_t)j & 1u);
+                mbar_wait(&kv_full[slot], (uint32_t)(i / KV_SLOTS) & 1u);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(sKV + slot * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    const uint32_t pa = p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32;
+                    umma_f16(tmem_base + O_COL, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE_BYTES),
+                             idesc_o, (j | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(pv_done);
+                umma_commit(&kv_empty[slot]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + S_COL;
+        const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + O_COL;
+        float m_ref = -INFINITY, l_sum = 0.f;
+        uint8_t* p_row = sP + r * 128;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(s_full, (uint32_t)j & 1u);
+            tc_fence_after();
+            const bool tail = (j == n_kv - 1) && (S % BKV != 0);
+            const int valid = S - j * BKV;      // columns < valid are real keys
+            // ---- pass A: row max ----
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_s + c * 32, v);
+                tmem_ld_wait();
+                if (tail) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
+            }
+            mx *= scale_log2;
+            const bool grow = mx > m_ref + 8.0f;
+            const float m_new = grow ? mx : m_ref;
+            const float alpha = (grow && j > 0) ? ex2_approx(m_ref - m_new) : 1.0f;
+            m_ref = m_new;
+            if (j > 0) {
+                mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);     // PV_{j-1} has consumed sP and finished updating O
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+                    for (int c = 0; c < HD / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_o + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        tmem_st_32x32(t_o + c * 32, v);
+                    }
+                    tmem_st_wait();
+                    l_sum *= alpha;
+                }
+            }
+            // ---- pass B: P = exp2(S * scale - m_ref) -> bf16 -> swizzled smem ----
+            float ls = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_s + c * 32, v);
+                tmem_ld_wait();
+                float p[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float e = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
+                    if (tail && (c * 32 + i >= valid)) e = 0.f;
+                    p[i] = e;
+                    ls += e;
+                }
+                uint8_t* dst = p_row + (c >> 1) * TILE_BYTES;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    uint4 u;
+                    u.x = pack_bf16x2(p[8 * qd + 0], p[8 * qd + 1]);
+                    u.y = pack_bf16x2(p[8 * qd + 2], p[8 * qd + 3]);
+                    u.z = pack_bf16x2(p[8 * qd + 4], p[8 * qd + 5]);
+                    u.w = pack_bf16x2(p[8 * qd + 6], p[8 * qd + 7]);
+                    const int k16 = (c & 1) * 4 + qd;
+                    *reinterpret_cast<uint4*>(dst + ((k16 ^ (r & 7)) << 4)) = u;
+                }
+            }
+            l_sum += ls;
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(s_empty);
+                mbar_arrive(p_full);
+            }
+        }
+        // ---- epilogue: O / l -> bf16 ----
+        mbar_wait(pv_done, (uint32_t)(n_kv - 1) & 1u);
+        tc_fence_after();
+        const int row = q0 + r;
+        const float inv = 1.0f / l_sum;
+        bf16* orow = O + ((long long)row_base + row) * o_rs + (long long)h * HD;
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_o + c * 32, v);
+            tmem_ld_wait();
+            if (row < S) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(v[8 * qd + 0]) * inv, __uint_as_float(v[8 * qd + 1]) * inv);
+                    u.y = pack_bf16x2(__uint_as_float(v[8 * qd + 2]) * inv, __uint_as_float(v[8 * qd + 3]) * inv);
+                    u.z = pack_bf16x2(__uint_as_float(v[8 * qd + 4]) * inv, __uint_as_float(v[8 * qd + 5]) * inv);
+                    u.w = pack_bf16x2(__uint_as_float(v[8 * qd + 6]) * inv, __uint_as_float(v[8 * qd + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + qd * 8) = u;
+                }
+            }
+        }
+        if (LSE && row < S) LSE[((long long)b * H + h) * S + row] = (m_ref + log2f(l_sum)) * 0.69314718055994531f;
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<TMEM_COLS_ATT>(tmem_base);
+}
+
+int g_attn_tc = 1;
+
+}  // namespace
+
+TA_API int ta_attn_set_tc(int on) {
+    g_attn_tc = on ? 1 : 0;
+    return 0;
+}
+
+// internal: returns 1 if this shape is handled by the tcgen05 kernel (and launches it), 0 if the caller should use mma.sync
+int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* lse, int B, int S, int Hq, int Hkv, int head_dim,
+                  long long q_rs, long long k_rs, long long v_rs, long long o_rs, int causal, float scale, cudaStream_t st,
+                  int* handled) {
+    *handled = 0;
+    if (!g_attn_tc || head_dim != 64 || causal || Hq != Hkv || S < 1) return 0;
+    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+         reinterpret_cast<uintptr_t>(o)) & 15)
+        return 0;
+    CUtensorMap tq, tk, tv;
+    const long long rows = (long long)B * S;
+    int rc = k_make_tensor_map_2d(&tq, q, rows, (long long)Hq * HD, q_rs, BQ);
+    if (rc) return rc;
+    rc = k_make_tensor_map_2d(&tk, k, rows, (long long)Hkv * HD, k_rs, BKV);
+    if (rc) return rc;
+    rc = k_make_tensor_map_2d(&tv, v, rows, (long long)Hkv * HD, v_rs, BKV);
+    if (rc) return rc;
+    static bool done = false;
+    if (!done) {
+        TA_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
+        TA_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        done = true;
+    }
+    dim3 grid((S + BQ - 1) / BQ, Hq, B);
+    attn_tc_fwd_kernel<<<grid, ATT_THREADS, SMEM_ATT, st>>>(tq, tk, tv, o, lse, S, Hq, o_rs, scale * 1.4426950408889634f);
+    TA_LAUNCH_CHECK();
+    *handled = 1;
+    return 0;
+}

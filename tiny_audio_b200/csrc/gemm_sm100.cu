@@ -98,6 +98,107 @@ __device__ __forceinline__ void load_f32x32(const float* src, float (&v)[32]) {
     }
 }
 
+// One accumulator tile (this thread's TMEM lane = one output row, BN columns starting at tile_col0) -> global memory
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, long long row, bool row_ok, long long tile_col0, const EpiArgs& ep) {
+    if constexpr (EPI == TA_EPI_SWIGLU) {
+        // tile columns come in 128-wide groups: [64 gate | 64 up] (weights interleaved by the host)
+#pragma unroll 1
+        for (int sb = 0; sb < BN / 128; ++sb) {
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t rg[32], ru[32];
+                tmem_ld_32x32(taddr + sb * 128 + c * 32, rg);
+                tmem_ld_32x32(taddr + sb * 128 + 64 + c * 32, ru);
+                tmem_ld_wait();
+                __syncwarp();
+                if (row_ok) {
+                    float g[32], u[32], h[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        g[i] = bf16_round(__uint_as_float(rg[i]));
+                        u[i] = bf16_round(__uint_as_float(ru[i]));
+                        const float s = bf16_round(g[i] * sigmoidf_(g[i]));   // act_fn output is bf16 under autocast
+                        h[i] = s * u[i];
+                    }
+                    const long long col_gu = tile_col0 + sb * 128 + c * 32;
+                    const long long col_h = (tile_col0 + sb * 128) / 2 + c * 32;
+                    store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col_h, h);
+                    if (ep.out2) {
+                        bf16* gu = reinterpret_cast<bf16*>(ep.out2) + row * ep.ldo2 + col_gu;
+                        store_bf16x32(gu, g);
+                        store_bf16x32(gu + 64, u);
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait();
+            __syncwarp();
+            if (row_ok) {
+            const long long col = tile_col0 + c * 32;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if constexpr (EPI != TA_EPI_F32 && EPI != TA_EPI_SWIGLU_BWD) {
+                if (ep.bias) {
+                    float b[32];
+                    load_f32x32(ep.bias + col, b);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += b[i];
+                }
+            }
+            if constexpr (EPI == TA_EPI_BF16) {
+                store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
+            } else if constexpr (EPI == TA_EPI_BF16_GELU) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(bf16_round(v[i]));
+                store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
+            } else if constexpr (EPI == TA_EPI_BF16_RESID) {
+                float rs[32];
+                load_bf16x32(reinterpret_cast<const bf16*>(ep.resid) + row * ep.ldr + col, rs);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = rs[i] + bf16_round(v[i]);
+                store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
+            } else if constexpr (EPI == TA_EPI_F32_RESID) {
+                float rs[32];
+                load_f32x32(reinterpret_cast<const float*>(ep.resid) + row * ep.ldr + col, rs);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = rs[i] + bf16_round(v[i]);
+                store_f32x32(reinterpret_cast<float*>(ep.out) + row * ep.ldo + col, v);
+            } else if constexpr (EPI == TA_EPI_F32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= ep.alpha;
+                store_f32x32(reinterpret_cast<float*>(ep.out) + row * ep.ldo + col, v);
+            } else if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
+                // v = d(h) for h columns [col, col+32); the stash holds (gate, up) interleaved in 64-blocks
+                const long long jb = col / 64, jo = col % 64;
+                const bf16* gu = ep.aux + row * ep.ldaux + jb * 128 + jo;
+                float g[32], u[32], dg[32], du[32];
+                load_bf16x32(gu, g);
+                load_bf16x32(gu + 64, u);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float dh = bf16_round(v[i]);
+                    const float sg = sigmoidf_(g[i]);
+                    const float silu = bf16_round(g[i] * sg);
+                    du[i] = dh * silu;
+                    dg[i] = dh * u[i] * (sg * (1.0f + g[i] * (1.0f - sg)));
+                }
+                bf16* o = reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + jb * 128 + jo;
+                store_bf16x32(o, dg);
+                store_bf16x32(o + 64, du);
+            }
+            }   // row_ok
+            __syncwarp();
+        }
+    }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
@@ -203,102 +304,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const bool row_ok = row < M;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 
-            if constexpr (EPI == TA_EPI_SWIGLU) {
-                // tile columns come in 128-wide groups: [64 gate | 64 up] (weights interleaved by the host)
-#pragma unroll 1
-                for (int sb = 0; sb < BN / 128; ++sb) {
-#pragma unroll 1
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t rg[32], ru[32];
-                        tmem_ld_32x32(taddr + sb * 128 + c * 32, rg);
-                        tmem_ld_32x32(taddr + sb * 128 + 64 + c * 32, ru);
-                        tmem_ld_wait();
-                        __syncwarp();
-                        if (row_ok) {
-                            float g[32], u[32], h[32];
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                g[i] = bf16_round(__uint_as_float(rg[i]));
-                                u[i] = bf16_round(__uint_as_float(ru[i]));
-                                const float s = bf16_round(g[i] * sigmoidf_(g[i]));   // act_fn output is bf16 under autocast
-                                h[i] = s * u[i];
-                            }
-                            const long long col_gu = (long long)n_blk * BN + sb * 128 + c * 32;
-                            const long long col_h = ((long long)n_blk * BN + sb * 128) / 2 + c * 32;
-                            store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col_h, h);
-                            if (ep.out2) {
-                                bf16* gu = reinterpret_cast<bf16*>(ep.out2) + row * ep.ldo2 + col_gu;
-                                store_bf16x32(gu, g);
-                                store_bf16x32(gu + 64, u);
-                            }
-                        }
-                    }
-                }
-            } else {
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + c * 32, r);
-                    tmem_ld_wait();
-                    __syncwarp();
-                    if (row_ok) {
-                    const long long col = (long long)n_blk * BN + c * 32;
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if constexpr (EPI != TA_EPI_F32 && EPI != TA_EPI_SWIGLU_BWD) {
-                        if (ep.bias) {
-                            float b[32];
-                            load_f32x32(ep.bias + col, b);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] += b[i];
-                        }
-                    }
-                    if constexpr (EPI == TA_EPI_BF16) {
-                        store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
-                    } else if constexpr (EPI == TA_EPI_BF16_GELU) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(bf16_round(v[i]));
-                        store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
-                    } else if constexpr (EPI == TA_EPI_BF16_RESID) {
-                        float rs[32];
-                        load_bf16x32(reinterpret_cast<const bf16*>(ep.resid) + row * ep.ldr + col, rs);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = rs[i] + bf16_round(v[i]);
-                        store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
-                    } else if constexpr (EPI == TA_EPI_F32_RESID) {
-                        float rs[32];
-                        load_f32x32(reinterpret_cast<const float*>(ep.resid) + row * ep.ldr + col, rs);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = rs[i] + bf16_round(v[i]);
-                        store_f32x32(reinterpret_cast<float*>(ep.out) + row * ep.ldo + col, v);
-                    } else if constexpr (EPI == TA_EPI_F32) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] *= ep.alpha;
-                        store_f32x32(reinterpret_cast<float*>(ep.out) + row * ep.ldo + col, v);
-                    } else if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
-                        // v = d(h) for h columns [col, col+32); the stash holds (gate, up) interleaved in 64-blocks
-                        const long long jb = col / 64, jo = col % 64;
-                        const bf16* gu = ep.aux + row * ep.ldaux + jb * 128 + jo;
-                        float g[32], u[32], dg[32], du[32];
-                        load_bf16x32(gu, g);
-                        load_bf16x32(gu + 64, u);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float dh = bf16_round(v[i]);
-                            const float sg = sigmoidf_(g[i]);
-                            const float silu = bf16_round(g[i] * sg);
-                            du[i] = dh * silu;
-                            dg[i] = dh * u[i] * (sg * (1.0f + g[i] * (1.0f - sg)));
-                        }
-                        bf16* o = reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + jb * 128 + jo;
-                        store_bf16x32(o, dg);
-                        store_bf16x32(o + 64, du);
-                    }
-                    }   // row_ok
-                    __syncwarp();
-                }
-            }
+            epilogue_tile<BN, EPI>(taddr, row, row_ok, (long long)n_blk * BN, ep);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
@@ -310,6 +316,199 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+
+// =============================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair (cluster 2x1x1, two SMs of one TPC) owns a 256 x BN tile.
+//   CTA r holds A rows [m0 + 128 r, +128) and the B rows [n0 + r BN/2, + BN/2) of every stage; the leader (rank 0)
+//   issues tcgen05.mma.cta_group::2 with M = 256, which reads both CTAs' shared memory and writes each CTA's
+//   128 x BN accumulator half into its own TMEM.  Per CTA and k-block this loads 16 KB (A) + BN/2*128 B (B half)
+//   instead of 16 KB + BN*128 B: a third less L2->SMEM traffic and shared-memory read bandwidth than the 1-CTA kernel.
+//   Barriers:  full[s]   (leader only, count 1)  <- both CTAs' TMA complete_tx + the leader's expect_tx of both halves
+//              empty[s]  (each CTA,   count 1)   <- tcgen05.commit ... multicast::cluster (mask 0b11)
+//              tfull[a]  (each CTA,   count 1)   <- tcgen05.commit multicast
+//              tempty[a] (leader only, count 8)  <- 4 epilogue warps of each CTA (remote arrive from rank 1)
+// =============================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> rank 0 of the pair
+
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint64_t* leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on rank 0's copy of `bar`
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+template <int BN>
+struct Cfg2 {
+    static constexpr int A_BYTES = BM * BK * 2;            // 128 rows of A per CTA
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;      // half of the B tile per CTA
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 6 : 8;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, EpiArgs ep) {
+    using C = Cfg2<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + C::STAGES * C::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + C::STAGES;
+    uint64_t* tfull = bars + 2 * C::STAGES;
+    uint64_t* tempty = bars + 2 * C::STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int tiles_n = N / BN;
+    const int tiles_m = (M + 2 * BM - 1) / (2 * BM);
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], 8);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs load their own halves) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+                const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
+                const int row0 = m_blk * 2 * BM + (int)rank * BM;
+                const int nrow0 = n_blk * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+                    tma_load_2d_2sm(smA + stage * C::A_BYTES, &tmA, &full[stage], kb * BK, row0);
+                    tma_load_2d_2sm(smB + stage * C::B_BYTES, &tmB, &full[stage], kb * BK, nrow0);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(smA + stage * C::A_BYTES);
+                    const uint32_t b0 = smem_u32(smB + stage * C::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ad = umma_desc_sw128_kmajor(a0 + k * UMMA_K * 2);
+                        const uint64_t bd = umma_desc_sw128_kmajor(b0 + k * UMMA_K * 2);
+                        umma_f16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit_2sm(&empty[stage]);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tfull[as]);
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, their own 128 rows) =====================
+        const int q = warp & 3;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+            const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const long long row = (long long)m_blk * 2 * BM + (long long)rank * BM + q * 32 + lane;
+            const bool row_ok = row < M;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            epilogue_tile<BN, EPI>(taddr, row, row_ok, (long long)n_blk * BN, ep);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty[as]);
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // nobody exits (or frees TMEM) while the peer may still signal / read
+    if (warp == 2) tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -380,6 +579,15 @@ int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, 
     return 0;
 }
 
+}  // namespace
+
+// shared with attn_tc.cu (kernels.cuh)
+int k_make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    return make_map(out, ptr, rows, cols, ld, box_rows);
+}
+
+namespace {
+
 int g_num_sms = 0;
 int num_sms() {
     if (g_num_sms == 0) {
@@ -422,7 +630,40 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, i
     }
 }
 
+template <int BN, int EPI>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiArgs& ep, cudaStream_t st) {
+    using C = Cfg2<BN>;
+    auto kern = gemm2_kernel<BN, EPI>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
+    int pairs = num_sms() / 2;
+    if (tiles < pairs) pairs = tiles;
+    kern<<<2 * pairs, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, M, N, K, ep);
+    TA_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int BN>
+int dispatch_epi2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiArgs& ep,
+                  cudaStream_t st) {
+    switch (epi) {
+        case TA_EPI_BF16: return launch2<BN, TA_EPI_BF16>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_BF16_GELU: return launch2<BN, TA_EPI_BF16_GELU>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_BF16_RESID: return launch2<BN, TA_EPI_BF16_RESID>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_F32_RESID: return launch2<BN, TA_EPI_F32_RESID>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_F32: return launch2<BN, TA_EPI_F32>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_SWIGLU: return launch2<BN, TA_EPI_SWIGLU>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_SWIGLU_BWD: return launch2<BN, TA_EPI_SWIGLU_BWD>(ta, tb, M, N, K, ep, st);
+        default: ta_set_error("unknown epilogue mode %d", epi); return -1;
+    }
+}
+
 int g_force_bn = 0;
+int g_cta_pair = 1;   // 1 (default): CTA-pair kernel (cta_group::2, 256 x N tiles); 0: 1-CTA kernel (cta_group::1)
 
 }  // namespace
 
@@ -432,6 +673,11 @@ TA_API int ta_gemm_set_tile_n(int bn) {
         return -1;
     }
     g_force_bn = bn;
+    return 0;
+}
+
+TA_API int ta_gemm_set_cta_pair(int on) {
+    g_cta_pair = on ? 1 : 0;
     return 0;
 }
 
@@ -451,9 +697,15 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
     CUtensorMap ta, tb;
     int rc = make_map(&ta, A, M, K, lda, BM);
     if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (g_cta_pair) {
+        rc = make_map(&tb, B, N, K, ldb, bn / 2);     // each CTA of the pair loads half of the B tile
+        if (rc) return rc;
+        if (bn == 256) return dispatch_epi2<256>(epi, ta, tb, M, N, K, ep, st);
+        return dispatch_epi2<128>(epi, ta, tb, M, N, K, ep, st);
+    }
     rc = make_map(&tb, B, N, K, ldb, bn);
     if (rc) return rc;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (bn == 256) return dispatch_epi<256>(epi, ta, tb, M, N, K, ep, st);
     return dispatch_epi<128>(epi, ta, tb, M, N, K, ep, st);
 }

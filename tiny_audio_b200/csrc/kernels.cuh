@@ -27,3 +27,11 @@ int k_transpose_bf16(const bf16* in, bf16* out, int R, int C, long long ld_in, l
 int k_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t st);
 int k_frame_stack(const bf16* x, bf16* out, int B, int S, int n, int k, int D, cudaStream_t st);
 int k_sumsq(const float* g, long long n, float* out, cudaStream_t st);
+
+// 2-D bf16 row-major tensor map, box = {64 cols, box_rows}, SWIZZLE_128B, zero fill out of bounds (cached)
+int k_make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
+
+// tcgen05 attention forward (attn_tc.cu): *handled = 1 when the shape is supported and the kernel was launched
+int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* lse, int B, int S, int Hq, int Hkv, int head_dim,
+                  long long q_rs, long long k_rs, long long v_rs, long long o_rs, int causal, float scale, cudaStream_t st,
+                  int* handled);

@@ -60,10 +60,12 @@ _SIGS = {
     "ta_launch_count": ([], C.c_ulonglong),
     "ta_gemm_bf16": ([P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, C.POINTER(GemmEpilogue), P], c_int),
     "ta_gemm_set_tile_n": ([c_int], c_int),
+    "ta_gemm_set_cta_pair": ([c_int], c_int),
     "ta_logmel_workspace_floats": ([c_int, c_int, C.POINTER(c_ll)], c_int),
     "ta_logmel_fwd": ([P, c_ll, c_int, c_int, P, P, P, P], c_int),
     "ta_mel_to_conv1_im2col": ([P, c_int, c_int, P, P], c_int),
     "ta_attn_fwd": ([P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_int, c_float, P], c_int),
+    "ta_attn_set_tc": ([c_int], c_int),
     "ta_attn_bwd": ([P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
                      c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_int, c_float, P], c_int),
     "ta_im2col_k3": ([P, P, c_int, c_int, c_int, c_int, P], c_int),
@@ -119,6 +121,11 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res
+    # tuning / A-B switches (both kernels of each pair are parity-tested; defaults are the fast ones)
+    if os.environ.get("TA_GEMM_CTA_PAIR") is not None:
+        lib.ta_gemm_set_cta_pair(int(os.environ["TA_GEMM_CTA_PAIR"]))
+    if os.environ.get("TA_ATTN_TC") is not None:
+        lib.ta_attn_set_tc(int(os.environ["TA_ATTN_TC"]))
     _lib = lib
     return lib
 
