@@ -35,7 +35,8 @@ enum {
     TA_EPI_F32_RESID = 3,  /* out f32  = resid_f32 + bf16(acc + bias)                            */
     TA_EPI_F32 = 4,        /* out f32  = alpha * acc                                             */
     TA_EPI_SWIGLU = 5,     /* B rows interleaved [64 gate | 64 up]: out bf16 [M,N/2] = silu(g)*u; out2 = (g,u) stash */
-    TA_EPI_SWIGLU_BWD = 6  /* acc = d(h) [M,N]; aux = (g,u) stash [M,2N]; out bf16 [M,2N] = (d gate | d up)          */
+    TA_EPI_SWIGLU_BWD = 6, /* acc = d(h) [M,N]; aux = (g,u) stash [M,2N]; out bf16 [M,2N] = (d gate | d up)          */
+    TA_EPI_BF16_ROPE = 7   /* out bf16 = rope(acc + bias): GLM-ASR partial rotary on columns < rope_cols (64-wide heads, 32 dims) */
 };
 
 typedef struct ta_gemm_epilogue {
@@ -49,6 +50,10 @@ typedef struct ta_gemm_epilogue {
     const void* aux;    /* SWIGLU_BWD: the stash */
     long long ldaux;
     float alpha;        /* F32 mode scale; 0 -> 1 */
+    const float* rope_cos; /* BF16_ROPE: fp32 [rope_seq, 16] */
+    const float* rope_sin;
+    int rope_seq;       /* position = row % rope_seq */
+    int rope_cols;      /* rotate output columns [0, rope_cols) (the q and k blocks of a fused qkv projection) */
 } ta_gemm_epilogue;
 
 int ta_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epilogue_mode,

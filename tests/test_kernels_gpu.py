@@ -112,6 +112,25 @@ def test_gemm_swiglu_fwd_bwd(cuda, bn, pair):
         L.check(lib.ta_gemm_set_cta_pair(DEFAULT_PAIR))
 
 
+@pytest.mark.parametrize("pair", [0, 1])
+def test_gemm_rope_epilogue(cuda, pair):
+    """q|k|v projection with the GLM-ASR partial rotary embedding fused into the epilogue == plain GEMM + ta_enc_rope."""
+    lib = L.load()
+    L.check(lib.ta_gemm_set_cta_pair(pair))
+    B, S, H, hd, rd = 2, 150, 4, 64, 32
+    D = H * hd
+    x, w = rnd(B * S, D, seed=1), rnd(3 * D, D, seed=2, scale=0.06)
+    bias = rnd(3 * D, dtype=F32, seed=3)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, rd, 2).float() / rd))
+    fr = torch.arange(S).float()[:, None] * inv[None]
+    cos, sin = fr.cos().cuda().contiguous(), fr.sin().cuda().contiguous()
+    ref = L.gemm(x, w, epi=L.EPI_BF16, bias=bias)
+    L.check(lib.ta_enc_rope(L.ptr(ref), L.ptr(cos), L.ptr(sin), B * S, S, H, hd, rd, L.stream_ptr()))
+    out = L.gemm(x, w, epi=L.EPI_BF16_ROPE, bias=bias, rope=(cos, sin, S, 2 * D))
+    L.check(lib.ta_gemm_set_cta_pair(DEFAULT_PAIR))
+    assert torch.equal(out, ref)
+
+
 # ------------------------------------------------------------------ attention
 def ref_attn(q, k, v, causal, scale):
     B, S, Hq, hd = q.shape

@@ -21,8 +21,8 @@ constexpr int HD = 64;
 constexpr int BQ = 128, BKV = 128;
 constexpr int TILE_BYTES = 128 * 64 * 2;   // every smem tile here is 128 rows x 128 B
 constexpr int KV_SLOTS = 3;
-constexpr int ATT_THREADS = 256;
-constexpr int SMEM_ATT = TILE_BYTES * (1 + KV_SLOTS + 2) + 256 + 1024;
+constexpr int ATT_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: softmax (2 threads per row)
+constexpr int SMEM_ATT = TILE_BYTES * (1 + KV_SLOTS + 2) + 256 + 3 * 1024 + 1024;   // tiles + barriers + exchange floats + align
 constexpr int TMEM_COLS_ATT = 256;
 constexpr uint32_t S_COL = 0, O_COL = 128;
 
@@ -74,6 +74,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint64_t* p_full = s_full + 2;
     uint64_t* pv_done = s_full + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
+    float* sXch = reinterpret_cast<float*>(smem + TILE_BYTES * (1 + KV_SLOTS + 2) + 256);   // [3][2][128] max (x2) / sum exchange
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -93,8 +94,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_init(&kv_empty[s], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(s_empty, 4);
-        mbar_init(p_full, 4);
+        mbar_init(s_empty, 8);
+        mbar_init(p_full, 8);
         mbar_init(pv_done, 1);
         mbar_fence_init();
     }
@@ -155,34 +156,47 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     } else if (warp >= 4) {
+        // two threads per query row: warp (4+q) and warp (8+q) share TMEM lane quadrant q and split the columns
         const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
         const int r = q * 32 + lane;
-        const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + S_COL;
-        const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + O_COL;
+        const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + S_COL + (uint32_t)(half * 64);
+        const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + O_COL + (uint32_t)(half * 32);
         float m_ref = -INFINITY, l_sum = 0.f;
-        uint8_t* p_row = sP + r * 128;
+        uint8_t* p_row = sP + half * TILE_BYTES + r * 128;
+        const uint32_t bar_id = 1 + q;
         for (int j = 0; j < n_kv; ++j) {
             mbar_wait(s_full, (uint32_t)j & 1u);
             tc_fence_after();
             const bool tail = (j == n_kv - 1) && (S % BKV != 0);
-            const int valid = S - j * BKV;      // columns < valid are real keys
-            // ---- pass A: row max ----
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_s + c * 32, v);
+            const int valid = S - j * BKV - half * 64;      // my columns < valid are real keys
+            // ---- pass A: row max over my 64 columns, then combine with the partner thread ----
+            float mx;
+            {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(t_s, v0);
+                tmem_ld_32x32(t_s + 32, v1);
                 tmem_ld_wait();
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 if (tail) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) {
+                        if (i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v0[i]));
+                        if (32 + i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v1[i]));
+                    }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) {
+                        m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v0[i]));
+                        m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v1[i]));
+                    }
                 }
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             }
-            mx *= scale_log2;
+            float* xch = sXch + (j & 1) * 256;
+            xch[half * 128 + r] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]) * scale_log2;
             const bool grow = mx > m_ref + 8.0f;
             const float m_new = grow ? mx : m_ref;
             const float alpha = (grow && j > 0) ? ex2_approx(m_ref - m_new) : 1.0f;
@@ -191,47 +205,47 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);     // PV_{j-1} has consumed sP and finished updating O
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll 1
-                    for (int c = 0; c < HD / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_o + c * 32, v);
-                        tmem_ld_wait();
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_o, v);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        tmem_st_32x32(t_o + c * 32, v);
-                    }
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                    tmem_st_32x32(t_o, v);
                     tmem_st_wait();
                     l_sum *= alpha;
                 }
             }
-            // ---- pass B: P = exp2(S * scale - m_ref) -> bf16 -> swizzled smem ----
-            float ls = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_s + c * 32, v);
+            // ---- pass B: P = exp2(S * scale - m_ref) -> bf16 -> swizzled smem (my 64 columns = sub-tile `half`) ----
+            {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(t_s, v0);
+                tmem_ld_32x32(t_s + 32, v1);
                 tmem_ld_wait();
-                float p[32];
+                float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float e = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
-                    if (tail && (c * 32 + i >= valid)) e = 0.f;
-                    p[i] = e;
-                    ls += e;
-                }
-                uint8_t* dst = p_row + (c >> 1) * TILE_BYTES;
+                for (int c = 0; c < 2; ++c) {
+                    float p[32];
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    uint4 u;
-                    u.x = pack_bf16x2(p[8 * qd + 0], p[8 * qd + 1]);
-                    u.y = pack_bf16x2(p[8 * qd + 2], p[8 * qd + 3]);
-                    u.z = pack_bf16x2(p[8 * qd + 4], p[8 * qd + 5]);
-                    u.w = pack_bf16x2(p[8 * qd + 6], p[8 * qd + 7]);
-                    const int k16 = (c & 1) * 4 + qd;
-                    *reinterpret_cast<uint4*>(dst + ((k16 ^ (r & 7)) << 4)) = u;
+                    for (int i = 0; i < 32; ++i) {
+                        const float x = __uint_as_float(c ? v1[i] : v0[i]);
+                        float e = ex2_approx(fmaf(x, scale_log2, -m_ref));
+                        if (tail && (c * 32 + i >= valid)) e = 0.f;
+                        p[i] = e;
+                        l4[i & 3] += e;
+                    }
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        uint4 u;
+                        u.x = pack_bf16x2(p[8 * qd + 0], p[8 * qd + 1]);
+                        u.y = pack_bf16x2(p[8 * qd + 2], p[8 * qd + 3]);
+                        u.z = pack_bf16x2(p[8 * qd + 4], p[8 * qd + 5]);
+                        u.w = pack_bf16x2(p[8 * qd + 6], p[8 * qd + 7]);
+                        const int k16 = c * 4 + qd;
+                        *reinterpret_cast<uint4*>(p_row + ((k16 ^ (r & 7)) << 4)) = u;
+                    }
                 }
+                l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
             }
-            l_sum += ls;
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
@@ -240,16 +254,19 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_arrive(p_full);
             }
         }
-        // ---- epilogue: O / l -> bf16 ----
+        // ---- epilogue: O / l -> bf16 (my 32 of the 64 head dims) ----
+        float* xch = sXch + 512;
+        xch[half * 128 + r] = l_sum;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        l_sum += xch[(half ^ 1) * 128 + r];
         mbar_wait(pv_done, (uint32_t)(n_kv - 1) & 1u);
         tc_fence_after();
         const int row = q0 + r;
         const float inv = 1.0f / l_sum;
-        bf16* orow = O + ((long long)row_base + row) * o_rs + (long long)h * HD;
-#pragma unroll 1
-        for (int c = 0; c < HD / 32; ++c) {
+        bf16* orow = O + ((long long)row_base + row) * o_rs + (long long)h * HD + half * 32;
+        {
             uint32_t v[32];
-            tmem_ld_32x32(t_o + c * 32, v);
+            tmem_ld_32x32(t_o, v);
             tmem_ld_wait();
             if (row < S) {
 #pragma unroll
@@ -259,11 +276,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     u.y = pack_bf16x2(__uint_as_float(v[8 * qd + 2]) * inv, __uint_as_float(v[8 * qd + 3]) * inv);
                     u.z = pack_bf16x2(__uint_as_float(v[8 * qd + 4]) * inv, __uint_as_float(v[8 * qd + 5]) * inv);
                     u.w = pack_bf16x2(__uint_as_float(v[8 * qd + 6]) * inv, __uint_as_float(v[8 * qd + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + qd * 8) = u;
+                    *reinterpret_cast<uint4*>(orow + qd * 8) = u;
                 }
             }
         }
-        if (LSE && row < S) LSE[((long long)b * H + h) * S + row] = (m_ref + log2f(l_sum)) * 0.69314718055994531f;
+        if (LSE && half == 0 && row < S) LSE[((long long)b * H + h) * S + row] = (m_ref + log2f(l_sum)) * 0.69314718055994531f;
         tc_fence_before();
     }
 

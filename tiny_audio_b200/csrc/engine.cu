@@ -23,10 +23,12 @@ struct Carver {
 
 inline int gemm(const void* A, long long lda, const void* B, long long ldb, long long M, int N, int K, int epi, void* out,
                 long long ldo, const float* bias, const void* resid, void* out2, long long ldo2, const void* aux,
-                long long ldaux, cudaStream_t st, float alpha = 1.0f) {
+                long long ldaux, cudaStream_t st, float alpha = 1.0f, const float* rope_cos = nullptr,
+                const float* rope_sin = nullptr, int rope_seq = 0, int rope_cols = 0) {
     if (M == 0) return 0;
     ta_gemm_epilogue e;
     memset(&e, 0, sizeof(e));
+    e.rope_cos = rope_cos; e.rope_sin = rope_sin; e.rope_seq = rope_seq; e.rope_cols = rope_cols;
     e.out = out; e.ldo = ldo; e.bias = bias; e.resid = resid; e.ldr = ldo; e.out2 = out2; e.ldo2 = ldo2; e.aux = aux;
     e.ldaux = ldaux; e.alpha = alpha;
     return ta_gemm_bf16(A, lda, B, ldb, (int)M, N, K, epi, &e, st);
@@ -68,7 +70,8 @@ TA_API int ta_encoder_workspace_bytes(const ta_encoder_weights* w, int B, int T,
 TA_API int ta_encoder_forward(const ta_encoder_weights* w, const void* conv1_im2col, int B, int T, void* workspace,
                               long long workspace_bytes, void* out, void* stream) {
     TA_REQUIRE(w && conv1_im2col && workspace && out, "ta_encoder_forward: null pointer");
-    TA_REQUIRE(w->head_dim == 64 && w->heads * w->head_dim == w->dim, "encoder: head_dim must be 64 and heads*64 == dim");
+    TA_REQUIRE(w->head_dim == 64 && w->heads * w->head_dim == w->dim && w->rot_dim == 32,
+               "encoder: head_dim must be 64 (rotary 32) and heads*64 == dim");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int S = enc_out_len(T);
     TA_REQUIRE(S <= w->max_pos, "encoder: %d frames exceed the rotary table (%d)", S, w->max_pos);
@@ -91,9 +94,9 @@ TA_API int ta_encoder_forward(const ta_encoder_weights* w, const void* conv1_im2
     for (int l = 0; l < w->n_layers; ++l) {
         const void* const* L = w->layers + (long long)l * TA_ENC_PTRS_PER_LAYER;
         RUN(k_layernorm_bf16(x, (const float*)L[TA_ENC_LN1_W], (const float*)L[TA_ENC_LN1_B], h, M, D, w->ln_eps, st));
-        RUN(gemm(h, D, L[TA_ENC_WQKV], D, M, 3 * D, D, TA_EPI_BF16, qkv, 3 * D, (const float*)L[TA_ENC_BQKV], nullptr, nullptr, 0,
-                 nullptr, 0, st));
-        RUN(k_enc_rope(qkv, w->rope_cos, w->rope_sin, M, S, w->heads, w->head_dim, w->rot_dim, st));
+        // q|k|v projection with bias and the partial rotary embedding fused into the epilogue
+        RUN(gemm(h, D, L[TA_ENC_WQKV], D, M, 3 * D, D, TA_EPI_BF16_ROPE, qkv, 3 * D, (const float*)L[TA_ENC_BQKV], nullptr, nullptr, 0,
+                 nullptr, 0, st, 1.0f, w->rope_cos, w->rope_sin, S, 2 * D));
         RUN(ta_attn_fwd(qkv, qkv + D, qkv + 2 * D, h, nullptr, B, S, w->heads, w->heads, w->head_dim, 3 * D, 3 * D, 3 * D, D, 0,
                         scale, st));
         RUN(gemm(h, D, L[TA_ENC_WO], D, M, D, D, TA_EPI_BF16_RESID, x, D, (const float*)L[TA_ENC_BO], x, nullptr, 0, nullptr, 0, st));

@@ -37,7 +37,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: two epilogue groups (column halves)
 
 template <int BN>
 struct Cfg {
@@ -60,6 +60,10 @@ struct EpiArgs {
     const bf16* aux;
     long long ldaux;
     float alpha;
+    const float* rope_cos;   // BF16_ROPE: [seq, 16] tables, rotation applied to columns < rope_cols, first 32 dims of each 64-wide head
+    const float* rope_sin;
+    int rope_seq;
+    int rope_cols;
 };
 
 __device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32]) {
@@ -100,13 +104,16 @@ __device__ __forceinline__ void load_f32x32(const float* src, float (&v)[32]) {
 
 // One accumulator tile (this thread's TMEM lane = one output row, BN columns starting at tile_col0) -> global memory
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(uint32_t taddr, long long row, bool row_ok, long long tile_col0, const EpiArgs& ep) {
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, long long row, bool row_ok, long long tile_col0, const EpiArgs& ep,
+                                              int grp /* 0 / 1: which half of the tile's columns this warp group owns */) {
     if constexpr (EPI == TA_EPI_SWIGLU) {
         // tile columns come in 128-wide groups: [64 gate | 64 up] (weights interleaved by the host)
+        const int sb_lo = (BN == 256) ? grp : 0, sb_hi = (BN == 256) ? grp + 1 : 1;
+        const int c_lo = (BN == 256) ? 0 : grp, c_hi = (BN == 256) ? 2 : grp + 1;
 #pragma unroll 1
-        for (int sb = 0; sb < BN / 128; ++sb) {
+        for (int sb = sb_lo; sb < sb_hi; ++sb) {
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
+            for (int c = c_lo; c < c_hi; ++c) {
                 uint32_t rg[32], ru[32];
                 tmem_ld_32x32(taddr + sb * 128 + c * 32, rg);
                 tmem_ld_32x32(taddr + sb * 128 + 64 + c * 32, ru);
@@ -134,7 +141,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, long long row, boo
         }
     } else {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = grp * (BN / 64); c < (grp + 1) * (BN / 64); ++c) {
             uint32_t r[32];
             tmem_ld_32x32(taddr + c * 32, r);
             tmem_ld_wait();
@@ -152,7 +159,29 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, long long row, boo
                     for (int i = 0; i < 32; ++i) v[i] += b[i];
                 }
             }
-            if constexpr (EPI == TA_EPI_BF16) {
+            if constexpr (EPI == TA_EPI_BF16_ROPE) {
+                // partial rotary embedding fused into the q|k|v projection: head = 64 columns, rotary dims = its first 32
+                // (= exactly this chunk when col % 64 == 0), pairs (i, i+16)   (HF:models/glmasr/modeling_glmasr.py:156-171)
+                if (col < ep.rope_cols && (col & 63) == 0) {
+                    const int pos = (int)(row % ep.rope_seq);
+                    float cs[16], sn[16];
+                    const float4* c4 = reinterpret_cast<const float4*>(ep.rope_cos + pos * 16);
+                    const float4* s4 = reinterpret_cast<const float4*>(ep.rope_sin + pos * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a = c4[i], b = s4[i];
+                        cs[4 * i] = a.x; cs[4 * i + 1] = a.y; cs[4 * i + 2] = a.z; cs[4 * i + 3] = a.w;
+                        sn[4 * i] = b.x; sn[4 * i + 1] = b.y; sn[4 * i + 2] = b.z; sn[4 * i + 3] = b.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float x1 = bf16_round(v[i]), x2 = bf16_round(v[i + 16]);
+                        v[i] = x1 * cs[i] - x2 * sn[i];
+                        v[i + 16] = x2 * cs[i] + x1 * sn[i];
+                    }
+                }
+                store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
+            } else if constexpr (EPI == TA_EPI_BF16) {
                 store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
             } else if constexpr (EPI == TA_EPI_BF16_GELU) {
 #pragma unroll
@@ -234,7 +263,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 4);
+            mbar_init(&tempty[s], 8);
         }
         mbar_fence_init();
     }
@@ -304,7 +333,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const bool row_ok = row < M;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 
-            epilogue_tile<BN, EPI>(taddr, row, row_ok, (long long)n_blk * BN, ep);
+            epilogue_tile<BN, EPI>(taddr, row, row_ok, (long long)n_blk * BN, ep, (warp - 4) >> 2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
@@ -424,7 +453,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 8);
+            mbar_init(&tempty[s], 16);
         }
         mbar_fence_init();
     }
@@ -496,7 +525,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const long long row = (long long)m_blk * 2 * BM + (long long)rank * BM + q * 32 + lane;
             const bool row_ok = row < M;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            epilogue_tile<BN, EPI>(taddr, row, row_ok, (long long)n_blk * BN, ep);
+            epilogue_tile<BN, EPI>(taddr, row, row_ok, (long long)n_blk * BN, ep, (warp - 4) >> 2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty[as]);
@@ -626,6 +655,7 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, i
         case TA_EPI_F32: return launch<BN, TA_EPI_F32>(ta, tb, M, N, K, ep, st);
         case TA_EPI_SWIGLU: return launch<BN, TA_EPI_SWIGLU>(ta, tb, M, N, K, ep, st);
         case TA_EPI_SWIGLU_BWD: return launch<BN, TA_EPI_SWIGLU_BWD>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_BF16_ROPE: return launch<BN, TA_EPI_BF16_ROPE>(ta, tb, M, N, K, ep, st);
         default: ta_set_error("unknown epilogue mode %d", epi); return -1;
     }
 }
@@ -658,6 +688,7 @@ int dispatch_epi2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, 
         case TA_EPI_F32: return launch2<BN, TA_EPI_F32>(ta, tb, M, N, K, ep, st);
         case TA_EPI_SWIGLU: return launch2<BN, TA_EPI_SWIGLU>(ta, tb, M, N, K, ep, st);
         case TA_EPI_SWIGLU_BWD: return launch2<BN, TA_EPI_SWIGLU_BWD>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_BF16_ROPE: return launch2<BN, TA_EPI_BF16_ROPE>(ta, tb, M, N, K, ep, st);
         default: ta_set_error("unknown epilogue mode %d", epi); return -1;
     }
 }
@@ -694,6 +725,8 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
     ep.out = e->out; ep.ldo = e->ldo; ep.bias = e->bias; ep.resid = e->resid; ep.ldr = e->ldr ? e->ldr : e->ldo;
     ep.out2 = e->out2; ep.ldo2 = e->ldo2; ep.aux = reinterpret_cast<const bf16*>(e->aux); ep.ldaux = e->ldaux;
     ep.alpha = e->alpha == 0.0f ? 1.0f : e->alpha;
+    ep.rope_cos = e->rope_cos; ep.rope_sin = e->rope_sin; ep.rope_seq = e->rope_seq; ep.rope_cols = e->rope_cols;
+    if (epi == TA_EPI_BF16_ROPE) TA_REQUIRE(e->rope_cos && e->rope_sin && e->rope_seq > 0, "rope epilogue needs cos/sin tables and the sequence length");
     CUtensorMap ta, tb;
     int rc = make_map(&ta, A, M, K, lda, BM);
     if (rc) return rc;

@@ -18,7 +18,7 @@ c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 P = c_void_p
 
 # epilogue modes (enum in the header)
-EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESID, EPI_F32_RESID, EPI_F32, EPI_SWIGLU, EPI_SWIGLU_BWD = range(7)
+EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESID, EPI_F32_RESID, EPI_F32, EPI_SWIGLU, EPI_SWIGLU_BWD, EPI_BF16_ROPE = range(8)
 ENC_PTRS_PER_LAYER = 12
 LM_PTRS_PER_LAYER = 12
 (ENC_LN1_W, ENC_LN1_B, ENC_WQKV, ENC_BQKV, ENC_WO, ENC_BO, ENC_LN2_W, ENC_LN2_B, ENC_W1, ENC_B1, ENC_W2, ENC_B2) = range(12)
@@ -27,7 +27,8 @@ LM_PTRS_PER_LAYER = 12
 
 class GemmEpilogue(C.Structure):
     _fields_ = [("out", P), ("ldo", c_ll), ("bias", P), ("resid", P), ("ldr", c_ll), ("out2", P), ("ldo2", c_ll),
-                ("aux", P), ("ldaux", c_ll), ("alpha", c_float)]
+                ("aux", P), ("ldaux", c_ll), ("alpha", c_float), ("rope_cos", P), ("rope_sin", P), ("rope_seq", c_int),
+                ("rope_cols", c_int)]
 
 
 class EncoderWeights(C.Structure):
@@ -157,7 +158,8 @@ def require_cuda(*tensors: torch.Tensor) -> None:
 # --------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, *, epi: int = EPI_BF16, out: Optional[torch.Tensor] = None,
          bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
-         aux: Optional[torch.Tensor] = None, alpha: float = 1.0, k: Optional[int] = None) -> torch.Tensor:
+         aux: Optional[torch.Tensor] = None, alpha: float = 1.0, k: Optional[int] = None,
+         rope: Optional[tuple] = None) -> torch.Tensor:
     """out = epilogue(a @ b.T);  a [M,K] bf16, b [N,K] bf16 (both row-major, K contiguous)."""
     lib = load()
     require_cuda(a, b)
@@ -176,7 +178,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, epi: int = EPI_BF16, out: Optional
             out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
     e = GemmEpilogue(ptr(out), out.stride(0), ptr(bias), ptr(resid), resid.stride(0) if resid is not None else 0,
                      ptr(out2), out2.stride(0) if out2 is not None else 0, ptr(aux),
-                     aux.stride(0) if aux is not None else 0, alpha)
+                     aux.stride(0) if aux is not None else 0, alpha,
+                     ptr(rope[0]) if rope else None, ptr(rope[1]) if rope else None, rope[2] if rope else 0, rope[3] if rope else 0)
     check(lib.ta_gemm_bf16(ptr(a), a.stride(0), ptr(b), b.stride(0), M, N, K, epi, C.byref(e), stream_ptr()))
     return out
 
