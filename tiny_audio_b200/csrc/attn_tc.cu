@@ -17,14 +17,22 @@
 
 namespace {
 
-constexpr int HD = 64;
 constexpr int BQ = 128, BKV = 128;
-constexpr int TILE_BYTES = 128 * 64 * 2;   // every smem tile here is 128 rows x 128 B
+constexpr int TILE16 = 128 * 64 * 2;       // one [128 rows x 64 bf16] SWIZZLE_128B sub-tile
 constexpr int KV_SLOTS = 3;
-constexpr int ATT_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: softmax (2 threads per row)
-constexpr int SMEM_ATT = TILE_BYTES * (1 + KV_SLOTS + 2) + 256 + 3 * 1024 + 1024;   // tiles + barriers + exchange floats + align
+constexpr int ATT_THREADS = 384;           // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: softmax (2 threads per row)
 constexpr int TMEM_COLS_ATT = 256;
 constexpr uint32_t S_COL = 0, O_COL = 128;
+
+template <int HD>
+struct AttCfg {
+    static constexpr int NSUB = HD / 64;
+    static constexpr int TILE_BYTES = NSUB * TILE16;                  // Q, K or V tile: 128 rows x HD
+    static constexpr int P_BYTES = 2 * TILE16;                        // P: 128 x 128 bf16
+    static constexpr int BAR_OFF = TILE_BYTES * (1 + KV_SLOTS) + P_BYTES;
+    static constexpr int SMEM = BAR_OFF + 256 + 3 * 1024 + 1024;      // + barriers + exchange floats + 1 KB alignment slack
+    static constexpr int CTAS_PER_SM = (HD == 64) ? 2 : 1;
+};
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -44,7 +52,8 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// MN-major SWIZZLE_128B operand (rows = K index, 64 bf16 = 128 B of the MN index per row; 8-row groups 1024 B apart)
+// MN-major SWIZZLE_128B operand (rows = K index, 64 bf16 = 128 B of the MN index per row; 8-row groups 1024 B apart;
+// further 64-wide MN atoms `lbo_bytes` apart)
 __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
@@ -55,17 +64,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
     return d;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(ATT_THREADS, AttCfg<HD>::CTAS_PER_SM)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int H,
+                   const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int Hq, int Hkv,
                    long long o_rs, float scale_log2) {
+    using C = AttCfg<HD>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* sQ = smem;
-    uint8_t* sKV = smem + TILE_BYTES;
-    uint8_t* sP = smem + TILE_BYTES * (1 + KV_SLOTS);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TILE_BYTES * (1 + KV_SLOTS + 2));
+    uint8_t* sKV = smem + C::TILE_BYTES;
+    uint8_t* sP = smem + C::TILE_BYTES * (1 + KV_SLOTS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;
     uint64_t* kv_empty = bars + 1 + KV_SLOTS;
@@ -74,12 +85,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint64_t* p_full = s_full + 2;
     uint64_t* pv_done = s_full + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
-    float* sXch = reinterpret_cast<float*>(smem + TILE_BYTES * (1 + KV_SLOTS + 2) + 256);   // [3][2][128] max (x2) / sum exchange
+    float* sXch = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);   // [3][2][128]: row max (double buffered) / row sum exchange
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int hk = h / (Hq / Hkv);
     const int q0 = qt * BQ;
-    const int n_kv = (S + BKV - 1) / BKV;
+    const int n_kv_all = (S + BKV - 1) / BKV;
+    const int n_kv = CAUSAL ? min(n_kv_all, qt + 1) : n_kv_all;
     const int row_base = b * S;
 
     if (warp == 0 && lane == 0) {
@@ -105,21 +118,23 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, TILE_BYTES);
-            tma_load_2d(sQ, &tmQ, q_full, h * HD, row_base + q0);
+    if (warp < 4) {
+        if (warp == 0 && lane == 0) {
+            mbar_arrive_expect_tx(q_full, C::TILE_BYTES);
+#pragma unroll
+            for (int u = 0; u < C::NSUB; ++u) tma_load_2d(sQ + u * TILE16, &tmQ, q_full, h * HD + u * 64, row_base + q0);
             for (int i = 0; i < 2 * n_kv; ++i) {
                 const int slot = i % KV_SLOTS;
                 const uint32_t ph = (uint32_t)(i / KV_SLOTS) & 1u;
                 mbar_wait(&kv_empty[slot], ph ^ 1);
-                mbar_arrive_expect_tx(&kv_full[slot], TILE_BYTES);
+                mbar_arrive_expect_tx(&kv_full[slot], C::TILE_BYTES);
                 const int j = i >> 1;
-                tma_load_2d(sKV + slot * TILE_BYTES, (i & 1) ? &tmV : &tmK, &kv_full[slot], h * HD, row_base + j * BKV);
+#pragma unroll
+                for (int u = 0; u < C::NSUB; ++u)
+                    tma_load_2d(sKV + slot * C::TILE_BYTES + u * TILE16, (i & 1) ? &tmV : &tmK, &kv_full[slot], hk * HD + u * 64,
+                                row_base + j * BKV);
             }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
+        } else if (warp == 1 && lane == 0) {
             constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
             constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
             const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
@@ -128,11 +143,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_wait(&kv_full[slot], (uint32_t)(i / KV_SLOTS) & 1u);
                 mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t k_addr = smem_u32(sKV + slot * TILE_BYTES);
+                const uint32_t k_addr = smem_u32(sKV + slot * C::TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    umma_f16(tmem_base + S_COL, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(k_addr + k * 32),
-                             idesc_s, k != 0 ? 1u : 0u);
+                for (int k = 0; k < HD / 16; ++k) {
+                    const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
+                    umma_f16(tmem_base + S_COL, umma_desc_sw128_kmajor(q_addr + off), umma_desc_sw128_kmajor(k_addr + off), idesc_s,
+                             k != 0 ? 1u : 0u);
+                }
                 umma_commit(s_full);
                 umma_commit(&kv_empty[slot]);
             };
@@ -144,55 +161,61 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_wait(p_full, (uint32_t)j & 1u);
                 mbar_wait(&kv_full[slot], (uint32_t)(i / KV_SLOTS) & 1u);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(sKV + slot * TILE_BYTES);
+                const uint32_t v_addr = smem_u32(sKV + slot * C::TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < BKV / 16; ++k) {
-                    const uint32_t pa = p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32;
-                    umma_f16(tmem_base + O_COL, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE_BYTES),
-                             idesc_o, (j | k) != 0 ? 1u : 0u);
+                    const uint32_t pa = p_addr + (k >> 2) * TILE16 + (k & 3) * 32;
+                    umma_f16(tmem_base + O_COL, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16), idesc_o,
+                             (j | k) != 0 ? 1u : 0u);
                 }
                 umma_commit(pv_done);
                 umma_commit(&kv_empty[slot]);
             }
         }
-    } else if (warp >= 4) {
+    } else {
         // two threads per query row: warp (4+q) and warp (8+q) share TMEM lane quadrant q and split the columns
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         const int r = q * 32 + lane;
+        constexpr int OW = HD / 2;                   // O columns owned by this thread
         const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + S_COL + (uint32_t)(half * 64);
-        const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + O_COL + (uint32_t)(half * 32);
+        const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + O_COL + (uint32_t)(half * OW);
         float m_ref = -INFINITY, l_sum = 0.f;
-        uint8_t* p_row = sP + half * TILE_BYTES + r * 128;
+        uint8_t* p_row = sP + half * TILE16 + r * 128;
         const uint32_t bar_id = 1 + q;
         for (int j = 0; j < n_kv; ++j) {
             mbar_wait(s_full, (uint32_t)j & 1u);
             tc_fence_after();
-            const bool tail = (j == n_kv - 1) && (S % BKV != 0);
-            const int valid = S - j * BKV - half * 64;      // my columns < valid are real keys
-            // ---- pass A: row max over my 64 columns, then combine with the partner thread ----
-            float mx;
-            {
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(t_s, v0);
-                tmem_ld_32x32(t_s + 32, v1);
-                tmem_ld_wait();
-                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                if (tail) {
+            // my columns e = 0..63 are real (unmasked) keys iff e <= lim
+            int lim = S - j * BKV - half * 64 - 1;
+            if (CAUSAL && j == qt) lim = min(lim, r - half * 64);
+            lim = min(lim, 63);
+            const bool full_tile = __all_sync(0xffffffffu, lim >= 63);
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(t_s, v0);
+            tmem_ld_32x32(t_s + 32, v1);
+            tmem_ld_wait();
+            // S now lives in registers: release its TMEM columns so the MMA warp can issue S_{j+1} during this softmax
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (full_tile) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v0[i]));
-                        if (32 + i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v1[i]));
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v0[i]));
-                        m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v1[i]));
-                    }
+                for (int i = 0; i < 32; ++i) {
+                    m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v0[i]));
+                    m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v1[i]));
                 }
-                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i > lim) v0[i] = 0xff800000u;          // -inf
+                    if (32 + i > lim) v1[i] = 0xff800000u;
+                    m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v0[i]));
+                    m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v1[i]));
+                }
             }
+            float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             float* xch = sXch + (j & 1) * 256;
             xch[half * 128 + r] = mx;
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
@@ -204,57 +227,51 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (j > 0) {
                 mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);     // PV_{j-1} has consumed sP and finished updating O
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, grow)) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_o, v);
+            }
+            // ---- P = exp2(S * scale - m_ref) -> bf16 -> swizzled smem (my 64 columns = sub-tile `half`) ----
+            float l4[4] = {0.f, 0.f, 0.f, 0.f};
+            const float neg_m = -m_ref;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    float e[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const float x = __uint_as_float(c ? v1[8 * qd + t] : v0[8 * qd + t]);
+                        e[t] = ex2_approx(fmaf(x, scale_log2, neg_m));     // exp2(-inf) = 0 for masked columns
+                        l4[t & 3] += e[t];
+                    }
+                    uint4 u;
+                    u.x = pack_bf16x2(e[0], e[1]);
+                    u.y = pack_bf16x2(e[2], e[3]);
+                    u.z = pack_bf16x2(e[4], e[5]);
+                    u.w = pack_bf16x2(e[6], e[7]);
+                    const int k16 = c * 4 + qd;
+                    *reinterpret_cast<uint4*>(p_row + ((k16 ^ (r & 7)) << 4)) = u;
+                }
+            }
+            // lazy rescale of O (rare): done after the exp phase so that S's registers are dead by now
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+                for (int c = 0; c < OW / 32; ++c) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(t_o + c * 32, o);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                    tmem_st_32x32(t_o, v);
-                    tmem_st_wait();
-                    l_sum *= alpha;
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st_32x32(t_o + c * 32, o);
                 }
+                tmem_st_wait();
+                l_sum *= alpha;
             }
-            // ---- pass B: P = exp2(S * scale - m_ref) -> bf16 -> swizzled smem (my 64 columns = sub-tile `half`) ----
-            {
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(t_s, v0);
-                tmem_ld_32x32(t_s + 32, v1);
-                tmem_ld_wait();
-                float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    float p[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float x = __uint_as_float(c ? v1[i] : v0[i]);
-                        float e = ex2_approx(fmaf(x, scale_log2, -m_ref));
-                        if (tail && (c * 32 + i >= valid)) e = 0.f;
-                        p[i] = e;
-                        l4[i & 3] += e;
-                    }
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        uint4 u;
-                        u.x = pack_bf16x2(p[8 * qd + 0], p[8 * qd + 1]);
-                        u.y = pack_bf16x2(p[8 * qd + 2], p[8 * qd + 3]);
-                        u.z = pack_bf16x2(p[8 * qd + 4], p[8 * qd + 5]);
-                        u.w = pack_bf16x2(p[8 * qd + 6], p[8 * qd + 7]);
-                        const int k16 = c * 4 + qd;
-                        *reinterpret_cast<uint4*>(p_row + ((k16 ^ (r & 7)) << 4)) = u;
-                    }
-                }
-                l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-            }
+            l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(s_empty);
-                mbar_arrive(p_full);
-            }
+            if (lane == 0) mbar_arrive(p_full);
         }
-        // ---- epilogue: O / l -> bf16 (my 32 of the 64 head dims) ----
+        // ---- epilogue: O / l -> bf16 (my OW of the HD head dims) ----
         float* xch = sXch + 512;
         xch[half * 128 + r] = l_sum;
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
@@ -263,10 +280,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
         const int row = q0 + r;
         const float inv = 1.0f / l_sum;
-        bf16* orow = O + ((long long)row_base + row) * o_rs + (long long)h * HD + half * 32;
-        {
+        bf16* orow = O + ((long long)row_base + row) * o_rs + (long long)h * HD + half * OW;
+#pragma unroll 1
+        for (int c = 0; c < OW / 32; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32(t_o, v);
+            tmem_ld_32x32(t_o + c * 32, v);
             tmem_ld_wait();
             if (row < S) {
 #pragma unroll
@@ -276,17 +294,34 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     u.y = pack_bf16x2(__uint_as_float(v[8 * qd + 2]) * inv, __uint_as_float(v[8 * qd + 3]) * inv);
                     u.z = pack_bf16x2(__uint_as_float(v[8 * qd + 4]) * inv, __uint_as_float(v[8 * qd + 5]) * inv);
                     u.w = pack_bf16x2(__uint_as_float(v[8 * qd + 6]) * inv, __uint_as_float(v[8 * qd + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + qd * 8) = u;
+                    *reinterpret_cast<uint4*>(orow + c * 32 + qd * 8) = u;
                 }
             }
         }
-        if (LSE && half == 0 && row < S) LSE[((long long)b * H + h) * S + row] = (m_ref + log2f(l_sum)) * 0.69314718055994531f;
+        if (LSE && half == 0 && row < S) LSE[((long long)b * Hq + h) * S + row] = (m_ref + log2f(l_sum)) * 0.69314718055994531f;
         tc_fence_before();
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<TMEM_COLS_ATT>(tmem_base);
+}
+
+template <int HD, bool CAUSAL>
+int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* o, float* lse, int B, int S, int Hq,
+                   int Hkv, long long o_rs, float scale, cudaStream_t st) {
+    using C = AttCfg<HD>;
+    auto kern = attn_tc_fwd_kernel<HD, CAUSAL>;
+    static bool done = false;
+    if (!done) {
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        done = true;
+    }
+    dim3 grid((S + BQ - 1) / BQ, Hq, B);
+    kern<<<grid, ATT_THREADS, C::SMEM, st>>>(tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f);
+    TA_LAUNCH_CHECK();
+    return 0;
 }
 
 int g_attn_tc = 1;
@@ -298,32 +333,28 @@ TA_API int ta_attn_set_tc(int on) {
     return 0;
 }
 
-// internal: returns 1 if this shape is handled by the tcgen05 kernel (and launches it), 0 if the caller should use mma.sync
+// internal: *handled = 1 if this shape runs on the tcgen05 kernel (and was launched), 0 if the caller should use mma.sync
 int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* lse, int B, int S, int Hq, int Hkv, int head_dim,
                   long long q_rs, long long k_rs, long long v_rs, long long o_rs, int causal, float scale, cudaStream_t st,
                   int* handled) {
     *handled = 0;
-    if (!g_attn_tc || head_dim != 64 || causal || Hq != Hkv || S < 1) return 0;
+    if (!g_attn_tc || (head_dim != 64 && head_dim != 128) || S < 1 || Hq % Hkv != 0) return 0;
     if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
          reinterpret_cast<uintptr_t>(o)) & 15)
         return 0;
     CUtensorMap tq, tk, tv;
     const long long rows = (long long)B * S;
-    int rc = k_make_tensor_map_2d(&tq, q, rows, (long long)Hq * HD, q_rs, BQ);
+    int rc = k_make_tensor_map_2d(&tq, q, rows, (long long)Hq * head_dim, q_rs, BQ);
     if (rc) return rc;
-    rc = k_make_tensor_map_2d(&tk, k, rows, (long long)Hkv * HD, k_rs, BKV);
+    rc = k_make_tensor_map_2d(&tk, k, rows, (long long)Hkv * head_dim, k_rs, BKV);
     if (rc) return rc;
-    rc = k_make_tensor_map_2d(&tv, v, rows, (long long)Hkv * HD, v_rs, BKV);
+    rc = k_make_tensor_map_2d(&tv, v, rows, (long long)Hkv * head_dim, v_rs, BKV);
     if (rc) return rc;
-    static bool done = false;
-    if (!done) {
-        TA_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
-        TA_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        done = true;
-    }
-    dim3 grid((S + BQ - 1) / BQ, Hq, B);
-    attn_tc_fwd_kernel<<<grid, ATT_THREADS, SMEM_ATT, st>>>(tq, tk, tv, o, lse, S, Hq, o_rs, scale * 1.4426950408889634f);
-    TA_LAUNCH_CHECK();
     *handled = 1;
-    return 0;
+    if (head_dim == 64) {
+        if (causal) return launch_attn_tc<64, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+        return launch_attn_tc<64, false>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+    }
+    if (causal) return launch_attn_tc<128, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+    return launch_attn_tc<128, false>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
 }

@@ -46,7 +46,7 @@ struct Cfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
 };
 
 struct EpiArgs {
@@ -105,7 +105,8 @@ __device__ __forceinline__ void load_f32x32(const float* src, float (&v)[32]) {
 // One accumulator tile (this thread's TMEM lane = one output row, BN columns starting at tile_col0) -> global memory
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, long long row, bool row_ok, long long tile_col0, const EpiArgs& ep,
-                                              int grp /* 0 / 1: which half of the tile's columns this warp group owns */) {
+                                              int grp /* 0 / 1: which half of the tile's columns this warp group owns */,
+                                              const float* s_bias /* smem: bias of this tile's BN columns */) {
     if constexpr (EPI == TA_EPI_SWIGLU) {
         // tile columns come in 128-wide groups: [64 gate | 64 up] (weights interleaved by the host)
         const int sb_lo = (BN == 256) ? grp : 0, sb_hi = (BN == 256) ? grp + 1 : 1;
@@ -140,10 +141,35 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, long long row, boo
             }
         }
     } else {
+        // operands read from global memory (residual / SwiGLU stash) are prefetched one chunk ahead as raw 16-byte vectors
+        constexpr int NRAW = (EPI == TA_EPI_F32_RESID || EPI == TA_EPI_SWIGLU_BWD) ? 8 : (EPI == TA_EPI_BF16_RESID) ? 4 : 1;
+        uint4 cur[NRAW], nxt[NRAW];
+        auto prefetch = [&](int c, uint4 (&dst)[NRAW]) {
+            if constexpr (EPI == TA_EPI_BF16_RESID || EPI == TA_EPI_F32_RESID || EPI == TA_EPI_SWIGLU_BWD) {
+                if (!row_ok) return;
+                const long long col = tile_col0 + c * 32;
+                if constexpr (EPI == TA_EPI_BF16_RESID) {
+                    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.resid) + row * ep.ldr + col);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = p[i];
+                } else if constexpr (EPI == TA_EPI_F32_RESID) {
+                    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(ep.resid) + row * ep.ldr + col);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = p[i];
+                } else {
+                    const uint4* p = reinterpret_cast<const uint4*>(ep.aux + row * ep.ldaux + (col / 64) * 128 + (col % 64));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { dst[i] = p[i]; dst[4 + i] = p[8 + i]; }   // gate chunk, up chunk (+64 elements)
+                }
+            }
+        };
+        const int c_lo = grp * (BN / 64), c_hi = (grp + 1) * (BN / 64);
+        prefetch(c_lo, cur);
 #pragma unroll 1
-        for (int c = grp * (BN / 64); c < (grp + 1) * (BN / 64); ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
             uint32_t r[32];
             tmem_ld_32x32(taddr + c * 32, r);
+            if (c + 1 < c_hi) prefetch(c + 1, nxt);
             tmem_ld_wait();
             __syncwarp();
             if (row_ok) {
@@ -152,11 +178,13 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, long long row, boo
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
             if constexpr (EPI != TA_EPI_F32 && EPI != TA_EPI_SWIGLU_BWD) {
-                if (ep.bias) {
-                    float b[32];
-                    load_f32x32(ep.bias + col, b);
+                if (ep.bias) {   // staged in shared memory once per tile by the epilogue warps
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 32);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += b[i];
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = b4[i];
+                        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                    }
                 }
             }
             if constexpr (EPI == TA_EPI_BF16_ROPE) {
@@ -188,16 +216,24 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, long long row, boo
                 for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(bf16_round(v[i]));
                 store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
             } else if constexpr (EPI == TA_EPI_BF16_RESID) {
-                float rs[32];
-                load_bf16x32(reinterpret_cast<const bf16*>(ep.resid) + row * ep.ldr + col, rs);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = rs[i] + bf16_round(v[i]);
+                for (int i = 0; i < 4; ++i) {
+                    const float2 a = unpack_bf16x2(cur[i].x), b = unpack_bf16x2(cur[i].y), cc = unpack_bf16x2(cur[i].z),
+                                 d = unpack_bf16x2(cur[i].w);
+                    v[8 * i + 0] = a.x + bf16_round(v[8 * i + 0]); v[8 * i + 1] = a.y + bf16_round(v[8 * i + 1]);
+                    v[8 * i + 2] = b.x + bf16_round(v[8 * i + 2]); v[8 * i + 3] = b.y + bf16_round(v[8 * i + 3]);
+                    v[8 * i + 4] = cc.x + bf16_round(v[8 * i + 4]); v[8 * i + 5] = cc.y + bf16_round(v[8 * i + 5]);
+                    v[8 * i + 6] = d.x + bf16_round(v[8 * i + 6]); v[8 * i + 7] = d.y + bf16_round(v[8 * i + 7]);
+                }
                 store_bf16x32(reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + col, v);
             } else if constexpr (EPI == TA_EPI_F32_RESID) {
-                float rs[32];
-                load_f32x32(reinterpret_cast<const float*>(ep.resid) + row * ep.ldr + col, rs);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = rs[i] + bf16_round(v[i]);
+                for (int i = 0; i < 8; ++i) {
+                    v[4 * i + 0] = __uint_as_float(cur[i].x) + bf16_round(v[4 * i + 0]);
+                    v[4 * i + 1] = __uint_as_float(cur[i].y) + bf16_round(v[4 * i + 1]);
+                    v[4 * i + 2] = __uint_as_float(cur[i].z) + bf16_round(v[4 * i + 2]);
+                    v[4 * i + 3] = __uint_as_float(cur[i].w) + bf16_round(v[4 * i + 3]);
+                }
                 store_f32x32(reinterpret_cast<float*>(ep.out) + row * ep.ldo + col, v);
             } else if constexpr (EPI == TA_EPI_F32) {
 #pragma unroll
@@ -206,23 +242,35 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, long long row, boo
             } else if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
                 // v = d(h) for h columns [col, col+32); the stash holds (gate, up) interleaved in 64-blocks
                 const long long jb = col / 64, jo = col % 64;
-                const bf16* gu = ep.aux + row * ep.ldaux + jb * 128 + jo;
-                float g[32], u[32], dg[32], du[32];
-                load_bf16x32(gu, g);
-                load_bf16x32(gu + 64, u);
+                float dg[32], du[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float dh = bf16_round(v[i]);
-                    const float sg = sigmoidf_(g[i]);
-                    const float silu = bf16_round(g[i] * sg);
-                    du[i] = dh * silu;
-                    dg[i] = dh * u[i] * (sg * (1.0f + g[i] * (1.0f - sg)));
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t gw[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+                    const uint32_t uw[4] = {cur[4 + i].x, cur[4 + i].y, cur[4 + i].z, cur[4 + i].w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 g2 = unpack_bf16x2(gw[t]), u2 = unpack_bf16x2(uw[t]);
+                        const float gq[2] = {g2.x, g2.y}, uq[2] = {u2.x, u2.y};
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int k = 8 * i + 2 * t + e;
+                            const float dh = bf16_round(v[k]);
+                            const float sg = sigmoidf_(gq[e]);
+                            const float silu = bf16_round(gq[e] * sg);
+                            du[k] = dh * silu;
+                            dg[k] = dh * uq[e] * (sg * (1.0f + gq[e] * (1.0f - sg)));
+                        }
+                    }
                 }
                 bf16* o = reinterpret_cast<bf16*>(ep.out) + row * ep.ldo + jb * 128 + jo;
                 store_bf16x32(o, dg);
                 store_bf16x32(o + 64, du);
             }
             }   // row_ok
+            if (c + 1 < c_hi) {
+#pragma unroll
+                for (int i = 0; i < NRAW; ++i) cur[i] = nxt[i];
+            }
             __syncwarp();
         }
     }
@@ -244,6 +292,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* tfull = bars + 2 * C::STAGES;
     uint64_t* tempty = bars + 2 * C::STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    float* s_bias_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [2][BN]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -323,17 +372,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;   // TMEM lane quadrant this warp may touch
+        int tile_iter = 0;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
+            if (ep.bias) {   // stage this tile's bias (BN floats) in shared memory; double buffered across tiles
+                float* sb = s_bias_all + (tile_iter & 1) * BN;
+                const int e_tid = (warp - 4) * 32 + lane;
+                if (e_tid < BN) sb[e_tid] = ep.bias[(long long)n_blk * BN + e_tid];
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            const float* s_bias = s_bias_all + (tile_iter & 1) * BN;
+            ++tile_iter;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const long long row = (long long)m_blk * BM + q * 32 + lane;
             const bool row_ok = row < M;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 
-            epilogue_tile<BN, EPI>(taddr, row, row_ok, (long long)n_blk * BN, ep, (warp - 4) >> 2);
+            epilogue_tile<BN, EPI>(taddr, row, row_ok, (long long)n_blk * BN, ep, (warp - 4) >> 2, s_bias);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
@@ -413,7 +471,7 @@ struct Cfg2 {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 6 : 8;
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2 * BN * 4;
 };
 
 template <int BN, int EPI>
@@ -431,6 +489,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint64_t* tfull = bars + 2 * C::STAGES;
     uint64_t* tempty = bars + 2 * C::STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    float* s_bias_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [2][BN]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -516,16 +575,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs, their own 128 rows) =====================
         const int q = warp & 3;
+        int tile_iter = 0;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = pair; tile < num_tiles; tile += n_pairs) {
             const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
+            if (ep.bias) {   // stage this tile's bias (BN floats) in shared memory; double buffered across tiles
+                float* sb = s_bias_all + (tile_iter & 1) * BN;
+                const int e_tid = (warp - 4) * 32 + lane;
+                if (e_tid < BN) sb[e_tid] = ep.bias[(long long)n_blk * BN + e_tid];
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            const float* s_bias = s_bias_all + (tile_iter & 1) * BN;
+            ++tile_iter;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const long long row = (long long)m_blk * 2 * BM + (long long)rank * BM + q * 32 + lane;
             const bool row_ok = row < M;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            epilogue_tile<BN, EPI>(taddr, row, row_ok, (long long)n_blk * BN, ep, (warp - 4) >> 2);
+            epilogue_tile<BN, EPI>(taddr, row, row_ok, (long long)n_blk * BN, ep, (warp - 4) >> 2, s_bias);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty[as]);

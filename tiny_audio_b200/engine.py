@@ -134,7 +134,7 @@ class PackedLM:
             return t
 
         V, D, F = d.vocab, d.lm_dim, d.lm_ffn
-        self.vocab_pad = _round_up(V, 128)
+        self.vocab_pad = _round_up(V, 256)      # 256: lets the lm_head GEMMs use the 256-wide tile
         emb = sd["model.embed_tokens.weight"]
         assert emb.shape[0] == V, f"embedding rows {emb.shape[0]} != vocab {V}"
         self.embed_f32 = dev(emb, F32)
