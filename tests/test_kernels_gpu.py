@@ -170,9 +170,11 @@ def test_attn_fwd(cuda, B, S, Hq, Hkv, hd, causal, tc):
     assert e < 1e-2 and max_err(lse, lref) < 2e-3
 
 
-@pytest.mark.parametrize("B,S,Hq,Hkv", [(2, 77, 4, 2), (2, 464, 16, 8), (1, 130, 2, 2)])
-def test_attn_bwd(cuda, B, S, Hq, Hkv):
+@pytest.mark.parametrize("tc", [1, 0])
+@pytest.mark.parametrize("B,S,Hq,Hkv", [(2, 77, 4, 2), (2, 464, 16, 8), (1, 130, 2, 2), (2, 256, 2, 1), (1, 300, 4, 4)])
+def test_attn_bwd(cuda, B, S, Hq, Hkv, tc):
     lib = L.load()
+    L.check(lib.ta_attn_set_tc(tc))
     hd = 128
     scale = hd ** -0.5
     q, k, v = rnd(B, S, Hq, hd, seed=1), rnd(B, S, Hkv, hd, seed=2), rnd(B, S, Hkv, hd, seed=3)
@@ -193,7 +195,8 @@ def test_attn_bwd(cuda, B, S, Hq, Hkv):
     (oref * do.float()).sum().backward()
     torch.cuda.synchronize()
     e = [rel_err(dq.view_as(q), qf.grad), rel_err(dk.view_as(k), kf.grad), rel_err(dv.view_as(v), vf.grad)]
-    print(f"attn bwd S={S}: rel dq {e[0]:.3e} dk {e[1]:.3e} dv {e[2]:.3e}")
+    L.check(lib.ta_attn_set_tc(1))
+    print(f"attn bwd S={S} tc={tc}: rel dq {e[0]:.3e} dk {e[1]:.3e} dv {e[2]:.3e}")
     assert max(e) < 2e-2
 
 

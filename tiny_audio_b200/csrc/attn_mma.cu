@@ -492,6 +492,14 @@ TA_API int ta_attn_bwd(const void* q, const void* k, const void* v, const void* 
         TA_LAUNCH_CHECK();
     }
     TA_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)B * S * dq_rs, st));
+    if (k_attn_tc_enabled()) {   // tcgen05 kernel (attn_tc_bwd.cu); the mma.sync kernel below stays as A/B reference
+        int handled = 0;
+        const int rc = k_attn_tc_bwd((const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)d_o, lse, dsum_ws, dq_acc, (bf16*)dk,
+                                     (bf16*)dv, B, S, Hq, Hkv, head_dim, q_rs, k_rs, v_rs, do_rs, dq_rs, dk_rs, dv_rs, causal, scale, st,
+                                     &handled);
+        if (rc) return rc;
+        if (handled) return 0;
+    }
     const int smem = 4 * TILE * HD * 2 + TILE * TILE * 2 + 2 * TILE * 4;
     dim3 grid((S + TILE - 1) / TILE, Hkv, B);
     const float sl2 = scale * 1.4426950408889634f;

@@ -332,6 +332,7 @@ TA_API int ta_attn_set_tc(int on) {
     g_attn_tc = on ? 1 : 0;
     return 0;
 }
+int k_attn_tc_enabled() { return g_attn_tc; }
 
 // internal: *handled = 1 if this shape runs on the tcgen05 kernel (and was launched), 0 if the caller should use mma.sync
 int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* lse, int B, int S, int Hq, int Hkv, int head_dim,

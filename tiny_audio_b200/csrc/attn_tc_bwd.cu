@@ -1,0 +1,324 @@
+// tcgen05 flash-attention BACKWARD for the Qwen3 decoder shape: head_dim 128, causal, GQA (16 q / 8 kv heads)
+// (autograd of HF:models/qwen3/modeling_qwen3.py:273-291 through HF:integrations/sdpa_attention.py).
+// Successor of attn_bwd_kernel<128,true> (mma.sync, legacy tensor path).
+//
+// One CTA = one (batch, kv head, 128-key tile); it keeps K and V in shared memory and dK, dV in TMEM, and loops over
+// the q heads of the group and the query tiles at or below the diagonal.  Per iteration, five 128x128x128 UMMAs:
+//     S^T  = K  Q^T         (TMEM cols   0..127)           dP^T = V  dO^T        (cols 128..255)
+//     -- softmax-backward warps: P^T = exp2(S^T c - lse_q), dS^T = P^T (dP^T - D_q) -> bf16 -> smem --
+//     dV  += P^T  dO        (cols 256..383)                dK  += dS^T Q         (cols 384..511)
+//     dQ   = dS   K         (reuses cols 0..127; A = dS^T read as an MN-major operand, B = K MN-major)
+// dQ tiles are scaled and added to the fp32 dQ buffer with vector reductions (several CTAs contribute to a q tile);
+// dK (scaled) and dV are written once as bf16 at the end.  All operand tiles are [128 rows x 64 bf16] SWIZZLE_128B
+// sub-tiles; "MN-major" operands are the same tiles consumed through the transposing descriptor form.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tinyaudio_b200.h"
+
+namespace {
+
+constexpr int HD = 128;
+constexpr int BT = 128;                    // q tile = kv tile = 128
+constexpr int TILE16 = 128 * 64 * 2;       // one [128 x 64] bf16 sub-tile
+constexpr int TILE = 2 * TILE16;           // [128 x 128] bf16
+constexpr int BWD_THREADS = 384;
+constexpr int BAR_OFF = 6 * TILE;          // sK sV sQ sdO sP sdS
+constexpr int SMEM_BWD = BAR_OFF + 256 + 4 * 128 * 4 + 1024;   // + barriers + (lse, D) double buffered + align slack
+constexpr uint32_t ST_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 384;
+
+__device__ __forceinline__ float ex2_approx_b(float x) {
+    float y;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return umma_desc_sw128_kmajor(addr); }
+__device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr) {   // MN-major, 64-wide MN atoms TILE16 apart
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((TILE16 >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                   const float* __restrict__ LSE, const float* __restrict__ Dsum, float* __restrict__ dQacc,
+                   bf16* __restrict__ dK, bf16* __restrict__ dV, int S, int Hq, int Hkv, long long dq_rs, long long dk_rs,
+                   long long dv_rs, float scale, float scale_log2) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    uint8_t* sK = smem;
+    uint8_t* sV = smem + TILE;
+    uint8_t* sQ = smem + 2 * TILE;
+    uint8_t* sdO = smem + 3 * TILE;
+    uint8_t* sP = smem + 4 * TILE;
+    uint8_t* sdS = smem + 5 * TILE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+    uint64_t* kv_full = bars;
+    uint64_t* qdo_full = bars + 1;
+    uint64_t* qdo_empty = bars + 2;
+    uint64_t* s_full = bars + 3;
+    uint64_t* pds_full = bars + 4;
+    uint64_t* dq_full = bars + 5;
+    uint64_t* dq_empty = bars + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* sVec = reinterpret_cast<float*>(smem + BAR_OFF + 256);   // [2 buffers][lse*log2e (128) | D (128)]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+    const int G = Hq / Hkv;
+    const int kv0 = kt * BT;
+    const int n_q = (S + BT - 1) / BT;
+    const int n_it = G * (n_q - kt);                 // causal: query tiles qt >= kt
+    const int row_base = b * S;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        tma_prefetch_desc(&tmdO);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(kv_full, 1);
+        mbar_init(qdo_full, 1);
+        mbar_init(qdo_empty, 1);
+        mbar_init(s_full, 1);
+        mbar_init(pds_full, 8);
+        mbar_init(dq_full, 1);
+        mbar_init(dq_empty, 8);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(kv_full, 2 * TILE);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                tma_load_2d(sK + u * TILE16, &tmK, kv_full, hk * HD + u * 64, row_base + kv0);
+                tma_load_2d(sV + u * TILE16, &tmV, kv_full, hk * HD + u * 64, row_base + kv0);
+            }
+            for (int it = 0; it < n_it; ++it) {
+                const int g = it / (n_q - kt), qt = kt + it % (n_q - kt);
+                const int h = hk * G + g;
+                mbar_wait(qdo_empty, ((uint32_t)it & 1u) ^ 1u);
+                mbar_arrive_expect_tx(qdo_full, 2 * TILE);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    tma_load_2d(sQ + u * TILE16, &tmQ, qdo_full, h * HD + u * 64, row_base + qt * BT);
+                    tma_load_2d(sdO + u * TILE16, &tmdO, qdo_full, h * HD + u * 64, row_base + qt * BT);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t id_kk = umma_idesc_bf16(BT, BT);                              // A, B K-major
+            constexpr uint32_t id_kmn = umma_idesc_bf16(BT, HD) | (1u << 16);                // B MN-major
+            constexpr uint32_t id_mnmn = umma_idesc_bf16(BT, HD) | (1u << 15) | (1u << 16);  // A and B MN-major
+            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO), aP = smem_u32(sP),
+                           adS = smem_u32(sdS);
+            mbar_wait(kv_full, 0);
+            for (int it = 0; it < n_it; ++it) {
+                const uint32_t ph = (uint32_t)it & 1u;
+                mbar_wait(qdo_full, ph);
+                mbar_wait(dq_empty, ph ^ 1u);          // previous dQ tile has been read out of TMEM[0,128)
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
+                    umma_f16(tmem_base + ST_COL, desc_k(aK + off), desc_k(aQ + off), id_kk, k != 0 ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
+                    umma_f16(tmem_base + DP_COL, desc_k(aV + off), desc_k(adO + off), id_kk, k != 0 ? 1u : 0u);
+                }
+                umma_commit(s_full);
+                mbar_wait(pds_full, ph);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {      // contraction over the 128 queries, 16 per step
+                    const uint32_t offk = (k >> 2) * TILE16 + (k & 3) * 32;
+                    umma_f16(tmem_base + DV_COL, desc_k(aP + offk), desc_mn(adO + k * 2048), id_kmn, (it | k) != 0 ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t offk = (k >> 2) * TILE16 + (k & 3) * 32;
+                    umma_f16(tmem_base + DK_COL, desc_k(adS + offk), desc_mn(aQ + k * 2048), id_kmn, (it | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(qdo_empty);            // Q / dO tiles may be overwritten by the next iteration's TMA
+#pragma unroll
+                for (int k = 0; k < 8; ++k)        // contraction over the 128 keys
+                    umma_f16(tmem_base + ST_COL, desc_mn(adS + k * 2048), desc_mn(aK + k * 2048), id_mnmn, k != 0 ? 1u : 0u);
+                umma_commit(dq_full);
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int r = q * 32 + lane;                                   // my TMEM lane: key row (softmax) / query row (dQ)
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint8_t* p_row = sP + half * TILE16 + r * 128;
+        uint8_t* ds_row = sdS + half * TILE16 + r * 128;
+        for (int it = 0; it < n_it; ++it) {
+            const uint32_t ph = (uint32_t)it & 1u;
+            const int g = it / (n_q - kt), qt = kt + it % (n_q - kt);
+            const int h = hk * G + g;
+            const int q0 = qt * BT;
+            // per-query vectors of this tile (double buffered): lse * log2(e), D
+            float* vec = sVec + (it & 1) * 256;
+            if (half == 0) {
+                const int qi = q0 + r;
+                vec[r] = (qi < S) ? LSE[((long long)b * Hq + h) * S + qi] * 1.4426950408889634f : 0.f;
+            } else {
+                const int qi = q0 + r;
+                vec[128 + r] = (qi < S) ? Dsum[((long long)b * Hq + h) * S + qi] : 0.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(s_full, ph);
+            tc_fence_after();
+            // masks: element (kv = kv0 + r, query = q0 + col) is live iff kv < S, query < S, kv <= query
+            const int kv = kv0 + r;
+            const bool need_mask = (qt == kt) || (q0 + BT > S) || (kv0 + BT > S);
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t st[32], dp[32];
+                tmem_ld_32x32(lane_base + ST_COL + half * 64 + c * 32, st);
+                tmem_ld_32x32(lane_base + DP_COL + half * 64 + c * 32, dp);
+                tmem_ld_wait();
+                const float* lse_c = vec + half * 64 + c * 32;
+                const float* d_c = vec + 128 + half * 64 + c * 32;
+                float pv[32], dsv[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float p = ex2_approx_b(fmaf(__uint_as_float(st[i]), scale_log2, -lse_c[i]));
+                    if (need_mask) {
+                        const int qi = q0 + half * 64 + c * 32 + i;
+                        if (kv >= S || qi >= S || kv > qi) p = 0.f;
+                    }
+                    pv[i] = p;
+                    dsv[i] = p * (__uint_as_float(dp[i]) - d_c[i]);
+                }
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    uint4 u, w;
+                    u.x = pack_bf16x2(pv[8 * qd + 0], pv[8 * qd + 1]);
+                    u.y = pack_bf16x2(pv[8 * qd + 2], pv[8 * qd + 3]);
+                    u.z = pack_bf16x2(pv[8 * qd + 4], pv[8 * qd + 5]);
+                    u.w = pack_bf16x2(pv[8 * qd + 6], pv[8 * qd + 7]);
+                    w.x = pack_bf16x2(dsv[8 * qd + 0], dsv[8 * qd + 1]);
+                    w.y = pack_bf16x2(dsv[8 * qd + 2], dsv[8 * qd + 3]);
+                    w.z = pack_bf16x2(dsv[8 * qd + 4], dsv[8 * qd + 5]);
+                    w.w = pack_bf16x2(dsv[8 * qd + 6], dsv[8 * qd + 7]);
+                    const int off = (((c * 4 + qd) ^ (r & 7)) << 4);
+                    *reinterpret_cast<uint4*>(p_row + off) = u;
+                    *reinterpret_cast<uint4*>(ds_row + off) = w;
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pds_full);
+            // ---- dQ tile: rows = queries, my 64 of the 128 head dims ----
+            mbar_wait(dq_full, ph);
+            tc_fence_after();
+            {
+                const int qi = q0 + r;
+                float* dst = dQacc + ((long long)row_base + qi) * dq_rs + (long long)h * HD + half * 64;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(lane_base + ST_COL + half * 64 + c * 32, v);
+                    tmem_ld_wait();
+                    if (qi < S) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            red_add_v4(dst + c * 32 + 4 * i, __uint_as_float(v[4 * i]) * scale, __uint_as_float(v[4 * i + 1]) * scale,
+                                       __uint_as_float(v[4 * i + 2]) * scale, __uint_as_float(v[4 * i + 3]) * scale);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_empty);
+        }
+        // ---- epilogue: dV, dK (scaled) -> bf16; the last dq_full also covers every earlier UMMA ----
+        const int kv = kv0 + r;
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+            bf16* dst = (which ? dK : dV) + ((long long)row_base + kv) * (which ? dk_rs : dv_rs) + (long long)hk * HD + half * 64;
+            const float mul = which ? scale : 1.0f;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(lane_base + (which ? DK_COL : DV_COL) + half * 64 + c * 32, v);
+                tmem_ld_wait();
+                if (kv < S) {
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        uint4 u;
+                        u.x = pack_bf16x2(__uint_as_float(v[8 * qd + 0]) * mul, __uint_as_float(v[8 * qd + 1]) * mul);
+                        u.y = pack_bf16x2(__uint_as_float(v[8 * qd + 2]) * mul, __uint_as_float(v[8 * qd + 3]) * mul);
+                        u.z = pack_bf16x2(__uint_as_float(v[8 * qd + 4]) * mul, __uint_as_float(v[8 * qd + 5]) * mul);
+                        u.w = pack_bf16x2(__uint_as_float(v[8 * qd + 6]) * mul, __uint_as_float(v[8 * qd + 7]) * mul);
+                        *reinterpret_cast<uint4*>(dst + c * 32 + qd * 8) = u;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+// internal: tcgen05 backward for head_dim 128 + causal; *handled = 0 -> caller uses the mma.sync kernel.
+// dsum (rowsum(dO*O)) must already be computed and dq_acc zeroed by the caller.
+int k_attn_tc_bwd(const bf16* q, const bf16* k, const bf16* v, const bf16* d_o, const float* lse, const float* dsum, float* dq_acc,
+                  bf16* dk, bf16* dv, int B, int S, int Hq, int Hkv, int head_dim, long long q_rs, long long k_rs, long long v_rs,
+                  long long do_rs, long long dq_rs, long long dk_rs, long long dv_rs, int causal, float scale, cudaStream_t st,
+                  int* handled) {
+    *handled = 0;
+    if (head_dim != HD || !causal || Hq % Hkv != 0 || S < 1) return 0;
+    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+         reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(dq_acc) | reinterpret_cast<uintptr_t>(dk) |
+         reinterpret_cast<uintptr_t>(dv)) & 15)
+        return 0;
+    if ((dq_rs % 4) || (dk_rs % 8) || (dv_rs % 8)) return 0;
+    CUtensorMap tq, tk, tv, tdo;
+    const long long rows = (long long)B * S;
+    int rc = k_make_tensor_map_2d(&tq, q, rows, (long long)Hq * HD, q_rs, BT);
+    if (rc) return rc;
+    rc = k_make_tensor_map_2d(&tk, k, rows, (long long)Hkv * HD, k_rs, BT);
+    if (rc) return rc;
+    rc = k_make_tensor_map_2d(&tv, v, rows, (long long)Hkv * HD, v_rs, BT);
+    if (rc) return rc;
+    rc = k_make_tensor_map_2d(&tdo, d_o, rows, (long long)Hq * HD, do_rs, BT);
+    if (rc) return rc;
+    static bool done = false;
+    if (!done) {
+        TA_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
+        done = true;
+    }
+    dim3 grid((S + BT - 1) / BT, Hkv, B);
+    attn_tc_bwd_kernel<<<grid, BWD_THREADS, SMEM_BWD, st>>>(tq, tk, tv, tdo, lse, dsum, dq_acc, dk, dv, S, Hq, Hkv, dq_rs, dk_rs, dv_rs,
+                                                           scale, scale * 1.4426950408889634f);
+    TA_LAUNCH_CHECK();
+    *handled = 1;
+    return 0;
+}

@@ -35,3 +35,8 @@ int k_make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long
 int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* lse, int B, int S, int Hq, int Hkv, int head_dim,
                   long long q_rs, long long k_rs, long long v_rs, long long o_rs, int causal, float scale, cudaStream_t st,
                   int* handled);
+int k_attn_tc_enabled();
+int k_attn_tc_bwd(const bf16* q, const bf16* k, const bf16* v, const bf16* d_o, const float* lse, const float* dsum, float* dq_acc,
+                  bf16* dk, bf16* dv, int B, int S, int Hq, int Hkv, int head_dim, long long q_rs, long long k_rs, long long v_rs,
+                  long long do_rs, long long dq_rs, long long dk_rs, long long dv_rs, int causal, float scale, cudaStream_t st,
+                  int* handled);

@@ -63,3 +63,24 @@ for tc in (0, 1):
                                                H, hd, 3 * H * hd, 3 * H * hd, 3 * H * hd, H * hd, 0, hd ** -0.5, L.stream_ptr())), reps=5)
     print(f"enc attention fwd tc={tc}: {t:.3f} ms  {4.0 * B * H * S * S * hd / t / 1e9:.0f} TF/s", flush=True)
 lib.ta_attn_set_tc(1)
+
+# decoder attention fwd + bwd (causal GQA, hd 128)
+B, S, Hq, Hkv, hd = 32, 464, 16, 8, 128
+q = torch.randn(B, S, Hq * hd, device=dev, dtype=BF16)
+k = torch.randn(B, S, Hkv * hd, device=dev, dtype=BF16)
+v = torch.randn(B, S, Hkv * hd, device=dev, dtype=BF16)
+do = torch.randn(B, S, Hq * hd, device=dev, dtype=BF16)
+o = torch.empty_like(q)
+lse = torch.empty(B, Hq, S, device=dev, dtype=F32)
+dsum = torch.empty_like(lse)
+dq = torch.empty(B, S, Hq * hd, device=dev, dtype=F32)
+dk, dv = torch.empty_like(k), torch.empty_like(v)
+for tc in (0, 1):
+    lib.ta_attn_set_tc(tc)
+    tf = timeit(lambda: L.check(lib.ta_attn_fwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), L.ptr(lse), B, S, Hq, Hkv, hd, Hq * hd, Hkv * hd,
+                                                Hkv * hd, Hq * hd, 1, hd ** -0.5, L.stream_ptr())), reps=5)
+    tb = timeit(lambda: L.check(lib.ta_attn_bwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), L.ptr(do), L.ptr(lse), L.ptr(dsum), L.ptr(dq),
+                                                L.ptr(dk), L.ptr(dv), B, S, Hq, Hkv, hd, Hq * hd, Hkv * hd, Hkv * hd, Hq * hd, Hq * hd,
+                                                Hq * hd, Hkv * hd, Hkv * hd, 1, hd ** -0.5, L.stream_ptr())), reps=5)
+    print(f"lm attention tc={tc}: fwd {tf:.3f} ms  bwd (prep+memset+main) {tb:.3f} ms", flush=True)
+lib.ta_attn_set_tc(1)
