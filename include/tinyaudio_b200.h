@@ -86,6 +86,7 @@ int ta_mel_to_conv1_im2col(const float* mel /*(B,128,T)*/, int B, int T, void* o
 int ta_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int Hq, int Hkv,
                 int head_dim, long long q_rs, long long k_rs, long long v_rs, long long o_rs, int causal, float scale,
                 void* stream);
+int ta_debug_set(int key, int value); /* profiling experiments only; never changes results when left at 0 */
 int ta_attn_set_tc(int on); /* 1 (default): encoder-shape forward runs on tcgen05 (attn_tc.cu); 0: mma.sync kernel */
 int ta_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                 float* dsum_ws, float* dq_acc, void* dk, void* dv, int B, int S, int Hq, int Hkv, int head_dim,

@@ -50,7 +50,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                    const float* __restrict__ LSE, const float* __restrict__ Dsum, float* __restrict__ dQacc,
                    bf16* __restrict__ dK, bf16* __restrict__ dV, int S, int Hq, int Hkv, long long dq_rs, long long dk_rs,
-                   long long dv_rs, float scale, float scale_log2) {
+                   long long dv_rs, float scale, float scale_log2, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -241,7 +241,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     uint32_t v[32];
                     tmem_ld_32x32(lane_base + ST_COL + half * 64 + c * 32, v);
                     tmem_ld_wait();
-                    if (qi < S) {
+                    if (qi < S && !(dbg & 1)) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
                             red_add_v4(dst + c * 32 + 4 * i, __uint_as_float(v[4 * i]) * scale, __uint_as_float(v[4 * i + 1]) * scale,
@@ -285,7 +285,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
+int g_bwd_dbg = 0;
 }  // namespace
+
+TA_API int ta_debug_set(int key, int value) {   // experiments only (key 1: attention-backward switches)
+    if (key == 1) g_bwd_dbg = value;
+    return 0;
+}
 
 // internal: tcgen05 backward for head_dim 128 + causal; *handled = 0 -> caller uses the mma.sync kernel.
 // dsum (rowsum(dO*O)) must already be computed and dq_acc zeroed by the caller.
@@ -317,7 +323,7 @@ int k_attn_tc_bwd(const bf16* q, const bf16* k, const bf16* v, const bf16* d_o, 
     }
     dim3 grid((S + BT - 1) / BT, Hkv, B);
     attn_tc_bwd_kernel<<<grid, BWD_THREADS, SMEM_BWD, st>>>(tq, tk, tv, tdo, lse, dsum, dq_acc, dk, dv, S, Hq, Hkv, dq_rs, dk_rs, dv_rs,
-                                                           scale, scale * 1.4426950408889634f);
+                                                           scale, scale * 1.4426950408889634f, g_bwd_dbg);
     TA_LAUNCH_CHECK();
     *handled = 1;
     return 0;

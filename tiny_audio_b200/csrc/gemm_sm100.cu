@@ -406,6 +406,257 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 
+
+// ----------------------------------------------------------------------------------------------
+// Epilogue through shared memory + TMA store (pair kernel).  Each epilogue warp group (4 warps = the 128 rows of the
+// CTA's accumulator) owns two 16 KB staging buffers; a "sub-tile" is [128 rows x 128 bytes] (64 bf16 or 32 fp32
+// columns) written with the SWIZZLE_128B pattern the output tensor map expects, then stored by one elected thread.
+// This replaces 32-row-strided 16-byte global stores (32 sectors per warp instruction) by one bulk store per sub-tile
+// and lets TMA clip the M tail.
+// ----------------------------------------------------------------------------------------------
+constexpr int STG_BYTES = 128 * 128;
+
+struct Stager {
+    uint8_t* buf;       // this group's 2 x STG_BYTES
+    uint32_t bar_id;    // named barrier of the group's 128 threads
+    int r;              // my row (0..127)
+    int n;              // sub-tiles issued so far
+    bool leader;
+
+    __device__ __forceinline__ uint8_t* begin() {
+        if (leader && n >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        return buf + (n & 1) * STG_BYTES + r * 128;
+    }
+    __device__ __forceinline__ void end(const CUtensorMap* map, int col0, int row0) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (leader) {
+            tma_store_2d(map, buf + (n & 1) * STG_BYTES, col0, row0);
+            tma_store_commit();
+        }
+        ++n;
+    }
+    __device__ __forceinline__ void drain() {
+        if (leader) tma_store_wait_all();
+    }
+};
+
+// 32 bf16 values = half (which = 0 / 1) of my 128-byte staging row
+__device__ __forceinline__ void stage_bf16x32(uint8_t* row_ptr, int r, int which, const float (&v)[32]) {
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * qd + 0], v[8 * qd + 1]);
+        u.y = pack_bf16x2(v[8 * qd + 2], v[8 * qd + 3]);
+        u.z = pack_bf16x2(v[8 * qd + 4], v[8 * qd + 5]);
+        u.w = pack_bf16x2(v[8 * qd + 6], v[8 * qd + 7]);
+        *reinterpret_cast<uint4*>(row_ptr + (((which * 4 + qd) ^ (r & 7)) << 4)) = u;
+    }
+}
+// 32 fp32 values = my whole 128-byte staging row
+__device__ __forceinline__ void stage_f32x32(uint8_t* row_ptr, int r, const float (&v)[32]) {
+#pragma unroll
+    for (int qd = 0; qd < 8; ++qd)
+        *reinterpret_cast<float4*>(row_ptr + ((qd ^ (r & 7)) << 4)) = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row, bool row_ok, int tile_row0, long long tile_col0,
+                                                  const EpiArgs& ep, int grp, const float* s_bias, Stager& sg,
+                                                  const CUtensorMap* tmC, const CUtensorMap* tmC2) {
+    const int r = sg.r;
+    if constexpr (EPI == TA_EPI_SWIGLU) {
+        // 128 accumulator columns = [64 gate | 64 up] -> one h sub-tile (64 cols) + optional (gate, up) stash sub-tiles
+        const int sb_lo = (BN == 256) ? grp : 0, sb_hi = (BN == 256) ? grp + 1 : 1;
+#pragma unroll 1
+        for (int sb = sb_lo; sb < sb_hi; ++sb) {
+            if (BN == 128 && grp == 1) break;   // 128-wide tiles: one group does the whole (small) tile
+            uint8_t* hrow = sg.begin();
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t rg[32], ru[32];
+                tmem_ld_32x32(taddr + sb * 128 + c * 32, rg);
+                tmem_ld_32x32(taddr + sb * 128 + 64 + c * 32, ru);
+                tmem_ld_wait();
+                float h[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float g = bf16_round(__uint_as_float(rg[i])), u = bf16_round(__uint_as_float(ru[i]));
+                    h[i] = bf16_round(g * sigmoidf_(g)) * u;
+                }
+                stage_bf16x32(hrow, r, c, h);
+            }
+            sg.end(tmC, (int)((tile_col0 + sb * 128) / 2), tile_row0);
+            if (ep.out2) {
+#pragma unroll 1
+                for (int part = 0; part < 2; ++part) {      // gate block, up block
+                    uint8_t* prow = sg.begin();
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t rr[32];
+                        tmem_ld_32x32(taddr + sb * 128 + part * 64 + c * 32, rr);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+                        stage_bf16x32(prow, r, c, v);
+                    }
+                    sg.end(tmC2, (int)(tile_col0 + sb * 128 + part * 64), tile_row0);
+                }
+            }
+        }
+    } else {
+        constexpr bool F32OUT = (EPI == TA_EPI_F32 || EPI == TA_EPI_F32_RESID);
+        constexpr int NRAW = (EPI == TA_EPI_F32_RESID || EPI == TA_EPI_SWIGLU_BWD) ? 8 : (EPI == TA_EPI_BF16_RESID) ? 4 : 1;
+        uint4 cur[NRAW], nxt[NRAW];
+        auto prefetch = [&](int c, uint4 (&dst)[NRAW]) {
+            if constexpr (EPI == TA_EPI_BF16_RESID || EPI == TA_EPI_F32_RESID || EPI == TA_EPI_SWIGLU_BWD) {
+                if (!row_ok) return;
+                const long long col = tile_col0 + c * 32;
+                if constexpr (EPI == TA_EPI_BF16_RESID) {
+                    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.resid) + row * ep.ldr + col);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = p[i];
+                } else if constexpr (EPI == TA_EPI_F32_RESID) {
+                    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(ep.resid) + row * ep.ldr + col);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = p[i];
+                } else {
+                    const uint4* p = reinterpret_cast<const uint4*>(ep.aux + row * ep.ldaux + (col / 64) * 128 + (col % 64));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { dst[i] = p[i]; dst[4 + i] = p[8 + i]; }
+                }
+            }
+        };
+        const int c_lo = grp * (BN / 64), c_hi = (grp + 1) * (BN / 64);
+        prefetch(c_lo, cur);
+        uint8_t* srow = nullptr;
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; ++c) {
+            const long long col = tile_col0 + c * 32;
+            // sub-tile boundaries: fp32 outputs and SwiGLU-backward flush every chunk, bf16 outputs every second chunk
+            const bool first = (EPI != TA_EPI_SWIGLU_BWD) && (F32OUT || ((c - c_lo) & 1) == 0);
+            if (first) srow = sg.begin();
+            uint32_t rr[32];
+            tmem_ld_32x32(taddr + c * 32, rr);
+            if (c + 1 < c_hi) prefetch(c + 1, nxt);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+            if constexpr (EPI != TA_EPI_F32 && EPI != TA_EPI_SWIGLU_BWD) {
+                if (ep.bias) {
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = b4[i];
+                        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                    }
+                }
+            }
+            if constexpr (EPI == TA_EPI_BF16_ROPE) {
+                if (col < ep.rope_cols && (col & 63) == 0) {
+                    const int pos = (int)(row % ep.rope_seq);
+                    const float4* c4 = reinterpret_cast<const float4*>(ep.rope_cos + pos * 16);
+                    const float4* s4 = reinterpret_cast<const float4*>(ep.rope_sin + pos * 16);
+                    float cs[16], sn[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a = c4[i], b = s4[i];
+                        cs[4 * i] = a.x; cs[4 * i + 1] = a.y; cs[4 * i + 2] = a.z; cs[4 * i + 3] = a.w;
+                        sn[4 * i] = b.x; sn[4 * i + 1] = b.y; sn[4 * i + 2] = b.z; sn[4 * i + 3] = b.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float x1 = bf16_round(v[i]), x2 = bf16_round(v[i + 16]);
+                        v[i] = x1 * cs[i] - x2 * sn[i];
+                        v[i + 16] = x2 * cs[i] + x1 * sn[i];
+                    }
+                }
+            } else if constexpr (EPI == TA_EPI_BF16_GELU) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(bf16_round(v[i]));
+            } else if constexpr (EPI == TA_EPI_BF16_RESID) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 a = unpack_bf16x2(cur[i].x), b = unpack_bf16x2(cur[i].y), cc = unpack_bf16x2(cur[i].z),
+                                 d = unpack_bf16x2(cur[i].w);
+                    v[8 * i + 0] = a.x + bf16_round(v[8 * i + 0]); v[8 * i + 1] = a.y + bf16_round(v[8 * i + 1]);
+                    v[8 * i + 2] = b.x + bf16_round(v[8 * i + 2]); v[8 * i + 3] = b.y + bf16_round(v[8 * i + 3]);
+                    v[8 * i + 4] = cc.x + bf16_round(v[8 * i + 4]); v[8 * i + 5] = cc.y + bf16_round(v[8 * i + 5]);
+                    v[8 * i + 6] = d.x + bf16_round(v[8 * i + 6]); v[8 * i + 7] = d.y + bf16_round(v[8 * i + 7]);
+                }
+            } else if constexpr (EPI == TA_EPI_F32_RESID) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    v[4 * i + 0] = __uint_as_float(cur[i].x) + bf16_round(v[4 * i + 0]);
+                    v[4 * i + 1] = __uint_as_float(cur[i].y) + bf16_round(v[4 * i + 1]);
+                    v[4 * i + 2] = __uint_as_float(cur[i].z) + bf16_round(v[4 * i + 2]);
+                    v[4 * i + 3] = __uint_as_float(cur[i].w) + bf16_round(v[4 * i + 3]);
+                }
+            } else if constexpr (EPI == TA_EPI_F32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= ep.alpha;
+            }
+            if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
+                // v = d(h) for h columns [col, col+32) -> (d gate, d up) chunks of the interleaved [M, 2F] gradient
+                float dg[32], du[32];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t gw[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+                    const uint32_t uw[4] = {cur[4 + i].x, cur[4 + i].y, cur[4 + i].z, cur[4 + i].w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 g2 = unpack_bf16x2(gw[t]), u2 = unpack_bf16x2(uw[t]);
+                        const float gq[2] = {g2.x, g2.y}, uq[2] = {u2.x, u2.y};
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int k = 8 * i + 2 * t + e;
+                            const float dh = bf16_round(v[k]);
+                            const float sgm = sigmoidf_(gq[e]);
+                            du[k] = dh * bf16_round(gq[e] * sgm);
+                            dg[k] = dh * uq[e] * (sgm * (1.0f + gq[e] * (1.0f - sgm)));
+                        }
+                    }
+                }
+                // two consecutive chunks cover h columns [64 j, 64 j + 64): their d(gate) halves fill the sub-tile at output
+                // columns [128 j, +64) and their d(up) halves the one at [128 j + 64, +64); both staging buffers are used at once
+                const int which = (c - c_lo) & 1;
+                uint8_t* rowA = sg.buf + r * 128;
+                uint8_t* rowB = sg.buf + STG_BYTES + r * 128;
+                if (which == 0) {
+                    if (sg.leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(sg.bar_id) : "memory");
+                }
+                stage_bf16x32(rowA, r, which, dg);
+                stage_bf16x32(rowB, r, which, du);
+                if (which == 1) {
+                    const int jb = (int)((col - 32) / 64);
+                    fence_proxy_async_smem();
+                    asm volatile("bar.sync %0, 128;" ::"r"(sg.bar_id) : "memory");
+                    if (sg.leader) {
+                        tma_store_2d(tmC, sg.buf, jb * 128, tile_row0);
+                        tma_store_2d(tmC, sg.buf + STG_BYTES, jb * 128 + 64, tile_row0);
+                        tma_store_commit();
+                    }
+                }
+            } else if constexpr (F32OUT) {
+                stage_f32x32(srow, r, v);
+                sg.end(tmC, (int)col, tile_row0);
+            } else {
+                const int which = (c - c_lo) & 1;
+                stage_bf16x32(srow, r, which, v);
+                if (which == 1) sg.end(tmC, (int)(col - 32), tile_row0);
+            }
+            if (c + 1 < c_hi) {
+#pragma unroll
+                for (int i = 0; i < NRAW; ++i) cur[i] = nxt[i];
+            }
+        }
+    }
+}
+
 // =============================================================================================================
 // 2-CTA variant (cta_group::2): a CTA pair (cluster 2x1x1, two SMs of one TPC) owns a 256 x BN tile.
 //   CTA r holds A rows [m0 + 128 r, +128) and the B rows [n0 + r BN/2, + BN/2) of every stage; the leader (rank 0)
@@ -469,27 +720,31 @@ struct Cfg2 {
     static constexpr int A_BYTES = BM * BK * 2;            // 128 rows of A per CTA
     static constexpr int B_BYTES = (BN / 2) * BK * 2;      // half of the B tile per CTA
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 6 : 8;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2 * BN * 4;
+    static constexpr int STG_OFF = STAGES * STAGE_BYTES;                   // 2 groups x 2 staging buffers x 16 KB (1024-aligned)
+    static constexpr int BAR_OFF = STG_OFF + 4 * STG_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 2 * BN * 4 + 1024;
 };
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, EpiArgs ep) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int M, int N, int K, EpiArgs ep) {
     using C = Cfg2<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* smA = smem;
     uint8_t* smB = smem + C::STAGES * C::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint8_t* smStage = smem + C::STG_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
     uint64_t* full = bars;
     uint64_t* empty = bars + C::STAGES;
     uint64_t* tfull = bars + 2 * C::STAGES;
     uint64_t* tempty = bars + 2 * C::STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-    float* s_bias_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [2][BN]
+    float* s_bias_all = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);   // [2][BN]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -504,6 +759,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        tma_prefetch_desc(&tmC2);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -575,6 +832,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs, their own 128 rows) =====================
         const int q = warp & 3;
+        const int grp = (warp - 4) >> 2;
+        Stager sg;
+        sg.buf = smStage + grp * 2 * STG_BYTES;
+        sg.bar_id = 2 + grp;
+        sg.r = q * 32 + lane;
+        sg.n = 0;
+        sg.leader = (q == 0 && lane == 0);
         int tile_iter = 0;
         int as = 0;
         uint32_t aphase = 0;
@@ -593,13 +857,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const long long row = (long long)m_blk * 2 * BM + (long long)rank * BM + q * 32 + lane;
             const bool row_ok = row < M;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            epilogue_tile<BN, EPI>(taddr, row, row_ok, (long long)n_blk * BN, ep, (warp - 4) >> 2, s_bias);
+            epilogue_tile_tma<BN, EPI>(taddr, row, row_ok, m_blk * 2 * BM + (int)rank * BM, (long long)n_blk * BN, ep, grp, s_bias, sg,
+                                       &tmC, &tmC2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty[as]);
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
+        sg.drain();              // all bulk stores of this group have left shared memory and are complete
     }
 
     tc_fence_before();
@@ -630,7 +896,7 @@ EncodeTiledFn get_encode_fn() {
 struct MapKey {
     const void* ptr;
     long long rows, cols, ld;
-    int box_rows;
+    int box_rows;   // negative: fp32 elements (box = 32 x |box_rows|)
     bool operator==(const MapKey& o) const {
         return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
     }
@@ -647,8 +913,8 @@ std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // 2-D bf16 row-major [rows, cols] (ld elements), box = {64 cols, box_rows}, SWIZZLE_128B, zero fill out of bounds
-int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
-    MapKey key{ptr, rows, cols, ld, box_rows};
+int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows, bool f32 = false) {
+    MapKey key{ptr, rows, cols, ld, f32 ? -box_rows : box_rows};
     {
         std::lock_guard<std::mutex> g(g_map_mu);
         auto it = g_maps.find(key);
@@ -660,12 +926,13 @@ int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, 
     EncodeTiledFn fn = get_encode_fn();
     TA_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
     TA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand pointer must be 16-byte aligned");
-    TA_REQUIRE((ld * 2) % 16 == 0, "GEMM operand leading dimension must be a multiple of 8 elements (got %lld)", ld);
+    const int esz = f32 ? 4 : 2;
+    TA_REQUIRE((ld * esz) % 16 == 0, "GEMM operand leading dimension must be a multiple of 16 bytes (got %lld elements)", ld);
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : BK), (cuuint32_t)box_rows};   // 128-byte inner extent either way
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows,
@@ -729,7 +996,8 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, i
 }
 
 template <int BN, int EPI>
-int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiArgs& ep, cudaStream_t st) {
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2, int M, int N, int K,
+            const EpiArgs& ep, cudaStream_t st) {
     using C = Cfg2<BN>;
     auto kern = gemm2_kernel<BN, EPI>;
     static bool attr_done = false;
@@ -740,23 +1008,23 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, c
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
     int pairs = num_sms() / 2;
     if (tiles < pairs) pairs = tiles;
-    kern<<<2 * pairs, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, M, N, K, ep);
+    kern<<<2 * pairs, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, tc, tc2, M, N, K, ep);
     TA_LAUNCH_CHECK();
     return 0;
 }
 
 template <int BN>
-int dispatch_epi2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiArgs& ep,
-                  cudaStream_t st) {
+int dispatch_epi2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2, int M, int N,
+                  int K, const EpiArgs& ep, cudaStream_t st) {
     switch (epi) {
-        case TA_EPI_BF16: return launch2<BN, TA_EPI_BF16>(ta, tb, M, N, K, ep, st);
-        case TA_EPI_BF16_GELU: return launch2<BN, TA_EPI_BF16_GELU>(ta, tb, M, N, K, ep, st);
-        case TA_EPI_BF16_RESID: return launch2<BN, TA_EPI_BF16_RESID>(ta, tb, M, N, K, ep, st);
-        case TA_EPI_F32_RESID: return launch2<BN, TA_EPI_F32_RESID>(ta, tb, M, N, K, ep, st);
-        case TA_EPI_F32: return launch2<BN, TA_EPI_F32>(ta, tb, M, N, K, ep, st);
-        case TA_EPI_SWIGLU: return launch2<BN, TA_EPI_SWIGLU>(ta, tb, M, N, K, ep, st);
-        case TA_EPI_SWIGLU_BWD: return launch2<BN, TA_EPI_SWIGLU_BWD>(ta, tb, M, N, K, ep, st);
-        case TA_EPI_BF16_ROPE: return launch2<BN, TA_EPI_BF16_ROPE>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_BF16: return launch2<BN, TA_EPI_BF16>(ta, tb, tc, tc2, M, N, K, ep, st);
+        case TA_EPI_BF16_GELU: return launch2<BN, TA_EPI_BF16_GELU>(ta, tb, tc, tc2, M, N, K, ep, st);
+        case TA_EPI_BF16_RESID: return launch2<BN, TA_EPI_BF16_RESID>(ta, tb, tc, tc2, M, N, K, ep, st);
+        case TA_EPI_F32_RESID: return launch2<BN, TA_EPI_F32_RESID>(ta, tb, tc, tc2, M, N, K, ep, st);
+        case TA_EPI_F32: return launch2<BN, TA_EPI_F32>(ta, tb, tc, tc2, M, N, K, ep, st);
+        case TA_EPI_SWIGLU: return launch2<BN, TA_EPI_SWIGLU>(ta, tb, tc, tc2, M, N, K, ep, st);
+        case TA_EPI_SWIGLU_BWD: return launch2<BN, TA_EPI_SWIGLU_BWD>(ta, tb, tc, tc2, M, N, K, ep, st);
+        case TA_EPI_BF16_ROPE: return launch2<BN, TA_EPI_BF16_ROPE>(ta, tb, tc, tc2, M, N, K, ep, st);
         default: ta_set_error("unknown epilogue mode %d", epi); return -1;
     }
 }
@@ -802,8 +1070,19 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
     if (g_cta_pair) {
         rc = make_map(&tb, B, N, K, ldb, bn / 2);     // each CTA of the pair loads half of the B tile
         if (rc) return rc;
-        if (bn == 256) return dispatch_epi2<256>(epi, ta, tb, M, N, K, ep, st);
-        return dispatch_epi2<128>(epi, ta, tb, M, N, K, ep, st);
+        // output maps for the TMA-store epilogue: [M, width] with 128-byte wide sub-tiles
+        const bool f32out = (epi == TA_EPI_F32 || epi == TA_EPI_F32_RESID);
+        const long long out_cols = (epi == TA_EPI_SWIGLU) ? N / 2 : (epi == TA_EPI_SWIGLU_BWD) ? 2LL * N : N;
+        CUtensorMap tc, tc2;
+        rc = make_map(&tc, e->out, M, out_cols, e->ldo, BM, f32out);
+        if (rc) return rc;
+        tc2 = tc;
+        if (epi == TA_EPI_SWIGLU && e->out2) {
+            rc = make_map(&tc2, e->out2, M, N, e->ldo2, BM, false);
+            if (rc) return rc;
+        }
+        if (bn == 256) return dispatch_epi2<256>(epi, ta, tb, tc, tc2, M, N, K, ep, st);
+        return dispatch_epi2<128>(epi, ta, tb, tc, tc2, M, N, K, ep, st);
     }
     rc = make_map(&tb, B, N, K, ldb, bn);
     if (rc) return rc;

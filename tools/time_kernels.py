@@ -84,3 +84,10 @@ for tc in (0, 1):
                                                 Hq * hd, Hkv * hd, Hkv * hd, 1, hd ** -0.5, L.stream_ptr())), reps=5)
     print(f"lm attention tc={tc}: fwd {tf:.3f} ms  bwd (prep+memset+main) {tb:.3f} ms", flush=True)
 lib.ta_attn_set_tc(1)
+
+lib.ta_debug_set(1, 1)
+tb = timeit(lambda: L.check(lib.ta_attn_bwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), L.ptr(do), L.ptr(lse), L.ptr(dsum), L.ptr(dq),
+                                            L.ptr(dk), L.ptr(dv), B, S, Hq, Hkv, hd, Hq * hd, Hkv * hd, Hkv * hd, Hq * hd, Hq * hd,
+                                            Hq * hd, Hkv * hd, Hkv * hd, 1, hd ** -0.5, L.stream_ptr())), reps=5)
+print(f"lm attention bwd WITHOUT dQ atomics (experiment): {tb:.3f} ms", flush=True)
+lib.ta_debug_set(1, 0)
