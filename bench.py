@@ -207,7 +207,7 @@ def run_ours(args):
                     num_items_in_batch=n_items_global)
         out.loss.backward()
         opt.step()
-        return float(out.loss)          # device -> host read of the step's loss
+        return float(out.loss.detach())   # device -> host read of the step's loss
 
     def barrier():
         if world > 1:

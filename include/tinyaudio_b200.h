@@ -211,6 +211,7 @@ typedef struct ta_lm_step_args {
     float* d_inputs_embeds;       /* [B*S, dim] fp32 out (with_backward) */
     void* workspace;
     long long workspace_bytes;
+    float* final_hidden;          /* optional [B*S, dim] fp32: last layer's output BEFORE the final norm (for ta_lm_hidden_to_logits) */
 } ta_lm_step_args;
 int ta_lm_workspace_bytes(const ta_lm_weights* w, int B, int S, int n_labelled, int with_backward, long long* bytes);
 int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args* a, void* stream);

@@ -429,6 +429,29 @@ def model_forward(W, batch: Dict[str, Tensor], cfg: PathConfig = FULL, num_items
     return loss, logits
 
 
+@torch.no_grad()
+def greedy_generate(W, batch, cfg: PathConfig = FULL, max_new_tokens: int = 8):
+    """Greedy ids by re-running the whole forward per token (reference: asr_modeling.py:562-646, greedy defaults).
+    Returns (ids [B, T_new], top-1 minus top-2 logit margin [B, T_new])."""
+    ids = batch["input_ids"].clone()
+    counts = batch["audio_token_counts"]
+    mel = batch["input_features"].float() if "input_features" in batch else log_mel(batch["waveform"], cfg)
+    audio = projector_forward(W["projector"], encoder_forward(W["encoder"], mel, cfg), cfg)
+    packed = gather_audio_embeds(audio, counts)
+    out, margins = [], []
+    for _ in range(max_new_tokens):
+        emb = F.embedding(ids, W["lm"]["model.embed_tokens.weight"])
+        emb = scatter_audio(emb, ids, packed, cfg.audio_token_id)
+        hid = lm_forward(W["lm"], emb, cfg)[:, -1]
+        logits = F.linear(hid, W["lm"]["lm_head.weight"])
+        top = logits.topk(2, -1).values
+        nxt = logits.argmax(-1)
+        out.append(nxt)
+        margins.append(top[:, 0] - top[:, 1])
+        ids = torch.cat([ids, nxt[:, None]], 1)
+    return torch.stack(out, 1), torch.stack(margins, 1)
+
+
 def clip_grad_norm(grads: Dict[str, Tensor], max_norm: float) -> Tuple[Tensor, float]:
     """torch.nn.utils.clip_grad_norm_ semantics: total 2-norm; scale by max_norm/(norm+1e-6) clamped to 1."""
     total = torch.sqrt(sum((g.float() ** 2).sum() for g in grads.values()))

@@ -127,3 +127,29 @@ def test_linearity_in_num_items_and_determinism(cuda):
         assert rel(g2[k] * 2, g1[k]) < 2e-2     # dlogits are rounded to bf16 after the 1/num_items scale
         assert rel(g3[k], g1[k]) < 1e-4
     assert abs(float(l1) - float(l3)) < 1e-6 * abs(float(l1))
+
+
+def test_greedy_ids_match_oracle(cuda):
+    """Greedy token ids (north star: bit-exact).  With random weights the decoder's logits are nearly flat, so the LM is
+    'sharpened' (embedding std 0.04) and ids are compared, teacher-forced on the oracle's prefix, at every step whose
+    top-1 margin in the fp32 oracle exceeds 0.2 -- above the bf16 logit noise of the production recipe."""
+    cfg = po.small_config(enc_layers=1, lm_layers=2)
+    W = po.init_weights(cfg, seed=9, emb_std=0.04)
+    hp = HotPath(PathDims.from_any(cfg.to_dict()), W["encoder"], W["lm"], "cuda")
+    batch = po.synthetic_batch(cfg, 2, 1.0, seed=9, response_len=2)
+    prompt = batch["input_ids"][:, : int((batch["labels"][0] != -100).nonzero().min())]
+    T = 6
+    ref_ids, margin = po.greedy_generate(W, dict(batch, input_ids=prompt), cfg, max_new_tokens=T)
+    params = {k: v.clone().cuda().contiguous() for k, v in W["projector"].items()}
+    kw = dict(proj_params=params, waveform=batch["waveform"].cuda(), audio_token_counts=batch["audio_token_counts"].cuda())
+    checked = 0
+    for t in range(T):
+        forced = torch.cat([prompt, ref_ids[:, :t]], 1)
+        got = hp.greedy_generate(input_ids=forced.cuda(), max_new_tokens=1, **kw).cpu()[:, 0]
+        for b in range(ref_ids.shape[0]):
+            if float(margin[b, t]) > 0.2:
+                checked += 1
+                assert int(got[b]) == int(ref_ids[b, t]), f"sample {b} step {t}: {int(got[b])} != {int(ref_ids[b, t])} (margin {float(margin[b, t]):.2f})"
+    free = hp.greedy_generate(input_ids=prompt.cuda(), max_new_tokens=T, **kw).cpu()
+    print("greedy: decisive steps checked", checked, "of", 2 * T, "free-running ids", free.tolist(), "oracle", ref_ids.tolist())
+    assert free.shape == ref_ids.shape and checked >= 4

@@ -311,6 +311,30 @@ class ASRModel(PreTrainedModel, GenerationMixin):
             loss = None
         return CausalLMOutputWithPast(loss=loss, logits=None)
 
+    @torch.no_grad()
+    def generate(self, input_ids: Optional[torch.Tensor] = None, input_features: Optional[torch.Tensor] = None,
+                 audio_attention_mask: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
+                 audio_token_counts: Optional[torch.Tensor] = None, max_new_tokens: Optional[int] = None, **kwargs) -> torch.Tensor:
+        """Greedy transcription ids (reference: asr_modeling.py:562-646 with num_beams=1, do_sample=False).  Returns only the
+        newly generated tokens, like the reference (it strips the prompt, :644-646).  `input_ids` must hold the prompt with
+        its <audio> placeholders (the reference builds it from the tokenizer's chat template when it is None; that needs a
+        real tokenizer and is left to ASRProcessor)."""
+        if input_ids is None or input_features is None:
+            raise NotImplementedError("generate() needs input_ids (prompt with <audio> placeholders) and input_features")
+        if kwargs.get("num_beams", 1) != 1 or kwargs.get("do_sample", False):
+            raise NotImplementedError("only greedy decoding is implemented on the B200 path")
+        hot = self._hot_path()
+        feats = input_features.to(hot.device)
+        pr = self.projector
+        params = {k: p.detach().float().contiguous() for k, p in zip(_PROJ_KEYS, (pr.linear_1.weight, pr.norm.weight,
+                                                                               pr.linear_2.weight, pr.norm_2.weight))}
+        kw = dict(waveform=feats.float().contiguous()) if feats.dim() == 2 else dict(input_features=feats)
+        gc = self.generation_config
+        eos = gc.eos_token_id if isinstance(gc.eos_token_id, (list, tuple)) else [gc.eos_token_id]
+        return hot.greedy_generate(input_ids=input_ids, proj_params=params, audio_token_counts=audio_token_counts,
+                                   max_new_tokens=int(max_new_tokens or gc.max_new_tokens or 128),
+                                   eos_token_ids=[e for e in eos if e is not None], pad_token_id=int(gc.pad_token_id or 0), **kw)
+
     # ------------------------------------------------------------------ persistence (projector-only, reference layout)
     def save_pretrained(self, save_directory, **kwargs):
         from safetensors.torch import save_file

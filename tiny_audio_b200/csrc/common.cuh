@@ -52,18 +52,21 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-// exact-erf GELU for GEMM epilogues in ~14 instructions (2 MUFU): Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7,
-// arranged so that both tails keep their relative accuracy:  q = 0.5*(1 - erf(|x|/sqrt2));  gelu = x>=0 ? x - x*q : x*q
+// exact-erf GELU for GEMM epilogues in 15 instructions (2 MUFU): Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7.
+//   a = |x| sqrt(log2(e)/2);  t = 1/(1 + p' a);  q = 0.5 (1 - erf(|x|/sqrt2)) = t P(t) 2^(-a^2)   (0.5 folded into P)
+//   gelu(x) = max(x, 0) - |x| q            (both tails keep their relative accuracy)
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float q = 0.5f * p * t * __expf(-z * z);
-    const float xq = x * q;
-    return x >= 0.f ? x - xq : xq;
+    const float a = fabsf(x) * 0.84932180028801904272f;                 // sqrt(log2(e) / 2)
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(a, 0.2727374809f, 1.0f)));   // p / sqrt(log2 e)
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * a));
+    float p = fmaf(0.5307027145f, t, -0.7265760135f);
+    p = fmaf(p, t, 0.7107068705f);
+    p = fmaf(p, t, -0.142248368f);
+    p = fmaf(p, t, 0.127414796f);
+    const float q = p * t * e;
+    return fmaxf(x, 0.0f) - fabsf(x) * q;
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 

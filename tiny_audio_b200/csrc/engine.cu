@@ -292,6 +292,8 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
         x_in = x_out;
     }
     const float* x_final = x_in;
+    if (a->final_hidden)   // pre-final-norm hidden states for callers that need logits of arbitrary rows (generate)
+        TA_CHECK_CUDA(cudaMemcpyAsync(a->final_hidden, x_final, sizeof(float) * M * D, cudaMemcpyDeviceToDevice, st));
 
     // ------------------------------ head: final norm on the labelled rows, lm_head, CE ------------------------------
     if (nl > 0) {

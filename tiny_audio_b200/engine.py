@@ -335,9 +335,76 @@ class HotPath:
         demb = self.ws.typed("d_inputs_embeds", (B * S, d.lm_dim), F32) if with_backward else None
         row_loss = torch.empty(nl, device=self.device, dtype=F32) if want_row_loss else None
         args = L.LmStepArgs(B, S, nl, int(with_backward), L.ptr(emb), L.ptr(rows), L.ptr(targets), inv_items, L.ptr(loss),
-                            L.ptr(row_loss), L.ptr(demb), L.ptr(ws), n.value)
+                            L.ptr(row_loss), L.ptr(demb), L.ptr(ws), n.value, None)
         L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
         return loss, demb, row_loss
+
+    def lm_hidden(self, emb: torch.Tensor, B: int, S: int) -> torch.Tensor:
+        """Forward-only decoder pass; returns the last layer's output before the final norm, fp32 [B*S, dim]."""
+        d = self.dims
+        n = C.c_longlong()
+        L.check(self.lib.ta_lm_workspace_bytes(C.byref(self.lm.c), B, S, 0, 0, C.byref(n)))
+        ws = self.ws.get("lm", n.value)
+        loss = torch.zeros(1, device=self.device, dtype=F32)
+        hid = self.ws.typed("final_hidden", (B * S, d.lm_dim), F32)
+        args = L.LmStepArgs(B, S, 0, 0, L.ptr(emb), None, None, 1.0, L.ptr(loss), None, None, L.ptr(ws), n.value, L.ptr(hid))
+        L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
+        return hid
+
+    def logits_rows(self, hidden: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+        """final norm + tied lm_head on the given flat token rows -> bf16 logits [n_rows, vocab] (padding sliced off)."""
+        d = self.dims
+        nr = int(rows.numel())
+        rows = rows.to(device=self.device, dtype=torch.int32).contiguous()
+        normed = self.ws.typed("gen_normed", (nr, d.lm_dim), BF16)
+        logits = torch.empty(nr, self.lm.vocab_pad, device=self.device, dtype=BF16)
+        L.check(self.lib.ta_lm_hidden_to_logits(C.byref(self.lm.c), L.ptr(hidden), L.ptr(rows), nr, L.ptr(normed), L.ptr(logits),
+                                                L.stream_ptr()))
+        return logits[:, : d.vocab]
+
+    @torch.no_grad()
+    def audio_embeds(self, *, waveform=None, input_features=None, proj_params=None):
+        B = (waveform if waveform is not None else input_features).shape[0]
+        if waveform is not None:
+            im2, _, T = self.logmel(waveform)
+        else:
+            im2, T = self.mel_to_im2col(input_features)
+        enc = self.encode(im2, B, T)
+        xs, n_a = self.frame_stack(enc)
+        audio, _ = self.projector_forward(xs, proj_params, False)
+        return audio, n_a
+
+    @torch.no_grad()
+    def greedy_generate(self, *, input_ids: torch.Tensor, proj_params, waveform=None, input_features=None,
+                        audio_token_counts=None, max_new_tokens: int = 16, eos_token_ids=(), pad_token_id: int = 0):
+        """Greedy decoding (num_beams=1, do_sample=False: the reference's generation defaults, asr_config.py:103-111).
+        Round-1 implementation re-runs the decoder over the whole sequence for every new token (no KV cache yet --
+        SURVEY.md section 8f rank 1); all prompts in the batch have the same length (equal-length clips)."""
+        d = self.dims
+        ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
+        B = ids.shape[0]
+        audio, n_a = self.audio_embeds(waveform=waveform, input_features=input_features, proj_params=proj_params)
+        audio = audio.clone()
+        if audio_token_counts is None:
+            audio_token_counts = (ids == d.audio_token_id).sum(-1)
+        counts = audio_token_counts.to(device=self.device, dtype=torch.int64).contiguous()
+        eos = torch.tensor(list(eos_token_ids), device=self.device, dtype=torch.int64)
+        done = torch.zeros(B, dtype=torch.bool, device=self.device)
+        out = []
+        for _ in range(max_new_tokens):
+            S = ids.shape[1]
+            emb, _ = self.embed_scatter(ids, counts, audio, n_a)
+            hid = self.lm_hidden(emb, B, S)
+            last = torch.arange(B, device=self.device, dtype=torch.int32) * S + (S - 1)
+            nxt = self.logits_rows(hid, last).float().argmax(-1)
+            nxt = torch.where(done, torch.full_like(nxt, pad_token_id), nxt)
+            out.append(nxt)
+            if eos.numel():
+                done = done | (nxt[:, None] == eos[None, :]).any(-1)
+            ids = torch.cat([ids, nxt[:, None]], dim=1).contiguous()
+            if bool(done.all()):
+                break
+        return torch.stack(out, dim=1)
 
     # ------------------------------------------------------------------ the whole step
     def forward_backward(self, *, input_ids: torch.Tensor, labels_cpu: Optional[torch.Tensor], proj_params,

@@ -53,7 +53,8 @@ class LmWeights(C.Structure):
 class LmStepArgs(C.Structure):
     _fields_ = [("B", c_int), ("S", c_int), ("n_labelled", c_int), ("with_backward", c_int),
                 ("inputs_embeds", P), ("label_rows", P), ("label_targets", P), ("inv_num_items", c_float),
-                ("loss", P), ("row_loss", P), ("d_inputs_embeds", P), ("workspace", P), ("workspace_bytes", c_ll)]
+                ("loss", P), ("row_loss", P), ("d_inputs_embeds", P), ("workspace", P), ("workspace_bytes", c_ll),
+                ("final_hidden", P)]
 
 
 _SIGS = {
