@@ -74,7 +74,7 @@ class StubTok:
         return self.cfg.vocab
 
 
-def build_reference_model(cfg: po.PathConfig, W, mods):
+def build_reference_model(cfg: po.PathConfig, W, mods, projector="mlp"):
     from transformers import GlmAsrEncoderConfig, Qwen3Config, Qwen3ForCausalLM, WhisperFeatureExtractor
     from transformers.models.glmasr.modeling_glmasr import GlmAsrEncoder
 
@@ -115,7 +115,7 @@ def build_reference_model(cfg: po.PathConfig, W, mods):
     ASRModel._init_tokenizer = _tok
     ASRModel._create_feature_extractor = lambda self, config: WhisperFeatureExtractor(feature_size=cfg.n_mels)
     acfg = ASRConfig(audio_config=enc_cfg, text_config=txt_cfg, model_dtype="float32", attn_implementation="sdpa",
-                     projector_type="mlp", projector_pool_stride=cfg.proj_k, projector_hidden_dim=cfg.proj_hidden,
+                     projector_type=projector, projector_pool_stride=cfg.proj_k, projector_hidden_dim=cfg.proj_hidden,
                      audio_token_dropout=0.0)
     model = ASRModel(acfg)
     model.projector.load_state_dict(W["projector"], strict=True)
@@ -136,16 +136,29 @@ CASES = {
     "small_b3_ragged": (dict(enc_layers=1, lm_layers=1), 3, 1.5, None, 8, 13),
     "h2048_b2_2s":   (dict(proj_hidden=2048, enc_layers=1, lm_layers=1), 2, 2.0, None, 8, 14),
     "full_b1_4s":    ("full", 1, 4.0, None, 32, 21),
+    # config 4: QFormer projector (reference in eval mode: its dropout 0.1 has no bit-parity definition)
+    "qformer_b2_2s": (dict(enc_layers=1, lm_layers=1, _projector="qformer"), 2, 2.0, None, 8, 15),
 }
+
+
+def case_config(spec):
+    """-> (PathConfig, projector kind)"""
+    if spec == "full":
+        return po.FULL, "mlp"
+    spec = dict(spec)
+    kind = spec.pop("_projector", "mlp")
+    return po.small_config(**spec), kind
 
 
 def run_case(name, mods, outdir):
     spec, B, clip_s, pad_s, R, seed = CASES[name]
-    cfg = po.FULL if spec == "full" else po.small_config(**spec)
+    cfg, kind = case_config(spec)
     torch.manual_seed(0)
     t0 = time.time()
     W = po.init_weights(cfg, seed=seed)
-    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s)
+    if kind == "qformer":
+        W["projector"] = po.init_qformer_weights(cfg, seed=seed + 1000)
+    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s, projector=kind)
     if name == "small_b3_ragged":
         # ragged text: right-pad labels/ids of samples 1,2 and shrink their audio counts
         ids, labels, am = batch["input_ids"].clone(), batch["labels"].clone(), batch["attention_mask"].clone()
@@ -155,8 +168,10 @@ def run_case(name, mods, outdir):
             labels[b, -cut:] = -100
             am[b, -cut:] = 0
         batch.update(input_ids=ids, labels=labels, attention_mask=am)
-    model = build_reference_model(cfg, W, mods)
+    model = build_reference_model(cfg, W, mods, kind)
     model.train()
+    if kind == "qformer":
+        model.projector.eval()
 
     # reference feature extraction (HF WhisperFeatureExtractor through the collator's call, train.py:327-333)
     fe = model.feature_extractor

@@ -320,6 +320,77 @@ def projector_forward(w: Dict[str, Tensor], enc_out: Tensor, cfg: PathConfig = F
 
 
 # --------------------------------------------------------------------------------------
+# a6. QFormer projector (tiny_audio/projectors.py:359-475; HF:models/blip_2/modeling_blip_2.py:537-1042), eval mode (no dropout)
+# --------------------------------------------------------------------------------------
+QF_WINDOW, QF_DOWNSAMPLE, QF_HEADS, QF_LAYERS, QF_EPS = 15, 5, 16, 2, 1e-12
+
+
+def init_qformer_weights(cfg: PathConfig, seed: int = 77) -> Dict[str, Tensor]:
+    """Seeded weights under the reference's parameter names (QFormerAudioProjector.state_dict())."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    H, Fq = cfg.enc_dim, 4 * cfg.enc_dim
+
+    def lin(o, i):
+        return torch.randn(o, i, generator=g) / math.sqrt(i)
+
+    def vec(n, mean=0.0, std=0.05):
+        return mean + std * torch.randn(n, generator=g)
+
+    w = {"query": torch.randn(1, QF_WINDOW // QF_DOWNSAMPLE, H, generator=g),
+         "qformer.layernorm.weight": vec(H, 1.0, 0.1), "qformer.layernorm.bias": vec(H)}
+    for i in range(QF_LAYERS):
+        for att in ("attention", "crossattention"):
+            p = f"qformer.encoder.layer.{i}.{att}."
+            for n in ("query", "key", "value"):
+                w[p + f"attention.{n}.weight"] = lin(H, H)
+                w[p + f"attention.{n}.bias"] = vec(H)
+            w[p + "output.dense.weight"] = lin(H, H)
+            w[p + "output.dense.bias"] = vec(H)
+            w[p + "output.LayerNorm.weight"] = vec(H, 1.0, 0.1)
+            w[p + "output.LayerNorm.bias"] = vec(H)
+        p = f"qformer.encoder.layer.{i}."
+        w[p + "intermediate_query.dense.weight"] = lin(Fq, H)
+        w[p + "intermediate_query.dense.bias"] = vec(Fq)
+        w[p + "output_query.dense.weight"] = lin(H, Fq)
+        w[p + "output_query.dense.bias"] = vec(H)
+        w[p + "output_query.LayerNorm.weight"] = vec(H, 1.0, 0.1)
+        w[p + "output_query.LayerNorm.bias"] = vec(H)
+    w["linear.weight"] = lin(cfg.lm_dim, H)
+    w["linear.bias"] = vec(cfg.lm_dim)
+    return w
+
+
+def qformer_output_length(enc_len):
+    return ((enc_len + QF_WINDOW - 1) // QF_WINDOW) * (QF_WINDOW // QF_DOWNSAMPLE)
+
+
+def qformer_projector_forward(w: Dict[str, Tensor], enc_out: Tensor, cfg: PathConfig = FULL) -> Tensor:
+    B, S, H = enc_out.shape
+    nb = -(-S // QF_WINDOW)
+    x_enc = F.pad(enc_out.float(), (0, 0, 0, nb * QF_WINDOW - S)).reshape(B * nb, QF_WINDOW, H)
+    hd = H // QF_HEADS
+
+    def attend(p, x, src):
+        Wn = x.shape[0]
+        q = F.linear(x, w[p + "attention.query.weight"], w[p + "attention.query.bias"]).view(Wn, -1, QF_HEADS, hd).transpose(1, 2)
+        k = F.linear(src, w[p + "attention.key.weight"], w[p + "attention.key.bias"]).view(Wn, -1, QF_HEADS, hd).transpose(1, 2)
+        v = F.linear(src, w[p + "attention.value.weight"], w[p + "attention.value.bias"]).view(Wn, -1, QF_HEADS, hd).transpose(1, 2)
+        ctx = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1) @ v).transpose(1, 2).reshape(Wn, -1, H)
+        o = F.linear(ctx, w[p + "output.dense.weight"], w[p + "output.dense.bias"])
+        return F.layer_norm(o + x, (H,), w[p + "output.LayerNorm.weight"], w[p + "output.LayerNorm.bias"], QF_EPS)
+
+    x = F.layer_norm(w["query"], (H,), w["qformer.layernorm.weight"], w["qformer.layernorm.bias"], QF_EPS).expand(B * nb, -1, -1)
+    for i in range(QF_LAYERS):
+        p = f"qformer.encoder.layer.{i}."
+        x = attend(p + "attention.", x, x)
+        x = attend(p + "crossattention.", x, x_enc)
+        h = F.gelu(F.linear(x, w[p + "intermediate_query.dense.weight"], w[p + "intermediate_query.dense.bias"]))
+        f = F.linear(h, w[p + "output_query.dense.weight"], w[p + "output_query.dense.bias"])
+        x = F.layer_norm(f + x, (H,), w[p + "output_query.LayerNorm.weight"], w[p + "output_query.LayerNorm.bias"], QF_EPS)
+    return F.linear(x.reshape(B, nb * (QF_WINDOW // QF_DOWNSAMPLE), H), w["linear.weight"], w["linear.bias"])
+
+
+# --------------------------------------------------------------------------------------
 # a7. ragged gather + masked_scatter (tiny_audio/asr_modeling.py:27-44, 497-515)
 # --------------------------------------------------------------------------------------
 def gather_audio_embeds(audio_embeds: Tensor, token_counts: Tensor) -> Tensor:
@@ -408,7 +479,10 @@ def model_forward(W, batch: Dict[str, Tensor], cfg: PathConfig = FULL, num_items
     with torch.no_grad():
         enc = encoder_forward(W["encoder"], mel, cfg)
     parts["encoder_out"] = enc
-    audio = projector_forward(W["projector"], enc, cfg)
+    if "query" in W["projector"]:
+        audio = qformer_projector_forward(W["projector"], enc, cfg)
+    else:
+        audio = projector_forward(W["projector"], enc, cfg)
     parts["projector_out"] = audio
     ids = batch["input_ids"]
     counts = batch.get("audio_token_counts")
@@ -508,7 +582,7 @@ THINK_EMPTY = [151667, 271, 151668, 271]            # "<think>\n\n</think>\n\n" 
 
 
 def synthetic_batch(cfg: PathConfig, batch: int, clip_seconds: float, seed: int = 0, response_len: int = 64,
-                    pad_to_seconds: Optional[float] = None) -> Dict[str, Tensor]:
+                    pad_to_seconds: Optional[float] = None, projector: str = "mlp") -> Dict[str, Tensor]:
     """Equal-length clips, 0.1*N(0,1) waveform, chat-template prompt with N_a <audio> tokens, R seeded
     response ids; labels = -100 except response + <|im_end|>."""
     rng = np.random.default_rng(seed)
@@ -518,6 +592,8 @@ def synthetic_batch(cfg: PathConfig, batch: int, clip_seconds: float, seed: int 
     wave[:, :L] = 0.1 * rng.standard_normal((batch, L)).astype(np.float32)
     mel_len = L // cfg.hop
     n_a = int(projector_output_length(encoder_output_length(mel_len), cfg.proj_k))
+    if projector == "qformer":
+        n_a = int(qformer_output_length(encoder_output_length(mel_len)))
 
     def tid(t):   # map real-tokenizer ids into a reduced vocab deterministically
         return t if t < cfg.vocab - 1 else (t % (cfg.vocab - 1))

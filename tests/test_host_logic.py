@@ -58,7 +58,16 @@ def test_projector_contract():
     assert [k for k, _ in p.named_parameters()] == ["linear_1.weight", "norm.weight", "linear_2.weight", "norm_2.weight"]
     assert p.linear_1.weight.shape == (512, 1024) and p.linear_2.weight.shape == (512, 512)
     with pytest.raises(NotImplementedError):
-        PROJECTOR_CLASSES["qformer"](Cfg())
+        PROJECTOR_CLASSES["moe"](Cfg())
+    # reference tests/test_projectors.py:202-214: qformer lengths 15->3, 16->6, 30->6, 100->21; query shape
+    class QCfg:
+        encoder_dim, llm_dim, qformer_window_size, downsample_rate = 256, 512, 15, 5
+        qformer_hidden_size, qformer_num_layers, qformer_num_heads, qformer_intermediate_size = None, 2, 16, None
+    qf = PROJECTOR_CLASSES["qformer"](QCfg())
+    assert [qf.get_output_length(n) for n in (15, 16, 30, 100)] == [3, 6, 6, 21]
+    assert qf.query.shape == (1, 3, 256)
+    assert torch.equal(qf.get_output_length(torch.tensor([15, 100])), torch.tensor([3, 21]))
+    assert "qformer.encoder.layer.1.crossattention.attention.key.weight" in qf.state_dict() and "linear.bias" in qf.state_dict()
 
 
 def test_gather_audio_embeds_semantics():

@@ -7,24 +7,26 @@ import pytest
 import torch
 
 from oracle import path_oracle as po
-from oracle.make_golden import CASES, sub
+from oracle.make_golden import CASES, case_config, sub
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def load_case(name):
     spec, B, clip_s, pad_s, R, seed = CASES[name]
-    cfg = po.FULL if spec == "full" else po.small_config(**spec)
+    cfg, kind = case_config(spec)
     fx = np.load(os.path.join(GOLD, name + ".npz"))
     W = po.init_weights(cfg, seed=seed)
-    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s)
+    if kind == "qformer":
+        W["projector"] = po.init_qformer_weights(cfg, seed=seed + 1000)
+    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s, projector=kind)
     batch["input_ids"] = torch.from_numpy(fx["input_ids"])
     batch["labels"] = torch.from_numpy(fx["labels"])
     batch["attention_mask"] = torch.from_numpy(fx["attention_mask"])
     return cfg, fx, W, batch
 
 
-@pytest.mark.parametrize("name", ["small_b2_2s", "small_b3_ragged", "h2048_b2_2s", "small_b2_1s_pad30"])
+@pytest.mark.parametrize("name", ["small_b2_2s", "small_b3_ragged", "h2048_b2_2s", "small_b2_1s_pad30", "qformer_b2_2s"])
 def test_oracle_matches_reference_fixture(name):
     torch.set_num_threads(os.cpu_count())
     cfg, fx, W, batch = load_case(name)
@@ -39,6 +41,8 @@ def test_oracle_matches_reference_fixture(name):
     assert int(mask[0].sum()) == L // 160
     # token-count arithmetic (a2) -- integers, exact
     n_a = po.projector_output_length(po.encoder_output_length(L // 160), cfg.proj_k)
+    if "query" in W["projector"]:
+        n_a = po.qformer_output_length(po.encoder_output_length(L // 160))
     assert np.array_equal(fx["audio_token_counts"], np.full(len(fx["audio_token_counts"]), n_a))
     # forward pieces + loss + grads + optimiser (a3-a12)
     res = po.train_step(W, batch, cfg, lr=1e-3, max_grad_norm=1.0, num_items_in_batch=n_items)
@@ -58,8 +62,10 @@ def test_oracle_matches_reference_fixture(name):
         ref = fx["grad_sub." + k]
         assert np.abs(sub(g) - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7
         # torch's fp32 CPU .norm() of a 5M-element tensor carries ~4e-4 relative error (the oracle sums in fp32 pairwise)
-        assert abs(float(g.norm()) - float(fx["grad_l2." + k])) < 1e-3 * float(fx["grad_l2." + k])
-        assert np.abs(sub(res["params"][k]) - fx["new_param_sub." + k]).max() < 2e-5
+        # (gradients that are zero in exact arithmetic -- e.g. attention key biases -- are pure rounding noise: absolute floor)
+        assert abs(float(g.norm()) - float(fx["grad_l2." + k])) < 1e-3 * float(fx["grad_l2." + k]) + 1e-7
+        # (zero-gradient tensors move by lr * noise / (|noise| + eps): allow 1e-4 there)
+        assert np.abs(sub(res["params"][k]) - fx["new_param_sub." + k]).max() < 1e-4
     assert abs(float(res["grad_norm"]) - float(fx["grad_norm"])) < 1e-3 * float(fx["grad_norm"])
 
 

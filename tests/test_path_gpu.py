@@ -153,3 +153,41 @@ def test_greedy_ids_match_oracle(cuda):
     free = hp.greedy_generate(input_ids=prompt.cuda(), max_new_tokens=T, **kw).cpu()
     print("greedy: decisive steps checked", checked, "of", 2 * T, "free-running ids", free.tolist(), "oracle", ref_ids.tolist())
     assert free.shape == ref_ids.shape and checked >= 4
+
+
+def test_qformer_projector_path(cuda):
+    """BASELINE config 4 (projector_type=qformer) through the public ASRModel surface: loss and every projector gradient
+    against the oracle (pinned to the reference by tests/golden/qformer_b2_2s.npz).  Dropout is off (projector.eval()),
+    as in the golden run: the reference's dropout 0.1 has no bit-parity definition."""
+    from oracle.make_golden import CASES, case_config
+    from tiny_audio_b200.synthetic import build_offline_model
+    spec, B, clip_s, pad_s, R, seed = CASES["qformer_b2_2s"]
+    cfg, kind = case_config(spec)
+    fx = np.load(os.path.join(GOLD, "qformer_b2_2s.npz"))
+    W = po.init_weights(cfg, seed=seed)
+    W["projector"] = po.init_qformer_weights(cfg, seed=seed + 1000)
+    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, projector="qformer")
+    n_items = int(fx["num_items"])
+    model = build_offline_model(PathDims.from_any(cfg.to_dict()), device="cuda", enc_state=W["encoder"], lm_state=W["lm"],
+                                proj_state=W["projector"], projector_type="qformer")
+    model.train()
+    model.projector.eval()
+    out = model(input_ids=batch["input_ids"].cuda(), input_features=batch["waveform"].cuda(), labels=batch["labels"],
+                attention_mask=batch["attention_mask"].cuda(), audio_token_counts=batch["audio_token_counts"].cuda(),
+                num_items_in_batch=n_items)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    res = po.train_step(W, batch, cfg, num_items_in_batch=n_items)
+    print(f"[qformer] loss {float(out.loss):.5f} oracle {float(res['loss']):.5f} golden {float(fx['loss']):.5f}")
+    assert abs(float(out.loss) - float(res["loss"])) < 5e-3 and abs(float(out.loss) - float(fx["loss"])) < 5e-3
+    worst = 0.0
+    gmax = max(float(g.norm()) for g in res["grads"].values())
+    for k, p in model.projector.named_parameters():
+        ref = res["grads"][k]
+        if float(ref.norm()) < 1e-5 * gmax:      # zero in exact arithmetic (e.g. key biases under softmax): absolute check
+            assert float(p.grad.float().norm()) < 1e-3 * gmax, k
+            continue
+        e = rel(p.grad, ref)
+        worst = max(worst, e)
+        assert e < 8e-2, f"{k}: {e}"
+    print(f"[qformer] worst projector-grad rel err {worst:.3e} over {len(res['grads'])} tensors")

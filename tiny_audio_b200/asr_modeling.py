@@ -65,6 +65,27 @@ class _FusedPathLoss(torch.autograd.Function):
         return outs + (None, None)
 
 
+class _LmLossFn(torch.autograd.Function):
+    """loss(audio_embeds) for any projector: <audio> scatter -> Qwen3 -> CE with d(loss)/d(audio_embeds) computed in the same
+    pass by the CUDA engine; autograd then continues into the projector that produced `audio_embeds`."""
+
+    @staticmethod
+    def forward(ctx, audio, model, call):
+        hot: HotPath = model._hot_path()
+        B, n_a, D = audio.shape
+        flat = audio.detach().float().contiguous().view(B * n_a, D)
+        loss, d_audio = hot.lm_loss_and_audio_grad(audio=flat, n_a=n_a, with_backward=ctx.needs_input_grad[0], **call)
+        ctx.d_audio = d_audio.view(B, n_a, D).clone() if d_audio is not None else None
+        ctx.dtype = audio.dtype
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        if ctx.d_audio is None:
+            return None, None, None
+        return (ctx.d_audio * gout).to(ctx.dtype), None, None
+
+
 class ASRModel(PreTrainedModel, GenerationMixin):
     """Audio encoder (frozen) + projector (trainable) + causal LM (frozen): the reference's composition."""
 
@@ -306,7 +327,17 @@ class ASRModel(PreTrainedModel, GenerationMixin):
         if self.training and p > 0.0:
             call["frame_keep_prob"] = 1.0 - p
         pr = self.projector
-        loss = _FusedPathLoss.apply(pr.linear_1.weight, pr.norm.weight, pr.linear_2.weight, pr.norm_2.weight, self, call)
+        from .projectors import MLPAudioProjector
+        if isinstance(pr, MLPAudioProjector):
+            # fully fused path: projector forward/backward run inside the CUDA engine together with the towers
+            loss = _FusedPathLoss.apply(pr.linear_1.weight, pr.norm.weight, pr.linear_2.weight, pr.norm_2.weight, self, call)
+        else:
+            # generic projector (qformer): frozen encoder -> projector module (autograd) -> CUDA decoder + CE with
+            # d(loss)/d(audio embeddings) handed back to autograd
+            enc = hot.encode_audio(waveform=call.pop("waveform", None), input_features=call.pop("input_features", None),
+                                   frame_keep_prob=call.pop("frame_keep_prob", None)).clone()
+            audio = pr(enc)
+            loss = _LmLossFn.apply(audio.float(), self, call)
         if labels is None:
             loss = None
         return CausalLMOutputWithPast(loss=loss, logits=None)

@@ -125,7 +125,7 @@ __global__ void rmsnorm_f32_kernel(const float* __restrict__ x, const float* __r
 template <int MAXV>
 __global__ void rmsnorm_f32_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                                        float* __restrict__ dx, const int* __restrict__ row_index, long long rows, int D,
-                                       float eps, int accumulate) {
+                                       float eps, int accumulate, bf16* __restrict__ dx_bf16) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -166,6 +166,7 @@ __global__ void rmsnorm_f32_bwd_kernel(const bf16* __restrict__ dy, const float*
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] += rstd * (gv[i][j] - xv[i][j] * rstd * dot);
             st8_f32(dx + dst * D + c, o);
+            if (dx_bf16) st8_bf16(dx_bf16 + dst * D + c, o);   // operand of the next dgrad GEMM (autocast rounds the branch grad)
         }
 }
 
@@ -631,13 +632,13 @@ int k_rmsnorm_f32(const float* x, const float* w, bf16* y, const int* row_index,
 }
 
 int k_rmsnorm_f32_bwd(const bf16* dy, const float* x, const float* w, float* dx, const int* row_index, long long rows, int D,
-                      float eps, int accumulate, cudaStream_t st) {
+                      float eps, int accumulate, cudaStream_t st, bf16* dx_bf16) {
     TA_REQUIRE(D % 256 == 0 && D <= 2048, "rmsnorm bwd: D=%d must be a multiple of 256 and <= 2048", D);
     if (rows == 0) return 0;
     const int wpb = 8;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    if (D <= 1024) rmsnorm_f32_bwd_kernel<4><<<grid, wpb * 32, 0, st>>>(dy, x, w, dx, row_index, rows, D, eps, accumulate);
-    else rmsnorm_f32_bwd_kernel<8><<<grid, wpb * 32, 0, st>>>(dy, x, w, dx, row_index, rows, D, eps, accumulate);
+    if (D <= 1024) rmsnorm_f32_bwd_kernel<4><<<grid, wpb * 32, 0, st>>>(dy, x, w, dx, row_index, rows, D, eps, accumulate, dx_bf16);
+    else rmsnorm_f32_bwd_kernel<8><<<grid, wpb * 32, 0, st>>>(dy, x, w, dx, row_index, rows, D, eps, accumulate, dx_bf16);
     TA_LAUNCH_CHECK();
     return 0;
 }
@@ -775,7 +776,7 @@ TA_API int ta_rmsnorm_f32(const float* x, const float* w, void* y, const int* ro
 }
 TA_API int ta_rmsnorm_f32_bwd(const void* dy, const float* x, const float* w, float* dx, const int* row_index, long long rows, int D,
                               float eps, int accumulate, void* stream) {
-    return k_rmsnorm_f32_bwd((const bf16*)dy, x, w, dx, row_index, rows, D, eps, accumulate, ST(stream));
+    return k_rmsnorm_f32_bwd((const bf16*)dy, x, w, dx, row_index, rows, D, eps, accumulate, ST(stream), nullptr);
 }
 TA_API int ta_enc_rope(void* qkv, const float* cosT, const float* sinT, long long rows, int S, int H, int hd, int rd, void* stream) {
     return k_enc_rope((bf16*)qkv, cosT, sinT, rows, S, H, hd, rd, ST(stream));

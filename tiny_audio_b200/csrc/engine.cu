@@ -314,6 +314,7 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
                  nullptr, nullptr, 0, nullptr, 0, st));
         RUN(k_rmsnorm_f32_bwd(b.dhl, x_final, w->final_norm_w, dx, a->label_rows, nl, D, w->eps, 0, st));
     }
+    RUN(k_cast_f32_bf16(dx, b.dxb, M * D, st));   // later bf16 copies of dx come out of the RMSNorm-backward kernels
     for (int l = Lyr - 1; l >= 0; --l) {
         const void* const* Lw = w->layers + (long long)l * TA_LM_PTRS_PER_LAYER;
         const bf16* qkv = b.qkv + (long long)l * M * QKV;
@@ -324,20 +325,18 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
         const bf16* gu = b.gu + (long long)l * M * 2 * F;
         const float* x_l = (l == 0) ? a->inputs_embeds : (b.resid + (long long)l * M * D);
 
-        // MLP branch
-        RUN(k_cast_f32_bf16(dx, b.dxb, M * D, st));
+        // MLP branch (b.dxb = bf16(dx) was written by the previous RMSNorm backward / the cast above)
         RUN(gemm(b.dxb, D, Lw[TA_LM_WD_T], D, M, F, D, TA_EPI_SWIGLU_BWD, b.big, 2 * F, nullptr, nullptr, nullptr, 0, gu, 2 * F, st));
         RUN(gemm(b.big, 2 * F, Lw[TA_LM_WGU_T], 2 * F, M, D, 2 * F, TA_EPI_BF16, b.dxn, D, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
-        RUN(k_rmsnorm_f32_bwd(b.dxn, x_mid, (const float*)Lw[TA_LM_LN2_W], dx, nullptr, M, D, w->eps, 1, st));
+        RUN(k_rmsnorm_f32_bwd(b.dxn, x_mid, (const float*)Lw[TA_LM_LN2_W], dx, nullptr, M, D, w->eps, 1, st, b.dxb));
         // attention branch
-        RUN(k_cast_f32_bf16(dx, b.dxb, M * D, st));
         RUN(gemm(b.dxb, D, Lw[TA_LM_WO_T], D, M, QD, D, TA_EPI_BF16, b.datt, QD, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
         RUN(ta_attn_bwd(qk, qk + QD, qkv + QK, att, b.datt, lse, b.dsum, b.dq, b.dk, b.dv, B, S, Hq, Hkv, hd, QK, QK, QKV, QD, QD, QD,
                         KD, KD, 1, scale, st));
         RUN(k_lm_qknorm_rope_bwd(qkv, b.dq, b.dk, b.dv, b.big, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W],
                                  w->rope_cos, w->rope_sin, M, S, Hq, Hkv, w->eps, st));
         RUN(gemm(b.big, QKV, Lw[TA_LM_WQKV_T], QKV, M, D, QKV, TA_EPI_BF16, b.dxn, D, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
-        RUN(k_rmsnorm_f32_bwd(b.dxn, x_l, (const float*)Lw[TA_LM_LN1_W], dx, nullptr, M, D, w->eps, 1, st));
+        RUN(k_rmsnorm_f32_bwd(b.dxn, x_l, (const float*)Lw[TA_LM_LN1_W], dx, nullptr, M, D, w->eps, 1, st, l > 0 ? b.dxb : nullptr));
     }
     return 0;
 }

@@ -6,7 +6,7 @@ int k_im2col_k3(const bf16* x, bf16* out, int B, int T, int C, int stride, cudaS
 int k_layernorm_bf16(const bf16* x, const float* w, const float* b, bf16* y, long long rows, int D, float eps, cudaStream_t st);
 int k_rmsnorm_f32(const float* x, const float* w, bf16* y, const int* row_index, long long rows, int D, float eps, cudaStream_t st);
 int k_rmsnorm_f32_bwd(const bf16* dy, const float* x, const float* w, float* dx, const int* row_index, long long rows, int D,
-                      float eps, int accumulate, cudaStream_t st);
+                      float eps, int accumulate, cudaStream_t st, bf16* dx_bf16 = nullptr);
 int k_enc_rope(bf16* qkv, const float* cosT, const float* sinT, long long rows, int S, int H, int hd, int rd, cudaStream_t st);
 int k_lm_qknorm_rope_fwd(const bf16* qkv, bf16* qk, const float* qw, const float* kw, const float* cosT, const float* sinT,
                          long long M, int S, int Hq, int Hkv, float eps, cudaStream_t st);

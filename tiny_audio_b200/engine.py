@@ -406,6 +406,47 @@ class HotPath:
                 break
         return torch.stack(out, dim=1)
 
+    def lm_loss_and_audio_grad(self, *, input_ids, labels_cpu, audio, n_a, audio_token_counts=None, num_items_in_batch=None,
+                               with_backward=True):
+        """<audio> scatter -> Qwen3 -> CE (-> backward to the audio embeddings).  `audio` fp32 [B*n_a, lm_dim].
+        Returns (loss [1], d_audio [B*n_a, lm_dim] or None).  Projector-agnostic: any module that produces the audio
+        embeddings can sit in front of it (ASRModel uses it for every projector except the fused MLP path)."""
+        d = self.dims
+        B, S = input_ids.shape
+        if audio_token_counts is None:
+            audio_token_counts = (input_ids == d.audio_token_id).sum(-1)
+        counts = audio_token_counts.to(device=self.device, dtype=torch.int64).contiguous()
+        ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
+        emb, src = self.embed_scatter(ids, counts, audio, n_a)
+        if labels_cpu is not None:
+            rows, targets = label_rows_and_targets(labels_cpu)
+            n_items = float(rows.numel()) if num_items_in_batch is None else float(num_items_in_batch)
+            rows_d, tg_d = rows.to(self.device, non_blocking=True), targets.to(self.device, non_blocking=True)
+        else:
+            rows_d = torch.empty(0, dtype=torch.int32, device=self.device)
+            tg_d, n_items = rows_d, 1.0
+        loss, demb, _ = self.lm_step(emb, B, S, rows_d, tg_d, 1.0 / max(n_items, 1.0), with_backward)
+        d_audio = None
+        if with_backward:
+            d_audio = self.ws.typed("d_audio", (B * n_a, d.lm_dim), F32)
+            d_audio.zero_()
+            L.check(self.lib.ta_audio_grad_gather(L.ptr(src), L.ptr(demb), L.ptr(d_audio), B * S, d.lm_dim, L.stream_ptr()))
+        return loss, d_audio
+
+    @torch.no_grad()
+    def encode_audio(self, *, waveform=None, input_features=None, frame_keep_prob=None):
+        """log-mel (if needed) + frozen encoder (+ audio-token dropout) -> bf16 [B, S_e, enc_dim]."""
+        B = (waveform if waveform is not None else input_features).shape[0]
+        if waveform is not None:
+            im2, _, T = self.logmel(waveform)
+        else:
+            im2, T = self.mel_to_im2col(input_features)
+        enc = self.encode(im2, B, T)
+        if frame_keep_prob is not None and frame_keep_prob < 1.0:
+            keep = torch.bernoulli(torch.full(enc.shape[:-1], float(frame_keep_prob), device=self.device, dtype=F32))
+            enc.mul_(keep.unsqueeze(-1).to(enc.dtype))
+        return enc
+
     # ------------------------------------------------------------------ the whole step
     def forward_backward(self, *, input_ids: torch.Tensor, labels_cpu: Optional[torch.Tensor], proj_params,
                          waveform: Optional[torch.Tensor] = None, input_features: Optional[torch.Tensor] = None,

@@ -24,7 +24,7 @@ def num_audio_tokens(n_samples: int, hop: int = 160, k: int = 4) -> int:
 
 
 def synthetic_batch(dims: PathDims, batch: int, clip_seconds: float, seed: int = 0, response_len: int = 64,
-                    pad_to_seconds: Optional[float] = None, pin: bool = False) -> Dict[str, torch.Tensor]:
+                    pad_to_seconds: Optional[float] = None, pin: bool = False, projector: str = "mlp") -> Dict[str, torch.Tensor]:
     """Equal-length clips `0.1*N(0,1)`, prompt = chat template with N_a `<audio>` tokens, R seeded response ids,
     labels = -100 except response + <|im_end|>  (SURVEY.md section 8d)."""
     rng = np.random.default_rng(seed)
@@ -34,6 +34,8 @@ def synthetic_batch(dims: PathDims, batch: int, clip_seconds: float, seed: int =
     wave = np.zeros((batch, n_pad), dtype=np.float32)
     wave[:, :n] = 0.1 * rng.standard_normal((batch, n)).astype(np.float32)
     n_a = num_audio_tokens(n, dims.hop, dims.proj_k)
+    if projector == "qformer":                      # ceil(S_e / 15) windows x 3 queries (projectors.py:422-430)
+        n_a = (((n // dims.hop + 2 - 3) // 2 + 1) + 14) // 15 * 3
     V = dims.vocab
 
     def tid(t):
@@ -86,7 +88,7 @@ class StubTokenizer:
 
 
 def build_offline_model(dims: PathDims, device="cuda", seed: int = 1234, enc_state=None, lm_state=None, proj_state=None,
-                        audio_token_dropout: float = 0.0):
+                        audio_token_dropout: float = 0.0, projector_type: str = "mlp"):
     """ASRModel (tiny_audio_b200.asr_modeling) with GLM-ASR / Qwen3 modules of the given dims, random (seeded) or
     supplied weights, fp32 masters -- no network, no checkpoints."""
     from transformers import GlmAsrEncoderConfig, Qwen3Config, Qwen3ForCausalLM
@@ -139,7 +141,7 @@ def build_offline_model(dims: PathDims, device="cuda", seed: int = 1234, enc_sta
 
     _Offline.__name__ = "ASRModel"
     cfg = ASRConfig(audio_config=enc_cfg, text_config=txt_cfg, model_dtype="float32", attn_implementation="sdpa",
-                    projector_type="mlp", projector_pool_stride=dims.proj_k, projector_hidden_dim=dims.proj_hidden,
+                    projector_type=projector_type, projector_pool_stride=dims.proj_k, projector_hidden_dim=dims.proj_hidden,
                     audio_token_dropout=audio_token_dropout)
     torch.manual_seed(seed + 3)
     model = _Offline(cfg)
