@@ -271,9 +271,12 @@ def run_ours(args):
         t = e0.elapsed_time(e1) / reps / 1000.0
         ach = 2.0 * M * N * K / t / 1e12
         peak = pk["bf16_tflops"]
-        roof = {"bound": "tensor", "kernel": f"gemm_kernel<256,BF16_GELU> M={M} N={N} K={K} (encoder fc1)", "achieved": ach,
+        roof = {"bound": "tensor", "kernel": f"gemm2_kernel<256,BF16_GELU> (cta_group::2) M={M} N={N} K={K} (encoder fc1)", "achieved": ach,
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": f"{how} burst (kernel timed alone)",
-                "traffic": None, "step_tflops": 116.0e9 * audio_s / (ms_step / 1000.0) / 1e12 / world,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+                # (profiles/r01_ncu_top_kernels_summary.txt: 136.2 MB + 440.4 MB; algorithmic A + W + C = 626.7 MB, part of C stays in L2)
+                "traffic": 576.5e6 if (M, N, K) == (48000, 5120, 1280) else None,
+                "algorithmic_bytes": 2.0 * (M * K + N * K + M * N), "tensor_pipe_active_pct_ncu": 74.5, "step_tflops": 116.0e9 * audio_s / (ms_step / 1000.0) / 1e12 / world,
                 "step_frac_of_sustained": 116.0e9 * audio_s / (ms_step / 1000.0) / 1e12 / world / pk["bf16_tflops_sustained"]}
         del a, w, out
 
