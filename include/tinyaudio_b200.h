@@ -183,11 +183,20 @@ int ta_mlp_projector_backward(const ta_mlp_projector_weights* w, const void* x_s
  *   HF:loss/loss_utils.py:45-67, autograd backward HF:trainer.py:1935.  lm_head is evaluated on the labelled rows.
  * ---------------------------------------------------------------------------------------------- */
 enum { TA_LM_LN1_W = 0, TA_LM_WQKV, TA_LM_WQKV_T, TA_LM_QNORM_W, TA_LM_KNORM_W, TA_LM_WO, TA_LM_WO_T, TA_LM_LN2_W,
-       TA_LM_WGU, TA_LM_WGU_T, TA_LM_WD, TA_LM_WD_T, TA_LM_PTRS_PER_LAYER };
+       TA_LM_WGU, TA_LM_WGU_T, TA_LM_WD, TA_LM_WD_T,
+       /* LoRA (a11; tiny_audio/asr_modeling.py:289-301, peft r=8 alpha=32 on q,k,v,o,gate,up,down), NULL when lora_pad == 0:
+          A_*  bf16 [lora_pad, K_in]   stacked lora_A of the fused projection's adapters (q|k|v -> rows 0-7, 8-15, 16-23)
+          BT_* bf16 [lora_pad, N_out]  (alpha/r * lora_B)^T with the same row blocks                                     */
+       TA_LM_LORA_A_QKV, TA_LM_LORA_A_O, TA_LM_LORA_A_GU, TA_LM_LORA_A_D,
+       TA_LM_LORA_BT_QKV, TA_LM_LORA_BT_O, TA_LM_LORA_BT_GU, TA_LM_LORA_BT_D, TA_LM_PTRS_PER_LAYER };
+/* per-layer LoRA gradient outputs (fp32, caller-owned): dA [lora_pad, K_in] and dB' [N_out, lora_pad] = d loss / d (alpha/r * B) */
+enum { TA_LM_LORA_DA_QKV = 0, TA_LM_LORA_DB_QKV, TA_LM_LORA_DA_O, TA_LM_LORA_DB_O, TA_LM_LORA_DA_GU, TA_LM_LORA_DB_GU,
+       TA_LM_LORA_DA_D, TA_LM_LORA_DB_D, TA_LM_LORA_GRADS_PER_LAYER };
 typedef struct ta_lm_weights {
     int n_layers, dim, ffn, n_q_heads, n_kv_heads, head_dim, max_pos;
     long long vocab, vocab_pad;
     float eps;
+    int lora_pad;               /* 0, or 128: every W* / W*_T below carries lora_pad extra K columns ([W | aB] resp. [W^T | A^T]) */
     const float* embed_f32;     /* [vocab, dim]  (embedding lookup stays fp32 under autocast)            */
     const void* embed_bf16;     /* [vocab_pad, dim] bf16, rows >= vocab are zero (tied lm_head)          */
     const void* embed_bf16_t;   /* [dim, vocab_pad] bf16 (dgrad operand)                                  */
@@ -212,6 +221,7 @@ typedef struct ta_lm_step_args {
     void* workspace;
     long long workspace_bytes;
     float* final_hidden;          /* optional [B*S, dim] fp32: last layer's output BEFORE the final norm (for ta_lm_hidden_to_logits) */
+    float* const* lora_grads;     /* LoRA + backward: HOST array n_layers * TA_LM_LORA_GRADS_PER_LAYER device pointers */
 } ta_lm_step_args;
 int ta_lm_workspace_bytes(const ta_lm_weights* w, int B, int S, int n_labelled, int with_backward, long long* bytes);
 int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args* a, void* stream);

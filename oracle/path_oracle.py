@@ -419,9 +419,31 @@ def scatter_audio(inputs_embeds: Tensor, input_ids: Tensor, packed: Tensor, audi
 # --------------------------------------------------------------------------------------
 # a8/a9. Qwen3 forward + CE (HF:models/qwen3/modeling_qwen3.py:378-517; HF:loss/loss_utils.py:28-67)
 # --------------------------------------------------------------------------------------
+def init_lora_weights(cfg: PathConfig, seed: int = 55, rank: int = 8, alpha: float = 32.0, b_std: float = 0.02):
+    """peft-style adapters for q,k,v,o,gate,up,down of every decoder layer, stacked over layers: A [L, r, in] (kaiming-uniform
+    like peft), B [L, out, r].  peft initialises B to zero; a small random B is used here so that every gradient path is live."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    D, Fl, hd = cfg.lm_dim, cfg.lm_ffn, cfg.lm_head_dim
+    dims = {"q_proj": (D, cfg.lm_heads * hd), "k_proj": (D, cfg.lm_kv_heads * hd), "v_proj": (D, cfg.lm_kv_heads * hd),
+            "o_proj": (cfg.lm_heads * hd, D), "gate_proj": (D, Fl), "up_proj": (D, Fl), "down_proj": (Fl, D)}
+    A, Bm = {}, {}
+    for k, (i, o) in dims.items():
+        bound = 1.0 / math.sqrt(i)          # kaiming_uniform_(a=sqrt(5)) on [r, in]
+        A[k] = (torch.rand(cfg.lm_layers, rank, i, generator=g) * 2 - 1) * bound
+        Bm[k] = torch.randn(cfg.lm_layers, o, rank, generator=g) * b_std
+    return {"A": A, "B": Bm, "scaling": alpha / rank}
+
+
 def lm_forward(w: Dict[str, Tensor], inputs_embeds: Tensor, cfg: PathConfig = FULL,
-               attention_mask: Optional[Tensor] = None) -> Tensor:
-    """inputs_embeds (B, S, D) -> final-norm hidden states (B, S, D)."""
+               attention_mask: Optional[Tensor] = None, lora=None) -> Tensor:
+    """inputs_embeds (B, S, D) -> final-norm hidden states (B, S, D).  `lora`: adapters of init_lora_weights
+    (peft semantics: y = W x + alpha/r * B(A(x)), dropout 0; tiny_audio/asr_modeling.py:289-301)."""
+    def lin(x, name, layer, proj):
+        y = F.linear(x, w[name])
+        if lora is not None and proj in lora["A"]:
+            y = y + lora["scaling"] * F.linear(F.linear(x, lora["A"][proj][layer]), lora["B"][proj][layer])
+        return y
+
     x = inputs_embeds
     B, S, D = x.shape
     Hq, Hkv, hd = cfg.lm_heads, cfg.lm_kv_heads, cfg.lm_head_dim
@@ -433,9 +455,9 @@ def lm_forward(w: Dict[str, Tensor], inputs_embeds: Tensor, cfg: PathConfig = FU
     for i in range(cfg.lm_layers):
         p = f"model.layers.{i}."
         h = rms_norm(x, w[p + "input_layernorm.weight"], cfg.lm_eps)
-        q = F.linear(h, w[p + "self_attn.q_proj.weight"]).view(B, S, Hq, hd)
-        k = F.linear(h, w[p + "self_attn.k_proj.weight"]).view(B, S, Hkv, hd)
-        v = F.linear(h, w[p + "self_attn.v_proj.weight"]).view(B, S, Hkv, hd)
+        q = lin(h, p + "self_attn.q_proj.weight", i, "q_proj").view(B, S, Hq, hd)
+        k = lin(h, p + "self_attn.k_proj.weight", i, "k_proj").view(B, S, Hkv, hd)
+        v = lin(h, p + "self_attn.v_proj.weight", i, "v_proj").view(B, S, Hkv, hd)
         q = rms_norm(q, w[p + "self_attn.q_norm.weight"], cfg.lm_eps).transpose(1, 2)
         k = rms_norm(k, w[p + "self_attn.k_norm.weight"], cfg.lm_eps).transpose(1, 2)
         v = v.transpose(1, 2)
@@ -447,10 +469,10 @@ def lm_forward(w: Dict[str, Tensor], inputs_embeds: Tensor, cfg: PathConfig = FU
         s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
         s = s.masked_fill(~mask, float("-inf"))
         att = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, S, Hq * hd)
-        x = x + F.linear(att, w[p + "self_attn.o_proj.weight"])
+        x = x + lin(att, p + "self_attn.o_proj.weight", i, "o_proj")
         h = rms_norm(x, w[p + "post_attention_layernorm.weight"], cfg.lm_eps)
-        h = F.silu(F.linear(h, w[p + "mlp.gate_proj.weight"])) * F.linear(h, w[p + "mlp.up_proj.weight"])
-        x = x + F.linear(h, w[p + "mlp.down_proj.weight"])
+        h = F.silu(lin(h, p + "mlp.gate_proj.weight", i, "gate_proj")) * lin(h, p + "mlp.up_proj.weight", i, "up_proj")
+        x = x + lin(h, p + "mlp.down_proj.weight", i, "down_proj")
     return rms_norm(x, w["model.norm.weight"], cfg.lm_eps)
 
 
@@ -492,7 +514,7 @@ def model_forward(W, batch: Dict[str, Tensor], cfg: PathConfig = FULL, num_items
     emb = F.embedding(ids, W["lm"]["model.embed_tokens.weight"])
     emb = scatter_audio(emb, ids, packed, cfg.audio_token_id)
     parts["inputs_embeds"] = emb
-    hid = lm_forward(W["lm"], emb, cfg, batch.get("attention_mask"))
+    hid = lm_forward(W["lm"], emb, cfg, batch.get("attention_mask"), W.get("lora"))
     parts["hidden"] = hid
     logits = F.linear(hid, W["lm"]["lm_head.weight"])
     loss = None
@@ -551,9 +573,18 @@ def train_step(W, batch, cfg: PathConfig = FULL, lr=1e-3, max_grad_norm=1.0, wei
     """One optimiser step on the projector (configs 1-3).  Returns loss, grads, new params, state."""
     proj = {k: v.detach().clone().requires_grad_(True) for k, v in W["projector"].items()}
     W2 = {"encoder": W["encoder"], "lm": W["lm"], "projector": proj}
+    lora = None
+    if W.get("lora") is not None:
+        lora = {"scaling": W["lora"]["scaling"],
+                "A": {k: v.detach().clone().requires_grad_(True) for k, v in W["lora"]["A"].items()},
+                "B": {k: v.detach().clone().requires_grad_(True) for k, v in W["lora"]["B"].items()}}
+        W2["lora"] = lora
     loss, _ = model_forward(W2, batch, cfg, num_items_in_batch)
     loss.backward()
     grads = {k: v.grad.detach() for k, v in proj.items()}
+    lora_grads = None
+    if lora is not None:
+        lora_grads = {"A": {k: v.grad.detach() for k, v in lora["A"].items()}, "B": {k: v.grad.detach() for k, v in lora["B"].items()}}
     gnorm, coef = clip_grad_norm(grads, max_grad_norm)
     if state is None:
         state = {"step": 0, "m": {k: torch.zeros_like(v) for k, v in proj.items()},
@@ -567,7 +598,7 @@ def train_step(W, batch, cfg: PathConfig = FULL, lr=1e-3, max_grad_norm=1.0, wei
             proj[k].detach(), grads[k] * coef, state["m"][k], state["v"][k], state["step"], lr,
             weight_decay=wd)
     return {"loss": loss.detach(), "grads": grads, "grad_norm": gnorm, "clip_coef": coef,
-            "params": new_p, "state": state}
+            "params": new_p, "state": state, "lora_grads": lora_grads}
 
 
 # --------------------------------------------------------------------------------------

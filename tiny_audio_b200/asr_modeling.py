@@ -43,26 +43,43 @@ def _gather_audio_embeds(audio_embeds: torch.Tensor, token_counts: torch.Tensor)
 
 
 class _FusedPathLoss(torch.autograd.Function):
-    """loss = CE(Qwen3(scatter(projector(encoder(audio))))) with d(loss)/d(projector params) computed in the
-    same pass; backward only rescales the stored gradients by the incoming scalar."""
+    """loss = CE(Qwen3(scatter(projector(encoder(audio))))) with d(loss)/d(projector params) -- and d(loss)/d(LoRA A, B) when
+    adapters are attached -- computed in the same pass; backward only rescales the stored gradients by the incoming scalar.
+    Tensor arguments: the 4 projector parameters, then the stacked lora_A tensors, then the stacked lora_B tensors."""
 
     @staticmethod
-    def forward(ctx, w1, n1, w2, n2, model, call):
+    def forward(ctx, model, call, w1, n1, w2, n2, *lora_tensors):
         hot: HotPath = model._hot_path()
         params = {k: p.detach().float().contiguous() for k, p in zip(_PROJ_KEYS, (w1, n1, w2, n2))}
-        need = any(ctx.needs_input_grad[:4])
+        need = any(ctx.needs_input_grad[2:6])
         grads = {k: torch.empty_like(v) for k, v in params.items()} if need else None
-        loss, _ = hot.forward_backward(proj_params=params, grads=grads, **call)
+        adapters = getattr(model, "lora_adapters", None)
+        n_l = len(lora_tensors) // 2
+        need_lora = adapters is not None and any(ctx.needs_input_grad[6:])
+        if adapters is not None:
+            names = adapters.targets
+            hot.lm.update_lora({t: a.detach() for t, a in zip(names, lora_tensors[:n_l])},
+                               {t: b.detach() for t, b in zip(names, lora_tensors[n_l:])}, adapters.scaling)
+        loss, _ = hot.forward_backward(proj_params=params, grads=grads, lm_backward=need_lora, **call)
         ctx.grads = grads
         ctx.dtypes = (w1.dtype, n1.dtype, w2.dtype, n2.dtype)
+        ctx.lora_grads = None
+        if need_lora:
+            ga, gb = hot.lm.lora_grads(adapters.scaling, {t: adapters.rank for t in adapters.targets})
+            ctx.lora_grads = [ga[t].clone() for t in names] + [gb[t].clone() for t in names]
+            ctx.lora_dtypes = [t.dtype for t in lora_tensors]
+        ctx.n_lora = len(lora_tensors)
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, gout):
-        if ctx.grads is None:
-            return (None,) * 6
-        outs = tuple((ctx.grads[k] * gout).to(dt) for k, dt in zip(_PROJ_KEYS, ctx.dtypes))
-        return outs + (None, None)
+        proj = (None,) * 4
+        if ctx.grads is not None:
+            proj = tuple((ctx.grads[k] * gout).to(dt) for k, dt in zip(_PROJ_KEYS, ctx.dtypes))
+        lora = (None,) * ctx.n_lora
+        if ctx.lora_grads is not None:
+            lora = tuple((g * gout).to(dt) for g, dt in zip(ctx.lora_grads, ctx.lora_dtypes))
+        return (None, None) + proj + lora
 
 
 class _LmLossFn(torch.autograd.Function):
@@ -182,7 +199,19 @@ class ASRModel(PreTrainedModel, GenerationMixin):
         return proj.to(device=device, dtype=dtype)
 
     def _setup_lora(self, config: ASRConfig):
-        raise NotImplementedError("use_lora=True (BASELINE config 5) is a 'next' row and not built in this round")
+        """Attach LoRA adapters to the decoder (reference: asr_modeling.py:289-301 via peft; restated in lora.py).  The
+        container is registered under the language model so that its parameters are named `language_model.*`, which is
+        what scripts/train.py:413-418 keys the decoder learning-rate group on."""
+        from .lora import LoraAdapters
+        adapters = LoraAdapters(self.language_model.config, rank=config.lora_rank, alpha=config.lora_alpha,
+                                target_modules=config.lora_target_modules, dropout=config.lora_dropout)
+        dev = next(self.language_model.parameters()).device
+        self.language_model.add_module("lora_adapters", adapters.to(dev))
+        self._hot = None
+
+    @property
+    def lora_adapters(self):
+        return getattr(self.language_model, "lora_adapters", None)
 
     def _init_tokenizer(self, config: ASRConfig):
         from transformers import AutoTokenizer
@@ -235,7 +264,8 @@ class ASRModel(PreTrainedModel, GenerationMixin):
                             encoder_conv_layers=self.config.encoder_conv_layers)
 
     def state_dict(self, *args, **kwargs):
-        """Trainable weights only (projector), reference key names (`projector.linear_1.weight`, ...)."""
+        """Trainable weights only (projector), reference key names (`projector.linear_1.weight`, ...).  LoRA adapters are
+        serialised separately (peft layout, `lora_adapters.peft_state_dict()`), as in the reference (asr_modeling.py:398-422)."""
         return {f"projector.{k}": v for k, v in self.projector.state_dict().items()}
 
     def _compute_encoder_output_lengths(self, audio_attention_mask: torch.Tensor) -> torch.Tensor:
@@ -271,7 +301,8 @@ class ASRModel(PreTrainedModel, GenerationMixin):
         key = (dev.index, self.language_model.get_input_embeddings().weight.data_ptr())
         if self._hot is None or self._hot_key != key:
             with torch.no_grad():
-                self._hot = HotPath(self.path_dims(), self.audio_tower.state_dict(), self.language_model.state_dict(), dev)
+                lm_sd = {k: v for k, v in self.language_model.state_dict().items() if not k.startswith("lora_adapters.")}
+                self._hot = HotPath(self.path_dims(), self.audio_tower.state_dict(), lm_sd, dev, lora=self.lora_adapters is not None)
             self._hot_key = key
         return self._hot
 
@@ -330,7 +361,11 @@ class ASRModel(PreTrainedModel, GenerationMixin):
         from .projectors import MLPAudioProjector
         if isinstance(pr, MLPAudioProjector):
             # fully fused path: projector forward/backward run inside the CUDA engine together with the towers
-            loss = _FusedPathLoss.apply(pr.linear_1.weight, pr.norm.weight, pr.linear_2.weight, pr.norm_2.weight, self, call)
+            lora_t = ()
+            if self.lora_adapters is not None:
+                la, lb = self.lora_adapters.tensors()
+                lora_t = tuple(la.values()) + tuple(lb.values())
+            loss = _FusedPathLoss.apply(self, call, pr.linear_1.weight, pr.norm.weight, pr.linear_2.weight, pr.norm_2.weight, *lora_t)
         else:
             # generic projector (qformer): frozen encoder -> projector module (autograd) -> CUDA decoder + CE with
             # d(loss)/d(audio embeddings) handed back to autograd

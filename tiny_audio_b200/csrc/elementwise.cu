@@ -92,7 +92,7 @@ __global__ void layernorm_bf16_kernel(const bf16* __restrict__ x, const float* _
 // =============================================================================================================
 template <int MAXV>
 __global__ void rmsnorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y,
-                                   const int* __restrict__ row_index, long long rows, int D, float eps) {
+                                   const int* __restrict__ row_index, long long rows, int D, float eps, long long ldy) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -116,7 +116,7 @@ __global__ void rmsnorm_f32_kernel(const float* __restrict__ x, const float* __r
             ld8_f32(w + c, ww);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = ww[j] * (v[i][j] * rstd);
-            st8_bf16(y + row * D + c, o);
+            st8_bf16(y + row * ldy + c, o);
         }
 }
 
@@ -125,7 +125,7 @@ __global__ void rmsnorm_f32_kernel(const float* __restrict__ x, const float* __r
 template <int MAXV>
 __global__ void rmsnorm_f32_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                                        float* __restrict__ dx, const int* __restrict__ row_index, long long rows, int D,
-                                       float eps, int accumulate, bf16* __restrict__ dx_bf16) {
+                                       float eps, int accumulate, bf16* __restrict__ dx_bf16, long long ld_b) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -166,7 +166,7 @@ __global__ void rmsnorm_f32_bwd_kernel(const bf16* __restrict__ dy, const float*
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] += rstd * (gv[i][j] - xv[i][j] * rstd * dot);
             st8_f32(dx + dst * D + c, o);
-            if (dx_bf16) st8_bf16(dx_bf16 + dst * D + c, o);   // operand of the next dgrad GEMM (autocast rounds the branch grad)
+            if (dx_bf16) st8_bf16(dx_bf16 + dst * ld_b + c, o);   // operand of the next dgrad GEMM (autocast rounds the branch grad)
         }
 }
 
@@ -229,7 +229,8 @@ __global__ void lm_qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, bf16* __
 __global__ void lm_qknorm_rope_bwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ dq, const bf16* __restrict__ dk,
                                           const bf16* __restrict__ dv, bf16* __restrict__ dqkv, const float* __restrict__ qw,
                                           const float* __restrict__ kw, const float* __restrict__ cosT,
-                                          const float* __restrict__ sinT, long long M, int S, int Hq, int Hkv, float eps) {
+                                          const float* __restrict__ sinT, long long M, int S, int Hq, int Hkv, float eps,
+                                          long long ld_out) {
     const int HD = 128;
     const int heads = Hq + 2 * Hkv;
     const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -237,7 +238,7 @@ __global__ void lm_qknorm_rope_bwd_kernel(const bf16* __restrict__ qkv, const fl
     const int lane = threadIdx.x & 31;
     const int h = (int)(wid % heads);
     const long long row = wid / heads;
-    bf16* dst = dqkv + row * (long long)(heads * HD) + (long long)h * HD;
+    bf16* dst = dqkv + row * ld_out + (long long)h * HD;
     if (h >= Hq + Hkv) {   // v: plain copy
         const bf16* s = dv + row * (long long)(Hkv * HD) + (long long)(h - Hq - Hkv) * HD;
         *reinterpret_cast<uint32_t*>(dst + 2 * lane) = *reinterpret_cast<const uint32_t*>(s + 2 * lane);
@@ -543,6 +544,38 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
     }
 }
 
+// fp32 [rows, D] -> bf16 rows with leading dimension ld_out (D multiple of 4)
+__global__ void cast_rows_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long rows, int D, long long ld_out) {
+    const int vecs = D / 4;
+    const long long total = rows * vecs;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / vecs;
+        const int c = (int)(i % vecs) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(in + r * D + c);
+        uint2 u;
+        u.x = pack_bf16x2(v.x, v.y);
+        u.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(out + r * ld_out + c) = u;
+    }
+}
+
+// h = bf16(silu(gate)) * up from the interleaved (gate, up) stash [M, 2F] (64-blocks) -> [M, ld_h]  (LoRA wgrad recompute)
+__global__ void swiglu_h_kernel(const bf16* __restrict__ gu, bf16* __restrict__ h, long long M, int F, long long ld_h) {
+    const int chunks = F / 8;
+    const long long total = M * chunks;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / chunks;
+        const int j = (int)(i % chunks) * 8;
+        const bf16* src = gu + r * (2LL * F) + (j / 64) * 128 + (j % 64);
+        float g[8], u[8], o[8];
+        ld8_bf16(src, g);
+        ld8_bf16(src + 64, u);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = bf16_round(g[t] * sigmoidf_(g[t])) * u[t];
+        st8_bf16(h + r * ld_h + j, o);
+    }
+}
+
 // frame-stack copy for sequence lengths that are not a multiple of k (otherwise the stack is a free view):
 // out [B, n, k*D] <- x [B, S, D] rows 0 .. n*k-1      (tiny_audio/projectors.py:79-87)
 __global__ void frame_stack_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int B, int S, int n, int k, int D) {
@@ -620,25 +653,28 @@ int k_layernorm_bf16(const bf16* x, const float* w, const float* b, bf16* y, lon
     return 0;
 }
 
-int k_rmsnorm_f32(const float* x, const float* w, bf16* y, const int* row_index, long long rows, int D, float eps, cudaStream_t st) {
+int k_rmsnorm_f32(const float* x, const float* w, bf16* y, const int* row_index, long long rows, int D, float eps, cudaStream_t st,
+                  long long ldy) {
+    if (ldy == 0) ldy = D;
     TA_REQUIRE(D % 256 == 0 && D <= 2048, "rmsnorm: D=%d must be a multiple of 256 and <= 2048", D);
     if (rows == 0) return 0;
     const int wpb = 8;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    if (D <= 1024) rmsnorm_f32_kernel<4><<<grid, wpb * 32, 0, st>>>(x, w, y, row_index, rows, D, eps);
-    else rmsnorm_f32_kernel<8><<<grid, wpb * 32, 0, st>>>(x, w, y, row_index, rows, D, eps);
+    if (D <= 1024) rmsnorm_f32_kernel<4><<<grid, wpb * 32, 0, st>>>(x, w, y, row_index, rows, D, eps, ldy);
+    else rmsnorm_f32_kernel<8><<<grid, wpb * 32, 0, st>>>(x, w, y, row_index, rows, D, eps, ldy);
     TA_LAUNCH_CHECK();
     return 0;
 }
 
 int k_rmsnorm_f32_bwd(const bf16* dy, const float* x, const float* w, float* dx, const int* row_index, long long rows, int D,
-                      float eps, int accumulate, cudaStream_t st, bf16* dx_bf16) {
+                      float eps, int accumulate, cudaStream_t st, bf16* dx_bf16, long long ld_b) {
+    if (ld_b == 0) ld_b = D;
     TA_REQUIRE(D % 256 == 0 && D <= 2048, "rmsnorm bwd: D=%d must be a multiple of 256 and <= 2048", D);
     if (rows == 0) return 0;
     const int wpb = 8;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    if (D <= 1024) rmsnorm_f32_bwd_kernel<4><<<grid, wpb * 32, 0, st>>>(dy, x, w, dx, row_index, rows, D, eps, accumulate, dx_bf16);
-    else rmsnorm_f32_bwd_kernel<8><<<grid, wpb * 32, 0, st>>>(dy, x, w, dx, row_index, rows, D, eps, accumulate, dx_bf16);
+    if (D <= 1024) rmsnorm_f32_bwd_kernel<4><<<grid, wpb * 32, 0, st>>>(dy, x, w, dx, row_index, rows, D, eps, accumulate, dx_bf16, ld_b);
+    else rmsnorm_f32_bwd_kernel<8><<<grid, wpb * 32, 0, st>>>(dy, x, w, dx, row_index, rows, D, eps, accumulate, dx_bf16, ld_b);
     TA_LAUNCH_CHECK();
     return 0;
 }
@@ -661,11 +697,12 @@ int k_lm_qknorm_rope_fwd(const bf16* qkv, bf16* qk, const float* qw, const float
 
 int k_lm_qknorm_rope_bwd(const bf16* qkv, const float* dq, const bf16* dk, const bf16* dv, bf16* dqkv, const float* qw,
                          const float* kw, const float* cosT, const float* sinT, long long M, int S, int Hq, int Hkv, float eps,
-                         cudaStream_t st) {
+                         cudaStream_t st, long long ld_out) {
+    if (ld_out == 0) ld_out = (long long)(Hq + 2 * Hkv) * 128;
     const long long warps = M * (Hq + 2 * Hkv);
     const int wpb = 8;
     lm_qknorm_rope_bwd_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, st>>>(qkv, dq, dk, dv, dqkv, qw, kw, cosT, sinT, M,
-                                                                                          S, Hq, Hkv, eps);
+                                                                                          S, Hq, Hkv, eps, ld_out);
     TA_LAUNCH_CHECK();
     return 0;
 }
@@ -744,6 +781,22 @@ int k_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t st) {
     return 0;
 }
 
+int k_cast_rows_f32_bf16(const float* in, bf16* out, long long rows, int D, long long ld_out, cudaStream_t st) {
+    TA_REQUIRE(D % 4 == 0 && ld_out % 4 == 0, "cast rows: D and ld must be multiples of 4");
+    if (rows == 0) return 0;
+    cast_rows_f32_bf16_kernel<<<grid_for(rows * (D / 4), 256), 256, 0, st>>>(in, out, rows, D, ld_out);
+    TA_LAUNCH_CHECK();
+    return 0;
+}
+
+int k_swiglu_h(const bf16* gu, bf16* h, long long M, int F, long long ld_h, cudaStream_t st) {
+    TA_REQUIRE(F % 64 == 0, "swiglu_h: F must be a multiple of 64");
+    if (M == 0) return 0;
+    swiglu_h_kernel<<<grid_for(M * (F / 8), 256), 256, 0, st>>>(gu, h, M, F, ld_h);
+    TA_LAUNCH_CHECK();
+    return 0;
+}
+
 int k_frame_stack(const bf16* x, bf16* out, int B, int S, int n, int k, int D, cudaStream_t st) {
     TA_REQUIRE((k * D) % 8 == 0, "frame stack: k*D must be a multiple of 8");
     const long long total = (long long)B * n * ((k * D) / 8);
@@ -772,11 +825,11 @@ TA_API int ta_layernorm_bf16(const void* x, const float* w, const float* b, void
     return k_layernorm_bf16((const bf16*)x, w, b, (bf16*)y, rows, D, eps, ST(stream));
 }
 TA_API int ta_rmsnorm_f32(const float* x, const float* w, void* y, const int* row_index, long long rows, int D, float eps, void* stream) {
-    return k_rmsnorm_f32(x, w, (bf16*)y, row_index, rows, D, eps, ST(stream));
+    return k_rmsnorm_f32(x, w, (bf16*)y, row_index, rows, D, eps, ST(stream), 0);
 }
 TA_API int ta_rmsnorm_f32_bwd(const void* dy, const float* x, const float* w, float* dx, const int* row_index, long long rows, int D,
                               float eps, int accumulate, void* stream) {
-    return k_rmsnorm_f32_bwd((const bf16*)dy, x, w, dx, row_index, rows, D, eps, accumulate, ST(stream), nullptr);
+    return k_rmsnorm_f32_bwd((const bf16*)dy, x, w, dx, row_index, rows, D, eps, accumulate, ST(stream), nullptr, 0);
 }
 TA_API int ta_enc_rope(void* qkv, const float* cosT, const float* sinT, long long rows, int S, int H, int hd, int rd, void* stream) {
     return k_enc_rope((bf16*)qkv, cosT, sinT, rows, S, H, hd, rd, ST(stream));
@@ -789,7 +842,7 @@ TA_API int ta_lm_qknorm_rope_bwd(const void* qkv, const float* dq, const void* d
                                  const float* kw, const float* cosT, const float* sinT, long long M, int S, int Hq, int Hkv,
                                  float eps, void* stream) {
     return k_lm_qknorm_rope_bwd((const bf16*)qkv, dq, (const bf16*)dk, (const bf16*)dv, (bf16*)dqkv, qw, kw, cosT, sinT, M, S, Hq,
-                                Hkv, eps, ST(stream));
+                                Hkv, eps, ST(stream), 0);
 }
 TA_API int ta_proj_norm_fwd(const void* x, const float* w, void* y, long long rows, int D, float eps, int gelu, void* stream) {
     return k_proj_norm_fwd((const bf16*)x, w, y, rows, D, eps, gelu, ST(stream));

@@ -177,7 +177,14 @@ TA_API int ta_mlp_projector_backward(const ta_mlp_projector_weights* w, const vo
 }
 
 // =============================================================================================================
-// Qwen3: forward + CE + backward to inputs_embeds
+// Qwen3: forward + CE + backward to inputs_embeds  (+ optional LoRA adapters on all seven projections)
+//
+// LoRA (reference: tiny_audio/asr_modeling.py:289-301 -> peft LoraConfig(r, alpha, dropout 0) on q,k,v,o,gate,up,down):
+//   y = x W^T + s (x A^T) B^T.  Every projection keeps running as ONE tcgen05 GEMM by augmenting the contraction:
+//   the activation buffers carry P = lora_pad extra columns that hold t = x A^T (rank padded to P), and the packed
+//   weights carry P extra columns that hold s*B, so  [x | t] . [W | sB]^T  is the adapted projection; the dgrad GEMMs
+//   use [dy | u] . [W^T | A^T]^T with u = dy (sB).  Only the rank-P "down" products (t, u) and the A/B weight gradients
+//   are extra launches.
 // =============================================================================================================
 namespace {
 struct LmBufs {
@@ -186,58 +193,88 @@ struct LmBufs {
     float* resid_mid;  // [L][M, D]
     bf16* qkv;         // [L][M, QKV]
     bf16* qk;          // [L][M, QK]
-    bf16* att;         // [L][M, Hq*hd]
+    bf16* att;         // [L][M, QD + P]   (extra columns: t_o)
     float* lse;        // [L][B*Hq*S]
     bf16* gu;          // [L][M, 2F]
+    bf16* lt;          // [L][3][M, P]     LoRA only: t_qkv, t_gu, t_d
     // scratch
-    bf16* xn;          // [M, D]
-    bf16* h;           // [M, F]
+    bf16* xn;          // [M, D + P]
+    bf16* h;           // [M, F + P]
     bf16* hl;          // [n_lab, D]
     bf16* logits;      // [n_lab, Vpad]
     bf16* dhl;         // [n_lab, D]
-    float* dx;         // aliases d_inputs_embeds
-    bf16* dxb;         // [M, D]
-    bf16* big;         // [M, max(2F, QKV)]
+    bf16* dxb;         // [M, D + P]
+    bf16* big;         // [M, max(2F, QKV) + P]
     bf16* dxn;         // [M, D]
-    bf16* datt;        // [M, Hq*hd]
-    float* dq;         // [M, Hq*hd]
-    bf16* dk;          // [M, Hkv*hd]
-    bf16* dv;          // [M, Hkv*hd]
+    bf16* datt;        // [M, QD]
+    float* dq;         // [M, QD]
+    bf16* dk;          // [M, KD]
+    bf16* dv;          // [M, KD]
     float* dsum;       // [B*Hq*S]
+    bf16* tr_a;        // LoRA wgrad transposes: [max(2F, QKV), Mp], [P, Mp], [P, Mp], [max(F, QD), Mp]
+    bf16* tr_t;
+    bf16* tr_u;
+    bf16* tr_x;
     long long stride_layers;   // 1 if with_backward else 0
 };
 
 long long lm_carve(const ta_lm_weights* w, int B, int S, int n_lab, int with_bwd, void* ws, long long cap, LmBufs* b) {
-    const long long M = (long long)B * S, D = w->dim, F = w->ffn;
+    const long long M = (long long)B * S, D = w->dim, F = w->ffn, P = w->lora_pad;
     const long long QD = (long long)w->n_q_heads * w->head_dim, KD = (long long)w->n_kv_heads * w->head_dim;
     const long long QKV = QD + 2 * KD, QK = QD + KD;
     const long long L = with_bwd ? w->n_layers : 1;
+    const long long Mp = (M + 7) / 8 * 8;
     Carver c(ws, cap);
     b->stride_layers = with_bwd ? 1 : 0;
     b->resid = c.take<float>((with_bwd ? (w->n_layers + 1) : 2) * M * D);
     b->resid_mid = c.take<float>(L * M * D);
     b->qkv = c.take<bf16>(L * M * QKV);
     b->qk = c.take<bf16>(L * M * QK);
-    b->att = c.take<bf16>(L * M * QD);
+    b->att = c.take<bf16>(L * M * (QD + P));
     b->lse = c.take<float>(L * (long long)B * w->n_q_heads * S);
     b->gu = c.take<bf16>(L * M * 2 * F);
-    b->xn = c.take<bf16>(M * D);
-    b->h = c.take<bf16>(M * F);
+    b->lt = c.take<bf16>(P ? L * 3 * M * P : 0);
+    b->xn = c.take<bf16>(M * (D + P));
+    b->h = c.take<bf16>(M * (F + P));
     b->hl = c.take<bf16>((long long)n_lab * D);
     b->logits = c.take<bf16>((long long)n_lab * w->vocab_pad);
     b->dhl = c.take<bf16>((long long)n_lab * D);
     if (with_bwd) {
-        b->dxb = c.take<bf16>(M * D);
+        b->dxb = c.take<bf16>(M * (D + P));
         const long long bigw = (2 * F > QKV) ? 2 * F : QKV;
-        b->big = c.take<bf16>(M * bigw);
+        b->big = c.take<bf16>(M * (bigw + P));
         b->dxn = c.take<bf16>(M * D);
         b->datt = c.take<bf16>(M * QD);
         b->dq = c.take<float>(M * QD);
         b->dk = c.take<bf16>(M * KD);
         b->dv = c.take<bf16>(M * KD);
         b->dsum = c.take<float>((long long)B * w->n_q_heads * S);
+        if (P) {
+            b->tr_a = c.take<bf16>(bigw * Mp);
+            b->tr_t = c.take<bf16>(P * Mp);
+            b->tr_u = c.take<bf16>(P * Mp);
+            b->tr_x = c.take<bf16>(((F > QD) ? F : QD) * Mp);
+        }
     }
     return c.off;
+}
+
+inline int plain(const void* A, long long lda, const void* Bm, long long ldb, long long M, int N, int K, void* out, long long ldo,
+                 cudaStream_t st) {
+    return gemm(A, lda, Bm, ldb, M, N, K, TA_EPI_BF16, out, ldo, nullptr, nullptr, nullptr, 0, nullptr, 0, st);
+}
+
+// A / B gradients of one adapter group:  dBs[N_out, P] = dy^T t,  dA[P, K_in] = u^T x   (contractions over the M tokens)
+int lora_wgrad(const LmBufs& b, long long M, int P, const bf16* dy, long long ld_dy, int n_out, const bf16* t, long long ld_t,
+               const bf16* u, long long ld_u, const bf16* x, long long ld_x, int k_in, float* dA, float* dBs, cudaStream_t st) {
+    const long long Mp = (M + 7) / 8 * 8;
+    RUN(k_transpose_bf16(dy, b.tr_a, (int)M, n_out, ld_dy, Mp, st));
+    RUN(k_transpose_bf16(t, b.tr_t, (int)M, P, ld_t, Mp, st));
+    RUN(k_transpose_bf16(u, b.tr_u, (int)M, P, ld_u, Mp, st));
+    RUN(k_transpose_bf16(x, b.tr_x, (int)M, k_in, ld_x, Mp, st));
+    RUN(gemm(b.tr_a, Mp, b.tr_t, Mp, n_out, P, (int)M, TA_EPI_F32, dBs, P, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+    RUN(gemm(b.tr_u, Mp, b.tr_x, Mp, P, k_in, (int)M, TA_EPI_F32, dA, k_in, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+    return 0;
 }
 }  // namespace
 
@@ -254,13 +291,18 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
     TA_REQUIRE(a->S <= w->max_pos, "sequence length %d exceeds the rotary table (%d)", a->S, w->max_pos);
     TA_REQUIRE(!a->with_backward || a->d_inputs_embeds, "with_backward needs d_inputs_embeds");
     TA_REQUIRE(a->n_labelled == 0 || (a->label_rows && a->label_targets), "label rows / targets missing");
+    TA_REQUIRE(w->lora_pad == 0 || w->lora_pad == 128, "lora_pad must be 0 or 128");
+    const int P = w->lora_pad;
+    TA_REQUIRE(!(P && a->with_backward) || a->lora_grads, "LoRA backward needs the gradient pointer table");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int B = a->B, S = a->S, nl = a->n_labelled;
     const long long M = (long long)B * S;
     const int D = w->dim, F = w->ffn, Hq = w->n_q_heads, Hkv = w->n_kv_heads, hd = w->head_dim;
     const int QD = Hq * hd, KD = Hkv * hd, QKV = QD + 2 * KD, QK = QD + KD;
     const int Lyr = w->n_layers;
+    const long long ldX = D + P, ldH = F + P, ldAtt = QD + P;
     LmBufs b;
+    memset(&b, 0, sizeof(b));
     const long long need = lm_carve(w, B, S, nl, a->with_backward, a->workspace, a->workspace_bytes, &b);
     TA_REQUIRE(need <= a->workspace_bytes, "LM workspace too small: need %lld, have %lld", need, a->workspace_bytes);
     if (M == 0) return 0;
@@ -274,21 +316,35 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
         const void* const* Lw = w->layers + (long long)l * TA_LM_PTRS_PER_LAYER;
         bf16* qkv = b.qkv + sl * l * M * QKV;
         bf16* qk = b.qk + sl * l * M * QK;
-        bf16* att = b.att + sl * l * M * QD;
+        bf16* att = b.att + sl * l * M * ldAtt;
         float* lse = b.lse + sl * l * lse_n;
         float* x_mid = b.resid_mid + sl * l * M * D;
         bf16* gu = b.gu + sl * l * M * 2 * F;
+        bf16* lt = P ? b.lt + sl * l * 3 * M * P : nullptr;
         float* x_out = b.resid + (a->with_backward ? (long long)(l + 1) : (long long)((l + 1) & 1)) * M * D;
 
-        RUN(k_rmsnorm_f32(x_in, (const float*)Lw[TA_LM_LN1_W], b.xn, nullptr, M, D, w->eps, st));
-        RUN(gemm(b.xn, D, Lw[TA_LM_WQKV], D, M, QKV, D, TA_EPI_BF16, qkv, QKV, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+        RUN(k_rmsnorm_f32(x_in, (const float*)Lw[TA_LM_LN1_W], b.xn, nullptr, M, D, w->eps, st, ldX));
+        if (P) {   // t_qkv = xn A_qkv^T into the extra columns (+ a copy kept for the B gradients)
+            RUN(plain(b.xn, ldX, Lw[TA_LM_LORA_A_QKV], D, M, P, D, b.xn + D, ldX, st));
+            TA_CHECK_CUDA(cudaMemcpy2DAsync(lt, P * 2, b.xn + D, ldX * 2, P * 2, M, cudaMemcpyDeviceToDevice, st));
+        }
+        RUN(gemm(b.xn, ldX, Lw[TA_LM_WQKV], ldX, M, QKV, D + P, TA_EPI_BF16, qkv, QKV, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
         RUN(k_lm_qknorm_rope_fwd(qkv, qk, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W], w->rope_cos, w->rope_sin,
                                  M, S, Hq, Hkv, w->eps, st));
-        RUN(ta_attn_fwd(qk, qk + QD, qkv + QK, att, lse, B, S, Hq, Hkv, hd, QK, QK, QKV, QD, 1, scale, st));
-        RUN(gemm(att, QD, Lw[TA_LM_WO], QD, M, D, QD, TA_EPI_F32_RESID, x_mid, D, nullptr, x_in, nullptr, 0, nullptr, 0, st));
-        RUN(k_rmsnorm_f32(x_mid, (const float*)Lw[TA_LM_LN2_W], b.xn, nullptr, M, D, w->eps, st));
-        RUN(gemm(b.xn, D, Lw[TA_LM_WGU], D, M, 2 * F, D, TA_EPI_SWIGLU, b.h, F, nullptr, nullptr, gu, 2 * F, nullptr, 0, st));
-        RUN(gemm(b.h, F, Lw[TA_LM_WD], F, M, D, F, TA_EPI_F32_RESID, x_out, D, nullptr, x_mid, nullptr, 0, nullptr, 0, st));
+        RUN(ta_attn_fwd(qk, qk + QD, qkv + QK, att, lse, B, S, Hq, Hkv, hd, QK, QK, QKV, ldAtt, 1, scale, st));
+        if (P) RUN(plain(att, ldAtt, Lw[TA_LM_LORA_A_O], QD, M, P, QD, att + QD, ldAtt, st));
+        RUN(gemm(att, ldAtt, Lw[TA_LM_WO], ldAtt, M, D, QD + P, TA_EPI_F32_RESID, x_mid, D, nullptr, x_in, nullptr, 0, nullptr, 0, st));
+        RUN(k_rmsnorm_f32(x_mid, (const float*)Lw[TA_LM_LN2_W], b.xn, nullptr, M, D, w->eps, st, ldX));
+        if (P) {
+            RUN(plain(b.xn, ldX, Lw[TA_LM_LORA_A_GU], D, M, P, D, b.xn + D, ldX, st));
+            TA_CHECK_CUDA(cudaMemcpy2DAsync(lt + M * P, P * 2, b.xn + D, ldX * 2, P * 2, M, cudaMemcpyDeviceToDevice, st));
+        }
+        RUN(gemm(b.xn, ldX, Lw[TA_LM_WGU], ldX, M, 2 * F, D + P, TA_EPI_SWIGLU, b.h, ldH, nullptr, nullptr, gu, 2 * F, nullptr, 0, st));
+        if (P) {
+            RUN(plain(b.h, ldH, Lw[TA_LM_LORA_A_D], F, M, P, F, b.h + F, ldH, st));
+            TA_CHECK_CUDA(cudaMemcpy2DAsync(lt + 2 * M * P, P * 2, b.h + F, ldH * 2, P * 2, M, cudaMemcpyDeviceToDevice, st));
+        }
+        RUN(gemm(b.h, ldH, Lw[TA_LM_WD], ldH, M, D, F + P, TA_EPI_F32_RESID, x_out, D, nullptr, x_mid, nullptr, 0, nullptr, 0, st));
         x_in = x_out;
     }
     const float* x_final = x_in;
@@ -314,29 +370,58 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
                  nullptr, nullptr, 0, nullptr, 0, st));
         RUN(k_rmsnorm_f32_bwd(b.dhl, x_final, w->final_norm_w, dx, a->label_rows, nl, D, w->eps, 0, st));
     }
-    RUN(k_cast_f32_bf16(dx, b.dxb, M * D, st));   // later bf16 copies of dx come out of the RMSNorm-backward kernels
+    RUN(k_cast_rows_f32_bf16(dx, b.dxb, M, D, ldX, st));   // later bf16 copies of dx come out of the RMSNorm-backward kernels
+    const long long ldBig = ((2 * F > QKV) ? 2 * F : QKV) + P;
     for (int l = Lyr - 1; l >= 0; --l) {
         const void* const* Lw = w->layers + (long long)l * TA_LM_PTRS_PER_LAYER;
+        float* const* Lg = P ? a->lora_grads + (long long)l * TA_LM_LORA_GRADS_PER_LAYER : nullptr;
         const bf16* qkv = b.qkv + (long long)l * M * QKV;
         const bf16* qk = b.qk + (long long)l * M * QK;
-        const bf16* att = b.att + (long long)l * M * QD;
+        bf16* att = b.att + (long long)l * M * ldAtt;
         const float* lse = b.lse + (long long)l * lse_n;
         const float* x_mid = b.resid_mid + (long long)l * M * D;
         const bf16* gu = b.gu + (long long)l * M * 2 * F;
+        const bf16* lt = P ? b.lt + (long long)l * 3 * M * P : nullptr;
         const float* x_l = (l == 0) ? a->inputs_embeds : (b.resid + (long long)l * M * D);
 
-        // MLP branch (b.dxb = bf16(dx) was written by the previous RMSNorm backward / the cast above)
-        RUN(gemm(b.dxb, D, Lw[TA_LM_WD_T], D, M, F, D, TA_EPI_SWIGLU_BWD, b.big, 2 * F, nullptr, nullptr, nullptr, 0, gu, 2 * F, st));
-        RUN(gemm(b.big, 2 * F, Lw[TA_LM_WGU_T], 2 * F, M, D, 2 * F, TA_EPI_BF16, b.dxn, D, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
-        RUN(k_rmsnorm_f32_bwd(b.dxn, x_mid, (const float*)Lw[TA_LM_LN2_W], dx, nullptr, M, D, w->eps, 1, st, b.dxb));
-        // attention branch
-        RUN(gemm(b.dxb, D, Lw[TA_LM_WO_T], D, M, QD, D, TA_EPI_BF16, b.datt, QD, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
-        RUN(ta_attn_bwd(qk, qk + QD, qkv + QK, att, b.datt, lse, b.dsum, b.dq, b.dk, b.dv, B, S, Hq, Hkv, hd, QK, QK, QKV, QD, QD, QD,
+        // ---- MLP branch: b.dxb = bf16(d x_out) ----
+        if (P) {
+            RUN(plain(b.dxb, ldX, Lw[TA_LM_LORA_BT_D], D, M, P, D, b.dxb + D, ldX, st));          // u_d = dy (s B_d)
+            RUN(k_swiglu_h(gu, b.h, M, F, ldH, st));                                               // x of down_proj
+            RUN(lora_wgrad(b, M, P, b.dxb, ldX, D, lt + 2 * M * P, P, b.dxb + D, ldX, b.h, ldH, F, Lg[TA_LM_LORA_DA_D],
+                           Lg[TA_LM_LORA_DB_D], st));
+        }
+        RUN(gemm(b.dxb, ldX, Lw[TA_LM_WD_T], ldX, M, F, D + P, TA_EPI_SWIGLU_BWD, b.big, ldBig, nullptr, nullptr, nullptr, 0, gu, 2 * F,
+                 st));
+        if (P) {
+            RUN(plain(b.big, ldBig, Lw[TA_LM_LORA_BT_GU], 2 * F, M, P, 2 * F, b.big + 2 * F, ldBig, st));
+            RUN(k_rmsnorm_f32(x_mid, (const float*)Lw[TA_LM_LN2_W], b.xn, nullptr, M, D, w->eps, st, ldX));   // x of gate/up
+            RUN(lora_wgrad(b, M, P, b.big, ldBig, 2 * F, lt + M * P, P, b.big + 2 * F, ldBig, b.xn, ldX, D, Lg[TA_LM_LORA_DA_GU],
+                           Lg[TA_LM_LORA_DB_GU], st));
+        }
+        RUN(gemm(b.big, ldBig, Lw[TA_LM_WGU_T], 2 * F + P, M, D, 2 * F + P, TA_EPI_BF16, b.dxn, D, nullptr, nullptr, nullptr, 0, nullptr,
+                 0, st));
+        RUN(k_rmsnorm_f32_bwd(b.dxn, x_mid, (const float*)Lw[TA_LM_LN2_W], dx, nullptr, M, D, w->eps, 1, st, b.dxb, ldX));
+        // ---- attention branch ----
+        if (P) {
+            RUN(plain(b.dxb, ldX, Lw[TA_LM_LORA_BT_O], D, M, P, D, b.dxb + D, ldX, st));
+            RUN(lora_wgrad(b, M, P, b.dxb, ldX, D, att + QD, ldAtt, b.dxb + D, ldX, att, ldAtt, QD, Lg[TA_LM_LORA_DA_O],
+                           Lg[TA_LM_LORA_DB_O], st));
+        }
+        RUN(gemm(b.dxb, ldX, Lw[TA_LM_WO_T], ldX, M, QD, D + P, TA_EPI_BF16, b.datt, QD, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+        RUN(ta_attn_bwd(qk, qk + QD, qkv + QK, att, b.datt, lse, b.dsum, b.dq, b.dk, b.dv, B, S, Hq, Hkv, hd, QK, QK, QKV, ldAtt, QD, QD,
                         KD, KD, 1, scale, st));
         RUN(k_lm_qknorm_rope_bwd(qkv, b.dq, b.dk, b.dv, b.big, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W],
-                                 w->rope_cos, w->rope_sin, M, S, Hq, Hkv, w->eps, st));
-        RUN(gemm(b.big, QKV, Lw[TA_LM_WQKV_T], QKV, M, D, QKV, TA_EPI_BF16, b.dxn, D, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
-        RUN(k_rmsnorm_f32_bwd(b.dxn, x_l, (const float*)Lw[TA_LM_LN1_W], dx, nullptr, M, D, w->eps, 1, st, l > 0 ? b.dxb : nullptr));
+                                 w->rope_cos, w->rope_sin, M, S, Hq, Hkv, w->eps, st, ldBig));
+        if (P) {
+            RUN(plain(b.big, ldBig, Lw[TA_LM_LORA_BT_QKV], QKV, M, P, QKV, b.big + QKV, ldBig, st));
+            RUN(k_rmsnorm_f32(x_l, (const float*)Lw[TA_LM_LN1_W], b.xn, nullptr, M, D, w->eps, st, ldX));     // x of q/k/v
+            RUN(lora_wgrad(b, M, P, b.big, ldBig, QKV, lt, P, b.big + QKV, ldBig, b.xn, ldX, D, Lg[TA_LM_LORA_DA_QKV],
+                           Lg[TA_LM_LORA_DB_QKV], st));
+        }
+        RUN(gemm(b.big, ldBig, Lw[TA_LM_WQKV_T], QKV + P, M, D, QKV + P, TA_EPI_BF16, b.dxn, D, nullptr, nullptr, nullptr, 0, nullptr, 0,
+                 st));
+        RUN(k_rmsnorm_f32_bwd(b.dxn, x_l, (const float*)Lw[TA_LM_LN1_W], dx, nullptr, M, D, w->eps, 1, st, l > 0 ? b.dxb : nullptr, ldX));
     }
     return 0;
 }

@@ -4,15 +4,18 @@
 
 int k_im2col_k3(const bf16* x, bf16* out, int B, int T, int C, int stride, cudaStream_t st);
 int k_layernorm_bf16(const bf16* x, const float* w, const float* b, bf16* y, long long rows, int D, float eps, cudaStream_t st);
-int k_rmsnorm_f32(const float* x, const float* w, bf16* y, const int* row_index, long long rows, int D, float eps, cudaStream_t st);
+int k_rmsnorm_f32(const float* x, const float* w, bf16* y, const int* row_index, long long rows, int D, float eps, cudaStream_t st,
+                  long long ldy = 0);
 int k_rmsnorm_f32_bwd(const bf16* dy, const float* x, const float* w, float* dx, const int* row_index, long long rows, int D,
-                      float eps, int accumulate, cudaStream_t st, bf16* dx_bf16 = nullptr);
+                      float eps, int accumulate, cudaStream_t st, bf16* dx_bf16 = nullptr, long long ld_b = 0);
 int k_enc_rope(bf16* qkv, const float* cosT, const float* sinT, long long rows, int S, int H, int hd, int rd, cudaStream_t st);
 int k_lm_qknorm_rope_fwd(const bf16* qkv, bf16* qk, const float* qw, const float* kw, const float* cosT, const float* sinT,
                          long long M, int S, int Hq, int Hkv, float eps, cudaStream_t st);
 int k_lm_qknorm_rope_bwd(const bf16* qkv, const float* dq, const bf16* dk, const bf16* dv, bf16* dqkv, const float* qw,
                          const float* kw, const float* cosT, const float* sinT, long long M, int S, int Hq, int Hkv, float eps,
-                         cudaStream_t st);
+                         cudaStream_t st, long long ld_out = 0);
+int k_cast_rows_f32_bf16(const float* in, bf16* out, long long rows, int D, long long ld_out, cudaStream_t st);
+int k_swiglu_h(const bf16* gu, bf16* h, long long M, int F, long long ld_h, cudaStream_t st);
 int k_proj_norm_fwd(const bf16* x, const float* w, void* y, long long rows, int D, float eps, int gelu, cudaStream_t st);
 int k_proj_norm_bwd(const bf16* x, const float* w, const void* dy, int dy_is_f32, bf16* dx, float* dw, long long rows, int D,
                     float eps, int gelu, cudaStream_t st);

@@ -120,20 +120,31 @@ class PackedEncoder:
                                   L.ptr(self.rope_sin), C.cast(self.table, C.POINTER(L.P)))
 
 
-class PackedLM:
-    """Qwen3 weights in kernel layout (state_dict names = HF Qwen3ForCausalLM)."""
+LORA_PAD = 128          # rank padding of the augmented-K LoRA GEMMs (csrc/engine.cu)
+LORA_PROJS = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
 
-    def __init__(self, sd: Dict[str, torch.Tensor], dims: PathDims, device):
+
+class PackedLM:
+    """Qwen3 weights in kernel layout (state_dict names = HF Qwen3ForCausalLM).  With `lora=True` every projection weight
+    (and its transposed dgrad copy) is stored stacked over layers with LORA_PAD extra K columns that `update_lora` fills
+    with alpha/r * B (forward) resp. A^T (dgrad), so the adapted projection stays ONE GEMM."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], dims: PathDims, device, lora: bool = False):
         d = dims
         self.dims = d
         self.keep = []
+        self.lora_pad = LORA_PAD if lora else 0
+        P = self.lora_pad
 
         def dev(t, dtype):
             t = t.detach().to(device=device, dtype=dtype).contiguous()
             self.keep.append(t)
             return t
 
-        V, D, F = d.vocab, d.lm_dim, d.lm_ffn
+        V, D, F, Lyr = d.vocab, d.lm_dim, d.lm_ffn, d.lm_layers
+        QD, KD = d.lm_heads * d.lm_head_dim, d.lm_kv_heads * d.lm_head_dim
+        QKV = QD + 2 * KD
+        self.QD, self.KD, self.QKV = QD, KD, QKV
         self.vocab_pad = _round_up(V, 256)      # 256: lets the lm_head GEMMs use the 256-wide tile
         emb = sd["model.embed_tokens.weight"]
         assert emb.shape[0] == V, f"embedding rows {emb.shape[0]} != vocab {V}"
@@ -145,35 +156,117 @@ class PackedLM:
         self.final_norm_w = dev(sd["model.norm.weight"], F32)
         self.rope_cos, self.rope_sin = _rope_tables(d.lm_max_pos, d.lm_head_dim, d.lm_rope_theta, device, False)
         assert F % 64 == 0
+
+        def stacked(n_out, k_in):
+            return torch.zeros(Lyr, n_out, k_in + P, dtype=BF16, device=device)
+
+        # [W | aB] forward operands and [W^T | A^T] dgrad operands, stacked over layers
+        self.w = {"qkv": stacked(QKV, D), "o": stacked(D, QD), "gu": stacked(2 * F, D), "d": stacked(D, F)}
+        self.wt = {"qkv": stacked(D, QKV), "o": stacked(QD, D), "gu": stacked(D, 2 * F), "d": stacked(F, D)}
+        self.kin = {"qkv": D, "o": QD, "gu": D, "d": F}
+        self.nout = {"qkv": QKV, "o": D, "gu": 2 * F, "d": D}
+        if P:
+            self.lora_a = {g: torch.zeros(Lyr, P, self.kin[g], dtype=BF16, device=device) for g in self.kin}
+            self.lora_bt = {g: torch.zeros(Lyr, P, self.nout[g], dtype=BF16, device=device) for g in self.kin}
+            self.lora_da = {g: torch.zeros(Lyr, P, self.kin[g], dtype=F32, device=device) for g in self.kin}
+            self.lora_db = {g: torch.zeros(Lyr, self.nout[g], P, dtype=F32, device=device) for g in self.kin}
         ptrs = []
-        for i in range(d.lm_layers):
+        for i in range(Lyr):
             p = f"model.layers.{i}."
             wq, wk, wv = (sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv")
-            wqkv = dev(torch.cat([wq, wk, wv], 0), BF16)
-            wo = dev(sd[p + "self_attn.o_proj.weight"], BF16)
+            wqkv = torch.cat([wq, wk, wv], 0).to(device=device, dtype=BF16)
+            wo = sd[p + "self_attn.o_proj.weight"].to(device=device, dtype=BF16)
             g = sd[p + "mlp.gate_proj.weight"].reshape(F // 64, 1, 64, D)
             u = sd[p + "mlp.up_proj.weight"].reshape(F // 64, 1, 64, D)
-            wgu = dev(torch.cat([g, u], 1).reshape(2 * F, D), BF16)    # 64-row blocks: gate, up, gate, up ...
-            wd = dev(sd[p + "mlp.down_proj.weight"], BF16)
+            wgu = torch.cat([g, u], 1).reshape(2 * F, D).to(device=device, dtype=BF16)   # 64-row blocks: gate, up, gate, up ...
+            wd = sd[p + "mlp.down_proj.weight"].to(device=device, dtype=BF16)
+            for name, mat in (("qkv", wqkv), ("o", wo), ("gu", wgu), ("d", wd)):
+                self.w[name][i, :, : mat.shape[1]] = mat
+                self.wt[name][i, :, : mat.shape[0]] = mat.t()
             layer = [None] * L.LM_PTRS_PER_LAYER
             layer[L.LM_LN1_W] = dev(sd[p + "input_layernorm.weight"], F32)
-            layer[L.LM_WQKV] = wqkv
-            layer[L.LM_WQKV_T] = dev(wqkv.t(), BF16)
+            layer[L.LM_WQKV], layer[L.LM_WQKV_T] = self.w["qkv"][i], self.wt["qkv"][i]
             layer[L.LM_QNORM_W] = dev(sd[p + "self_attn.q_norm.weight"], F32)
             layer[L.LM_KNORM_W] = dev(sd[p + "self_attn.k_norm.weight"], F32)
-            layer[L.LM_WO] = wo
-            layer[L.LM_WO_T] = dev(wo.t(), BF16)
+            layer[L.LM_WO], layer[L.LM_WO_T] = self.w["o"][i], self.wt["o"][i]
             layer[L.LM_LN2_W] = dev(sd[p + "post_attention_layernorm.weight"], F32)
-            layer[L.LM_WGU] = wgu
-            layer[L.LM_WGU_T] = dev(wgu.t(), BF16)
-            layer[L.LM_WD] = wd
-            layer[L.LM_WD_T] = dev(wd.t(), BF16)
+            layer[L.LM_WGU], layer[L.LM_WGU_T] = self.w["gu"][i], self.wt["gu"][i]
+            layer[L.LM_WD], layer[L.LM_WD_T] = self.w["d"][i], self.wt["d"][i]
+            if P:
+                layer[L.LM_LORA_A_QKV], layer[L.LM_LORA_A_O] = self.lora_a["qkv"][i], self.lora_a["o"][i]
+                layer[L.LM_LORA_A_GU], layer[L.LM_LORA_A_D] = self.lora_a["gu"][i], self.lora_a["d"][i]
+                layer[L.LM_LORA_BT_QKV], layer[L.LM_LORA_BT_O] = self.lora_bt["qkv"][i], self.lora_bt["o"][i]
+                layer[L.LM_LORA_BT_GU], layer[L.LM_LORA_BT_D] = self.lora_bt["gu"][i], self.lora_bt["d"][i]
             ptrs.extend(layer)
         self.table = L.pointer_table(ptrs)
-        self.c = L.LmWeights(d.lm_layers, D, F, d.lm_heads, d.lm_kv_heads, d.lm_head_dim, d.lm_max_pos, V, self.vocab_pad,
-                             d.lm_eps, L.ptr(self.embed_f32), L.ptr(self.embed_bf16), L.ptr(self.embed_bf16_t),
+        self.grad_table = None
+        if P:
+            gp = []
+            for i in range(Lyr):
+                for g in ("qkv", "o", "gu", "d"):
+                    gp.extend([self.lora_da[g][i], self.lora_db[g][i]])
+            self.grad_table = L.pointer_table(gp)
+        self.c = L.LmWeights(Lyr, D, F, d.lm_heads, d.lm_kv_heads, d.lm_head_dim, d.lm_max_pos, V, self.vocab_pad,
+                             d.lm_eps, P, L.ptr(self.embed_f32), L.ptr(self.embed_bf16), L.ptr(self.embed_bf16_t),
                              L.ptr(self.final_norm_w), L.ptr(self.rope_cos), L.ptr(self.rope_sin),
                              C.cast(self.table, C.POINTER(L.P)))
+
+    # adapter j of a fused projection owns rank rows / columns [8 j, 8 j + r)
+    _GROUPS = {"qkv": ("q_proj", "k_proj", "v_proj"), "o": ("o_proj",), "gu": ("gate_proj", "up_proj"), "d": ("down_proj",)}
+
+    def _row_slices(self, g):
+        d = self.dims
+        F = d.lm_ffn
+        if g == "qkv":
+            return [slice(0, self.QD), slice(self.QD, self.QD + self.KD), slice(self.QD + self.KD, self.QKV)]
+        if g == "gu":
+            return ["gate", "up"]          # interleaved 64-row blocks, handled by a view
+        return [slice(0, self.nout[g])]
+
+    @torch.no_grad()
+    def update_lora(self, lora_a: Dict[str, torch.Tensor], lora_b: Dict[str, torch.Tensor], scaling: float):
+        """lora_a[proj]: [L, r, in] fp32, lora_b[proj]: [L, out, r] fp32 (stacked over layers).  Refreshes the rank-P operands
+        and the extra K columns of the augmented weights (a handful of strided copies per step)."""
+        P = self.lora_pad
+        assert P, "PackedLM was built without LoRA"
+        F = self.dims.lm_ffn
+        for g, projs in self._GROUPS.items():
+            K, N = self.kin[g], self.nout[g]
+            A, BT = self.lora_a[g], self.lora_bt[g]
+            for j, pj in enumerate(projs):
+                a, bm = lora_a[pj], lora_b[pj]
+                r = a.shape[1]
+                assert r <= 8, "rank > 8 needs a wider block layout"
+                A[:, 8 * j: 8 * j + r] = a.to(BF16)
+                bs = (bm.float() * scaling).to(BF16).transpose(1, 2)       # [L, r, out]
+                if g == "qkv":
+                    rs = self._row_slices(g)[j]
+                    BT[:, 8 * j: 8 * j + r, rs] = bs
+                elif g == "gu":
+                    v = BT.view(BT.shape[0], P, F // 64, 2, 64)             # columns in (block, gate|up, 64) order
+                    v[:, 8 * j: 8 * j + r, :, j, :] = bs.reshape(bs.shape[0], r, F // 64, 64)
+                else:
+                    BT[:, 8 * j: 8 * j + r] = bs
+            self.w[g][:, :, K: K + P] = BT.transpose(1, 2)                   # [W | aB]
+            self.wt[g][:, :, N: N + P] = A.transpose(1, 2)                   # [W^T | A^T]
+
+    def lora_grads(self, scaling: float, ranks: Dict[str, int]):
+        """Unpack the engine's gradient outputs into per-projection stacked gradients (views / small copies)."""
+        F = self.dims.lm_ffn
+        ga, gb = {}, {}
+        for g, projs in self._GROUPS.items():
+            dA, dB = self.lora_da[g], self.lora_db[g]                       # [L, P, K], [L, N, P]
+            for j, pj in enumerate(projs):
+                r = ranks[pj]
+                ga[pj] = dA[:, 8 * j: 8 * j + r]
+                cols = dB[:, :, 8 * j: 8 * j + r] * scaling                  # d/dB = alpha/r * d/d(aB)
+                if g == "qkv":
+                    gb[pj] = cols[:, self._row_slices(g)[j]]
+                elif g == "gu":
+                    gb[pj] = cols.reshape(cols.shape[0], F // 64, 2, 64, r)[:, :, j].reshape(cols.shape[0], F, r)
+                else:
+                    gb[pj] = cols
+        return ga, gb
 
 
 class _Workspaces:
@@ -209,14 +302,14 @@ def label_rows_and_targets(labels_cpu: torch.Tensor):
 class HotPath:
     """One GPU's replica of the frozen towers + the per-step driver."""
 
-    def __init__(self, dims: PathDims, enc_sd, lm_sd, device="cuda"):
+    def __init__(self, dims: PathDims, enc_sd, lm_sd, device="cuda", lora: bool = False):
         self.lib = L.load()
         self.dims = dims
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.TinyAudioB200Error("HotPath needs a CUDA device (no CPU fallback)")
         self.enc = PackedEncoder(enc_sd, dims, self.device)
-        self.lm = PackedLM(lm_sd, dims, self.device)
+        self.lm = PackedLM(lm_sd, dims, self.device, lora=lora)
         self.ws = _Workspaces(self.device)
         self.launches = 0
 
@@ -335,7 +428,8 @@ class HotPath:
         demb = self.ws.typed("d_inputs_embeds", (B * S, d.lm_dim), F32) if with_backward else None
         row_loss = torch.empty(nl, device=self.device, dtype=F32) if want_row_loss else None
         args = L.LmStepArgs(B, S, nl, int(with_backward), L.ptr(emb), L.ptr(rows), L.ptr(targets), inv_items, L.ptr(loss),
-                            L.ptr(row_loss), L.ptr(demb), L.ptr(ws), n.value, None)
+                            L.ptr(row_loss), L.ptr(demb), L.ptr(ws), n.value, None,
+                            C.cast(self.lm.grad_table, C.POINTER(L.P)) if (with_backward and self.lm.grad_table is not None) else None)
         L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
         return loss, demb, row_loss
 
@@ -347,7 +441,7 @@ class HotPath:
         ws = self.ws.get("lm", n.value)
         loss = torch.zeros(1, device=self.device, dtype=F32)
         hid = self.ws.typed("final_hidden", (B * S, d.lm_dim), F32)
-        args = L.LmStepArgs(B, S, 0, 0, L.ptr(emb), None, None, 1.0, L.ptr(loss), None, None, L.ptr(ws), n.value, L.ptr(hid))
+        args = L.LmStepArgs(B, S, 0, 0, L.ptr(emb), None, None, 1.0, L.ptr(loss), None, None, L.ptr(ws), n.value, L.ptr(hid), None)
         L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
         return hid
 
@@ -452,7 +546,7 @@ class HotPath:
                          waveform: Optional[torch.Tensor] = None, input_features: Optional[torch.Tensor] = None,
                          audio_token_counts: Optional[torch.Tensor] = None, num_items_in_batch: Optional[float] = None,
                          grads: Optional[Dict[str, torch.Tensor]] = None, return_parts: bool = False,
-                         frame_keep_prob: Optional[float] = None):
+                         frame_keep_prob: Optional[float] = None, lm_backward: Optional[bool] = None):
         """Returns (loss [1] fp32 device tensor, parts).  When `grads` is given (fp32 tensors shaped like the projector
         params) the backward runs and fills them with d(loss)/d(param)."""
         d = self.dims
@@ -471,7 +565,8 @@ class HotPath:
             keep = torch.bernoulli(torch.full(enc.shape[:-1], float(frame_keep_prob), device=self.device, dtype=F32))
             enc.mul_(keep.unsqueeze(-1).to(enc.dtype))
         xs, n_a = self.frame_stack(enc)
-        with_bwd = grads is not None
+        with_bwd = grads is not None                           # projector gradients wanted
+        lm_bwd = with_bwd if lm_backward is None else (lm_backward or with_bwd)   # LoRA-only training still needs the LM backward
         audio, stash = self.projector_forward(xs, proj_params, with_bwd)
         if audio_token_counts is None:
             audio_token_counts = (input_ids == d.audio_token_id).sum(-1)
@@ -488,7 +583,7 @@ class HotPath:
             tg_d = rows_d
             n_items = 1.0
         inv = 1.0 / max(n_items, 1.0)
-        loss, demb, _ = self.lm_step(emb, B, S, rows_d, tg_d, inv, with_bwd)
+        loss, demb, _ = self.lm_step(emb, B, S, rows_d, tg_d, inv, lm_bwd)
         if with_bwd:
             d_audio = self.ws.typed("d_audio", (B * n_a, d.lm_dim), F32)
             d_audio.zero_()

@@ -20,9 +20,11 @@ P = c_void_p
 # epilogue modes (enum in the header)
 EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESID, EPI_F32_RESID, EPI_F32, EPI_SWIGLU, EPI_SWIGLU_BWD, EPI_BF16_ROPE = range(8)
 ENC_PTRS_PER_LAYER = 12
-LM_PTRS_PER_LAYER = 12
+LM_PTRS_PER_LAYER = 20
+LM_LORA_GRADS_PER_LAYER = 8
 (ENC_LN1_W, ENC_LN1_B, ENC_WQKV, ENC_BQKV, ENC_WO, ENC_BO, ENC_LN2_W, ENC_LN2_B, ENC_W1, ENC_B1, ENC_W2, ENC_B2) = range(12)
-(LM_LN1_W, LM_WQKV, LM_WQKV_T, LM_QNORM_W, LM_KNORM_W, LM_WO, LM_WO_T, LM_LN2_W, LM_WGU, LM_WGU_T, LM_WD, LM_WD_T) = range(12)
+(LM_LN1_W, LM_WQKV, LM_WQKV_T, LM_QNORM_W, LM_KNORM_W, LM_WO, LM_WO_T, LM_LN2_W, LM_WGU, LM_WGU_T, LM_WD, LM_WD_T,
+ LM_LORA_A_QKV, LM_LORA_A_O, LM_LORA_A_GU, LM_LORA_A_D, LM_LORA_BT_QKV, LM_LORA_BT_O, LM_LORA_BT_GU, LM_LORA_BT_D) = range(20)
 
 
 class GemmEpilogue(C.Structure):
@@ -45,7 +47,7 @@ class MlpProjectorWeights(C.Structure):
 
 class LmWeights(C.Structure):
     _fields_ = [("n_layers", c_int), ("dim", c_int), ("ffn", c_int), ("n_q_heads", c_int), ("n_kv_heads", c_int),
-                ("head_dim", c_int), ("max_pos", c_int), ("vocab", c_ll), ("vocab_pad", c_ll), ("eps", c_float),
+                ("head_dim", c_int), ("max_pos", c_int), ("vocab", c_ll), ("vocab_pad", c_ll), ("eps", c_float), ("lora_pad", c_int),
                 ("embed_f32", P), ("embed_bf16", P), ("embed_bf16_t", P), ("final_norm_w", P),
                 ("rope_cos", P), ("rope_sin", P), ("layers", C.POINTER(P))]
 
@@ -54,7 +56,7 @@ class LmStepArgs(C.Structure):
     _fields_ = [("B", c_int), ("S", c_int), ("n_labelled", c_int), ("with_backward", c_int),
                 ("inputs_embeds", P), ("label_rows", P), ("label_targets", P), ("inv_num_items", c_float),
                 ("loss", P), ("row_loss", P), ("d_inputs_embeds", P), ("workspace", P), ("workspace_bytes", c_ll),
-                ("final_hidden", P)]
+                ("final_hidden", P), ("lora_grads", C.POINTER(P))]
 
 
 _SIGS = {
