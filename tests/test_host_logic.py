@@ -134,3 +134,43 @@ def test_tiny_audio_import_shim():
     import tiny_audio.projectors as c
     import tiny_audio_b200.asr_modeling as real
     assert b.ASRModel is real.ASRModel and hasattr(a, "ASRConfig") and "mlp" in c.PROJECTOR_CLASSES
+
+
+def test_checkpoint_round_trip_reference_layout(tmp_path):
+    """save_pretrained -> from_pretrained in the reference's on-disk layout (asr_modeling.py:59-131, 769-852): model.safetensors
+    holds only `projector.*`; LoRA adapters go to adapter_model.safetensors under peft's key names with adapter_config.json."""
+    import json
+    from safetensors.torch import load_file
+    from tiny_audio_b200.engine import PathDims
+    from tiny_audio_b200.synthetic import build_offline_model
+    dims = PathDims(enc_layers=1, lm_layers=2, vocab=5003, audio_token_id=5002)
+    m = build_offline_model(dims, device="cpu", use_lora=True)
+    with torch.no_grad():
+        for t in m.lora_adapters.targets:
+            m.lora_adapters.lora_B[t].normal_(0, 0.02)
+    m.save_pretrained(tmp_path)
+    files = {p.name for p in tmp_path.iterdir()}
+    assert {"config.json", "model.safetensors", "adapter_model.safetensors", "adapter_config.json", "preprocessor_config.json"} <= files
+    sd = load_file(str(tmp_path / "model.safetensors"))
+    assert sorted(sd) == sorted(f"projector.{k}" for k in m.projector.state_dict())
+    ad = load_file(str(tmp_path / "adapter_model.safetensors"))
+    assert "base_model.model.model.layers.1.self_attn.q_proj.lora_A.weight" in ad
+    assert "base_model.model.model.layers.0.mlp.down_proj.lora_B.weight" in ad
+    assert len(ad) == 2 * 7 * dims.lm_layers
+    assert ad["base_model.model.model.layers.0.mlp.gate_proj.lora_A.weight"].shape == (8, dims.lm_dim)
+    assert ad["base_model.model.model.layers.0.mlp.gate_proj.lora_B.weight"].shape == (dims.lm_ffn, 8)
+    cfg = json.loads((tmp_path / "adapter_config.json").read_text())
+    assert cfg["peft_type"] == "LORA" and cfg["r"] == 8 and cfg["lora_alpha"] == 32 and cfg["bias"] == "none"
+    assert sorted(cfg["target_modules"]) == sorted(["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"])
+    pc = json.loads((tmp_path / "preprocessor_config.json").read_text())
+    assert pc["processor_class"] == "ASRProcessor" and pc["auto_map"]["AutoProcessor"] == "asr_processing.ASRProcessor"
+
+    m2 = type(m).from_pretrained(str(tmp_path))             # config.json is re-read from the directory (offline)
+    assert m2.config.use_lora and m2.config.text_config.num_hidden_layers == dims.lm_layers
+    for (k, a), (_, b) in zip(m.projector.state_dict().items(), m2.projector.state_dict().items()):
+        assert torch.equal(a, b), k
+    for t in m.lora_adapters.targets:
+        assert torch.equal(m.lora_adapters.lora_A[t], m2.lora_adapters.lora_A[t])
+        assert torch.equal(m.lora_adapters.lora_B[t], m2.lora_adapters.lora_B[t])
+    trainable = [n for n, p in m2.named_parameters() if p.requires_grad]
+    assert len(trainable) == 4 + 14 and all(n.startswith(("projector.", "language_model.")) for n in trainable)

@@ -128,6 +128,15 @@ class ASRConfig(transformers.PretrainedConfig):
         self.pipeline_tag = "automatic-speech-recognition"
 
 
+    def to_diff_dict(self):
+        """HF serialises the difference to a default-constructed config; a default ASRConfig() resolves the two tower configs
+        from the hub, which is unavailable offline -- fall back to the full dict there (loads back identically)."""
+        try:
+            return super().to_diff_dict()
+        except OSError:
+            return self.to_dict()
+
+
 try:  # registering twice (e.g. next to the reference in one process) is tolerated by transformers 5.x
     transformers.AutoConfig.register("asr_model", ASRConfig, exist_ok=True)
 except TypeError:  # older signature

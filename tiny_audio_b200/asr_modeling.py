@@ -401,23 +401,80 @@ class ASRModel(PreTrainedModel, GenerationMixin):
                                    max_new_tokens=int(max_new_tokens or gc.max_new_tokens or 128),
                                    eos_token_ids=[e for e in eos if e is not None], pad_token_id=int(gc.pad_token_id or 0), **kw)
 
-    # ------------------------------------------------------------------ persistence (projector-only, reference layout)
+    # ------------------------------------------------------------------ persistence (reference checkpoint layout)
     def save_pretrained(self, save_directory, **kwargs):
+        """Checkpoint in the reference's on-disk layout (asr_modeling.py:769-852): `config.json`, `model.safetensors` holding
+        the overridden state_dict (trainable weights only, `projector.*` keys), tokenizer + feature-extractor files,
+        `preprocessor_config.json` with the ASRProcessor auto_map, and -- with LoRA attached -- peft's
+        `adapter_model.safetensors` / `adapter_config.json` (key names and fields as peft 0.19 writes them, so the files load
+        with `PeftModel.from_pretrained` in the stock stack).  The reference also copies its own python sources next to the
+        weights for trust_remote_code loading; this package's sources need the CUDA library and are not copied."""
         from safetensors.torch import save_file
         out = Path(save_directory)
         out.mkdir(parents=True, exist_ok=True)
-        self.config.save_pretrained(out)
-        save_file({k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}, str(out / "model.safetensors"))
+        self.config.vocab_size = self.language_model.config.vocab_size
+        if getattr(self.config, "text_config", None) is not None:
+            self.config.text_config.vocab_size = self.language_model.config.vocab_size
+        if hasattr(self.audio_tower.config, "num_mel_bins"):
+            self.config.audio_config.num_mel_bins = self.audio_tower.config.num_mel_bins
+        try:
+            self.config.save_pretrained(out)
+        except OSError:      # offline: the diff against a default ASRConfig() needs the hub (tower configs) -- write the full dict
+            self.config.to_json_file(str(out / "config.json"), use_diff=False)
+        save_file({k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}, str(out / "model.safetensors"),
+                  metadata={"format": "pt"})
         for obj in (getattr(self, "tokenizer", None), getattr(self, "feature_extractor", None)):
             if obj is not None and hasattr(obj, "save_pretrained"):
                 obj.save_pretrained(out)
-        (out / "tiny_audio_b200.json").write_text(json.dumps({"format": "projector-only", "keys": list(self.state_dict())}))
+        adapters = self.lora_adapters
+        if adapters is not None:
+            save_file({k: v.cpu().contiguous() for k, v in adapters.peft_state_dict().items()}, str(out / "adapter_model.safetensors"),
+                      metadata={"format": "pt"})
+            repo_id = (kwargs.get("repo_id") or kwargs.get("push_to_hub_model_id")
+                       or getattr(self.config, "pretrained_model_path", None) or "")
+            (out / "adapter_config.json").write_text(json.dumps({
+                "peft_type": "LORA", "task_type": "CAUSAL_LM", "base_model_name_or_path": repo_id, "r": adapters.rank,
+                "lora_alpha": adapters.alpha, "lora_dropout": 0.0, "bias": "none", "target_modules": list(adapters.targets),
+                "fan_in_fan_out": False, "inference_mode": False, "init_lora_weights": True, "modules_to_save": None,
+                "use_rslora": False, "use_dora": False}, indent=2))
+        pre = out / "preprocessor_config.json"
+        pc = json.loads(pre.read_text()) if pre.exists() else {}
+        pc.update({"processor_class": "ASRProcessor", "auto_map": {"AutoProcessor": "asr_processing.ASRProcessor"}})
+        pre.write_text(json.dumps(pc, indent=2))
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *args, **kwargs):
+        """Rebuild from a checkpoint directory written by this class or by the reference (asr_modeling.py:59-131): towers come
+        from the loader seams (config.audio_model_id / text_model_id), `model.safetensors` is overlaid non-strictly
+        (projector weights), then `adapter_model.safetensors` when config.use_lora and the adapter files exist."""
+        from safetensors.torch import load_file
+        config = kwargs.pop("config", None)
+        path = Path(pretrained_model_name_or_path)
+        if config is None:
+            config = ASRConfig.from_pretrained(str(path))
+        cls._is_loading_from_pretrained = True
+        try:
+            model = cls(config)
+            wfile = path / "model.safetensors"
+            if wfile.exists():
+                sd = load_file(str(wfile))
+                proj = {k[len("projector."):]: v for k, v in sd.items() if k.startswith("projector.")}
+                missing, unexpected = model.projector.load_state_dict(proj, strict=False)
+                if missing:
+                    raise RuntimeError(f"checkpoint {wfile} lacks projector weights {missing}")
+            if getattr(config, "use_lora", False):       # adapters are attached after the base weights, as in the reference
+                model._setup_lora(config)
+                afile = path / "adapter_model.safetensors"
+                if afile.exists() and (path / "adapter_config.json").exists():
+                    model.lora_adapters.load_peft_state_dict(load_file(str(afile)))
+            return model
+        finally:
+            cls._is_loading_from_pretrained = False
 
     def load_projector(self, path: str):
         from safetensors.torch import load_file
         sd = load_file(str(Path(path) / "model.safetensors"))
         self.projector.load_state_dict({k[len("projector."):]: v for k, v in sd.items() if k.startswith("projector.")})
-
 
 try:
     import transformers

@@ -11,6 +11,8 @@
 // reads S twice from TMEM (max pass, exp pass) to stay under 128 registers, and writes P as bf16 into shared memory
 // in the K-major SWIZZLE_128B layout the A-operand descriptor expects.  V is consumed as an MN-major B operand
 // straight from its row-major [kv][64] TMA tile.
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tinyaudio_b200.h"
@@ -19,7 +21,6 @@ namespace {
 
 constexpr int BQ = 128, BKV = 128;
 constexpr int TILE16 = 128 * 64 * 2;       // one [128 rows x 64 bf16] SWIZZLE_128B sub-tile
-constexpr int KV_SLOTS = 3;
 constexpr int ATT_THREADS = 384;           // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: softmax (2 threads per row)
 constexpr int TMEM_COLS_ATT = 256;
 constexpr uint32_t S_COL = 0, O_COL = 128;
@@ -27,6 +28,7 @@ constexpr uint32_t S_COL = 0, O_COL = 128;
 template <int HD>
 struct AttCfg {
     static constexpr int NSUB = HD / 64;
+    static constexpr int KV_SLOTS = (HD == 64) ? 3 : 4;               // K/V ring depth (HD 64: two CTAs per SM must fit)
     static constexpr int TILE_BYTES = NSUB * TILE16;                  // Q, K or V tile: 128 rows x HD
     static constexpr int P_BYTES = 2 * TILE16;                        // P: 128 x 128 bf16
     static constexpr int BAR_OFF = TILE_BYTES * (1 + KV_SLOTS) + P_BYTES;
@@ -75,12 +77,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* sQ = smem;
     uint8_t* sKV = smem + C::TILE_BYTES;
-    uint8_t* sP = smem + C::TILE_BYTES * (1 + KV_SLOTS);
+    uint8_t* sP = smem + C::TILE_BYTES * (1 + C::KV_SLOTS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;
-    uint64_t* kv_empty = bars + 1 + KV_SLOTS;
-    uint64_t* s_full = bars + 1 + 2 * KV_SLOTS;
+    uint64_t* kv_empty = bars + 1 + C::KV_SLOTS;
+    uint64_t* s_full = bars + 1 + 2 * C::KV_SLOTS;
     uint64_t* s_empty = s_full + 1;
     uint64_t* p_full = s_full + 2;
     uint64_t* pv_done = s_full + 3;
@@ -102,7 +104,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < KV_SLOTS; ++s) {
+        for (int s = 0; s < C::KV_SLOTS; ++s) {
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], 1);
         }
@@ -124,8 +126,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
             for (int u = 0; u < C::NSUB; ++u) tma_load_2d(sQ + u * TILE16, &tmQ, q_full, h * HD + u * 64, row_base + q0);
             for (int i = 0; i < 2 * n_kv; ++i) {
-                const int slot = i % KV_SLOTS;
-                const uint32_t ph = (uint32_t)(i / KV_SLOTS) & 1u;
+                const int slot = i % C::KV_SLOTS;
+                const uint32_t ph = (uint32_t)(i / C::KV_SLOTS) & 1u;
                 mbar_wait(&kv_empty[slot], ph ^ 1);
                 mbar_arrive_expect_tx(&kv_full[slot], C::TILE_BYTES);
                 const int j = i >> 1;
@@ -139,8 +141,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
             const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
             auto issue_s = [&](int j) {
-                const int i = 2 * j, slot = i % KV_SLOTS;
-                mbar_wait(&kv_full[slot], (uint32_t)(i / KV_SLOTS) & 1u);
+                const int i = 2 * j, slot = i % C::KV_SLOTS;
+                mbar_wait(&kv_full[slot], (uint32_t)(i / C::KV_SLOTS) & 1u);
                 mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(sKV + slot * C::TILE_BYTES);
@@ -157,9 +159,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             issue_s(0);
             for (int j = 0; j < n_kv; ++j) {
                 if (j + 1 < n_kv) issue_s(j + 1);
-                const int i = 2 * j + 1, slot = i % KV_SLOTS;
+                const int i = 2 * j + 1, slot = i % C::KV_SLOTS;
                 mbar_wait(p_full, (uint32_t)j & 1u);
-                mbar_wait(&kv_full[slot], (uint32_t)(i / KV_SLOTS) & 1u);
+                mbar_wait(&kv_full[slot], (uint32_t)(i / C::KV_SLOTS) & 1u);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(sKV + slot * C::TILE_BYTES);
 #pragma unroll
@@ -324,12 +326,295 @@ int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
     return 0;
 }
 
-int g_attn_tc = 1;
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant 2 (encoder shape, head_dim 64): one thread per query row, 6 warps per CTA, two CTAs per SM.
+//   warps 0-3 softmax (thread = query row = TMEM lane; the whole 128-column S row lives in registers, so S's TMEM columns
+//   are handed back to the MMA warp right after the load and there is no cross-warp row-max exchange), warp 4 TMA
+//   producer + TMEM allocator, warp 5 MMA issuer.
+//   POLY > 0: every POLY-th exponential of a full tile is evaluated on the FMA pipe (Cody-Waite range reduction + a
+//   degree-3 minimax polynomial, max rel. error 7.5e-5 -- far inside the bf16 rounding of P) instead of MUFU.EX2: the
+//   kernel is bound by the 16 exp2/clk/SM of the SFUs (tools/ubench/sfu.cu: a 3:1 mix sustains 20.8/clk/SM).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int ATT1_THREADS = 192;
+
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits now hold round(x)
+    const float f = x - (t - 12582912.0f);           // f in [-0.5, 0.5]
+    float p = fmaf(f, 0.05517143756151199f, 0.24261081218719482f);
+    p = fmaf(p, f, 0.6932609677314758f);
+    p = fmaf(p, f, 0.9999281167984009f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int HD>
+struct Att1Cfg {
+    static constexpr int NSUB = HD / 64;
+    // K/V ring depth 4: K_{j+1} re-uses the slot of K_{j-1} (free once S_{j-1} has been issued), so its TMA load starts
+    // almost two tiles ahead; with 3 slots it had to wait for PV_{j-1} and S_{j+1} arrived late (ncu: 13 % of the softmax
+    // warps' samples were the s_full wait).  2 CTAs x (16 K Q + 64 K ring + 32 K P + 128 B) + 2 x 1 K reserved < 228 K.
+    static constexpr int KV_SLOTS = 4;
+    static constexpr int TILE_BYTES = NSUB * TILE16;
+    static constexpr int P_BYTES = 2 * TILE16;
+    static constexpr int BAR_OFF = TILE_BYTES * (1 + KV_SLOTS) + P_BYTES;
+    static constexpr int SMEM = BAR_OFF + 128;
+};
+
+template <int HD, bool CAUSAL, int POLY>
+__global__ void __launch_bounds__(ATT1_THREADS, 2)
+attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int Hq, int Hkv,
+                    long long o_rs, float scale_log2) {
+    using C = Att1Cfg<HD>;
+    extern __shared__ __align__(1024) uint8_t smem_al[];
+    uint8_t* smem = smem_al;
+    if (smem_u32(smem) & 1023u) __trap();                 // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* sQ = smem;
+    uint8_t* sKV = smem + C::TILE_BYTES;
+    uint8_t* sP = smem + C::TILE_BYTES * (1 + C::KV_SLOTS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = bars + 1 + C::KV_SLOTS;
+    uint64_t* s_full = bars + 1 + 2 * C::KV_SLOTS;
+    uint64_t* s_empty = s_full + 1;
+    uint64_t* p_full = s_full + 2;
+    uint64_t* pv_done = s_full + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int hk = h / (Hq / Hkv);
+    const int q0 = qt * BQ;
+    const int n_kv_all = (S + BKV - 1) / BKV;
+    const int n_kv = CAUSAL ? min(n_kv_all, qt + 1) : n_kv_all;
+    const int row_base = b * S;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+            mbar_init(q_full, 1);
+            for (int s = 0; s < C::KV_SLOTS; ++s) {
+                mbar_init(&kv_full[s], 1);
+                mbar_init(&kv_empty[s], 1);
+            }
+            mbar_init(s_full, 1);
+            mbar_init(s_empty, 4);
+            mbar_init(p_full, 4);
+            mbar_init(pv_done, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc<TMEM_COLS_ATT>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, C::TILE_BYTES);
+#pragma unroll
+            for (int u = 0; u < C::NSUB; ++u) tma_load_2d(sQ + u * TILE16, &tmQ, q_full, h * HD + u * 64, row_base + q0);
+            for (int i = 0; i < 2 * n_kv; ++i) {
+                const int slot = i % C::KV_SLOTS;
+                const uint32_t ph = (uint32_t)(i / C::KV_SLOTS) & 1u;
+                mbar_wait(&kv_empty[slot], ph ^ 1);
+                mbar_arrive_expect_tx(&kv_full[slot], C::TILE_BYTES);
+                const int j = i >> 1;
+#pragma unroll
+                for (int u = 0; u < C::NSUB; ++u)
+                    tma_load_2d(sKV + slot * C::TILE_BYTES + u * TILE16, (i & 1) ? &tmV : &tmK, &kv_full[slot], hk * HD + u * 64,
+                                row_base + j * BKV);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
+            constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
+            const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+            auto issue_s = [&](int j) {
+                const int i = 2 * j, slot = i % C::KV_SLOTS;
+                mbar_wait(&kv_full[slot], (uint32_t)(i / C::KV_SLOTS) & 1u);
+                mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sKV + slot * C::TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                    const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
+                    umma_f16(tmem_base + S_COL, umma_desc_sw128_kmajor(q_addr + off), umma_desc_sw128_kmajor(k_addr + off), idesc_s,
+                             k != 0 ? 1u : 0u);
+                }
+                umma_commit(s_full);
+                umma_commit(&kv_empty[slot]);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) issue_s(j + 1);
+                const int i = 2 * j + 1, slot = i % C::KV_SLOTS;
+                mbar_wait(p_full, (uint32_t)j & 1u);
+                mbar_wait(&kv_full[slot], (uint32_t)(i / C::KV_SLOTS) & 1u);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(sKV + slot * C::TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    const uint32_t pa = p_addr + (k >> 2) * TILE16 + (k & 3) * 32;
+                    umma_f16(tmem_base + O_COL, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16), idesc_o,
+                             (j | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(pv_done);
+                umma_commit(&kv_empty[slot]);
+            }
+        }
+    } else {
+        const int r = warp * 32 + lane;                     // query row of the tile = TMEM lane
+        const uint32_t t_s = tmem_base + ((uint32_t)(warp * 32) << 16) + S_COL;
+        const uint32_t t_o = tmem_base + ((uint32_t)(warp * 32) << 16) + O_COL;
+        float m_ref = -INFINITY, l_sum = 0.f;
+        uint8_t* p_row = sP + r * 128;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(s_full, (uint32_t)j & 1u);
+            tc_fence_after();
+            int lim = S - j * BKV - 1;                      // my columns e = 0..127 are real (unmasked) keys iff e <= lim
+            if (CAUSAL && j == qt) lim = min(lim, r);
+            lim = min(lim, 127);
+            const bool full_tile = __all_sync(0xffffffffu, lim >= 127);
+            uint32_t v[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, v[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);            // S_j is in registers: the MMA warp may issue S_{j+1} now
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (!full_tile) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i > lim) v[c][i] = 0xff800000u;      // -inf
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[c][i]));
+            const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
+            const bool grow = mx > m_ref + 8.0f;
+            const float m_new = grow ? mx : m_ref;
+            const float alpha = (grow && j > 0) ? ex2_approx(m_ref - m_new) : 1.0f;
+            m_ref = m_new;
+            if (j > 0) {
+                mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);     // PV_{j-1} has consumed sP and finished updating O
+                tc_fence_after();
+            }
+            float l4[4] = {0.f, 0.f, 0.f, 0.f};
+            const float neg_m = -m_ref;
+            auto exp_phase = [&](auto use_poly) {
+                constexpr bool UP = decltype(use_poly)::value;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        float e[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            const float x = fmaf(__uint_as_float(v[c][8 * qd + t]), scale_log2, neg_m);
+                            if (UP && POLY > 0 && (t % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) e[t] = ex2_poly(x);
+                            else e[t] = ex2_approx(x);                    // exp2(-inf) = 0 for masked columns
+                            l4[t & 3] += e[t];
+                        }
+                        uint4 u;
+                        u.x = pack_bf16x2(e[0], e[1]);
+                        u.y = pack_bf16x2(e[2], e[3]);
+                        u.z = pack_bf16x2(e[4], e[5]);
+                        u.w = pack_bf16x2(e[6], e[7]);
+                        const int k16 = c * 4 + qd;                       // 16-byte chunk of the 256-byte P row
+                        *reinterpret_cast<uint4*>(p_row + (k16 >> 3) * TILE16 + (((k16 & 7) ^ (r & 7)) << 4)) = u;
+                    }
+                }
+            };
+            if (POLY > 0 && full_tile) exp_phase(std::true_type{});
+            else exp_phase(std::false_type{});
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {                 // lazy rescale of O (rare)
+#pragma unroll 1
+                for (int c = 0; c < HD / 32; ++c) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(t_o + c * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st_32x32(t_o + c * 32, o);
+                }
+                tmem_st_wait();
+                l_sum *= alpha;
+            }
+            l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(pv_done, (uint32_t)(n_kv - 1) & 1u);
+        tc_fence_after();
+        const int row = q0 + r;
+        const float inv = 1.0f / l_sum;
+        bf16* orow = O + ((long long)row_base + row) * o_rs + (long long)h * HD;
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_o + c * 32, o);
+            tmem_ld_wait();
+            if (row < S) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(o[8 * qd + 0]) * inv, __uint_as_float(o[8 * qd + 1]) * inv);
+                    u.y = pack_bf16x2(__uint_as_float(o[8 * qd + 2]) * inv, __uint_as_float(o[8 * qd + 3]) * inv);
+                    u.z = pack_bf16x2(__uint_as_float(o[8 * qd + 4]) * inv, __uint_as_float(o[8 * qd + 5]) * inv);
+                    u.w = pack_bf16x2(__uint_as_float(o[8 * qd + 6]) * inv, __uint_as_float(o[8 * qd + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + qd * 8) = u;
+                }
+            }
+        }
+        if (LSE && row < S) LSE[((long long)b * Hq + h) * S + row] = (m_ref + log2f(l_sum)) * 0.69314718055994531f;
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<TMEM_COLS_ATT>(tmem_base);
+}
+
+template <int HD, bool CAUSAL, int POLY>
+int launch_attn_tc1(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* o, float* lse, int B, int S, int Hq,
+                    int Hkv, long long o_rs, float scale, cudaStream_t st) {
+    using C = Att1Cfg<HD>;
+    auto kern = attn_tc_fwd1_kernel<HD, CAUSAL, POLY>;
+    static bool done = false;
+    if (!done) {
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        done = true;
+    }
+    dim3 grid((S + BQ - 1) / BQ, Hq, B);
+    kern<<<grid, ATT1_THREADS, C::SMEM, st>>>(tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f);
+    TA_LAUNCH_CHECK();
+    return 0;
+}
+
+// 0: mma.sync; 1: tcgen05, 2 threads per row everywhere; 2 (default): head_dim-64 non-causal runs the one-thread-per-row variant
+// (0.590 vs 0.632 ms per encoder layer at B=32, S=1500); 3 / 4: that variant with every 4th / 2nd exp2 on the FMA pipe -- slower
+// (0.68 / 0.75 ms): with two softmax warps per sub-partition the kernel is issue/latency-bound, not MUFU-bound (profiles/).
+int g_attn_tc = 2;
 
 }  // namespace
 
 TA_API int ta_attn_set_tc(int on) {
-    g_attn_tc = on ? 1 : 0;
+    g_attn_tc = (on < 0 || on > 4) ? 2 : on;
     return 0;
 }
 int k_attn_tc_enabled() { return g_attn_tc; }
@@ -352,6 +637,11 @@ int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* l
     rc = k_make_tensor_map_2d(&tv, v, rows, (long long)Hkv * head_dim, v_rs, BKV);
     if (rc) return rc;
     *handled = 1;
+    if (head_dim == 64 && !causal && g_attn_tc >= 2) {
+        if (g_attn_tc == 2) return launch_attn_tc1<64, false, 0>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+        if (g_attn_tc == 3) return launch_attn_tc1<64, false, 4>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+        return launch_attn_tc1<64, false, 2>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+    }
     if (head_dim == 64) {
         if (causal) return launch_attn_tc<64, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         return launch_attn_tc<64, false>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);

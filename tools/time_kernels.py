@@ -57,12 +57,12 @@ lib.ta_gemm_set_cta_pair(1)
 B, S, H, hd = 32, 1500, 20, 64
 qkv = torch.randn(B, S, 3 * H * hd, device=dev, dtype=BF16)
 o = torch.empty(B, S, H * hd, device=dev, dtype=BF16)
-for tc in (0, 1):
+for tc in (0, 1, 2, 3, 4):
     lib.ta_attn_set_tc(tc)
     t = timeit(lambda: L.check(lib.ta_attn_fwd(L.ptr(qkv), L.ptr(qkv[:, :, H * hd:]), L.ptr(qkv[:, :, 2 * H * hd:]), L.ptr(o), None, B, S, H,
                                                H, hd, 3 * H * hd, 3 * H * hd, 3 * H * hd, H * hd, 0, hd ** -0.5, L.stream_ptr())), reps=5)
     print(f"enc attention fwd tc={tc}: {t:.3f} ms  {4.0 * B * H * S * S * hd / t / 1e9:.0f} TF/s", flush=True)
-lib.ta_attn_set_tc(1)
+lib.ta_attn_set_tc(2)
 
 # decoder attention fwd + bwd (causal GQA, hd 128)
 B, S, Hq, Hkv, hd = 32, 464, 16, 8, 128
@@ -83,7 +83,7 @@ for tc in (0, 1):
                                                 L.ptr(dk), L.ptr(dv), B, S, Hq, Hkv, hd, Hq * hd, Hkv * hd, Hkv * hd, Hq * hd, Hq * hd,
                                                 Hq * hd, Hkv * hd, Hkv * hd, 1, hd ** -0.5, L.stream_ptr())), reps=5)
     print(f"lm attention tc={tc}: fwd {tf:.3f} ms  bwd (prep+memset+main) {tb:.3f} ms", flush=True)
-lib.ta_attn_set_tc(1)
+lib.ta_attn_set_tc(2)
 
 lib.ta_debug_set(1, 1)
 tb = timeit(lambda: L.check(lib.ta_attn_bwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), L.ptr(do), L.ptr(lse), L.ptr(dsum), L.ptr(dq),
