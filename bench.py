@@ -222,11 +222,16 @@ def run_ours(args):
             sampler.start()
         c0 = lib.ta_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        prof = sampler is not None and os.environ.get("TA_PROFILE_STEP") == "1"   # ncu --profile-from-start off
+        if prof:
+            torch.cuda.profiler.start()
         e0.record()
         for _ in range(steps):
             last = fn()
         e1.record()
         barrier()
+        if prof:
+            torch.cuda.profiler.stop()
         c1 = lib.ta_launch_count()
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)

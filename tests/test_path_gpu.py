@@ -249,7 +249,7 @@ def test_lora_adapters_vs_oracle(cuda):
 
 
 def test_lora_zero_b_is_identity_and_projector_freeze(cuda):
-    """peft's initial state (B = 0) must leave the loss exactly that of the adapter-free path (the extra K columns multiply
+    """peft's initial state (B = 0) must leave the loss that of the adapter-free path (up to the CE kernel's atomic summation order) (the extra K columns multiply
     zeros) and the projector gradients equal up to the summation order of the attention-backward dQ atomics (fp32
     red.global.add: not bit-reproducible run to run); dA is then identically zero and dB is not.  With freeze_projector the projector
     receives no gradient but the adapters still do (Stage-2 recipe, asr_modeling.py:112-115)."""
@@ -267,13 +267,14 @@ def test_lora_zero_b_is_identity_and_projector_freeze(cuda):
                                 proj_state=W["projector"])
     plain.train()
     loss_p = float(_model_step(plain, batch, n_items))
-    assert loss == loss_p, (loss, loss_p)
+    # the CE kernel sums the per-row losses with fp32 atomics (order not reproducible): equal up to that
+    assert abs(loss - loss_p) < 2e-6 * abs(loss_p), (loss, loss_p)
     for k, p in plain.projector.named_parameters():
         assert rel(p.grad, g_l[k]) < 1e-3, k                    # atomics order only
     del plain
     model.projector.requires_grad_(False)
     loss_f = float(_model_step(model, batch, n_items))
-    assert loss_f == loss
+    assert abs(loss_f - loss) < 2e-6 * abs(loss)
     assert all(p.grad is None for p in model.projector.parameters())
     for t in ad.targets:
         assert rel(ad.lora_B[t].grad, gb[t]) < 1e-3, t
