@@ -223,12 +223,38 @@ typedef struct ta_lm_step_args {
     long long workspace_bytes;
     float* final_hidden;          /* optional [B*S, dim] fp32: last layer's output BEFORE the final norm (for ta_lm_hidden_to_logits) */
     float* const* lora_grads;     /* LoRA + backward: HOST array n_layers * TA_LM_LORA_GRADS_PER_LAYER device pointers */
+    void* k_cache;                /* optional (prefill of generate): bf16 [n_layers, B, cache_max_seq, Hkv*hd]; rows [0, S) of every */
+    void* v_cache;                /*   layer receive the prompt's roped keys / values (use_cache=True in HF generate)             */
+    int cache_max_seq;
 } ta_lm_step_args;
 int ta_lm_workspace_bytes(const ta_lm_weights* w, int B, int S, int n_labelled, int with_backward, long long* bytes);
 int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args* a, void* stream);
 /* full-vocabulary logits for given rows (eval / generate):  logits bf16 [n_rows, vocab_pad] */
 int ta_lm_hidden_to_logits(const ta_lm_weights* w, const float* hidden_f32 /*[B*S, dim] pre-final-norm*/, const int* rows,
                            int n_rows, void* normed_ws /*bf16 [n_rows, dim]*/, void* logits_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * f1. greedy decode with a KV cache: ASRModel.generate -> language_model.generate(inputs_embeds, use_cache),
+ *     tiny_audio/asr_modeling.py:562-646; greedy defaults asr_config.py:103-111.  Prefill = ta_lm_forward_backward with
+ *     k_cache / v_cache set; then one ta_lm_decode_step per new token:
+ *       ids [B] int64 (the token fed at position *pos) -> embed -> 28 x [RMSNorm, qkv, head-norm + RoPE + cache append,
+ *       single-query attention over cache rows [0, *pos], o + residual, RMSNorm, SwiGLU MLP + residual] -> final norm ->
+ *       tied lm_head -> logits bf16 [B, vocab_pad] -> next_ids [B] = argmax;  *pos += 1 (device side, graph-replayable).
+ *     B <= 32 per call.  All linears are HBM-bound skinny products (csrc/decode.cu).
+ * ---------------------------------------------------------------------------------------------- */
+enum { TA_SKINNY_BF16 = 0,      /* out bf16 [M,N] = X W^T                                                   */
+       TA_SKINNY_F32_RESID = 1, /* out f32  [M,N] = resid + bf16(X W^T)                                     */
+       TA_SKINNY_SWIGLU = 2 };  /* W rows interleaved [64 gate | 64 up]: out bf16 [M,N/2] = bf16(silu(g)) * u */
+int ta_skinny_gemm_bf16(const void* X, long long ldx, const void* W, long long ldw, int M /*<= 32*/, int N, int K, int mode,
+                        void* out, long long ldo, const float* resid, void* stream);
+int ta_decode_attn(const void* q /*bf16 [B, Hq*128]*/, const void* k_cache /*bf16 [B, max_seq, Hkv*128]*/, const void* v_cache,
+                   void* out /*bf16 [B, ld_out]*/, long long ld_out, const int* pos /*device: attends rows [0, *pos]*/, int B, int Hq,
+                   int Hkv, int max_seq, float scale, void* stream);
+int ta_argmax_rows(const void* logits_bf16, long long ld, int rows, int V, long long* next_ids, void* stream);
+int ta_lm_decode_workspace_bytes(const ta_lm_weights* w, int B, long long* bytes);
+int ta_lm_decode_step(const ta_lm_weights* w, const long long* ids, int* pos /*device*/, int pos_host /*validation only*/,
+                      void* k_cache, void* v_cache, int cache_max_seq, int B, void* workspace, long long workspace_bytes,
+                      void* logits_bf16 /*[B, vocab_pad]*/, long long* next_ids /*[B]*/, void* stream);
 
 #ifdef __cplusplus
 }

@@ -439,3 +439,70 @@ def test_adamw_clip(cuda):
         opt.step(grads)
         for p, r in zip(ps, ref):
             assert max_err(p, r) < 2e-6
+
+
+# ------------------------------------------------------------------ KV-cache decode kernels (csrc/decode.cu)
+@pytest.mark.parametrize("M", [1, 5, 8, 13, 16, 32])
+@pytest.mark.parametrize("N,K", [(1024, 2048), (4096, 1024), (1024, 3200), (128, 1024)])
+def test_skinny_gemm_plain_and_resid(cuda, M, N, K):
+    lib = L.load()
+    ld = K + 64                                    # strided activations (the LoRA-augmented buffers are)
+    xb = rnd(M, ld, seed=M)
+    x = xb[:, :K]
+    w = rnd(N, K, seed=N + K, scale=0.05)
+    ref = x.float() @ w.float().t()
+    out = torch.empty(M, N, device="cuda", dtype=BF16)
+    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), ld, L.ptr(w), K, M, N, K, L.SKINNY_BF16, L.ptr(out), N, None, L.stream_ptr()))
+    assert rel_err(out, ref) < 4e-3
+    resid = rnd(M, N, seed=3, dtype=F32)
+    o32 = torch.empty(M, N, device="cuda", dtype=F32)
+    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), ld, L.ptr(w), K, M, N, K, L.SKINNY_F32_RESID, L.ptr(o32), N, L.ptr(resid), L.stream_ptr()))
+    assert rel_err(o32 - resid, ref.to(BF16).float()) < 4e-3
+    # bit-reproducible (fixed-order split-K reduction) and equal to the tcgen05 GEMM up to the accumulation order
+    out2 = torch.empty_like(out)
+    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), ld, L.ptr(w), K, M, N, K, L.SKINNY_BF16, L.ptr(out2), N, None, L.stream_ptr()))
+    assert torch.equal(out, out2)
+    big = L.gemm(x, w)
+    assert rel_err(out, big) < 3e-3
+
+
+@pytest.mark.parametrize("M", [3, 32])
+def test_skinny_gemm_swiglu(cuda, M):
+    lib = L.load()
+    D, Fd = 1024, 3072
+    x = rnd(M, D, seed=1)
+    wg, wu = rnd(Fd, D, seed=2, scale=0.04), rnd(Fd, D, seed=3, scale=0.04)
+    wgu = torch.cat([wg.view(Fd // 64, 1, 64, D), wu.view(Fd // 64, 1, 64, D)], 1).reshape(2 * Fd, D).contiguous()
+    h = torch.empty(M, Fd, device="cuda", dtype=BF16)
+    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), D, L.ptr(wgu), D, M, 2 * Fd, D, L.SKINNY_SWIGLU, L.ptr(h), Fd, None, L.stream_ptr()))
+    g = (x.float() @ wg.float().t()).to(BF16).float()
+    u = (x.float() @ wu.float().t()).to(BF16).float()
+    href = F.silu(g).to(BF16).float() * u
+    assert rel_err(h, href) < 6e-3
+    assert rel_err(h, L.gemm(x, wgu, epi=L.EPI_SWIGLU)) < 4e-3
+
+
+@pytest.mark.parametrize("B,n_keys,Hq,Hkv", [(1, 1, 16, 8), (3, 37, 16, 8), (32, 450, 16, 8), (2, 129, 4, 4)])
+def test_decode_attention_and_argmax(cuda, B, n_keys, Hq, Hkv):
+    lib = L.load()
+    hd, max_seq = 128, n_keys + 7
+    q = rnd(B, Hq * hd, seed=1)
+    kc = rnd(B, max_seq, Hkv * hd, seed=2)
+    vc = rnd(B, max_seq, Hkv * hd, seed=3)
+    out = torch.empty(B, Hq * hd, device="cuda", dtype=BF16)
+    pos = torch.tensor([n_keys - 1], device="cuda", dtype=torch.int32)
+    L.check(lib.ta_decode_attn(L.ptr(q), L.ptr(kc), L.ptr(vc), L.ptr(out), Hq * hd, L.ptr(pos), B, Hq, Hkv, max_seq, hd ** -0.5,
+                               L.stream_ptr()))
+    qf = q.float().view(B, Hq, 1, hd)
+    kf = kc[:, :n_keys].float().view(B, n_keys, Hkv, hd).permute(0, 2, 1, 3).repeat_interleave(Hq // Hkv, 1)
+    vf = vc[:, :n_keys].float().view(B, n_keys, Hkv, hd).permute(0, 2, 1, 3).repeat_interleave(Hq // Hkv, 1)
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) * hd ** -0.5, -1) @ vf
+    assert rel_err(out.view(B, Hq, hd), ref.squeeze(2)) < 6e-3
+    # argmax: lowest index on ties, padding columns ignored
+    V, ld = 1000, 1024
+    logits = rnd(B, ld, seed=5)
+    logits[:, V:] = 100.0
+    logits[0, 17] = logits[0, 900] = 50.0
+    ids = torch.empty(B, device="cuda", dtype=torch.int64)
+    L.check(lib.ta_argmax_rows(L.ptr(logits), ld, B, V, L.ptr(ids), L.stream_ptr()))
+    assert torch.equal(ids, logits[:, :V].float().argmax(-1)) and int(ids[0]) == 17

@@ -397,6 +397,12 @@ class ASRModel(PreTrainedModel, GenerationMixin):
         kw = dict(waveform=feats.float().contiguous()) if feats.dim() == 2 else dict(input_features=feats)
         gc = self.generation_config
         eos = gc.eos_token_id if isinstance(gc.eos_token_id, (list, tuple)) else [gc.eos_token_id]
+        adapters = getattr(self, "lora_adapters", None)
+        if adapters is not None:      # refresh the engine's adapter operands from the current parameters
+            a, b = adapters.tensors()
+            hot.lm.update_lora({t: v.detach() for t, v in a.items()}, {t: v.detach() for t, v in b.items()}, adapters.scaling)
+        use_cache = kwargs.get("use_cache")
+        kw["use_cache"] = bool(getattr(self.config, "use_cache", True) if use_cache is None else use_cache)
         return hot.greedy_generate(input_ids=input_ids, proj_params=params, audio_token_counts=audio_token_counts,
                                    max_new_tokens=int(max_new_tokens or gc.max_new_tokens or 128),
                                    eos_token_ids=[e for e in eos if e is not None], pad_token_id=int(gc.pad_token_id or 0), **kw)

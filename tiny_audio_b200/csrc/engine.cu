@@ -294,6 +294,8 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
     TA_REQUIRE(w->lora_pad == 0 || w->lora_pad == 128, "lora_pad must be 0 or 128");
     const int P = w->lora_pad;
     TA_REQUIRE(!(P && a->with_backward) || a->lora_grads, "LoRA backward needs the gradient pointer table");
+    TA_REQUIRE(!a->k_cache || (a->v_cache && a->S <= a->cache_max_seq), "prefill: v_cache missing or S %d > cache_max_seq %d", a->S,
+               a->cache_max_seq);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int B = a->B, S = a->S, nl = a->n_labelled;
     const long long M = (long long)B * S;
@@ -331,6 +333,11 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
         RUN(gemm(b.xn, ldX, Lw[TA_LM_WQKV], ldX, M, QKV, D + P, TA_EPI_BF16, qkv, QKV, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
         RUN(k_lm_qknorm_rope_fwd(qkv, qk, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W], w->rope_cos, w->rope_sin,
                                  M, S, Hq, Hkv, w->eps, st));
+        if (a->k_cache) {   // prefill of generate(): keep the prompt's roped keys and values for the decode steps
+            const long long per_layer = (long long)B * a->cache_max_seq * KD;
+            RUN(k_kv_cache_store(qk + QD, QK, qkv + QK, QKV, reinterpret_cast<bf16*>(a->k_cache) + l * per_layer,
+                                 reinterpret_cast<bf16*>(a->v_cache) + l * per_layer, B, S, KD, a->cache_max_seq, st));
+        }
         RUN(ta_attn_fwd(qk, qk + QD, qkv + QK, att, lse, B, S, Hq, Hkv, hd, QK, QK, QKV, ldAtt, 1, scale, st));
         if (P) RUN(plain(att, ldAtt, Lw[TA_LM_LORA_A_O], QD, M, P, QD, att + QD, ldAtt, st));
         RUN(gemm(att, ldAtt, Lw[TA_LM_WO], ldAtt, M, D, QD + P, TA_EPI_F32_RESID, x_mid, D, nullptr, x_in, nullptr, 0, nullptr, 0, st));
@@ -434,5 +441,85 @@ TA_API int ta_lm_hidden_to_logits(const ta_lm_weights* w, const float* hidden, c
     RUN(k_rmsnorm_f32(hidden, w->final_norm_w, (bf16*)normed_ws, rows, n_rows, w->dim, w->eps, st));
     RUN(gemm(normed_ws, w->dim, w->embed_bf16, w->dim, n_rows, (int)w->vocab_pad, w->dim, TA_EPI_BF16, logits, w->vocab_pad, nullptr,
              nullptr, nullptr, 0, nullptr, 0, st));
+    return 0;
+}
+
+// =============================================================================================================
+// greedy decode with a KV cache: one token per sequence (csrc/decode.cu holds the kernels)
+// =============================================================================================================
+namespace {
+struct DecBufs {
+    float *x0, *x1, *x2;   // [B, D] fp32 residual stream (layer in / mid / out)
+    bf16 *xn, *qkv, *q, *att, *h;
+};
+long long dec_carve(const ta_lm_weights* w, int B, void* ws, long long cap, DecBufs* b) {
+    const long long D = w->dim, F = w->ffn, P = w->lora_pad;
+    const long long QD = (long long)w->n_q_heads * w->head_dim, KD = (long long)w->n_kv_heads * w->head_dim;
+    Carver c(ws, cap);
+    b->x0 = c.take<float>(B * D);
+    b->x1 = c.take<float>(B * D);
+    b->x2 = c.take<float>(B * D);
+    b->xn = c.take<bf16>(B * (D + P));
+    b->qkv = c.take<bf16>(B * (QD + 2 * KD));
+    b->q = c.take<bf16>(B * QD);
+    b->att = c.take<bf16>(B * (QD + P));
+    b->h = c.take<bf16>(B * (F + P));
+    return c.off;
+}
+}  // namespace
+
+TA_API int ta_lm_decode_workspace_bytes(const ta_lm_weights* w, int B, long long* bytes) {
+    TA_REQUIRE(w && bytes, "null");
+    DecBufs b;
+    *bytes = dec_carve(w, B, nullptr, 0, &b) + 256;
+    return 0;
+}
+
+TA_API int ta_lm_decode_step(const ta_lm_weights* w, const long long* ids, int* pos, int pos_host, void* k_cache, void* v_cache,
+                             int cache_max_seq, int B, void* workspace, long long workspace_bytes, void* logits, long long* next_ids,
+                             void* stream) {
+    TA_REQUIRE(w && ids && pos && k_cache && v_cache && workspace && logits && next_ids, "ta_lm_decode_step: null pointer");
+    TA_REQUIRE(w->head_dim == 128, "Qwen3 path: head_dim must be 128");
+    TA_REQUIRE(B >= 1 && B <= 32, "decode step: batch %d not in [1, 32]", B);
+    TA_REQUIRE(pos_host >= 0 && pos_host < cache_max_seq && pos_host < w->max_pos, "decode step: position %d outside the cache (%d) / rotary table (%d)",
+               pos_host, cache_max_seq, w->max_pos);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int D = w->dim, F = w->ffn, Hq = w->n_q_heads, Hkv = w->n_kv_heads, hd = w->head_dim, P = w->lora_pad;
+    const int QD = Hq * hd, KD = Hkv * hd, QKV = QD + 2 * KD;
+    const long long ldX = D + P, ldH = F + P, ldAtt = QD + P;
+    DecBufs b;
+    const long long need = dec_carve(w, B, workspace, workspace_bytes, &b);
+    TA_REQUIRE(need <= workspace_bytes, "decode workspace too small: need %lld, have %lld", need, workspace_bytes);
+    const float scale = 1.0f / sqrtf((float)hd);
+    const long long per_layer = (long long)B * cache_max_seq * KD;
+
+    RUN(k_embed_rows(ids, w->embed_f32, b.x0, B, D, w->vocab, st));
+    float* x_in = b.x0;
+    float* x_mid = b.x1;
+    float* x_out = b.x2;
+    for (int l = 0; l < w->n_layers; ++l) {
+        const void* const* Lw = w->layers + (long long)l * TA_LM_PTRS_PER_LAYER;
+        bf16* kc = reinterpret_cast<bf16*>(k_cache) + l * per_layer;
+        bf16* vc = reinterpret_cast<bf16*>(v_cache) + l * per_layer;
+        RUN(k_rmsnorm_f32(x_in, (const float*)Lw[TA_LM_LN1_W], b.xn, nullptr, B, D, w->eps, st, ldX));
+        if (P) RUN(k_skinny_gemm(b.xn, ldX, (const bf16*)Lw[TA_LM_LORA_A_QKV], D, B, P, D, TA_SKINNY_BF16, b.xn + D, ldX, nullptr, st));
+        RUN(k_skinny_gemm(b.xn, ldX, (const bf16*)Lw[TA_LM_WQKV], ldX, B, QKV, D + P, TA_SKINNY_BF16, b.qkv, QKV, nullptr, st));
+        RUN(k_decode_qknorm_rope_cache(b.qkv, b.q, kc, vc, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W], w->rope_cos,
+                                       w->rope_sin, pos, B, Hq, Hkv, cache_max_seq, w->eps, st));
+        RUN(k_decode_attn(b.q, kc, vc, b.att, ldAtt, pos, B, Hq, Hkv, cache_max_seq, scale, st));
+        if (P) RUN(k_skinny_gemm(b.att, ldAtt, (const bf16*)Lw[TA_LM_LORA_A_O], QD, B, P, QD, TA_SKINNY_BF16, b.att + QD, ldAtt, nullptr, st));
+        RUN(k_skinny_gemm(b.att, ldAtt, (const bf16*)Lw[TA_LM_WO], ldAtt, B, D, QD + P, TA_SKINNY_F32_RESID, x_mid, D, x_in, st));
+        RUN(k_rmsnorm_f32(x_mid, (const float*)Lw[TA_LM_LN2_W], b.xn, nullptr, B, D, w->eps, st, ldX));
+        if (P) RUN(k_skinny_gemm(b.xn, ldX, (const bf16*)Lw[TA_LM_LORA_A_GU], D, B, P, D, TA_SKINNY_BF16, b.xn + D, ldX, nullptr, st));
+        RUN(k_skinny_gemm(b.xn, ldX, (const bf16*)Lw[TA_LM_WGU], ldX, B, 2 * F, D + P, TA_SKINNY_SWIGLU, b.h, ldH, nullptr, st));
+        if (P) RUN(k_skinny_gemm(b.h, ldH, (const bf16*)Lw[TA_LM_LORA_A_D], F, B, P, F, TA_SKINNY_BF16, b.h + F, ldH, nullptr, st));
+        RUN(k_skinny_gemm(b.h, ldH, (const bf16*)Lw[TA_LM_WD], ldH, B, D, F + P, TA_SKINNY_F32_RESID, x_out, D, x_mid, st));
+        float* t = x_in;
+        x_in = x_out;
+        x_out = t;
+    }
+    RUN(k_rmsnorm_f32(x_in, w->final_norm_w, b.xn, nullptr, B, D, w->eps, st, D));
+    RUN(k_skinny_gemm(b.xn, D, (const bf16*)w->embed_bf16, D, B, (int)w->vocab_pad, D, TA_SKINNY_BF16, logits, w->vocab_pad, nullptr, st));
+    RUN(k_argmax_rows((const bf16*)logits, w->vocab_pad, B, (int)w->vocab, next_ids, pos, st));
     return 0;
 }

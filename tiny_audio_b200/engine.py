@@ -429,21 +429,43 @@ class HotPath:
         row_loss = torch.empty(nl, device=self.device, dtype=F32) if want_row_loss else None
         args = L.LmStepArgs(B, S, nl, int(with_backward), L.ptr(emb), L.ptr(rows), L.ptr(targets), inv_items, L.ptr(loss),
                             L.ptr(row_loss), L.ptr(demb), L.ptr(ws), n.value, None,
-                            C.cast(self.lm.grad_table, C.POINTER(L.P)) if (with_backward and self.lm.grad_table is not None) else None)
+                            C.cast(self.lm.grad_table, C.POINTER(L.P)) if (with_backward and self.lm.grad_table is not None) else None,
+                            None, None, 0)
         L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
         return loss, demb, row_loss
 
-    def lm_hidden(self, emb: torch.Tensor, B: int, S: int) -> torch.Tensor:
-        """Forward-only decoder pass; returns the last layer's output before the final norm, fp32 [B*S, dim]."""
+    def lm_hidden(self, emb: torch.Tensor, B: int, S: int, kv_cache=None) -> torch.Tensor:
+        """Forward-only decoder pass; returns the last layer's output before the final norm, fp32 [B*S, dim].
+        `kv_cache` = (k, v, max_seq): the prompt's roped keys / values of every layer are stored in rows [0, S) (prefill)."""
         d = self.dims
         n = C.c_longlong()
         L.check(self.lib.ta_lm_workspace_bytes(C.byref(self.lm.c), B, S, 0, 0, C.byref(n)))
         ws = self.ws.get("lm", n.value)
         loss = torch.zeros(1, device=self.device, dtype=F32)
         hid = self.ws.typed("final_hidden", (B * S, d.lm_dim), F32)
-        args = L.LmStepArgs(B, S, 0, 0, L.ptr(emb), None, None, 1.0, L.ptr(loss), None, None, L.ptr(ws), n.value, L.ptr(hid), None)
+        kc, vc, ms = kv_cache if kv_cache is not None else (None, None, 0)
+        args = L.LmStepArgs(B, S, 0, 0, L.ptr(emb), None, None, 1.0, L.ptr(loss), None, None, L.ptr(ws), n.value, L.ptr(hid), None,
+                            L.ptr(kc), L.ptr(vc), ms)
         L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
         return hid
+
+    def new_kv_cache(self, B: int, max_seq: int):
+        """bf16 [layers, B, max_seq, Hkv*head_dim] x 2 (keys are stored normed + roped)."""
+        d = self.dims
+        shape = (d.lm_layers, B, max_seq, d.lm_kv_heads * d.lm_head_dim)
+        return (torch.empty(shape, device=self.device, dtype=BF16), torch.empty(shape, device=self.device, dtype=BF16), max_seq)
+
+    def decode_step(self, ids: torch.Tensor, pos_dev: torch.Tensor, pos_host: int, kv_cache, logits: torch.Tensor,
+                    next_ids: torch.Tensor):
+        """One KV-cache decode step (ta_lm_decode_step): feeds ids [B] at position *pos_dev, writes the bf16 logits
+        [B, vocab_pad] and next_ids [B] = argmax, and advances *pos_dev on the device."""
+        B = int(ids.numel())
+        kc, vc, ms = kv_cache
+        n = C.c_longlong()
+        L.check(self.lib.ta_lm_decode_workspace_bytes(C.byref(self.lm.c), B, C.byref(n)))
+        ws = self.ws.get("lm_decode", n.value)
+        L.check(self.lib.ta_lm_decode_step(C.byref(self.lm.c), L.ptr(ids), L.ptr(pos_dev), int(pos_host), L.ptr(kc), L.ptr(vc), ms, B,
+                                           L.ptr(ws), n.value, L.ptr(logits), L.ptr(next_ids), L.stream_ptr()))
 
     def logits_rows(self, hidden: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
         """final norm + tied lm_head on the given flat token rows -> bf16 logits [n_rows, vocab] (padding sliced off)."""
@@ -470,10 +492,13 @@ class HotPath:
 
     @torch.no_grad()
     def greedy_generate(self, *, input_ids: torch.Tensor, proj_params, waveform=None, input_features=None,
-                        audio_token_counts=None, max_new_tokens: int = 16, eos_token_ids=(), pad_token_id: int = 0):
+                        audio_token_counts=None, max_new_tokens: int = 16, eos_token_ids=(), pad_token_id: int = 0,
+                        use_cache: bool = True, sync_every: int = 8):
         """Greedy decoding (num_beams=1, do_sample=False: the reference's generation defaults, asr_config.py:103-111).
-        Round-1 implementation re-runs the decoder over the whole sequence for every new token (no KV cache yet --
-        SURVEY.md section 8f rank 1); all prompts in the batch have the same length (equal-length clips)."""
+        use_cache=True (default, like HF generate): one prefill pass that also fills the KV cache, then one
+        ta_lm_decode_step per new token (HBM-bound skinny kernels, csrc/decode.cu).  use_cache=False re-runs the decoder
+        over the whole sequence for every new token (kept as the A/B reference of the cache path).  All prompts in the
+        batch have the same length (equal-length clips); batches larger than 32 sequences fall back to use_cache=False."""
         d = self.dims
         ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
         B = ids.shape[0]
@@ -485,6 +510,34 @@ class HotPath:
         eos = torch.tensor(list(eos_token_ids), device=self.device, dtype=torch.int64)
         done = torch.zeros(B, dtype=torch.bool, device=self.device)
         out = []
+        if use_cache and B <= 32 and max_new_tokens > 0:
+            S0 = ids.shape[1]
+            cache = self.new_kv_cache(B, S0 + max_new_tokens)
+            emb, _ = self.embed_scatter(ids, counts, audio, n_a)
+            hid = self.lm_hidden(emb, B, S0, kv_cache=cache)
+            last = torch.arange(B, device=self.device, dtype=torch.int32) * S0 + (S0 - 1)
+            nxt = self.logits_rows(hid, last).float().argmax(-1)
+            pos_dev = torch.full((1,), S0, device=self.device, dtype=torch.int32)
+            logits = torch.empty(B, self.lm.vocab_pad, device=self.device, dtype=BF16)
+            flags = []                                                      # per step: have all sequences finished?
+            for t in range(max_new_tokens):
+                nxt = torch.where(done, torch.full_like(nxt, pad_token_id), nxt)
+                out.append(nxt)
+                if eos.numel():
+                    done = done | (nxt[:, None] == eos[None, :]).any(-1)
+                    flags.append(done.all())
+                    if (t + 1) % sync_every == 0 and bool(flags[-1]):       # host sync only every few tokens
+                        break
+                if t + 1 == max_new_tokens:
+                    break
+                fed, nxt = nxt.contiguous(), torch.empty_like(nxt)
+                self.decode_step(fed, pos_dev, S0 + t, cache, logits, nxt)
+            res = torch.stack(out, dim=1)
+            if flags:      # stop exactly where the token-by-token loop would have: the first step after which all are done
+                f = torch.stack(flags).nonzero()
+                if f.numel():
+                    res = res[:, : int(f[0]) + 1]
+            return res
         for _ in range(max_new_tokens):
             S = ids.shape[1]
             emb, _ = self.embed_scatter(ids, counts, audio, n_a)
