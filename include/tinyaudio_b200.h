@@ -244,9 +244,13 @@ int ta_lm_hidden_to_logits(const ta_lm_weights* w, const float* hidden_f32 /*[B*
  * ---------------------------------------------------------------------------------------------- */
 enum { TA_SKINNY_BF16 = 0,      /* out bf16 [M,N] = X W^T                                                   */
        TA_SKINNY_F32_RESID = 1, /* out f32  [M,N] = resid + bf16(X W^T)                                     */
-       TA_SKINNY_SWIGLU = 2 };  /* W rows interleaved [64 gate | 64 up]: out bf16 [M,N/2] = bf16(silu(g)) * u */
+       TA_SKINNY_SWIGLU = 2,    /* W rows interleaved [64 gate | 64 up]: out bf16 [M,N/2] = bf16(silu(g)) * u */
+       TA_SKINNY_PARTIAL = 3 }; /* out f32 [k_splits, M, ldo]: raw partial sums of a split-K product (small N)        */
 int ta_skinny_gemm_bf16(const void* X, long long ldx, const void* W, long long ldw, int M /*<= 32*/, int N, int K, int mode,
-                        void* out, long long ldo, const float* resid, void* stream);
+                        void* out, long long ldo, const float* resid, int k_splits /*1 unless TA_SKINNY_PARTIAL*/, void* stream);
+/* x_out = x_in + bf16(sum_s partial[s]) (partial may be NULL: x_out unused); y bf16 = RMSNorm(x_out) * w   (Qwen3RMSNorm) */
+int ta_decode_resid_rmsnorm(const float* x_in, const float* partial, int n_splits, int rows, float* x_out, const float* w,
+                            void* y_bf16, int D, float eps, long long ldy, void* stream);
 int ta_decode_attn(const void* q /*bf16 [B, Hq*128]*/, const void* k_cache /*bf16 [B, max_seq, Hkv*128]*/, const void* v_cache,
                    void* out /*bf16 [B, ld_out]*/, long long ld_out, const int* pos /*device: attends rows [0, *pos]*/, int B, int Hq,
                    int Hkv, int max_seq, float scale, void* stream);

@@ -452,18 +452,37 @@ def test_skinny_gemm_plain_and_resid(cuda, M, N, K):
     w = rnd(N, K, seed=N + K, scale=0.05)
     ref = x.float() @ w.float().t()
     out = torch.empty(M, N, device="cuda", dtype=BF16)
-    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), ld, L.ptr(w), K, M, N, K, L.SKINNY_BF16, L.ptr(out), N, None, L.stream_ptr()))
+    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), ld, L.ptr(w), K, M, N, K, L.SKINNY_BF16, L.ptr(out), N, None, 1, L.stream_ptr()))
     assert rel_err(out, ref) < 4e-3
     resid = rnd(M, N, seed=3, dtype=F32)
     o32 = torch.empty(M, N, device="cuda", dtype=F32)
-    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), ld, L.ptr(w), K, M, N, K, L.SKINNY_F32_RESID, L.ptr(o32), N, L.ptr(resid), L.stream_ptr()))
+    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), ld, L.ptr(w), K, M, N, K, L.SKINNY_F32_RESID, L.ptr(o32), N, L.ptr(resid), 1, L.stream_ptr()))
     assert rel_err(o32 - resid, ref.to(BF16).float()) < 4e-3
     # bit-reproducible (fixed-order split-K reduction) and equal to the tcgen05 GEMM up to the accumulation order
     out2 = torch.empty_like(out)
-    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), ld, L.ptr(w), K, M, N, K, L.SKINNY_BF16, L.ptr(out2), N, None, L.stream_ptr()))
+    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), ld, L.ptr(w), K, M, N, K, L.SKINNY_BF16, L.ptr(out2), N, None, 1, L.stream_ptr()))
     assert torch.equal(out, out2)
     big = L.gemm(x, w)
     assert rel_err(out, big) < 3e-3
+    # split-K partial sums + the fused reduce / bf16-round / residual / RMSNorm kernel that consumes them
+    if N == 1024:
+        for sp in (1, 2, 4):
+            if (K // 32) % sp:
+                continue
+            part = torch.empty(sp, M, N, device="cuda", dtype=F32)
+            L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), ld, L.ptr(w), K, M, N, K, L.SKINNY_PARTIAL, L.ptr(part), N, None, sp, L.stream_ptr()))
+            assert rel_err(part.sum(0), ref) < 1e-3
+            gw = rnd(N, seed=9, dtype=F32) + 1.0
+            x_out = torch.empty(M, N, device="cuda", dtype=F32)
+            y = torch.empty(M, N + 64, device="cuda", dtype=BF16)
+            L.check(lib.ta_decode_resid_rmsnorm(L.ptr(resid), L.ptr(part), sp, M, L.ptr(x_out), L.ptr(gw), L.ptr(y), N, 1e-6, N + 64, L.stream_ptr()))
+            xo_ref = resid + part.sum(0).to(BF16).float()
+            assert max_err(x_out, xo_ref) < 0.07 and rel_err(x_out, xo_ref) < 1e-3     # a bf16 ulp where the sum order moved a rounding
+            yr = xo_ref * torch.rsqrt(xo_ref.pow(2).mean(-1, keepdim=True) + 1e-6) * gw
+            assert rel_err(y[:, :N], yr) < 5e-3
+        y2 = torch.empty(M, N, device="cuda", dtype=BF16)
+        L.check(lib.ta_decode_resid_rmsnorm(L.ptr(resid), None, 0, M, None, L.ptr(gw), L.ptr(y2), N, 1e-6, N, L.stream_ptr()))
+        assert rel_err(y2, resid * torch.rsqrt(resid.pow(2).mean(-1, keepdim=True) + 1e-6) * gw) < 5e-3
 
 
 @pytest.mark.parametrize("M", [3, 32])
@@ -474,7 +493,7 @@ def test_skinny_gemm_swiglu(cuda, M):
     wg, wu = rnd(Fd, D, seed=2, scale=0.04), rnd(Fd, D, seed=3, scale=0.04)
     wgu = torch.cat([wg.view(Fd // 64, 1, 64, D), wu.view(Fd // 64, 1, 64, D)], 1).reshape(2 * Fd, D).contiguous()
     h = torch.empty(M, Fd, device="cuda", dtype=BF16)
-    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), D, L.ptr(wgu), D, M, 2 * Fd, D, L.SKINNY_SWIGLU, L.ptr(h), Fd, None, L.stream_ptr()))
+    L.check(lib.ta_skinny_gemm_bf16(L.ptr(x), D, L.ptr(wgu), D, M, 2 * Fd, D, L.SKINNY_SWIGLU, L.ptr(h), Fd, None, 1, L.stream_ptr()))
     g = (x.float() @ wg.float().t()).to(BF16).float()
     u = (x.float() @ wu.float().t()).to(BF16).float()
     href = F.silu(g).to(BF16).float() * u

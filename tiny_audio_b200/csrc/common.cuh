@@ -39,6 +39,31 @@ extern unsigned long long g_ta_launches;   // kernels launched by this library (
 
 typedef __nv_bfloat16 bf16;
 
+// ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the stream
+// is still running; it must call pdl_wait() before touching anything the predecessor writes (or reads, if it overwrites
+// it).  Everything before pdl_wait() -- index setup, prefetch of FROZEN weights -- overlaps the predecessor's tail.
+// ----------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 __host__ __device__ inline int64_t ceil_div_i64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -451,6 +451,7 @@ namespace {
 struct DecBufs {
     float *x0, *x1, *x2;   // [B, D] fp32 residual stream (layer in / mid / out)
     bf16 *xn, *qkv, *q, *att, *h;
+    float* part;           // [4, B, D] split-K partial sums of o_proj / down_proj
 };
 long long dec_carve(const ta_lm_weights* w, int B, void* ws, long long cap, DecBufs* b) {
     const long long D = w->dim, F = w->ffn, P = w->lora_pad;
@@ -464,6 +465,7 @@ long long dec_carve(const ta_lm_weights* w, int B, void* ws, long long cap, DecB
     b->q = c.take<bf16>(B * QD);
     b->att = c.take<bf16>(B * (QD + P));
     b->h = c.take<bf16>(B * (F + P));
+    b->part = c.take<float>(4 * B * D);
     return c.off;
 }
 }  // namespace
@@ -497,28 +499,33 @@ TA_API int ta_lm_decode_step(const ta_lm_weights* w, const long long* ids, int* 
     float* x_in = b.x0;
     float* x_mid = b.x1;
     float* x_out = b.x2;
+    const int sp_o = k_skinny_splits(D, QD + P), sp_d = k_skinny_splits(D, F + P);
+    const void* const* L0 = w->layers;
+    RUN(k_decode_resid_rmsnorm(x_in, nullptr, 0, B, nullptr, (const float*)L0[TA_LM_LN1_W], b.xn, D, w->eps, ldX, st));
     for (int l = 0; l < w->n_layers; ++l) {
         const void* const* Lw = w->layers + (long long)l * TA_LM_PTRS_PER_LAYER;
         bf16* kc = reinterpret_cast<bf16*>(k_cache) + l * per_layer;
         bf16* vc = reinterpret_cast<bf16*>(v_cache) + l * per_layer;
-        RUN(k_rmsnorm_f32(x_in, (const float*)Lw[TA_LM_LN1_W], b.xn, nullptr, B, D, w->eps, st, ldX));
         if (P) RUN(k_skinny_gemm(b.xn, ldX, (const bf16*)Lw[TA_LM_LORA_A_QKV], D, B, P, D, TA_SKINNY_BF16, b.xn + D, ldX, nullptr, st));
         RUN(k_skinny_gemm(b.xn, ldX, (const bf16*)Lw[TA_LM_WQKV], ldX, B, QKV, D + P, TA_SKINNY_BF16, b.qkv, QKV, nullptr, st));
-        RUN(k_decode_qknorm_rope_cache(b.qkv, b.q, kc, vc, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W], w->rope_cos,
-                                       w->rope_sin, pos, B, Hq, Hkv, cache_max_seq, w->eps, st));
-        RUN(k_decode_attn(b.q, kc, vc, b.att, ldAtt, pos, B, Hq, Hkv, cache_max_seq, scale, st));
+        RUN(k_decode_attn(b.qkv, nullptr, kc, vc, b.att, ldAtt, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W], w->rope_cos,
+                          w->rope_sin, pos, B, Hq, Hkv, cache_max_seq, w->eps, scale, st));
         if (P) RUN(k_skinny_gemm(b.att, ldAtt, (const bf16*)Lw[TA_LM_LORA_A_O], QD, B, P, QD, TA_SKINNY_BF16, b.att + QD, ldAtt, nullptr, st));
-        RUN(k_skinny_gemm(b.att, ldAtt, (const bf16*)Lw[TA_LM_WO], ldAtt, B, D, QD + P, TA_SKINNY_F32_RESID, x_mid, D, x_in, st));
-        RUN(k_rmsnorm_f32(x_mid, (const float*)Lw[TA_LM_LN2_W], b.xn, nullptr, B, D, w->eps, st, ldX));
+        // o_proj / down_proj have only dim / 16 = 64 row tiles: split K so that the whole GPU streams; the partial sums are
+        // reduced (fixed order), rounded to bf16 and added to the residual by the RMSNorm kernel that follows anyway
+        RUN(k_skinny_gemm(b.att, ldAtt, (const bf16*)Lw[TA_LM_WO], ldAtt, B, D, QD + P, TA_SKINNY_PARTIAL, b.part, D, nullptr, st, sp_o));
+        RUN(k_decode_resid_rmsnorm(x_in, b.part, sp_o, B, x_mid, (const float*)Lw[TA_LM_LN2_W], b.xn, D, w->eps, ldX, st));
         if (P) RUN(k_skinny_gemm(b.xn, ldX, (const bf16*)Lw[TA_LM_LORA_A_GU], D, B, P, D, TA_SKINNY_BF16, b.xn + D, ldX, nullptr, st));
         RUN(k_skinny_gemm(b.xn, ldX, (const bf16*)Lw[TA_LM_WGU], ldX, B, 2 * F, D + P, TA_SKINNY_SWIGLU, b.h, ldH, nullptr, st));
         if (P) RUN(k_skinny_gemm(b.h, ldH, (const bf16*)Lw[TA_LM_LORA_A_D], F, B, P, F, TA_SKINNY_BF16, b.h + F, ldH, nullptr, st));
-        RUN(k_skinny_gemm(b.h, ldH, (const bf16*)Lw[TA_LM_WD], ldH, B, D, F + P, TA_SKINNY_F32_RESID, x_out, D, x_mid, st));
+        RUN(k_skinny_gemm(b.h, ldH, (const bf16*)Lw[TA_LM_WD], ldH, B, D, F + P, TA_SKINNY_PARTIAL, b.part, D, nullptr, st, sp_d));
+        const bool last = (l + 1 == w->n_layers);
+        const float* next_norm = last ? w->final_norm_w : (const float*)(Lw + TA_LM_PTRS_PER_LAYER)[TA_LM_LN1_W];
+        RUN(k_decode_resid_rmsnorm(x_mid, b.part, sp_d, B, x_out, next_norm, b.xn, D, w->eps, last ? (long long)D : ldX, st));
         float* t = x_in;
         x_in = x_out;
         x_out = t;
     }
-    RUN(k_rmsnorm_f32(x_in, w->final_norm_w, b.xn, nullptr, B, D, w->eps, st, D));
     RUN(k_skinny_gemm(b.xn, D, (const bf16*)w->embed_bf16, D, B, (int)w->vocab_pad, D, TA_SKINNY_BF16, logits, w->vocab_pad, nullptr, st));
     RUN(k_argmax_rows((const bf16*)logits, w->vocab_pad, B, (int)w->vocab, next_ids, pos, st));
     return 0;

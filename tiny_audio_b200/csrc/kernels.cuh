@@ -33,14 +33,15 @@ int k_sumsq(const float* g, long long n, float* out, cudaStream_t st);
 
 // KV-cache decode path (decode.cu)
 int k_skinny_gemm(const bf16* X, long long ldx, const bf16* W, long long ldw, int M, int N, int K, int mode, void* out, long long ldo,
-                  const float* resid, cudaStream_t st);
-int k_decode_qknorm_rope_cache(const bf16* qkv, bf16* q_out, bf16* k_cache, bf16* v_cache, const float* qw, const float* kw,
-                               const float* cosT, const float* sinT, const int* pos, int B, int Hq, int Hkv, int max_seq, float eps,
-                               cudaStream_t st);
+                  const float* resid, cudaStream_t st, int k_splits = 1);
+int k_skinny_splits(int N, int K);
 int k_kv_cache_store(const bf16* k_src, long long k_ld, const bf16* v_src, long long v_ld, bf16* k_cache, bf16* v_cache, int B, int S,
                      int KD, int max_seq, cudaStream_t st);
-int k_decode_attn(const bf16* q, const bf16* k_cache, const bf16* v_cache, bf16* out, long long ld_out, const int* pos, int B, int Hq,
-                  int Hkv, int max_seq, float scale, cudaStream_t st);
+int k_decode_attn(const bf16* qkv, const bf16* q_ready, bf16* k_cache, bf16* v_cache, bf16* out, long long ld_out, const float* qw,
+                  const float* kw, const float* cosT, const float* sinT, const int* pos, int B, int Hq, int Hkv, int max_seq, float eps,
+                  float scale, cudaStream_t st);
+int k_decode_resid_rmsnorm(const float* x_in, const float* partial, int n_splits, int rows, float* x_out, const float* w, bf16* y, int D,
+                           float eps, long long ldy, cudaStream_t st);
 int k_embed_rows(const long long* ids, const float* table, float* out, int B, int D, long long vocab, cudaStream_t st);
 int k_argmax_rows(const bf16* logits, long long ld, int rows, int V, long long* next_ids, int* pos_inc, cudaStream_t st);
 

@@ -455,6 +455,31 @@ class HotPath:
         shape = (d.lm_layers, B, max_seq, d.lm_kv_heads * d.lm_head_dim)
         return (torch.empty(shape, device=self.device, dtype=BF16), torch.empty(shape, device=self.device, dtype=BF16), max_seq)
 
+    def _decode_graph(self, fed, nxt_buf, pos_dev, cache, logits, pos_host: int):
+        """CUDA graph of one decode step over the given (persistent, workspace-owned) buffers; cached per pointer set."""
+        key = (int(fed.numel()), cache[2], fed.data_ptr(), nxt_buf.data_ptr(), pos_dev.data_ptr(), cache[0].data_ptr(),
+               cache[1].data_ptr(), logits.data_ptr())
+        graphs = self.__dict__.setdefault("_decode_graphs", {})
+        g = graphs.get(key)
+        if g is None:
+            n = C.c_longlong()
+            L.check(self.lib.ta_lm_decode_workspace_bytes(C.byref(self.lm.c), int(fed.numel()), C.byref(n)))
+            self.ws.get("lm_decode", n.value)                  # allocate outside the capture
+            keep = pos_dev.clone()
+            self.decode_step(fed, pos_dev, pos_host, cache, logits, nxt_buf)      # eager warm-up (module load) before the capture;
+            pos_dev.copy_(keep)                                                   # its cache row is rewritten by the real step
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    self.decode_step(fed, pos_dev, pos_host, cache, logits, nxt_buf)
+            torch.cuda.current_stream().wait_stream(side)
+            pos_dev.copy_(keep)
+            graphs.clear()                                     # one live graph per HotPath is enough
+            graphs[key] = g
+        return g
+
     def decode_step(self, ids: torch.Tensor, pos_dev: torch.Tensor, pos_host: int, kv_cache, logits: torch.Tensor,
                     next_ids: torch.Tensor):
         """One KV-cache decode step (ta_lm_decode_step): feeds ids [B] at position *pos_dev, writes the bf16 logits
@@ -493,12 +518,14 @@ class HotPath:
     @torch.no_grad()
     def greedy_generate(self, *, input_ids: torch.Tensor, proj_params, waveform=None, input_features=None,
                         audio_token_counts=None, max_new_tokens: int = 16, eos_token_ids=(), pad_token_id: int = 0,
-                        use_cache: bool = True, sync_every: int = 8):
+                        use_cache: bool = True, sync_every: int = 8, use_graph: bool = False):
         """Greedy decoding (num_beams=1, do_sample=False: the reference's generation defaults, asr_config.py:103-111).
         use_cache=True (default, like HF generate): one prefill pass that also fills the KV cache, then one
         ta_lm_decode_step per new token (HBM-bound skinny kernels, csrc/decode.cu).  use_cache=False re-runs the decoder
-        over the whole sequence for every new token (kept as the A/B reference of the cache path).  All prompts in the
-        batch have the same length (equal-length clips); batches larger than 32 sequences fall back to use_cache=False."""
+        over the whole sequence for every new token (kept as the A/B reference of the cache path).  use_graph: the decode
+        step (~200 PDL launches, position counter on the device) is captured once per buffer set in a CUDA graph and replayed
+        (-5 % per token; off by default because the capture costs more than it saves on short transcripts).
+        All prompts in the batch have the same length (equal-length clips); batches larger than 32 sequences fall back to use_cache=False."""
         d = self.dims
         ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
         B = ids.shape[0]
@@ -512,13 +539,21 @@ class HotPath:
         out = []
         if use_cache and B <= 32 and max_new_tokens > 0:
             S0 = ids.shape[1]
-            cache = self.new_kv_cache(B, S0 + max_new_tokens)
+            if S0 + max_new_tokens > d.lm_max_pos:
+                raise L.TinyAudioB200Error(f"prompt {S0} + {max_new_tokens} new tokens exceed the rotary table ({d.lm_max_pos})")
+            max_seq = _round_up(S0 + max_new_tokens, 64)
+            kv_shape = (d.lm_layers, B, max_seq, d.lm_kv_heads * d.lm_head_dim)
+            cache = (self.ws.typed("kv_cache_k", kv_shape, BF16), self.ws.typed("kv_cache_v", kv_shape, BF16), max_seq)
             emb, _ = self.embed_scatter(ids, counts, audio, n_a)
             hid = self.lm_hidden(emb, B, S0, kv_cache=cache)
             last = torch.arange(B, device=self.device, dtype=torch.int32) * S0 + (S0 - 1)
             nxt = self.logits_rows(hid, last).float().argmax(-1)
-            pos_dev = torch.full((1,), S0, device=self.device, dtype=torch.int32)
-            logits = torch.empty(B, self.lm.vocab_pad, device=self.device, dtype=BF16)
+            pos_dev = self.ws.typed("decode_pos", (1,), torch.int32)
+            pos_dev.fill_(S0)
+            logits = self.ws.typed("decode_logits", (B, self.lm.vocab_pad), BF16)
+            fed = self.ws.typed("decode_ids_in", (B,), torch.int64)
+            nxt_buf = self.ws.typed("decode_ids_out", (B,), torch.int64)
+            step = self._decode_graph(fed, nxt_buf, pos_dev, cache, logits, S0) if (use_graph and max_new_tokens >= 8) else None
             flags = []                                                      # per step: have all sequences finished?
             for t in range(max_new_tokens):
                 nxt = torch.where(done, torch.full_like(nxt, pad_token_id), nxt)
@@ -530,8 +565,12 @@ class HotPath:
                         break
                 if t + 1 == max_new_tokens:
                     break
-                fed, nxt = nxt.contiguous(), torch.empty_like(nxt)
-                self.decode_step(fed, pos_dev, S0 + t, cache, logits, nxt)
+                fed.copy_(nxt)
+                if step is not None:
+                    step.replay()
+                else:
+                    self.decode_step(fed, pos_dev, S0 + t, cache, logits, nxt_buf)
+                nxt = nxt_buf.clone()
             res = torch.stack(out, dim=1)
             if flags:      # stop exactly where the token-by-token loop would have: the first step after which all are done
                 f = torch.stack(flags).nonzero()

@@ -18,7 +18,7 @@ c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 P = c_void_p
 
 # epilogue modes (enum in the header)
-SKINNY_BF16, SKINNY_F32_RESID, SKINNY_SWIGLU = range(3)
+SKINNY_BF16, SKINNY_F32_RESID, SKINNY_SWIGLU, SKINNY_PARTIAL = range(4)
 EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESID, EPI_F32_RESID, EPI_F32, EPI_SWIGLU, EPI_SWIGLU_BWD, EPI_BF16_ROPE = range(8)
 ENC_PTRS_PER_LAYER = 12
 LM_PTRS_PER_LAYER = 20
@@ -100,7 +100,8 @@ _SIGS = {
     "ta_lm_workspace_bytes": ([C.POINTER(LmWeights), c_int, c_int, c_int, c_int, C.POINTER(c_ll)], c_int),
     "ta_lm_forward_backward": ([C.POINTER(LmWeights), C.POINTER(LmStepArgs), P], c_int),
     "ta_lm_hidden_to_logits": ([C.POINTER(LmWeights), P, P, c_int, P, P, P], c_int),
-    "ta_skinny_gemm_bf16": ([P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, P, c_ll, P, P], c_int),
+    "ta_skinny_gemm_bf16": ([P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, P, c_ll, P, c_int, P], c_int),
+    "ta_decode_resid_rmsnorm": ([P, P, c_int, c_int, P, P, P, c_int, c_float, c_ll, P], c_int),
     "ta_decode_attn": ([P, P, P, P, c_ll, P, c_int, c_int, c_int, c_int, c_float, P], c_int),
     "ta_argmax_rows": ([P, c_ll, c_int, c_int, P, P], c_int),
     "ta_lm_decode_workspace_bytes": ([C.POINTER(LmWeights), c_int, C.POINTER(c_ll)], c_int),

@@ -1,4 +1,5 @@
 """Greedy generate at full model size: per-token latency of the KV-cache decode path vs the cache-free path."""
+import os
 import sys
 import time
 import torch
@@ -12,7 +13,7 @@ model = build_offline_model(dims, device=torch.device("cuda"), seed=1234)
 hot = model._hot_path()
 params = {k: p.detach().float().contiguous() for k, p in model.projector.state_dict().items()}
 clip = float(sys.argv[1]) if len(sys.argv) > 1 else 30.0
-for B in (1, 8, 32):
+for B in ((32,) if os.environ.get('TA_PROFILE_STEP') == '1' else (1, 8, 32)):
     host = synthetic_batch(dims, B, clip, seed=5, response_len=4)
     n_prompt = int((host["labels"][0] != -100).nonzero().min())
     prompt = host["input_ids"][:, :n_prompt].cuda()
@@ -36,6 +37,12 @@ for B in (1, 8, 32):
     for _ in range(3):
         hot.decode_step(ids, pos, S0, cache, logits, nxt)
     torch.cuda.synchronize()
+    if os.environ.get('TA_PROFILE_STEP') == '1':           # ncu --profile-from-start off: one decode step
+        pos.fill_(S0 + 40)
+        torch.cuda.profiler.start()
+        hot.decode_step(ids, pos, S0 + 40, cache, logits, nxt)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     pos.fill_(S0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 50
