@@ -193,6 +193,10 @@ enum { TA_LM_LN1_W = 0, TA_LM_WQKV, TA_LM_WQKV_T, TA_LM_QNORM_W, TA_LM_KNORM_W, 
 /* per-layer LoRA gradient outputs (fp32, caller-owned): dA [lora_pad, K_in] and dB' [N_out, lora_pad] = d loss / d (alpha/r * B) */
 enum { TA_LM_LORA_DA_QKV = 0, TA_LM_LORA_DB_QKV, TA_LM_LORA_DA_O, TA_LM_LORA_DB_O, TA_LM_LORA_DA_GU, TA_LM_LORA_DB_GU,
        TA_LM_LORA_DA_D, TA_LM_LORA_DB_D, TA_LM_LORA_GRADS_PER_LAYER };
+/* unfrozen LM (f3; configs/experiments/embedded.yaml:19-33 `freeze_language_model: false`): per-layer weight-gradient outputs, fp32,
+   caller-owned.  W* are overwritten, in the layout of the packed operand (WQKV rows = [q | k | v], WGU rows interleaved in 64-blocks);
+   the norm gradients are ACCUMULATED (atomics): the caller zeroes them before the step. */
+enum { TA_LM_G_WQKV = 0, TA_LM_G_WO, TA_LM_G_WGU, TA_LM_G_WD, TA_LM_G_LN1, TA_LM_G_LN2, TA_LM_G_QNORM, TA_LM_G_KNORM, TA_LM_GRADS_PER_LAYER };
 typedef struct ta_lm_weights {
     int n_layers, dim, ffn, n_q_heads, n_kv_heads, head_dim, max_pos;
     long long vocab, vocab_pad;
@@ -226,8 +230,25 @@ typedef struct ta_lm_step_args {
     void* k_cache;                /* optional (prefill of generate): bf16 [n_layers, B, cache_max_seq, Hkv*hd]; rows [0, S) of every */
     void* v_cache;                /*   layer receive the prompt's roped keys / values (use_cache=True in HF generate)             */
     int cache_max_seq;
+    float* const* lm_grads;       /* unfrozen LM + backward: HOST array n_layers * TA_LM_GRADS_PER_LAYER device pointers (else NULL) */
+    float* d_embed;               /*   fp32 [vocab_pad, dim]: tied embed_tokens / lm_head gradient (overwritten)                    */
+    float* d_final_norm;          /*   fp32 [dim], accumulated                                                                       */
+    const long long* input_ids;   /*   [B*S]: which rows of the table the text positions read                                       */
+    long long audio_token_id;
 } ta_lm_step_args;
+/* with_backward: 0 forward only; 1 backward to inputs_embeds (frozen LM, LoRA); 2 additionally the weight gradients (lm_grads) */
 int ta_lm_workspace_bytes(const ta_lm_weights* w, int B, int S, int n_labelled, int with_backward, long long* bytes);
+/* building blocks of the unfrozen recipe (exported for unit parity tests and the host-side operand refresh) */
+int ta_rmsnorm_dw(const void* dy_bf16, const float* x, const int* row_index, long long rows, int D, float eps, float* dw /*accumulated*/,
+                  void* stream);
+int ta_qknorm_dw(const void* qkv, const float* dq, const void* dk, const float* cos_t, const float* sin_t, long long M, int S, int Hq,
+                 int Hkv, float eps, float* d_q_norm_w /*[128] accumulated*/, float* d_k_norm_w, void* stream);
+int ta_embed_grad_scatter(const long long* input_ids, const float* d_inputs_embeds, float* d_table /*accumulated*/, long long n_tok,
+                          int D, long long vocab, long long audio_token_id, void* stream);
+/* fp32 master [R, C] -> bf16 operand rows (r / blk) * blk_stride + r % blk + row_off of dst (ld) and of the transposed copy dstT
+   [C, ldT] (optional): refreshes the packed Qwen3 operands after an optimiser step */
+int ta_pack_weight(const float* src, int R, int C, void* dst, long long ld, void* dstT, long long ldT, int blk, int blk_stride,
+                   int row_off, void* stream);
 int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args* a, void* stream);
 /* full-vocabulary logits for given rows (eval / generate):  logits bf16 [n_rows, vocab_pad] */
 int ta_lm_hidden_to_logits(const ta_lm_weights* w, const float* hidden_f32 /*[B*S, dim] pre-final-norm*/, const int* rows,

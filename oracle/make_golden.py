@@ -74,7 +74,7 @@ class StubTok:
         return self.cfg.vocab
 
 
-def build_reference_model(cfg: po.PathConfig, W, mods, projector="mlp"):
+def build_reference_model(cfg: po.PathConfig, W, mods, projector="mlp", freeze_lm=True):
     from transformers import GlmAsrEncoderConfig, Qwen3Config, Qwen3ForCausalLM, WhisperFeatureExtractor
     from transformers.models.glmasr.modeling_glmasr import GlmAsrEncoder
 
@@ -100,8 +100,9 @@ def build_reference_model(cfg: po.PathConfig, W, mods, projector="mlp"):
         m = Qwen3ForCausalLM._from_config(txt_cfg, attn_implementation=config.attn_implementation).to(dtype)
         m.load_state_dict(W["lm"], strict=True)
         m.tie_weights()
-        m.requires_grad_(False)
-        m.train(False)
+        if getattr(config, "freeze_language_model", True):      # the reference's own rule (asr_modeling.py:251-253)
+            m.requires_grad_(False)
+            m.train(False)
         return m
 
     tok = StubTok(cfg)
@@ -116,7 +117,7 @@ def build_reference_model(cfg: po.PathConfig, W, mods, projector="mlp"):
     ASRModel._create_feature_extractor = lambda self, config: WhisperFeatureExtractor(feature_size=cfg.n_mels)
     acfg = ASRConfig(audio_config=enc_cfg, text_config=txt_cfg, model_dtype="float32", attn_implementation="sdpa",
                      projector_type=projector, projector_pool_stride=cfg.proj_k, projector_hidden_dim=cfg.proj_hidden,
-                     audio_token_dropout=0.0)
+                     audio_token_dropout=0.0, freeze_language_model=freeze_lm)
     model = ASRModel(acfg)
     model.projector.load_state_dict(W["projector"], strict=True)
     return model
@@ -138,6 +139,8 @@ CASES = {
     "full_b1_4s":    ("full", 1, 4.0, None, 32, 21),
     # config 4: QFormer projector (reference in eval mode: its dropout 0.1 has no bit-parity definition)
     "qformer_b2_2s": (dict(enc_layers=1, lm_layers=1, _projector="qformer"), 2, 2.0, None, 8, 15),
+    # full decoder fine-tuning (configs/experiments/embedded.yaml:19-33, freeze_language_model: false): LM weight gradients
+    "unfrozen_b2_2s": (dict(enc_layers=1, lm_layers=2, _train_lm=True), 2, 2.0, None, 8, 16),
 }
 
 
@@ -147,12 +150,14 @@ def case_config(spec):
         return po.FULL, "mlp"
     spec = dict(spec)
     kind = spec.pop("_projector", "mlp")
+    spec.pop("_train_lm", None)
     return po.small_config(**spec), kind
 
 
 def run_case(name, mods, outdir):
     spec, B, clip_s, pad_s, R, seed = CASES[name]
     cfg, kind = case_config(spec)
+    train_lm = isinstance(spec, dict) and spec.get("_train_lm", False)
     torch.manual_seed(0)
     t0 = time.time()
     W = po.init_weights(cfg, seed=seed)
@@ -168,7 +173,7 @@ def run_case(name, mods, outdir):
             labels[b, -cut:] = -100
             am[b, -cut:] = 0
         batch.update(input_ids=ids, labels=labels, attention_mask=am)
-    model = build_reference_model(cfg, W, mods, kind)
+    model = build_reference_model(cfg, W, mods, kind, freeze_lm=not train_lm)
     model.train()
     if kind == "qformer":
         model.projector.eval()
@@ -192,6 +197,8 @@ def run_case(name, mods, outdir):
     loss = out.loss
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in model.projector.named_parameters()}
+    lm_grads = {k: p.grad.detach().clone() for k, p in model.language_model.named_parameters() if p.grad is not None}
+    assert bool(lm_grads) == bool(train_lm)
     gnorm = torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
     opt.step()
     new_params = {k: p.detach().clone() for k, p in model.projector.named_parameters()}
@@ -205,7 +212,10 @@ def run_case(name, mods, outdir):
     # ---- oracle vs reference (sanity; the test suite re-checks from the fixture) ----
     ob = dict(batch)
     ob["input_features"] = mel_ref
-    res = po.train_step(W, ob, cfg, lr=1e-3, max_grad_norm=1.0, num_items_in_batch=n_items)
+    res = po.train_step(W, ob, cfg, lr=1e-3, max_grad_norm=1.0, num_items_in_batch=n_items, train_lm=train_lm)
+    if train_lm:
+        worst = max(float((res["lm_grads"][k] - g).norm() / (g.norm() + 1e-12)) for k, g in lm_grads.items())
+        print(f"[{name}] LM weight gradients: {len(lm_grads)} tensors, worst oracle-vs-reference rel. error {worst:.2e}")
     mel_or = po.log_mel(batch["waveform"], cfg)
     print(f"[{name}] ref loss {float(loss):.6f} oracle {float(res['loss']):.6f}  "
           f"mel maxdiff {float((mel_or - mel_ref).abs().max()):.2e}  "
@@ -236,6 +246,9 @@ def run_case(name, mods, outdir):
         fx["grad_sub." + k] = sub(grads[k], 4096)
         fx["grad_l2." + k] = np.array(float(grads[k].norm()))
         fx["new_param_sub." + k] = sub(new_params[k], 4096)
+    for k, g in lm_grads.items():          # HF parameter names (the tied table appears once, as model.embed_tokens.weight)
+        fx["lm_grad_sub." + k] = sub(g, 2048)
+        fx["lm_grad_l2." + k] = np.array(float(g.norm()))
     np.savez_compressed(os.path.join(outdir, name + ".npz"), **fx)
     del model
 

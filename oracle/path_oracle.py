@@ -569,10 +569,17 @@ def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float,
 
 
 def train_step(W, batch, cfg: PathConfig = FULL, lr=1e-3, max_grad_norm=1.0, weight_decay=0.0, state=None,
-               num_items_in_batch=None):
-    """One optimiser step on the projector (configs 1-3).  Returns loss, grads, new params, state."""
+               num_items_in_batch=None, train_lm: bool = False):
+    """One optimiser step on the projector (configs 1-3).  Returns loss, grads, new params, state.
+    train_lm (configs/experiments/embedded.yaml:19-33, `freeze_language_model: false`; asr_modeling.py:251-254): the whole
+    decoder is trainable too -- its gradients are returned as `lm_grads` under HF parameter names (the tied
+    embed_tokens / lm_head table receives both contributions); the optimiser update below still covers the projector only."""
     proj = {k: v.detach().clone().requires_grad_(True) for k, v in W["projector"].items()}
-    W2 = {"encoder": W["encoder"], "lm": W["lm"], "projector": proj}
+    lm_w = W["lm"]
+    if train_lm:
+        lm_w = {k: v.detach().clone().requires_grad_(True) for k, v in W["lm"].items() if k != "lm_head.weight"}
+        lm_w["lm_head.weight"] = lm_w["model.embed_tokens.weight"]          # tie_word_embeddings
+    W2 = {"encoder": W["encoder"], "lm": lm_w, "projector": proj}
     lora = None
     if W.get("lora") is not None:
         lora = {"scaling": W["lora"]["scaling"],
@@ -597,8 +604,9 @@ def train_step(W, batch, cfg: PathConfig = FULL, lr=1e-3, max_grad_norm=1.0, wei
         new_p[k], state["m"][k], state["v"][k] = adamw_step(
             proj[k].detach(), grads[k] * coef, state["m"][k], state["v"][k], state["step"], lr,
             weight_decay=wd)
+    lm_grads = {k: v.grad.detach() for k, v in lm_w.items() if k != "lm_head.weight"} if train_lm else None
     return {"loss": loss.detach(), "grads": grads, "grad_norm": gnorm, "clip_coef": coef,
-            "params": new_p, "state": state, "lora_grads": lora_grads}
+            "params": new_p, "state": state, "lora_grads": lora_grads, "lm_grads": lm_grads}
 
 
 # --------------------------------------------------------------------------------------

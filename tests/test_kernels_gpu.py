@@ -525,3 +525,65 @@ def test_decode_attention_and_argmax(cuda, B, n_keys, Hq, Hkv):
     ids = torch.empty(B, device="cuda", dtype=torch.int64)
     L.check(lib.ta_argmax_rows(L.ptr(logits), ld, B, V, L.ptr(ids), L.stream_ptr()))
     assert torch.equal(ids, logits[:, :V].float().argmax(-1)) and int(ids[0]) == 17
+
+
+# ------------------------------------------------------------------ unfrozen-LM building blocks (csrc/lm_wgrad.cu)
+def test_norm_weight_grads_embed_scatter_and_pack(cuda):
+    lib = L.load()
+    M, D = 333, 1024
+    x = rnd(M, D, seed=1, dtype=F32)
+    dy = rnd(M, D, seed=2)
+    dw = torch.zeros(D, device="cuda", dtype=F32)
+    L.check(lib.ta_rmsnorm_dw(L.ptr(dy), L.ptr(x), None, M, D, 1e-6, L.ptr(dw), L.stream_ptr()))
+    ref = (dy.float() * x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6)).sum(0)
+    assert rel_err(dw, ref) < 1e-4
+    rows = torch.tensor([5, 0, 17, 200], device="cuda", dtype=torch.int32)
+    dw2 = torch.zeros(D, device="cuda", dtype=F32)
+    L.check(lib.ta_rmsnorm_dw(L.ptr(dy), L.ptr(x), L.ptr(rows), 4, D, 1e-6, L.ptr(dw2), L.stream_ptr()))
+    xs = x[rows.long()]
+    assert rel_err(dw2, (dy[:4].float() * xs * torch.rsqrt(xs.pow(2).mean(-1, keepdim=True) + 1e-6)).sum(0)) < 1e-4
+    # q / k norm gains through RoPE (autograd on the forward statement of lm_qknorm_rope_fwd_kernel)
+    B, S, Hq, Hkv, hd = 2, 37, 4, 2, 128
+    Mq = B * S
+    qkv = rnd(Mq, (Hq + 2 * Hkv) * hd, seed=3)
+    dq = rnd(Mq, Hq * hd, seed=4, dtype=F32)
+    dk = rnd(Mq, Hkv * hd, seed=5)
+    inv = 1.0 / (1e6 ** (torch.arange(0, hd, 2).float() / hd))
+    fr = torch.arange(S).float()[:, None] * inv[None]
+    cos, sin = fr.cos().cuda().contiguous(), fr.sin().cuda().contiguous()
+    qw = (1.0 + 0.1 * torch.randn(hd)).cuda().requires_grad_(True)
+    kw_ = (1.0 + 0.1 * torch.randn(hd)).cuda().requires_grad_(True)
+
+    def fwd(xh, w):      # xh [M, H, hd]
+        n = (xh * torch.rsqrt(xh.pow(2).mean(-1, keepdim=True) + 1e-6)).to(BF16).float() * w
+        c = torch.cat([cos, cos], -1).repeat(B, 1)[:, None]
+        s_ = torch.cat([sin, sin], -1).repeat(B, 1)[:, None]
+        rot = torch.cat([-n[..., hd // 2:], n[..., : hd // 2]], -1)
+        return n * c + rot * s_
+    qh = qkv[:, : Hq * hd].float().view(Mq, Hq, hd)
+    kh = qkv[:, Hq * hd: (Hq + Hkv) * hd].float().view(Mq, Hkv, hd)
+    ((fwd(qh, qw) * dq.view(Mq, Hq, hd)).sum() + (fwd(kh, kw_) * dk.float().view(Mq, Hkv, hd)).sum()).backward()
+    dqw = torch.zeros(hd, device="cuda", dtype=F32)
+    dkw = torch.zeros(hd, device="cuda", dtype=F32)
+    L.check(lib.ta_qknorm_dw(L.ptr(qkv), L.ptr(dq), L.ptr(dk), L.ptr(cos), L.ptr(sin), Mq, S, Hq, Hkv, 1e-6, L.ptr(dqw), L.ptr(dkw),
+                             L.stream_ptr()))
+    assert rel_err(dqw, qw.grad) < 1e-4 and rel_err(dkw, kw_.grad) < 1e-4
+    # embed_tokens scatter-add: text rows only, repeated ids accumulate
+    V, Dd, audio_id = 50, 64, 49
+    ids = torch.tensor([3, 49, 3, 7, 49, 0, 7, 7], device="cuda", dtype=torch.int64)
+    de = rnd(8, Dd, seed=6, dtype=F32)
+    tab = torch.zeros(V, Dd, device="cuda", dtype=F32)
+    L.check(lib.ta_embed_grad_scatter(L.ptr(ids), L.ptr(de), L.ptr(tab), 8, Dd, V, audio_id, L.stream_ptr()))
+    ref_tab = torch.zeros_like(tab)
+    keep = ids != audio_id
+    ref_tab.index_add_(0, ids[keep], de[keep])
+    assert max_err(tab, ref_tab) < 1e-6
+    # fp32 master -> packed bf16 (+ transposed copy), with the gate/up 64-row interleave and a row offset
+    Fd, Dk = 256, 96
+    wg, wu = rnd(Fd, Dk, seed=7, dtype=F32), rnd(Fd, Dk, seed=8, dtype=F32)
+    dst = torch.zeros(2 * Fd, Dk + 32, device="cuda", dtype=BF16)
+    dstT = torch.zeros(Dk, 2 * Fd + 16, device="cuda", dtype=BF16)
+    for j, src in enumerate((wg, wu)):
+        L.check(lib.ta_pack_weight(L.ptr(src), Fd, Dk, L.ptr(dst), Dk + 32, L.ptr(dstT), 2 * Fd + 16, 64, 128, 64 * j, L.stream_ptr()))
+    want = torch.cat([wg.view(Fd // 64, 1, 64, Dk), wu.view(Fd // 64, 1, 64, Dk)], 1).reshape(2 * Fd, Dk).to(BF16)
+    assert torch.equal(dst[:, :Dk], want) and torch.equal(dstT[:, : 2 * Fd], want.t()) and float(dst[:, Dk:].abs().max()) == 0.0

@@ -69,6 +69,29 @@ def test_oracle_matches_reference_fixture(name):
     assert abs(float(res["grad_norm"]) - float(fx["grad_norm"])) < 1e-3 * float(fx["grad_norm"])
 
 
+def test_oracle_unfrozen_lm_gradients_match_reference():
+    """freeze_language_model: false (configs/experiments/embedded.yaml:19-33): every Qwen3 weight gradient of the oracle against
+    the unmodified reference's autograd (tests/golden/unfrozen_b2_2s.npz)."""
+    torch.set_num_threads(os.cpu_count())
+    cfg, fx, W, batch = load_case("unfrozen_b2_2s")
+    n_items = int(fx["num_items"])
+    res = po.train_step(W, batch, cfg, lr=1e-3, max_grad_norm=1.0, num_items_in_batch=n_items, train_lm=True)
+    assert abs(float(res["loss"]) - float(fx["loss"])) < 2e-5
+    keys = [k[len("lm_grad_sub."):] for k in fx.files if k.startswith("lm_grad_sub.")]
+    assert len(keys) == 2 + 11 * cfg.lm_layers and set(keys) == set(res["lm_grads"])
+    for k in keys:
+        g, ref = res["lm_grads"][k], fx["lm_grad_sub." + k]
+        assert np.abs(sub(g, 2048) - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7, k
+        assert abs(float(g.norm()) - float(fx["lm_grad_l2." + k])) < 1e-3 * float(fx["lm_grad_l2." + k]) + 1e-7, k
+    for k, g in res["grads"].items():           # the projector gradients are unchanged by unfreezing the decoder
+        ref = fx["grad_sub." + k]
+        assert np.abs(sub(g) - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7
+    # the reference clips over ALL trainable parameters
+    total = (sum(float(g.double().pow(2).sum()) for g in res["lm_grads"].values())
+             + sum(float(g.double().pow(2).sum()) for g in res["grads"].values())) ** 0.5
+    assert abs(total - float(fx["grad_norm"])) < 1e-3 * float(fx["grad_norm"])
+
+
 def test_oracle_full_size_fixture():
     """Full-depth (32 + 28 layers) model, 1 x 4 s clip: loss and logits against the reference."""
     torch.set_num_threads(os.cpu_count())

@@ -225,6 +225,49 @@ def test_kv_cache_decode_matches_full_recompute(cuda):
     assert torch.equal(c1[0, :3], got[0, :3]) and (c1[0, 3:] == 0).all()
 
 
+def test_unfrozen_lm_weight_gradients_vs_oracle(cuda):
+    """freeze_language_model: false: the engine's Qwen3 weight gradients -- 7 linears, 4 norm gains
+    per layer, final norm, tied embed_tokens / lm_head table -- against the oracle (pinned to the reference by
+    tests/golden/unfrozen_b2_2s.npz), and the fp32-master -> packed-bf16 operand refresh after an update."""
+    cfg = po.small_config(enc_layers=1, lm_layers=2)
+    W = po.init_weights(cfg, seed=16)
+    batch = po.synthetic_batch(cfg, 2, 2.0, seed=16, response_len=8)
+    n_items = int((batch["labels"] != -100).sum())
+    ref = po.train_step(W, batch, cfg, num_items_in_batch=n_items, train_lm=True)
+    hp = HotPath(PathDims.from_any(cfg.to_dict()), W["encoder"], W["lm"], "cuda")
+    params = {k: v.clone().cuda().contiguous() for k, v in W["projector"].items()}
+    grads = {k: torch.zeros_like(v) for k, v in params.items()}
+    kw = dict(input_ids=batch["input_ids"].cuda(), labels_cpu=batch["labels"], proj_params=params, waveform=batch["waveform"].cuda(),
+              audio_token_counts=batch["audio_token_counts"].cuda(), num_items_in_batch=n_items)
+    loss, _ = hp.forward_backward(grads=grads, train_lm=True, **kw)
+    assert abs(float(loss) - float(ref["loss"])) < 5e-3
+    got = hp.lm.hf_grads()
+    assert set(got) == set(ref["lm_grads"])
+    worst = {}
+    for k, g in ref["lm_grads"].items():
+        e = rel(got[k].cpu(), g)
+        kind = k.split(".")[-2] if "layers" in k else k
+        worst[kind] = max(worst.get(kind, 0.0), e)
+        assert e < 8e-2, (k, e)
+    print("unfrozen LM: worst relative gradient error per parameter kind", {k: round(v, 4) for k, v in worst.items()})
+    for k in grads:
+        assert rel(grads[k].cpu(), ref["grads"][k]) < 6e-2, k
+    # run-to-run: weight gradients are overwritten (not accumulated), norm gradients re-zeroed
+    g1 = {k: v.clone() for k, v in got.items()}
+    hp.forward_backward(grads=grads, train_lm=True, **kw)
+    for k, v in hp.lm.hf_grads().items():
+        assert rel(v, g1[k]) < 2e-3, k
+    # operand refresh: perturb the masters, re-pack, and compare the loss with a HotPath built from the perturbed weights
+    g = torch.Generator().manual_seed(3)
+    W2 = {k: (v + 0.02 * v.abs().mean() * torch.randn(v.shape, generator=g)) for k, v in W["lm"].items() if k != "lm_head.weight"}
+    W2["lm_head.weight"] = W2["model.embed_tokens.weight"]
+    hp.lm.refresh_from({k: v.cuda().contiguous() for k, v in W2.items()})
+    l_refreshed, _ = hp.forward_backward(**kw)
+    hp2 = HotPath(PathDims.from_any(cfg.to_dict()), W["encoder"], W2, "cuda")
+    l_fresh, _ = hp2.forward_backward(**kw)
+    assert abs(float(l_refreshed) - float(l_fresh)) < 2e-6 * abs(float(l_fresh)) and abs(float(l_fresh) - float(loss)) > 1e-4
+
+
 def test_qformer_projector_path(cuda):
     """BASELINE config 4 (projector_type=qformer) through the public ASRModel surface: loss and every projector gradient
     against the oracle (pinned to the reference by tests/golden/qformer_b2_2s.npz).  Dropout is off (projector.eval()),

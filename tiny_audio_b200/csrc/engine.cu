@@ -218,7 +218,8 @@ struct LmBufs {
     long long stride_layers;   // 1 if with_backward else 0
 };
 
-long long lm_carve(const ta_lm_weights* w, int B, int S, int n_lab, int with_bwd, void* ws, long long cap, LmBufs* b) {
+long long lm_carve(const ta_lm_weights* w, int B, int S, int n_lab, int with_bwd, void* ws, long long cap, LmBufs* b,
+                   int train_lm = 0) {
     const long long M = (long long)B * S, D = w->dim, F = w->ffn, P = w->lora_pad;
     const long long QD = (long long)w->n_q_heads * w->head_dim, KD = (long long)w->n_kv_heads * w->head_dim;
     const long long QKV = QD + 2 * KD, QK = QD + KD;
@@ -254,6 +255,12 @@ long long lm_carve(const ta_lm_weights* w, int B, int S, int n_lab, int with_bwd
             b->tr_t = c.take<bf16>(P * Mp);
             b->tr_u = c.take<bf16>(P * Mp);
             b->tr_x = c.take<bf16>(((F > QD) ? F : QD) * Mp);
+        } else if (train_lm) {   // operand transposes of the weight-gradient GEMMs (dW = dY^T X, contraction over the tokens)
+            const long long nlp = ((long long)n_lab + 7) / 8 * 8;
+            const long long a1 = bigw * Mp, a2 = w->vocab_pad * nlp;
+            b->tr_a = c.take<bf16>(a1 > a2 ? a1 : a2);
+            const long long x1 = ((F > QD) ? F : QD) * Mp, x2 = D * nlp;
+            b->tr_x = c.take<bf16>(x1 > x2 ? x1 : x2);
         }
     }
     return c.off;
@@ -276,12 +283,22 @@ int lora_wgrad(const LmBufs& b, long long M, int P, const bf16* dy, long long ld
     RUN(gemm(b.tr_u, Mp, b.tr_x, Mp, P, k_in, (int)M, TA_EPI_F32, dA, k_in, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
     return 0;
 }
+// weight gradient of one linear:  dW[n_out, k_in] = dy^T x   (contraction over the M tokens; fp32 out, overwritten)
+int full_wgrad(const LmBufs& b, long long M, const bf16* dy, long long ld_dy, int n_out, const bf16* x, long long ld_x, int k_in,
+               float* dW, cudaStream_t st) {
+    const long long Mp = (M + 7) / 8 * 8;
+    RUN(k_transpose_bf16(dy, b.tr_a, (int)M, n_out, ld_dy, Mp, st));
+    RUN(k_transpose_bf16(x, b.tr_x, (int)M, k_in, ld_x, Mp, st));
+    RUN(gemm(b.tr_a, Mp, b.tr_x, Mp, n_out, k_in, (int)M, TA_EPI_F32, dW, k_in, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+    return 0;
+}
 }  // namespace
 
 TA_API int ta_lm_workspace_bytes(const ta_lm_weights* w, int B, int S, int n_labelled, int with_backward, long long* bytes) {
     TA_REQUIRE(w && bytes, "null");
     LmBufs b;
-    *bytes = lm_carve(w, B, S, n_labelled, with_backward, nullptr, 0, &b) + 256;
+    // with_backward: 0 forward only, 1 backward to the inputs (frozen LM), 2 backward + weight gradients (unfrozen LM)
+    *bytes = lm_carve(w, B, S, n_labelled, with_backward != 0, nullptr, 0, &b, with_backward == 2) + 256;
     return 0;
 }
 
@@ -305,7 +322,10 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
     const long long ldX = D + P, ldH = F + P, ldAtt = QD + P;
     LmBufs b;
     memset(&b, 0, sizeof(b));
-    const long long need = lm_carve(w, B, S, nl, a->with_backward, a->workspace, a->workspace_bytes, &b);
+    float* const* G_all = a->with_backward ? a->lm_grads : nullptr;      // unfrozen LM: per-layer weight-gradient outputs
+    TA_REQUIRE(!(G_all && P), "LoRA adapters and an unfrozen LM are mutually exclusive (asr_modeling.py:251-301)");
+    TA_REQUIRE(!G_all || (a->d_embed && a->d_final_norm && a->input_ids), "unfrozen LM: d_embed / d_final_norm / input_ids missing");
+    const long long need = lm_carve(w, B, S, nl, a->with_backward != 0, a->workspace, a->workspace_bytes, &b, G_all != nullptr);
     TA_REQUIRE(need <= a->workspace_bytes, "LM workspace too small: need %lld, have %lld", need, a->workspace_bytes);
     if (M == 0) return 0;
     const long long sl = b.stride_layers;
@@ -376,6 +396,14 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
         RUN(gemm(b.logits, w->vocab_pad, w->embed_bf16_t, w->vocab_pad, nl, D, (int)w->vocab_pad, TA_EPI_BF16, b.dhl, D, nullptr,
                  nullptr, nullptr, 0, nullptr, 0, st));
         RUN(k_rmsnorm_f32_bwd(b.dhl, x_final, w->final_norm_w, dx, a->label_rows, nl, D, w->eps, 0, st));
+        if (G_all) {
+            RUN(k_rmsnorm_dw(b.dhl, x_final, a->label_rows, nl, D, w->eps, a->d_final_norm, st));
+            // tied lm_head: d(embed)[v, :] = sum_rows d(logits)[row, v] * normed_hidden[row, :]  (overwrites; the embed_tokens
+            // contribution is scatter-added below)
+            RUN(full_wgrad(b, nl, b.logits, w->vocab_pad, (int)w->vocab_pad, b.hl, D, D, a->d_embed, st));
+        }
+    } else if (G_all) {
+        TA_CHECK_CUDA(cudaMemsetAsync(a->d_embed, 0, sizeof(float) * w->vocab_pad * D, st));
     }
     RUN(k_cast_rows_f32_bf16(dx, b.dxb, M, D, ldX, st));   // later bf16 copies of dx come out of the RMSNorm-backward kernels
     const long long ldBig = ((2 * F > QKV) ? 2 * F : QKV) + P;
@@ -398,8 +426,17 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
             RUN(lora_wgrad(b, M, P, b.dxb, ldX, D, lt + 2 * M * P, P, b.dxb + D, ldX, b.h, ldH, F, Lg[TA_LM_LORA_DA_D],
                            Lg[TA_LM_LORA_DB_D], st));
         }
+        float* const* Gl = G_all ? G_all + (long long)l * TA_LM_GRADS_PER_LAYER : nullptr;
+        if (Gl) {   // down_proj: x = h = silu(gate) * up recomputed from the stash
+            RUN(k_swiglu_h(gu, b.h, M, F, ldH, st));
+            RUN(full_wgrad(b, M, b.dxb, ldX, D, b.h, ldH, F, Gl[TA_LM_G_WD], st));
+        }
         RUN(gemm(b.dxb, ldX, Lw[TA_LM_WD_T], ldX, M, F, D + P, TA_EPI_SWIGLU_BWD, b.big, ldBig, nullptr, nullptr, nullptr, 0, gu, 2 * F,
                  st));
+        if (Gl) {   // gate / up (interleaved 64-row blocks, like the packed operand): x = RMSNorm(x_mid)
+            RUN(k_rmsnorm_f32(x_mid, (const float*)Lw[TA_LM_LN2_W], b.xn, nullptr, M, D, w->eps, st, ldX));
+            RUN(full_wgrad(b, M, b.big, ldBig, 2 * F, b.xn, ldX, D, Gl[TA_LM_G_WGU], st));
+        }
         if (P) {
             RUN(plain(b.big, ldBig, Lw[TA_LM_LORA_BT_GU], 2 * F, M, P, 2 * F, b.big + 2 * F, ldBig, st));
             RUN(k_rmsnorm_f32(x_mid, (const float*)Lw[TA_LM_LN2_W], b.xn, nullptr, M, D, w->eps, st, ldX));   // x of gate/up
@@ -408,8 +445,10 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
         }
         RUN(gemm(b.big, ldBig, Lw[TA_LM_WGU_T], 2 * F + P, M, D, 2 * F + P, TA_EPI_BF16, b.dxn, D, nullptr, nullptr, nullptr, 0, nullptr,
                  0, st));
+        if (Gl) RUN(k_rmsnorm_dw(b.dxn, x_mid, nullptr, M, D, w->eps, Gl[TA_LM_G_LN2], st));
         RUN(k_rmsnorm_f32_bwd(b.dxn, x_mid, (const float*)Lw[TA_LM_LN2_W], dx, nullptr, M, D, w->eps, 1, st, b.dxb, ldX));
         // ---- attention branch ----
+        if (Gl) RUN(full_wgrad(b, M, b.dxb, ldX, D, att, ldAtt, QD, Gl[TA_LM_G_WO], st));
         if (P) {
             RUN(plain(b.dxb, ldX, Lw[TA_LM_LORA_BT_O], D, M, P, D, b.dxb + D, ldX, st));
             RUN(lora_wgrad(b, M, P, b.dxb, ldX, D, att + QD, ldAtt, b.dxb + D, ldX, att, ldAtt, QD, Lg[TA_LM_LORA_DA_O],
@@ -420,6 +459,11 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
                         KD, KD, 1, scale, st));
         RUN(k_lm_qknorm_rope_bwd(qkv, b.dq, b.dk, b.dv, b.big, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W],
                                  w->rope_cos, w->rope_sin, M, S, Hq, Hkv, w->eps, st, ldBig));
+        if (Gl) {
+            RUN(k_qknorm_dw(qkv, b.dq, b.dk, w->rope_cos, w->rope_sin, M, S, Hq, Hkv, w->eps, Gl[TA_LM_G_QNORM], Gl[TA_LM_G_KNORM], st));
+            RUN(k_rmsnorm_f32(x_l, (const float*)Lw[TA_LM_LN1_W], b.xn, nullptr, M, D, w->eps, st, ldX));     // x of q/k/v
+            RUN(full_wgrad(b, M, b.big, ldBig, QKV, b.xn, ldX, D, Gl[TA_LM_G_WQKV], st));
+        }
         if (P) {
             RUN(plain(b.big, ldBig, Lw[TA_LM_LORA_BT_QKV], QKV, M, P, QKV, b.big + QKV, ldBig, st));
             RUN(k_rmsnorm_f32(x_l, (const float*)Lw[TA_LM_LN1_W], b.xn, nullptr, M, D, w->eps, st, ldX));     // x of q/k/v
@@ -428,8 +472,11 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
         }
         RUN(gemm(b.big, ldBig, Lw[TA_LM_WQKV_T], QKV + P, M, D, QKV + P, TA_EPI_BF16, b.dxn, D, nullptr, nullptr, nullptr, 0, nullptr, 0,
                  st));
+        if (Gl) RUN(k_rmsnorm_dw(b.dxn, x_l, nullptr, M, D, w->eps, Gl[TA_LM_G_LN1], st));
         RUN(k_rmsnorm_f32_bwd(b.dxn, x_l, (const float*)Lw[TA_LM_LN1_W], dx, nullptr, M, D, w->eps, 1, st, l > 0 ? b.dxb : nullptr, ldX));
     }
+    if (G_all)   // embed_tokens: the text positions' input gradients flow into the (tied) table
+        RUN(k_embed_grad_scatter(a->input_ids, dx, a->d_embed, M, D, w->vocab, a->audio_token_id, st));
     return 0;
 }
 

@@ -31,6 +31,13 @@ int k_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t st);
 int k_frame_stack(const bf16* x, bf16* out, int B, int S, int n, int k, int D, cudaStream_t st);
 int k_sumsq(const float* g, long long n, float* out, cudaStream_t st);
 
+// unfrozen-LM recipe (lm_wgrad.cu)
+int k_rmsnorm_dw(const bf16* dy, const float* x, const int* row_index, long long rows, int D, float eps, float* dw, cudaStream_t st);
+int k_qknorm_dw(const bf16* qkv, const float* dq, const bf16* dk, const float* cosT, const float* sinT, long long M, int S, int Hq, int Hkv,
+                float eps, float* dqw, float* dkw, cudaStream_t st);
+int k_embed_grad_scatter(const long long* ids, const float* d_emb, float* d_table, long long n_tok, int D, long long vocab,
+                         long long audio_id, cudaStream_t st);
+
 // KV-cache decode path (decode.cu)
 int k_skinny_gemm(const bf16* X, long long ldx, const bf16* W, long long ldw, int M, int N, int K, int mode, void* out, long long ldo,
                   const float* resid, cudaStream_t st, int k_splits = 1);

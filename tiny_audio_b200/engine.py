@@ -135,6 +135,8 @@ class PackedLM:
         self.keep = []
         self.lora_pad = LORA_PAD if lora else 0
         P = self.lora_pad
+        self._vec = {}
+        self.wgrad_flat = None
 
         def dev(t, dtype):
             t = t.detach().to(device=device, dtype=dtype).contiguous()
@@ -197,6 +199,8 @@ class PackedLM:
                 layer[L.LM_LORA_A_GU], layer[L.LM_LORA_A_D] = self.lora_a["gu"][i], self.lora_a["d"][i]
                 layer[L.LM_LORA_BT_QKV], layer[L.LM_LORA_BT_O] = self.lora_bt["qkv"][i], self.lora_bt["o"][i]
                 layer[L.LM_LORA_BT_GU], layer[L.LM_LORA_BT_D] = self.lora_bt["gu"][i], self.lora_bt["d"][i]
+            for slot in (L.LM_LN1_W, L.LM_QNORM_W, L.LM_KNORM_W, L.LM_LN2_W):
+                self._vec[(i, slot)] = layer[slot]
             ptrs.extend(layer)
         self.table = L.pointer_table(ptrs)
         self.grad_table = None
@@ -210,6 +214,99 @@ class PackedLM:
                              d.lm_eps, P, L.ptr(self.embed_f32), L.ptr(self.embed_bf16), L.ptr(self.embed_bf16_t),
                              L.ptr(self.final_norm_w), L.ptr(self.rope_cos), L.ptr(self.rope_sin),
                              C.cast(self.table, C.POINTER(L.P)))
+
+    # ------------------------------------------------------------------ unfrozen LM
+    _MATS = (("self_attn.q_proj", "qkv", 0), ("self_attn.k_proj", "qkv", 1), ("self_attn.v_proj", "qkv", 2), ("self_attn.o_proj", "o", 0),
+             ("mlp.gate_proj", "gu", 0), ("mlp.up_proj", "gu", 1), ("mlp.down_proj", "d", 0))
+
+    def enable_weight_grads(self):
+        """Allocate the engine's weight-gradient outputs as views of ONE flat fp32 buffer (a single NCCL all-reduce covers it)
+        and the per-layer pointer table ta_lm_forward_backward fills.  Layouts follow the packed operands (header)."""
+        if getattr(self, "wgrad_flat", None) is not None:
+            return
+        assert self.lora_pad == 0, "LoRA adapters and an unfrozen LM are mutually exclusive"
+        d = self.dims
+        Lyr, D, F = d.lm_layers, d.lm_dim, d.lm_ffn
+        shapes = {"qkv": (Lyr, self.QKV, D), "o": (Lyr, D, self.QD), "gu": (Lyr, 2 * F, D), "d": (Lyr, D, F), "ln1": (Lyr, D),
+                  "ln2": (Lyr, D), "qn": (Lyr, d.lm_head_dim), "kn": (Lyr, d.lm_head_dim), "fnorm": (D,), "embed": (self.vocab_pad, D)}
+        total = sum(math.prod(v) for v in shapes.values())
+        self.wgrad_flat = torch.zeros(total, dtype=F32, device=self.embed_f32.device)
+        self.wgrad, off = {}, 0
+        for k, shp in shapes.items():
+            n = math.prod(shp)
+            self.wgrad[k] = self.wgrad_flat[off: off + n].view(*shp)
+            off += n
+        small = sum(math.prod(shapes[k]) for k in ("ln1", "ln2", "qn", "kn", "fnorm"))
+        o0 = sum(math.prod(shapes[k]) for k in ("qkv", "o", "gu", "d"))
+        self.wgrad_small = self.wgrad_flat[o0: o0 + small]          # the accumulated (atomic) outputs: zeroed before every step
+        gp = []
+        for i in range(Lyr):
+            gp.extend([self.wgrad[k][i] for k in ("qkv", "o", "gu", "d", "ln1", "ln2", "qn", "kn")])
+        self.wgrad_table = L.pointer_table(gp)
+
+    def hf_grads(self) -> Dict[str, torch.Tensor]:
+        """The weight gradients under HF Qwen3ForCausalLM parameter names.  q/k/v/o/down/norm/embedding gradients are views of the
+        flat buffer; gate/up are de-interleaved copies (two strided copies per step)."""
+        d = self.dims
+        F, D, Lyr = d.lm_ffn, d.lm_dim, d.lm_layers
+        g = self.wgrad
+        gu = g["gu"].view(Lyr, F // 64, 2, 64, D)
+        gate = gu[:, :, 0].reshape(Lyr, F, D)
+        up = gu[:, :, 1].reshape(Lyr, F, D)
+        out = {"model.embed_tokens.weight": g["embed"][: d.vocab], "model.norm.weight": g["fnorm"]}
+        for i in range(Lyr):
+            p = f"model.layers.{i}."
+            out[p + "self_attn.q_proj.weight"] = g["qkv"][i, : self.QD]
+            out[p + "self_attn.k_proj.weight"] = g["qkv"][i, self.QD: self.QD + self.KD]
+            out[p + "self_attn.v_proj.weight"] = g["qkv"][i, self.QD + self.KD:]
+            out[p + "self_attn.o_proj.weight"] = g["o"][i]
+            out[p + "mlp.gate_proj.weight"] = gate[i]
+            out[p + "mlp.up_proj.weight"] = up[i]
+            out[p + "mlp.down_proj.weight"] = g["d"][i]
+            out[p + "input_layernorm.weight"] = g["ln1"][i]
+            out[p + "post_attention_layernorm.weight"] = g["ln2"][i]
+            out[p + "self_attn.q_norm.weight"] = g["qn"][i]
+            out[p + "self_attn.k_norm.weight"] = g["kn"][i]
+        return out
+
+    @torch.no_grad()
+    def refresh_from(self, sd: Dict[str, torch.Tensor]):
+        """Re-pack the bf16 operands (and their transposed dgrad copies) from the fp32 master weights after an optimiser step:
+        one ta_pack_weight launch per matrix.  fp32 vectors (norm gains) and the fp32 embedding table are used in place when the
+        masters already live on this device (no copies), else they are copied."""
+        d = self.dims
+        lib = L.load()
+        st = L.stream_ptr()
+        F, D = d.lm_ffn, d.lm_dim
+        row_off = {"qkv": (0, self.QD, self.QD + self.KD)}
+        for i in range(d.lm_layers):
+            p = f"model.layers.{i}."
+            for name, grp, j in self._MATS:
+                src = sd[p + name + ".weight"]
+                assert src.is_cuda and src.dtype == F32 and src.is_contiguous(), f"{p + name}: fp32 contiguous CUDA master expected"
+                R, Cc = src.shape
+                if grp == "gu":
+                    blk, stride, off = 64, 128, 64 * j
+                else:
+                    blk, stride, off = R, R, (row_off["qkv"][j] if grp == "qkv" else 0)
+                w, wt = self.w[grp][i], self.wt[grp][i]
+                L.check(lib.ta_pack_weight(L.ptr(src), R, Cc, L.ptr(w), w.stride(0), L.ptr(wt), wt.stride(0), blk, stride, off, st))
+        emb = sd["model.embed_tokens.weight"]
+        L.check(lib.ta_pack_weight(L.ptr(emb), emb.shape[0], D, L.ptr(self.embed_bf16), D, L.ptr(self.embed_bf16_t), self.vocab_pad,
+                                   emb.shape[0], emb.shape[0], 0, st))
+        if emb.data_ptr() != self.embed_f32.data_ptr():
+            self.embed_f32.copy_(emb)
+        # norm gains: the kernels read fp32 vectors; alias-or-copy
+        names = [(L.LM_LN1_W, "input_layernorm.weight"), (L.LM_QNORM_W, "self_attn.q_norm.weight"), (L.LM_KNORM_W, "self_attn.k_norm.weight"),
+                 (L.LM_LN2_W, "post_attention_layernorm.weight")]
+        for i in range(d.lm_layers):
+            for slot, nm in names:
+                src = sd[f"model.layers.{i}.{nm}"]
+                dst = self._vec[(i, slot)]
+                if src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src)
+        if sd["model.norm.weight"].data_ptr() != self.final_norm_w.data_ptr():
+            self.final_norm_w.copy_(sd["model.norm.weight"])
 
     # adapter j of a fused projection owns rank rows / columns [8 j, 8 j + r)
     _GROUPS = {"qkv": ("q_proj", "k_proj", "v_proj"), "o": ("o_proj",), "gu": ("gate_proj", "up_proj"), "d": ("down_proj",)}
@@ -418,11 +515,16 @@ class HotPath:
 
     # ------------------------------------------------------------------ decoder + loss (+ backward to inputs_embeds)
     def lm_step(self, emb: torch.Tensor, B: int, S: int, rows: torch.Tensor, targets: torch.Tensor, inv_items: float,
-                with_backward: bool, want_row_loss: bool = False):
+                with_backward: bool, want_row_loss: bool = False, train_lm: bool = False, input_ids: Optional[torch.Tensor] = None):
+        """train_lm (unfrozen LM): the backward also fills self.lm.wgrad (PackedLM.enable_weight_grads) -- needs input_ids."""
         d = self.dims
         nl = int(rows.numel())
         n = C.c_longlong()
-        L.check(self.lib.ta_lm_workspace_bytes(C.byref(self.lm.c), B, S, nl, int(with_backward), C.byref(n)))
+        train_lm = bool(train_lm and with_backward)
+        if train_lm:
+            self.lm.enable_weight_grads()
+            self.lm.wgrad_small.zero_()
+        L.check(self.lib.ta_lm_workspace_bytes(C.byref(self.lm.c), B, S, nl, 2 if train_lm else int(with_backward), C.byref(n)))
         ws = self.ws.get("lm", n.value)
         loss = torch.zeros(1, device=self.device, dtype=F32)
         demb = self.ws.typed("d_inputs_embeds", (B * S, d.lm_dim), F32) if with_backward else None
@@ -430,7 +532,10 @@ class HotPath:
         args = L.LmStepArgs(B, S, nl, int(with_backward), L.ptr(emb), L.ptr(rows), L.ptr(targets), inv_items, L.ptr(loss),
                             L.ptr(row_loss), L.ptr(demb), L.ptr(ws), n.value, None,
                             C.cast(self.lm.grad_table, C.POINTER(L.P)) if (with_backward and self.lm.grad_table is not None) else None,
-                            None, None, 0)
+                            None, None, 0,
+                            C.cast(self.lm.wgrad_table, C.POINTER(L.P)) if train_lm else None,
+                            L.ptr(self.lm.wgrad["embed"]) if train_lm else None, L.ptr(self.lm.wgrad["fnorm"]) if train_lm else None,
+                            L.ptr(input_ids) if train_lm else None, d.audio_token_id)
         L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
         return loss, demb, row_loss
 
@@ -445,7 +550,7 @@ class HotPath:
         hid = self.ws.typed("final_hidden", (B * S, d.lm_dim), F32)
         kc, vc, ms = kv_cache if kv_cache is not None else (None, None, 0)
         args = L.LmStepArgs(B, S, 0, 0, L.ptr(emb), None, None, 1.0, L.ptr(loss), None, None, L.ptr(ws), n.value, L.ptr(hid), None,
-                            L.ptr(kc), L.ptr(vc), ms)
+                            L.ptr(kc), L.ptr(vc), ms, None, None, None, None, 0)
         L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
         return hid
 
@@ -638,7 +743,7 @@ class HotPath:
                          waveform: Optional[torch.Tensor] = None, input_features: Optional[torch.Tensor] = None,
                          audio_token_counts: Optional[torch.Tensor] = None, num_items_in_batch: Optional[float] = None,
                          grads: Optional[Dict[str, torch.Tensor]] = None, return_parts: bool = False,
-                         frame_keep_prob: Optional[float] = None, lm_backward: Optional[bool] = None):
+                         frame_keep_prob: Optional[float] = None, lm_backward: Optional[bool] = None, train_lm: bool = False):
         """Returns (loss [1] fp32 device tensor, parts).  When `grads` is given (fp32 tensors shaped like the projector
         params) the backward runs and fills them with d(loss)/d(param)."""
         d = self.dims
@@ -659,6 +764,7 @@ class HotPath:
         xs, n_a = self.frame_stack(enc)
         with_bwd = grads is not None                           # projector gradients wanted
         lm_bwd = with_bwd if lm_backward is None else (lm_backward or with_bwd)   # LoRA-only training still needs the LM backward
+        lm_bwd = lm_bwd or train_lm                                               # unfrozen LM: weight gradients -> self.lm.wgrad
         audio, stash = self.projector_forward(xs, proj_params, with_bwd)
         if audio_token_counts is None:
             audio_token_counts = (input_ids == d.audio_token_id).sum(-1)
@@ -675,7 +781,7 @@ class HotPath:
             tg_d = rows_d
             n_items = 1.0
         inv = 1.0 / max(n_items, 1.0)
-        loss, demb, _ = self.lm_step(emb, B, S, rows_d, tg_d, inv, lm_bwd)
+        loss, demb, _ = self.lm_step(emb, B, S, rows_d, tg_d, inv, lm_bwd, train_lm=train_lm, input_ids=ids)
         if with_bwd:
             d_audio = self.ws.typed("d_audio", (B * n_a, d.lm_dim), F32)
             d_audio.zero_()

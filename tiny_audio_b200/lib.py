@@ -23,6 +23,8 @@ EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESID, EPI_F32_RESID, EPI_F32, EPI_SWIGLU, EPI
 ENC_PTRS_PER_LAYER = 12
 LM_PTRS_PER_LAYER = 20
 LM_LORA_GRADS_PER_LAYER = 8
+LM_GRADS_PER_LAYER = 8
+(LM_G_WQKV, LM_G_WO, LM_G_WGU, LM_G_WD, LM_G_LN1, LM_G_LN2, LM_G_QNORM, LM_G_KNORM) = range(8)
 (ENC_LN1_W, ENC_LN1_B, ENC_WQKV, ENC_BQKV, ENC_WO, ENC_BO, ENC_LN2_W, ENC_LN2_B, ENC_W1, ENC_B1, ENC_W2, ENC_B2) = range(12)
 (LM_LN1_W, LM_WQKV, LM_WQKV_T, LM_QNORM_W, LM_KNORM_W, LM_WO, LM_WO_T, LM_LN2_W, LM_WGU, LM_WGU_T, LM_WD, LM_WD_T,
  LM_LORA_A_QKV, LM_LORA_A_O, LM_LORA_A_GU, LM_LORA_A_D, LM_LORA_BT_QKV, LM_LORA_BT_O, LM_LORA_BT_GU, LM_LORA_BT_D) = range(20)
@@ -57,7 +59,8 @@ class LmStepArgs(C.Structure):
     _fields_ = [("B", c_int), ("S", c_int), ("n_labelled", c_int), ("with_backward", c_int),
                 ("inputs_embeds", P), ("label_rows", P), ("label_targets", P), ("inv_num_items", c_float),
                 ("loss", P), ("row_loss", P), ("d_inputs_embeds", P), ("workspace", P), ("workspace_bytes", c_ll),
-                ("final_hidden", P), ("lora_grads", C.POINTER(P)), ("k_cache", P), ("v_cache", P), ("cache_max_seq", c_int)]
+                ("final_hidden", P), ("lora_grads", C.POINTER(P)), ("k_cache", P), ("v_cache", P), ("cache_max_seq", c_int),
+                ("lm_grads", C.POINTER(P)), ("d_embed", P), ("d_final_norm", P), ("input_ids", P), ("audio_token_id", c_ll)]
 
 
 _SIGS = {
@@ -100,6 +103,10 @@ _SIGS = {
     "ta_lm_workspace_bytes": ([C.POINTER(LmWeights), c_int, c_int, c_int, c_int, C.POINTER(c_ll)], c_int),
     "ta_lm_forward_backward": ([C.POINTER(LmWeights), C.POINTER(LmStepArgs), P], c_int),
     "ta_lm_hidden_to_logits": ([C.POINTER(LmWeights), P, P, c_int, P, P, P], c_int),
+    "ta_rmsnorm_dw": ([P, P, P, c_ll, c_int, c_float, P, P], c_int),
+    "ta_qknorm_dw": ([P, P, P, P, P, c_ll, c_int, c_int, c_int, c_float, P, P, P], c_int),
+    "ta_embed_grad_scatter": ([P, P, P, c_ll, c_int, c_ll, c_ll, P], c_int),
+    "ta_pack_weight": ([P, c_int, c_int, P, c_ll, P, c_ll, c_int, c_int, c_int, P], c_int),
     "ta_skinny_gemm_bf16": ([P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, P, c_ll, P, c_int, P], c_int),
     "ta_decode_resid_rmsnorm": ([P, P, c_int, c_int, P, P, P, c_int, c_float, c_ll, P], c_int),
     "ta_decode_attn": ([P, P, P, P, c_ll, P, c_int, c_int, c_int, c_int, c_float, P], c_int),
