@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--clip-seconds", type=float, default=30.0)
     ap.add_argument("--response-len", type=int, default=64)
     ap.add_argument("--proj-hidden", type=int, default=2048, help="projector hidden dim (2048 = the ~12 M variant)")
+    ap.add_argument("--train-lm", action="store_true",
+                    help="unfrozen-LM recipe (freeze_language_model: false, configs/experiments/embedded.yaml): the whole Qwen3 "
+                         "decoder trains too -- weight-gradient GEMMs, 596 M-parameter AdamW, operand re-pack; NOT the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
@@ -148,7 +151,8 @@ def run_reference(args):
 
 
 def workload_config(args, n_gpus):
-    return {"workload": f"tiny-audio train step: MLP projector (hidden {args.proj_hidden}), GLM-ASR encoder 32L + Qwen3-0.6B 28L, "
+    recipe = "UNFROZEN Qwen3 decoder (freeze_language_model: false), " if getattr(args, "train_lm", False) else ""
+    return {"workload": f"tiny-audio train step: {recipe}MLP projector (hidden {args.proj_hidden}), GLM-ASR encoder 32L + Qwen3-0.6B 28L, "
                         f"batch {args.batch}/GPU x {args.clip_seconds:g} s 16 kHz clips, response {args.response_len} tokens",
             "global_batch": args.batch * n_gpus, "clip_seconds": args.clip_seconds, "parallelism": f"dp{n_gpus}",
             "padding": "longest (equal-length clips)", "audio_token_dropout": 0.0, "grad_accum": 1,
@@ -175,13 +179,22 @@ def run_ours(args):
     lib = L.load()
 
     dims = PathDims(proj_hidden=args.proj_hidden)
-    model = build_offline_model(dims, device=dev, seed=1234)
+    model = build_offline_model(dims, device=dev, seed=1234, freeze_language_model=not args.train_lm)
     model.train()
     hot = model._hot_path()
     # the HF modules only own the fp32 master copies; free them (the packed bf16 copies in `hot` are what runs)
     names = [n for n, _ in model.projector.named_parameters()]
     params = [p for _, p in model.projector.named_parameters()]
-    opt = ClipAdamW(params, lr=1e-3, max_grad_norm=1.0)
+    if args.train_lm:
+        # the reference's parameter groups (scripts/train.py:384-437): `language_model.*` gets the decoder lr / weight decay,
+        # norm gains are excluded from decay
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        dec = [p for n, p in named if n.startswith("language_model.") and p.dim() > 1]
+        dec_nd = [p for n, p in named if n.startswith("language_model.") and p.dim() <= 1]
+        opt = ClipAdamW([dict(params=params, lr=1e-3, weight_decay=0.0), dict(params=dec, lr=2e-5, weight_decay=0.01),
+                         dict(params=dec_nd, lr=2e-5, weight_decay=0.0)], max_grad_norm=1.0)
+    else:
+        opt = ClipAdamW(params, lr=1e-3, max_grad_norm=1.0)
 
     B = args.batch
     host = synthetic_batch(dims, B, args.clip_seconds, seed=100 + rank, response_len=args.response_len, pin=True)
@@ -195,6 +208,13 @@ def run_ours(args):
     gmap = {n: p.grad for n, p in zip(names, params)}
 
     def step_resident():
+        if args.train_lm:      # unfrozen decoder: the public surface routes the ~310 LM parameters' gradients
+            opt.zero_grad()
+            out = model(input_ids=d_ids, input_features=d_wave, labels=labels_cpu, audio_token_counts=d_cnt,
+                        num_items_in_batch=n_items_global)
+            out.loss.backward()
+            opt.step()
+            return out.loss.detach()
         loss, _ = hot.forward_backward(input_ids=d_ids, labels_cpu=labels_cpu, proj_params=pmap, waveform=d_wave,
                                        audio_token_counts=d_cnt, num_items_in_batch=n_items_global, grads=gmap)
         opt.step()
@@ -283,6 +303,11 @@ def run_ours(args):
                 "traffic": 576.5e6 if (M, N, K) == (48000, 5120, 1280) else None,
                 "algorithmic_bytes": 2.0 * (M * K + N * K + M * N), "tensor_pipe_active_pct_ncu": 74.5, "step_tflops": 116.0e9 * audio_s / (ms_step / 1000.0) / 1e12 / world,
                 "step_frac_of_sustained": 116.0e9 * audio_s / (ms_step / 1000.0) / 1e12 / world / pk["bf16_tflops_sustained"]}
+        if args.train_lm:      # + weight-gradient GEMMs of the decoder: 2 * P_lm_lin * S_lm (body) + 2 * P_head * n_labelled (tied head)
+            extra = (2.0 * 440.4e6 * 464 + 2.0 * 155.6e6 * (args.response_len + 1)) / args.clip_seconds
+            gf = 116.0e9 + extra
+            roof["step_tflops"] = gf * audio_s / (ms_step / 1000.0) / 1e12 / world
+            roof["step_frac_of_sustained"] = roof["step_tflops"] / pk["bf16_tflops_sustained"]
         del a, w, out
 
     cpu = None

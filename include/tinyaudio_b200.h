@@ -58,6 +58,10 @@ typedef struct ta_gemm_epilogue {
 
 int ta_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epilogue_mode,
                  const ta_gemm_epilogue* epilogue, void* stream);
+/* weight-gradient form: C fp32 [M,N] = alpha * At^T . Bt with At bf16 [K,M], Bt bf16 [K,N] row-major (both operands MN-major UMMA
+ * tiles straight from the activations; autograd's dW = dY^T X of every nn.Linear, HF:trainer.py:1935) */
+int ta_gemm_bf16_tn(const void* At, long long ldat, const void* Bt, long long ldbt, int M, int N, int K, float* out, long long ldo,
+                    float alpha, void* stream);
 int ta_gemm_set_tile_n(int bn); /* 0 = auto, 128, 256 (testing / tuning) */
 int ta_gemm_set_cta_pair(int on); /* 1: CTA-pair kernel (tcgen05 cta_group::2, 256 x N tiles); 0: 1-CTA kernel */
 

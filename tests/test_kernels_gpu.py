@@ -587,3 +587,21 @@ def test_norm_weight_grads_embed_scatter_and_pack(cuda):
         L.check(lib.ta_pack_weight(L.ptr(src), Fd, Dk, L.ptr(dst), Dk + 32, L.ptr(dstT), 2 * Fd + 16, 64, 128, 64 * j, L.stream_ptr()))
     want = torch.cat([wg.view(Fd // 64, 1, 64, Dk), wu.view(Fd // 64, 1, 64, Dk)], 1).reshape(2 * Fd, Dk).to(BF16)
     assert torch.equal(dst[:, :Dk], want) and torch.equal(dstT[:, : 2 * Fd], want.t()) and float(dst[:, Dk:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 200), (1024, 3072, 1000), (6144, 1024, 928), (384, 1024, 2080)])
+def test_gemm_tn_weight_gradient_form(cuda, M, N, K):
+    """C = At^T Bt with both operands MN-major (dW = dY^T X): against fp32 torch and against the transposed-copy route."""
+    ld_a, ld_b = M + 64, N + 8
+    at = rnd(K, ld_a, seed=1)[:, :M]
+    bt = rnd(K, ld_b, seed=2)[:, :N]
+    out = L.gemm_tn(at, bt)
+    ref = at.float().t() @ bt.float()
+    assert out.shape == (M, N) and rel_err(out, ref) < 1e-3
+    Kp = (K + 7) // 8 * 8
+    a_t = torch.zeros(M, Kp, device="cuda", dtype=BF16)
+    b_t = torch.zeros(N, Kp, device="cuda", dtype=BF16)
+    a_t[:, :K], b_t[:, :K] = at.t(), bt.t()
+    via = L.gemm(a_t, b_t, epi=L.EPI_F32, k=K)
+    assert rel_err(out, via) < 1e-5
+    assert rel_err(L.gemm_tn(at, bt, alpha=0.5), 0.5 * ref) < 1e-3

@@ -391,3 +391,60 @@ def test_lora_zero_b_is_identity_and_projector_freeze(cuda):
     assert all(p.grad is None for p in model.projector.parameters())
     for t in ad.targets:
         assert rel(ad.lora_B[t].grad, gb[t]) < 1e-3, t
+
+
+def test_unfrozen_lm_through_public_surface_and_optimizer(cuda):
+    """freeze_language_model=False through ASRModel(**batch) -> loss.backward() -> ClipAdamW.step() with the reference's
+    parameter groups (names starting `language_model.` get their own lr / weight decay, norm gains no decay: train.py:384-437):
+    every `language_model.*` parameter receives the oracle's gradient, the update is AdamW with the global-norm clip over ALL
+    trainable parameters, the next forward runs on the updated (re-packed) weights, and state_dict() carries the decoder."""
+    from tiny_audio_b200.optim import ClipAdamW
+    from tiny_audio_b200.synthetic import build_offline_model
+    cfg = po.small_config(enc_layers=1, lm_layers=2)
+    W = po.init_weights(cfg, seed=23)
+    batch = po.synthetic_batch(cfg, 2, 2.0, seed=23, response_len=6)
+    n_items = int((batch["labels"] != -100).sum())
+    ref = po.train_step(W, batch, cfg, num_items_in_batch=n_items, train_lm=True)
+    model = build_offline_model(PathDims.from_any(cfg.to_dict()), device="cuda", enc_state=W["encoder"], lm_state=W["lm"],
+                                proj_state=W["projector"], freeze_language_model=False)
+    model.train()
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    assert any(n.startswith("language_model.") for n, _ in named) and not any(n.startswith("audio_tower.") for n, _ in named)
+    assert sum(1 for n, _ in named if n.startswith("language_model.")) == 2 + 11 * cfg.lm_layers
+    dec = [p for n, p in named if n.startswith("language_model.") and p.dim() > 1]
+    dec_nd = [p for n, p in named if n.startswith("language_model.") and p.dim() <= 1]
+    proj = [p for n, p in named if not n.startswith("language_model.")]
+    lr_p, lr_d = 1e-3, 2e-4
+    opt = ClipAdamW([dict(params=proj, lr=lr_p, weight_decay=0.0), dict(params=dec, lr=lr_d, weight_decay=0.01),
+                     dict(params=dec_nd, lr=lr_d, weight_decay=0.0)], max_grad_norm=1.0)
+    before = {n: p.detach().clone() for n, p in named}
+    opt.zero_grad()
+    out = model(input_ids=batch["input_ids"].cuda(), input_features=batch["waveform"].cuda(), labels=batch["labels"],
+                attention_mask=batch["attention_mask"].cuda(), audio_token_counts=batch["audio_token_counts"].cuda(),
+                num_items_in_batch=n_items)
+    out.loss.backward()
+    assert abs(float(out.loss) - float(ref["loss"])) < 5e-3
+    for n, p in named:
+        if n.startswith("language_model."):
+            g = ref["lm_grads"][n[len("language_model."):]]
+            assert rel(p.grad.cpu(), g) < 8e-2, n
+    gsq = sum(float(p.grad.double().pow(2).sum()) for _, p in named)
+    opt.step()
+    torch.cuda.synchronize()
+    assert abs(float(opt.grad_norm()) - gsq ** 0.5) < 1e-3 * gsq ** 0.5
+    coef = min(1.0, 1.0 / (gsq ** 0.5 + 1e-6))
+    for n, p in named:      # first AdamW step: p - lr * (g / (|g| + eps) + wd * p) with the clipped gradient
+        g = p.grad * coef
+        lr = lr_p if not n.startswith("language_model.") else lr_d
+        wd = 0.01 if (n.startswith("language_model.") and p.dim() > 1) else 0.0
+        want = before[n] * (1.0 - lr * wd) - lr * g / (g.abs() + 1e-8)
+        assert float((p.detach() - want).abs().max()) < 2e-6 + 1e-3 * lr, n
+    # next forward: operands re-packed from the updated masters == a model built from the updated weights
+    loss2 = float(_model_step(model, batch, n_items))
+    lm_sd = {k[len("language_model."):]: v.detach().cpu() for k, v in model.state_dict().items() if k.startswith("language_model.")}
+    assert len(lm_sd) >= 2 + 11 * cfg.lm_layers
+    fresh = build_offline_model(PathDims.from_any(cfg.to_dict()), device="cuda", enc_state=W["encoder"], lm_state=lm_sd,
+                                proj_state={k: v.detach().cpu() for k, v in model.projector.state_dict().items()})
+    fresh.train()
+    loss3 = float(_model_step(fresh, batch, n_items))
+    assert abs(loss2 - loss3) < 2e-6 * abs(loss3) and abs(loss2 - float(out.loss)) > 1e-5

@@ -45,7 +45,9 @@ def _gather_audio_embeds(audio_embeds: torch.Tensor, token_counts: torch.Tensor)
 class _FusedPathLoss(torch.autograd.Function):
     """loss = CE(Qwen3(scatter(projector(encoder(audio))))) with d(loss)/d(projector params) -- and d(loss)/d(LoRA A, B) when
     adapters are attached -- computed in the same pass; backward only rescales the stored gradients by the incoming scalar.
-    Tensor arguments: the 4 projector parameters, then the stacked lora_A tensors, then the stacked lora_B tensors."""
+    Tensor arguments: the 4 projector parameters, then EITHER the stacked lora_A tensors followed by the stacked lora_B tensors
+    OR (freeze_language_model=False) every Qwen3 parameter in `language_model.named_parameters()` order, whose gradients the
+    engine produces as well."""
 
     @staticmethod
     def forward(ctx, model, call, w1, n1, w2, n2, *lora_tensors):
@@ -54,6 +56,9 @@ class _FusedPathLoss(torch.autograd.Function):
         need = any(ctx.needs_input_grad[2:6])
         grads = {k: torch.empty_like(v) for k, v in params.items()} if need else None
         adapters = getattr(model, "lora_adapters", None)
+        train_lm = adapters is None and len(lora_tensors) > 0          # the extra tensors are the decoder's own parameters
+        if train_lm:
+            return _FusedPathLoss._forward_unfrozen(ctx, model, hot, call, params, grads, lora_tensors, (w1, n1, w2, n2))
         n_l = len(lora_tensors) // 2
         need_lora = adapters is not None and any(ctx.needs_input_grad[6:])
         if adapters is not None:
@@ -69,6 +74,26 @@ class _FusedPathLoss(torch.autograd.Function):
             ctx.lora_grads = [ga[t].clone() for t in names] + [gb[t].clone() for t in names]
             ctx.lora_dtypes = [t.dtype for t in lora_tensors]
         ctx.n_lora = len(lora_tensors)
+        return loss.reshape(())
+
+    @staticmethod
+    def _forward_unfrozen(ctx, model, hot, call, params, grads, lm_tensors, proj_tensors):
+        names = [n for n, _ in model.language_model.named_parameters()]
+        assert len(names) == len(lm_tensors)
+        version = sum(int(t._version) for t in lm_tensors)
+        if getattr(model, "_lm_pack_version", None) != version:        # the optimiser moved the masters: refresh the bf16 operands
+            hot.lm.refresh_from({n: t.detach() for n, t in zip(names, lm_tensors)})
+            model._lm_pack_version = version
+        need_lm = any(ctx.needs_input_grad[6:])
+        loss, _ = hot.forward_backward(proj_params=params, grads=grads, train_lm=need_lm, **call)
+        ctx.grads = grads
+        ctx.dtypes = tuple(t.dtype for t in proj_tensors)
+        ctx.lora_grads = None
+        if need_lm:
+            hg = hot.lm.hf_grads()
+            ctx.lora_grads = [hg[n] for n in names]       # views of the engine's flat buffer; scaled (= copied) in backward
+            ctx.lora_dtypes = [t.dtype for t in lm_tensors]
+        ctx.n_lora = len(lm_tensors)
         return loss.reshape(())
 
     @staticmethod
@@ -177,9 +202,8 @@ class ASRModel(PreTrainedModel, GenerationMixin):
         if getattr(config, "freeze_language_model", True):
             lm.requires_grad_(False)
             lm.train(False)
-        else:
-            raise NotImplementedError("freeze_language_model=False (full decoder fine-tuning) is a 'next' row "
-                                      "(SURVEY.md section 8f rank 3) and not built yet")
+        # else: full decoder fine-tuning (configs/experiments/embedded.yaml:19-33): the parameters stay trainable fp32 masters;
+        # the CUDA engine computes their gradients and re-packs its bf16 operands after every update (engine.py:PackedLM)
         return lm
 
     def _create_projector(self, config: ASRConfig, dtype: torch.dtype) -> nn.Module:
@@ -266,7 +290,11 @@ class ASRModel(PreTrainedModel, GenerationMixin):
     def state_dict(self, *args, **kwargs):
         """Trainable weights only (projector), reference key names (`projector.linear_1.weight`, ...).  LoRA adapters are
         serialised separately (peft layout, `lora_adapters.peft_state_dict()`), as in the reference (asr_modeling.py:398-422)."""
-        return {f"projector.{k}": v for k, v in self.projector.state_dict().items()}
+        sd = {f"projector.{k}": v for k, v in self.projector.state_dict().items()}
+        if not getattr(self.config, "freeze_language_model", True):      # fine-tuned decoder travels with the checkpoint (:409-422)
+            sd.update({f"language_model.{k}": v for k, v in self.language_model.state_dict().items()
+                       if not k.startswith("lora_adapters.")})
+        return sd
 
     def _compute_encoder_output_lengths(self, audio_attention_mask: torch.Tensor) -> torch.Tensor:
         return compute_encoder_output_length(audio_attention_mask.sum(dim=-1), self.config.encoder_conv_layers)
@@ -365,6 +393,8 @@ class ASRModel(PreTrainedModel, GenerationMixin):
             if self.lora_adapters is not None:
                 la, lb = self.lora_adapters.tensors()
                 lora_t = tuple(la.values()) + tuple(lb.values())
+            elif not getattr(self.config, "freeze_language_model", True):
+                lora_t = tuple(p for _, p in self.language_model.named_parameters())
             loss = _FusedPathLoss.apply(self, call, pr.linear_1.weight, pr.norm.weight, pr.linear_2.weight, pr.norm_2.weight, *lora_t)
         else:
             # generic projector (qformer): frozen encoder -> projector module (autograd) -> CUDA decoder + CE with

@@ -288,8 +288,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 int g_bwd_dbg = 0;
 }  // namespace
 
+int g_wgrad_transposed = 0;   // key 2: 1 = weight-gradient GEMMs through transposed operand copies (A/B reference of the TN kernel)
 TA_API int ta_debug_set(int key, int value) {   // experiments only (key 1: attention-backward switches)
     if (key == 1) g_bwd_dbg = value;
+    if (key == 2) g_wgrad_transposed = value;
     return 0;
 }
 

@@ -5,6 +5,8 @@
 #include "kernels.cuh"
 #include "tinyaudio_b200.h"
 
+extern int g_wgrad_transposed;   // attn_tc_bwd.cu (ta_debug_set key 2)
+
 namespace {
 
 struct Carver {
@@ -161,18 +163,27 @@ TA_API int ta_mlp_projector_backward(const ta_mlp_projector_weights* w, const vo
     const int H = w->hidden, O = w->out_dim, I = w->in_dim;
     // norm_2 backward -> d(y2) (bf16), d(norm_2.weight)
     RUN(k_proj_norm_bwd((const bf16*)y2, w->norm2_w, d_out, 1, dy2, d_norm2_w, M, O, w->eps, 0, st));
-    // wgrad linear_2: dW2[O,H] = dy2^T . a1      (contraction over the M rows)
-    RUN(k_transpose_bf16(dy2, tA, (int)M, O, O, Mp, st));
-    RUN(k_transpose_bf16((const bf16*)a1, tB, (int)M, H, H, Mp, st));
-    RUN(gemm(tA, Mp, tB, Mp, O, H, (int)M, TA_EPI_F32, d_w2, H, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+    // wgrad linear_2: dW2[O,H] = dy2^T . a1      (contraction over the M rows; TN GEMM: operands as they lie in memory)
+    const bool tn = !g_wgrad_transposed;
+    if (tn) {
+        RUN(ta_gemm_bf16_tn(dy2, O, a1, H, O, H, (int)M, d_w2, H, 1.0f, st));
+    } else {
+        RUN(k_transpose_bf16(dy2, tA, (int)M, O, O, Mp, st));
+        RUN(k_transpose_bf16((const bf16*)a1, tB, (int)M, H, H, Mp, st));
+        RUN(gemm(tA, Mp, tB, Mp, O, H, (int)M, TA_EPI_F32, d_w2, H, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+    }
     // dgrad linear_2: d(a1)[M,H] = dy2 . W2
     RUN(gemm(dy2, O, w->w2_t, O, M, H, O, TA_EPI_BF16, da1, H, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
     // GELU + norm backward (in place: d(a1) -> d(y1)), d(norm.weight)
     RUN(k_proj_norm_bwd((const bf16*)y1, w->norm_w, da1, 0, da1, d_norm_w, M, H, w->eps, 1, st));
     // wgrad linear_1: dW1[H,I] = dy1^T . x_stacked
-    RUN(k_transpose_bf16(da1, tA, (int)M, H, H, Mp, st));
-    RUN(k_transpose_bf16((const bf16*)x_stacked, tB, (int)M, I, I, Mp, st));
-    RUN(gemm(tA, Mp, tB, Mp, H, I, (int)M, TA_EPI_F32, d_w1, I, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+    if (tn) {
+        RUN(ta_gemm_bf16_tn(da1, H, x_stacked, I, H, I, (int)M, d_w1, I, 1.0f, st));
+    } else {
+        RUN(k_transpose_bf16(da1, tA, (int)M, H, H, Mp, st));
+        RUN(k_transpose_bf16((const bf16*)x_stacked, tB, (int)M, I, I, Mp, st));
+        RUN(gemm(tA, Mp, tB, Mp, H, I, (int)M, TA_EPI_F32, d_w1, I, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+    }
     return 0;
 }
 
@@ -274,6 +285,11 @@ inline int plain(const void* A, long long lda, const void* Bm, long long ldb, lo
 // A / B gradients of one adapter group:  dBs[N_out, P] = dy^T t,  dA[P, K_in] = u^T x   (contractions over the M tokens)
 int lora_wgrad(const LmBufs& b, long long M, int P, const bf16* dy, long long ld_dy, int n_out, const bf16* t, long long ld_t,
                const bf16* u, long long ld_u, const bf16* x, long long ld_x, int k_in, float* dA, float* dBs, cudaStream_t st) {
+    if (!g_wgrad_transposed) {
+        RUN(ta_gemm_bf16_tn(dy, ld_dy, t, ld_t, n_out, P, (int)M, dBs, P, 1.0f, st));
+        RUN(ta_gemm_bf16_tn(u, ld_u, x, ld_x, P, k_in, (int)M, dA, k_in, 1.0f, st));
+        return 0;
+    }
     const long long Mp = (M + 7) / 8 * 8;
     RUN(k_transpose_bf16(dy, b.tr_a, (int)M, n_out, ld_dy, Mp, st));
     RUN(k_transpose_bf16(t, b.tr_t, (int)M, P, ld_t, Mp, st));
@@ -286,6 +302,8 @@ int lora_wgrad(const LmBufs& b, long long M, int P, const bf16* dy, long long ld
 // weight gradient of one linear:  dW[n_out, k_in] = dy^T x   (contraction over the M tokens; fp32 out, overwritten)
 int full_wgrad(const LmBufs& b, long long M, const bf16* dy, long long ld_dy, int n_out, const bf16* x, long long ld_x, int k_in,
                float* dW, cudaStream_t st) {
+    if (!g_wgrad_transposed)   // both operands MN-major straight from the activations (gemm_sm100.cu, TN variant)
+        return ta_gemm_bf16_tn(dy, ld_dy, x, ld_x, n_out, k_in, (int)M, dW, k_in, 1.0f, st);
     const long long Mp = (M + 7) / 8 * 8;
     RUN(k_transpose_bf16(dy, b.tr_a, (int)M, n_out, ld_dy, Mp, st));
     RUN(k_transpose_bf16(x, b.tr_x, (int)M, k_in, ld_x, Mp, st));

@@ -727,7 +727,22 @@ struct Cfg2 {
     static constexpr int SMEM_BYTES = BAR_OFF + 256 + 2 * BN * 4 + 1024;
 };
 
-template <int BN, int EPI>
+// MN-major SWIZZLE_128B operand tile (TN variant below): rows = K index (128 B = 64 bf16 of the M / N index per row), 8-row groups
+// 1024 B apart, further 64-wide M / N atoms `lbo_bytes` apart -- the layout a plain 2-D TMA box {64 cols, K rows} of a row-major
+// [K, M] matrix produces (same descriptor form as attn_tc.cu uses for V)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor_g(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// TN = true: C[M,N] = At^T . Bt with At [K, M] and Bt [K, N] row-major (both operands MN-major): the weight-gradient GEMM
+// dW = dY^T X reads the activations as they lie in memory (contraction over the token rows), no transposed copies.
+template <int BN, int EPI, bool TN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int M, int N, int K, EpiArgs ep) {
@@ -792,8 +807,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
-                    tma_load_2d_2sm(smA + stage * C::A_BYTES, &tmA, &full[stage], kb * BK, row0);
-                    tma_load_2d_2sm(smB + stage * C::B_BYTES, &tmB, &full[stage], kb * BK, nrow0);
+                    if constexpr (TN) {      // boxes {64 m (or n), 64 k}: one 8 KB atom per 64 output rows / columns
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i)
+                            tma_load_2d_2sm(smA + stage * C::A_BYTES + i * 8192, &tmA, &full[stage], row0 + 64 * i, kb * BK);
+#pragma unroll
+                        for (int i = 0; i < BN / 128; ++i)
+                            tma_load_2d_2sm(smB + stage * C::B_BYTES + i * 8192, &tmB, &full[stage], nrow0 + 64 * i, kb * BK);
+                    } else {
+                        tma_load_2d_2sm(smA + stage * C::A_BYTES, &tmA, &full[stage], kb * BK, row0);
+                        tma_load_2d_2sm(smB + stage * C::B_BYTES, &tmB, &full[stage], kb * BK, nrow0);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -801,7 +825,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN) | (TN ? ((1u << 15) | (1u << 16)) : 0u);
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -817,8 +841,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const uint32_t b0 = smem_u32(smB + stage * C::B_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t ad = umma_desc_sw128_kmajor(a0 + k * UMMA_K * 2);
-                        const uint64_t bd = umma_desc_sw128_kmajor(b0 + k * UMMA_K * 2);
+                        const uint64_t ad = TN ? umma_desc_sw128_mnmajor_g(a0 + k * UMMA_K * 128, 8192) : umma_desc_sw128_kmajor(a0 + k * UMMA_K * 2);
+                        const uint64_t bd = TN ? umma_desc_sw128_mnmajor_g(b0 + k * UMMA_K * 128, 8192) : umma_desc_sw128_kmajor(b0 + k * UMMA_K * 2);
                         umma_f16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit_2sm(&empty[stage]);
@@ -995,11 +1019,11 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, i
     }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool TN = false>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2, int M, int N, int K,
             const EpiArgs& ep, cudaStream_t st) {
     using C = Cfg2<BN>;
-    auto kern = gemm2_kernel<BN, EPI>;
+    auto kern = gemm2_kernel<BN, EPI, TN>;
     static bool attr_done = false;
     if (!attr_done) {
         TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -1046,6 +1070,28 @@ TA_API int ta_gemm_set_tile_n(int bn) {
 TA_API int ta_gemm_set_cta_pair(int on) {
     g_cta_pair = on ? 1 : 0;
     return 0;
+}
+
+// C fp32 [M, N] = alpha * At^T . Bt,  At bf16 [K, M] (ld ldat), Bt bf16 [K, N] (ld ldbt): weight gradients dW = dY^T X
+TA_API int ta_gemm_bf16_tn(const void* At, long long ldat, const void* Bt, long long ldbt, int M, int N, int K, float* out, long long ldo,
+                           float alpha, void* stream) {
+    TA_REQUIRE(At && Bt && out, "ta_gemm_bf16_tn: null pointer");
+    TA_REQUIRE(M > 0 && N > 0 && K > 0, "ta_gemm_bf16_tn: empty problem M=%d N=%d K=%d", M, N, K);
+    TA_REQUIRE(N % 128 == 0, "ta_gemm_bf16_tn: N=%d must be a multiple of 128", N);
+    const int bn = (N % 256 == 0) ? 256 : 128;
+    EpiArgs ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.out = out; ep.ldo = ldo; ep.ldr = ldo; ep.alpha = alpha == 0.0f ? 1.0f : alpha;
+    CUtensorMap ta, tb, tc;
+    int rc = make_map(&ta, At, K, M, ldat, 64);        // rows = contraction index, box {64 m, 64 k}
+    if (rc) return rc;
+    rc = make_map(&tb, Bt, K, N, ldbt, 64);
+    if (rc) return rc;
+    rc = make_map(&tc, out, M, N, ldo, BM, true);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (bn == 256) return launch2<256, TA_EPI_F32, true>(ta, tb, tc, tc, M, N, K, ep, st);
+    return launch2<128, TA_EPI_F32, true>(ta, tb, tc, tc, M, N, K, ep, st);
 }
 
 TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epi,

@@ -67,6 +67,7 @@ _SIGS = {
     "ta_version": ([], c_int),
     "ta_launch_count": ([], C.c_ulonglong),
     "ta_gemm_bf16": ([P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, C.POINTER(GemmEpilogue), P], c_int),
+    "ta_gemm_bf16_tn": ([P, c_ll, P, c_ll, c_int, c_int, c_int, P, c_ll, c_float, P], c_int),
     "ta_gemm_set_tile_n": ([c_int], c_int),
     "ta_gemm_set_cta_pair": ([c_int], c_int),
     "ta_logmel_workspace_floats": ([c_int, c_int, C.POINTER(c_ll)], c_int),
@@ -199,6 +200,20 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, epi: int = EPI_BF16, out: Optional
                      aux.stride(0) if aux is not None else 0, alpha,
                      ptr(rope[0]) if rope else None, ptr(rope[1]) if rope else None, rope[2] if rope else 0, rope[3] if rope else 0)
     check(lib.ta_gemm_bf16(ptr(a), a.stride(0), ptr(b), b.stride(0), M, N, K, epi, C.byref(e), stream_ptr()))
+    return out
+
+
+def gemm_tn(at: torch.Tensor, bt: torch.Tensor, out: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
+    """out fp32 [M, N] = alpha * at.T @ bt;  at [K, M] bf16, bt [K, N] bf16 (row-major): dW = dY^T X without transposed copies."""
+    lib = load()
+    require_cuda(at, bt)
+    assert at.dtype == torch.bfloat16 and bt.dtype == torch.bfloat16 and at.stride(-1) == 1 and bt.stride(-1) == 1
+    K, M = at.shape
+    N = bt.shape[1]
+    assert bt.shape[0] == K
+    if out is None:
+        out = torch.empty(M, N, device=at.device, dtype=torch.float32)
+    check(lib.ta_gemm_bf16_tn(ptr(at), at.stride(0), ptr(bt), bt.stride(0), M, N, K, ptr(out), out.stride(0), alpha, stream_ptr()))
     return out
 
 

@@ -23,12 +23,20 @@ from . import lib as L
 class ClipAdamW(torch.optim.Optimizer):
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, max_grad_norm: float = 1.0, process_group=None):
-        params = [p for p in params if p.requires_grad]
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        params = list(params)
+        if params and isinstance(params[0], dict):      # torch-style parameter groups (decoder lr / weight decay: train.py:384-437)
+            groups = [dict(g, params=[p for p in g["params"] if p.requires_grad]) for g in params]
+            groups = [g for g in groups if g["params"]]
+            super().__init__(groups, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+            params = [p for g in groups for p in g["params"]]
+        else:
+            params = [p for p in params if p.requires_grad]
+            super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.lib = L.load()
         self.max_grad_norm = max_grad_norm
         self.process_group = process_group
         self._params = params
+        self._index = {id(p): i for i, p in enumerate(params)}
         for p in params:
             L.require_cuda(p)
             assert p.dtype == torch.float32 and p.is_contiguous(), "ClipAdamW needs contiguous fp32 parameters"
@@ -71,10 +79,13 @@ class ClipAdamW(torch.optim.Optimizer):
         g = self.param_groups[0]
         for group in self.param_groups:
             for p in group["params"]:
-                i = next(j for j, q in enumerate(self._params) if q is p)
+                i = self._index[id(p)]
                 off, k = self._slices[i]
                 L.check(self.lib.ta_adamw_clip_step(
                     L.ptr(p), L.ptr(self.flat_grad[off: off + k]), L.ptr(self.m[off: off + k]), L.ptr(self.v[off: off + k]), k,
                     group["lr"], group["betas"][0], group["betas"][1], group["eps"], group["weight_decay"], self.step_count,
                     self.max_grad_norm, L.ptr(self.gnorm_sq), st))
+                # the kernel writes through the raw pointer: tell autograd (and ASRModel's operand-refresh check, which keys on
+                # the parameters' version counters) that the tensor changed
+                torch.autograd.graph.increment_version(p)
         return None

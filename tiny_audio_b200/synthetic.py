@@ -89,7 +89,7 @@ class StubTokenizer:
 
 def build_offline_model(dims: PathDims, device="cuda", seed: int = 1234, enc_state=None, lm_state=None, proj_state=None,
                         audio_token_dropout: float = 0.0, projector_type: str = "mlp", use_lora: bool = False,
-                        freeze_projector: bool = False):
+                        freeze_projector: bool = False, freeze_language_model: bool = True):
     """ASRModel (tiny_audio_b200.asr_modeling) with GLM-ASR / Qwen3 modules of the given dims, random (seeded) or
     supplied weights, fp32 masters -- no network, no checkpoints."""
     from transformers import GlmAsrEncoderConfig, Qwen3Config, Qwen3ForCausalLM
@@ -129,8 +129,9 @@ def build_offline_model(dims: PathDims, device="cuda", seed: int = 1234, enc_sta
             if lm_state is not None:
                 m.load_state_dict(lm_state, strict=True)
                 m.tie_weights()
-            m.requires_grad_(False)
-            m.train(False)
+            if getattr(config, "freeze_language_model", True):
+                m.requires_grad_(False)
+                m.train(False)
             return m
 
         def _init_tokenizer(self, config):
@@ -143,7 +144,8 @@ def build_offline_model(dims: PathDims, device="cuda", seed: int = 1234, enc_sta
     _Offline.__name__ = "ASRModel"
     cfg = ASRConfig(audio_config=enc_cfg, text_config=txt_cfg, model_dtype="float32", attn_implementation="sdpa",
                     projector_type=projector_type, projector_pool_stride=dims.proj_k, projector_hidden_dim=dims.proj_hidden,
-                    audio_token_dropout=audio_token_dropout, use_lora=use_lora, freeze_projector=freeze_projector)
+                    audio_token_dropout=audio_token_dropout, use_lora=use_lora, freeze_projector=freeze_projector,
+                    freeze_language_model=freeze_language_model)
     torch.manual_seed(seed + 3)
     model = _Offline(cfg)
     if proj_state is not None:
