@@ -49,5 +49,80 @@ if "attn_lm" in which:
         L.check(lib.ta_attn_bwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), L.ptr(do), L.ptr(lse), L.ptr(dsum), L.ptr(dq), L.ptr(dk),
                                 L.ptr(dv), B, S, Hq, Hkv, hd, Hq * hd, Hkv * hd, Hkv * hd, Hq * hd, Hq * hd, Hq * hd, Hkv * hd,
                                 Hkv * hd, 1, hd ** -0.5, L.stream_ptr()))
+
+# ---- HBM-bound kernels at production shapes (run with:  python tools/prof_kernels.py hbm) ----
+if "hbm" in which:
+    import ctypes as C
+    from tiny_audio_b200.engine import FusedClipAdamW
+    torch.manual_seed(0)
+    # log-mel: 32 x 30 s clips
+    B, Ls = 32, 480000
+    wave = 0.1 * torch.randn(B, Ls, device=dev)
+    n = C.c_longlong()
+    L.check(lib.ta_logmel_workspace_floats(B, Ls, C.byref(n)))
+    ws = torch.empty(n.value, device=dev, dtype=F32)
+    im2 = torch.empty(B * (Ls // 160), 384, device=dev, dtype=BF16)
+    for _ in range(2):
+        L.check(lib.ta_logmel_fwd(L.ptr(wave), wave.stride(0), B, Ls, L.ptr(ws), None, L.ptr(im2), L.stream_ptr()))
+    # encoder LayerNorm: 48000 x 1280 bf16
+    rows, D = 48000, 1280
+    x = torch.randn(rows, D, device=dev, dtype=BF16)
+    w = torch.ones(D, device=dev, dtype=F32)
+    y = torch.empty_like(x)
+    for _ in range(2):
+        L.check(lib.ta_layernorm_bf16(L.ptr(x), L.ptr(w), L.ptr(w), L.ptr(y), rows, D, 1e-5, L.stream_ptr()))
+    # decoder RMSNorm fwd / bwd: 14848 x 1024 fp32 residual stream
+    rows, D = 14848, 1024
+    xf = torch.randn(rows, D, device=dev, dtype=F32)
+    w1 = torch.ones(D, device=dev, dtype=F32)
+    yb = torch.empty(rows, D, device=dev, dtype=BF16)
+    dx = torch.zeros(rows, D, device=dev, dtype=F32)
+    dw = torch.zeros(D, device=dev, dtype=F32)
+    for _ in range(2):
+        L.check(lib.ta_rmsnorm_f32(L.ptr(xf), L.ptr(w1), L.ptr(yb), None, rows, D, 1e-6, L.stream_ptr()))
+        L.check(lib.ta_rmsnorm_f32_bwd(L.ptr(yb), L.ptr(xf), L.ptr(w1), L.ptr(dx), None, rows, D, 1e-6, 1, L.stream_ptr()))
+        L.check(lib.ta_rmsnorm_dw(L.ptr(yb), L.ptr(xf), None, rows, D, 1e-6, L.ptr(dw), L.stream_ptr()))
+    # CE on the labelled rows: 2080 x 152064 bf16 logits
+    R, V, Vp = 2080, 151936, 152064
+    lg = torch.randn(R, Vp, device=dev, dtype=BF16)
+    tg = torch.randint(0, V, (R,), device=dev, dtype=torch.int32)
+    loss = torch.zeros(1, device=dev, dtype=F32)
+    for _ in range(2):
+        L.check(lib.ta_ce_fwd_bwd(L.ptr(lg), Vp, L.ptr(tg), R, V, Vp, 1.0 / R, L.ptr(loss), None, 1, L.stream_ptr()))
+    # clip + AdamW over the 12.6 M projector parameters (H = 2048)
+    ps = [torch.randn(2048, 5120, device=dev), torch.randn(1024, 2048, device=dev)]
+    opt = FusedClipAdamW(ps, lr=1e-3)
+    gs = [torch.randn_like(p) for p in ps]
+    for _ in range(2):
+        opt.step(gs)
+if "decode" in which:
+    # decode-path kernels: tied lm_head for 32 sequences (HBM-bound weight stream), gate/up SwiGLU, split-K o_proj, attention over 433 cached keys
+    M = 32
+    xn = torch.randn(M, 1024, device=dev, dtype=BF16)
+    emb = torch.randn(152064, 1024, device=dev, dtype=BF16) * 0.03
+    logits = torch.empty(M, 152064, device=dev, dtype=BF16)
+    wgu = torch.randn(6144, 1024, device=dev, dtype=BF16) * 0.03
+    h = torch.empty(M, 3072, device=dev, dtype=BF16)
+    wo = torch.randn(1024, 2048, device=dev, dtype=BF16) * 0.03
+    att = torch.randn(M, 2048, device=dev, dtype=BF16)
+    part = torch.empty(4, M, 1024, device=dev, dtype=F32)
+    Hq, Hkv, hd, n_keys = 16, 8, 128, 433
+    q = torch.randn(M, Hq * hd, device=dev, dtype=BF16)
+    kc = torch.randn(M, 512, Hkv * hd, device=dev, dtype=BF16)
+    vc = torch.randn(M, 512, Hkv * hd, device=dev, dtype=BF16)
+    o = torch.empty(M, Hq * hd, device=dev, dtype=BF16)
+    pos = torch.tensor([n_keys - 1], device=dev, dtype=torch.int32)
+    for _ in range(2):
+        L.check(lib.ta_skinny_gemm_bf16(L.ptr(xn), 1024, L.ptr(emb), 1024, M, 152064, 1024, L.SKINNY_BF16, L.ptr(logits), 152064, None, 1, L.stream_ptr()))
+        L.check(lib.ta_skinny_gemm_bf16(L.ptr(xn), 1024, L.ptr(wgu), 1024, M, 6144, 1024, L.SKINNY_SWIGLU, L.ptr(h), 3072, None, 1, L.stream_ptr()))
+        L.check(lib.ta_skinny_gemm_bf16(L.ptr(att), 2048, L.ptr(wo), 2048, M, 1024, 2048, L.SKINNY_PARTIAL, L.ptr(part), 1024, None, 4, L.stream_ptr()))
+        L.check(lib.ta_decode_attn(L.ptr(q), L.ptr(kc), L.ptr(vc), L.ptr(o), Hq * hd, L.ptr(pos), M, Hq, Hkv, 512, hd ** -0.5, L.stream_ptr()))
+if "wgrad" in which:
+    # weight-gradient GEMM (TN form): d(W_gate_up) [6144, 1024] = dY^T X over 14848 tokens
+    dy = torch.randn(14848, 6144, device=dev, dtype=BF16)
+    xx = torch.randn(14848, 1024, device=dev, dtype=BF16)
+    out = torch.empty(6144, 1024, device=dev, dtype=F32)
+    for _ in range(3):
+        L.gemm_tn(dy, xx, out=out)
 torch.cuda.synchronize()
 print("done")
