@@ -31,14 +31,15 @@ def _worker(rank, world, port, out):
     keys = ("waveform", "input_ids", "labels", "attention_mask", "audio_token_counts", "sample_lengths")
     mine = dp.shard_batch({k: full[k] for k in keys}, rank, world)
     n_global = dp.global_num_items(mine["labels"])
-    res = po.train_step(W, mine, cfg, num_items_in_batch=n_global)
-    flat = torch.cat([g.reshape(-1) for g in res["grads"].values()])
+    res = po.train_step(W, mine, cfg, num_items_in_batch=n_global, train_lm=True)
+    # one flat buffer: projector gradients followed by every decoder gradient (the unfrozen recipe all-reduces both at once)
+    flat = torch.cat([g.reshape(-1) for g in res["grads"].values()] + [res["lm_grads"][k].reshape(-1) for k in sorted(res["lm_grads"])])
     dp.allreduce_flat_(flat)
     loss = res["loss"].clone()
     dist.all_reduce(loss)
     if rank == 0:
-        ref = po.train_step(W, {k: full[k] for k in keys}, cfg, num_items_in_batch=int((full["labels"] != -100).sum()))
-        flat_ref = torch.cat([g.reshape(-1) for g in ref["grads"].values()])
+        ref = po.train_step(W, {k: full[k] for k in keys}, cfg, num_items_in_batch=int((full["labels"] != -100).sum()), train_lm=True)
+        flat_ref = torch.cat([g.reshape(-1) for g in ref["grads"].values()] + [ref["lm_grads"][k].reshape(-1) for k in sorted(ref["lm_grads"])])
         out.put((n_global, int((full["labels"] != -100).sum()), float(loss), float(ref["loss"]),
                  float((flat - flat_ref).norm() / flat_ref.norm())))
     dist.destroy_process_group()
