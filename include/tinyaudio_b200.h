@@ -92,7 +92,8 @@ int ta_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
                 void* stream);
 int ta_debug_set(int key, int value); /* profiling experiments only; never changes results when left at 0 */
 int ta_attn_set_tc(int mode); /* 0: mma.sync kernels; 1: tcgen05, two threads per query row; 2 (default): tcgen05, head_dim-64 forward with one
-                                 thread per row (attn_tc.cu); 3 / 4: mode 2 with every 4th / 2nd exp2 evaluated on the FMA pipe (experiment) */
+                                 thread per row (attn_tc.cu); 3 / 4: mode 2 with every 4th / 2nd exp2 evaluated on the FMA pipe (experiment);
+                                 5: head_dim-64 forward as two independent 64-key streams per row (split-KV inside the CTA, 8 softmax warps) */
 int ta_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                 float* dsum_ws, float* dq_acc, void* dk, void* dv, int B, int S, int Hq, int Hkv, int head_dim,
                 long long q_rs, long long k_rs, long long v_rs, long long o_rs, long long do_rs, long long dq_rs,

@@ -606,6 +606,277 @@ int launch_attn_tc1(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant 3 (encoder shape, head_dim 64, non-causal): two threads per query row that never talk inside the loop.
+//   Thread `half` of a row owns key columns [64 half, 64 half + 64) of every 128-key tile as an independent KV stream: its own
+//   running reference max / sum and its OWN output accumulator in TMEM (O_a at columns [128,192), O_b at [192,256)), i.e. a
+//   split-KV (flash-decoding style) decomposition inside the CTA.  The PV product of a tile is issued as two K = 64 groups, one
+//   per accumulator.  The two streams are merged once, after the last tile.  Compared with variant 1 there is no per-tile row-max
+//   exchange (bar.sync) and compared with variant 2 each thread keeps 64 instead of 128 scores in registers, so 8 softmax warps
+//   per CTA x 2 CTAs = 4 warps per SM sub-partition hide the TMEM-load / barrier / MUFU latencies (tools/ubench/sfu2.cu: the
+//   softmax instruction mix needs > 2 warps per sub-partition to approach the 16 exp2/clk/SM ceiling).
+//   warps 0-7 softmax (q = warp & 3 = TMEM lane quadrant, half = warp >> 2), warp 8 TMA producer + TMEM allocator, warp 9 MMA.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int ATT2_THREADS = 320;
+
+template <int HD>
+__global__ void __launch_bounds__(ATT2_THREADS, 2)
+attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int Hq, int Hkv,
+                    long long o_rs, float scale_log2) {
+    static_assert(HD == 64, "variant 3 is the encoder shape");
+    using C = Att1Cfg<HD>;
+    extern __shared__ __align__(1024) uint8_t smem_al[];
+    uint8_t* smem = smem_al;
+    if (smem_u32(smem) & 1023u) __trap();                 // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* sQ = smem;
+    uint8_t* sKV = smem + C::TILE_BYTES;
+    uint8_t* sP = smem + C::TILE_BYTES * (1 + C::KV_SLOTS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = bars + 1 + C::KV_SLOTS;
+    uint64_t* s_full = bars + 1 + 2 * C::KV_SLOTS;
+    uint64_t* s_empty = s_full + 1;
+    uint64_t* p_full = s_full + 2;
+    uint64_t* pv_done = s_full + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int hk = h / (Hq / Hkv);
+    const int q0 = qt * BQ;
+    const int n_kv = (S + BKV - 1) / BKV;
+    const int row_base = b * S;
+    constexpr uint32_t OA_COL = 128, OB_COL = 192;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+            mbar_init(q_full, 1);
+            for (int s = 0; s < C::KV_SLOTS; ++s) {
+                mbar_init(&kv_full[s], 1);
+                mbar_init(&kv_empty[s], 1);
+            }
+            mbar_init(s_full, 1);
+            mbar_init(s_empty, 8);
+            mbar_init(p_full, 8);
+            mbar_init(pv_done, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc<TMEM_COLS_ATT>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, C::TILE_BYTES);
+            tma_load_2d(sQ, &tmQ, q_full, h * HD, row_base + q0);
+            for (int i = 0; i < 2 * n_kv; ++i) {
+                const int slot = i % C::KV_SLOTS;
+                const uint32_t ph = (uint32_t)(i / C::KV_SLOTS) & 1u;
+                mbar_wait(&kv_empty[slot], ph ^ 1);
+                mbar_arrive_expect_tx(&kv_full[slot], C::TILE_BYTES);
+                tma_load_2d(sKV + slot * C::TILE_BYTES, (i & 1) ? &tmV : &tmK, &kv_full[slot], hk * HD, row_base + (i >> 1) * BKV);
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
+            constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
+            const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+            auto issue_s = [&](int j) {
+                const int i = 2 * j, slot = i % C::KV_SLOTS;
+                mbar_wait(&kv_full[slot], (uint32_t)(i / C::KV_SLOTS) & 1u);
+                mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sKV + slot * C::TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_f16(tmem_base + S_COL, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s,
+                             k != 0 ? 1u : 0u);
+                umma_commit(s_full);
+                umma_commit(&kv_empty[slot]);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) issue_s(j + 1);
+                const int i = 2 * j + 1, slot = i % C::KV_SLOTS;
+                mbar_wait(p_full, (uint32_t)j & 1u);
+                mbar_wait(&kv_full[slot], (uint32_t)(i / C::KV_SLOTS) & 1u);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(sKV + slot * C::TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {      // keys [0,64) -> O_a, keys [64,128) -> O_b
+                    const uint32_t pa = p_addr + (k >> 2) * TILE16 + (k & 3) * 32;
+                    umma_f16(tmem_base + ((k < 4) ? OA_COL : OB_COL), umma_desc_sw128_kmajor(pa),
+                             umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16), idesc_o, (j | (k & 3)) != 0 ? 1u : 0u);
+                }
+                umma_commit(pv_done);
+                umma_commit(&kv_empty[slot]);
+            }
+        }
+    } else {
+        const int q = warp & 3, half = warp >> 2;
+        const int r = q * 32 + lane;                        // query row of the tile = TMEM lane
+        const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + S_COL + (uint32_t)(half * 64);
+        const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + (half ? OB_COL : OA_COL);
+        float m_ref = -INFINITY, l_sum = 0.f;
+        uint8_t* p_row = sP + half * TILE16 + r * 128;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(s_full, (uint32_t)j & 1u);
+            tc_fence_after();
+            const int lim = min(S - j * BKV - half * 64 - 1, 63);       // my columns e = 0..63 are real keys iff e <= lim
+            uint32_t v[2][32];
+            tmem_ld_32x32(t_s, v[0]);
+            tmem_ld_32x32(t_s + 32, v[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);            // S_j is in registers: the MMA warp may issue S_{j+1} now
+            if (lim < 63) {                                 // only the last tile(s): warp-uniform
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i > lim) v[c][i] = 0xff800000u;      // -inf
+            }
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[c][i]));
+            const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
+            // a stream whose keys are all masked so far keeps m_ref = -inf; exp2(-inf - (-inf)) must not happen: use 0 as reference
+            const bool grow = mx > m_ref + 8.0f;
+            const float m_new = grow ? mx : m_ref;
+            const float alpha = (grow && m_ref != -INFINITY) ? ex2_approx(m_ref - m_new) : 1.0f;
+            m_ref = m_new;
+            if (j > 0) {
+                mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);     // PV_{j-1} has consumed sP and finished updating O_a / O_b
+                tc_fence_after();
+            }
+            float l4[4] = {0.f, 0.f, 0.f, 0.f};
+            const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    float e[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        e[t] = ex2_approx(fmaf(__uint_as_float(v[c][8 * qd + t]), scale_log2, neg_m));     // exp2(-inf) = 0 when masked
+                        l4[t & 3] += e[t];
+                    }
+                    uint4 u;
+                    u.x = pack_bf16x2(e[0], e[1]);
+                    u.y = pack_bf16x2(e[2], e[3]);
+                    u.z = pack_bf16x2(e[4], e[5]);
+                    u.w = pack_bf16x2(e[6], e[7]);
+                    const int k16 = c * 4 + qd;                           // 16-byte chunk of my 128-byte half row
+                    *reinterpret_cast<uint4*>(p_row + ((k16 ^ (r & 7)) << 4)) = u;
+                }
+            }
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {                 // lazy rescale of my accumulator (rare)
+#pragma unroll 1
+                for (int c = 0; c < HD / 32; ++c) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(t_o + c * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st_32x32(t_o + c * 32, o);
+                }
+                tmem_st_wait();
+                l_sum *= alpha;
+            }
+            l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(pv_done, (uint32_t)(n_kv - 1) & 1u);
+        tc_fence_after();
+        // ---- merge the two KV streams of each row: stream b hands (m, l, O_b) to stream a through shared memory (sP is free now) ----
+        float* xO = reinterpret_cast<float*>(sP);               // [64 cols][128 rows] fp32 = 32 KB, column-major: conflict free
+        float* xML = reinterpret_cast<float*>(sQ);              // [2][128]  (Q is dead: every S has been issued and completed)
+        const uint32_t pair_bar = 1 + q;                        // named barrier per lane quadrant: warps q and q + 4
+        if (half == 1) {
+#pragma unroll 1
+            for (int c = 0; c < HD / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld_32x32(t_o + c * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xO[(c * 32 + i) * 128 + r] = __uint_as_float(o[i]);
+            }
+            xML[r] = m_ref;
+            xML[128 + r] = l_sum;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        } else {
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            const float m_b = xML[r], l_b = xML[128 + r];
+            const float m = fmaxf(m_ref, m_b);                  // stream a always has real keys (S >= 1), so m is finite
+            const float wa = ex2_approx(m_ref - m), wb = (m_b == -INFINITY) ? 0.f : ex2_approx(m_b - m);
+            const float l_tot = l_sum * wa + l_b * wb;
+            const float inv = 1.0f / l_tot;
+            const int row = q0 + r;
+            bf16* orow = O + ((long long)row_base + row) * o_rs + (long long)h * HD;
+#pragma unroll 1
+            for (int c = 0; c < HD / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld_32x32(t_o + c * 32, o);
+                tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(o[i]) * wa + xO[(c * 32 + i) * 128 + r] * wb) * inv;
+                if (row < S) {
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        uint4 u;
+                        u.x = pack_bf16x2(f[8 * qd + 0], f[8 * qd + 1]);
+                        u.y = pack_bf16x2(f[8 * qd + 2], f[8 * qd + 3]);
+                        u.z = pack_bf16x2(f[8 * qd + 4], f[8 * qd + 5]);
+                        u.w = pack_bf16x2(f[8 * qd + 6], f[8 * qd + 7]);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + qd * 8) = u;
+                    }
+                }
+            }
+            if (LSE && row < S) LSE[((long long)b * Hq + h) * S + row] = (m + log2f(l_tot)) * 0.69314718055994531f;
+        }
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<TMEM_COLS_ATT>(tmem_base);
+}
+
+template <int HD>
+int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* o, float* lse, int B, int S, int Hq,
+                    int Hkv, long long o_rs, float scale, cudaStream_t st) {
+    using C = Att1Cfg<HD>;
+    auto kern = attn_tc_fwd2_kernel<HD>;
+    static bool done = false;
+    if (!done) {
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        done = true;
+    }
+    dim3 grid((S + BQ - 1) / BQ, Hq, B);
+    kern<<<grid, ATT2_THREADS, C::SMEM, st>>>(tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f);
+    TA_LAUNCH_CHECK();
+    return 0;
+}
+
 // 0: mma.sync; 1: tcgen05, 2 threads per row everywhere; 2 (default): head_dim-64 non-causal runs the one-thread-per-row variant
 // (0.590 vs 0.632 ms per encoder layer at B=32, S=1500); 3 / 4: that variant with every 4th / 2nd exp2 on the FMA pipe -- slower
 // (0.68 / 0.75 ms): with two softmax warps per sub-partition the kernel is issue/latency-bound, not MUFU-bound (profiles/).
@@ -614,7 +885,7 @@ int g_attn_tc = 2;
 }  // namespace
 
 TA_API int ta_attn_set_tc(int on) {
-    g_attn_tc = (on < 0 || on > 4) ? 2 : on;
+    g_attn_tc = (on < 0 || on > 5) ? 2 : on;
     return 0;
 }
 int k_attn_tc_enabled() { return g_attn_tc; }
@@ -638,6 +909,7 @@ int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* l
     if (rc) return rc;
     *handled = 1;
     if (head_dim == 64 && !causal && g_attn_tc >= 2) {
+        if (g_attn_tc == 5) return launch_attn_tc2<64>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 2) return launch_attn_tc1<64, false, 0>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 3) return launch_attn_tc1<64, false, 4>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         return launch_attn_tc1<64, false, 2>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);

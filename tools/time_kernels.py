@@ -57,7 +57,7 @@ lib.ta_gemm_set_cta_pair(1)
 B, S, H, hd = 32, 1500, 20, 64
 qkv = torch.randn(B, S, 3 * H * hd, device=dev, dtype=BF16)
 o = torch.empty(B, S, H * hd, device=dev, dtype=BF16)
-for tc in (0, 1, 2, 3, 4):
+for tc in (0, 1, 2, 3, 4, 5):
     lib.ta_attn_set_tc(tc)
     t = timeit(lambda: L.check(lib.ta_attn_fwd(L.ptr(qkv), L.ptr(qkv[:, :, H * hd:]), L.ptr(qkv[:, :, 2 * H * hd:]), L.ptr(o), None, B, S, H,
                                                H, hd, 3 * H * hd, 3 * H * hd, 3 * H * hd, H * hd, 0, hd ** -0.5, L.stream_ptr())), reps=5)
