@@ -448,3 +448,53 @@ def test_unfrozen_lm_through_public_surface_and_optimizer(cuda):
     fresh.train()
     loss3 = float(_model_step(fresh, batch, n_items))
     assert abs(loss2 - loss3) < 2e-6 * abs(loss3) and abs(loss2 - float(out.loss)) > 1e-5
+
+
+def test_generate_public_surface_builds_prompt_and_supports_qformer(cuda):
+    """ASRModel.generate: (a) with explicit prompt ids == HotPath.greedy_generate; (b) without input_ids the prompt is built from the
+    tokenizer's chat template with N_a <audio> placeholders like the reference (asr_modeling.py:588-617) and gives the same ids;
+    (c) a non-MLP projector (qformer) goes encoder -> projector module -> CUDA decoder."""
+    from tiny_audio_b200.synthetic import StubTokenizer, build_offline_model
+    from tiny_audio_b200 import synthetic as syn
+    cfg = po.small_config(enc_layers=1, lm_layers=2)
+    dims = PathDims.from_any(cfg.to_dict())
+    W = po.init_weights(cfg, seed=9, emb_std=0.04)
+    batch = po.synthetic_batch(cfg, 2, 1.0, seed=9, response_len=2)
+    prompt = batch["input_ids"][:, : int((batch["labels"][0] != -100).nonzero().min())]
+    model = build_offline_model(dims, device="cuda", enc_state=W["encoder"], lm_state=W["lm"], proj_state=W["projector"])
+    model.eval()
+    T = 5
+    a = model.generate(input_ids=prompt.cuda(), input_features=batch["waveform"].cuda(), max_new_tokens=T).cpu()
+    hp = model._hot_path()
+    params = {k: v.clone().cuda().contiguous() for k, v in W["projector"].items()}
+    eos = model.generation_config.eos_token_id
+    eos = list(eos) if isinstance(eos, (list, tuple)) else [eos]
+    ref = hp.greedy_generate(input_ids=prompt.cuda(), proj_params=params, waveform=batch["waveform"].cuda(), max_new_tokens=T,
+                             eos_token_ids=eos, pad_token_id=int(model.generation_config.pad_token_id or 0)).cpu()
+    assert torch.equal(a, ref) and a.shape[0] == 2 and 1 <= a.shape[1] <= T
+
+    class ChatTok(StubTokenizer):
+        def apply_chat_template(self, messages, tokenize=True, add_generation_prompt=True, return_tensors="pt", enable_thinking=False):
+            assert tokenize and add_generation_prompt and enable_thinking is False and messages[-1]["role"] == "user"
+            content = messages[-1]["content"]
+            n = content.count("<audio>")
+            assert content == "<audio>" * n + " Transcribe the speech to text"
+            return prompt[:1].clone() if n == int(batch["audio_token_counts"][0]) else None
+
+    model.tokenizer = ChatTok(dims.vocab, dims.audio_token_id)
+    L_samples = int(batch["sample_lengths"][0])
+    frame_mask = torch.ones(2, L_samples // 160, dtype=torch.int64)
+    b = model.generate(input_features=batch["waveform"].cuda(), audio_attention_mask=frame_mask, max_new_tokens=T).cpu()
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        model.generate(input_features=batch["waveform"].cuda(), max_new_tokens=T)
+    # (c) QFormer projector
+    Wq = po.init_weights(cfg, seed=15)
+    Wq["projector"] = po.init_qformer_weights(cfg, seed=1015)
+    qb = po.synthetic_batch(cfg, 2, 2.0, seed=15, response_len=2, projector="qformer")
+    qprompt = qb["input_ids"][:, : int((qb["labels"][0] != -100).nonzero().min())]
+    qm = build_offline_model(dims, device="cuda", enc_state=Wq["encoder"], lm_state=Wq["lm"], proj_state=Wq["projector"],
+                             projector_type="qformer")
+    qm.eval()
+    out = qm.generate(input_ids=qprompt.cuda(), input_features=qb["waveform"].cuda(), max_new_tokens=3)
+    assert out.shape[0] == 2 and 1 <= out.shape[1] <= 3 and out.dtype == torch.int64

@@ -412,19 +412,49 @@ class ASRModel(PreTrainedModel, GenerationMixin):
                  audio_attention_mask: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
                  audio_token_counts: Optional[torch.Tensor] = None, max_new_tokens: Optional[int] = None, **kwargs) -> torch.Tensor:
         """Greedy transcription ids (reference: asr_modeling.py:562-646 with num_beams=1, do_sample=False).  Returns only the
-        newly generated tokens, like the reference (it strips the prompt, :644-646).  `input_ids` must hold the prompt with
-        its <audio> placeholders (the reference builds it from the tokenizer's chat template when it is None; that needs a
-        real tokenizer and is left to ASRProcessor)."""
-        if input_ids is None or input_features is None:
-            raise NotImplementedError("generate() needs input_ids (prompt with <audio> placeholders) and input_features")
+        newly generated tokens, like the reference (it strips the prompt, :644-646).  `input_ids` holds the prompt with its <audio>
+        placeholders; when it is None the prompt is built from the tokenizer's chat template exactly as the reference does
+        (:588-617; needs `audio_attention_mask` to size the placeholder run)."""
+        if input_features is None:
+            raise ValueError("input_features required for generation")
+        if input_ids is None:
+            # build the prompt like the reference (asr_modeling.py:588-617): N_a <audio> placeholders + the transcribe instruction
+            # through the tokenizer's chat template (thinking mode off), one prompt shared by the whole batch
+            if audio_attention_mask is None:
+                raise ValueError("audio_attention_mask required for generation")
+            if not hasattr(self.tokenizer, "apply_chat_template"):
+                raise NotImplementedError("generate() without input_ids needs a tokenizer with a chat template")
+            n_audio = self._get_num_audio_tokens(audio_attention_mask)
+            system_prompt = kwargs.pop("system_prompt", None) or self.system_prompt
+            messages = []
+            if system_prompt:
+                messages.append({"role": "system", "content": system_prompt})
+            content = "<audio>" * n_audio
+            if self.TRANSCRIBE_PROMPT:
+                content += " " + self.TRANSCRIBE_PROMPT
+            messages.append({"role": "user", "content": content})
+            chat = self.tokenizer.apply_chat_template(messages, tokenize=True, add_generation_prompt=True, return_tensors="pt",
+                                                      enable_thinking=False)
+            input_ids = chat.input_ids if hasattr(chat, "input_ids") else chat
+            input_ids = torch.as_tensor(input_ids)
+            if input_ids.dim() == 1:
+                input_ids = input_ids.unsqueeze(0)
+            if input_ids.shape[0] == 1 and input_features.shape[0] > 1:
+                input_ids = input_ids.expand(input_features.shape[0], -1)
+        kwargs.pop("system_prompt", None)
         if kwargs.get("num_beams", 1) != 1 or kwargs.get("do_sample", False):
             raise NotImplementedError("only greedy decoding is implemented on the B200 path")
         hot = self._hot_path()
         feats = input_features.to(hot.device)
         pr = self.projector
-        params = {k: p.detach().float().contiguous() for k, p in zip(_PROJ_KEYS, (pr.linear_1.weight, pr.norm.weight,
-                                                                               pr.linear_2.weight, pr.norm_2.weight))}
         kw = dict(waveform=feats.float().contiguous()) if feats.dim() == 2 else dict(input_features=feats)
+        from .projectors import MLPAudioProjector
+        if isinstance(pr, MLPAudioProjector):
+            params = {k: p.detach().float().contiguous() for k, p in zip(_PROJ_KEYS, (pr.linear_1.weight, pr.norm.weight,
+                                                                                   pr.linear_2.weight, pr.norm_2.weight))}
+        else:       # generic projector (qformer): CUDA encoder -> projector module -> CUDA decoder
+            params = None
+            kw = dict(audio_embeds=pr(hot.encode_audio(**kw).clone()).float())
         gc = self.generation_config
         eos = gc.eos_token_id if isinstance(gc.eos_token_id, (list, tuple)) else [gc.eos_token_id]
         adapters = getattr(self, "lora_adapters", None)

@@ -48,15 +48,19 @@ constexpr int SK_SMEM = SK_STAGES * SK_STAGE_BYTES;
 // in flight, across item boundaries and -- the weights being frozen -- already before the PDL wait.  When one step covers
 // the whole contraction (K <= 1024, no split) the token fragments are loaded once per CTA and stay in registers.
 //   SK_PARTIAL: out = fp32 [k_splits, M, ldo] raw partial sums (reduced in fixed order by decode_resid_rmsnorm_kernel).
-template <int TT, int EPI>
+//   SIMPLE (K == 1024, no split): one pipeline step per tile and every chunk valid -- the item / tile index arithmetic, its integer
+//   divisions and all per-chunk predicates fold away at compile time (ncu: the general form executed 555 instructions per warp
+//   and tile, most of them this bookkeeping, and was issue-bound at 2.75 TB/s on the lm_head).
+template <int TT, int EPI, bool SIMPLE>
 __global__ void __launch_bounds__(SK_WARPS * 32)
 skinny_gemm_kernel(const bf16* __restrict__ X, long long ldx, const bf16* __restrict__ W, long long ldw, int M, int n_tiles, int K,
-                   int k_splits, void* __restrict__ out, long long ldo, const float* __restrict__ resid) {
+                   int k_splits_rt, void* __restrict__ out, long long ldo, const float* __restrict__ resid) {
     __shared__ float red[SK_WARPS][SK_ROWS][TT * 8 + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int cps = (K >> 5) / k_splits;                       // chunks per split
-    const int gpi = (cps + SK_GROUP - 1) / SK_GROUP;           // pipeline steps per item
+    const int k_splits = SIMPLE ? 1 : k_splits_rt;
+    const int cps = SIMPLE ? SK_GROUP : (K >> 5) / k_splits;   // chunks per split
+    const int gpi = SIMPLE ? 1 : (cps + SK_GROUP - 1) / SK_GROUP;   // pipeline steps per item
     const int n_items = n_tiles * k_splits;
     const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_steps = my_items * gpi;
@@ -87,7 +91,7 @@ skinny_gemm_kernel(const bf16* __restrict__ X, long long ldx, const bf16* __rest
 #pragma unroll
             for (int u = 0; u < SK_UNROLL; ++u) {
                 const int c = c0 + u * SK_WARPS;
-                if (c < c_end) {
+                if (SIMPLE || c < c_end) {
                     cp_async16(slot + (2 * u) * (SK_WARPS * 32), w_lo + c * 32, true);
                     cp_async16(slot + (2 * u + 1) * (SK_WARPS * 32), w_hi + c * 32, true);
                 }
@@ -103,7 +107,7 @@ skinny_gemm_kernel(const bf16* __restrict__ X, long long ldx, const bf16* __rest
 #pragma unroll
         for (int u = 0; u < SK_UNROLL; ++u) {
             const int c = c0 + u * SK_WARPS;
-            if (c < c_end) {
+            if (SIMPLE || c < c_end) {
 #pragma unroll
                 for (int j = 0; j < TT; ++j) xa[u][j] = *reinterpret_cast<const uint4*>(x_row[j] + c * 32);
             }
@@ -132,7 +136,7 @@ skinny_gemm_kernel(const bf16* __restrict__ X, long long ldx, const bf16* __rest
             const uint4* slot = sk_ring + (step % SK_STAGES) * (2 * SK_UNROLL * SK_WARPS * 32) + threadIdx.x;
 #pragma unroll
             for (int u = 0; u < SK_UNROLL; ++u) {
-                if (c0 + u * SK_WARPS < c_end) {
+                if (SIMPLE || c0 + u * SK_WARPS < c_end) {
                     ca[u] = slot[(2 * u) * (SK_WARPS * 32)];
                     cb[u] = slot[(2 * u + 1) * (SK_WARPS * 32)];
                 }
@@ -141,7 +145,7 @@ skinny_gemm_kernel(const bf16* __restrict__ X, long long ldx, const bf16* __rest
         load_w(step + SK_STAGES - 1);                            // refill the slot consumed one step ago
 #pragma unroll
         for (int u = 0; u < SK_UNROLL; ++u) {
-            if (c0 + u * SK_WARPS < c_end) {
+            if (SIMPLE || c0 + u * SK_WARPS < c_end) {
 #pragma unroll
                 for (int j = 0; j < TT; ++j) {
                     mma_bf16_16816(acc[j], ca[u].x, cb[u].x, ca[u].y, cb[u].y, xa[u][j].x, xa[u][j].y);
@@ -198,19 +202,24 @@ int skinny_launch(const bf16* X, long long ldx, const bf16* W, long long ldw, in
     const int n_tiles = N / SK_ROWS;
     const int items = n_tiles * k_splits;
     const int grid = items < 148 ? items : 148;      // one persistent CTA per SM (the ring takes most of its shared memory)
+    const bool simple = (K == 32 * SK_GROUP && k_splits == 1);
     static bool attr_done = false;
     if (!attr_done) {
-        TA_CHECK_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<1, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
-        TA_CHECK_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<2, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
-        TA_CHECK_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<4, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
+#define TA_SK_ATTR(TT_, S_) TA_CHECK_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<TT_, EPI, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM))
+        TA_SK_ATTR(1, false); TA_SK_ATTR(2, false); TA_SK_ATTR(4, false);
+        TA_SK_ATTR(1, true); TA_SK_ATTR(2, true); TA_SK_ATTR(4, true);
+#undef TA_SK_ATTR
         attr_done = true;
     }
-    if (M <= 8)
-        TA_CHECK_CUDA(launch_pdl(skinny_gemm_kernel<1, EPI>, grid, SK_WARPS * 32, SK_SMEM, st, X, ldx, W, ldw, M, n_tiles, K, k_splits, out, ldo, resid));
-    else if (M <= 16)
-        TA_CHECK_CUDA(launch_pdl(skinny_gemm_kernel<2, EPI>, grid, SK_WARPS * 32, SK_SMEM, st, X, ldx, W, ldw, M, n_tiles, K, k_splits, out, ldo, resid));
-    else
-        TA_CHECK_CUDA(launch_pdl(skinny_gemm_kernel<4, EPI>, grid, SK_WARPS * 32, SK_SMEM, st, X, ldx, W, ldw, M, n_tiles, K, k_splits, out, ldo, resid));
+#define TA_SK_LAUNCH(TT_, S_)                                                                                                          \
+    TA_CHECK_CUDA(launch_pdl(skinny_gemm_kernel<TT_, EPI, S_>, grid, SK_WARPS * 32, SK_SMEM, st, X, ldx, W, ldw, M, n_tiles, K, k_splits, out, \
+                             ldo, resid))
+    if (simple) {
+        if (M <= 8) TA_SK_LAUNCH(1, true); else if (M <= 16) TA_SK_LAUNCH(2, true); else TA_SK_LAUNCH(4, true);
+    } else {
+        if (M <= 8) TA_SK_LAUNCH(1, false); else if (M <= 16) TA_SK_LAUNCH(2, false); else TA_SK_LAUNCH(4, false);
+    }
+#undef TA_SK_LAUNCH
     TA_LAUNCH_CHECK();
     return 0;
 }

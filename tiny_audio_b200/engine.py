@@ -621,7 +621,7 @@ class HotPath:
         return audio, n_a
 
     @torch.no_grad()
-    def greedy_generate(self, *, input_ids: torch.Tensor, proj_params, waveform=None, input_features=None,
+    def greedy_generate(self, *, input_ids: torch.Tensor, proj_params=None, waveform=None, input_features=None, audio_embeds=None,
                         audio_token_counts=None, max_new_tokens: int = 16, eos_token_ids=(), pad_token_id: int = 0,
                         use_cache: bool = True, sync_every: int = 8, use_graph: bool = False):
         """Greedy decoding (num_beams=1, do_sample=False: the reference's generation defaults, asr_config.py:103-111).
@@ -634,8 +634,12 @@ class HotPath:
         d = self.dims
         ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
         B = ids.shape[0]
-        audio, n_a = self.audio_embeds(waveform=waveform, input_features=input_features, proj_params=proj_params)
-        audio = audio.clone()
+        if audio_embeds is not None:      # any projector module's output, fp32 [B, n_a, lm_dim] (QFormer: asr_modeling.generate)
+            n_a = int(audio_embeds.shape[1])
+            audio = audio_embeds.detach().to(device=self.device, dtype=F32).contiguous().view(B * n_a, d.lm_dim)
+        else:
+            audio, n_a = self.audio_embeds(waveform=waveform, input_features=input_features, proj_params=proj_params)
+            audio = audio.clone()
         if audio_token_counts is None:
             audio_token_counts = (ids == d.audio_token_id).sum(-1)
         counts = audio_token_counts.to(device=self.device, dtype=torch.int64).contiguous()
