@@ -605,3 +605,48 @@ def test_gemm_tn_weight_gradient_form(cuda, M, N, K):
     via = L.gemm(a_t, b_t, epi=L.EPI_F32, k=K)
     assert rel_err(out, via) < 1e-5
     assert rel_err(L.gemm_tn(at, bt, alpha=0.5), 0.5 * ref) < 1e-3
+
+
+def test_gemm_tail_wave_split(cuda):
+    """Optional tile choice (ta_gemm_set_tail_split): a mostly empty last wave of 256 x 256 tiles is issued as 256 x 128 tiles for the
+    trailing row blocks (two launches).  Every row-indexed epilogue operand must be offset correctly: compare with the unsplit launch."""
+    lib = L.load()
+    M, K = 4864 + 77, 512                      # 20 row blocks x (1024 / 256) = 80 tiles on 74 CTA pairs -> split
+    x = rnd(M, K, seed=1)
+
+    def both(fn):
+        L.check(lib.ta_gemm_set_tail_split(1))
+        c0 = int(lib.ta_launch_count())
+        a = fn()
+        n_split = int(lib.ta_launch_count()) - c0
+        L.check(lib.ta_gemm_set_tail_split(0))
+        c0 = int(lib.ta_launch_count())
+        b = fn()
+        n_plain = int(lib.ta_launch_count()) - c0
+        assert n_split == 2 and n_plain == 1, (n_split, n_plain)
+        return a, b
+
+    w = rnd(1024, K, seed=2, scale=0.05)
+    bias = rnd(1024, seed=3, dtype=F32)
+    a, b = both(lambda: L.gemm(x, w, epi=L.EPI_BF16_GELU, bias=bias))
+    assert torch.equal(a, b) and rel_err(a, F.gelu((x.float() @ w.float().t() + bias).to(BF16).float())) < 6e-3
+    rb = rnd(M, 1024, seed=4)
+    a, b = both(lambda: L.gemm(x, w, epi=L.EPI_BF16_RESID, bias=bias, resid=rb))
+    assert torch.equal(a, b)
+    rf = rnd(M, 1024, seed=5, dtype=F32)
+    a, b = both(lambda: L.gemm(x, w, epi=L.EPI_F32_RESID, resid=rf))
+    assert torch.equal(a, b) and rel_err(a, rf + (x.float() @ w.float().t()).to(BF16).float()) < 1e-3
+    # SwiGLU forward (+ stash) and backward: N = 2048 interleaved rows -> 8 column tiles x 20 row blocks = 160 tiles (2.16 waves)
+    Fd = 1024
+    wgu = rnd(2 * Fd, K, seed=6, scale=0.05)
+    def fwd():
+        gu = torch.empty(M, 2 * Fd, device="cuda", dtype=BF16)
+        h = L.gemm(x, wgu, epi=L.EPI_SWIGLU, out2=gu)
+        return torch.cat([h, gu], 1)
+    a, b = both(fwd)
+    assert torch.equal(a, b)
+    gu = a[:, Fd:].contiguous()
+    dy = rnd(M, 256, seed=7)
+    wd_t = rnd(Fd, 256, seed=8, scale=0.1)
+    a, b = both(lambda: L.gemm(dy, wd_t, epi=L.EPI_SWIGLU_BWD, aux=gu))
+    assert torch.equal(a, b)

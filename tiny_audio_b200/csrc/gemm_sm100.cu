@@ -1054,6 +1054,9 @@ int dispatch_epi2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const C
 }
 
 int g_force_bn = 0;
+int g_tail_split = 0; // 1: split off a poorly filled last wave into 256 x 128 tiles (ta_gemm_set_tail_split).  Off by default: on the
+                      // power-capped B200 the step did not get faster (130.4 vs 129.3 ms) -- SMs idling in a short last wave hand their
+                      // power budget to the busy ones, which then clock higher, so the quantisation loss is mostly virtual here.
 int g_cta_pair = 1;   // 1 (default): CTA-pair kernel (cta_group::2, 256 x N tiles); 0: 1-CTA kernel (cta_group::1)
 
 }  // namespace
@@ -1064,6 +1067,11 @@ TA_API int ta_gemm_set_tile_n(int bn) {
         return -1;
     }
     g_force_bn = bn;
+    return 0;
+}
+
+TA_API int ta_gemm_set_tail_split(int on) {
+    g_tail_split = on ? 1 : 0;
     return 0;
 }
 
@@ -1125,21 +1133,53 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
         }
     }
     if (use_pair) {
-        rc = make_map(&tb, B, N, K, ldb, bn / 2);     // each CTA of the pair loads half of the B tile
-        if (rc) return rc;
-        // output maps for the TMA-store epilogue: [M, width] with 128-byte wide sub-tiles
         const bool f32out = (epi == TA_EPI_F32 || epi == TA_EPI_F32_RESID);
         const long long out_cols = (epi == TA_EPI_SWIGLU) ? N / 2 : (epi == TA_EPI_SWIGLU_BWD) ? 2LL * N : N;
-        CUtensorMap tc, tc2;
-        rc = make_map(&tc, e->out, M, out_cols, e->ldo, BM, f32out);
-        if (rc) return rc;
-        tc2 = tc;
-        if (epi == TA_EPI_SWIGLU && e->out2) {
-            rc = make_map(&tc2, e->out2, M, N, e->ldo2, BM, false);
-            if (rc) return rc;
+        // rows [row0, row0 + rows) of the problem with tile width bnp (all row-indexed epilogue operands are offset accordingly)
+        auto run_rows = [&](long long row0, int rows, int bnp) -> int {
+            EpiArgs e2 = ep;
+            e2.out = reinterpret_cast<uint8_t*>(ep.out) + row0 * ep.ldo * (f32out ? 4 : 2);
+            if (ep.resid) e2.resid = reinterpret_cast<const uint8_t*>(ep.resid) + row0 * ep.ldr * (epi == TA_EPI_F32_RESID ? 4 : 2);
+            if (ep.out2) e2.out2 = reinterpret_cast<uint8_t*>(ep.out2) + row0 * ep.ldo2 * 2;
+            if (ep.aux) e2.aux = ep.aux + row0 * ep.ldaux;
+            CUtensorMap ma, mb, tc, tc2;
+            int r2 = make_map(&ma, reinterpret_cast<const bf16*>(A) + row0 * lda, rows, K, lda, BM);
+            if (r2) return r2;
+            r2 = make_map(&mb, B, N, K, ldb, bnp / 2);     // each CTA of the pair loads half of the B tile
+            if (r2) return r2;
+            // output maps for the TMA-store epilogue: [rows, width] with 128-byte wide sub-tiles
+            r2 = make_map(&tc, e2.out, rows, out_cols, e->ldo, BM, f32out);
+            if (r2) return r2;
+            tc2 = tc;
+            if (epi == TA_EPI_SWIGLU && e->out2) {
+                r2 = make_map(&tc2, e2.out2, rows, N, e->ldo2, BM, false);
+                if (r2) return r2;
+            }
+            if (bnp == 256) return dispatch_epi2<256>(epi, ma, mb, tc, tc2, rows, N, K, e2, st);
+            return dispatch_epi2<128>(epi, ma, mb, tc, tc2, rows, N, K, e2, st);
+        };
+        // Wave quantisation: the persistent kernel runs ceil(tiles / 74 CTA pairs) waves of 256 x 256 tiles.  When the last wave
+        // would be mostly empty (the decoder's N = 1024 products: 232 tiles = 3.14 waves -> 4), the trailing row blocks are
+        // issued as a second launch with 256 x 128 tiles, which fills the SMs with half-cost tiles (3 + ~0.55 instead of 4).
+        if (bn == 256 && !g_force_bn && g_tail_split && epi != TA_EPI_BF16_ROPE) {
+            const int pairs = num_sms() / 2;
+            const int tm = (M + 2 * BM - 1) / (2 * BM), tn = N / 256;
+            const long long tiles = (long long)tm * tn;
+            const long long full = tiles / pairs, rem = tiles % pairs;
+            if (full >= 1 && rem > 0 && rem * 100 < (long long)pairs * 60) {
+                const int m_main = (int)((full * pairs) / tn);          // row blocks that fill `full` waves
+                const int rem_m = tm - m_main;
+                const long long tail_tiles = (long long)rem_m * (N / 128);
+                const double cost_split = (double)((m_main * (long long)tn + pairs - 1) / pairs) + 0.58 * (double)((tail_tiles + pairs - 1) / pairs);
+                if (m_main > 0 && rem_m > 0 && cost_split + 0.15 < (double)(full + 1)) {
+                    const long long rows_main = (long long)m_main * 2 * BM;
+                    rc = run_rows(0, (int)rows_main, 256);
+                    if (rc) return rc;
+                    return run_rows(rows_main, (int)(M - rows_main), 128);
+                }
+            }
         }
-        if (bn == 256) return dispatch_epi2<256>(epi, ta, tb, tc, tc2, M, N, K, ep, st);
-        return dispatch_epi2<128>(epi, ta, tb, tc, tc2, M, N, K, ep, st);
+        return run_rows(0, M, bn);
     }
     rc = make_map(&tb, B, N, K, ldb, bn);
     if (rc) return rc;

@@ -70,6 +70,7 @@ _SIGS = {
     "ta_gemm_bf16_tn": ([P, c_ll, P, c_ll, c_int, c_int, c_int, P, c_ll, c_float, P], c_int),
     "ta_gemm_set_tile_n": ([c_int], c_int),
     "ta_gemm_set_cta_pair": ([c_int], c_int),
+    "ta_gemm_set_tail_split": ([c_int], c_int),
     "ta_logmel_workspace_floats": ([c_int, c_int, C.POINTER(c_ll)], c_int),
     "ta_logmel_fwd": ([P, c_ll, c_int, c_int, P, P, P, P], c_int),
     "ta_mel_to_conv1_im2col": ([P, c_int, c_int, P, P], c_int),
@@ -144,6 +145,8 @@ def load() -> C.CDLL:
     # tuning / A-B switches (both kernels of each pair are parity-tested; defaults are the fast ones)
     if os.environ.get("TA_GEMM_CTA_PAIR") is not None:
         lib.ta_gemm_set_cta_pair(int(os.environ["TA_GEMM_CTA_PAIR"]))
+    if os.environ.get("TA_GEMM_TAIL_SPLIT") is not None:
+        lib.ta_gemm_set_tail_split(int(os.environ["TA_GEMM_TAIL_SPLIT"]))
     if os.environ.get("TA_ATTN_TC") is not None:
         lib.ta_attn_set_tc(int(os.environ["TA_ATTN_TC"]))
     _lib = lib
