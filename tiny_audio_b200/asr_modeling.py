@@ -366,7 +366,7 @@ class ASRModel(PreTrainedModel, GenerationMixin):
         `labels` may live on the host (no device->host sync) or on the device (one sync to build the row list)."""
         if input_ids is None or input_features is None:
             raise NotImplementedError("the B200 hot path covers audio+text batches (input_ids and input_features); "
-                                      "text-only / cached decoding is a 'next' row (DESIGN.md)")
+                                      "text-only batches are outside the hot path; cached decoding goes through generate()")
         if past_key_values is not None or inputs_embeds is not None:
             raise NotImplementedError("past_key_values / inputs_embeds are not supported on the training hot path")
         hot = self._hot_path()
