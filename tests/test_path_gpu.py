@@ -498,3 +498,66 @@ def test_generate_public_surface_builds_prompt_and_supports_qformer(cuda):
     qm.eval()
     out = qm.generate(input_ids=qprompt.cuda(), input_features=qb["waveform"].cuda(), max_new_tokens=3)
     assert out.shape[0] == 2 and 1 <= out.shape[1] <= 3 and out.dtype == torch.int64
+
+
+def test_full_size_model_loss_vs_reference_fixture(cuda):
+    """The BASELINE metric's parity half at FULL model size (32-layer GLM-ASR encoder + 28-layer Qwen3-0.6B, vocabulary 151 936):
+    CE loss of the bf16 CUDA path against the unmodified fp32 reference (tests/golden/full_b1_4s.npz: 1 x 4 s clip), plus the
+    projector-gradient sub-samples of the same fixture.  Target (north star): |delta loss| <= 1e-3."""
+    from oracle.make_golden import CASES
+    spec, B, clip_s, pad_s, R, seed = CASES["full_b1_4s"]
+    cfg = po.FULL
+    fx = np.load(os.path.join(GOLD, "full_b1_4s.npz"))
+    W, hp = build(cfg, seed)
+    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s)
+    batch["input_ids"] = torch.from_numpy(fx["input_ids"])
+    batch["labels"] = torch.from_numpy(fx["labels"])
+    n_items = int(fx["num_items"])
+    loss, parts, params, grads = run_step(hp, W, batch, n_items)
+    d = abs(float(loss) - float(fx["loss"]))
+    e_mel = float(np.abs(sub(parts["mel"], 8192) - fx["mel_sub"]).max())
+    e_enc = float(np.linalg.norm(sub(parts["encoder_out"], 8192) - fx["enc_sub"]) / np.linalg.norm(fx["enc_sub"]))
+    print(f"[full_b1_4s] loss {float(loss):.5f} vs reference {float(fx['loss']):.5f}: |delta| {d:.2e}; mel max err {e_mel:.2e}; "
+          f"encoder out (32 layers, bf16) rel err {e_enc:.3e}")
+    assert e_mel < 2e-4
+    assert e_enc < 5e-2
+    assert d < 1e-3                 # the north-star bound; measured 1.0e-4 (12.18883 vs 12.18893)
+    for k in grads:
+        ref = fx["grad_sub." + k]
+        eg = float(np.linalg.norm(sub(grads[k]) - ref) / (np.linalg.norm(ref) + 1e-12))
+        print(f"   grad {k}: rel vs reference sub-sample {eg:.3e}")
+        assert eg < 0.12            # 60 layers of bf16 rounding between the loss and the projector
+
+
+def test_full_size_batch_properties(cuda):
+    """Size-independent properties at the full model size and the benchmark's clip length (30 s, 375 audio tokens per clip):
+    with sum / num_items normalisation the batch loss is the sum of the single-clip losses, the projector gradient is the sum of
+    the single-clip gradients, and permuting the clips of a batch changes neither."""
+    from tiny_audio_b200.synthetic import build_offline_model, synthetic_batch
+    dims = PathDims(proj_hidden=2048)
+    model = build_offline_model(dims, device="cuda", seed=77)
+    hp = model._hot_path()
+    params = {k: p.detach().float().contiguous() for k, p in model.projector.state_dict().items()}
+    B = 3
+    host = synthetic_batch(dims, B, 30.0, seed=5, response_len=16)
+    n_items = int((host["labels"] != -100).sum())
+
+    def run(sel):
+        g = {k: torch.zeros_like(v) for k, v in params.items()}
+        loss, _ = hp.forward_backward(input_ids=host["input_ids"][sel].cuda(), labels_cpu=host["labels"][sel], proj_params=params,
+                                      waveform=host["input_features"][sel].cuda(), audio_token_counts=host["audio_token_counts"][sel].cuda(),
+                                      num_items_in_batch=n_items, grads=g)
+        torch.cuda.synchronize()
+        return float(loss), {k: v.clone() for k, v in g.items()}
+
+    l_all, g_all = run([0, 1, 2])
+    l_perm, g_perm = run([2, 0, 1])
+    singles = [run([b]) for b in range(B)]
+    l_sum = sum(l for l, _ in singles)
+    assert abs(l_all - l_perm) < 2e-5 * abs(l_all)
+    assert abs(l_all - l_sum) < 2e-5 * abs(l_all), (l_all, l_sum)
+    for k in g_all:
+        g_sum = sum(g[k] for _, g in singles)
+        assert rel(g_all[k], g_sum) < 2e-2, k          # d(logits) is rounded to bf16 per row, the sums differ in rounding only
+        assert rel(g_all[k], g_perm[k]) < 2e-2, k
+    assert all(torch.isfinite(v).all() for v in g_all.values())
