@@ -110,7 +110,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's PyTorch fp32 path on the host cores
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference(args, steps: int, warmup: int, batch: int):
+def cpu_reference(args, steps: int, warmup: int, batch: int, keep_inputs: bool = False):
     from oracle import path_oracle as po   # the one place bench.py executes oracle/ : as the timed CPU baseline
     # intra-op threads: all cores up to 32 -- beyond that torch's CPU kernels get SLOWER on this workload (measured:
     # 128 threads -> 0.10 audio-s/s vs 8 threads -> 3.3 audio-s/s for the same step)
@@ -121,18 +121,26 @@ def cpu_reference(args, steps: int, warmup: int, batch: int):
     n_items = int((b["labels"] != -100).sum())
     state = None
     times = []
+    first_loss = None
+    proj0 = {k: v.clone() for k, v in W["projector"].items()}
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         res = po.train_step(W, b, cfg, lr=1e-3, max_grad_norm=1.0, state=state, num_items_in_batch=n_items)
+        if first_loss is None:
+            first_loss = float(res["loss"])
         state = res["state"]
         W["projector"] = res["params"]
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     ms = 1000.0 * sum(times) / len(times)
-    return {"value": batch * args.clip_seconds / (ms / 1000.0), "ms_per_step": ms, "cores": torch.get_num_threads(),
-            "sample": f"B={batch} x {args.clip_seconds:g}s clip(s), full-size model, fp32, {steps} step(s) after {warmup} warm-up",
-            "loss": float(res["loss"])}
+    out = {"value": batch * args.clip_seconds / (ms / 1000.0), "ms_per_step": ms, "cores": torch.get_num_threads(),
+           "sample": f"B={batch} x {args.clip_seconds:g}s clip(s), full-size model, fp32, {steps} step(s) after {warmup} warm-up",
+           "loss": float(res["loss"])}
+    if keep_inputs:      # for the CE-loss delta: the same seeded weights and batch go through the CUDA path (run_ours)
+        W0 = {"encoder": W["encoder"], "lm": W["lm"], "projector": proj0}     # the first step's loss belongs to the initial projector
+        out["_parity"] = (cfg, W0, b, n_items, float(first_loss))
+    return out
 
 
 def run_reference(args):
@@ -311,16 +319,29 @@ def run_ours(args):
         del a, w, out
 
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del model
-        r = cpu_reference(args, 1, 1, args.cpu_sample_batch)
+        r = cpu_reference(args, 1, 1, args.cpu_sample_batch, keep_inputs=True)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        # second half of the BASELINE metric: CE-loss delta vs the reference arithmetic on identical seeded weights and inputs
+        # (the oracle is pinned to the unmodified reference by tests/golden; here it is the checker, not the product)
+        from tiny_audio_b200.engine import HotPath
+        cfg_o, W0, b0, n0, loss_ref = r["_parity"]
+        hp = HotPath(PathDims.from_any(cfg_o.to_dict()), W0["encoder"], W0["lm"], dev)
+        pp = {k: v.clone().to(dev).contiguous() for k, v in W0["projector"].items()}
+        l_gpu, _ = hp.forward_backward(input_ids=b0["input_ids"].to(dev), labels_cpu=b0["labels"], proj_params=pp,
+                                       waveform=b0["waveform"].to(dev), audio_token_counts=b0["audio_token_counts"].to(dev),
+                                       num_items_in_batch=n0)
+        parity = {"ce_loss_cuda_bf16": float(l_gpu), "ce_loss_reference_fp32": loss_ref, "ce_loss_delta": abs(float(l_gpu) - loss_ref),
+                  "sample": f"B={args.cpu_sample_batch} x {args.clip_seconds:g} s, full-size model, identical seeded weights and inputs"}
+        del hp
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "loss": float(last_loss)}
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "parity": parity, "loss": float(last_loss)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
