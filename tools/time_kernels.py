@@ -91,3 +91,14 @@ tb = timeit(lambda: L.check(lib.ta_attn_bwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(
                                             Hq * hd, Hkv * hd, Hkv * hd, 1, hd ** -0.5, L.stream_ptr())), reps=5)
 print(f"lm attention bwd WITHOUT dQ atomics (experiment): {tb:.3f} ms", flush=True)
 lib.ta_debug_set(1, 0)
+
+# log-mel front end: 32 x 30 s clips
+import ctypes as C
+B, Ls = 32, 480000
+wave = 0.1 * torch.randn(B, Ls, device=dev)
+n = C.c_longlong()
+L.check(lib.ta_logmel_workspace_floats(B, Ls, C.byref(n)))
+ws = torch.empty(n.value, device=dev, dtype=F32)
+im2 = torch.empty(B * (Ls // 160), 384, device=dev, dtype=BF16)
+t = timeit(lambda: L.check(lib.ta_logmel_fwd(L.ptr(wave), wave.stride(0), B, Ls, L.ptr(ws), None, L.ptr(im2), L.stream_ptr())), reps=10)
+print(f"log-mel 32 x 30 s (power + finalize + im2col): {t:.3f} ms  ({B * (4 * Ls + 4 * 128 * (Ls // 160)) / t / 1e6:.0f} GB/s algorithmic)", flush=True)
