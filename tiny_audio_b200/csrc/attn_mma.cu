@@ -209,23 +209,28 @@ attn_fwd_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K, const bf
 template <int HD>
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ D,
                                      int B, int S, int Hq, long long o_rs, long long do_rs) {
-    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    // HD / 8 lanes per (token, head), 16-byte loads: a warp reads 512 contiguous bytes of O and of dO
+    constexpr int LPH = HD / 8;
+    const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPH;
+    const int sub = threadIdx.x % LPH;
     const long long total = (long long)B * S * Hq;
-    if (wid >= total) return;
-    const int h = (int)(wid % Hq);
-    const long long bs = wid / Hq;
+    const bool live = item < total;
+    const long long it = live ? item : 0;
+    const int h = (int)(it % Hq);
+    const long long bs = it / Hq;
     const int s = (int)(bs % S), b = (int)(bs / S);
-    const bf16* o = O + bs * o_rs + (long long)h * HD;
-    const bf16* d = dO + bs * do_rs + (long long)h * HD;
+    const uint4 uo = *reinterpret_cast<const uint4*>(O + bs * o_rs + (long long)h * HD + 8 * sub);
+    const uint4 ud = *reinterpret_cast<const uint4*>(dO + bs * do_rs + (long long)h * HD + 8 * sub);
+    const uint32_t wo[4] = {uo.x, uo.y, uo.z, uo.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w};
     float acc = 0.f;
-    for (int i = lane * 2; i < HD; i += 64) {
-        const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + i));
-        const float2 c = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(d + i));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = unpack_bf16x2(wo[i]), c = unpack_bf16x2(wd[i]);
         acc += a.x * c.x + a.y * c.y;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) D[((long long)b * Hq + h) * S + s] = acc;
+#pragma unroll
+    for (int o = LPH / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live && sub == 0) D[((long long)b * Hq + h) * S + s] = acc;
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -485,9 +490,8 @@ TA_API int ta_attn_bwd(const void* q, const void* k, const void* v, const void* 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int HD = 128;
     {
-        const long long warps = (long long)B * S * Hq;
-        const int wpb = 8;
-        attn_bwd_prep_kernel<HD><<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+        const long long threads = (long long)B * S * Hq * (HD / 8);
+        attn_bwd_prep_kernel<HD><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
             (const bf16*)o, (const bf16*)d_o, dsum_ws, B, S, Hq, o_rs, do_rs);
         TA_LAUNCH_CHECK();
     }
