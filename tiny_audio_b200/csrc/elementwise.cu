@@ -265,51 +265,78 @@ __global__ void lm_qknorm_rope_bwd_kernel(const bf16* __restrict__ qkv, const fl
                                           const float* __restrict__ kw, const float* __restrict__ cosT,
                                           const float* __restrict__ sinT, long long M, int S, int Hq, int Hkv, float eps,
                                           long long ld_out) {
+    // 8 lanes per (row, head), lane l8 owns dims [8 l8, +8) and [64 + 8 l8, +8): 16-byte accesses throughout (see the forward kernel)
     const int HD = 128;
     const int heads = Hq + 2 * Hkv;
-    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wid >= M * heads) return;
-    const int lane = threadIdx.x & 31;
-    const int h = (int)(wid % heads);
-    const long long row = wid / heads;
-    bf16* dst = dqkv + row * ld_out + (long long)h * HD;
-    if (h >= Hq + Hkv) {   // v: plain copy
-        const bf16* s = dv + row * (long long)(Hkv * HD) + (long long)(h - Hq - Hkv) * HD;
-        *reinterpret_cast<uint32_t*>(dst + 2 * lane) = *reinterpret_cast<const uint32_t*>(s + 2 * lane);
-        *reinterpret_cast<uint32_t*>(dst + 64 + 2 * lane) = *reinterpret_cast<const uint32_t*>(s + 64 + 2 * lane);
-        return;
+    const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int l8 = threadIdx.x & 7;
+    const bool live = item < M * heads;
+    const long long it = live ? item : 0;
+    const int h = (int)(it % heads);
+    const long long row = it / heads;
+    bf16* dst = dqkv + row * ld_out + (long long)h * HD + 8 * l8;
+    const bool is_v = h >= Hq + Hkv;
+    float g_lo[8], g_hi[8];   // dy for my 8 + 8 dims
+    if (is_v) {               // v: plain copy (still takes part in the shuffles below with zeros)
+        const bf16* sv = dv + row * (long long)(Hkv * HD) + (long long)(h - Hq - Hkv) * HD + 8 * l8;
+        if (live) {
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(sv);
+            *reinterpret_cast<uint4*>(dst + 64) = *reinterpret_cast<const uint4*>(sv + 64);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { g_lo[i] = 0.f; g_hi[i] = 0.f; }
+    } else if (h < Hq) {
+        const float* sq = dq + row * (long long)(Hq * HD) + (long long)h * HD + 8 * l8;
+        ld8_f32(sq, g_lo);
+        ld8_f32(sq + 64, g_hi);
+    } else {
+        const bf16* sk = dk + row * (long long)(Hkv * HD) + (long long)(h - Hq) * HD + 8 * l8;
+        ld8_bf16(sk, g_lo);
+        ld8_bf16(sk + 64, g_hi);
     }
     const int pos = (int)(row % S);
-    float g0, g1, g2, g3;   // dy for dims 2l, 2l+1, 2l+64, 2l+65
-    const float* w;
-    if (h < Hq) {
-        const float* s = dq + row * (long long)(Hq * HD) + (long long)h * HD;
-        const float2 lo = *reinterpret_cast<const float2*>(s + 2 * lane), hi = *reinterpret_cast<const float2*>(s + 64 + 2 * lane);
-        g0 = lo.x; g1 = lo.y; g2 = hi.x; g3 = hi.y;
-        w = qw;
-    } else {
-        const bf16* s = dk + row * (long long)(Hkv * HD) + (long long)(h - Hq) * HD;
-        const float2 lo = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(s + 2 * lane));
-        const float2 hi = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(s + 64 + 2 * lane));
-        g0 = lo.x; g1 = lo.y; g2 = hi.x; g3 = hi.y;
-        w = kw;
-    }
-    const float c0 = cosT[pos * 64 + 2 * lane], c1 = cosT[pos * 64 + 2 * lane + 1];
-    const float s0 = sinT[pos * 64 + 2 * lane], s1 = sinT[pos * 64 + 2 * lane + 1];
-    // rope^T
-    const float z0 = g0 * c0 + g2 * s0, z1 = g1 * c1 + g3 * s1;
-    const float z2 = g2 * c0 - g0 * s0, z3 = g3 * c1 - g1 * s1;
-    // through the gain
-    const float d0 = z0 * w[2 * lane], d1 = z1 * w[2 * lane + 1], d2 = z2 * w[64 + 2 * lane], d3 = z3 * w[64 + 2 * lane + 1];
-    const bf16* src = qkv + row * (long long)(heads * HD) + (long long)h * HD;
-    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 2 * lane));
-    const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 64 + 2 * lane));
-    const float ss = warp_sum(a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y);
+    const int hx = is_v ? 0 : h;                                   // any valid head for the (unused) v-lane loads
+    const float* w = ((hx < Hq) ? qw : kw) + 8 * l8;
+    const bf16* src = qkv + row * (long long)(heads * HD) + (long long)hx * HD + 8 * l8;
+    float c[8], sn[8], wl[8], wh[8], a[8], b[8];
+    ld8_f32(cosT + pos * 64 + 8 * l8, c);
+    ld8_f32(sinT + pos * 64 + 8 * l8, sn);
+    ld8_f32(w, wl);
+    ld8_f32(w + 64, wh);
+    ld8_bf16(src, a);
+    ld8_bf16(src + 64, b);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += a[i] * a[i] + b[i] * b[i];
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
     const float rstd = rsqrtf(ss / HD + eps);
-    const float n0 = a.x * rstd, n1 = a.y * rstd, n2 = b.x * rstd, n3 = b.y * rstd;
-    const float dot = warp_sum(d0 * n0 + d1 * n1 + d2 * n2 + d3 * n3) / HD;
-    *reinterpret_cast<uint32_t*>(dst + 2 * lane) = pack_bf16x2(rstd * (d0 - n0 * dot), rstd * (d1 - n1 * dot));
-    *reinterpret_cast<uint32_t*>(dst + 64 + 2 * lane) = pack_bf16x2(rstd * (d2 - n2 * dot), rstd * (d3 - n3 * dot));
+    float d_lo[8], d_hi[8], n_lo[8], n_hi[8];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        // rope^T, then through the gain
+        d_lo[i] = (g_lo[i] * c[i] + g_hi[i] * sn[i]) * wl[i];
+        d_hi[i] = (g_hi[i] * c[i] - g_lo[i] * sn[i]) * wh[i];
+        n_lo[i] = a[i] * rstd;
+        n_hi[i] = b[i] * rstd;
+        dot += d_lo[i] * n_lo[i] + d_hi[i] * n_hi[i];
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    dot /= HD;
+    if (live && !is_v) {
+        float o_lo[8], o_hi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            o_lo[i] = rstd * (d_lo[i] - n_lo[i] * dot);
+            o_hi[i] = rstd * (d_hi[i] - n_hi[i] * dot);
+        }
+        st8_bf16(dst, o_lo);
+        st8_bf16(dst + 64, o_hi);
+    }
 }
 
 // =============================================================================================================
@@ -505,24 +532,28 @@ ce_fwd_bwd_kernel(bf16* __restrict__ logits, long long ld, const int* __restrict
     bf16* lr = logits + row * ld;
     const int tgt = targets[row];
     const int nvec = Vpad / 8;
-    float mx = -INFINITY;
+    // one pass for max and sum (online softmax: rescale the running sum when the running max grows), a second pass for the gradient
+    float m_run = -INFINITY, s_run = 0.f;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
         float v[8];
         ld8_bf16(lr + i * 8, v);
+        float vm = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (i * 8 + j < V) mx = fmaxf(mx, v[j]);
-    }
-    mx = block_max(mx, red);
-    float se = 0.f;
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        float v[8];
-        ld8_bf16(lr + i * 8, v);
+        for (int j = 0; j < 8; ++j) {
+            if (i * 8 + j >= V) v[j] = -INFINITY;
+            vm = fmaxf(vm, v[j]);
+        }
+        if (vm > -INFINITY) {
+            const float m_new = fmaxf(m_run, vm);
+            float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (i * 8 + j < V) se += __expf(v[j] - mx);
+            for (int j = 0; j < 8; ++j) acc += __expf(v[j] - m_new);      // exp(-inf) = 0 for the padding columns
+            s_run = s_run * __expf(m_run - m_new) + acc;                   // exp(-inf - m_new) = 0 on the first vector
+            m_run = m_new;
+        }
     }
-    se = block_sum(se, red);
+    const float mx = block_max(m_run, red);
+    float se = block_sum((m_run > -INFINITY) ? s_run * __expf(m_run - mx) : 0.f, red);
     const float lse = mx + logf(se);
     if (threadIdx.x == 0) {
         const float lt = __bfloat162float(lr[tgt]);
@@ -733,10 +764,10 @@ int k_lm_qknorm_rope_bwd(const bf16* qkv, const float* dq, const bf16* dk, const
                          const float* kw, const float* cosT, const float* sinT, long long M, int S, int Hq, int Hkv, float eps,
                          cudaStream_t st, long long ld_out) {
     if (ld_out == 0) ld_out = (long long)(Hq + 2 * Hkv) * 128;
-    const long long warps = M * (Hq + 2 * Hkv);
-    const int wpb = 8;
-    lm_qknorm_rope_bwd_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, st>>>(qkv, dq, dk, dv, dqkv, qw, kw, cosT, sinT, M,
-                                                                                          S, Hq, Hkv, eps, ld_out);
+    const long long threads = M * (Hq + 2 * Hkv) * 8;      // 8 lanes per (row, head)
+    if (threads == 0) return 0;
+    lm_qknorm_rope_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(qkv, dq, dk, dv, dqkv, qw, kw, cosT, sinT, M, S, Hq, Hkv,
+                                                                                   eps, ld_out);
     TA_LAUNCH_CHECK();
     return 0;
 }
