@@ -37,7 +37,7 @@ UNIT = "audio-s/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU (weak scaling)")
@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--cpu-threads", type=int, default=32)
+    ap.add_argument("--parity-batch", type=int, default=4,
+                    help="clips in the CE-loss parity sample (oracle forward on the host vs the CUDA path, same seeded weights/inputs)")
     return ap.parse_args()
 
 
@@ -64,7 +66,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -73,7 +75,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -311,6 +313,41 @@ def run_ours(args):
                 "traffic": 576.5e6 if (M, N, K) == (48000, 5120, 1280) else None,
                 "algorithmic_bytes": 2.0 * (M * K + N * K + M * N), "tensor_pipe_active_pct_ncu": 74.5, "step_tflops": 116.0e9 * audio_s / (ms_step / 1000.0) / 1e12 / world,
                 "step_frac_of_sustained": 116.0e9 * audio_s / (ms_step / 1000.0) / 1e12 / world / pk["bf16_tflops_sustained"]}
+        # the Qwen3 FFN GEMMs the north star names (M = B x S_lm tokens, dim 1024, ffn 3072), timed alone the same way, with the
+        # epilogues the training step uses: gate_up with fused SwiGLU + (gate, up) stash for the backward; down + fp32 residual
+        S_lm = int(host["input_ids"].shape[1])
+        Mt, Dl, Fl = B * S_lm, dims.lm_dim, dims.lm_ffn
+        xq = torch.randn(Mt, Dl, device=dev, dtype=torch.bfloat16)
+        wgu = torch.randn(2 * Fl, Dl, device=dev, dtype=torch.bfloat16) * 0.03
+        hq = torch.empty(Mt, Fl, device=dev, dtype=torch.bfloat16)
+        guq = torch.empty(Mt, 2 * Fl, device=dev, dtype=torch.bfloat16)
+        wdn = torch.randn(Dl, Fl, device=dev, dtype=torch.bfloat16) * 0.03
+        rq = torch.zeros(Mt, Dl, device=dev, dtype=torch.float32)
+        yq = torch.empty(Mt, Dl, device=dev, dtype=torch.float32)
+
+        def time_alone(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                fn()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / reps / 1000.0
+
+        t_gu = time_alone(lambda: L.gemm(xq, wgu, epi=L.EPI_SWIGLU, out=hq, out2=guq))
+        t_gu0 = time_alone(lambda: L.gemm(xq, wgu, epi=L.EPI_SWIGLU, out=hq))
+        t_dn = time_alone(lambda: L.gemm(hq, wdn, epi=L.EPI_F32_RESID, resid=rq, out=yq))
+        f_gu, f_dn = 2.0 * Mt * 2 * Fl * Dl, 2.0 * Mt * Dl * Fl
+        roof["qwen3_ffn"] = {
+            "shape": f"M={Mt} dim={Dl} ffn={Fl}",
+            "gate_up_swiglu_stash": {"us": t_gu * 1e6, "tflops": f_gu / t_gu / 1e12, "frac": f_gu / t_gu / 1e12 / peak},
+            "gate_up_swiglu_nostash": {"us": t_gu0 * 1e6, "tflops": f_gu / t_gu0 / 1e12, "frac": f_gu / t_gu0 / 1e12 / peak},
+            "down_resid": {"us": t_dn * 1e6, "tflops": f_dn / t_dn / 1e12, "frac": f_dn / t_dn / 1e12 / peak},
+            "tensor_pipe_active_pct_ncu": {"gate_up_swiglu_stash": 65.0, "source": "profiles/r01_ncu_top_kernels_summary.txt"}}
+        del xq, wgu, hq, guq, wdn, rq, yq
         if args.train_lm:      # + weight-gradient GEMMs of the decoder: 2 * P_lm_lin * S_lm (body) + 2 * P_head * n_labelled (tied head)
             extra = (2.0 * 440.4e6 * 464 + 2.0 * 155.6e6 * (args.response_len + 1)) / args.clip_seconds
             gf = 116.0e9 + extra
@@ -334,7 +371,21 @@ def run_ours(args):
                                        waveform=b0["waveform"].to(dev), audio_token_counts=b0["audio_token_counts"].to(dev),
                                        num_items_in_batch=n0)
         parity = {"ce_loss_cuda_bf16": float(l_gpu), "ce_loss_reference_fp32": loss_ref, "ce_loss_delta": abs(float(l_gpu) - loss_ref),
-                  "sample": f"B={args.cpu_sample_batch} x {args.clip_seconds:g} s, full-size model, identical seeded weights and inputs"}
+                  "sample": f"B={args.cpu_sample_batch} x {args.clip_seconds:g} s, full-size model, identical seeded weights and inputs",
+                  # yardstick: the unmodified reference's OWN fp32 vs bf16-autocast CE on identical weights/inputs
+                  "reference_own_bf16_vs_fp32_delta": 1.29e-3}
+        if args.parity_batch > args.cpu_sample_batch:
+            # the metric's CE loss is a batch mean: a larger sample (forward only on the host) averages the per-token bf16 rounding
+            from oracle import path_oracle as po
+            bp = po.synthetic_batch(cfg_o, args.parity_batch, args.clip_seconds, seed=1, response_len=args.response_len)
+            n_p = int((bp["labels"] != -100).sum())
+            with torch.no_grad():
+                l_ref_p, _ = po.model_forward(W0, bp, cfg_o, n_p)
+            l_gpu_p, _ = hp.forward_backward(input_ids=bp["input_ids"].to(dev), labels_cpu=bp["labels"], proj_params=pp,
+                                             waveform=bp["waveform"].to(dev), audio_token_counts=bp["audio_token_counts"].to(dev),
+                                             num_items_in_batch=n_p)
+            parity["batch_sample"] = {"sample": f"B={args.parity_batch} x {args.clip_seconds:g} s", "ce_loss_cuda_bf16": float(l_gpu_p),
+                                      "ce_loss_reference_fp32": float(l_ref_p), "ce_loss_delta": abs(float(l_gpu_p) - float(l_ref_p))}
         del hp
 
     if rank == 0:

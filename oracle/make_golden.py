@@ -74,7 +74,7 @@ class StubTok:
         return self.cfg.vocab
 
 
-def build_reference_model(cfg: po.PathConfig, W, mods, projector="mlp", freeze_lm=True):
+def build_reference_model(cfg: po.PathConfig, W, mods, projector="mlp", freeze_lm=True, **config_extras):
     from transformers import GlmAsrEncoderConfig, Qwen3Config, Qwen3ForCausalLM, WhisperFeatureExtractor
     from transformers.models.glmasr.modeling_glmasr import GlmAsrEncoder
 
@@ -117,7 +117,7 @@ def build_reference_model(cfg: po.PathConfig, W, mods, projector="mlp", freeze_l
     ASRModel._create_feature_extractor = lambda self, config: WhisperFeatureExtractor(feature_size=cfg.n_mels)
     acfg = ASRConfig(audio_config=enc_cfg, text_config=txt_cfg, model_dtype="float32", attn_implementation="sdpa",
                      projector_type=projector, projector_pool_stride=cfg.proj_k, projector_hidden_dim=cfg.proj_hidden,
-                     audio_token_dropout=0.0, freeze_language_model=freeze_lm)
+                     audio_token_dropout=0.0, freeze_language_model=freeze_lm, **config_extras)
     model = ASRModel(acfg)
     model.projector.load_state_dict(W["projector"], strict=True)
     return model
@@ -141,7 +141,15 @@ CASES = {
     "qformer_b2_2s": (dict(enc_layers=1, lm_layers=1, _projector="qformer"), 2, 2.0, None, 8, 15),
     # full decoder fine-tuning (configs/experiments/embedded.yaml:19-33, freeze_language_model: false): LM weight gradients
     "unfrozen_b2_2s": (dict(enc_layers=1, lm_layers=2, _train_lm=True), 2, 2.0, None, 8, 16),
+    # the two remaining registered projectors (projectors.py:482-487).  moe: training mode with router_jitter_noise = 0 (the jitter is
+    # RNG: no bit-parity definition), so the load-balance + z-loss term IS part of the loss; seed 21 keeps every token's 2nd/3rd
+    # router logits 0.87 apart, far beyond the bf16 encoder's perturbation, so the top-2 choice cannot flip between precisions
+    "mosa_b2_2s": (dict(enc_layers=1, lm_layers=1, _projector="mosa"), 2, 2.0, None, 8, 17),
+    "moe_b2_2s": (dict(enc_layers=1, lm_layers=1, _projector="moe"), 2, 2.0, None, 8, 21),
 }
+
+PROJECTOR_INIT = {"qformer": po.init_qformer_weights, "mosa": po.init_mosa_weights, "moe": po.init_moe_weights}
+PROJECTOR_CONFIG_EXTRAS = {"moe": dict(router_jitter_noise=0.0)}
 
 
 def case_config(spec):
@@ -161,8 +169,8 @@ def run_case(name, mods, outdir):
     torch.manual_seed(0)
     t0 = time.time()
     W = po.init_weights(cfg, seed=seed)
-    if kind == "qformer":
-        W["projector"] = po.init_qformer_weights(cfg, seed=seed + 1000)
+    if kind in PROJECTOR_INIT:
+        W["projector"] = PROJECTOR_INIT[kind](cfg, seed=seed + 1000)
     batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s, projector=kind)
     if name == "small_b3_ragged":
         # ragged text: right-pad labels/ids of samples 1,2 and shrink their audio counts
@@ -173,7 +181,7 @@ def run_case(name, mods, outdir):
             labels[b, -cut:] = -100
             am[b, -cut:] = 0
         batch.update(input_ids=ids, labels=labels, attention_mask=am)
-    model = build_reference_model(cfg, W, mods, kind, freeze_lm=not train_lm)
+    model = build_reference_model(cfg, W, mods, kind, freeze_lm=not train_lm, **PROJECTOR_CONFIG_EXTRAS.get(kind, {}))
     model.train()
     if kind == "qformer":
         model.projector.eval()
@@ -196,7 +204,8 @@ def run_case(name, mods, outdir):
     out = model(**ref_batch, num_items_in_batch=torch.tensor(n_items))
     loss = out.loss
     loss.backward()
-    grads = {k: p.grad.detach().clone() for k, p in model.projector.named_parameters()}
+    # an expert no token selected never enters the graph (moe dispatch loop, projectors.py:328-345): grad None == zero
+    grads = {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)) for k, p in model.projector.named_parameters()}
     lm_grads = {k: p.grad.detach().clone() for k, p in model.language_model.named_parameters() if p.grad is not None}
     assert bool(lm_grads) == bool(train_lm)
     gnorm = torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
@@ -242,6 +251,8 @@ def run_case(name, mods, outdir):
         "logits_argmax": logits.argmax(-1).numpy().astype(np.int64),
         "grad_norm": np.array(float(gnorm)),
     }
+    if hasattr(model.projector, "get_aux_loss"):
+        fx["aux_loss"] = np.array(float(model.projector.get_aux_loss()))
     for k in grads:
         fx["grad_sub." + k] = sub(grads[k], 4096)
         fx["grad_l2." + k] = np.array(float(grads[k].norm()))

@@ -391,6 +391,122 @@ def qformer_projector_forward(w: Dict[str, Tensor], enc_out: Tensor, cfg: PathCo
 
 
 # --------------------------------------------------------------------------------------
+# f4. MOSA projector (tiny_audio/projectors.py:103-177): conv downsampler x2 -> dense softmax mixture of 2-layer GELU adapters
+# --------------------------------------------------------------------------------------
+MOSA_ADAPTER_HIDDEN, MOSA_ROUTER_HIDDEN, MOSA_EXPERTS = 4096, 512, 4
+
+
+def _adapter_weights(w, prefix, g, i_dim, h_dim, o_dim, fc2_std=None):
+    """SimpleAdapter parameters (projectors.py:90-100) under the reference's names: fc1 / fc2 with biases."""
+    w[prefix + "fc1.weight"] = torch.randn(h_dim, i_dim, generator=g) / math.sqrt(i_dim)
+    w[prefix + "fc1.bias"] = 0.05 * torch.randn(h_dim, generator=g)
+    w[prefix + "fc2.weight"] = torch.randn(o_dim, h_dim, generator=g) * (fc2_std if fc2_std else 1.0 / math.sqrt(h_dim))
+    w[prefix + "fc2.bias"] = 0.05 * torch.randn(o_dim, generator=g)
+
+
+def init_mosa_weights(cfg: PathConfig, seed: int = 78) -> Dict[str, Tensor]:
+    """Seeded weights under MOSAProjector.state_dict() names (projectors.py:133-151)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    D, O = cfg.enc_dim, cfg.lm_dim
+    w = {"downsampler.0.weight": torch.randn(D, D, 3, generator=g) / math.sqrt(3 * D),
+         "downsampler.0.bias": 0.05 * torch.randn(D, generator=g),
+         "downsampler.2.weight": torch.randn(O, D, 3, generator=g) / math.sqrt(3 * D),
+         "downsampler.2.bias": 0.05 * torch.randn(O, generator=g),
+         "router.0.weight": torch.randn(MOSA_ROUTER_HIDDEN, O, generator=g) / math.sqrt(O),
+         "router.0.bias": 0.05 * torch.randn(MOSA_ROUTER_HIDDEN, generator=g),
+         "router.2.weight": torch.randn(MOSA_EXPERTS, MOSA_ROUTER_HIDDEN, generator=g) * (2.0 / math.sqrt(MOSA_ROUTER_HIDDEN)),
+         "router.2.bias": 0.05 * torch.randn(MOSA_EXPERTS, generator=g)}
+    for i in range(MOSA_EXPERTS):
+        _adapter_weights(w, f"experts.{i}.", g, O, MOSA_ADAPTER_HIDDEN, O)
+    return w
+
+
+def mosa_output_length(enc_len):
+    """Two k=3, s=2, p=1 convolutions (projectors.py:172-177)."""
+    for _ in range(2):
+        enc_len = (enc_len + 2 * 1 - 3) // 2 + 1
+    return enc_len
+
+
+def mosa_projector_forward(w: Dict[str, Tensor], enc_out: Tensor, cfg: PathConfig = FULL) -> Tensor:
+    """projectors.py:153-170: every expert sees every token; outputs are mixed with the router's softmax."""
+    x = enc_out.float().transpose(1, 2)
+    for idx in ("0", "2"):                      # nn.Sequential(Conv1d, GELU, Conv1d, GELU)
+        x = F.gelu(F.conv1d(x, w[f"downsampler.{idx}.weight"], w[f"downsampler.{idx}.bias"], stride=2, padding=1))
+    x = x.transpose(1, 2)
+    hidden = F.relu(F.linear(x, w["router.0.weight"], w["router.0.bias"]))
+    mix = torch.softmax(F.linear(hidden, w["router.2.weight"], w["router.2.bias"]), dim=-1)
+    out = None
+    for i in range(mix.shape[-1]):
+        y = F.linear(F.gelu(F.linear(x, w[f"experts.{i}.fc1.weight"], w[f"experts.{i}.fc1.bias"])),
+                     w[f"experts.{i}.fc2.weight"], w[f"experts.{i}.fc2.bias"]) * mix[..., i:i + 1]
+        out = y if out is None else out + y
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# f4. shared + sparse MoE projector (tiny_audio/projectors.py:185-351): frame-stack -> RMSNorm -> shared adapter + top-k of E adapters
+# --------------------------------------------------------------------------------------
+MOE_EXPERTS, MOE_TOP_K, MOE_AUX_COEF, MOE_Z_COEF = 4, 2, 0.01, 1e-4
+
+
+def init_moe_weights(cfg: PathConfig, seed: int = 79) -> Dict[str, Tensor]:
+    """Seeded weights under MoEAudioProjector.state_dict() names (projectors.py:223-235); the scales follow its
+    _init_weights (:242-251): router std 0.02, fc2 std 0.01."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    I, H, O = cfg.enc_dim * cfg.proj_k, cfg.proj_hidden, cfg.lm_dim
+    w = {"norm.weight": 1.0 + 0.1 * torch.randn(I, generator=g),
+         "router.weight": 0.02 * torch.randn(MOE_EXPERTS, I, generator=g)}
+    for i in range(MOE_EXPERTS):
+        _adapter_weights(w, f"experts.{i}.", g, I, H, O, fc2_std=0.01)
+    _adapter_weights(w, "shared_expert.", g, I, H, O, fc2_std=0.01)
+    return w
+
+
+def moe_router(w: Dict[str, Tensor], flat: Tensor):
+    """projectors.py:291-309 without jitter: fp32 softmax over the router logits, top-k, weights renormalised with +1e-6."""
+    logits = F.linear(flat, w["router.weight"])
+    probs = torch.softmax(logits.float(), dim=-1)
+    top_w, top_i = torch.topk(probs, MOE_TOP_K, dim=-1)
+    top_w = top_w / (top_w.sum(dim=-1, keepdim=True) + 1e-6)
+    return logits, probs, top_w, top_i
+
+
+def moe_projector_forward(w: Dict[str, Tensor], enc_out: Tensor, cfg: PathConfig = FULL, training: bool = True):
+    """-> (audio embeddings, aux loss).  projectors.py:257-347 with router_jitter_noise = 0 (the jitter is RNG: no parity
+    definition).  aux = load-balance + z-loss in training mode, 0 in eval mode (:311-325)."""
+    x = rms_norm(frame_stack(enc_out.float(), cfg.proj_k), w["norm.weight"], cfg.proj_eps)
+    B, n, I = x.shape
+    flat = x.reshape(B * n, I)
+
+    def adapter(prefix, t):
+        return F.linear(F.gelu(F.linear(t, w[prefix + "fc1.weight"], w[prefix + "fc1.bias"])), w[prefix + "fc2.weight"], w[prefix + "fc2.bias"])
+
+    out = adapter("shared_expert.", flat)
+    logits, probs, top_w, top_i = moe_router(w, flat)
+    aux = torch.zeros((), dtype=torch.float32)
+    if training:
+        n_e = probs.shape[-1]
+        balance = MOE_AUX_COEF * ((probs.mean(0) - 1.0 / n_e) ** 2).mean() * n_e
+        aux = balance + MOE_Z_COEF * torch.logsumexp(logits, dim=-1).pow(2).mean()
+    for e in range(probs.shape[-1]):                          # sparse dispatch: only the tokens that picked expert e
+        rows, slot = torch.nonzero(top_i == e, as_tuple=True)
+        if rows.numel():
+            out = out.index_add(0, rows, adapter(f"experts.{e}.", flat[rows]) * top_w[rows, slot].unsqueeze(-1))
+    return out.view(B, n, -1), aux
+
+
+def projector_kind(weights: Dict[str, Tensor]) -> str:
+    if "query" in weights:
+        return "qformer"
+    if "downsampler.0.weight" in weights:
+        return "mosa"
+    if "router.weight" in weights:
+        return "moe"
+    return "mlp"
+
+
+# --------------------------------------------------------------------------------------
 # a7. ragged gather + masked_scatter (tiny_audio/asr_modeling.py:27-44, 497-515)
 # --------------------------------------------------------------------------------------
 def gather_audio_embeds(audio_embeds: Tensor, token_counts: Tensor) -> Tensor:
@@ -501,8 +617,13 @@ def model_forward(W, batch: Dict[str, Tensor], cfg: PathConfig = FULL, num_items
     with torch.no_grad():
         enc = encoder_forward(W["encoder"], mel, cfg)
     parts["encoder_out"] = enc
-    if "query" in W["projector"]:
+    kind, aux = projector_kind(W["projector"]), None
+    if kind == "qformer":
         audio = qformer_projector_forward(W["projector"], enc, cfg)
+    elif kind == "mosa":
+        audio = mosa_projector_forward(W["projector"], enc, cfg)
+    elif kind == "moe":
+        audio, aux = moe_projector_forward(W["projector"], enc, cfg, training=batch.get("projector_training", True))
     else:
         audio = projector_forward(W["projector"], enc, cfg)
     parts["projector_out"] = audio
@@ -520,6 +641,9 @@ def model_forward(W, batch: Dict[str, Tensor], cfg: PathConfig = FULL, num_items
     loss = None
     if batch.get("labels") is not None:
         loss = causal_lm_loss(logits, batch["labels"], num_items_in_batch)
+        if aux is not None:                  # projector.get_aux_loss() is added to the LM loss (asr_modeling.py:528-531)
+            loss = loss + aux
+            parts["aux_loss"] = aux
     if return_parts:
         return loss, logits, parts
     return loss, logits
@@ -588,7 +712,7 @@ def train_step(W, batch, cfg: PathConfig = FULL, lr=1e-3, max_grad_norm=1.0, wei
         W2["lora"] = lora
     loss, _ = model_forward(W2, batch, cfg, num_items_in_batch)
     loss.backward()
-    grads = {k: v.grad.detach() for k, v in proj.items()}
+    grads = {k: (v.grad.detach() if v.grad is not None else torch.zeros_like(v)) for k, v in proj.items()}   # unselected MoE experts: None
     lora_grads = None
     if lora is not None:
         lora_grads = {"A": {k: v.grad.detach() for k, v in lora["A"].items()}, "B": {k: v.grad.detach() for k, v in lora["B"].items()}}
@@ -633,6 +757,8 @@ def synthetic_batch(cfg: PathConfig, batch: int, clip_seconds: float, seed: int 
     n_a = int(projector_output_length(encoder_output_length(mel_len), cfg.proj_k))
     if projector == "qformer":
         n_a = int(qformer_output_length(encoder_output_length(mel_len)))
+    elif projector == "mosa":
+        n_a = int(mosa_output_length(encoder_output_length(mel_len)))
 
     def tid(t):   # map real-tokenizer ids into a reduced vocab deterministically
         return t if t < cfg.vocab - 1 else (t % (cfg.vocab - 1))

@@ -57,8 +57,26 @@ def test_projector_contract():
     assert torch.equal(p.get_output_length(torch.tensor([100, 50])), torch.tensor([25, 12]))
     assert [k for k, _ in p.named_parameters()] == ["linear_1.weight", "norm.weight", "linear_2.weight", "norm_2.weight"]
     assert p.linear_1.weight.shape == (512, 1024) and p.linear_2.weight.shape == (512, 512)
-    with pytest.raises(NotImplementedError):
-        PROJECTOR_CLASSES["moe"](Cfg())
+    # reference tests/test_projectors.py:110-118 (mosa: two k=3/s=2/p=1 convolutions) and :152-166 (moe: frame-stack lengths,
+    # shared expert, aux loss accessor)
+    class MCfg(Cfg):
+        num_experts, num_experts_per_tok, router_aux_loss_coef = 4, 2, 0.01
+    mosa = PROJECTOR_CLASSES["mosa"](MCfg())
+    assert [mosa.get_output_length(n) for n in (100, 101, 4, 5)] == [25, 26, 1, 2]
+    assert torch.equal(mosa.get_output_length(torch.tensor([100, 101])), torch.tensor([25, 26]))
+    assert {"downsampler.0.weight", "downsampler.2.bias", "router.0.weight", "router.2.bias", "experts.3.fc1.weight",
+            "experts.0.fc2.bias"} <= set(mosa.state_dict()) and len(mosa.state_dict()) == 8 + 4 * 4
+    assert mosa.downsampler[2].weight.shape == (512, 256, 3) and mosa.experts[0].fc1.weight.shape == (4096, 512)
+    moe = PROJECTOR_CLASSES["moe"](MCfg())
+    assert moe.get_output_length(100) == 25 and moe.get_output_length(101) == 25
+    assert hasattr(moe, "shared_expert") and len(moe.experts) == 4 and moe.top_k == 2
+    assert set(moe.state_dict()) == ({"norm.weight", "router.weight"}
+                                     | {f"{e}.{l}.{t}" for e in ["shared_expert"] + [f"experts.{i}" for i in range(4)]
+                                        for l in ("fc1", "fc2") for t in ("weight", "bias")})
+    assert moe.get_aux_loss().numel() == 1 and float(moe.get_aux_loss()) == 0.0
+    for proj in (mosa, moe):
+        with pytest.raises(Exception, match="no CPU fallback"):
+            proj(torch.randn(1, 16, 256))
     # reference tests/test_projectors.py:202-214: qformer lengths 15->3, 16->6, 30->6, 100->21; query shape
     class QCfg:
         encoder_dim, llm_dim, qformer_window_size, downsample_rate = 256, 512, 15, 5
@@ -68,6 +86,45 @@ def test_projector_contract():
     assert qf.query.shape == (1, 3, 256)
     assert torch.equal(qf.get_output_length(torch.tensor([15, 100])), torch.tensor([3, 21]))
     assert "qformer.encoder.layer.1.crossattention.attention.key.weight" in qf.state_dict() and "linear.bias" in qf.state_dict()
+
+
+@pytest.mark.parametrize("kind", ["mosa", "moe"])
+def test_mixture_projector_host_logic_matches_oracle(kind, monkeypatch):
+    """The host-side structure of the mixture projectors -- im2col column order of the stride-2 convolutions, the adapters folded
+    into two wide products, gates (softmax / renormalised top-k with exact zeros, shared adapter at 1), fc2 biases, aux loss --
+    against the oracle (which is pinned to the reference's classes by tests/golden/{mosa,moe}_b2_2s.npz).  The tcgen05 GEMM is
+    replaced by an fp32 stand-in HERE ONLY so the algebra can be checked without a GPU; the GPU parity tests run the real kernels."""
+    from oracle import path_oracle as po
+    import tiny_audio_b200.projectors as P
+    monkeypatch.setattr(P, "tc_linear", lambda x, w, b=None: torch.nn.functional.linear(
+        x.float(), w.float(), b.float() if b is not None else None))
+
+    class Cfg:
+        encoder_dim, llm_dim, projector_pool_stride, projector_hidden_dim = 1280, 1024, 4, 1024
+        num_experts, num_experts_per_tok, router_aux_loss_coef, router_jitter_noise = 4, 2, 0.01, 0.0
+    cfg = po.small_config()
+    w = (po.init_mosa_weights if kind == "mosa" else po.init_moe_weights)(cfg, 5)
+    m = P.PROJECTOR_CLASSES[kind](Cfg())
+    m.load_state_dict(w, strict=True)
+    m.train()
+    x = torch.randn(2, 101, cfg.enc_dim, generator=torch.Generator().manual_seed(3))
+    y = m._mixture(x)
+    wr = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    ref = (po.mosa_projector_forward if kind == "mosa" else po.moe_projector_forward)(wr, x, cfg)
+    aux_ref = 0.0
+    if kind == "moe":
+        ref, aux_ref = ref
+        assert float(aux_ref) > 0 and abs(float(m.get_aux_loss()) - float(aux_ref)) < 1e-8
+    assert y.shape == ref.shape and float((y - ref).abs().max()) < 1e-5
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(4))
+    ((ref * g).sum() + aux_ref).backward()
+    ((y * g).sum() + (m.get_aux_loss() if kind == "moe" else 0.0)).backward()
+    for k, p in m.named_parameters():
+        assert float((p.grad - wr[k].grad).norm()) <= 1e-4 * float(wr[k].grad.norm()) + 1e-7, k
+    if kind == "moe":                   # eval mode: no aux term (projectors.py:311-325)
+        m.eval()
+        m._mixture(x)
+        assert float(m.get_aux_loss()) == 0.0
 
 
 def test_gather_audio_embeds_semantics():

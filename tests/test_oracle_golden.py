@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import path_oracle as po
-from oracle.make_golden import CASES, case_config, sub
+from oracle.make_golden import CASES, PROJECTOR_INIT, case_config, sub
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -17,8 +17,8 @@ def load_case(name):
     cfg, kind = case_config(spec)
     fx = np.load(os.path.join(GOLD, name + ".npz"))
     W = po.init_weights(cfg, seed=seed)
-    if kind == "qformer":
-        W["projector"] = po.init_qformer_weights(cfg, seed=seed + 1000)
+    if kind in PROJECTOR_INIT:
+        W["projector"] = PROJECTOR_INIT[kind](cfg, seed=seed + 1000)
     batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s, projector=kind)
     batch["input_ids"] = torch.from_numpy(fx["input_ids"])
     batch["labels"] = torch.from_numpy(fx["labels"])
@@ -26,7 +26,8 @@ def load_case(name):
     return cfg, fx, W, batch
 
 
-@pytest.mark.parametrize("name", ["small_b2_2s", "small_b3_ragged", "h2048_b2_2s", "small_b2_1s_pad30", "qformer_b2_2s"])
+@pytest.mark.parametrize("name", ["small_b2_2s", "small_b3_ragged", "h2048_b2_2s", "small_b2_1s_pad30", "qformer_b2_2s",
+                                  "mosa_b2_2s", "moe_b2_2s"])
 def test_oracle_matches_reference_fixture(name):
     torch.set_num_threads(os.cpu_count())
     cfg, fx, W, batch = load_case(name)
@@ -41,8 +42,10 @@ def test_oracle_matches_reference_fixture(name):
     assert int(mask[0].sum()) == L // 160
     # token-count arithmetic (a2) -- integers, exact
     n_a = po.projector_output_length(po.encoder_output_length(L // 160), cfg.proj_k)
-    if "query" in W["projector"]:
+    if po.projector_kind(W["projector"]) == "qformer":
         n_a = po.qformer_output_length(po.encoder_output_length(L // 160))
+    elif po.projector_kind(W["projector"]) == "mosa":
+        n_a = po.mosa_output_length(po.encoder_output_length(L // 160))
     assert np.array_equal(fx["audio_token_counts"], np.full(len(fx["audio_token_counts"]), n_a))
     # forward pieces + loss + grads + optimiser (a3-a12)
     res = po.train_step(W, batch, cfg, lr=1e-3, max_grad_norm=1.0, num_items_in_batch=n_items)
@@ -52,6 +55,8 @@ def test_oracle_matches_reference_fixture(name):
     assert np.abs(sub(parts["projector_out"], 8192) - fx["proj_sub"]).max() < 2e-4
     assert abs(float(res["loss"]) - float(fx["loss"])) < 2e-5
     assert abs(float(loss_mean) - float(fx["loss_mean_path"])) < 2e-5
+    if "aux_loss" in fx.files:      # moe: load-balance + z-loss, part of the loss above (asr_modeling.py:528-531)
+        assert float(fx["aux_loss"]) > 0 and abs(float(parts["aux_loss"]) - float(fx["aux_loss"])) < 1e-7
     lab_pos = torch.nn.functional.pad(batch["labels"], (0, 1), value=-100)[:, 1:] != -100
     assert np.abs(sub(logits[lab_pos], 8192) - fx["logits_lab_sub"]).max() < 2e-4
     # greedy ids: identical wherever the reference's top-1 margin exceeds fp32 noise

@@ -306,6 +306,87 @@ def test_qformer_projector_path(cuda):
     print(f"[qformer] worst projector-grad rel err {worst:.3e} over {len(res['grads'])} tensors")
 
 
+@pytest.mark.parametrize("kind", ["mosa", "moe"])
+def test_mixture_projector_modules_vs_oracle(cuda, kind):
+    """MOSAProjector / MoEAudioProjector in isolation on diverse (random) encoder frames, so that every expert is selected by
+    some token: forward output, aux loss and every parameter gradient against the oracle (pinned to the reference's classes)
+    on the SAME bf16-representable input and upstream gradient.  Both sides route in fp32, so the top-2 choice is identical;
+    the tolerance is the bf16-operand GEMM recipe vs fp32."""
+    from tiny_audio_b200.projectors import PROJECTOR_CLASSES
+
+    class Cfg:
+        encoder_dim, llm_dim, projector_pool_stride, projector_hidden_dim = 1280, 1024, 4, 1024
+        num_experts, num_experts_per_tok, router_aux_loss_coef, router_jitter_noise = 4, 2, 0.01, 0.0
+    cfg = po.small_config()
+    w = (po.init_mosa_weights if kind == "mosa" else po.init_moe_weights)(cfg, 31)
+    x = torch.randn(3, 203, cfg.enc_dim, generator=torch.Generator().manual_seed(5)).bfloat16()
+    m = PROJECTOR_CLASSES[kind](Cfg()).cuda()
+    m.load_state_dict(w, strict=True)
+    m.train()
+    y = m(x.cuda())
+    wr = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    ref = (po.mosa_projector_forward if kind == "mosa" else po.moe_projector_forward)(wr, x.float(), cfg)
+    aux_ref = torch.zeros(())
+    if kind == "moe":
+        ref, aux_ref = ref
+        _, _, _, top_i = po.moe_router(w, po.rms_norm(po.frame_stack(x.float(), 4), w["norm.weight"], 1e-6).reshape(-1, 5120))
+        assert torch.bincount(top_i.flatten(), minlength=4).min() > 0          # every expert is exercised
+        assert abs(float(m.get_aux_loss()) - float(aux_ref)) < 1e-5 * max(1.0, abs(float(aux_ref)))
+    assert y.shape == ref.shape
+    e_out = rel(y, ref)
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6))
+    ((ref * g).sum() + aux_ref).backward()
+    ((y * g.cuda()).sum() + (m.get_aux_loss() if kind == "moe" else 0.0)).backward()
+    torch.cuda.synchronize()
+    worst = max(rel(p.grad, wr[k].grad) for k, p in m.named_parameters())
+    print(f"[{kind} module] out rel {e_out:.3e}, worst grad rel {worst:.3e}")
+    assert e_out < 2e-2
+    for k, p in m.named_parameters():
+        assert rel(p.grad, wr[k].grad) < 4e-2, k
+
+
+@pytest.mark.parametrize("kind", ["mosa", "moe"])
+def test_mixture_projector_paths(cuda, kind):
+    """projector_type = mosa / moe (the two remaining names of the reference's PROJECTOR_CLASSES, projectors.py:482-487) through
+    the public ASRModel surface: CUDA encoder -> projector module on the tcgen05 GEMM -> CUDA decoder + CE, aux loss added
+    (asr_modeling.py:528-531).  Loss and projector gradients against the oracle and the reference-generated fixture."""
+    from oracle.make_golden import CASES, PROJECTOR_CONFIG_EXTRAS, PROJECTOR_INIT, case_config
+    from tiny_audio_b200.synthetic import build_offline_model
+    name = f"{kind}_b2_2s"
+    spec, B, clip_s, pad_s, R, seed = CASES[name]
+    cfg, _ = case_config(spec)
+    fx = np.load(os.path.join(GOLD, name + ".npz"))
+    W = po.init_weights(cfg, seed=seed)
+    W["projector"] = PROJECTOR_INIT[kind](cfg, seed=seed + 1000)
+    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, projector=kind)
+    n_items = int(fx["num_items"])
+    model = build_offline_model(PathDims.from_any(cfg.to_dict()), device="cuda", enc_state=W["encoder"], lm_state=W["lm"],
+                                proj_state=W["projector"], projector_type=kind, **PROJECTOR_CONFIG_EXTRAS.get(kind, {}))
+    model.train()
+    assert int(model.projector.get_output_length(100)) == int(fx["audio_token_counts"][0])
+    out = model(input_ids=batch["input_ids"].cuda(), input_features=batch["waveform"].cuda(), labels=batch["labels"],
+                attention_mask=batch["attention_mask"].cuda(), audio_token_counts=batch["audio_token_counts"].cuda(),
+                num_items_in_batch=n_items)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    res = po.train_step(W, batch, cfg, num_items_in_batch=n_items)
+    print(f"[{kind}] loss {float(out.loss):.5f} oracle {float(res['loss']):.5f} golden {float(fx['loss']):.5f}")
+    assert abs(float(out.loss) - float(res["loss"])) < 5e-3 and abs(float(out.loss) - float(fx["loss"])) < 5e-3
+    if kind == "moe":
+        assert abs(float(model.projector.get_aux_loss()) - float(fx["aux_loss"])) < 2e-2 * float(fx["aux_loss"])
+    worst = 0.0
+    gmax = max(float(g.norm()) for g in res["grads"].values())
+    for k, p in model.projector.named_parameters():
+        ref = res["grads"][k]
+        if float(ref.norm()) < 1e-5 * gmax:      # an expert no token selected: exactly zero on both sides
+            assert float(p.grad.float().norm()) < 1e-3 * gmax, k
+            continue
+        e = rel(p.grad, ref)
+        worst = max(worst, e)
+        assert e < 8e-2, f"{k}: {e}"
+    print(f"[{kind}] worst projector-grad rel err {worst:.3e} over {len(res['grads'])} tensors")
+
+
 def _lora_model_and_batch(seed=41, zero_b=False):
     from tiny_audio_b200.synthetic import build_offline_model
     cfg = po.small_config(enc_layers=2, lm_layers=3)

@@ -397,12 +397,16 @@ class ASRModel(PreTrainedModel, GenerationMixin):
                 lora_t = tuple(p for _, p in self.language_model.named_parameters())
             loss = _FusedPathLoss.apply(self, call, pr.linear_1.weight, pr.norm.weight, pr.linear_2.weight, pr.norm_2.weight, *lora_t)
         else:
-            # generic projector (qformer): frozen encoder -> projector module (autograd) -> CUDA decoder + CE with
+            # generic projector (qformer / mosa / moe): frozen encoder -> projector module (autograd) -> CUDA decoder + CE with
             # d(loss)/d(audio embeddings) handed back to autograd
             enc = hot.encode_audio(waveform=call.pop("waveform", None), input_features=call.pop("input_features", None),
                                    frame_keep_prob=call.pop("frame_keep_prob", None)).clone()
             audio = pr(enc)
             loss = _LmLossFn.apply(audio.float(), self, call)
+            if labels is not None and hasattr(pr, "get_aux_loss"):       # MoE load-balance + z-loss (asr_modeling.py:528-531)
+                aux = pr.get_aux_loss()
+                if aux is not None and aux.numel() > 0:
+                    loss = loss + aux.to(loss.device)
         if labels is None:
             loss = None
         return CausalLMOutputWithPast(loss=loss, logits=None)

@@ -6,7 +6,10 @@
 `MLPAudioProjector` keeps the reference's parameter names (`linear_1.weight`, `norm.weight`,
 `linear_2.weight`, `norm_2.weight`, all bias-free; projectors.py:23-71) so checkpoints interchange, but
 its arithmetic runs in libtinyaudio_b200 (frame-stack as a view, tcgen05 GEMMs, fused RMSNorm(+GELU)
-kernels, hand-written backward).  There is no PyTorch fallback: CPU tensors raise.
+kernels, hand-written backward).  `QFormerAudioProjector`, `MOSAProjector` and `MoEAudioProjector` (the other three
+registered names, projectors.py:482-487) run every wide linear -- forward, dgrad and wgrad -- on the same tcgen05 GEMM
+through `tc_linear`; the mixture projectors fold all their adapters into two GEMMs (`folded_adapter_mixture`).
+There is no PyTorch fallback: CPU tensors raise.
 """
 from __future__ import annotations
 
@@ -132,7 +135,8 @@ class MLPAudioProjector(nn.Module):
 
 class _TcLinearFn(torch.autograd.Function):
     """y = x W^T + b on the tcgen05 GEMM (bf16 operands, fp32 accumulate), with dgrad and wgrad on the same kernel:
-    dx = dy W,  dW = dy^T x (fp32 out, operands transposed by ta_transpose_bf16),  db = column sums of dy."""
+    dx = dy W,  dW = dy^T x (fp32 out; the TN form of the GEMM reads both row-major activations as MN-major operands, no
+    transposed copies),  db = column sums of dy."""
 
     @staticmethod
     def forward(ctx, x, w, b):
@@ -164,12 +168,16 @@ class _TcLinearFn(torch.autograd.Function):
             # the GEMM needs an output width that is a multiple of 128: all widths on this path are (1280, 5120, ...)
             dx = L.gemm(dy2, wt, epi=L.EPI_BF16).view(*lead, K).to(xdt)
         if ctx.needs_input_grad[1]:
-            Mp = (M + 7) // 8 * 8
-            dyt = torch.zeros(N, Mp, device=wb.device, dtype=BF16)
-            xt = torch.zeros(K, Mp, device=wb.device, dtype=BF16)
-            L.check(lib.ta_transpose_bf16(L.ptr(dy2), L.ptr(dyt), M, N, N, Mp, st))
-            L.check(lib.ta_transpose_bf16(L.ptr(x2), L.ptr(xt), M, K, K, Mp, st))
-            dw = L.gemm(dyt, xt, epi=L.EPI_F32, k=M).to(wdt)
+            if K % 128 == 0:
+                # weight-gradient form of the GEMM: dW = dy^T x straight from the row-major activations (both operands MN-major)
+                dw = L.gemm_tn(dy2, x2).to(wdt)
+            else:
+                Mp = (M + 7) // 8 * 8
+                dyt = torch.zeros(N, Mp, device=wb.device, dtype=BF16)
+                xt = torch.zeros(K, Mp, device=wb.device, dtype=BF16)
+                L.check(lib.ta_transpose_bf16(L.ptr(dy2), L.ptr(dyt), M, N, N, Mp, st))
+                L.check(lib.ta_transpose_bf16(L.ptr(x2), L.ptr(xt), M, K, K, Mp, st))
+                dw = L.gemm(dyt, xt, epi=L.EPI_F32, k=M).to(wdt)
         if bdt is not None and ctx.needs_input_grad[2]:
             db = dy2.float().sum(0).to(bdt)
         return dx, dw, db
@@ -263,26 +271,163 @@ class QFormerAudioProjector(nn.Module):
         return out
 
 
-class _NotOnThePath(nn.Module):
-    """mosa / moe are registered names in the reference (projectors.py:482-487) but no BASELINE config uses them
-    (out of scope); they fail loudly instead of silently running a different implementation."""
+class SimpleAdapter(nn.Module):
+    """Parameter holder with the reference's names (`fc1`, `fc2`, both with bias; projectors.py:90-100).  The arithmetic does
+    not run here: the mixture projectors below fold all adapters into two wide tcgen05 GEMMs."""
 
-    kind = "?"
+    def __init__(self, input_dim: int, hidden_dim: int, output_dim: int):
+        super().__init__()
+        self.fc1 = nn.Linear(input_dim, hidden_dim)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden_dim, output_dim)
+
+
+def folded_adapter_mixture(x, adapters, gates):
+    """sum_e gates[:, e] * adapter_e(x)  for 2-layer GELU adapters, as TWO GEMMs instead of 2 * E:
+
+        h   = x @ [W1_0; W1_1; ...]^T + [b1_0, b1_1, ...]                    one GEMM, N = E * hidden
+        out = [g_0 * gelu(h_0) | g_1 * gelu(h_1) | ...] @ [W2_0 | W2_1 | ...]^T  one GEMM, K = E * hidden
+              + gates @ [b2_0; b2_1; ...]
+
+    so the mixture is summed by the tensor core's fp32 accumulator (TMEM) rather than by E elementwise passes over the
+    outputs.  A gate of exactly 0 reproduces a token that did not select the expert (sparse top-k routing, evaluated densely:
+    no host sync on the routing decision, no ragged launches).  x [M, I] (any float dtype), gates [M, E] fp32.  Autograd
+    flows through `tc_linear` (dgrad + wgrad on the same GEMM kernel), the concatenations and the gate product."""
+    E = len(adapters)
+    hid = adapters[0].fc1.out_features
+    w1 = torch.cat([a.fc1.weight for a in adapters], dim=0)
+    b1 = torch.cat([a.fc1.bias for a in adapters], dim=0)
+    w2 = torch.cat([a.fc2.weight for a in adapters], dim=1)
+    b2 = torch.stack([a.fc2.bias for a in adapters], dim=0).float()
+    h = tc_linear(x, w1, b1)
+    act = torch.nn.functional.gelu(h.float()).view(-1, E, hid) * gates.unsqueeze(-1)
+    return tc_linear(act.view(-1, E * hid), w2).float() + gates @ b2
+
+
+class MOSAProjector(nn.Module):
+    """MOSA-Base projector (reference: tiny_audio/projectors.py:103-177): two k=3 / stride-2 convolutions with GELU (4x
+    downsampling), a 2-layer ReLU router, and a dense softmax mixture of 4 two-layer GELU adapters.  Same parameter names and
+    default initialisation as the reference (`downsampler.{0,2}`, `router.{0,2}`, `experts.{i}.fc{1,2}`), so checkpoints
+    interchange.  On the B200 path each convolution is an im2col view + one tcgen05 GEMM (K = 3 * C_in), the router's wide layer
+    is a GEMM, and the four adapters are folded into two GEMMs (`folded_adapter_mixture`); the 512 -> 4 router head, softmax
+    and GELU are PyTorch glue (< 1 % of the projector's FLOPs)."""
+
+    ADAPTER_HIDDEN_DIM = 4096
+    ROUTER_HIDDEN_DIM = 512
+    CONV_KERNEL = 3
+    CONV_STRIDE = 2
+    CONV_PADDING = 1
 
     def __init__(self, config):
         super().__init__()
-        raise NotImplementedError(
-            f"projector_type={self.kind!r} is not implemented in tiny_audio_b200 yet (hot-path scope: 'mlp'); "
-            "see DESIGN.md 'out of scope / next'.")
+        self.encoder_dim = getattr(config, "encoder_dim", None) or 1280
+        self.llm_dim = getattr(config, "llm_dim", None) or 2048
+        self.num_experts = getattr(config, "num_experts", None) or 4
+        conv = dict(kernel_size=self.CONV_KERNEL, stride=self.CONV_STRIDE, padding=self.CONV_PADDING)
+        self.downsampler = nn.Sequential(nn.Conv1d(self.encoder_dim, self.encoder_dim, **conv), nn.GELU(),
+                                         nn.Conv1d(self.encoder_dim, self.llm_dim, **conv), nn.GELU())
+        self.router = nn.Sequential(nn.Linear(self.llm_dim, self.ROUTER_HIDDEN_DIM), nn.ReLU(),
+                                    nn.Linear(self.ROUTER_HIDDEN_DIM, self.num_experts))
+        self.experts = nn.ModuleList([SimpleAdapter(self.llm_dim, self.ADAPTER_HIDDEN_DIM, self.llm_dim)
+                                      for _ in range(self.num_experts)])
+
+    def get_output_length(self, input_length):
+        length = input_length
+        for _ in range(2):
+            length = (length + 2 * self.CONV_PADDING - self.CONV_KERNEL) // self.CONV_STRIDE + 1
+        return length
+
+    def _conv_gelu(self, x, conv):
+        """Conv1d(k=3, s=2, p=1) + GELU on token-major activations: x [B, S, C] -> [B, S', C_out].  The im2col operand row for
+        output step t is (c, tap) -> x[2t - 1 + tap, c], which is exactly `weight.view(C_out, C * 3)`'s column order."""
+        F_ = torch.nn.functional
+        B = x.shape[0]
+        cols = F_.pad(x, (0, 0, self.CONV_PADDING, self.CONV_PADDING)).unfold(1, self.CONV_KERNEL, self.CONV_STRIDE)
+        y = tc_linear(cols.reshape(B, cols.shape[1], -1), conv.weight.reshape(conv.weight.shape[0], -1), conv.bias)
+        return F_.gelu(y.float())
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise L.TinyAudioB200Error("MOSAProjector runs only on CUDA (tiny_audio_b200 has no CPU fallback)")
+        return self._mixture(x)
+
+    def _mixture(self, x):
+        F_ = torch.nn.functional
+        x = self._conv_gelu(self._conv_gelu(x, self.downsampler[0]), self.downsampler[2])
+        B, n, D = x.shape
+        flat = x.reshape(B * n, D)
+        hidden = F_.relu(tc_linear(flat, self.router[0].weight, self.router[0].bias).float())
+        mix = torch.softmax(F_.linear(hidden, self.router[2].weight.float(), self.router[2].bias.float()), dim=-1)
+        return folded_adapter_mixture(flat, list(self.experts), mix).view(B, n, -1)
 
 
-def _stub(kind):
-    return type(f"{kind.upper()}ProjectorUnavailable", (_NotOnThePath,), {"kind": kind})
+class MoEAudioProjector(nn.Module):
+    """Shared + sparse mixture-of-experts projector (reference: tiny_audio/projectors.py:185-351): frame-stack -> RMSNorm ->
+    shared adapter + top-k of `num_experts` adapters, with the load-balance + z-loss auxiliary term exposed through
+    `get_aux_loss()` (added to the LM loss by ASRModel.forward, asr_modeling.py:528-531).  Parameter names, defaults and
+    `_init_weights` follow the reference.  The router (in_dim -> 4 logits, fp32 softmax, top-k, renormalisation with +1e-6,
+    multiplicative jitter in training mode) is PyTorch glue on the device -- no `.any()` / `torch.where` host syncs as in the
+    reference's dispatch loop; the shared adapter and the experts run as ONE folded mixture (gate 1 for the shared adapter,
+    the renormalised top-k weight or exactly 0 for each expert): two tcgen05 GEMMs forward, four backward."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.k = getattr(config, "projector_pool_stride", 4)
+        self.aux_coef = getattr(config, "router_aux_loss_coef", 0.01)
+        self.router_z_loss_coef = getattr(config, "router_z_loss_coef", 1e-4)
+        self.router_jitter_noise = getattr(config, "router_jitter_noise", 0.01)
+        in_dim = config.encoder_dim * self.k
+        out_dim = config.llm_dim
+        hidden_dim = getattr(config, "projector_hidden_dim", None) or out_dim
+        self.num_experts = getattr(config, "num_experts", 4)
+        self.top_k = getattr(config, "num_experts_per_tok", 2)
+        self.norm = _Gain(in_dim, 1e-6)
+        self.router = nn.Linear(in_dim, self.num_experts, bias=False)
+        self.experts = nn.ModuleList([SimpleAdapter(in_dim, hidden_dim, out_dim) for _ in range(self.num_experts)])
+        self.shared_expert = SimpleAdapter(in_dim, hidden_dim, out_dim)
+        with torch.no_grad():           # reference _init_weights (:242-251)
+            nn.init.normal_(self.router.weight, mean=0.0, std=0.02)
+            for adapter in [self.shared_expert, *self.experts]:
+                nn.init.xavier_uniform_(adapter.fc1.weight)
+                nn.init.normal_(adapter.fc2.weight, mean=0.0, std=0.01)
+        self.last_aux_loss = torch.tensor(0.0)
+
+    def get_output_length(self, input_length):
+        return frame_stack_length(input_length, self.k)
+
+    def get_aux_loss(self) -> torch.Tensor:
+        return self.last_aux_loss
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise L.TinyAudioB200Error("MoEAudioProjector runs only on CUDA (tiny_audio_b200 has no CPU fallback)")
+        return self._mixture(x)
+
+    def _mixture(self, x):
+        B, S, D = x.shape
+        n = frame_stack_length(S, self.k)
+        flat = x[:, : n * self.k].reshape(B * n, self.k * D).float()
+        flat = self.norm.weight.float() * (flat * torch.rsqrt(flat.pow(2).mean(-1, keepdim=True) + self.norm.variance_epsilon))
+        logits = torch.nn.functional.linear(flat, self.router.weight.float())
+        if self.training and self.router_jitter_noise > 0:
+            logits = logits * torch.empty_like(logits).uniform_(1.0 - self.router_jitter_noise, 1.0 + self.router_jitter_noise)
+        probs = torch.softmax(logits, dim=-1, dtype=torch.float32)
+        top_w, top_i = torch.topk(probs, self.top_k, dim=-1)
+        top_w = top_w / (top_w.sum(dim=-1, keepdim=True) + 1e-6)
+        if self.training:
+            balance = self.aux_coef * ((probs.mean(0) - 1.0 / self.num_experts) ** 2).mean() * self.num_experts
+            self.last_aux_loss = balance + self.router_z_loss_coef * torch.logsumexp(logits, dim=-1).pow(2).mean()
+        else:
+            self.last_aux_loss = torch.zeros((), device=x.device)
+        # gates [M, 1 + E]: the shared adapter always on, each expert with its renormalised top-k weight or exactly 0
+        gates = torch.cat([torch.ones_like(probs[:, :1]), torch.zeros_like(probs).scatter(1, top_i, top_w)], dim=1)
+        out = folded_adapter_mixture(flat, [self.shared_expert, *self.experts], gates)
+        return out.view(B, n, -1)
 
 
 PROJECTOR_CLASSES = {
     "mlp": MLPAudioProjector,
-    "mosa": _stub("mosa"),
-    "moe": _stub("moe"),
+    "mosa": MOSAProjector,
+    "moe": MoEAudioProjector,
     "qformer": QFormerAudioProjector,
 }

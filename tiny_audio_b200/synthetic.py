@@ -36,6 +36,10 @@ def synthetic_batch(dims: PathDims, batch: int, clip_seconds: float, seed: int =
     n_a = num_audio_tokens(n, dims.hop, dims.proj_k)
     if projector == "qformer":                      # ceil(S_e / 15) windows x 3 queries (projectors.py:422-430)
         n_a = (((n // dims.hop + 2 - 3) // 2 + 1) + 14) // 15 * 3
+    elif projector == "mosa":                       # two k=3, s=2, p=1 convolutions (projectors.py:172-177)
+        n_a = (n // dims.hop + 2 - 3) // 2 + 1
+        for _ in range(2):
+            n_a = (n_a + 2 - 3) // 2 + 1
     V = dims.vocab
 
     def tid(t):
@@ -89,7 +93,7 @@ class StubTokenizer:
 
 def build_offline_model(dims: PathDims, device="cuda", seed: int = 1234, enc_state=None, lm_state=None, proj_state=None,
                         audio_token_dropout: float = 0.0, projector_type: str = "mlp", use_lora: bool = False,
-                        freeze_projector: bool = False, freeze_language_model: bool = True):
+                        freeze_projector: bool = False, freeze_language_model: bool = True, **config_extras):
     """ASRModel (tiny_audio_b200.asr_modeling) with GLM-ASR / Qwen3 modules of the given dims, random (seeded) or
     supplied weights, fp32 masters -- no network, no checkpoints."""
     from transformers import GlmAsrEncoderConfig, Qwen3Config, Qwen3ForCausalLM
@@ -145,7 +149,7 @@ def build_offline_model(dims: PathDims, device="cuda", seed: int = 1234, enc_sta
     cfg = ASRConfig(audio_config=enc_cfg, text_config=txt_cfg, model_dtype="float32", attn_implementation="sdpa",
                     projector_type=projector_type, projector_pool_stride=dims.proj_k, projector_hidden_dim=dims.proj_hidden,
                     audio_token_dropout=audio_token_dropout, use_lora=use_lora, freeze_projector=freeze_projector,
-                    freeze_language_model=freeze_language_model)
+                    freeze_language_model=freeze_language_model, **config_extras)
     torch.manual_seed(seed + 3)
     model = _Offline(cfg)
     if proj_state is not None:
