@@ -47,6 +47,11 @@ def parse():
     ap.add_argument("--train-lm", action="store_true",
                     help="unfrozen-LM recipe (freeze_language_model: false, configs/experiments/embedded.yaml): the whole Qwen3 "
                          "decoder trains too -- weight-gradient GEMMs, 596 M-parameter AdamW, operand re-pack; NOT the headline workload")
+    ap.add_argument("--projector", default="mlp", choices=["mlp", "qformer", "mosa", "moe"],
+                    help="projector plugin (BASELINE configs[3] = qformer); non-mlp projectors run as modules on the tcgen05 GEMM "
+                         "between the CUDA encoder and the CUDA decoder -- NOT the headline workload")
+    ap.add_argument("--lora", action="store_true",
+                    help="BASELINE configs[4]: MLP projector + Qwen3 LoRA r=8 on q,k,v,o,gate,up,down -- NOT the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
@@ -162,7 +167,11 @@ def run_reference(args):
 
 def workload_config(args, n_gpus):
     recipe = "UNFROZEN Qwen3 decoder (freeze_language_model: false), " if getattr(args, "train_lm", False) else ""
-    return {"workload": f"tiny-audio train step: {recipe}MLP projector (hidden {args.proj_hidden}), GLM-ASR encoder 32L + Qwen3-0.6B 28L, "
+    if getattr(args, "lora", False):
+        recipe += "Qwen3 LoRA r=8 (q,k,v,o,gate,up,down) + "
+    kind = getattr(args, "projector", "mlp")
+    proj = f"MLP projector (hidden {args.proj_hidden})" if kind == "mlp" else f"{kind} projector"
+    return {"workload": f"tiny-audio train step: {recipe}{proj}, GLM-ASR encoder 32L + Qwen3-0.6B 28L, "
                         f"batch {args.batch}/GPU x {args.clip_seconds:g} s 16 kHz clips, response {args.response_len} tokens",
             "global_batch": args.batch * n_gpus, "clip_seconds": args.clip_seconds, "parallelism": f"dp{n_gpus}",
             "padding": "longest (equal-length clips)", "audio_token_dropout": 0.0, "grad_accum": 1,
@@ -189,13 +198,18 @@ def run_ours(args):
     lib = L.load()
 
     dims = PathDims(proj_hidden=args.proj_hidden)
-    model = build_offline_model(dims, device=dev, seed=1234, freeze_language_model=not args.train_lm)
+    generic = args.projector != "mlp" or args.lora           # routes through the public surface (module projector / adapters)
+    extras = dict(router_jitter_noise=0.0) if args.projector == "moe" else {}
+    model = build_offline_model(dims, device=dev, seed=1234, freeze_language_model=not args.train_lm, projector_type=args.projector,
+                                use_lora=args.lora, **extras)
     model.train()
     hot = model._hot_path()
     # the HF modules only own the fp32 master copies; free them (the packed bf16 copies in `hot` are what runs)
     names = [n for n, _ in model.projector.named_parameters()]
     params = [p for _, p in model.projector.named_parameters()]
-    if args.train_lm:
+    if generic and not args.train_lm:
+        opt = ClipAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, max_grad_norm=1.0)
+    elif args.train_lm:
         # the reference's parameter groups (scripts/train.py:384-437): `language_model.*` gets the decoder lr / weight decay,
         # norm gains are excluded from decay
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
@@ -207,7 +221,8 @@ def run_ours(args):
         opt = ClipAdamW(params, lr=1e-3, max_grad_norm=1.0)
 
     B = args.batch
-    host = synthetic_batch(dims, B, args.clip_seconds, seed=100 + rank, response_len=args.response_len, pin=True)
+    host = synthetic_batch(dims, B, args.clip_seconds, seed=100 + rank, response_len=args.response_len, pin=True,
+                           projector=args.projector)
     n_lab_local = int((host["labels"] != -100).sum())
     n_items_global = n_lab_local * world            # equal-length synthetic batches: arithmetic, no collective needed
     d_wave = host["input_features"].to(dev)
@@ -218,7 +233,7 @@ def run_ours(args):
     gmap = {n: p.grad for n, p in zip(names, params)}
 
     def step_resident():
-        if args.train_lm:      # unfrozen decoder: the public surface routes the ~310 LM parameters' gradients
+        if args.train_lm or generic:      # unfrozen decoder / module projector / LoRA: the public surface routes the gradients
             opt.zero_grad()
             out = model(input_ids=d_ids, input_features=d_wave, labels=labels_cpu, audio_token_counts=d_cnt,
                         num_items_in_batch=n_items_global)
@@ -357,7 +372,9 @@ def run_ours(args):
 
     cpu = None
     parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if generic and roof is not None:      # the 116 GFLOP/audio-s work figure is the MLP-projector path's
+        roof["step_tflops"] = roof["step_frac_of_sustained"] = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not generic:
         del model
         r = cpu_reference(args, 1, 1, args.cpu_sample_batch, keep_inputs=True)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}

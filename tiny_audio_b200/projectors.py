@@ -166,7 +166,9 @@ class _TcLinearFn(torch.autograd.Function):
             wt = torch.empty(K, N, device=wb.device, dtype=BF16)
             L.check(lib.ta_transpose_bf16(L.ptr(wb), L.ptr(wt), N, K, K, N, st))
             # the GEMM needs an output width that is a multiple of 128: all widths on this path are (1280, 5120, ...)
-            dx = L.gemm(dy2, wt, epi=L.EPI_BF16).view(*lead, K).to(xdt)
+            # fp32 activations in -> fp32 gradient out: the mixture projectors' gate gradients are sums over E * hidden products of
+            # this tensor with strong cancellation, a bf16 round trip here costs them several % (measured 6.8e-2 -> see tests)
+            dx = L.gemm(dy2, wt, epi=L.EPI_F32 if xdt == torch.float32 else L.EPI_BF16).view(*lead, K).to(xdt)
         if ctx.needs_input_grad[1]:
             if K % 128 == 0:
                 # weight-gradient form of the GEMM: dW = dy^T x straight from the row-major activations (both operands MN-major)
