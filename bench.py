@@ -52,6 +52,9 @@ def parse():
                          "between the CUDA encoder and the CUDA decoder -- NOT the headline workload")
     ap.add_argument("--lora", action="store_true",
                     help="BASELINE configs[4]: MLP projector + Qwen3 LoRA r=8 on q,k,v,o,gate,up,down -- NOT the headline workload")
+    ap.add_argument("--trace-kernels", default=None, metavar="FILE",
+                    help="after the timed region, run ONE more step under torch.profiler (CUPTI activity tracing, no replay) and write "
+                         "the per-kernel device-time table to FILE: the in-situ complement of the serialised ncu launch list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
@@ -178,6 +181,34 @@ def workload_config(args, n_gpus):
             "l2_policy": "per-step inputs+activations (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
+def trace_kernels(step, path, header):
+    """One step under torch.profiler; per-kernel device time (CUPTI activity records: real clocks, warm caches, no replay)."""
+    import collections
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        step()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        tot, cnt = collections.defaultdict(float), collections.Counter()
+        for ev in prof.events():
+            if getattr(ev, "device_type", None) is None or "cuda" not in str(ev.device_type).lower():
+                continue
+            us = float(getattr(ev, "device_time", 0.0) or getattr(ev, "cuda_time", 0.0) or 0.0)
+            name = ev.name.split("(")[0].replace("void ", "")
+            tot[name] += us
+            cnt[name] += 1
+        T = sum(tot.values())
+        lines = [header, f"total {T / 1000.0:.3f} ms of kernel time over {sum(cnt.values())} device activities (one step, in situ)"]
+        lines += [f"{v / 1000.0:9.3f} ms {100.0 * v / max(T, 1e-9):5.1f}%  n={cnt[k]:4d}  {k[:140]}"
+                  for k, v in sorted(tot.items(), key=lambda kv: -kv[1])]
+    except Exception as e:          # a diagnostic must never cost the bench line
+        lines = [header, f"trace failed: {type(e).__name__}: {e}"]
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
@@ -291,6 +322,9 @@ def run_ours(args):
     audio_s = B * world * args.clip_seconds
     value = audio_s / (ms_step / 1000.0)
 
+    if args.trace_kernels and rank == 0:
+        trace_kernels(step_resident, args.trace_kernels,
+                      f"# {workload_config(args, world)['workload']} -- {ms_step:.2f} ms/step measured without the profiler")
     e2e = None
     if not args.no_e2e:
         ms_e2e, _, _, _ = timed(step_e2e, args.steps, 2)

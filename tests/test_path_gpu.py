@@ -100,6 +100,32 @@ def test_small_configs_vs_oracle_and_golden(cuda, name):
         assert agree > 0.98, f"{k}: update sign agreement {agree}"
 
 
+def test_config2_shape_10s_clips_vs_oracle(cuda):
+    """BASELINE configs[1] geometry (MLP projector, 10 s clips: 160 000 samples -> 1000 mel frames -> 500 encoder frames -> 125 audio
+    tokens) at reduced depth and batch 4: token-count arithmetic exact, loss / projector gradients / one fused clip+AdamW step
+    against the oracle."""
+    cfg = po.small_config()
+    W, hp = build(cfg, 52)
+    batch = po.synthetic_batch(cfg, 4, 10.0, seed=52, response_len=24)
+    assert batch["waveform"].shape == (4, 160000) and int(batch["audio_token_counts"][0]) == 125
+    n_items = int((batch["labels"] != -100).sum())
+    loss, parts, params, grads = run_step(hp, W, batch, n_items)
+    assert tuple(parts["encoder_out"].shape) == (4, 500, cfg.enc_dim) and tuple(parts["projector_out"].shape)[:2] == (4, 125)
+    res = po.train_step(W, batch, cfg, lr=1e-3, max_grad_norm=1.0, num_items_in_batch=n_items)
+    print(f"[10 s] loss {float(loss):.5f} oracle {float(res['loss']):.5f}")
+    assert abs(float(loss) - float(res["loss"])) < 5e-3
+    for k in grads:
+        assert rel(grads[k], res["grads"][k]) < 6e-2, k
+    opt = FusedClipAdamW(list(params.values()), lr=1e-3, max_grad_norm=1.0)
+    opt.step(list(grads.values()))
+    torch.cuda.synchronize()
+    assert abs(float(opt.grad_norm()) - float(res["grad_norm"])) < 5e-2 * float(res["grad_norm"])
+    for k in params:        # the first AdamW step moves every element by ~lr * sign(g): compare the direction where |g| is not tiny
+        upd, ref = params[k].cpu() - W["projector"][k], res["params"][k] - W["projector"][k]
+        big = res["grads"][k].abs() > 1e-3 * res["grads"][k].abs().max()
+        assert float((torch.sign(upd[big]) == torch.sign(ref[big])).float().mean()) > 0.98, k
+
+
 def test_mel_features_path_matches_waveform_path(cuda):
     cfg = po.small_config(enc_layers=1, lm_layers=1)
     W, hp = build(cfg, 3)
