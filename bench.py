@@ -196,7 +196,7 @@ def trace_kernels(step, path, header):
             if getattr(ev, "device_type", None) is None or "cuda" not in str(ev.device_type).lower():
                 continue
             us = float(getattr(ev, "device_time", 0.0) or getattr(ev, "cuda_time", 0.0) or 0.0)
-            name = ev.name.split("(")[0].replace("void ", "")
+            name = ev.name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("(")[0].replace("void ", "")
             tot[name] += us
             cnt[name] += 1
         T = sum(tot.values())
