@@ -181,6 +181,27 @@ def workload_config(args, n_gpus):
             "l2_policy": "per-step inputs+activations (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
+def path_flops(dims, clip_seconds: float, S_lm: int, n_labelled: int, n_a: int, train_lm: bool = False):
+    """FLOPs of one train step per clip (2 FLOP/MAC, causal attention counted at half, attention backward = 2.5 x forward):
+    SURVEY.md section 8d's general formula.  `reference`: the work the reference path does (lm_head + its dgrad on ALL S_lm
+    positions) -- the figure section 8d quotes (3.49 TFLOP per 30 s clip = 116 GFLOP per audio-second at S_lm = 464);
+    `executed`: what this implementation launches (lm_head and its dgrad only on the labelled rows)."""
+    d = dims
+    T = int(clip_seconds * 16000) // d.hop
+    S_e = (T + 2 - 3) // 2 + 1
+    D, Fe, Le = d.enc_dim, d.enc_ffn, d.enc_layers
+    enc = 2.0 * S_e * Le * (4 * D * D + 2 * D * Fe) + 4.0 * S_e * S_e * D * Le + 2.0 * T * d.n_mels * D * 3 + 2.0 * S_e * D * D * 3
+    kD, H, O = d.proj_k * D, d.proj_hidden, d.lm_dim
+    proj = 2.0 * n_a * (kD * H + H * O) + 2.0 * n_a * kD * H + 4.0 * n_a * H * O          # fwd + wgrad W1 + (wgrad, dgrad) W2
+    QD, KD = d.lm_heads * d.lm_head_dim, d.lm_kv_heads * d.lm_head_dim
+    p_lin = d.lm_layers * (O * (QD + 2 * KD) + QD * O + 3 * O * d.lm_ffn)
+    lm = 4.0 * S_lm * p_lin + 3.5 * (2.0 * S_lm * S_lm * QD * d.lm_layers)
+    if train_lm:
+        lm += 2.0 * S_lm * p_lin + 2.0 * d.vocab * O * n_labelled                         # weight gradients (body + tied head)
+    head = 4.0 * d.vocab * O
+    return {"reference": enc + proj + lm + head * S_lm, "executed": enc + proj + lm + head * n_labelled}
+
+
 def trace_kernels(step, path, header):
     """One step under torch.profiler; per-kernel device time (CUPTI activity records: real clocks, warm caches, no replay)."""
     import collections
@@ -360,8 +381,16 @@ def run_ours(args):
                 # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
                 # (profiles/r01_ncu_top_kernels_summary.txt: 136.2 MB + 440.4 MB; algorithmic A + W + C = 626.7 MB, part of C stays in L2)
                 "traffic": 576.5e6 if (M, N, K) == (48000, 5120, 1280) else None,
-                "algorithmic_bytes": 2.0 * (M * K + N * K + M * N), "tensor_pipe_active_pct_ncu": 74.5, "step_tflops": 116.0e9 * audio_s / (ms_step / 1000.0) / 1e12 / world,
-                "step_frac_of_sustained": 116.0e9 * audio_s / (ms_step / 1000.0) / 1e12 / world / pk["bf16_tflops_sustained"]}
+                "algorithmic_bytes": 2.0 * (M * K + N * K + M * N), "tensor_pipe_active_pct_ncu": 74.5}
+        # whole step as TFLOP/s per GPU: SURVEY 8d's work figure (the reference's work) and the work actually launched
+        fl = path_flops(dims, args.clip_seconds, int(host["input_ids"].shape[1]), n_lab_local // B, int(host["audio_token_counts"][0]),
+                        train_lm=args.train_lm)
+        per_s = B / (ms_step / 1000.0) / 1e12
+        roof.update({"step_tflops": fl["reference"] * per_s, "step_frac_of_sustained": fl["reference"] * per_s / pk["bf16_tflops_sustained"],
+                     "step_tflops_executed": fl["executed"] * per_s,
+                     "work": {"gflop_per_audio_second_reference_path": fl["reference"] / args.clip_seconds / 1e9,
+                              "gflop_per_audio_second_executed": fl["executed"] / args.clip_seconds / 1e9,
+                              "note": "reference path = SURVEY 8d formula (lm_head on all positions); executed = lm_head on labelled rows only"}})
         # the Qwen3 FFN GEMMs the north star names (M = B x S_lm tokens, dim 1024, ffn 3072), timed alone the same way, with the
         # epilogues the training step uses: gate_up with fused SwiGLU + (gate, up) stash for the backward; down + fp32 residual
         S_lm = int(host["input_ids"].shape[1])
@@ -397,17 +426,12 @@ def run_ours(args):
             "down_resid": {"us": t_dn * 1e6, "tflops": f_dn / t_dn / 1e12, "frac": f_dn / t_dn / 1e12 / peak},
             "tensor_pipe_active_pct_ncu": {"gate_up_swiglu_stash": 65.0, "source": "profiles/r01_ncu_top_kernels_summary.txt"}}
         del xq, wgu, hq, guq, wdn, rq, yq
-        if args.train_lm:      # + weight-gradient GEMMs of the decoder: 2 * P_lm_lin * S_lm (body) + 2 * P_head * n_labelled (tied head)
-            extra = (2.0 * 440.4e6 * 464 + 2.0 * 155.6e6 * (args.response_len + 1)) / args.clip_seconds
-            gf = 116.0e9 + extra
-            roof["step_tflops"] = gf * audio_s / (ms_step / 1000.0) / 1e12 / world
-            roof["step_frac_of_sustained"] = roof["step_tflops"] / pk["bf16_tflops_sustained"]
         del a, w, out
 
     cpu = None
     parity = None
     if generic and roof is not None:      # the 116 GFLOP/audio-s work figure is the MLP-projector path's
-        roof["step_tflops"] = roof["step_frac_of_sustained"] = None
+        roof["step_tflops"] = roof["step_frac_of_sustained"] = roof["step_tflops_executed"] = roof["work"] = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not generic:
         del model
         r = cpu_reference(args, 1, 1, args.cpu_sample_batch, keep_inputs=True)
