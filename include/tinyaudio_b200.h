@@ -129,6 +129,14 @@ int ta_ce_fwd_bwd(void* logits_bf16, long long ld, const int* targets, long long
                   float* loss_sum, float* row_loss, int write_grad, void* stream);
 int ta_transpose_bf16(const void* in, void* out, int R, int C, long long ld_in, long long ld_out, void* stream);
 int ta_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+/* a6. QFormer projector window attention (tiny_audio/projectors.py:431-475 -> HF:models/blip_2/modeling_blip_2.py:579-634):
+ *     per (window, head): out = dropout(softmax(scale * q k^T)) v with nq <= 4 queries, nk <= 16 keys, head_dim <= 96.
+ *     q, out, dq bf16 [n_win, nq, heads*head_dim]; k, v, dk, dv bf16 [n_win, nk, heads*head_dim];
+ *     drop_mask NULL or f32 [n_win, heads, nq, nk] holding 0 or 1/(1-p) (what F.dropout multiplies by). */
+int ta_window_attn_fwd(const void* q, const void* k, const void* v, const float* drop_mask, void* out, long long n_win, int nq,
+                       int nk, int heads, int head_dim, float scale, void* stream);
+int ta_window_attn_bwd(const void* q, const void* k, const void* v, const float* drop_mask, const void* d_out, void* dq, void* dk,
+                       void* dv, long long n_win, int nq, int nk, int heads, int head_dim, float scale, void* stream);
 /* tiny_audio/projectors.py:79-87 (_frame_stack): row j <- frames k*j .. k*j+k-1, feature-major per frame */
 int ta_frame_stack(const void* x /*bf16 [B,S,D]*/, void* out /*bf16 [B,n,k*D]*/, int B, int S, int n, int k, int D, void* stream);
 

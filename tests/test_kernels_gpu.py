@@ -650,3 +650,42 @@ def test_gemm_tail_wave_split(cuda):
     wd_t = rnd(Fd, 256, seed=8, scale=0.1)
     a, b = both(lambda: L.gemm(dy, wd_t, epi=L.EPI_SWIGLU_BWD, aux=gu))
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n_win,nq,nk,heads,hd,p_drop", [(37, 3, 3, 16, 80, 0.0), (37, 3, 15, 16, 80, 0.0), (200, 3, 15, 16, 80, 0.1),
+                                                        (5, 1, 16, 4, 96, 0.3), (9, 4, 7, 3, 64, 0.0), (3, 2, 1, 2, 33, 0.0)])
+def test_window_attention_fwd_bwd(cuda, n_win, nq, nk, heads, hd, p_drop):
+    """QFormer window attention kernel (ta_window_attn_fwd / _bwd) against fp32 torch autograd on the same bf16 inputs, with and
+    without a dropout mask (HF:models/blip_2/modeling_blip_2.py:579-634)."""
+    from tiny_audio_b200.projectors import _WindowAttnFn
+    H = heads * hd
+    q, k, v = rnd(n_win, nq, H, seed=1), rnd(n_win, nk, H, seed=2), rnd(n_win, nk, H, seed=3)
+    g = rnd(n_win, nq, H, seed=4)
+    mask = None
+    if p_drop > 0:
+        torch.manual_seed(7)
+        mask = F.dropout(torch.ones(n_win, heads, nq, nk, device="cuda"), p_drop, True).contiguous()
+    qa, ka, va = (t.clone().requires_grad_(True) for t in (q, k, v))
+    out = _WindowAttnFn.apply(qa, ka, va, mask, heads)
+    out.backward(g)
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    qh, kh, vh = (t.view(n_win, -1, heads, hd).transpose(1, 2) for t in (qr, kr, vr))
+    probs = torch.softmax(qh @ kh.transpose(-1, -2) / hd ** 0.5, dim=-1)
+    if mask is not None:
+        probs = probs * mask
+    ref = (probs @ vh).transpose(1, 2).reshape(n_win, nq, H)
+    ref.backward(g.float())
+    assert out.dtype == BF16 and out.shape == ref.shape
+    assert rel_err(out, ref) < 6e-3                                   # bf16 output rounding
+    for name, a, r in (("dq", qa.grad, qr.grad), ("dk", ka.grad, kr.grad), ("dv", va.grad, vr.grad)):
+        if nk == 1 and name in ("dq", "dk"):                          # one key: softmax is constant, gradients are exactly zero
+            assert float(a.float().abs().max()) == 0.0 and float(r.abs().max()) < 1e-6
+            continue
+        assert rel_err(a, r) < 6e-3, name
+
+
+def test_window_attention_rejects_unsupported_shapes(cuda):
+    lib = L.load()
+    t = rnd(2, 5, 128, seed=1)
+    rc = lib.ta_window_attn_fwd(L.ptr(t), L.ptr(t), L.ptr(t), None, L.ptr(torch.empty_like(t)), 2, 5, 5, 2, 64, 0.125, L.stream_ptr())
+    assert rc != 0 and b"queries per window" in lib.ta_last_error_string()

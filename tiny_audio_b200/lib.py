@@ -95,6 +95,8 @@ _SIGS = {
     "ta_transpose_bf16": ([P, P, c_int, c_int, c_ll, c_ll, P], c_int),
     "ta_cast_f32_bf16": ([P, P, c_ll, P], c_int),
     "ta_frame_stack": ([P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "ta_window_attn_fwd": ([P, P, P, P, P, c_ll, c_int, c_int, c_int, c_int, c_float, P], c_int),
+    "ta_window_attn_bwd": ([P, P, P, P, P, P, P, P, c_ll, c_int, c_int, c_int, c_int, c_float, P], c_int),
     "ta_grad_sumsq": ([P, c_ll, P, P], c_int),
     "ta_adamw_clip_step": ([P, P, P, P, c_ll, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P, P], c_int),
     "ta_encoder_workspace_bytes": ([C.POINTER(EncoderWeights), c_int, c_int, C.POINTER(c_ll)], c_int),

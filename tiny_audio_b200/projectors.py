@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -189,13 +190,59 @@ def tc_linear(x, weight, bias=None):
     return _TcLinearFn.apply(x, weight, bias)
 
 
+class _WindowAttnFn(torch.autograd.Function):
+    """dropout(softmax(q k^T / sqrt(hd))) v per (window, head) for the QFormer's tiny attention problems (3 queries x 3 or 15
+    keys x 80): one warp per (window, head) in csrc/window_attn.cu, bf16 in / out, probabilities recomputed in the backward."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, drop_mask, heads):
+        from .engine import BF16
+        lib = L.load()
+        L.require_cuda(q, k, v)
+        Wn, nq, H = q.shape
+        nk = k.shape[1]
+        hd = H // heads
+        qb, kb, vb = (t.detach().to(BF16).contiguous() for t in (q, k, v))
+        out = torch.empty_like(qb)
+        scale = 1.0 / math.sqrt(hd)
+        L.check(lib.ta_window_attn_fwd(L.ptr(qb), L.ptr(kb), L.ptr(vb), L.ptr(drop_mask), L.ptr(out), Wn, nq, nk, heads, hd, scale,
+                                       L.stream_ptr()))
+        ctx.save_for_backward(qb, kb, vb, drop_mask)
+        ctx.meta = (heads, scale, q.dtype, k.dtype, v.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from .engine import BF16
+        lib = L.load()
+        qb, kb, vb, drop_mask = ctx.saved_tensors
+        heads, scale, qdt, kdt, vdt = ctx.meta
+        Wn, nq, H = qb.shape
+        nk = kb.shape[1]
+        gb = g.detach().to(BF16).contiguous()
+        dq, dk, dv = torch.empty_like(qb), torch.empty_like(kb), torch.empty_like(vb)
+        L.check(lib.ta_window_attn_bwd(L.ptr(qb), L.ptr(kb), L.ptr(vb), L.ptr(drop_mask), L.ptr(gb), L.ptr(dq), L.ptr(dk), L.ptr(dv),
+                                       Wn, nq, nk, heads, H // heads, scale, L.stream_ptr()))
+        return dq.to(qdt), dk.to(kdt), dv.to(vdt), None, None
+
+
+def window_attention(q, k, v, heads: int, dropout_p: float = 0.0, training: bool = False):
+    """q [W, nq, H], k / v [W, nk, H] -> [W, nq, H] bf16.  Dropout on the probabilities uses torch's RNG (F.dropout on a tensor of
+    ones gives the 0 or 1/(1-p) multipliers), so seeding behaves like the reference's nn.Dropout."""
+    mask = None
+    if training and dropout_p > 0.0:
+        mask = torch.nn.functional.dropout(torch.ones(q.shape[0], heads, q.shape[1], k.shape[1], device=q.device,
+                                                      dtype=torch.float32), dropout_p, True).contiguous()
+    return _WindowAttnFn.apply(q, k, v, mask, heads)
+
+
 class QFormerAudioProjector(nn.Module):
     """BLIP-2 QFormer projector with learnable queries (reference: tiny_audio/projectors.py:359-475; arithmetic of
     HF:models/blip_2/modeling_blip_2.py:537-1042).  Parameter names and initialisation are the reference's (the HF
     `Blip2QFormerModel` is instantiated as the owner of the weights, exactly as the reference does), so checkpoints
     interchange.  Every linear -- q/k/v/o of self- and cross-attention, the FFN, the final projection; forward, dgrad and
-    wgrad -- runs on the tcgen05 GEMM; LayerNorm, the 3x3 / 3x15 softmax attention and GELU are PyTorch glue (< 1 % of the
-    projector's FLOPs; dedicated kernels are a 'next' item in DESIGN.md)."""
+    wgrad -- runs on the tcgen05 GEMM; the 3x3 / 3x15 softmax attention is one warp per (window, head) in csrc/window_attn.cu
+    (forward and backward); LayerNorm, GELU and the residual adds are PyTorch glue."""
 
     def __init__(self, config):
         super().__init__()
@@ -219,6 +266,8 @@ class QFormerAudioProjector(nn.Module):
         self.qformer = AutoModel.from_config(qcfg)      # weight owner only; its forward is never called
         self.linear = nn.Linear(hidden, llm_dim)
         self.p_hidden, self.p_attn, self.ln_eps = 0.1, 0.1, 1e-12
+        # window attention kernel (csrc/window_attn.cu) instead of batched fp32 matmuls + softmax + transposes in PyTorch
+        self.fused_attention = os.environ.get("TA_QFORMER_FUSED_ATTN", "1") != "0"
 
     def get_output_length(self, input_length):
         nblocks = (input_length + self.window_size - 1) // self.window_size
@@ -232,12 +281,15 @@ class QFormerAudioProjector(nn.Module):
         q = tc_linear(x, att.attention.query.weight, att.attention.query.bias)
         k = tc_linear(kv_src, att.attention.key.weight, att.attention.key.bias)
         v = tc_linear(kv_src, att.attention.value.weight, att.attention.value.bias)
-        q = q.view(Wn, nq, self.num_heads, hd).transpose(1, 2).float()
-        k = k.view(Wn, -1, self.num_heads, hd).transpose(1, 2).float()
-        v = v.view(Wn, -1, self.num_heads, hd).transpose(1, 2).float()
-        probs = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
-        probs = F_.dropout(probs, self.p_attn, self.training)
-        ctx = (probs @ v).transpose(1, 2).reshape(Wn, nq, H)
+        if self.fused_attention:
+            ctx = window_attention(q, k, v, self.num_heads, self.p_attn, self.training)
+        else:       # PyTorch glue (A/B reference for the kernel)
+            q = q.view(Wn, nq, self.num_heads, hd).transpose(1, 2).float()
+            k = k.view(Wn, -1, self.num_heads, hd).transpose(1, 2).float()
+            v = v.view(Wn, -1, self.num_heads, hd).transpose(1, 2).float()
+            probs = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
+            probs = F_.dropout(probs, self.p_attn, self.training)
+            ctx = (probs @ v).transpose(1, 2).reshape(Wn, nq, H)
         o = tc_linear(ctx, att.output.dense.weight, att.output.dense.bias).float()
         o = F_.dropout(o, self.p_hidden, self.training)
         return F_.layer_norm(o + x.float(), (H,), att.output.LayerNorm.weight.float(), att.output.LayerNorm.bias.float(), self.ln_eps)
