@@ -216,6 +216,8 @@ def trace_kernels(step, path, header):
         for ev in prof.events():
             if getattr(ev, "device_type", None) is None or "cuda" not in str(ev.device_type).lower():
                 continue
+            if "#" in ev.name:          # profiler annotation ranges mirrored onto the device timeline (Optimizer.step#...), not kernels
+                continue
             us = float(getattr(ev, "device_time", 0.0) or getattr(ev, "cuda_time", 0.0) or 0.0)
             name = ev.name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("(")[0].replace("void ", "")
             tot[name] += us
