@@ -137,6 +137,9 @@ int ta_window_attn_fwd(const void* q, const void* k, const void* v, const float*
                        int nk, int heads, int head_dim, float scale, void* stream);
 int ta_window_attn_bwd(const void* q, const void* k, const void* v, const float* drop_mask, const void* d_out, void* dq, void* dk,
                        void* dv, long long n_win, int nq, int nk, int heads, int head_dim, float scale, void* stream);
+/* A/B switch: 1 = lanes over head_dim (any head_dim), 2 = key per lane with 16-byte accesses (head_dim % 8 == 0, else falls back
+ * to 1); returns the previous setting */
+int ta_window_attn_set_variant(int variant);
 /* tiny_audio/projectors.py:79-87 (_frame_stack): row j <- frames k*j .. k*j+k-1, feature-major per frame */
 int ta_frame_stack(const void* x /*bf16 [B,S,D]*/, void* out /*bf16 [B,n,k*D]*/, int B, int S, int n, int k, int D, void* stream);
 

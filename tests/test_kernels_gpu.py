@@ -652,11 +652,21 @@ def test_gemm_tail_wave_split(cuda):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("n_win,nq,nk,heads,hd,p_drop", [(37, 3, 3, 16, 80, 0.0), (37, 3, 15, 16, 80, 0.0), (200, 3, 15, 16, 80, 0.1),
                                                         (5, 1, 16, 4, 96, 0.3), (9, 4, 7, 3, 64, 0.0), (3, 2, 1, 2, 33, 0.0)])
-def test_window_attention_fwd_bwd(cuda, n_win, nq, nk, heads, hd, p_drop):
-    """QFormer window attention kernel (ta_window_attn_fwd / _bwd) against fp32 torch autograd on the same bf16 inputs, with and
-    without a dropout mask (HF:models/blip_2/modeling_blip_2.py:579-634)."""
+def test_window_attention_fwd_bwd(cuda, n_win, nq, nk, heads, hd, p_drop, variant):
+    """QFormer window attention kernels (ta_window_attn_fwd / _bwd, both formulations; variant 2 falls back to 1 when
+    head_dim % 8 != 0) against fp32 torch autograd on the same bf16 inputs, with and without a dropout mask
+    (HF:models/blip_2/modeling_blip_2.py:579-634)."""
+    prev = L.load().ta_window_attn_set_variant(variant)
+    try:
+        _window_attention_case(n_win, nq, nk, heads, hd, p_drop)
+    finally:
+        L.load().ta_window_attn_set_variant(prev)
+
+
+def _window_attention_case(n_win, nq, nk, heads, hd, p_drop):
     from tiny_audio_b200.projectors import _WindowAttnFn
     H = heads * hd
     q, k, v = rnd(n_win, nq, H, seed=1), rnd(n_win, nk, H, seed=2), rnd(n_win, nk, H, seed=3)

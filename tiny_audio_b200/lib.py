@@ -97,6 +97,7 @@ _SIGS = {
     "ta_frame_stack": ([P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
     "ta_window_attn_fwd": ([P, P, P, P, P, c_ll, c_int, c_int, c_int, c_int, c_float, P], c_int),
     "ta_window_attn_bwd": ([P, P, P, P, P, P, P, P, c_ll, c_int, c_int, c_int, c_int, c_float, P], c_int),
+    "ta_window_attn_set_variant": ([c_int], c_int),
     "ta_grad_sumsq": ([P, c_ll, P, P], c_int),
     "ta_adamw_clip_step": ([P, P, P, P, c_ll, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P, P], c_int),
     "ta_encoder_workspace_bytes": ([C.POINTER(EncoderWeights), c_int, c_int, C.POINTER(c_ll)], c_int),
@@ -149,6 +150,8 @@ def load() -> C.CDLL:
         lib.ta_gemm_set_cta_pair(int(os.environ["TA_GEMM_CTA_PAIR"]))
     if os.environ.get("TA_GEMM_TAIL_SPLIT") is not None:
         lib.ta_gemm_set_tail_split(int(os.environ["TA_GEMM_TAIL_SPLIT"]))
+    if os.environ.get("TA_WINDOW_ATTN_VARIANT") is not None:
+        lib.ta_window_attn_set_variant(int(os.environ["TA_WINDOW_ATTN_VARIANT"]))
     if os.environ.get("TA_ATTN_TC") is not None:
         lib.ta_attn_set_tc(int(os.environ["TA_ATTN_TC"]))
     _lib = lib
