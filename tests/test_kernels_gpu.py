@@ -1,6 +1,7 @@
 """Unit parity of each CUDA kernel against a plain torch fp32 statement of the same op (-m gpu)."""
 import ctypes as C
 import math
+import os
 
 import pytest
 import torch
@@ -652,9 +653,17 @@ def test_gemm_tail_wave_split(cuda):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
-@pytest.mark.parametrize("n_win,nq,nk,heads,hd,p_drop", [(37, 3, 3, 16, 80, 0.0), (37, 3, 15, 16, 80, 0.0), (200, 3, 15, 16, 80, 0.1),
-                                                        (5, 1, 16, 4, 96, 0.3), (9, 4, 7, 3, 64, 0.0), (3, 2, 1, 2, 33, 0.0)])
+# variant 2 (key per lane): its hardware run was cut off by the GPU budget after the first three geometries below -- the QFormer's
+# production shapes, with and without the dropout mask -- had passed in BOTH variants; the remaining variant-2 geometries are checked
+# against a scalar emulation of the kernel's index logic only and stay opt-in (TA_TEST_WINDOW_ATTN_V2=1) until seen green on a B200.
+# The library default is variant 1.
+_WINDOW_SHAPES = [(37, 3, 3, 16, 80, 0.0), (37, 3, 15, 16, 80, 0.0), (200, 3, 15, 16, 80, 0.1), (5, 1, 16, 4, 96, 0.3), (9, 4, 7, 3, 64, 0.0),
+                  (3, 2, 1, 2, 33, 0.0)]
+_WINDOW_CASES = [c + (1,) for c in _WINDOW_SHAPES] + [c + (2,) for c in
+                                                      (_WINDOW_SHAPES if os.environ.get("TA_TEST_WINDOW_ATTN_V2") == "1" else _WINDOW_SHAPES[:3])]
+
+
+@pytest.mark.parametrize("n_win,nq,nk,heads,hd,p_drop,variant", _WINDOW_CASES)
 def test_window_attention_fwd_bwd(cuda, n_win, nq, nk, heads, hd, p_drop, variant):
     """QFormer window attention kernels (ta_window_attn_fwd / _bwd, both formulations; variant 2 falls back to 1 when
     head_dim % 8 != 0) against fp32 torch autograd on the same bf16 inputs, with and without a dropout mask
