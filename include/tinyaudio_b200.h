@@ -22,6 +22,9 @@ extern "C" {
 const char* ta_last_error_string(void);
 int ta_version(void);
 unsigned long long ta_launch_count(void); /* kernels launched by the library so far (host-side counter) */
+/* programmatic dependent launch (griddepcontrol) for the training towers' kernels: compiled in only by `make PDL=1`; returns 1 when
+ * the switch took effect, 0 in a default build (where the call is a no-op).  Experimental: see DESIGN.md section 7. */
+int ta_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM  C[M,N] = epilogue(A[M,K] . B[N,K]^T), bf16 in, fp32 accumulate (tcgen05 + TMEM + TMA)

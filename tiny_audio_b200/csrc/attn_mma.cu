@@ -209,6 +209,7 @@ attn_fwd_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K, const bf
 template <int HD>
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ D,
                                      int B, int S, int Hq, long long o_rs, long long do_rs) {
+    TA_PDL_ENTRY();
     // HD / 8 lanes per (token, head), 16-byte loads: a warp reads 512 contiguous bytes of O and of dO
     constexpr int LPH = HD / 8;
     const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPH;
@@ -491,9 +492,8 @@ TA_API int ta_attn_bwd(const void* q, const void* k, const void* v, const void* 
     constexpr int HD = 128;
     {
         const long long threads = (long long)B * S * Hq * (HD / 8);
-        attn_bwd_prep_kernel<HD><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-            (const bf16*)o, (const bf16*)d_o, dsum_ws, B, S, Hq, o_rs, do_rs);
-        TA_LAUNCH_CHECK();
+        TA_KERNEL_LAUNCH(attn_bwd_prep_kernel<HD>, (unsigned)((threads + 255) / 256), 256, 0, st, (const bf16*)o, (const bf16*)d_o, dsum_ws, B,
+                         S, Hq, o_rs, do_rs);
     }
     TA_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)B * S * dq_rs, st));
     if (k_attn_tc_enabled()) {   // tcgen05 kernel (attn_tc_bwd.cu); the mma.sync kernel below stays as A/B reference

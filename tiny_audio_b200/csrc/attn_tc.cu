@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttCfg<HD>::CTAS_PER_SM)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int Hq, int Hkv,
                    long long o_rs, float scale_log2) {
+    TA_PDL_ENTRY();
     using C = AttCfg<HD>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -321,8 +322,7 @@ int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
         done = true;
     }
     dim3 grid((S + BQ - 1) / BQ, Hq, B);
-    kern<<<grid, ATT_THREADS, C::SMEM, st>>>(tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f);
-    TA_LAUNCH_CHECK();
+    TA_KERNEL_LAUNCH(kern, grid, ATT_THREADS, C::SMEM, st, tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f);
     return 0;
 }
 
@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(ATT1_THREADS, 2)
 attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int Hq, int Hkv,
                     long long o_rs, float scale_log2) {
+    TA_PDL_ENTRY();
     using C = Att1Cfg<HD>;
     extern __shared__ __align__(1024) uint8_t smem_al[];
     uint8_t* smem = smem_al;
@@ -601,8 +602,7 @@ int launch_attn_tc1(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
         done = true;
     }
     dim3 grid((S + BQ - 1) / BQ, Hq, B);
-    kern<<<grid, ATT1_THREADS, C::SMEM, st>>>(tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f);
-    TA_LAUNCH_CHECK();
+    TA_KERNEL_LAUNCH(kern, grid, ATT1_THREADS, C::SMEM, st, tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f);
     return 0;
 }
 

@@ -51,6 +51,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const float* __restrict__ LSE, const float* __restrict__ Dsum, float* __restrict__ dQacc,
                    bf16* __restrict__ dK, bf16* __restrict__ dV, int S, int Hq, int Hkv, long long dq_rs, long long dk_rs,
                    long long dv_rs, float scale, float scale_log2, int dbg) {
+    TA_PDL_ENTRY();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -324,9 +325,8 @@ int k_attn_tc_bwd(const bf16* q, const bf16* k, const bf16* v, const bf16* d_o, 
         done = true;
     }
     dim3 grid((S + BT - 1) / BT, Hkv, B);
-    attn_tc_bwd_kernel<<<grid, BWD_THREADS, SMEM_BWD, st>>>(tq, tk, tv, tdo, lse, dsum, dq_acc, dk, dv, S, Hq, Hkv, dq_rs, dk_rs, dv_rs,
-                                                           scale, scale * 1.4426950408889634f, g_bwd_dbg);
-    TA_LAUNCH_CHECK();
+    TA_KERNEL_LAUNCH(attn_tc_bwd_kernel, grid, BWD_THREADS, SMEM_BWD, st, tq, tk, tv, tdo, lse, dsum, dq_acc, dk, dv, S, Hq, Hkv, dq_rs, dk_rs,
+                     dv_rs, scale, scale * 1.4426950408889634f, g_bwd_dbg);
     *handled = 1;
     return 0;
 }

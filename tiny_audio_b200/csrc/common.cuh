@@ -64,6 +64,40 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 #endif
 
+// PDL for the TRAINING towers is compile-gated (make PDL=1 -> -DTA_PDL): in a default build TA_PDL_ENTRY() is empty and
+// TA_KERNEL_LAUNCH is the plain <<< >>> launch, i.e. the binary is the one the parity tests and profiles were run on.  In a PDL
+// build every hot-loop kernel executes griddepcontrol.wait + launch_dependents at TA_PDL_ENTRY() (before its first global-memory
+// access; wait first, so at most ONE dependent grid is ever parked behind a running one) and is launched with the
+// programmatic-stream-serialization attribute while ta_set_pdl(1) is in effect (runtime A/B inside the PDL build).
+// Status: compiles, NOT yet run on hardware.
+#ifdef TA_PDL
+extern int g_ta_pdl;
+#define TA_PDL_ENTRY()              \
+    do {                            \
+        pdl_wait();                 \
+        pdl_launch_dependents();    \
+    } while (0)
+#define TA_KERNEL_LAUNCH(kern, grid, block, smem, st, ...)                                  \
+    do {                                                                                    \
+        if (g_ta_pdl) {                                                                     \
+            TA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__)); \
+            ++g_ta_launches;                                                                \
+        } else {                                                                            \
+            kern<<<grid, block, smem, st>>>(__VA_ARGS__);                                   \
+            TA_LAUNCH_CHECK();                                                              \
+        }                                                                                   \
+    } while (0)
+#else
+#define TA_PDL_ENTRY() \
+    do {               \
+    } while (0)
+#define TA_KERNEL_LAUNCH(kern, grid, block, smem, st, ...) \
+    do {                                                   \
+        kern<<<grid, block, smem, st>>>(__VA_ARGS__);      \
+        TA_LAUNCH_CHECK();                                 \
+    } while (0)
+#endif
+
 __host__ __device__ inline int64_t ceil_div_i64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -53,6 +53,7 @@ template <int MAXV>   // MAXV = max 8-element vectors per lane
 __global__ void __launch_bounds__(256)
 layernorm_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       bf16* __restrict__ y, long long rows, int D, float eps) {
+    TA_PDL_ENTRY();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -109,6 +110,7 @@ layernorm_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ w, c
 template <int MAXV>
 __global__ void rmsnorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y,
                                    const int* __restrict__ row_index, long long rows, int D, float eps, long long ldy) {
+    TA_PDL_ENTRY();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -142,6 +144,7 @@ template <int MAXV>
 __global__ void rmsnorm_f32_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                                        float* __restrict__ dx, const int* __restrict__ row_index, long long rows, int D,
                                        float eps, int accumulate, bf16* __restrict__ dx_bf16, long long ld_b) {
+    TA_PDL_ENTRY();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -217,6 +220,7 @@ __global__ void enc_rope_kernel(bf16* __restrict__ qkv, const float* __restrict_
 __global__ void lm_qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ qk, const float* __restrict__ qw,
                                           const float* __restrict__ kw, const float* __restrict__ cosT,
                                           const float* __restrict__ sinT, long long M, int S, int Hq, int Hkv, float eps) {
+    TA_PDL_ENTRY();
     // 8 lanes per (row, head): lane l8 owns dims [8 l8, +8) and [64 + 8 l8, +8) -- the RoPE pairs (d, d + 64) stay in one thread and every
     // access is a 16-byte vector (a warp covers 4 consecutive heads = 1 KB contiguous); 4-byte accesses ran at 40 % of the HBM rate
     const int HD = 128;
@@ -265,6 +269,7 @@ __global__ void lm_qknorm_rope_bwd_kernel(const bf16* __restrict__ qkv, const fl
                                           const float* __restrict__ kw, const float* __restrict__ cosT,
                                           const float* __restrict__ sinT, long long M, int S, int Hq, int Hkv, float eps,
                                           long long ld_out) {
+    TA_PDL_ENTRY();
     // 8 lanes per (row, head), lane l8 owns dims [8 l8, +8) and [64 + 8 l8, +8): 16-byte accesses throughout (see the forward kernel)
     const int HD = 128;
     const int heads = Hq + 2 * Hkv;
@@ -712,9 +717,8 @@ int k_layernorm_bf16(const bf16* x, const float* w, const float* b, bf16* y, lon
     TA_REQUIRE(D % 256 == 0 && D <= 2048, "layernorm: D=%d must be a multiple of 256 and <= 2048", D);
     const int wpb = 8;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    if (D <= 1280) layernorm_bf16_kernel<5><<<grid, wpb * 32, 0, st>>>(x, w, b, y, rows, D, eps);
-    else layernorm_bf16_kernel<8><<<grid, wpb * 32, 0, st>>>(x, w, b, y, rows, D, eps);
-    TA_LAUNCH_CHECK();
+    if (D <= 1280) TA_KERNEL_LAUNCH(layernorm_bf16_kernel<5>, grid, wpb * 32, 0, st, x, w, b, y, rows, D, eps);
+    else TA_KERNEL_LAUNCH(layernorm_bf16_kernel<8>, grid, wpb * 32, 0, st, x, w, b, y, rows, D, eps);
     return 0;
 }
 
@@ -725,9 +729,8 @@ int k_rmsnorm_f32(const float* x, const float* w, bf16* y, const int* row_index,
     if (rows == 0) return 0;
     const int wpb = 8;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    if (D <= 1024) rmsnorm_f32_kernel<4><<<grid, wpb * 32, 0, st>>>(x, w, y, row_index, rows, D, eps, ldy);
-    else rmsnorm_f32_kernel<8><<<grid, wpb * 32, 0, st>>>(x, w, y, row_index, rows, D, eps, ldy);
-    TA_LAUNCH_CHECK();
+    if (D <= 1024) TA_KERNEL_LAUNCH(rmsnorm_f32_kernel<4>, grid, wpb * 32, 0, st, x, w, y, row_index, rows, D, eps, ldy);
+    else TA_KERNEL_LAUNCH(rmsnorm_f32_kernel<8>, grid, wpb * 32, 0, st, x, w, y, row_index, rows, D, eps, ldy);
     return 0;
 }
 
@@ -738,9 +741,10 @@ int k_rmsnorm_f32_bwd(const bf16* dy, const float* x, const float* w, float* dx,
     if (rows == 0) return 0;
     const int wpb = 8;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    if (D <= 1024) rmsnorm_f32_bwd_kernel<4><<<grid, wpb * 32, 0, st>>>(dy, x, w, dx, row_index, rows, D, eps, accumulate, dx_bf16, ld_b);
-    else rmsnorm_f32_bwd_kernel<8><<<grid, wpb * 32, 0, st>>>(dy, x, w, dx, row_index, rows, D, eps, accumulate, dx_bf16, ld_b);
-    TA_LAUNCH_CHECK();
+    if (D <= 1024)
+        TA_KERNEL_LAUNCH(rmsnorm_f32_bwd_kernel<4>, grid, wpb * 32, 0, st, dy, x, w, dx, row_index, rows, D, eps, accumulate, dx_bf16, ld_b);
+    else
+        TA_KERNEL_LAUNCH(rmsnorm_f32_bwd_kernel<8>, grid, wpb * 32, 0, st, dy, x, w, dx, row_index, rows, D, eps, accumulate, dx_bf16, ld_b);
     return 0;
 }
 
@@ -755,8 +759,7 @@ int k_lm_qknorm_rope_fwd(const bf16* qkv, bf16* qk, const float* qw, const float
                          long long M, int S, int Hq, int Hkv, float eps, cudaStream_t st) {
     const long long threads = M * (Hq + Hkv) * 8;      // 8 lanes per (row, head)
     if (threads == 0) return 0;
-    lm_qknorm_rope_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(qkv, qk, qw, kw, cosT, sinT, M, S, Hq, Hkv, eps);
-    TA_LAUNCH_CHECK();
+    TA_KERNEL_LAUNCH(lm_qknorm_rope_fwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, qkv, qk, qw, kw, cosT, sinT, M, S, Hq, Hkv, eps);
     return 0;
 }
 
@@ -766,9 +769,8 @@ int k_lm_qknorm_rope_bwd(const bf16* qkv, const float* dq, const bf16* dk, const
     if (ld_out == 0) ld_out = (long long)(Hq + 2 * Hkv) * 128;
     const long long threads = M * (Hq + 2 * Hkv) * 8;      // 8 lanes per (row, head)
     if (threads == 0) return 0;
-    lm_qknorm_rope_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(qkv, dq, dk, dv, dqkv, qw, kw, cosT, sinT, M, S, Hq, Hkv,
-                                                                                   eps, ld_out);
-    TA_LAUNCH_CHECK();
+    TA_KERNEL_LAUNCH(lm_qknorm_rope_bwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, qkv, dq, dk, dv, dqkv, qw, kw, cosT, sinT, M, S,
+                     Hq, Hkv, eps, ld_out);
     return 0;
 }
 

@@ -31,6 +31,17 @@ TA_API const char* ta_last_error_string(void) { return g_err; }
 TA_API int ta_version(void) { return 100; }
 unsigned long long g_ta_launches = 0;
 TA_API unsigned long long ta_launch_count(void) { return g_ta_launches; }
+// programmatic dependent launch for the training towers: only in builds made with `make PDL=1` (common.cuh); returns 1 when the
+// request took effect, 0 when this build has no PDL code (the default build)
+#ifdef TA_PDL
+int g_ta_pdl = 0;
+TA_API int ta_set_pdl(int on) {
+    g_ta_pdl = on ? 1 : 0;
+    return 1;
+}
+#else
+TA_API int ta_set_pdl(int) { return 0; }
+#endif
 
 namespace {
 
@@ -794,6 +805,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    TA_PDL_ENTRY();              // PDL builds: the prologue above overlaps the predecessor's tail; every global access is below
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs load their own halves) =====================
@@ -1032,8 +1044,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
     int pairs = num_sms() / 2;
     if (tiles < pairs) pairs = tiles;
-    kern<<<2 * pairs, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, tc, tc2, M, N, K, ep);
-    TA_LAUNCH_CHECK();
+    TA_KERNEL_LAUNCH(kern, 2 * pairs, GEMM_THREADS, C::SMEM_BYTES, st, ta, tb, tc, tc2, M, N, K, ep);
     return 0;
 }
 

@@ -66,6 +66,7 @@ class LmStepArgs(C.Structure):
 _SIGS = {
     "ta_version": ([], c_int),
     "ta_launch_count": ([], C.c_ulonglong),
+    "ta_set_pdl": ([c_int], c_int),
     "ta_gemm_bf16": ([P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, C.POINTER(GemmEpilogue), P], c_int),
     "ta_gemm_bf16_tn": ([P, c_ll, P, c_ll, c_int, c_int, c_int, P, c_ll, c_float, P], c_int),
     "ta_gemm_set_tile_n": ([c_int], c_int),
@@ -150,6 +151,9 @@ def load() -> C.CDLL:
         lib.ta_gemm_set_cta_pair(int(os.environ["TA_GEMM_CTA_PAIR"]))
     if os.environ.get("TA_GEMM_TAIL_SPLIT") is not None:
         lib.ta_gemm_set_tail_split(int(os.environ["TA_GEMM_TAIL_SPLIT"]))
+    if os.environ.get("TA_PDL") is not None:          # effective only in a `make PDL=1` build of the library
+        if lib.ta_set_pdl(int(os.environ["TA_PDL"])) == 0 and int(os.environ["TA_PDL"]):
+            raise TinyAudioB200Error("TA_PDL=1 requested but libtinyaudio_b200.so was built without PDL (make -C tiny_audio_b200/csrc PDL=1)")
     if os.environ.get("TA_WINDOW_ATTN_VARIANT") is not None:
         lib.ta_window_attn_set_variant(int(os.environ["TA_WINDOW_ATTN_VARIANT"]))
     if os.environ.get("TA_ATTN_TC") is not None:
