@@ -66,7 +66,10 @@ int ta_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, int
 int ta_gemm_bf16_tn(const void* At, long long ldat, const void* Bt, long long ldbt, int M, int N, int K, float* out, long long ldo,
                     float alpha, void* stream);
 int ta_gemm_set_tile_n(int bn); /* 0 = auto, 128, 256 (testing / tuning) */
-int ta_gemm_set_tail_split(int on); /* 1: a mostly empty last wave of 256 x 256 tiles is issued as a second launch of 256 x 128 tiles (default 0:
+int ta_gemm_set_tail_split(int on);
+/* ta_gemm_bf16_tn: split the token contraction of few-tile / deep-K weight-gradient products over all CTA pairs, partial tiles
+ * reduce-added into the (zeroed) fp32 output by TMA.  0 = off (default).  Experimental, not yet run on hardware. */
+int ta_gemm_set_tn_splitk(int on); /* 1: a mostly empty last wave of 256 x 256 tiles is issued as a second launch of 256 x 128 tiles (default 0:
                                        no gain under the 1 kW power cap, see gemm_sm100.cu) */
 int ta_gemm_set_cta_pair(int on); /* 1: CTA-pair kernel (tcgen05 cta_group::2, 256 x N tiles); 0: 1-CTA kernel */
 

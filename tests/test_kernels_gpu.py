@@ -608,6 +608,30 @@ def test_gemm_tn_weight_gradient_form(cuda, M, N, K):
     assert rel_err(L.gemm_tn(at, bt, alpha=0.5), 0.5 * ref) < 1e-3
 
 
+@pytest.mark.skipif(os.environ.get("TA_TEST_UNVERIFIED") != "1",
+                    reason="split-K form of the TN GEMM (ta_gemm_set_tn_splitk): compiled and reviewed, not yet run on hardware -- opt-in")
+@pytest.mark.parametrize("M,N,K", [(128, 128, 14688), (6144, 128, 14688), (128, 1024, 14688), (128, 2048, 12000), (1024, 3072, 1000),
+                                   (384, 1024, 2080)])
+def test_gemm_tn_split_k(cuda, M, N, K):
+    """Few-tile / deep-K weight-gradient products (rank-8 LoRA gradients padded to 128: 4 ... 24 output tiles, 230 k-blocks) with the
+    contraction split over all CTA pairs and the partial tiles reduce-added by TMA: equal to the unsplit kernel up to fp32 summation
+    order, and to fp32 torch.  Shapes with many tiles or a shallow K must keep taking the unsplit path."""
+    lib = L.load()
+    at, bt = rnd(K, M + 8, seed=1)[:, :M], rnd(K, N + 8, seed=2)[:, :N]
+    ref = at.float().t() @ bt.float()
+    L.check(lib.ta_gemm_set_tn_splitk(0))
+    plain = L.gemm_tn(at, bt)
+    try:
+        L.check(lib.ta_gemm_set_tn_splitk(1))
+        out = torch.full((M, N + 16), 7.0, device="cuda", dtype=F32)[:, :N]      # stale contents + a padded leading dimension
+        L.gemm_tn(at, bt, out=out)
+        half = L.gemm_tn(at, bt, alpha=0.5)
+    finally:
+        L.check(lib.ta_gemm_set_tn_splitk(0))
+    assert rel_err(out, plain) < 1e-5 and rel_err(out, ref) < 1e-3
+    assert rel_err(half, 0.5 * ref) < 1e-3
+
+
 def test_gemm_tail_wave_split(cuda):
     """Optional tile choice (ta_gemm_set_tail_split): a mostly empty last wave of 256 x 256 tiles is issued as 256 x 128 tiles for the
     trailing row blocks (two launches).  Every row-indexed epilogue operand must be offset correctly: compare with the unsplit launch."""

@@ -75,6 +75,7 @@ struct EpiArgs {
     const float* rope_sin;
     int rope_seq;
     int rope_cols;
+    int k_splits;            // SPLITK instantiations only: the contraction is cut into k_splits ranges whose partial tiles are reduce-added
 };
 
 __device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32]) {
@@ -439,11 +440,13 @@ struct Stager {
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         return buf + (n & 1) * STG_BYTES + r * 128;
     }
+    template <bool REDUCE = false>
     __device__ __forceinline__ void end(const CUtensorMap* map, int col0, int row0) {
         fence_proxy_async_smem();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (leader) {
-            tma_store_2d(map, buf + (n & 1) * STG_BYTES, col0, row0);
+            if constexpr (REDUCE) tma_reduce_add_2d(map, buf + (n & 1) * STG_BYTES, col0, row0);
+            else tma_store_2d(map, buf + (n & 1) * STG_BYTES, col0, row0);
             tma_store_commit();
         }
         ++n;
@@ -472,7 +475,7 @@ __device__ __forceinline__ void stage_f32x32(uint8_t* row_ptr, int r, const floa
         *reinterpret_cast<float4*>(row_ptr + ((qd ^ (r & 7)) << 4)) = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool REDUCE = false>
 __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row, bool row_ok, int tile_row0, long long tile_col0,
                                                   const EpiArgs& ep, int grp, const float* s_bias, Stager& sg,
                                                   const CUtensorMap* tmC, const CUtensorMap* tmC2) {
@@ -654,7 +657,7 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
                 }
             } else if constexpr (F32OUT) {
                 stage_f32x32(srow, r, v);
-                sg.end(tmC, (int)col, tile_row0);
+                sg.template end<REDUCE>(tmC, (int)col, tile_row0);
             } else {
                 const int which = (c - c_lo) & 1;
                 stage_bf16x32(srow, r, which, v);
@@ -753,7 +756,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor_g(uint32_t smem_addr
 
 // TN = true: C[M,N] = At^T . Bt with At [K, M] and Bt [K, N] row-major (both operands MN-major): the weight-gradient GEMM
 // dW = dY^T X reads the activations as they lie in memory (contraction over the token rows), no transposed copies.
-template <int BN, int EPI, bool TN = false>
+// SPLITK (fp32 output only): work item w = (k range w / num_tiles, tile w % num_tiles); every item reduce-adds its partial tile into
+// a ZEROED output with TMA (cp.reduce.async.bulk.tensor .add), so few-tile / deep-K products (rank-8 LoRA gradients, d(lm_head),
+// projector weight gradients) still fill all CTA pairs.
+template <int BN, int EPI, bool TN = false, bool SPLITK = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int M, int N, int K, EpiArgs ep) {
@@ -781,6 +787,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int tiles_m = (M + 2 * BM - 1) / (2 * BM);
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (K + BK - 1) / BK;
+    static_assert(!SPLITK || EPI == TA_EPI_F32, "split-K reduces fp32 partial tiles");
+    const int kb_per = SPLITK ? (num_kb + ep.k_splits - 1) / ep.k_splits : num_kb;      // k-blocks per work item
+    const int num_work = SPLITK ? num_tiles * ep.k_splits : num_tiles;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -812,11 +821,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+            for (int work = pair; work < num_work; work += n_pairs) {
+                const int tile = SPLITK ? work % num_tiles : work;
+                const int kb0 = SPLITK ? (work / num_tiles) * kb_per : 0;
+                const int kb1 = SPLITK ? min(num_kb, kb0 + kb_per) : num_kb;
                 const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
                 const int row0 = m_blk * 2 * BM + (int)rank * BM;
                 const int nrow0 = n_blk * BN + (int)rank * (BN / 2);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
                     if constexpr (TN) {      // boxes {64 m (or n), 64 k}: one 8 KB atom per 64 output rows / columns
@@ -842,11 +854,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+            for (int work = pair; work < num_work; work += n_pairs) {
+                const int kb0 = SPLITK ? (work / num_tiles) * kb_per : 0;
+                const int kb1 = SPLITK ? min(num_kb, kb0 + kb_per) : num_kb;
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(smA + stage * C::A_BYTES);
@@ -855,7 +869,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t ad = TN ? umma_desc_sw128_mnmajor_g(a0 + k * UMMA_K * 128, 8192) : umma_desc_sw128_kmajor(a0 + k * UMMA_K * 2);
                         const uint64_t bd = TN ? umma_desc_sw128_mnmajor_g(b0 + k * UMMA_K * 128, 8192) : umma_desc_sw128_kmajor(b0 + k * UMMA_K * 2);
-                        umma_f16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_f16_2sm(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                     }
                     umma_commit_2sm(&empty[stage]);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -878,7 +892,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         int tile_iter = 0;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+        for (int work = pair; work < num_work; work += n_pairs) {
+            const int tile = SPLITK ? work % num_tiles : work;
             const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
             if (ep.bias) {   // stage this tile's bias (BN floats) in shared memory; double buffered across tiles
                 float* sb = s_bias_all + (tile_iter & 1) * BN;
@@ -893,8 +908,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const long long row = (long long)m_blk * 2 * BM + (long long)rank * BM + q * 32 + lane;
             const bool row_ok = row < M;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            epilogue_tile_tma<BN, EPI>(taddr, row, row_ok, m_blk * 2 * BM + (int)rank * BM, (long long)n_blk * BN, ep, grp, s_bias, sg,
-                                       &tmC, &tmC2);
+            epilogue_tile_tma<BN, EPI, SPLITK>(taddr, row, row_ok, m_blk * 2 * BM + (int)rank * BM, (long long)n_blk * BN, ep, grp, s_bias,
+                                               sg, &tmC, &tmC2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty[as]);
@@ -1031,17 +1046,17 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, i
     }
 }
 
-template <int BN, int EPI, bool TN = false>
+template <int BN, int EPI, bool TN = false, bool SPLITK = false>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2, int M, int N, int K,
             const EpiArgs& ep, cudaStream_t st) {
     using C = Cfg2<BN>;
-    auto kern = gemm2_kernel<BN, EPI, TN>;
+    auto kern = gemm2_kernel<BN, EPI, TN, SPLITK>;
     static bool attr_done = false;
     if (!attr_done) {
         TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_done = true;
     }
-    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN) * (SPLITK ? ep.k_splits : 1);
     int pairs = num_sms() / 2;
     if (tiles < pairs) pairs = tiles;
     TA_KERNEL_LAUNCH(kern, 2 * pairs, GEMM_THREADS, C::SMEM_BYTES, st, ta, tb, tc, tc2, M, N, K, ep);
@@ -1086,6 +1101,14 @@ TA_API int ta_gemm_set_tail_split(int on) {
     return 0;
 }
 
+// split-K for the weight-gradient (TN) form: 0 = off (default), 1 = on for few-tile / deep-K problems.  Experimental: compiled
+// and reviewed, not yet run on hardware.
+int g_tn_splitk = 0;
+TA_API int ta_gemm_set_tn_splitk(int on) {
+    g_tn_splitk = on ? 1 : 0;
+    return 0;
+}
+
 TA_API int ta_gemm_set_cta_pair(int on) {
     g_cta_pair = on ? 1 : 0;
     return 0;
@@ -1109,6 +1132,24 @@ TA_API int ta_gemm_bf16_tn(const void* At, long long ldat, const void* Bt, long 
     rc = make_map(&tc, out, M, N, ldo, BM, true);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    ep.k_splits = 1;
+    if (g_tn_splitk) {
+        // few output tiles, deep contraction (rank-8 LoRA gradients: 4 ... 24 tiles x 230 k-blocks): cut K so that every CTA pair
+        // gets a work item, each at least 8 k-blocks long; partial tiles are reduce-added into the zeroed output
+        const int pairs = num_sms() / 2;
+        const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / bn);
+        const int num_kb = (K + BK - 1) / BK;
+        int splits = tiles * 2 <= pairs ? pairs / tiles : 1;
+        if (splits > num_kb / 8) splits = num_kb / 8;
+        if (splits > 1) {
+            const int kb_per = (num_kb + splits - 1) / splits;
+            splits = (num_kb + kb_per - 1) / kb_per;          // no empty k range
+            ep.k_splits = splits;
+            TA_CHECK_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+            if (bn == 256) return launch2<256, TA_EPI_F32, true, true>(ta, tb, tc, tc, M, N, K, ep, st);
+            return launch2<128, TA_EPI_F32, true, true>(ta, tb, tc, tc, M, N, K, ep, st);
+        }
+    }
     if (bn == 256) return launch2<256, TA_EPI_F32, true>(ta, tb, tc, tc, M, N, K, ep, st);
     return launch2<128, TA_EPI_F32, true>(ta, tb, tc, tc, M, N, K, ep, st);
 }
@@ -1123,6 +1164,7 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
     int bn = g_force_bn ? g_force_bn : ((N % 256 == 0) ? 256 : 128);
     if (N % bn != 0) bn = 128;
     EpiArgs ep;
+    ep.k_splits = 1;
     ep.out = e->out; ep.ldo = e->ldo; ep.bias = e->bias; ep.resid = e->resid; ep.ldr = e->ldr ? e->ldr : e->ldo;
     ep.out2 = e->out2; ep.ldo2 = e->ldo2; ep.aux = reinterpret_cast<const bf16*>(e->aux); ep.ldaux = e->ldaux;
     ep.alpha = e->alpha == 0.0f ? 1.0f : e->alpha;

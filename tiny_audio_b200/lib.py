@@ -72,6 +72,7 @@ _SIGS = {
     "ta_gemm_set_tile_n": ([c_int], c_int),
     "ta_gemm_set_cta_pair": ([c_int], c_int),
     "ta_gemm_set_tail_split": ([c_int], c_int),
+    "ta_gemm_set_tn_splitk": ([c_int], c_int),
     "ta_logmel_workspace_floats": ([c_int, c_int, C.POINTER(c_ll)], c_int),
     "ta_logmel_fwd": ([P, c_ll, c_int, c_int, P, P, P, P], c_int),
     "ta_mel_to_conv1_im2col": ([P, c_int, c_int, P, P], c_int),
@@ -149,6 +150,8 @@ def load() -> C.CDLL:
     # tuning / A-B switches (both kernels of each pair are parity-tested; defaults are the fast ones)
     if os.environ.get("TA_GEMM_CTA_PAIR") is not None:
         lib.ta_gemm_set_cta_pair(int(os.environ["TA_GEMM_CTA_PAIR"]))
+    if os.environ.get("TA_GEMM_TN_SPLITK") is not None:
+        lib.ta_gemm_set_tn_splitk(int(os.environ["TA_GEMM_TN_SPLITK"]))
     if os.environ.get("TA_GEMM_TAIL_SPLIT") is not None:
         lib.ta_gemm_set_tail_split(int(os.environ["TA_GEMM_TAIL_SPLIT"]))
     if os.environ.get("TA_PDL") is not None:          # effective only in a `make PDL=1` build of the library
