@@ -231,3 +231,21 @@ def test_checkpoint_round_trip_reference_layout(tmp_path):
         assert torch.equal(m.lora_adapters.lora_B[t], m2.lora_adapters.lora_B[t])
     trainable = [n for n, p in m2.named_parameters() if p.requires_grad]
     assert len(trainable) == 4 + 14 and all(n.startswith(("projector.", "language_model.")) for n in trainable)
+
+
+def test_tiny_audio_shim_resolves_off_path_modules_in_the_reference_checkout(tmp_path):
+    """scripts/train.py:44-50 imports tiny_audio.asr_config / asr_modeling (hot path: this repo) AND tiny_audio.augmentation (off the
+    path: must stay the reference's own module).  With `PYTHONPATH=<this repo>:<tiny-audio checkout>` the shim package has to serve both."""
+    import subprocess
+    import sys
+    fake = tmp_path / "checkout" / "tiny_audio"
+    fake.mkdir(parents=True)
+    (fake / "__init__.py").write_text("raise RuntimeError('the reference package __init__ must not run')\n")
+    (fake / "asr_modeling.py").write_text("ASRModel = 'reference'\n")
+    (fake / "augmentation.py").write_text("from .asr_config import ASRConfig\nNoiseAugmentation = ('reference', ASRConfig.__module__)\n")
+    code = ("import tiny_audio.asr_modeling as m, tiny_audio.augmentation as a; "
+            "print(m.ASRModel.__module__, a.NoiseAugmentation[0], a.NoiseAugmentation[1])")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, str(tmp_path / "checkout")]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.split()[-3:] == ["tiny_audio_b200.asr_modeling", "reference", "tiny_audio_b200.asr_config"]
