@@ -249,3 +249,35 @@ def test_tiny_audio_shim_resolves_off_path_modules_in_the_reference_checkout(tmp
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.split()[-3:] == ["tiny_audio_b200.asr_modeling", "reference", "tiny_audio_b200.asr_config"]
+
+
+def test_integer_semantics_match_reference_vectors():
+    """Token-count arithmetic of the PRODUCT modules (and of the oracle) for every mel length 1 .. 3000 and every registered projector,
+    plus the ragged gather, bit-exact against vectors generated by the unmodified reference (oracle/make_integer_golden.py)."""
+    from oracle import path_oracle as po
+    from oracle.make_integer_golden import Cfg
+    from tiny_audio_b200.asr_config import compute_encoder_output_length
+    from tiny_audio_b200.asr_modeling import _gather_audio_embeds
+    from tiny_audio_b200.projectors import PROJECTOR_CLASSES, MLPAudioProjector
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "integer_semantics.npz"))
+    mel, enc = fx["mel_frames"], fx["encoder_frames"]
+    assert np.array_equal(compute_encoder_output_length(torch.from_numpy(mel)).numpy(), enc)
+    assert [int(compute_encoder_output_length(int(t))) for t in mel[:50]] == enc[:50].tolist()
+    assert np.array_equal(po.encoder_output_length(torch.from_numpy(mel)).numpy(), enc)
+    enc_t = torch.from_numpy(enc)
+    for kind in ("mlp", "mosa", "moe", "qformer"):
+        proj = PROJECTOR_CLASSES[kind](Cfg())
+        want = fx[f"audio_tokens.{kind}"]
+        assert np.array_equal(torch.as_tensor(proj.get_output_length(enc_t)).numpy(), want), kind      # tensor form (collator)
+        assert [int(proj.get_output_length(int(e))) for e in enc[::37]] == want[::37].tolist(), kind   # int form (processor)
+    for k in (2, 5):
+        c = Cfg()
+        c.projector_pool_stride = k
+        assert np.array_equal(torch.as_tensor(MLPAudioProjector(c).get_output_length(enc_t)).numpy(), fx[f"audio_tokens.mlp.k{k}"])
+    assert np.array_equal(po.projector_output_length(enc_t, 4).numpy(), fx["audio_tokens.mlp"])
+    assert np.array_equal(po.qformer_output_length(enc_t).numpy(), fx["audio_tokens.qformer"])
+    assert np.array_equal(po.mosa_output_length(enc_t).numpy(), fx["audio_tokens.mosa"])
+    for i in range(int(fx["gather.n_cases"])):
+        x, counts, out = (torch.from_numpy(fx[f"gather.{i}.{n}"]) for n in ("x", "counts", "out"))
+        assert torch.equal(_gather_audio_embeds(x, counts), out), i
+        assert torch.equal(po.gather_audio_embeds(x, counts), out), i
