@@ -1,6 +1,7 @@
 """Integer golden vectors from the UNMODIFIED reference (runs only where /root/reference exists): the token-count arithmetic the
 collator and the processor rely on (scripts/train.py:335-338, tiny_audio/asr_processing.py:95-110) for every registered projector,
-and the ragged gather of audio embeddings (tiny_audio/asr_modeling.py:27-44).  Output: tests/golden/integer_semantics.npz
+the ragged gather of audio embeddings (tiny_audio/asr_modeling.py:27-44), and what ASRProcessor.__call__ builds (chat messages,
+ids, masks; asr_processing.py:51-128).  Output: tests/golden/integer_semantics.npz, tests/golden/processor_calls.json
 
 usage:  python oracle/make_integer_golden.py
 """
@@ -24,8 +25,61 @@ class Cfg:
     qformer_intermediate_size = None
 
 
+class RecordingTokenizer:
+    """Stands in for the Qwen3 tokenizer (not available offline): records what apply_chat_template receives and returns ids that are a
+    deterministic function of the messages (one 777 per <audio> placeholder), so two processors agree iff they build the same chat."""
+
+    def __init__(self):
+        self.calls = []
+
+    def convert_tokens_to_ids(self, t):
+        return 777 if t == "<audio>" else None
+
+    def apply_chat_template(self, messages, tokenize=True, add_generation_prompt=False, return_tensors=None, enable_thinking=None):
+        self.calls.append(dict(messages=messages, add_generation_prompt=add_generation_prompt, enable_thinking=enable_thinking,
+                               tokenize=tokenize))
+        ids = []
+        for m in messages:
+            rest = m["content"].replace("<audio>", "")
+            ids += [1 + len(m["role"])] + [777] * m["content"].count("<audio>") + [10 + sum(map(ord, rest)) % 1000]
+        if add_generation_prompt:
+            ids.append(5)
+        return torch.tensor([ids])
+
+
+class StackProjector:
+    def get_output_length(self, n):
+        return (n - 4) // 4 + 1
+
+
+PROCESSOR_CASES = ((16000, None, None), (12345, "hello world", None), (48000, None, "You are helpful."), (None, None, None),
+                   (8000, "x", "sys"))
+
+
+def run_processor_cases(processor_cls):
+    """ASRProcessor.__call__ (tiny_audio/asr_processing.py:51-128) on audio only / audio + text / system prompt / text only."""
+    from transformers import WhisperFeatureExtractor
+    rng = np.random.default_rng(3)
+    out = []
+    for audio_len, text, system_prompt in PROCESSOR_CASES:
+        tok = RecordingTokenizer()
+        proc = processor_cls(WhisperFeatureExtractor(feature_size=128), tok, projector=StackProjector())
+        audio = rng.standard_normal(audio_len).astype(np.float32) if audio_len else None
+        res = proc(audio=audio, text=text, system_prompt=system_prompt)
+        rec = {"calls": tok.calls, "input_ids": res["input_ids"].tolist(), "attention_mask": res["attention_mask"].tolist(),
+               "keys": sorted(res.keys())}
+        if audio_len:
+            rec["audio_mask_sum"] = int(res["audio_attention_mask"].sum())
+            rec["feat_shape"] = list(res["input_features"].shape)
+        out.append(rec)
+    return out
+
+
 def main():
     mods = load_reference()
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "processor_calls.json"), "w") as f:
+        json.dump(run_processor_cases(mods["asr_processing"].ASRProcessor), f, indent=1)
     P, A, M = mods["projectors"], mods["asr_config"], mods["asr_modeling"]
     mel = np.arange(1, 3001, dtype=np.int64)                       # mel frames 1 .. 3000 (30 s)
     enc = np.array([int(A.compute_encoder_output_length(int(t))) for t in mel], dtype=np.int64)

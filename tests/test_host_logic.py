@@ -281,3 +281,17 @@ def test_integer_semantics_match_reference_vectors():
         x, counts, out = (torch.from_numpy(fx[f"gather.{i}.{n}"]) for n in ("x", "counts", "out"))
         assert torch.equal(_gather_audio_embeds(x, counts), out), i
         assert torch.equal(po.gather_audio_embeds(x, counts), out), i
+
+
+def test_processor_builds_the_reference_chat_and_counts():
+    """ASRProcessor.__call__ of the product against what the unmodified reference's processor produced for the same inputs
+    (tests/golden/processor_calls.json): chat messages incl. the <audio> placeholder run and the transcribe instruction,
+    add_generation_prompt / enable_thinking flags, ids, masks, feature shapes."""
+    import json
+    from oracle.make_integer_golden import run_processor_cases
+    from tiny_audio_b200.asr_processing import ASRProcessor
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "processor_calls.json")))
+    got = json.loads(json.dumps(run_processor_cases(ASRProcessor)))
+    assert len(got) == len(want) == 5
+    for g, w in zip(got, want):
+        assert g == w
