@@ -75,9 +75,25 @@ def run_processor_cases(processor_cls):
     return out
 
 
+def config_dicts(config_cls):
+    """ASRConfig(...).to_dict() for the default recipe and for two overridden ones (asr_config.py:36-220), sub-configs built offline."""
+    from transformers import GlmAsrEncoderConfig, Qwen3Config
+    out = {}
+    for name, kw in (("default", {}), ("qformer_lora", dict(projector_type="qformer", use_lora=True, lora_rank=16, max_new_tokens=64,
+                                                           freeze_projector=True)),
+                     ("unfrozen_moe", dict(projector_type="moe", freeze_language_model=False, num_experts=8, projector_hidden_dim=2048,
+                                           audio_token_dropout=0.05, system_prompt=""))):
+        d = config_cls(audio_config=GlmAsrEncoderConfig(), text_config=Qwen3Config(), **kw).to_dict()
+        d.pop("transformers_version", None)
+        out[name] = d
+    return out
+
+
 def main():
     mods = load_reference()
     import json
+    with open(os.path.join(ROOT, "tests", "golden", "asr_config_dicts.json"), "w") as f:
+        json.dump(config_dicts(mods["asr_config"].ASRConfig), f, indent=1, sort_keys=True, default=str)
     with open(os.path.join(ROOT, "tests", "golden", "processor_calls.json"), "w") as f:
         json.dump(run_processor_cases(mods["asr_processing"].ASRProcessor), f, indent=1)
     P, A, M = mods["projectors"], mods["asr_config"], mods["asr_modeling"]

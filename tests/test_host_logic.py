@@ -295,3 +295,18 @@ def test_processor_builds_the_reference_chat_and_counts():
     assert len(got) == len(want) == 5
     for g, w in zip(got, want):
         assert g == w
+
+
+def test_asr_config_serialises_like_the_reference():
+    """ASRConfig.to_dict() -- every field, default and nested tower config -- equals what the unmodified reference's ASRConfig produced
+    for the default recipe and two overridden ones (tests/golden/asr_config_dicts.json; checkpoints' config.json interchange)."""
+    import json
+    from oracle.make_integer_golden import config_dicts
+    from tiny_audio_b200.asr_config import ASRConfig
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "asr_config_dicts.json")))
+    got = json.loads(json.dumps(config_dicts(ASRConfig), sort_keys=True, default=str))
+    assert set(got) == set(want) == {"default", "qformer_lora", "unfrozen_moe"}
+    for name in want:
+        assert set(got[name]) == set(want[name]), name
+        for k in want[name]:
+            assert got[name][k] == want[name][k], (name, k)
