@@ -89,9 +89,42 @@ def config_dicts(config_cls):
     return out
 
 
+def model_surface(build):
+    """What scripts/train.py and the HF Trainer see of the model: `state_dict()` keys in order (checkpoint layout,
+    tiny_audio/asr_modeling.py:398-422), names of the trainable parameters (optimizer groups, train.py:384-437) and class-level
+    attributes, for every projector type and for the unfrozen-decoder recipe.  `build(kind, freeze_lm)` -> model."""
+    out = {}
+    for kind, freeze_lm in (("mlp", True), ("qformer", True), ("mosa", True), ("moe", True), ("mlp", False)):
+        m = build(kind, freeze_lm)
+        out[f"{kind}{'' if freeze_lm else '+unfrozen_lm'}"] = {
+            "state_dict_keys": list(m.state_dict().keys()),
+            "trainable": [n for n, p in m.named_parameters() if p.requires_grad],
+            "n_parameters": sum(p.numel() for p in m.parameters()),
+            "class_attrs": {a: getattr(type(m), a, None) for a in ("base_model_prefix", "main_input_name", "_supports_flash_attn_2",
+                                                                      "supports_gradient_checkpointing", "TRANSCRIBE_PROMPT")},
+            "training_flags_after_train()": [m.train().audio_tower.training, m.language_model.training, m.projector.training],
+        }
+    return out
+
+
+def _reference_builder(mods):
+    from oracle import path_oracle as po
+    from oracle.make_golden import PROJECTOR_CONFIG_EXTRAS, PROJECTOR_INIT, build_reference_model
+    cfg = po.small_config(enc_layers=1, lm_layers=1)
+
+    def build(kind, freeze_lm):
+        W = po.init_weights(cfg, seed=3)
+        if kind in PROJECTOR_INIT:
+            W["projector"] = PROJECTOR_INIT[kind](cfg, seed=5)
+        return build_reference_model(cfg, W, mods, kind, freeze_lm=freeze_lm, **PROJECTOR_CONFIG_EXTRAS.get(kind, {}))
+    return build
+
+
 def main():
     mods = load_reference()
     import json
+    with open(os.path.join(ROOT, "tests", "golden", "model_surface.json"), "w") as f:
+        json.dump(model_surface(_reference_builder(mods)), f, indent=1)
     with open(os.path.join(ROOT, "tests", "golden", "asr_config_dicts.json"), "w") as f:
         json.dump(config_dicts(mods["asr_config"].ASRConfig), f, indent=1, sort_keys=True, default=str)
     with open(os.path.join(ROOT, "tests", "golden", "processor_calls.json"), "w") as f:

@@ -310,3 +310,30 @@ def test_asr_config_serialises_like_the_reference():
         assert set(got[name]) == set(want[name]), name
         for k in want[name]:
             assert got[name][k] == want[name][k], (name, k)
+
+
+def test_model_surface_matches_reference():
+    """state_dict keys (in order), trainable-parameter names, parameter count, class attributes and train()/eval() bookkeeping of
+    ASRModel for all four projector types and the unfrozen-decoder recipe, against what the unmodified reference's ASRModel exposed
+    (tests/golden/model_surface.json, built offline through the same loader seams)."""
+    import json
+    from oracle import path_oracle as po
+    from oracle.make_golden import PROJECTOR_CONFIG_EXTRAS, PROJECTOR_INIT
+    from oracle.make_integer_golden import model_surface
+    from tiny_audio_b200.engine import PathDims
+    from tiny_audio_b200.synthetic import build_offline_model
+    cfg = po.small_config(enc_layers=1, lm_layers=1)
+
+    def build(kind, freeze_lm):
+        W = po.init_weights(cfg, seed=3)
+        if kind in PROJECTOR_INIT:
+            W["projector"] = PROJECTOR_INIT[kind](cfg, seed=5)
+        return build_offline_model(PathDims.from_any(cfg.to_dict()), device="cpu", enc_state=W["encoder"], lm_state=W["lm"],
+                                   proj_state=W["projector"], projector_type=kind, freeze_language_model=freeze_lm,
+                                   **PROJECTOR_CONFIG_EXTRAS.get(kind, {}))
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "model_surface.json")))
+    got = json.loads(json.dumps(model_surface(build)))
+    assert set(got) == set(want) and len(want) == 5
+    for name in want:
+        for field in want[name]:
+            assert got[name][field] == want[name][field], (name, field)
