@@ -337,3 +337,20 @@ def test_model_surface_matches_reference():
     for name in want:
         for field in want[name]:
             assert got[name][field] == want[name][field], (name, field)
+
+
+def test_generate_rejects_settings_it_would_otherwise_ignore():
+    """Greedy decoding without logits processors is what the B200 path implements (= the reference's defaults, asr_config.py:103-111);
+    anything that would change the chosen tokens must raise instead of being dropped."""
+    from oracle import path_oracle as po
+    from tiny_audio_b200.engine import PathDims
+    from tiny_audio_b200.synthetic import build_offline_model
+    cfg = po.small_config(enc_layers=1, lm_layers=1)
+    m = build_offline_model(PathDims.from_any(cfg.to_dict()), device="cpu")
+    x, ids = torch.zeros(1, 16000), torch.tensor([[1, cfg.audio_token_id, 3]])
+    for kw in (dict(repetition_penalty=1.2), dict(no_repeat_ngram_size=3), dict(min_new_tokens=4), dict(num_beams=2), dict(do_sample=True)):
+        with pytest.raises(NotImplementedError):
+            m.generate(input_ids=ids, input_features=x, **kw)
+    m.generation_config.repetition_penalty = 1.1            # set through the config, not the call
+    with pytest.raises(NotImplementedError, match="repetition_penalty"):
+        m.generate(input_ids=ids, input_features=x)

@@ -448,6 +448,15 @@ class ASRModel(PreTrainedModel, GenerationMixin):
         kwargs.pop("system_prompt", None)
         if kwargs.get("num_beams", 1) != 1 or kwargs.get("do_sample", False):
             raise NotImplementedError("only greedy decoding is implemented on the B200 path")
+        # the reference's defaults are neutral (asr_config.py:103-111); a logits processor that would change the greedy choice must not
+        # be dropped silently
+        gcfg = self.generation_config
+        for name, neutral in (("repetition_penalty", 1.0), ("no_repeat_ngram_size", 0), ("min_new_tokens", 0), ("num_beams", 1),
+                              ("do_sample", False)):
+            value = kwargs.get(name, getattr(gcfg, name, neutral))
+            if value not in (None, neutral):
+                raise NotImplementedError(f"generate(): {name}={value!r} is not supported on the B200 path (greedy decoding without "
+                                          f"logits processors only; the reference's default is {neutral!r})")
         hot = self._hot_path()
         feats = input_features.to(hot.device)
         pr = self.projector
