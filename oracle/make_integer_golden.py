@@ -120,9 +120,39 @@ def _reference_builder(mods):
     return build
 
 
+GENERATE_CASE = dict(seed=31, batch=2, clip_s=2.0, response_len=4, new_tokens=8)
+
+
+def generate_inputs():
+    """Seeded small model + batch whose prompt ends with the assistant header (everything before the first label)."""
+    from oracle import path_oracle as po
+    c = GENERATE_CASE
+    cfg = po.small_config(enc_layers=2, lm_layers=2)
+    W = po.init_weights(cfg, seed=c["seed"])
+    batch = po.synthetic_batch(cfg, c["batch"], c["clip_s"], seed=c["seed"], response_len=c["response_len"])
+    first = int((batch["labels"][0] != -100).nonzero()[0])
+    return cfg, W, batch, batch["input_ids"][:, :first].contiguous()
+
+
+def reference_generate(mods):
+    """Greedy ids from the reference's OWN ASRModel.generate (tiny_audio/asr_modeling.py:562-646 -> HF generate, greedy defaults)."""
+    from oracle.make_golden import build_reference_model
+    cfg, W, batch, prompt = generate_inputs()
+    ref = build_reference_model(cfg, W, mods, "mlp")
+    ref.eval()
+    L = int(batch["sample_lengths"][0])
+    feats = ref.feature_extractor([batch["waveform"][b, :L].numpy() for b in range(prompt.shape[0])], sampling_rate=16000,
+                                  padding="longest", return_attention_mask=True, return_tensors="pt")
+    out = ref.generate(input_ids=prompt, input_features=feats.input_features, audio_attention_mask=feats.attention_mask,
+                       attention_mask=torch.ones_like(prompt), max_new_tokens=GENERATE_CASE["new_tokens"])
+    return prompt.numpy(), out.numpy()
+
+
 def main():
     mods = load_reference()
     import json
+    prompt, ids = reference_generate(mods)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "generate_ids.npz"), prompt=prompt, ids=ids)
     with open(os.path.join(ROOT, "tests", "golden", "model_surface.json"), "w") as f:
         json.dump(model_surface(_reference_builder(mods)), f, indent=1)
     with open(os.path.join(ROOT, "tests", "golden", "asr_config_dicts.json"), "w") as f:

@@ -112,3 +112,18 @@ def test_mel_filter_bank_matches_hf():
     ref = mel_filter_bank(201, 128, 0.0, 8000.0, 16000, norm="slaney", mel_scale="slaney")
     assert np.abs(po.mel_filter_bank() - ref).max() < 1e-12
     assert (np.abs(ref) > 0).sum(0).max() <= 16      # the CUDA kernel's per-filter tap budget (logmel.cu MAXW)
+
+
+def test_oracle_greedy_ids_match_reference_generate():
+    """The oracle's greedy decoding against ids produced by the unmodified reference's ASRModel.generate -> HF generate
+    (tests/golden/generate_ids.npz): the chain CUDA path == oracle (tests/test_path_gpu.py) == reference is closed on both ends."""
+    from oracle.make_integer_golden import GENERATE_CASE, generate_inputs
+    torch.set_num_threads(os.cpu_count())
+    fx = np.load(os.path.join(GOLD, "generate_ids.npz"))
+    cfg, W, batch, prompt = generate_inputs()
+    assert np.array_equal(prompt.numpy(), fx["prompt"])
+    ob = dict(batch)
+    ob["input_ids"] = prompt
+    ids, margins = po.greedy_generate(W, ob, cfg, max_new_tokens=GENERATE_CASE["new_tokens"])
+    assert float(margins.min()) > 1e-4          # every step is decisive at fp32 precision
+    assert np.array_equal(ids.numpy(), fx["ids"])
