@@ -13,7 +13,7 @@ average_tokens_across_devices (HF:trainer.py:2141-2143, 2013-2018).
 """
 from __future__ import annotations
 
-from typing import Iterable, Optional
+from typing import Iterable
 
 import torch
 
