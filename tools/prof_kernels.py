@@ -124,5 +124,46 @@ if "wgrad" in which:
     out = torch.empty(6144, 1024, device=dev, dtype=F32)
     for _ in range(3):
         L.gemm_tn(dy, xx, out=out)
+if "lm_gemm" in which:
+    # the decoder GEMMs that run furthest below the tensor roofline in situ: SwiGLU-backward epilogue (502 TFLOP/s)
+    # and the N = 1024 products with the fp32-residual epilogue (818 TFLOP/s; 232 tiles = 3.14 waves on 74 CTA pairs)
+    M, D, Fd = 14688, 1024, 3072
+    dy = torch.randn(M, D, device=dev, dtype=BF16)
+    wd_t = torch.randn(Fd, D, device=dev, dtype=BF16) * 0.03
+    gu = torch.randn(M, 2 * Fd, device=dev, dtype=BF16)
+    dgu = torch.empty(M, 2 * Fd, device=dev, dtype=BF16)
+    h = torch.randn(M, Fd, device=dev, dtype=BF16)
+    wd = torch.randn(D, Fd, device=dev, dtype=BF16) * 0.03
+    resid = torch.zeros(M, D, device=dev, dtype=F32)
+    y = torch.empty(M, D, device=dev, dtype=F32)
+    for _ in range(3):
+        L.gemm(dy, wd_t, epi=L.EPI_SWIGLU_BWD, aux=gu, out=dgu)
+        L.gemm(h, wd, epi=L.EPI_F32_RESID, resid=resid, out=y)
+if "window" in which:
+    # QFormer window attention at batch 32 x 30 s: 3200 windows, 16 heads x 80, cross-attention (15 keys), both formulations
+    from tiny_audio_b200.projectors import _WindowAttnFn
+    Wn, heads, hd = 3200, 16, 80
+    q = torch.randn(Wn, 3, heads * hd, device=dev, dtype=BF16, requires_grad=True)
+    k = torch.randn(Wn, 15, heads * hd, device=dev, dtype=BF16, requires_grad=True)
+    v = torch.randn(Wn, 15, heads * hd, device=dev, dtype=BF16, requires_grad=True)
+    g = torch.randn(Wn, 3, heads * hd, device=dev, dtype=BF16)
+    for variant in (1, 2):
+        prev = lib.ta_window_attn_set_variant(variant)
+        for _ in range(2):
+            _WindowAttnFn.apply(q, k, v, None, heads).backward(g)
+        lib.ta_window_attn_set_variant(prev)
+if "lora_wgrad" in which:
+    # rank-8 (padded to 128) LoRA gradient products: dBs [6144, 128] = dy^T t and dA [128, 1024] = u^T x over 14688 tokens,
+    # unsplit and with the split-K form (ta_gemm_set_tn_splitk)
+    M = 14688
+    dy = torch.randn(M, 6144, device=dev, dtype=BF16)
+    t = torch.randn(M, 128, device=dev, dtype=BF16)
+    x = torch.randn(M, 1024, device=dev, dtype=BF16)
+    for on in (0, 1):
+        L.check(lib.ta_gemm_set_tn_splitk(on))
+        for _ in range(3):
+            L.gemm_tn(dy, t)
+            L.gemm_tn(t, x)
+    L.check(lib.ta_gemm_set_tn_splitk(0))
 torch.cuda.synchronize()
 print("done")
