@@ -463,6 +463,22 @@ def run_ours(args):
                                              num_items_in_batch=n_p)
             parity["batch_sample"] = {"sample": f"B={args.parity_batch} x {args.clip_seconds:g} s", "ce_loss_cuda_bf16": float(l_gpu_p),
                                       "ce_loss_reference_fp32": float(l_ref_p), "ce_loss_delta": abs(float(l_gpu_p) - float(l_ref_p))}
+        # like-for-like precision: the unmodified reference's own fp32 and bf16-autocast CE on these exact samples, recorded in the build
+        # container by oracle/make_reference_precision_gap.py (a fixture, not the oracle); only valid for the default sample definition
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "reference_precision_gap.json")) as f:
+                gap = json.load(f)
+            c = gap["config"]
+            if (c["proj_hidden"], c["clip_seconds"], c["response_len"]) == (args.proj_hidden, args.clip_seconds, args.response_len):
+                for key, tgt, n in (("B1", parity, args.cpu_sample_batch), ("B4", parity.get("batch_sample"), args.parity_batch)):
+                    g = gap.get(key)
+                    if tgt is None or g is None or g["batch"] != n or abs(g["ce_loss_reference_fp32"] - tgt["ce_loss_reference_fp32"]) > 1e-5:
+                        continue            # not the recorded sample (or the oracle and the recorded reference disagree: say nothing)
+                    tgt["ce_loss_reference_bf16_autocast"] = g["ce_loss_reference_bf16_autocast"]
+                    tgt["ce_loss_delta_vs_reference_bf16_autocast"] = abs(tgt["ce_loss_cuda_bf16"] - g["ce_loss_reference_bf16_autocast"])
+                    tgt["reference_own_bf16_vs_fp32_delta"] = g["gap"]
+        except Exception:
+            pass
         del hp
 
     if rank == 0:

@@ -1,0 +1,54 @@
+"""CE loss of the UNMODIFIED reference in fp32 and under its production recipe (fp32 masters + bf16 autocast,
+configs/training/production.yaml:49) on bench.py's two parity samples -- full-size model, seeded weights (seed 1), 30 s clips.
+Runs only where /root/reference exists (needs ~12 GB of RAM, a minute of CPU).  Output: tests/golden/reference_precision_gap.json,
+which bench.py reads to report the CUDA path's distance to the reference at LIKE-FOR-LIKE precision next to the fp32 delta.
+
+usage:  python oracle/make_reference_precision_gap.py
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import path_oracle as po  # noqa: E402
+from oracle.make_golden import build_reference_model, load_reference  # noqa: E402
+
+SAMPLES = {"B1": dict(batch=1, batch_seed=0), "B4": dict(batch=4, batch_seed=1)}      # bench.py: cpu_sample_batch / parity_batch
+COMMON = dict(weights_seed=1, proj_hidden=2048, clip_seconds=30.0, response_len=64)
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    mods = load_reference()
+    cfg = po.PathConfig(proj_hidden=COMMON["proj_hidden"])
+    W = po.init_weights(cfg, seed=COMMON["weights_seed"])
+    ref = build_reference_model(cfg, W, mods, "mlp")
+    ref.train()
+    out = {"config": dict(COMMON, model="GLM-ASR encoder 32L + Qwen3-0.6B 28L, MLP projector", autocast="torch.autocast('cpu', bfloat16)",
+                          torch=torch.__version__)}
+    for name, s in SAMPLES.items():
+        batch = po.synthetic_batch(cfg, s["batch"], COMMON["clip_seconds"], seed=s["batch_seed"], response_len=COMMON["response_len"])
+        n_items = int((batch["labels"] != -100).sum())
+        L = int(batch["sample_lengths"][0])
+        feats = ref.feature_extractor([batch["waveform"][b, :L].numpy() for b in range(s["batch"])], sampling_rate=16000,
+                                      padding="longest", return_attention_mask=True, return_tensors="pt")
+        rb = dict(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"], labels=batch["labels"],
+                  input_features=feats.input_features, audio_attention_mask=feats.attention_mask,
+                  audio_token_counts=batch["audio_token_counts"])
+        with torch.no_grad():
+            fp32 = float(ref(**rb, num_items_in_batch=torch.tensor(n_items)).loss)
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                bf16 = float(ref(**rb, num_items_in_batch=torch.tensor(n_items)).loss)
+        out[name] = dict(s, num_items=n_items, ce_loss_reference_fp32=fp32, ce_loss_reference_bf16_autocast=bf16, gap=abs(fp32 - bf16))
+        print(name, out[name], flush=True)
+    with open(os.path.join(ROOT, "tests", "golden", "reference_precision_gap.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -127,3 +127,22 @@ def test_oracle_greedy_ids_match_reference_generate():
     ids, margins = po.greedy_generate(W, ob, cfg, max_new_tokens=GENERATE_CASE["new_tokens"])
     assert float(margins.min()) > 1e-4          # every step is decisive at fp32 precision
     assert np.array_equal(ids.numpy(), fx["ids"])
+
+
+def test_oracle_equals_recorded_reference_on_the_bench_parity_sample():
+    """bench.py's CE-loss parity sample (full-size model, seed-1 weights, 1 x 30 s clip): the oracle's fp32 loss against the value the
+    unmodified reference produced (tests/golden/reference_precision_gap.json), which also records the reference's own bf16-autocast
+    loss -- the like-for-like yardstick bench.py reports next to the fp32 delta."""
+    import json
+    torch.set_num_threads(os.cpu_count())
+    gap = json.load(open(os.path.join(GOLD, "reference_precision_gap.json")))
+    c, s1 = gap["config"], gap["B1"]
+    cfg = po.PathConfig(proj_hidden=c["proj_hidden"])
+    W = po.init_weights(cfg, seed=c["weights_seed"])
+    batch = po.synthetic_batch(cfg, s1["batch"], c["clip_seconds"], seed=s1["batch_seed"], response_len=c["response_len"])
+    assert int((batch["labels"] != -100).sum()) == s1["num_items"]
+    with torch.no_grad():
+        loss, _ = po.model_forward(W, batch, cfg, s1["num_items"])
+    assert abs(float(loss) - s1["ce_loss_reference_fp32"]) < 2e-5
+    # the production recipe's own distance to fp32 on this sample is of the order of the 1e-3 budget
+    assert 2e-4 < s1["gap"] < 3e-3 and gap["B4"]["gap"] < s1["gap"]
