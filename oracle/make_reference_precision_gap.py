@@ -22,6 +22,37 @@ SAMPLES = {"B1": dict(batch=1, batch_seed=0), "B4": dict(batch=4, batch_seed=1)}
 COMMON = dict(weights_seed=1, proj_hidden=2048, clip_seconds=30.0, response_len=64)
 
 
+def gradient_gap(mods):
+    """Projector gradients of the reference, fp32 vs bf16 autocast, on the full-size 4 s fixture (tests/golden/full_b1_4s.npz's
+    inputs): the yardstick for the CUDA path's 2.8-3.6e-2 against fp32 (tests/test_path_gpu.py)."""
+    from oracle.make_golden import CASES
+    _, B, clip_s, _, R, seed = CASES["full_b1_4s"]
+    cfg = po.FULL
+    W = po.init_weights(cfg, seed=seed)
+    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R)
+    n_items = int((batch["labels"] != -100).sum())
+    ref = build_reference_model(cfg, W, mods, "mlp")
+    ref.train()
+    L = int(batch["sample_lengths"][0])
+    feats = ref.feature_extractor([batch["waveform"][b, :L].numpy() for b in range(B)], sampling_rate=16000, padding="longest",
+                                  return_attention_mask=True, return_tensors="pt")
+    rb = dict(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"], labels=batch["labels"],
+              input_features=feats.input_features, audio_attention_mask=feats.attention_mask,
+              audio_token_counts=batch["audio_token_counts"])
+
+    def run(autocast):
+        ref.zero_grad()
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+            loss = ref(**rb, num_items_in_batch=torch.tensor(n_items)).loss
+        loss.backward()
+        return float(loss.detach()), {k: p.grad.detach().clone() for k, p in ref.projector.named_parameters()}
+
+    l32, g32 = run(False)
+    l16, g16 = run(True)
+    return {"ce_loss_reference_fp32": l32, "ce_loss_reference_bf16_autocast": l16,
+            "grad_rel_err_bf16_vs_fp32": {k: float((g16[k].float() - g32[k]).norm() / g32[k].norm()) for k in g32}}
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     mods = load_reference()
@@ -46,6 +77,8 @@ def main():
                 bf16 = float(ref(**rb, num_items_in_batch=torch.tensor(n_items)).loss)
         out[name] = dict(s, num_items=n_items, ce_loss_reference_fp32=fp32, ce_loss_reference_bf16_autocast=bf16, gap=abs(fp32 - bf16))
         print(name, out[name], flush=True)
+    out["full_b1_4s_gradients"] = gradient_gap(mods)
+    print(out["full_b1_4s_gradients"], flush=True)
     with open(os.path.join(ROOT, "tests", "golden", "reference_precision_gap.json"), "w") as f:
         json.dump(out, f, indent=1)
 
