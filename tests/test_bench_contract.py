@@ -42,3 +42,25 @@ def test_step_flop_formula_matches_survey_figure():
     assert f["executed"] < f["reference"] and abs((f["reference"] - f["executed"]) - 4.0 * d.vocab * d.lm_dim * (464 - 65)) < 1.0
     g = bench.path_flops(d, 30.0, 464, 65, 375, train_lm=True)
     assert g["executed"] - f["executed"] > 2.0 * 440e6 * 464              # + the decoder's weight-gradient GEMMs
+
+
+def test_clock_sampler_summarises_nvidia_smi_rows():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+    cs = bench.ClockSampler(0)
+    cs.proc = FakeProc()
+    cs.rows = [["0", "1530", "1965", "998.1", "0x4", "Not Active", "Not Active", "Not Active", "Active"],
+               ["0", "1672", "1965", "1001.3", "0x4", "Not Active", "Not Active", "Not Active", "Active"],
+               ["0", "1545", "1965", "1000.0", "0x0", "Not Active", "Not Active", "Not Active", "Not Active"],
+               ["garbled"]]
+    got = cs.stop()
+    assert got == {"sm_mhz": 1545.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3}
+    cs2 = bench.ClockSampler(0)          # nvidia-smi could not be started: the line says so instead of inventing clocks
+    assert cs2.stop()["reasons"] == ["nvidia-smi unavailable"]
