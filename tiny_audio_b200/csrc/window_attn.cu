@@ -382,7 +382,9 @@ window_attn2_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
     }
 }
 
-int g_window_attn_variant = 1;      // 1: lanes over head_dim (any head_dim); 2: key per lane (head_dim % 8 == 0)
+// 1: lanes over head_dim (any head_dim); 2 (default): key per lane (head_dim % 8 == 0, else variant 1 runs).  Measured on a B200,
+// QFormer recipe at batch 32 x 30 s: 133.8 ms/step with variant 1, 128.9 ms with variant 2 (profiles/r02_c01_*)
+int g_window_attn_variant = 2;
 
 bool use_variant2(int hd, const void* a, const void* b, const void* c, const void* d) {
     auto aligned = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };

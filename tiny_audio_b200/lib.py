@@ -12,7 +12,9 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtinyaudio_b200.so")
+# TA_LIB_VARIANT=pdl selects the A/B build `make PDL=1` leaves next to the default library (csrc/Makefile)
+_VARIANT = os.environ.get("TA_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, f"libtinyaudio_b200{'_' + _VARIANT if _VARIANT else ''}.so")
 
 c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 P = c_void_p
