@@ -56,6 +56,12 @@ def parse():
                     help="after the timed region, run ONE more step under torch.profiler (CUPTI activity tracing, no replay) and write "
                          "the per-kernel device-time table to FILE: the in-situ complement of the serialised ncu launch list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short timed runs of the other BASELINE configurations (32 x 10 s, 8 x 30 s, qformer, LoRA)")
+    ap.add_argument("--other-steps", type=int, default=5)
+    ap.add_argument("--no-dp-parity", action="store_true")
+    ap.add_argument("--dp-parity-batch", type=int, default=64,
+                    help="clips of the ONE global batch the data-parallel parity check shards over the ranks (BASELINE configs[2]: 64)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--cpu-threads", type=int, default=32)
@@ -157,11 +163,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference(args, max(1, args.steps), max(0, min(args.warmup, 1)), args.cpu_sample_batch)
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+    # exactly K timed steps after W warm-up steps, each step = ONE train step on a bounded sample of the workload (B = 1 clip of the
+    # named length: a 32-clip step takes minutes on the host); `value` scales with the clip count, so audio-s/s is comparable
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    r = cpu_reference(args, steps, warmup, args.cpu_sample_batch)
+    cfg = workload_config(args, args.gpus)          # the arm's config is OUR arm's (the contract); what was timed is in `sample`
+    sample = (f"each timed step = one full train step (fwd + bwd + clip + AdamW) of the oracle port on {args.cpu_sample_batch} x "
+              f"{args.clip_seconds:g} s clip(s), not {args.batch}: a bounded sample of the workload (audio-s/s is per clip-second); "
+              f"{steps} timed steps after {warmup} warm-up")
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, args.gpus),
+            "config": cfg, "sample": sample,
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -235,12 +248,141 @@ def trace_kernels(step, path, header):
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
+def ncu_metric(kernel_prefix: str, shape: str):
+    """Entry of profiles/ncu_metrics.json (written by tools/ncu_summary.py --json from an `ncu --set full` capture) for a kernel +
+    shape, or None: the bench line quotes DRAM traffic / tensor-pipe % from the committed profile, never from a literal."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_metrics.json")) as f:
+            db = json.load(f)
+    except Exception:
+        return None
+    for key, e in db.items():
+        if e.get("kernel", "").replace(" ", "").startswith(kernel_prefix.replace(" ", "")) and shape.replace(" ", "") in e.get("shape", "").replace(" ", ""):
+            return e
+    return None
+
+
+class Workload:
+    """One recipe (projector plugin, LoRA / unfrozen decoder or not) at full model size on this rank's GPU: model, optimiser,
+    a synthetic batch, and the two step functions (device-resident inputs / public API from pinned host buffers)."""
+
+    def __init__(self, args, dims, dev, rank, world, projector="mlp", lora=False, train_lm=False):
+        from tiny_audio_b200.optim import ClipAdamW
+        from tiny_audio_b200.synthetic import build_offline_model
+        self.args, self.dims, self.dev, self.rank, self.world = args, dims, dev, rank, world
+        self.projector, self.lora, self.train_lm = projector, lora, train_lm
+        self.generic = projector != "mlp" or lora           # routes through the public surface (module projector / adapters)
+        extras = dict(router_jitter_noise=0.0) if projector == "moe" else {}
+        self.model = build_offline_model(dims, device=dev, seed=1234, freeze_language_model=not train_lm, projector_type=projector,
+                                         use_lora=lora, **extras)
+        self.model.train()
+        self.hot = self.model._hot_path()
+        self.names = [n for n, _ in self.model.projector.named_parameters()]
+        self.params = [p for _, p in self.model.projector.named_parameters()]
+        # bench.py is a plain torchrun loop (no DistributedDataParallel wrapper): the optimiser owns the one all-reduce
+        if self.generic and not train_lm:
+            self.opt = ClipAdamW([p for p in self.model.parameters() if p.requires_grad], lr=1e-3, max_grad_norm=1.0, allreduce=True)
+        elif train_lm:
+            # the reference's parameter groups (scripts/train.py:384-437): `language_model.*` gets the decoder lr / weight decay.  Its
+            # decay split only exempts nn.LayerNorm modules and biases -- Qwen3's RMSNorm gains decay with the rest
+            # (tests/test_reference_trainpy.py runs the unmodified create_optimizer over this model and gets these two groups)
+            dec = [p for n, p in self.model.named_parameters() if p.requires_grad and n.startswith("language_model.")]
+            self.opt = ClipAdamW([dict(params=self.params, lr=1e-3, weight_decay=0.0), dict(params=dec, lr=2e-5, weight_decay=0.01)],
+                                 max_grad_norm=1.0, allreduce=True)
+        else:
+            self.opt = ClipAdamW(self.params, lr=1e-3, max_grad_norm=1.0, allreduce=True)
+        self.pmap = {n: p.data for n, p in zip(self.names, self.params)}
+        self.gmap = {n: p.grad for n, p in zip(self.names, self.params)}
+
+    def set_batch(self, B, clip_seconds, seed=None):
+        from tiny_audio_b200.synthetic import synthetic_batch
+        a = self.args
+        self.B, self.clip_seconds = B, clip_seconds
+        self.host = synthetic_batch(self.dims, B, clip_seconds, seed=(100 + self.rank) if seed is None else seed,
+                                    response_len=a.response_len, pin=True, projector=self.projector)
+        self.n_lab_local = int((self.host["labels"] != -100).sum())
+        self.n_items_global = self.n_lab_local * self.world      # equal-length synthetic batches: arithmetic, no collective needed
+        self.d_wave = self.host["input_features"].to(self.dev)
+        self.d_ids = self.host["input_ids"].to(self.dev)
+        self.d_cnt = self.host["audio_token_counts"].to(self.dev)
+        return self
+
+    def step_resident(self):
+        if self.train_lm or self.generic:      # unfrozen decoder / module projector / LoRA: the public surface routes the gradients
+            self.opt.zero_grad()
+            out = self.model(input_ids=self.d_ids, input_features=self.d_wave, labels=self.host["labels"], audio_token_counts=self.d_cnt,
+                             num_items_in_batch=self.n_items_global)
+            out.loss.backward()
+            self.opt.step()
+            return out.loss.detach()
+        loss, _ = self.hot.forward_backward(input_ids=self.d_ids, labels=self.host["labels"], proj_params=self.pmap, waveform=self.d_wave,
+                                            audio_token_counts=self.d_cnt, num_items_in_batch=self.n_items_global, grads=self.gmap)
+        self.opt.step()
+        return loss
+
+    def step_e2e(self):
+        h = self.host
+        self.opt.zero_grad()
+        out = self.model(input_ids=h["input_ids"], input_features=h["input_features"], labels=h["labels"], attention_mask=h["attention_mask"],
+                         audio_token_counts=h["audio_token_counts"], num_items_in_batch=self.n_items_global)
+        out.loss.backward()
+        self.opt.step()
+        return float(out.loss.detach())   # device -> host read of the step's loss
+
+    def h2d_bytes(self):
+        return sum(self.host[k].numel() * self.host[k].element_size() for k in ("input_features", "input_ids", "audio_token_counts"))
+
+    def free(self):
+        self.model = self.hot = self.opt = self.pmap = self.gmap = self.params = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def dp_parity(w: Workload, global_batch: int, clip_seconds: float):
+    """North star: "CE loss within 1e-3 of the reference at 1/2/4/8 GPUs".  ONE seeded global batch (BASELINE configs[2]: 64 clips)
+    is sharded over the ranks (tiny_audio_b200.dp.shard_batch), every rank normalises by the GLOBAL label-token count, the
+    projector gradients are SUM-all-reduced (the step's one collective) and the losses summed; rank 0 then runs the WHOLE global batch
+    alone.  Reported: both losses, their delta, and the relative difference of the reduced gradient -- comparable across the N = 1/2/4/8
+    runs of the scaling sweep because the 64 clips are the same at every N."""
+    import torch.distributed as dist
+    from tiny_audio_b200 import dp
+    from tiny_audio_b200.synthetic import synthetic_batch
+    dev, rank, world = w.dev, w.rank, w.world
+    if global_batch % world != 0:
+        return {"skipped": f"global batch {global_batch} not divisible by {world} ranks"}
+    gb = synthetic_batch(w.dims, global_batch, clip_seconds, seed=4242, response_len=w.args.response_len)
+    keys = ("input_features", "input_ids", "labels", "audio_token_counts")
+    mine = dp.shard_batch({k: gb[k] for k in keys}, rank, world)
+    n_global = dp.global_num_items(mine["labels"], device=dev)
+
+    def run(b):
+        grads = {n: torch.zeros_like(p) for n, p in w.pmap.items()}
+        loss, _ = w.hot.forward_backward(input_ids=b["input_ids"].to(dev), labels=b["labels"], proj_params=w.pmap, waveform=b["input_features"].to(dev),
+                                         audio_token_counts=b["audio_token_counts"].to(dev), num_items_in_batch=n_global, grads=grads)
+        return loss.clone(), torch.cat([grads[n].reshape(-1) for n in w.names])
+
+    loss_r, flat = run(mine)
+    dp.allreduce_flat_(flat)
+    if world > 1:
+        dist.all_reduce(loss_r, op=dist.ReduceOp.SUM)
+    out = {"global_batch": global_batch, "clip_seconds": clip_seconds, "n_ranks": world, "batch_seed": 4242, "num_items_global": int(n_global),
+           "loss_dp": float(loss_r), "grad_checksum_dp": {"sum": float(flat.double().sum()), "l2": float(flat.double().norm())}}
+    if rank == 0:
+        if world > 1:
+            loss_1, flat_1 = run({k: gb[k] for k in keys})
+        else:
+            loss_1, flat_1 = loss_r, flat
+        out.update({"loss_single_gpu": float(loss_1), "dp_loss_delta": abs(float(loss_r) - float(loss_1)),
+                    "grad_rel_err_vs_single_gpu": float((flat - flat_1).double().norm() / (flat_1.double().norm() + 1e-30))})
+    torch.cuda.synchronize()
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from tiny_audio_b200 import lib as L
     from tiny_audio_b200.engine import PathDims
-    from tiny_audio_b200.optim import ClipAdamW
-    from tiny_audio_b200.synthetic import build_offline_model, synthetic_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -252,61 +394,13 @@ def run_ours(args):
     lib = L.load()
 
     dims = PathDims(proj_hidden=args.proj_hidden)
-    generic = args.projector != "mlp" or args.lora           # routes through the public surface (module projector / adapters)
-    extras = dict(router_jitter_noise=0.0) if args.projector == "moe" else {}
-    model = build_offline_model(dims, device=dev, seed=1234, freeze_language_model=not args.train_lm, projector_type=args.projector,
-                                use_lora=args.lora, **extras)
-    model.train()
-    hot = model._hot_path()
-    # the HF modules only own the fp32 master copies; free them (the packed bf16 copies in `hot` are what runs)
-    names = [n for n, _ in model.projector.named_parameters()]
-    params = [p for _, p in model.projector.named_parameters()]
-    if generic and not args.train_lm:
-        opt = ClipAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, max_grad_norm=1.0)
-    elif args.train_lm:
-        # the reference's parameter groups (scripts/train.py:384-437): `language_model.*` gets the decoder lr / weight decay,
-        # norm gains are excluded from decay
-        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
-        dec = [p for n, p in named if n.startswith("language_model.") and p.dim() > 1]
-        dec_nd = [p for n, p in named if n.startswith("language_model.") and p.dim() <= 1]
-        opt = ClipAdamW([dict(params=params, lr=1e-3, weight_decay=0.0), dict(params=dec, lr=2e-5, weight_decay=0.01),
-                         dict(params=dec_nd, lr=2e-5, weight_decay=0.0)], max_grad_norm=1.0)
-    else:
-        opt = ClipAdamW(params, lr=1e-3, max_grad_norm=1.0)
-
+    generic = args.projector != "mlp" or args.lora
+    w = Workload(args, dims, dev, rank, world, projector=args.projector, lora=args.lora, train_lm=args.train_lm)
     B = args.batch
-    host = synthetic_batch(dims, B, args.clip_seconds, seed=100 + rank, response_len=args.response_len, pin=True,
-                           projector=args.projector)
-    n_lab_local = int((host["labels"] != -100).sum())
-    n_items_global = n_lab_local * world            # equal-length synthetic batches: arithmetic, no collective needed
-    d_wave = host["input_features"].to(dev)
-    d_ids = host["input_ids"].to(dev)
-    d_cnt = host["audio_token_counts"].to(dev)
-    labels_cpu = host["labels"]
-    pmap = {n: p.data for n, p in zip(names, params)}
-    gmap = {n: p.grad for n, p in zip(names, params)}
-
-    def step_resident():
-        if args.train_lm or generic:      # unfrozen decoder / module projector / LoRA: the public surface routes the gradients
-            opt.zero_grad()
-            out = model(input_ids=d_ids, input_features=d_wave, labels=labels_cpu, audio_token_counts=d_cnt,
-                        num_items_in_batch=n_items_global)
-            out.loss.backward()
-            opt.step()
-            return out.loss.detach()
-        loss, _ = hot.forward_backward(input_ids=d_ids, labels_cpu=labels_cpu, proj_params=pmap, waveform=d_wave,
-                                       audio_token_counts=d_cnt, num_items_in_batch=n_items_global, grads=gmap)
-        opt.step()
-        return loss
-
-    def step_e2e():
-        opt.zero_grad()
-        out = model(input_ids=host["input_ids"], input_features=host["input_features"], labels=host["labels"],
-                    attention_mask=host["attention_mask"], audio_token_counts=host["audio_token_counts"],
-                    num_items_in_batch=n_items_global)
-        out.loss.backward()
-        opt.step()
-        return float(out.loss.detach())   # device -> host read of the step's loss
+    w.set_batch(B, args.clip_seconds)
+    host = w.host
+    n_lab_local = w.n_lab_local
+    step_resident, step_e2e = w.step_resident, w.step_e2e
 
     def barrier():
         if world > 1:
@@ -351,9 +445,42 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         ms_e2e, _, _, _ = timed(step_e2e, args.steps, 2)
-        h2d = sum(host[k].numel() * host[k].element_size() for k in ("input_features", "input_ids", "audio_token_counts"))
-        e2e = {"value": audio_s / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+        e2e = {"value": audio_s / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": w.h2d_bytes(),
                "d2h_bytes_per_step": 4}
+
+    # ---- data-parallel parity on ONE global batch (configs[2]: 64 x 30 s), every rank takes part ----
+    parity_dp = None
+    if not generic and not args.train_lm and not args.no_dp_parity:
+        try:
+            parity_dp = dp_parity(w, args.dp_parity_batch, args.clip_seconds)
+        except Exception as e:      # a diagnostic must never cost the bench line (all ranks fail alike: no rank is left in a collective)
+            parity_dp = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- the other BASELINE configurations, a few timed steps each (device-resident inputs, same timing rules) ----
+    other = None
+    if not args.no_other_configs and not generic and not args.train_lm:
+        other = {}
+        k_steps, k_warm = args.other_steps, 3
+
+        def measure(wl, Bc, clip_s, label):
+            wl.set_batch(Bc, clip_s)
+            smp = ClockSampler(local) if rank == 0 else None
+            ms, n_launch, clk, loss = timed(wl.step_resident, k_steps, k_warm, smp)
+            other[label] = {"workload": f"{wl.projector} projector{' + Qwen3 LoRA r=8' if wl.lora else ''}, batch {Bc}/GPU x {clip_s:g} s",
+                            "global_batch": Bc * world, "ms_per_step": ms, "value": Bc * world * clip_s / (ms / 1000.0), "unit": UNIT,
+                            "steps": k_steps, "warmup": k_warm, "gpu_launches": int(n_launch), "clocks": clk, "loss": float(loss)}
+        try:
+            measure(w, 32, 10.0, "configs[1] mlp 32 x 10 s")
+            measure(w, 8, 30.0, "configs[2] mlp 8/GPU x 30 s (global 64 at 8 GPUs)")
+            w.set_batch(B, args.clip_seconds)          # the roofline / parity code below reads the headline batch
+            for label, kw in (("configs[3] qformer 32 x 30 s", dict(projector="qformer")), ("configs[4] mlp + LoRA 32 x 30 s", dict(lora=True))):
+                wl = Workload(args, dims, dev, rank, world, **kw)
+                measure(wl, 32, 30.0, label)
+                wl.free()
+                del wl
+        except Exception as e:
+            other["error"] = f"{type(e).__name__}: {e}"
+        host = w.host
 
     # ---- roofline of the dominant kernel: the tcgen05 GEMM, timed alone on its largest shape of the step ----
     roof = None
@@ -362,48 +489,9 @@ def run_ours(args):
         S_e = int(args.clip_seconds * 16000) // 160 // 2
         M, N, K = B * S_e, dims.enc_ffn, dims.enc_dim          # encoder fc1 (+bias+GELU): 32 launches / step
         a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
-        w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.03
+        wt = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.03
         bias = torch.zeros(N, device=dev, dtype=torch.float32)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        for _ in range(3):
-            L.gemm(a, w, epi=L.EPI_BF16_GELU, bias=bias, out=out)
-        torch.cuda.synchronize()
-        reps = 10
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            L.gemm(a, w, epi=L.EPI_BF16_GELU, bias=bias, out=out)
-        e1.record()
-        torch.cuda.synchronize()
-        t = e0.elapsed_time(e1) / reps / 1000.0
-        ach = 2.0 * M * N * K / t / 1e12
-        peak = pk["bf16_tflops"]
-        roof = {"bound": "tensor", "kernel": f"gemm2_kernel<256,BF16_GELU> (cta_group::2) M={M} N={N} K={K} (encoder fc1)", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": f"{how} burst (kernel timed alone)",
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
-                # (profiles/r01_ncu_top_kernels_summary.txt: 136.2 MB + 440.4 MB; algorithmic A + W + C = 626.7 MB, part of C stays in L2)
-                "traffic": 576.5e6 if (M, N, K) == (48000, 5120, 1280) else None,
-                "algorithmic_bytes": 2.0 * (M * K + N * K + M * N), "tensor_pipe_active_pct_ncu": 74.5}
-        # whole step as TFLOP/s per GPU: SURVEY 8d's work figure (the reference's work) and the work actually launched
-        fl = path_flops(dims, args.clip_seconds, int(host["input_ids"].shape[1]), n_lab_local // B, int(host["audio_token_counts"][0]),
-                        train_lm=args.train_lm)
-        per_s = B / (ms_step / 1000.0) / 1e12
-        roof.update({"step_tflops": fl["reference"] * per_s, "step_frac_of_sustained": fl["reference"] * per_s / pk["bf16_tflops_sustained"],
-                     "step_tflops_executed": fl["executed"] * per_s,
-                     "work": {"gflop_per_audio_second_reference_path": fl["reference"] / args.clip_seconds / 1e9,
-                              "gflop_per_audio_second_executed": fl["executed"] / args.clip_seconds / 1e9,
-                              "note": "reference path = SURVEY 8d formula (lm_head on all positions); executed = lm_head on labelled rows only"}})
-        # the Qwen3 FFN GEMMs the north star names (M = B x S_lm tokens, dim 1024, ffn 3072), timed alone the same way, with the
-        # epilogues the training step uses: gate_up with fused SwiGLU + (gate, up) stash for the backward; down + fp32 residual
-        S_lm = int(host["input_ids"].shape[1])
-        Mt, Dl, Fl = B * S_lm, dims.lm_dim, dims.lm_ffn
-        xq = torch.randn(Mt, Dl, device=dev, dtype=torch.bfloat16)
-        wgu = torch.randn(2 * Fl, Dl, device=dev, dtype=torch.bfloat16) * 0.03
-        hq = torch.empty(Mt, Fl, device=dev, dtype=torch.bfloat16)
-        guq = torch.empty(Mt, 2 * Fl, device=dev, dtype=torch.bfloat16)
-        wdn = torch.randn(Dl, Fl, device=dev, dtype=torch.bfloat16) * 0.03
-        rq = torch.zeros(Mt, Dl, device=dev, dtype=torch.float32)
-        yq = torch.empty(Mt, Dl, device=dev, dtype=torch.float32)
 
         def time_alone(fn, reps=20):
             for _ in range(3):
@@ -417,25 +505,76 @@ def run_ours(args):
             torch.cuda.synchronize()
             return a0.elapsed_time(a1) / reps / 1000.0
 
+        t = time_alone(lambda: L.gemm(a, wt, epi=L.EPI_BF16_GELU, bias=bias, out=out), reps=10)
+        ach = 2.0 * M * N * K / t / 1e12
+        peak = pk["bf16_tflops"]
+        prof = ncu_metric("gemm2_kernel<256,1", f"M={M} N={N} K={K}")
+        roof = {"bound": "tensor", "kernel": f"gemm2_kernel<256,BF16_GELU> (cta_group::2) M={M} N={N} K={K} (encoder fc1)", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": f"{how} burst (kernel timed alone)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch: read from profiles/ncu_metrics.json (ncu --set full capture of
+                # this kernel at this shape; null when no committed capture matches)
+                "traffic": prof["dram_bytes"] if prof else None,
+                "algorithmic_bytes": 2.0 * (M * K + N * K + M * N),
+                "tensor_pipe_active_pct_ncu": prof["tensor_pipe_active_pct"] if prof else None,
+                "ncu_source": ({"file": prof["source"], "git_sha": prof["git_sha"]} if prof else None)}
+        # whole step as TFLOP/s per GPU: the work actually launched leads; SURVEY 8d's figure (the reference's work) beside it
+        fl = path_flops(dims, args.clip_seconds, int(host["input_ids"].shape[1]), n_lab_local // B, int(host["audio_token_counts"][0]),
+                        train_lm=args.train_lm)
+        per_s = B / (ms_step / 1000.0) / 1e12
+        roof.update({"step_tflops": fl["executed"] * per_s, "step_frac_of_sustained": fl["executed"] * per_s / pk["bf16_tflops_sustained"],
+                     "step_tflops_reference_work": fl["reference"] * per_s,
+                     "work": {"gflop_per_audio_second_executed": fl["executed"] / args.clip_seconds / 1e9,
+                              "gflop_per_audio_second_reference_path": fl["reference"] / args.clip_seconds / 1e9,
+                              "note": "executed = lm_head on labelled rows only (what this implementation launches); reference path = SURVEY 8d "
+                                      "formula (lm_head on all positions)"}})
+        # the Qwen3 FFN GEMMs the north star names (M = B x S_lm tokens, dim 1024, ffn 3072), timed alone the same way, with the
+        # epilogues the training step uses: gate_up with fused SwiGLU + (gate, up) stash for the backward; down + fp32 residual;
+        # d(h) with the SwiGLU-backward epilogue
+        S_lm = int(host["input_ids"].shape[1])
+        Mt, Dl, Fl = B * S_lm, dims.lm_dim, dims.lm_ffn
+        xq = torch.randn(Mt, Dl, device=dev, dtype=torch.bfloat16)
+        wgu = torch.randn(2 * Fl, Dl, device=dev, dtype=torch.bfloat16) * 0.03
+        hq = torch.empty(Mt, Fl, device=dev, dtype=torch.bfloat16)
+        guq = torch.empty(Mt, 2 * Fl, device=dev, dtype=torch.bfloat16)
+        dguq = torch.empty(Mt, 2 * Fl, device=dev, dtype=torch.bfloat16)
+        wdn = torch.randn(Dl, Fl, device=dev, dtype=torch.bfloat16) * 0.03
+        wdn_t = wdn.t().contiguous()
+        rq = torch.zeros(Mt, Dl, device=dev, dtype=torch.float32)
+        yq = torch.empty(Mt, Dl, device=dev, dtype=torch.float32)
         t_gu = time_alone(lambda: L.gemm(xq, wgu, epi=L.EPI_SWIGLU, out=hq, out2=guq))
         t_gu0 = time_alone(lambda: L.gemm(xq, wgu, epi=L.EPI_SWIGLU, out=hq))
         t_dn = time_alone(lambda: L.gemm(hq, wdn, epi=L.EPI_F32_RESID, resid=rq, out=yq))
+        t_bw = time_alone(lambda: L.gemm(xq, wdn_t, epi=L.EPI_SWIGLU_BWD, aux=guq, out=dguq))
         f_gu, f_dn = 2.0 * Mt * 2 * Fl * Dl, 2.0 * Mt * Dl * Fl
-        roof["qwen3_ffn"] = {
-            "shape": f"M={Mt} dim={Dl} ffn={Fl}",
-            "gate_up_swiglu_stash": {"us": t_gu * 1e6, "tflops": f_gu / t_gu / 1e12, "frac": f_gu / t_gu / 1e12 / peak},
-            "gate_up_swiglu_nostash": {"us": t_gu0 * 1e6, "tflops": f_gu / t_gu0 / 1e12, "frac": f_gu / t_gu0 / 1e12 / peak},
-            "down_resid": {"us": t_dn * 1e6, "tflops": f_dn / t_dn / 1e12, "frac": f_dn / t_dn / 1e12 / peak},
-            "tensor_pipe_active_pct_ncu": {"gate_up_swiglu_stash": 65.0, "source": "profiles/r01_ncu_top_kernels_summary.txt"}}
-        del xq, wgu, hq, guq, wdn, rq, yq
-        del a, w, out
+        p5, p3, p6 = (ncu_metric("gemm2_kernel<256,5", ""), ncu_metric("gemm2_kernel<256,3", ""), ncu_metric("gemm2_kernel<256,6", ""))
+
+        def ffn_entry(tt, fl_, pm):
+            return {"us": tt * 1e6, "tflops": fl_ / tt / 1e12, "frac": fl_ / tt / 1e12 / peak,
+                    "tensor_pipe_active_pct_ncu": pm["tensor_pipe_active_pct"] if pm else None,
+                    "ncu_source": ({"file": pm["source"], "git_sha": pm["git_sha"], "shape": pm["shape"]} if pm else None)}
+        roof["qwen3_ffn"] = {"shape": f"M={Mt} dim={Dl} ffn={Fl}", "gate_up_swiglu_stash": ffn_entry(t_gu, f_gu, p5),
+                             "gate_up_swiglu_nostash": ffn_entry(t_gu0, f_gu, None), "down_resid": ffn_entry(t_dn, f_dn, p3),
+                             "dh_swiglu_backward": ffn_entry(t_bw, f_dn, p6)}
+        del xq, wgu, hq, guq, dguq, wdn, wdn_t, rq, yq
+        # encoder self-attention alone (32 launches / step): 4 S^2 hd FLOP per (clip, head)
+        Hh, hd_e = dims.enc_heads, dims.enc_dim // dims.enc_heads
+        qkv = torch.randn(B, S_e, 3 * dims.enc_dim, device=dev, dtype=torch.bfloat16)
+        ao = torch.empty(B, S_e, dims.enc_dim, device=dev, dtype=torch.bfloat16)
+        t_at = time_alone(lambda: L.check(lib.ta_attn_fwd(L.ptr(qkv), L.ptr(qkv[:, :, dims.enc_dim:]), L.ptr(qkv[:, :, 2 * dims.enc_dim:]), L.ptr(ao), None,
+                                                          B, S_e, Hh, Hh, hd_e, 3 * dims.enc_dim, 3 * dims.enc_dim, 3 * dims.enc_dim, dims.enc_dim, 0,
+                                                          hd_e ** -0.5, L.stream_ptr())), reps=10)
+        f_at = 4.0 * S_e * S_e * hd_e * Hh * B
+        roof["encoder_attention"] = {"shape": f"B={B} S={S_e} H={Hh} hd={hd_e}", "us": t_at * 1e6, "tflops": f_at / t_at / 1e12,
+                                     "frac": f_at / t_at / 1e12 / peak,
+                                     "note": "bound by exp2 on the SFUs, not by the tensor pipe (256 FLOP per exponential at head_dim 64)"}
+        del a, wt, out, qkv, ao
 
     cpu = None
     parity = None
     if generic and roof is not None:      # the 116 GFLOP/audio-s work figure is the MLP-projector path's
-        roof["step_tflops"] = roof["step_frac_of_sustained"] = roof["step_tflops_executed"] = roof["work"] = None
+        roof["step_tflops"] = roof["step_frac_of_sustained"] = roof["step_tflops_reference_work"] = roof["work"] = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not generic:
-        del model
+        w.free()
         r = cpu_reference(args, 1, 1, args.cpu_sample_batch, keep_inputs=True)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         # second half of the BASELINE metric: CE-loss delta vs the reference arithmetic on identical seeded weights and inputs
@@ -444,7 +583,7 @@ def run_ours(args):
         cfg_o, W0, b0, n0, loss_ref = r["_parity"]
         hp = HotPath(PathDims.from_any(cfg_o.to_dict()), W0["encoder"], W0["lm"], dev)
         pp = {k: v.clone().to(dev).contiguous() for k, v in W0["projector"].items()}
-        l_gpu, _ = hp.forward_backward(input_ids=b0["input_ids"].to(dev), labels_cpu=b0["labels"], proj_params=pp,
+        l_gpu, _ = hp.forward_backward(input_ids=b0["input_ids"].to(dev), labels=b0["labels"], proj_params=pp,
                                        waveform=b0["waveform"].to(dev), audio_token_counts=b0["audio_token_counts"].to(dev),
                                        num_items_in_batch=n0)
         parity = {"ce_loss_cuda_bf16": float(l_gpu), "ce_loss_reference_fp32": loss_ref, "ce_loss_delta": abs(float(l_gpu) - loss_ref),
@@ -458,7 +597,7 @@ def run_ours(args):
             n_p = int((bp["labels"] != -100).sum())
             with torch.no_grad():
                 l_ref_p, _ = po.model_forward(W0, bp, cfg_o, n_p)
-            l_gpu_p, _ = hp.forward_backward(input_ids=bp["input_ids"].to(dev), labels_cpu=bp["labels"], proj_params=pp,
+            l_gpu_p, _ = hp.forward_backward(input_ids=bp["input_ids"].to(dev), labels=bp["labels"], proj_params=pp,
                                              waveform=bp["waveform"].to(dev), audio_token_counts=bp["audio_token_counts"].to(dev),
                                              num_items_in_batch=n_p)
             parity["batch_sample"] = {"sample": f"B={args.parity_batch} x {args.clip_seconds:g} s", "ce_loss_cuda_bf16": float(l_gpu_p),
@@ -480,12 +619,17 @@ def run_ours(args):
         except Exception:
             pass
         del hp
+    if parity_dp is not None:
+        parity = dict(parity or {}, dp=parity_dp)
+        if "dp_loss_delta" in parity_dp:
+            parity["dp_loss_delta"] = parity_dp["dp_loss_delta"]
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "parity": parity, "loss": float(last_loss)}
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "parity": parity, "other_configs": other,
+                "loss": float(last_loss)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

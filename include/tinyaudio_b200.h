@@ -148,6 +148,14 @@ int ta_window_attn_bwd(const void* q, const void* k, const void* v, const float*
 int ta_window_attn_set_variant(int variant);
 /* tiny_audio/projectors.py:79-87 (_frame_stack): row j <- frames k*j .. k*j+k-1, feature-major per frame */
 int ta_frame_stack(const void* x /*bf16 [B,S,D]*/, void* out /*bf16 [B,n,k*D]*/, int B, int S, int n, int k, int D, void* stream);
+/* a4. tiny_audio/asr_modeling.py:458-479 (_maybe_drop_audio_tokens): whole encoder frames zeroed by a {0,1} keep mask, no rescale.
+ * The Bernoulli draw stays with torch's generator (same RNG contract as the reference); this applies it in place. */
+int ta_frame_keep_mask(void* x /*bf16 [rows,D], in place*/, const float* keep /*[rows]*/, long long rows, int D, void* stream);
+/* a9. HF:loss/loss_utils.py:56-59 (shift labels by one, ignore_index -100) as device-side bookkeeping: ascending flat positions
+ * p = b*S + s with labels[b, s+1] != -100, their targets, and the count -- replaces a labels.cpu() + nonzero() on the host when
+ * the Trainer hands device-resident labels; the caller reads back the 4-byte count to size the lm_head product. */
+int ta_label_rows(const long long* labels /*[B,S]*/, int B, int S, int* rows /*[B*S]*/, int* targets /*[B*S]*/, int* count /*[1]*/,
+                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a12. optimiser: clip_grad_norm_(1.0) + torch.optim.AdamW(fused) (configs/training/production.yaml:5-9)

@@ -130,6 +130,8 @@ def sub(t: torch.Tensor, n: int = 4096) -> np.ndarray:
     return f[::step][:n].float().numpy().copy()
 
 
+DROPOUT_SEED = 4242
+
 CASES = {
     # name: (cfg kwargs or 'full', batch, clip_s, pad_s, response_len, seed)
     "small_b2_2s":   (dict(), 2, 2.0, None, 16, 11),
@@ -146,6 +148,10 @@ CASES = {
     # router logits 0.87 apart, far beyond the bf16 encoder's perturbation, so the top-2 choice cannot flip between precisions
     "mosa_b2_2s": (dict(enc_layers=1, lm_layers=1, _projector="mosa"), 2, 2.0, None, 8, 17),
     "moe_b2_2s": (dict(enc_layers=1, lm_layers=1, _projector="moe"), 2, 2.0, None, 8, 21),
+    # audio_token_dropout = 0.10 (the production value, configs/config.yaml:32) in train mode: the reference draws its Bernoulli
+    # keep mask from torch's CPU generator right after `torch.manual_seed(DROPOUT_SEED)`; the mask it drew is recorded so that
+    # the oracle and the CUDA path can replay the same draw (asr_modeling.py:458-479)
+    "dropout_b2_2s": (dict(enc_layers=1, lm_layers=1, _dropout=0.10), 2, 2.0, None, 8, 23),
 }
 
 PROJECTOR_INIT = {"qformer": po.init_qformer_weights, "mosa": po.init_mosa_weights, "moe": po.init_moe_weights}
@@ -159,6 +165,7 @@ def case_config(spec):
     spec = dict(spec)
     kind = spec.pop("_projector", "mlp")
     spec.pop("_train_lm", None)
+    spec.pop("_dropout", None)
     return po.small_config(**spec), kind
 
 
@@ -166,6 +173,7 @@ def run_case(name, mods, outdir):
     spec, B, clip_s, pad_s, R, seed = CASES[name]
     cfg, kind = case_config(spec)
     train_lm = isinstance(spec, dict) and spec.get("_train_lm", False)
+    p_drop = float(spec.get("_dropout", 0.0)) if isinstance(spec, dict) else 0.0
     torch.manual_seed(0)
     t0 = time.time()
     W = po.init_weights(cfg, seed=seed)
@@ -182,6 +190,7 @@ def run_case(name, mods, outdir):
             am[b, -cut:] = 0
         batch.update(input_ids=ids, labels=labels, attention_mask=am)
     model = build_reference_model(cfg, W, mods, kind, freeze_lm=not train_lm, **PROJECTOR_CONFIG_EXTRAS.get(kind, {}))
+    model.config.audio_token_dropout = p_drop
     model.train()
     if kind == "qformer":
         model.projector.eval()
@@ -201,7 +210,24 @@ def run_case(name, mods, outdir):
     n_items = int((batch["labels"] != -100).sum())
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.999),
                             eps=1e-8, weight_decay=0.0)
-    out = model(**ref_batch, num_items_in_batch=torch.tensor(n_items))
+    keep_mask = None
+    if p_drop > 0.0:
+        # instrumentation, not a modification: record what torch.bernoulli returns inside the reference's forward
+        drawn, real_bernoulli = [], torch.bernoulli
+        torch.bernoulli = lambda *a, **k: (drawn.append(real_bernoulli(*a, **k)), drawn[-1])[1]
+        torch.manual_seed(DROPOUT_SEED)
+        try:
+            out = model(**ref_batch, num_items_in_batch=torch.tensor(n_items))
+        finally:
+            torch.bernoulli = real_bernoulli
+        assert len(drawn) == 1, "the MLP recipe draws exactly one Bernoulli tensor per forward"
+        keep_mask = drawn[0].clone()
+        torch.manual_seed(DROPOUT_SEED)             # the draw is the first consumer of the generator: replayable from the seed alone
+        assert torch.equal(keep_mask, torch.bernoulli(torch.full(keep_mask.shape, 1.0 - p_drop)))
+        assert 0 < int((keep_mask == 0).sum()) < keep_mask.numel() // 2
+        batch["frame_keep_mask"] = keep_mask
+    else:
+        out = model(**ref_batch, num_items_in_batch=torch.tensor(n_items))
     loss = out.loss
     loss.backward()
     # an expert no token selected never enters the graph (moe dispatch loop, projectors.py:328-345): grad None == zero
@@ -215,7 +241,8 @@ def run_case(name, mods, outdir):
     with torch.no_grad():
         enc_out = model.audio_tower(input_features=mel_ref).last_hidden_state
         model.projector.load_state_dict(W["projector"])
-        proj_out = model.projector(enc_out)
+        proj_out = model.projector(enc_out if keep_mask is None else enc_out * keep_mask.unsqueeze(-1))
+        torch.manual_seed(DROPOUT_SEED)     # same draw again (dropout case)
         out_mean = model(**ref_batch)       # per-micro-batch mean path (loss_utils.py:35-36)
 
     # ---- oracle vs reference (sanity; the test suite re-checks from the fixture) ----
@@ -253,6 +280,9 @@ def run_case(name, mods, outdir):
     }
     if hasattr(model.projector, "get_aux_loss"):
         fx["aux_loss"] = np.array(float(model.projector.get_aux_loss()))
+    if keep_mask is not None:
+        fx["frame_keep_mask"] = keep_mask.numpy().astype(np.float32)
+        fx["dropout_p"], fx["dropout_seed"] = np.array(p_drop), np.array(DROPOUT_SEED)
     for k in grads:
         fx["grad_sub." + k] = sub(grads[k], 4096)
         fx["grad_l2." + k] = np.array(float(grads[k].norm()))

@@ -53,9 +53,55 @@ def gradient_gap(mods):
             "grad_rel_err_bf16_vs_fp32": {k: float((g16[k].float() - g32[k]).norm() / g32[k].norm()) for k in g32}}
 
 
+SMALL_CASES = ("small_b2_2s", "small_b3_ragged", "h2048_b2_2s", "small_b2_1s_pad30", "dropout_b2_2s")
+
+
+def small_case_gaps(mods):
+    """The reference's own fp32 and bf16-autocast CE on the small parity cases of tests/golden (same weights, same inputs): the
+    like-for-like target the GPU parity tests assert 1e-3 against (tests/test_path_gpu.py)."""
+    import numpy as np
+    from oracle.make_golden import CASES, DROPOUT_SEED
+    out = {}
+    for name in SMALL_CASES:
+        spec, B, clip_s, pad_s, R, seed = CASES[name]
+        cfg = po.small_config(**{k: v for k, v in spec.items() if not k.startswith("_")})
+        fx = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        W = po.init_weights(cfg, seed=seed)
+        batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s)
+        ref = build_reference_model(cfg, W, mods, "mlp")
+        ref.train()
+        p_drop = float(spec.get("_dropout", 0.0))
+        ref.config.audio_token_dropout = p_drop
+        L = int(batch["sample_lengths"][0])
+        feats = ref.feature_extractor([batch["waveform"][b, :L].numpy() for b in range(B)], sampling_rate=16000,
+                                      padding="max_length" if pad_s == 30.0 else "longest", return_attention_mask=True, return_tensors="pt")
+        rb = dict(input_ids=torch.from_numpy(fx["input_ids"]), attention_mask=torch.from_numpy(fx["attention_mask"]),
+                  labels=torch.from_numpy(fx["labels"]), input_features=feats.input_features, audio_attention_mask=feats.attention_mask,
+                  audio_token_counts=torch.from_numpy(fx["audio_token_counts"]))
+        n_items = int(fx["num_items"])
+        with torch.no_grad():
+            torch.manual_seed(DROPOUT_SEED)
+            fp32 = float(ref(**rb, num_items_in_batch=torch.tensor(n_items)).loss)
+            torch.manual_seed(DROPOUT_SEED)          # fp32 hidden states under autocast too (final LayerNorm): same Bernoulli draw
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                bf16 = float(ref(**rb, num_items_in_batch=torch.tensor(n_items)).loss)
+        assert abs(fp32 - float(fx["loss"])) < 2e-5, (name, fp32, float(fx["loss"]))
+        out[name] = dict(num_items=n_items, ce_loss_reference_fp32=fp32, ce_loss_reference_bf16_autocast=bf16, gap=abs(fp32 - bf16))
+        print(name, out[name], flush=True)
+    return out
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     mods = load_reference()
+    path = os.path.join(ROOT, "tests", "golden", "reference_precision_gap.json")
+    if "--small-only" in sys.argv:       # add / refresh the small cases without redoing the full-size runs
+        with open(path) as f:
+            out = json.load(f)
+        out["small_cases"] = small_case_gaps(mods)
+        with open(path, "w") as f:
+            json.dump(out, f, indent=1)
+        return
     cfg = po.PathConfig(proj_hidden=COMMON["proj_hidden"])
     W = po.init_weights(cfg, seed=COMMON["weights_seed"])
     ref = build_reference_model(cfg, W, mods, "mlp")
@@ -79,7 +125,8 @@ def main():
         print(name, out[name], flush=True)
     out["full_b1_4s_gradients"] = gradient_gap(mods)
     print(out["full_b1_4s_gradients"], flush=True)
-    with open(os.path.join(ROOT, "tests", "golden", "reference_precision_gap.json"), "w") as f:
+    out["small_cases"] = small_case_gaps(mods)
+    with open(path, "w") as f:
         json.dump(out, f, indent=1)
 
 

@@ -607,7 +607,8 @@ def causal_lm_loss(logits: Tensor, labels: Tensor, num_items_in_batch=None) -> T
 def model_forward(W, batch: Dict[str, Tensor], cfg: PathConfig = FULL, num_items_in_batch=None,
                   return_parts: bool = False):
     """batch keys: input_features (B,n_mels,T) [or waveform (B,L)], input_ids, labels,
-    attention_mask (optional), audio_token_counts (optional)."""
+    attention_mask (optional), audio_token_counts (optional), frame_keep_mask (optional, (B,S_e) of {0,1}: the Bernoulli draw of
+    `_maybe_drop_audio_tokens`, tiny_audio/asr_modeling.py:458-479 -- whole encoder frames are zeroed, no rescale)."""
     parts = {}
     if "input_features" in batch:
         mel = batch["input_features"].float()
@@ -617,6 +618,8 @@ def model_forward(W, batch: Dict[str, Tensor], cfg: PathConfig = FULL, num_items
     with torch.no_grad():
         enc = encoder_forward(W["encoder"], mel, cfg)
     parts["encoder_out"] = enc
+    if batch.get("frame_keep_mask") is not None:
+        enc = enc * batch["frame_keep_mask"].to(enc.dtype).unsqueeze(-1)
     kind, aux = projector_kind(W["projector"]), None
     if kind == "qformer":
         audio = qformer_projector_forward(W["projector"], enc, cfg)

@@ -233,6 +233,72 @@ def test_checkpoint_round_trip_reference_layout(tmp_path):
     assert len(trainable) == 4 + 14 and all(n.startswith(("projector.", "language_model.")) for n in trainable)
 
 
+def test_unfrozen_decoder_checkpoint_round_trip(tmp_path):
+    """freeze_language_model=False (configs/experiments/embedded.yaml:19-33): state_dict / model.safetensors carry the fine-tuned decoder
+    as `language_model.*` (asr_modeling.py:409-422) and from_pretrained restores it with load_state_dict(strict=False) like the
+    reference (asr_modeling.py:84-93) -- the reloaded model must NOT run the base decoder under the trained projector."""
+    from safetensors.torch import load_file
+    from tiny_audio_b200.engine import PathDims
+    from tiny_audio_b200.synthetic import build_offline_model
+    dims = PathDims(enc_layers=1, lm_layers=2, vocab=5003, audio_token_id=5002)
+    m = build_offline_model(dims, device="cpu", freeze_language_model=False, seed=11)
+    with torch.no_grad():                                   # "fine-tune": move every trainable tensor away from its seeded init
+        for p in m.language_model.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+        for p in m.projector.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    m.save_pretrained(tmp_path)
+    sd = load_file(str(tmp_path / "model.safetensors"))
+    assert any(k.startswith("language_model.model.layers.1.mlp.down_proj") for k in sd) and "language_model.model.embed_tokens.weight" in sd
+    assert "language_model.lm_head.weight" not in sd        # tied to embed_tokens: written once, as HF's save_pretrained does
+    assert set(m.state_dict()) >= set(sd) and "language_model.lm_head.weight" in m.state_dict()
+    m2 = type(m).from_pretrained(str(tmp_path))             # the towers are re-seeded by the offline loader seams, then overlaid
+    for (k, a), (_, b) in zip(m.language_model.state_dict().items(), m2.language_model.state_dict().items()):
+        assert torch.equal(a, b), k
+    for (k, a), (_, b) in zip(m.projector.state_dict().items(), m2.projector.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert m2.language_model.lm_head.weight.data_ptr() == m2.language_model.model.embed_tokens.weight.data_ptr()
+    assert all(p.requires_grad for p in m2.language_model.parameters())
+    # a frozen-decoder model given the same file must refuse nothing and change nothing outside the projector ... but a checkpoint
+    # with weights the model has no place for is an error, not a silent drop
+    from safetensors.torch import save_file
+    save_file(dict(sd, **{"projector.not_a_weight": torch.zeros(1)}), str(tmp_path / "model.safetensors"))
+    with pytest.raises(RuntimeError, match="no place for"):
+        type(m).from_pretrained(str(tmp_path))
+    (tmp_path / "model.safetensors").unlink()               # reference behaviour: proceeds with a fresh projector; here it says so
+    with pytest.warns(UserWarning, match="no model.safetensors"):
+        type(m).from_pretrained(str(tmp_path))
+
+
+def test_clip_adamw_state_dict_interchanges_with_torch_adamw():
+    """HF Trainer writes optimizer.state_dict() to optimizer.pt and reloads it on resume: ClipAdamW exposes its flat moment buffers in
+    torch.optim.AdamW's layout, so moments and the step count survive the round trip and interchange with the reference's
+    adamw_torch_fused checkpoints.  (Construction / (de)serialisation launch no kernels: runs on the CPU with the loader stubbed.)"""
+    from tiny_audio_b200 import lib, optim
+    real_load, real_req = lib.load, lib.require_cuda
+    lib.load, lib.require_cuda = (lambda: None), (lambda *a: None)
+    try:
+        p1, p2 = torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5))
+        o = optim.ClipAdamW([p1, p2], lr=2e-3)
+        o.m.normal_()
+        o.v.uniform_()
+        o.step_count = 7
+        sd = o.state_dict()
+        ref = torch.optim.AdamW([p1, p2], lr=2e-3)
+        ref.load_state_dict(sd)
+        st = ref.state_dict()["state"]
+        assert float(st[0]["step"]) == 7.0 and torch.equal(st[0]["exp_avg"].reshape(-1), o.m[:12]) and torch.equal(st[1]["exp_avg_sq"], o.v[12:])
+        o2 = optim.ClipAdamW([p1, p2], lr=2e-3)
+        o2.load_state_dict(ref.state_dict())
+        assert o2.step_count == 7 and torch.equal(o2.m, o.m) and torch.equal(o2.v, o.v)
+        assert p1.grad.data_ptr() == o2.flat_grad.data_ptr() and p2.grad.data_ptr() == o2.flat_grad.data_ptr() + 4 * 12
+        # who reduces: explicit.  Default = this optimiser, unless the model is declared DDP-wrapped
+        assert optim.ClipAdamW([p1]).allreduce is True and optim.ClipAdamW([p1], ddp_wrapped=True).allreduce is False
+        assert optim.ClipAdamW([p1], allreduce=False).allreduce is False
+    finally:
+        lib.load, lib.require_cuda = real_load, real_req
+
+
 def test_tiny_audio_shim_resolves_off_path_modules_in_the_reference_checkout(tmp_path):
     """scripts/train.py:44-50 imports tiny_audio.asr_config / asr_modeling (hot path: this repo) AND tiny_audio.augmentation (off the
     path: must stay the reference's own module).  With `PYTHONPATH=<this repo>:<tiny-audio checkout>` the shim package has to serve both."""

@@ -23,11 +23,13 @@ def load_case(name):
     batch["input_ids"] = torch.from_numpy(fx["input_ids"])
     batch["labels"] = torch.from_numpy(fx["labels"])
     batch["attention_mask"] = torch.from_numpy(fx["attention_mask"])
+    if "frame_keep_mask" in fx.files:       # audio_token_dropout case: replay the Bernoulli draw the reference made
+        batch["frame_keep_mask"] = torch.from_numpy(fx["frame_keep_mask"])
     return cfg, fx, W, batch
 
 
 @pytest.mark.parametrize("name", ["small_b2_2s", "small_b3_ragged", "h2048_b2_2s", "small_b2_1s_pad30", "qformer_b2_2s",
-                                  "mosa_b2_2s", "moe_b2_2s"])
+                                  "mosa_b2_2s", "moe_b2_2s", "dropout_b2_2s"])
 def test_oracle_matches_reference_fixture(name):
     torch.set_num_threads(os.cpu_count())
     cfg, fx, W, batch = load_case(name)
@@ -72,6 +74,19 @@ def test_oracle_matches_reference_fixture(name):
         # (zero-gradient tensors move by lr * noise / (|noise| + eps): allow 1e-4 there)
         assert np.abs(sub(res["params"][k]) - fx["new_param_sub." + k]).max() < 1e-4
     assert abs(float(res["grad_norm"]) - float(fx["grad_norm"])) < 1e-3 * float(fx["grad_norm"])
+
+
+def test_audio_token_dropout_mask_is_the_seeded_bernoulli_draw():
+    """a4 (asr_modeling.py:458-479): the keep mask recorded from the unmodified reference (train mode, audio_token_dropout = 0.10) is
+    `torch.bernoulli(full((B, S_e), 1 - p))` drawn first after `torch.manual_seed(seed)` -- the RNG contract the CUDA path keeps
+    (HotPath.apply_frame_dropout draws the same way on its device) -- and it zeroes whole frames without rescaling."""
+    fx = np.load(os.path.join(GOLD, "dropout_b2_2s.npz"))
+    mask = torch.from_numpy(fx["frame_keep_mask"])
+    p = float(fx["dropout_p"])
+    assert abs(p - 0.10) < 1e-12 and set(np.unique(fx["frame_keep_mask"]).tolist()) == {0.0, 1.0}
+    torch.manual_seed(int(fx["dropout_seed"]))
+    assert torch.equal(mask, torch.bernoulli(torch.full(mask.shape, 1.0 - p)))
+    assert tuple(mask.shape) == tuple(fx["enc_shape"][:2]) and 0 < int((mask == 0).sum()) < mask.numel() // 2
 
 
 def test_oracle_unfrozen_lm_gradients_match_reference():
@@ -127,6 +142,28 @@ def test_oracle_greedy_ids_match_reference_generate():
     ids, margins = po.greedy_generate(W, ob, cfg, max_new_tokens=GENERATE_CASE["new_tokens"])
     assert float(margins.min()) > 1e-4          # every step is decisive at fp32 precision
     assert np.array_equal(ids.numpy(), fx["ids"])
+
+
+def test_oracle_reproduces_full_size_reference_generate_ids():
+    """tests/golden/generate_full_b8.npz (full-size model, 8 sequences x 16 free-running tokens from the UNMODIFIED reference's
+    ASRModel.generate, sharpened LM with planted rows: oracle/make_generate_golden.py).  One teacher-forced fp32 oracle forward over
+    prompt + reference ids reproduces every greedy decision (causal: position p's logits are step p's) with the recorded margins."""
+    import torch.nn.functional as F
+    from oracle.make_generate_golden import apply_planted, case_inputs
+    torch.set_num_threads(os.cpu_count())
+    fx = np.load(os.path.join(GOLD, "generate_full_b8.npz"))
+    cfg, W, batch, prompt = case_inputs()
+    assert np.array_equal(prompt.numpy(), fx["prompt"])
+    apply_planted(W, fx["planted_tokens"], fx["planted_rows_bf16"])
+    ids = torch.cat([prompt, torch.from_numpy(fx["ids"])], 1)
+    with torch.no_grad():
+        _, logits = po.model_forward(W, dict(batch, input_ids=ids, labels=None, attention_mask=None), cfg)
+    S0, T = prompt.shape[1], fx["ids"].shape[1]
+    step_logits = logits[:, S0 - 1: S0 - 1 + T]
+    assert np.array_equal(step_logits.argmax(-1).numpy(), fx["ids"])
+    top2 = step_logits.topk(2, -1).values
+    assert np.abs((top2[..., 0] - top2[..., 1]).numpy() - fx["margins"]).max() < 1e-3 and float(fx["margins"].min()) >= 0.5
+    assert bool(fx["ids_bf16_autocast_equal"])          # the reference's own bf16-autocast run produced the same ids
 
 
 def test_oracle_equals_recorded_reference_on_the_bench_parity_sample():

@@ -15,6 +15,17 @@ from tiny_audio_b200.engine import FusedClipAdamW, HotPath, PathDims  # noqa: E4
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
+def reference_band_distance(name, loss):
+    """Distance of a CUDA-path CE loss to the band spanned by the UNMODIFIED reference's own fp32 and bf16-autocast losses on the
+    same weights and inputs (tests/golden/reference_precision_gap.json, oracle/make_reference_precision_gap.py).  The reference
+    trains under bf16 autocast (configs/training/production.yaml:49) and its two precisions differ by up to 4e-3 on these 18-34
+    token samples, so "within 1e-3 of the reference" is asserted against that band (0 inside it)."""
+    import json
+    g = json.load(open(os.path.join(GOLD, "reference_precision_gap.json")))["small_cases"][name]
+    lo, hi = sorted((g["ce_loss_reference_fp32"], g["ce_loss_reference_bf16_autocast"]))
+    return max(lo - loss, loss - hi, 0.0), g
+
+
 def rel(a, b):
     a, b = a.float().cpu(), b.float().cpu()
     return float((a - b).norm() / (b.norm() + 1e-12))
@@ -30,6 +41,17 @@ def build(cfg, seed):
     W = po.init_weights(cfg, seed=seed)
     hp = HotPath(PathDims.from_any(cfg.to_dict()), W["encoder"], W["lm"], "cuda")
     return W, hp
+
+
+_FULL_CACHE = {}
+
+
+def build_full(seed):
+    """Full-size (32 + 28 layers, V = 151 936) seeded weights, generated once per session (1.2 G parameters on the host)."""
+    if seed not in _FULL_CACHE:
+        _FULL_CACHE.clear()
+        _FULL_CACHE[seed] = po.init_weights(po.FULL, seed=seed)
+    return _FULL_CACHE[seed]
 
 
 def run_step(hp, W, batch, n_items, use_wave=True):
@@ -71,7 +93,12 @@ def test_small_configs_vs_oracle_and_golden(cuda, name):
     assert e_mel < 2e-4                     # fp32 DFT vs fp32 FFT on the (x+4)/4 scale
     assert e_enc < 3e-2                     # bf16 encoder (2 layers) vs fp32
     assert e_proj < 3e-2
-    assert d_loss < 5e-3 and d_gold < 5e-3  # CE (mean over labelled tokens), bf16 recipe vs fp32
+    band, g = reference_band_distance(name, float(loss))
+    print(f"   reference fp32 {g['ce_loss_reference_fp32']:.5f}, reference bf16-autocast {g['ce_loss_reference_bf16_autocast']:.5f}: "
+          f"distance to the reference's band {band:.2e} (vs fp32 {d_gold:.2e}, vs bf16-autocast "
+          f"{abs(float(loss) - g['ce_loss_reference_bf16_autocast']):.2e})")
+    assert band < 1e-3                      # north-star bound, against the reference at the precisions it runs in
+    assert d_loss < 5e-3 and d_gold < 5e-3  # and never further than the reference's own bf16-vs-fp32 gap scale from fp32
     for k in grads:
         e = rel(grads[k], res["grads"][k])
         eg = float(np.linalg.norm(sub(grads[k]) - fx["grad_sub." + k]) / (np.linalg.norm(fx["grad_sub." + k]) + 1e-12))
@@ -98,6 +125,54 @@ def test_small_configs_vs_oracle_and_golden(cuda, name):
         big = res["grads"][k].abs() > 1e-3 * res["grads"][k].abs().max()
         agree = float((torch.sign(upd[big]) == torch.sign(ref_upd[big])).float().mean())
         assert agree > 0.98, f"{k}: update sign agreement {agree}"
+
+
+def test_audio_token_dropout_vs_reference_fixture(cuda):
+    """a4, audio_token_dropout = 0.10 (the production value, configs/config.yaml:32; asr_modeling.py:458-479): the CUDA path with the
+    keep mask the unmodified reference drew (tests/golden/dropout_b2_2s.npz) against that reference run and the oracle -- loss,
+    projector gradients, zeroed frames exact; then the RNG contract: without an injected mask the path draws
+    torch.bernoulli(full((B, S_e), 0.9)) from torch's generator, so the same seed reproduces the same step bit for bit."""
+    from oracle.make_golden import CASES
+    spec, B, clip_s, pad_s, R, seed = CASES["dropout_b2_2s"]
+    cfg = po.small_config(**{k: v for k, v in spec.items() if not k.startswith("_")})
+    fx = np.load(os.path.join(GOLD, "dropout_b2_2s.npz"))
+    W, hp = build(cfg, seed)
+    batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R)
+    assert np.array_equal(batch["input_ids"].numpy(), fx["input_ids"])
+    keep = torch.from_numpy(fx["frame_keep_mask"])
+    n_items = int(fx["num_items"])
+
+    def step(**kw):
+        params = {k: v.clone().cuda().contiguous() for k, v in W["projector"].items()}
+        grads = {k: torch.zeros_like(v) for k, v in params.items()}
+        loss, parts = hp.forward_backward(input_ids=batch["input_ids"].cuda(), labels=batch["labels"], proj_params=params,
+                                          waveform=batch["waveform"].cuda(), audio_token_counts=batch["audio_token_counts"].cuda(),
+                                          num_items_in_batch=n_items, grads=grads, return_parts=True, **kw)
+        torch.cuda.synchronize()
+        return float(loss), parts["encoder_out"].clone(), grads
+
+    loss, enc, grads = step(frame_keep_mask=keep)
+    dropped = enc.float().abs().sum(-1).cpu() == 0
+    assert torch.equal(dropped, keep == 0)                                   # exactly the reference's frames are zero
+    res = po.train_step(W, dict(batch, frame_keep_mask=keep), cfg, lr=1e-3, max_grad_norm=1.0, num_items_in_batch=n_items)
+    loss_nodrop, _, _ = step()
+    print(f"[dropout] loss {loss:.5f} oracle {float(res['loss']):.5f} reference {float(fx['loss']):.5f} (without dropout {loss_nodrop:.5f})")
+    assert abs(float(res["loss"]) - float(fx["loss"])) < 2e-5               # oracle == reference on this draw
+    assert abs(loss - float(fx["loss"])) < 5e-3                              # bf16 recipe vs the fp32 reference
+    assert reference_band_distance("dropout_b2_2s", loss)[0] < 1e-3
+    assert abs(loss_nodrop - loss) > 1e-4                                    # the mask matters
+    for k in grads:
+        e = rel(grads[k], res["grads"][k])
+        eg = float(np.linalg.norm(sub(grads[k]) - fx["grad_sub." + k]) / (np.linalg.norm(fx["grad_sub." + k]) + 1e-12))
+        assert e < 6e-2 and eg < 8e-2, (k, e, eg)
+    # RNG contract: seeded draw on the device == what the path uses when no mask is injected
+    torch.manual_seed(99)
+    expect = torch.bernoulli(torch.full(keep.shape, 0.9, device="cuda", dtype=torch.float32))
+    torch.manual_seed(99)
+    l_a, enc_a, g_a = step(frame_keep_prob=0.9)
+    l_b, enc_b, g_b = step(frame_keep_mask=expect)
+    assert torch.equal((enc_a.float().abs().sum(-1) == 0).cpu(), (expect == 0).cpu()) and torch.equal(enc_a, enc_b)
+    assert abs(l_a - l_b) < 1e-6 * abs(l_a)              # CE row sums are fp32 atomics
 
 
 def test_config2_shape_10s_clips_vs_oracle(cuda):
@@ -609,6 +684,123 @@ def test_generate_public_surface_builds_prompt_and_supports_qformer(cuda):
     assert out.shape[0] == 2 and 1 <= out.shape[1] <= 3 and out.dtype == torch.int64
 
 
+def test_forward_surface_logits_text_only_inputs_embeds_and_device_labels(cuda):
+    """SURVEY 8b / asr_modeling.py:481-533: `outputs.logits` (returned when there are no labels, or on request), text-only and
+    `inputs_embeds` forwards through the CUDA decoder, and device-resident labels (ta_label_rows: no labels.cpu()) -- each against
+    the oracle's forward on the same weights."""
+    import torch.nn.functional as F
+    from tiny_audio_b200.synthetic import build_offline_model
+    cfg = po.small_config(enc_layers=1, lm_layers=2)
+    W = po.init_weights(cfg, seed=61, emb_std=0.04)
+    batch = po.synthetic_batch(cfg, 3, 1.0, seed=61, response_len=7)
+    batch["labels"][1, -5:] = -100                                    # ragged label counts
+    n_items = int((batch["labels"] != -100).sum())
+    model = build_offline_model(PathDims.from_any(cfg.to_dict()), device="cuda", enc_state=W["encoder"], lm_state=W["lm"],
+                                proj_state=W["projector"])
+    model.train()
+    hp = model._hot_path()
+    # device-side label bookkeeping == the host's (HF:loss/loss_utils.py:56-59), ascending and exact
+    from tiny_audio_b200.engine import label_rows_and_targets
+    r_h, t_h = label_rows_and_targets(batch["labels"])
+    r_d, t_d, n = hp.label_rows(batch["labels"].cuda())
+    assert n == n_items == r_h.numel() and torch.equal(r_d.cpu(), r_h) and torch.equal(t_d.cpu(), t_h)
+    assert hp.label_rows(torch.full((2, 5), -100).cuda())[2] == 0
+    kw = dict(input_ids=batch["input_ids"].cuda(), input_features=batch["waveform"].cuda(), audio_token_counts=batch["audio_token_counts"].cuda(),
+              attention_mask=batch["attention_mask"].cuda())
+    o_host = model(labels=batch["labels"], num_items_in_batch=n_items, **kw)
+    o_dev = model(labels=batch["labels"].cuda(), num_items_in_batch=torch.tensor(n_items, device="cuda"), **kw)
+    assert o_host.logits is None and o_dev.logits is None              # training call: lm_head on the labelled rows only
+    assert abs(float(o_host.loss) - float(o_dev.loss)) < 1e-6 * abs(float(o_host.loss))
+    o_dev.loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.projector.parameters())
+    # oracle forward
+    with torch.no_grad():
+        loss_o, logits_o, parts = po.model_forward(W, batch, cfg, n_items, return_parts=True)
+
+    def check_logits(got, ref, tag):
+        assert got.dtype == torch.bfloat16 and tuple(got.shape) == tuple(ref.shape), (tag, got.shape, ref.shape)
+        g = got.float().cpu()
+        e = float((g - ref).norm() / ref.norm())
+        top2 = ref.topk(2, -1).values
+        sure = (top2[..., 0] - top2[..., 1]) > 0.25                    # above the bf16 logit noise
+        agree = bool((g.argmax(-1)[sure] == ref.argmax(-1)[sure]).all())
+        print(f"[logits {tag}] rel err {e:.3e}, decisive positions {int(sure.sum())}/{sure.numel()} argmax equal: {agree}")
+        assert e < 3e-2 and agree and int(sure.sum()) > 0
+
+    with torch.no_grad():
+        o_score = model(**kw)                                           # no labels: the reference returns logits, so do we
+    assert o_score.loss is None
+    check_logits(o_score.logits, logits_o, "audio+text, no labels")
+    o_both = model(labels=batch["labels"].cuda(), num_items_in_batch=n_items, return_logits=True, **kw)
+    assert abs(float(o_both.loss) - float(o_host.loss)) < 1e-6 * abs(float(o_host.loss)) and abs(float(o_both.loss) - float(loss_o)) < 5e-3
+    assert torch.equal(o_both.logits, o_score.logits)
+    # inputs_embeds (asr_modeling.py:496-497): the oracle's scattered embeddings in, same logits out
+    with torch.no_grad():
+        o_emb = model(inputs_embeds=parts["inputs_embeds"].cuda())
+    check_logits(o_emb.logits, logits_o, "inputs_embeds")
+    # text-only forward (reference tests/test_asr_modeling.py:213-240)
+    ids = torch.randint(0, cfg.vocab - 2, (2, 9))
+    labels = ids.clone()
+    labels[:, :3] = -100
+    with torch.no_grad():
+        hid = po.lm_forward(W["lm"], F.embedding(ids, W["lm"]["model.embed_tokens.weight"]), cfg)
+        ref_logits = F.linear(hid, W["lm"]["lm_head.weight"])
+        ref_loss = po.causal_lm_loss(ref_logits, labels)
+        o_txt = model(input_ids=ids.cuda(), attention_mask=torch.ones_like(ids).cuda())
+        o_txt_l = model(input_ids=ids.cuda(), labels=labels.cuda())
+    assert o_txt.loss is None and tuple(o_txt.logits.shape) == (2, 9, cfg.vocab)
+    check_logits(o_txt.logits, ref_logits, "text only")
+    assert o_txt_l.logits is None and abs(float(o_txt_l.loss) - float(ref_loss)) < 5e-3
+    with pytest.raises(ValueError):
+        model()
+
+
+def test_generic_projector_routes_decoder_gradients(cuda):
+    """a non-MLP projector (qformer) combined with LoRA adapters or an unfrozen decoder must still hand the decoder's
+    trainable tensors their gradients (before: grad None -> the decoder silently never learned).  Loss and gradients vs the oracle."""
+    from tiny_audio_b200.synthetic import build_offline_model
+    cfg = po.small_config(enc_layers=1, lm_layers=2)
+    W = po.init_weights(cfg, seed=71)
+    W["projector"] = po.init_qformer_weights(cfg, seed=72)
+    W["lora"] = po.init_lora_weights(cfg, 73, rank=8, alpha=32.0, b_std=0.02)
+    batch = po.synthetic_batch(cfg, 2, 2.0, seed=71, response_len=6, projector="qformer")
+    n_items = int((batch["labels"] != -100).sum())
+    dims = PathDims.from_any(cfg.to_dict())
+    model = build_offline_model(dims, device="cuda", enc_state=W["encoder"], lm_state=W["lm"], proj_state=W["projector"],
+                                projector_type="qformer", use_lora=True)
+    ad = model.lora_adapters
+    with torch.no_grad():
+        for t in ad.targets:
+            ad.lora_A[t].copy_(W["lora"]["A"][t])
+            ad.lora_B[t].copy_(W["lora"]["B"][t])
+    model.train()
+    model.projector.eval()                                             # QFormer dropout off (no bit-parity definition)
+    loss = _model_step(model, batch, n_items)
+    res = po.train_step(W, batch, cfg, num_items_in_batch=n_items)
+    assert abs(float(loss) - float(res["loss"])) < 5e-3
+    for t in ad.targets:
+        assert ad.lora_A[t].grad is not None and ad.lora_B[t].grad is not None, t
+        ea, eb = rel(ad.lora_A[t].grad, res["lora_grads"]["A"][t]), rel(ad.lora_B[t].grad, res["lora_grads"]["B"][t])
+        assert ea < 6e-2 and eb < 6e-2, (t, ea, eb)
+    worst = max(rel(p.grad, res["grads"][k]) for k, p in model.projector.named_parameters())
+    print(f"[qformer + lora] loss {float(loss):.5f} oracle {float(res['loss']):.5f}; worst projector grad rel err {worst:.3e}")
+    assert worst < 8e-2
+    del model
+    # unfrozen decoder behind the same projector
+    W2 = {k: v for k, v in W.items() if k != "lora"}
+    m2 = build_offline_model(dims, device="cuda", enc_state=W["encoder"], lm_state=W["lm"], proj_state=W["projector"],
+                             projector_type="qformer", freeze_language_model=False)
+    m2.train()
+    m2.projector.eval()
+    loss2 = _model_step(m2, batch, n_items)
+    res2 = po.train_step(W2, batch, cfg, num_items_in_batch=n_items, train_lm=True)
+    assert abs(float(loss2) - float(res2["loss"])) < 5e-3
+    named = dict(m2.language_model.named_parameters())
+    for k, g in res2["lm_grads"].items():
+        assert named[k].grad is not None, k
+        assert rel(named[k].grad, g) < 8e-2, (k, rel(named[k].grad, g))
+
+
 def test_full_size_model_loss_vs_reference_fixture(cuda):
     """The BASELINE metric's parity half at FULL model size (32-layer GLM-ASR encoder + 28-layer Qwen3-0.6B, vocabulary 151 936):
     CE loss of the bf16 CUDA path against the unmodified fp32 reference (tests/golden/full_b1_4s.npz: 1 x 4 s clip), plus the
@@ -617,7 +809,8 @@ def test_full_size_model_loss_vs_reference_fixture(cuda):
     spec, B, clip_s, pad_s, R, seed = CASES["full_b1_4s"]
     cfg = po.FULL
     fx = np.load(os.path.join(GOLD, "full_b1_4s.npz"))
-    W, hp = build(cfg, seed)
+    W = build_full(seed)
+    hp = HotPath(PathDims.from_any(cfg.to_dict()), W["encoder"], W["lm"], "cuda")
     batch = po.synthetic_batch(cfg, B, clip_s, seed=seed, response_len=R, pad_to_seconds=pad_s)
     batch["input_ids"] = torch.from_numpy(fx["input_ids"])
     batch["labels"] = torch.from_numpy(fx["labels"])
@@ -636,6 +829,53 @@ def test_full_size_model_loss_vs_reference_fixture(cuda):
         eg = float(np.linalg.norm(sub(grads[k]) - ref) / (np.linalg.norm(ref) + 1e-12))
         print(f"   grad {k}: rel vs reference sub-sample {eg:.3e}")
         assert eg < 0.12            # 60 layers of bf16 rounding between the loss and the projector
+
+
+def test_full_size_greedy_ids_equal_reference_generate(cuda):
+    """North star: greedy token ids bit-exact.  FULL model size, free-running, 16 new tokens, B = 8 and B = 1, through the KV-cache
+    decode path AND the cache-free path: `torch.equal` to the ids the UNMODIFIED reference's ASRModel.generate -> HF generate
+    produced on identical weights and inputs (tests/golden/generate_full_b8.npz, oracle/make_generate_golden.py: a sharpened LM
+    with planted tokens, every step's fp32 top-1 margin >= 0.5 -- ten times the bf16 logit noise; the reference's own
+    bf16-autocast run gives the same ids).  All 128 generated ids are distinct and each one is fed back as an input."""
+    from oracle.make_generate_golden import CASE, apply_planted, case_inputs
+    fx = np.load(os.path.join(GOLD, "generate_full_b8.npz"))
+    assert bool(fx["ids_bf16_autocast_equal"]) and float(fx["margins"].min()) >= 0.5
+    cfg = po.FULL
+    _, _, batch, prompt = case_inputs_light()
+    assert np.array_equal(prompt.numpy(), fx["prompt"])
+    W = build_full(CASE["weights_seed"])
+    table = W["lm"]["model.embed_tokens.weight"]
+    saved = table[torch.from_numpy(fx["planted_tokens"])].clone()
+    try:
+        apply_planted(W, fx["planted_tokens"], fx["planted_rows_bf16"])
+        hp = HotPath(PathDims.from_any(cfg.to_dict()), W["encoder"], W["lm"], "cuda")
+    finally:
+        table[torch.from_numpy(fx["planted_tokens"])] = saved        # the cached weights stay pristine for the other tests
+    params = {k: v.clone().cuda().contiguous() for k, v in W["projector"].items()}
+    ref = torch.from_numpy(fx["ids"])
+    T = ref.shape[1]
+    assert T >= 16 and ref.shape[0] == 8 and len(set(ref.reshape(-1).tolist())) == ref.numel()
+    for sel in (slice(0, 8), slice(0, 1), slice(5, 6)):
+        kw = dict(proj_params=params, waveform=batch["waveform"][sel].cuda(), audio_token_counts=batch["audio_token_counts"][sel].cuda())
+        got = hp.greedy_generate(input_ids=prompt[sel].cuda(), max_new_tokens=T, use_cache=True, **kw).cpu()
+        assert torch.equal(got, ref[sel]), (sel, got.tolist(), ref[sel].tolist())
+    got = hp.greedy_generate(input_ids=prompt.cuda(), max_new_tokens=T, use_cache=False, proj_params=params,
+                             waveform=batch["waveform"].cuda(), audio_token_counts=batch["audio_token_counts"].cuda()).cpu()
+    assert torch.equal(got, ref)
+    graph = hp.greedy_generate(input_ids=prompt.cuda(), max_new_tokens=T, use_cache=True, use_graph=True, proj_params=params,
+                               waveform=batch["waveform"].cuda(), audio_token_counts=batch["audio_token_counts"].cuda()).cpu()
+    assert torch.equal(graph, ref)
+
+
+def case_inputs_light():
+    """oracle.make_generate_golden.case_inputs without regenerating the 1.2 G weights (the test takes them from build_full)."""
+    from oracle import make_generate_golden as mg
+    real = po.init_weights
+    po.init_weights = lambda cfg, seed=0, **k: None
+    try:
+        return mg.case_inputs()
+    finally:
+        po.init_weights = real
 
 
 def test_full_size_batch_properties(cuda):

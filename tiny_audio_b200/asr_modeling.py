@@ -42,58 +42,54 @@ def _gather_audio_embeds(audio_embeds: torch.Tensor, token_counts: torch.Tensor)
     return audio_embeds[keep]
 
 
+def _prepare_decoder(model, hot: HotPath, extra) -> str:
+    """Bring the engine's decoder operands in line with the trainable decoder tensors `extra` (the tensors ASRModel._decoder_tensors
+    returned): LoRA -> refresh the rank-padded A / B operands; unfrozen LM -> re-pack the bf16 operands when the optimiser moved the
+    fp32 masters.  Returns the decoder mode: "frozen" | "lora" | "unfrozen"."""
+    adapters = model.lora_adapters
+    if adapters is not None:
+        n = len(extra) // 2
+        names = adapters.targets
+        hot.lm.update_lora({t: a.detach() for t, a in zip(names, extra[:n])}, {t: b.detach() for t, b in zip(names, extra[n:])},
+                           adapters.scaling)
+        return "lora"
+    if len(extra) > 0:
+        model._refresh_packed_lm(hot)
+        return "unfrozen"
+    return "frozen"
+
+
+def _decoder_grads(model, hot: HotPath, mode: str):
+    """Gradients of the trainable decoder tensors, in ASRModel._decoder_tensors order (valid until the next engine call)."""
+    if mode == "lora":
+        adapters = model.lora_adapters
+        ga, gb = hot.lm.lora_grads(adapters.scaling, {t: adapters.rank for t in adapters.targets})
+        return [ga[t].clone() for t in adapters.targets] + [gb[t].clone() for t in adapters.targets]
+    hg = hot.lm.hf_grads()          # views of the engine's flat buffer; scaled (= copied) in backward
+    return [hg[n] for n, _ in model.language_model.named_parameters()]
+
+
 class _FusedPathLoss(torch.autograd.Function):
-    """loss = CE(Qwen3(scatter(projector(encoder(audio))))) with d(loss)/d(projector params) -- and d(loss)/d(LoRA A, B) when
-    adapters are attached -- computed in the same pass; backward only rescales the stored gradients by the incoming scalar.
-    Tensor arguments: the 4 projector parameters, then EITHER the stacked lora_A tensors followed by the stacked lora_B tensors
-    OR (freeze_language_model=False) every Qwen3 parameter in `language_model.named_parameters()` order, whose gradients the
-    engine produces as well."""
+    """loss = CE(Qwen3(scatter(projector(encoder(audio))))) with d(loss)/d(projector params) -- and d(loss)/d(trainable decoder
+    tensors) -- computed in the same pass; backward only rescales the stored gradients by the incoming scalar.
+    Tensor arguments: the 4 projector parameters, then ASRModel._decoder_tensors(): EITHER the stacked lora_A tensors followed by
+    the stacked lora_B tensors OR (freeze_language_model=False) every Qwen3 parameter in `language_model.named_parameters()`
+    order, OR nothing (frozen decoder)."""
 
     @staticmethod
-    def forward(ctx, model, call, w1, n1, w2, n2, *lora_tensors):
+    def forward(ctx, model, call, w1, n1, w2, n2, *extra):
         hot: HotPath = model._hot_path()
         params = {k: p.detach().float().contiguous() for k, p in zip(_PROJ_KEYS, (w1, n1, w2, n2))}
         need = any(ctx.needs_input_grad[2:6])
         grads = {k: torch.empty_like(v) for k, v in params.items()} if need else None
-        adapters = getattr(model, "lora_adapters", None)
-        train_lm = adapters is None and len(lora_tensors) > 0          # the extra tensors are the decoder's own parameters
-        if train_lm:
-            return _FusedPathLoss._forward_unfrozen(ctx, model, hot, call, params, grads, lora_tensors, (w1, n1, w2, n2))
-        n_l = len(lora_tensors) // 2
-        need_lora = adapters is not None and any(ctx.needs_input_grad[6:])
-        if adapters is not None:
-            names = adapters.targets
-            hot.lm.update_lora({t: a.detach() for t, a in zip(names, lora_tensors[:n_l])},
-                               {t: b.detach() for t, b in zip(names, lora_tensors[n_l:])}, adapters.scaling)
-        loss, _ = hot.forward_backward(proj_params=params, grads=grads, lm_backward=need_lora, **call)
+        mode = _prepare_decoder(model, hot, extra)
+        need_dec = mode != "frozen" and any(ctx.needs_input_grad[6:])
+        loss, _ = hot.forward_backward(proj_params=params, grads=grads, lm_backward=need_dec, train_lm=(need_dec and mode == "unfrozen"),
+                                       **call)
         ctx.grads = grads
         ctx.dtypes = (w1.dtype, n1.dtype, w2.dtype, n2.dtype)
-        ctx.lora_grads = None
-        if need_lora:
-            ga, gb = hot.lm.lora_grads(adapters.scaling, {t: adapters.rank for t in adapters.targets})
-            ctx.lora_grads = [ga[t].clone() for t in names] + [gb[t].clone() for t in names]
-            ctx.lora_dtypes = [t.dtype for t in lora_tensors]
-        ctx.n_lora = len(lora_tensors)
-        return loss.reshape(())
-
-    @staticmethod
-    def _forward_unfrozen(ctx, model, hot, call, params, grads, lm_tensors, proj_tensors):
-        names = [n for n, _ in model.language_model.named_parameters()]
-        assert len(names) == len(lm_tensors)
-        version = sum(int(t._version) for t in lm_tensors)
-        if getattr(model, "_lm_pack_version", None) != version:        # the optimiser moved the masters: refresh the bf16 operands
-            hot.lm.refresh_from({n: t.detach() for n, t in zip(names, lm_tensors)})
-            model._lm_pack_version = version
-        need_lm = any(ctx.needs_input_grad[6:])
-        loss, _ = hot.forward_backward(proj_params=params, grads=grads, train_lm=need_lm, **call)
-        ctx.grads = grads
-        ctx.dtypes = tuple(t.dtype for t in proj_tensors)
-        ctx.lora_grads = None
-        if need_lm:
-            hg = hot.lm.hf_grads()
-            ctx.lora_grads = [hg[n] for n in names]       # views of the engine's flat buffer; scaled (= copied) in backward
-            ctx.lora_dtypes = [t.dtype for t in lm_tensors]
-        ctx.n_lora = len(lm_tensors)
+        ctx.dec_grads = _decoder_grads(model, hot, mode) if need_dec else None
+        ctx.dec_dtypes = [t.dtype for t in extra]
         return loss.reshape(())
 
     @staticmethod
@@ -101,31 +97,45 @@ class _FusedPathLoss(torch.autograd.Function):
         proj = (None,) * 4
         if ctx.grads is not None:
             proj = tuple((ctx.grads[k] * gout).to(dt) for k, dt in zip(_PROJ_KEYS, ctx.dtypes))
-        lora = (None,) * ctx.n_lora
-        if ctx.lora_grads is not None:
-            lora = tuple((g * gout).to(dt) for g, dt in zip(ctx.lora_grads, ctx.lora_dtypes))
-        return (None, None) + proj + lora
+        dec = (None,) * len(ctx.dec_dtypes)
+        if ctx.dec_grads is not None:
+            dec = tuple((g * gout).to(dt) for g, dt in zip(ctx.dec_grads, ctx.dec_dtypes))
+        return (None, None) + proj + dec
 
 
 class _LmLossFn(torch.autograd.Function):
-    """loss(audio_embeds) for any projector: <audio> scatter -> Qwen3 -> CE with d(loss)/d(audio_embeds) computed in the same
-    pass by the CUDA engine; autograd then continues into the projector that produced `audio_embeds`."""
+    """loss(audio_embeds) for any projector: <audio> scatter -> Qwen3 -> CE with d(loss)/d(audio_embeds) -- and d(loss)/d(trainable
+    decoder tensors: LoRA A / B or the unfrozen Qwen3 parameters) -- computed in the same pass by the CUDA engine; autograd then
+    continues into the projector that produced `audio_embeds`.  `audio` is None for a batch without audio (text-only forward, or
+    `inputs_embeds` given in `call`)."""
 
     @staticmethod
-    def forward(ctx, audio, model, call):
+    def forward(ctx, model, call, audio, *extra):
         hot: HotPath = model._hot_path()
-        B, n_a, D = audio.shape
-        flat = audio.detach().float().contiguous().view(B * n_a, D)
-        loss, d_audio = hot.lm_loss_and_audio_grad(audio=flat, n_a=n_a, with_backward=ctx.needs_input_grad[0], **call)
-        ctx.d_audio = d_audio.view(B, n_a, D).clone() if d_audio is not None else None
-        ctx.dtype = audio.dtype
+        mode = _prepare_decoder(model, hot, extra)
+        need_audio = audio is not None and ctx.needs_input_grad[2]
+        need_dec = mode != "frozen" and any(ctx.needs_input_grad[3:])
+        kw = dict(with_backward=need_audio, lm_backward=need_dec, train_lm=(need_dec and mode == "unfrozen"))
+        if audio is not None:
+            B, n_a, D = audio.shape
+            flat = audio.detach().float().contiguous().view(B * n_a, D)
+            loss, d_audio = hot.lm_loss_and_audio_grad(audio=flat, n_a=n_a, **kw, **call)
+            ctx.d_audio = d_audio.view(B, n_a, D).clone() if d_audio is not None else None
+            ctx.dtype = audio.dtype
+        else:
+            loss, _ = hot.lm_loss_and_audio_grad(audio=None, n_a=0, **kw, **call)
+            ctx.d_audio = None
+        ctx.dec_grads = _decoder_grads(model, hot, mode) if need_dec else None
+        ctx.dec_dtypes = [t.dtype for t in extra]
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, gout):
-        if ctx.d_audio is None:
-            return None, None, None
-        return (ctx.d_audio * gout).to(ctx.dtype), None, None
+        d_audio = (ctx.d_audio * gout).to(ctx.dtype) if ctx.d_audio is not None else None
+        dec = (None,) * len(ctx.dec_dtypes)
+        if ctx.dec_grads is not None:
+            dec = tuple((g * gout).to(dt) for g, dt in zip(ctx.dec_grads, ctx.dec_dtypes))
+        return (None, None, d_audio) + dec
 
 
 class ASRModel(PreTrainedModel, GenerationMixin):
@@ -322,17 +332,50 @@ class ASRModel(PreTrainedModel, GenerationMixin):
             lm_rope_theta=float(rope_t.get("rope_theta", getattr(tc, "rope_theta", 1e6))), lm_eps=tc.rms_norm_eps,
             vocab=emb.shape[0], audio_token_id=int(self.audio_token_id))
 
+    def _frozen_versions(self) -> int:
+        """Sum of the in-place version counters of the frozen towers' tensors: an in-place weight load (load_state_dict, a
+        copy_ into a parameter) after the operands were packed must not go unnoticed."""
+        ts = self.__dict__.get("_frozen_tensors")
+        if ts is None:
+            # parameters only: buffers (rotary inv_freq) are not used by the engine, and a DDP wrapper re-broadcasts them every step
+            ts = list(self.audio_tower.parameters())
+            if getattr(self.config, "freeze_language_model", True):
+                ts += [p for n, p in self.language_model.named_parameters() if not n.startswith("lora_adapters.")]
+            self.__dict__["_frozen_tensors"] = ts
+        return sum(int(t._version) for t in ts)
+
     def _hot_path(self) -> HotPath:
         dev = next(self.projector.parameters()).device
         if dev.type != "cuda":
             raise L.TinyAudioB200Error("ASRModel.forward needs the model on a CUDA device (no CPU fallback)")
-        key = (dev.index, self.language_model.get_input_embeddings().weight.data_ptr())
+        emb = self.language_model.get_input_embeddings().weight
+        key = (dev.index, emb.data_ptr(), self._frozen_versions())
         if self._hot is None or self._hot_key != key:
+            self.__dict__.pop("_frozen_tensors", None)
             with torch.no_grad():
                 lm_sd = {k: v for k, v in self.language_model.state_dict().items() if not k.startswith("lora_adapters.")}
                 self._hot = HotPath(self.path_dims(), self.audio_tower.state_dict(), lm_sd, dev, lora=self.lora_adapters is not None)
-            self._hot_key = key
+            self._hot_key = (dev.index, emb.data_ptr(), self._frozen_versions())
+            self._lm_pack_version = None
         return self._hot
+
+    def _decoder_tensors(self):
+        """The decoder's trainable tensors the CUDA engine produces gradients for: stacked LoRA A then B tensors, or every Qwen3
+        parameter when the decoder is unfrozen, or nothing."""
+        if self.lora_adapters is not None:
+            la, lb = self.lora_adapters.tensors()
+            return tuple(la.values()) + tuple(lb.values())
+        if not getattr(self.config, "freeze_language_model", True):
+            return tuple(p for _, p in self.language_model.named_parameters())
+        return ()
+
+    def _refresh_packed_lm(self, hot: HotPath) -> None:
+        """Unfrozen decoder: re-pack the engine's bf16 operands when the fp32 masters moved (optimiser step, in-place load)."""
+        named = list(self.language_model.named_parameters())
+        version = sum(int(t._version) for _, t in named)
+        if getattr(self, "_lm_pack_version", None) != version:
+            hot.lm.refresh_from({n: t.detach() for n, t in named})
+            self._lm_pack_version = version
 
     def _encode_audio(self, audio_features: torch.Tensor, expected_token_counts: torch.Tensor) -> torch.Tensor:
         """Reference signature (asr_modeling.py:434-456): packed audio embeddings (sum(counts), llm_dim)."""
@@ -361,55 +404,83 @@ class ASRModel(PreTrainedModel, GenerationMixin):
                 labels: Optional[torch.Tensor] = None, use_cache: Optional[bool] = None,
                 cache_position: Optional[torch.Tensor] = None, audio_token_counts: Optional[torch.Tensor] = None,
                 **kwargs) -> CausalLMOutputWithPast:
-        """Training / scoring forward.  `input_features` is either the reference's (B, n_mels, T) log-mel tensor or,
-        on the fast path, the zero-padded 16 kHz waveform (B, L) -- the log-mel then runs on the GPU (ta_logmel_fwd).
-        `labels` may live on the host (no device->host sync) or on the device (one sync to build the row list)."""
-        if input_ids is None or input_features is None:
-            raise NotImplementedError("the B200 hot path covers audio+text batches (input_ids and input_features); "
-                                      "text-only batches are outside the hot path; cached decoding goes through generate()")
-        if past_key_values is not None or inputs_embeds is not None:
-            raise NotImplementedError("past_key_values / inputs_embeds are not supported on the training hot path")
+        """Training / scoring forward (reference: asr_modeling.py:481-533).
+
+        `input_features` is either the reference's (B, n_mels, T) log-mel tensor or, on the fast path, the zero-padded 16 kHz
+        waveform (B, L) -- the log-mel then runs on the GPU (ta_logmel_fwd).  Without `input_features` the batch is text-only
+        (or `inputs_embeds`) and only the CUDA decoder runs.  `labels` may live on the host or on the device.
+
+        `outputs.logits`: the reference always returns the decoder's logits for every position.  Here they are produced when
+        there are no labels (scoring / text-only calls), or on request (`return_logits=True`, or `config.return_logits`); a
+        training call with labels returns `logits=None` by default, because the fused path evaluates the lm_head only on the
+        labelled rows (that is what keeps 9 GB of logits out of HBM).  Logits are bf16 [B, S, vocab], the dtype the reference
+        produces under its bf16-autocast recipe.
+
+        `attention_mask`: right padding (what the tokenizer this model configures produces, padding_side = "right") needs no
+        mask under causal attention -- padded positions only influence themselves and carry label -100.  Left-padded batches
+        are served by generate()."""
+        if past_key_values is not None:
+            raise NotImplementedError("past_key_values: cached decoding goes through ASRModel.generate() on the B200 path")
+        if input_ids is None and inputs_embeds is None:
+            raise ValueError("You must specify exactly one of input_ids or inputs_embeds")
         hot = self._hot_path()
         dev = hot.device
-        feats = input_features.to(dev, non_blocking=True)
-        call = dict(input_ids=input_ids.to(dev, non_blocking=True),
-                    labels_cpu=(labels.cpu() if labels is not None else None),
-                    audio_token_counts=(audio_token_counts.to(dev, non_blocking=True) if audio_token_counts is not None else None))
-        if feats.dim() == 2:
-            call["waveform"] = feats.float().contiguous()
-        else:
-            call["input_features"] = feats
+        return_logits = kwargs.pop("return_logits", None)
+        if return_logits is None:
+            return_logits = bool(getattr(self.config, "return_logits", False)) or labels is None
         nib = kwargs.get("num_items_in_batch")
+        call = dict(labels=labels, want_hidden=bool(return_logits))
         if nib is not None:
             call["num_items_in_batch"] = float(nib)
-        p = float(getattr(self.config, "audio_token_dropout", 0.0))
-        if self.training and p > 0.0:
-            call["frame_keep_prob"] = 1.0 - p
-        pr = self.projector
-        from .projectors import MLPAudioProjector
-        if isinstance(pr, MLPAudioProjector):
-            # fully fused path: projector forward/backward run inside the CUDA engine together with the towers
-            lora_t = ()
-            if self.lora_adapters is not None:
-                la, lb = self.lora_adapters.tensors()
-                lora_t = tuple(la.values()) + tuple(lb.values())
-            elif not getattr(self.config, "freeze_language_model", True):
-                lora_t = tuple(p for _, p in self.language_model.named_parameters())
-            loss = _FusedPathLoss.apply(self, call, pr.linear_1.weight, pr.norm.weight, pr.linear_2.weight, pr.norm_2.weight, *lora_t)
+        extra = self._decoder_tensors()
+        with_audio = input_features is not None and input_ids is not None and inputs_embeds is None
+        if labels is None and torch.is_grad_enabled():      # nothing to differentiate: a scoring call must not run the backward
+            with torch.no_grad():
+                return self.forward(input_ids=input_ids, input_features=input_features, audio_attention_mask=audio_attention_mask,
+                                    attention_mask=attention_mask, position_ids=position_ids, inputs_embeds=inputs_embeds,
+                                    audio_token_counts=audio_token_counts, return_logits=return_logits, **kwargs)
+        if not with_audio:
+            # text-only / inputs_embeds forward (asr_modeling.py:496-497, 517-526): the CUDA decoder alone
+            if inputs_embeds is not None:
+                call["inputs_embeds"] = inputs_embeds
+                B, S = int(inputs_embeds.shape[0]), int(inputs_embeds.shape[1])
+            else:
+                B, S = input_ids.shape
+            if input_ids is not None:
+                call["input_ids"] = input_ids.to(dev, non_blocking=True)
+            loss = _LmLossFn.apply(self, call, None, *extra)
         else:
-            # generic projector (qformer / mosa / moe): frozen encoder -> projector module (autograd) -> CUDA decoder + CE with
-            # d(loss)/d(audio embeddings) handed back to autograd
-            enc = hot.encode_audio(waveform=call.pop("waveform", None), input_features=call.pop("input_features", None),
-                                   frame_keep_prob=call.pop("frame_keep_prob", None)).clone()
-            audio = pr(enc)
-            loss = _LmLossFn.apply(audio.float(), self, call)
-            if labels is not None and hasattr(pr, "get_aux_loss"):       # MoE load-balance + z-loss (asr_modeling.py:528-531)
-                aux = pr.get_aux_loss()
-                if aux is not None and aux.numel() > 0:
-                    loss = loss + aux.to(loss.device)
+            B, S = input_ids.shape
+            feats = input_features.to(dev, non_blocking=True)
+            call.update(input_ids=input_ids.to(dev, non_blocking=True),
+                        audio_token_counts=(audio_token_counts.to(dev, non_blocking=True) if audio_token_counts is not None else None))
+            audio_kw = dict(waveform=feats.float().contiguous()) if feats.dim() == 2 else dict(input_features=feats)
+            p = float(getattr(self.config, "audio_token_dropout", 0.0))
+            if self.training and p > 0.0:
+                audio_kw["frame_keep_prob"] = 1.0 - p
+            keep_mask = kwargs.pop("audio_frame_keep_mask", None)     # parity hook: replay a given Bernoulli draw (tests)
+            if keep_mask is not None:
+                audio_kw["frame_keep_mask"] = keep_mask
+            pr = self.projector
+            from .projectors import MLPAudioProjector
+            if isinstance(pr, MLPAudioProjector):
+                # fully fused path: projector forward/backward run inside the CUDA engine together with the towers
+                call.update(audio_kw)
+                loss = _FusedPathLoss.apply(self, call, pr.linear_1.weight, pr.norm.weight, pr.linear_2.weight, pr.norm_2.weight, *extra)
+            else:
+                # generic projector (qformer / mosa / moe): frozen encoder -> projector module (autograd) -> CUDA decoder + CE with
+                # d(loss)/d(audio embeddings) handed back to autograd
+                enc = hot.encode_audio(**audio_kw).clone()
+                audio = pr(enc)
+                loss = _LmLossFn.apply(self, call, audio.float(), *extra)
+                if labels is not None and hasattr(pr, "get_aux_loss"):       # MoE load-balance + z-loss (asr_modeling.py:528-531)
+                    aux = pr.get_aux_loss()
+                    if aux is not None and aux.numel() > 0:
+                        loss = loss + aux.to(loss.device)
+        logits = hot.logits_all(B, S) if return_logits else None     # from the final hidden states the engine kept (want_hidden)
         if labels is None:
             loss = None
-        return CausalLMOutputWithPast(loss=loss, logits=None)
+        return CausalLMOutputWithPast(loss=loss, logits=logits)
 
     @torch.no_grad()
     def generate(self, input_ids: Optional[torch.Tensor] = None, input_features: Optional[torch.Tensor] = None,
@@ -470,10 +541,7 @@ class ASRModel(PreTrainedModel, GenerationMixin):
             kw = dict(audio_embeds=pr(hot.encode_audio(**kw).clone()).float())
         gc = self.generation_config
         eos = gc.eos_token_id if isinstance(gc.eos_token_id, (list, tuple)) else [gc.eos_token_id]
-        adapters = getattr(self, "lora_adapters", None)
-        if adapters is not None:      # refresh the engine's adapter operands from the current parameters
-            a, b = adapters.tensors()
-            hot.lm.update_lora({t: v.detach() for t, v in a.items()}, {t: v.detach() for t, v in b.items()}, adapters.scaling)
+        _prepare_decoder(self, hot, self._decoder_tensors())      # current LoRA operands / re-packed decoder after optimiser steps
         use_cache = kwargs.get("use_cache")
         kw["use_cache"] = bool(getattr(self.config, "use_cache", True) if use_cache is None else use_cache)
         return hot.greedy_generate(input_ids=input_ids, proj_params=params, audio_token_counts=audio_token_counts,
@@ -500,8 +568,14 @@ class ASRModel(PreTrainedModel, GenerationMixin):
             self.config.save_pretrained(out)
         except OSError:      # offline: the diff against a default ASRConfig() needs the hub (tower configs) -- write the full dict
             self.config.to_json_file(str(out / "config.json"), use_diff=False)
-        save_file({k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}, str(out / "model.safetensors"),
-                  metadata={"format": "pt"})
+        tensors, seen = {}, {}
+        for k, v in self.state_dict().items():          # tied tensors (lm_head / embed_tokens) are written once, as HF's save_pretrained does
+            key = (v.data_ptr(), tuple(v.shape), tuple(v.stride()))
+            if key in seen and v.numel() > 0:
+                continue
+            seen[key] = k
+            tensors[k] = v.detach().cpu().contiguous().clone()
+        save_file(tensors, str(out / "model.safetensors"), metadata={"format": "pt"})
         for obj in (getattr(self, "tokenizer", None), getattr(self, "feature_extractor", None)):
             if obj is not None and hasattr(obj, "save_pretrained"):
                 obj.save_pretrained(out)
@@ -523,32 +597,58 @@ class ASRModel(PreTrainedModel, GenerationMixin):
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, *args, **kwargs):
-        """Rebuild from a checkpoint directory written by this class or by the reference (asr_modeling.py:59-131): towers come
-        from the loader seams (config.audio_model_id / text_model_id), `model.safetensors` is overlaid non-strictly
-        (projector weights), then `adapter_model.safetensors` when config.use_lora and the adapter files exist."""
+        """Rebuild from a checkpoint written by this class or by the reference (asr_modeling.py:59-131): towers come from the
+        loader seams (config.audio_model_id / text_model_id), then `model.safetensors` -- resolved like the reference does, through
+        transformers' `cached_file` (local directory or hub repo id, `subfolder` / `revision` honoured) -- is overlaid with
+        `load_state_dict(strict=False)`: the projector, and the fine-tuned decoder (`language_model.*`) when the checkpoint was
+        trained with freeze_language_model=False.  With config.use_lora the adapters are attached afterwards and
+        `adapter_model.safetensors` is loaded when `adapter_config.json` exists (fresh adapters otherwise)."""
         from safetensors.torch import load_file
+        from transformers.utils.hub import cached_file
         config = kwargs.pop("config", None)
-        path = Path(pretrained_model_name_or_path)
+        name = str(pretrained_model_name_or_path)
         if config is None:
-            config = ASRConfig.from_pretrained(str(path))
+            config = ASRConfig.from_pretrained(name, **kwargs)
+        cache_kwargs = {k: kwargs[k] for k in ("subfolder", "revision") if kwargs.get(k)}
+
+        def resolve(fname):
+            return cached_file(name, fname, _raise_exceptions_for_missing_entries=False, **cache_kwargs)
+
         cls._is_loading_from_pretrained = True
         try:
             model = cls(config)
-            wfile = path / "model.safetensors"
-            if wfile.exists():
-                sd = load_file(str(wfile))
-                proj = {k[len("projector."):]: v for k, v in sd.items() if k.startswith("projector.")}
-                missing, unexpected = model.projector.load_state_dict(proj, strict=False)
-                if missing:
-                    raise RuntimeError(f"checkpoint {wfile} lacks projector weights {missing}")
+            wfile = resolve("model.safetensors")
+            if wfile is not None:
+                sd = load_file(wfile)
+                result = model.load_state_dict(sd, strict=False)
+                lost = [k for k in result.unexpected_keys]
+                if lost:
+                    raise RuntimeError(f"checkpoint {wfile} holds weights this model has no place for: {lost[:8]}")
+                want = [f"projector.{k}" for k in model.projector.state_dict()]
+                absent = [k for k in want if k not in sd]
+                if absent:
+                    raise RuntimeError(f"checkpoint {wfile} lacks projector weights {absent[:8]}")
+                model._hot = None                   # packed operands (if any) are stale now
+                model._lm_pack_version = None
+            else:       # the reference proceeds silently with a freshly initialised projector; say so
+                import warnings
+                warnings.warn(f"{name}: no model.safetensors found -- the projector keeps its random initialisation", stacklevel=2)
             if getattr(config, "use_lora", False):       # adapters are attached after the base weights, as in the reference
                 model._setup_lora(config)
-                afile = path / "adapter_model.safetensors"
-                if afile.exists() and (path / "adapter_config.json").exists():
-                    model.lora_adapters.load_peft_state_dict(load_file(str(afile)))
+                if resolve("adapter_config.json") is not None:
+                    afile = resolve("adapter_model.safetensors")
+                    if afile is None:
+                        raise RuntimeError(f"{name}: adapter_config.json without adapter_model.safetensors")
+                    model.lora_adapters.load_peft_state_dict(load_file(afile))
             return model
         finally:
             cls._is_loading_from_pretrained = False
+
+    def push_to_hub(self, repo_id: str, **kwargs):
+        """Reference behaviour (asr_modeling.py:854-865): remember the repo id so that save_pretrained writes it into
+        adapter_config.json (`base_model_name_or_path`), then defer to the stock uploader."""
+        self.config.pretrained_model_path = repo_id
+        return super().push_to_hub(repo_id, **kwargs)
 
     def load_projector(self, path: str):
         from safetensors.torch import load_file

@@ -663,6 +663,64 @@ __global__ void frame_stack_kernel(const bf16* __restrict__ x, bf16* __restrict_
 // =============================================================================================================
 // global-norm clip + AdamW (torch.optim.AdamW semantics; clip_grad_norm_ with error_if_nonfinite=False)
 // =============================================================================================================
+// audio-token dropout (tiny_audio/asr_modeling.py:458-479): whole encoder frames are zeroed by a {0,1} keep mask, no rescale.
+// x bf16 [rows, D] in place, keep fp32 [rows] (the Bernoulli draw itself comes from torch's generator, as in the reference)
+__global__ void frame_keep_mask_kernel(bf16* __restrict__ x, const float* __restrict__ keep, long long rows, int D) {
+    const int vecs = D / 8;
+    const long long total = rows * vecs;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / vecs;
+        if (keep[r] == 0.0f) *reinterpret_cast<uint4*>(x + r * D + (i % vecs) * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// Label bookkeeping of the causal-LM loss (HF:loss/loss_utils.py:56-59) on the device: position p = (b, s) predicts labels[b, s + 1];
+// the flat indices p of the non-ignored (!= -100) positions are compacted in ascending order into rows[], their targets into
+// targets[], and the count goes to *count.  One block (B * S is a few 10^4): ordered, deterministic.
+__global__ void __launch_bounds__(1024)
+label_rows_kernel(const long long* __restrict__ labels, int B, int S, int* __restrict__ rows, int* __restrict__ targets,
+                  int* __restrict__ count) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    const int total = B * S;
+    for (int base = 0; base < total; base += 1024) {
+        const int p = base + tid;
+        long long tgt = -100;
+        if (p < total && (p % S) != S - 1) tgt = labels[p + 1];
+        const int flag = tgt != -100 ? 1 : 0;
+        int incl = flag;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) s_warp[wp] = incl;
+        __syncthreads();
+        if (wp == 0) {
+            int v = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += n;
+            }
+            s_warp[lane] = v;
+        }
+        __syncthreads();
+        if (flag) {
+            const int rank = s_carry + (wp ? s_warp[wp - 1] : 0) + incl - 1;
+            rows[rank] = p;
+            targets[rank] = (int)tgt;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry += s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) *count = s_carry;
+}
+
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
     __shared__ float red[40];
     float s = 0.f;
@@ -941,6 +999,25 @@ TA_API int ta_cast_f32_bf16(const float* in, void* out, long long n, void* strea
 }
 TA_API int ta_frame_stack(const void* x, void* out, int B, int S, int n, int k, int D, void* stream) {
     return k_frame_stack((const bf16*)x, (bf16*)out, B, S, n, k, D, ST(stream));
+}
+
+// encoder frames [rows, D] bf16 *= keep[rows] in {0, 1}  (audio_token_dropout, asr_modeling.py:458-479)
+TA_API int ta_frame_keep_mask(void* x, const float* keep, long long rows, int D, void* stream) {
+    TA_REQUIRE(x && keep, "ta_frame_keep_mask: null pointer");
+    TA_REQUIRE(D % 8 == 0, "ta_frame_keep_mask: D=%d must be a multiple of 8", D);
+    if (rows == 0) return 0;
+    frame_keep_mask_kernel<<<grid_for(rows * (D / 8), 256), 256, 0, ST(stream)>>>((bf16*)x, keep, rows, D);
+    TA_LAUNCH_CHECK();
+    return 0;
+}
+
+// labels int64 [B, S] (device) -> ascending flat positions p with labels[p + 1] != -100 (same row), their targets, and the count
+TA_API int ta_label_rows(const long long* labels, int B, int S, int* rows, int* targets, int* count, void* stream) {
+    TA_REQUIRE(labels && rows && targets && count, "ta_label_rows: null pointer");
+    TA_REQUIRE(B >= 0 && S >= 1 && (long long)B * S < (1LL << 31), "ta_label_rows: bad shape B=%d S=%d", B, S);
+    label_rows_kernel<<<1, 1024, 0, ST(stream)>>>(labels, B, S, rows, targets, count);
+    TA_LAUNCH_CHECK();
+    return 0;
 }
 
 // grads -> global 2-norm^2 accumulated into *gnorm_sq (caller zeroes it once per step, calls this per tensor)

@@ -151,8 +151,10 @@ class PackedLM:
         emb = sd["model.embed_tokens.weight"]
         assert emb.shape[0] == V, f"embedding rows {emb.shape[0]} != vocab {V}"
         self.embed_f32 = dev(emb, F32)
+        head = sd.get("lm_head.weight", emb)         # Qwen3-0.6B ties lm_head to embed_tokens; an untied head is packed on its own
+        self.tied_head = head.data_ptr() == emb.data_ptr() or (head.shape == emb.shape and bool(torch.equal(head, emb)))
         eb = torch.zeros(self.vocab_pad, D, dtype=BF16, device=device)
-        eb[:V] = self.embed_f32.to(BF16)            # tied lm_head (autocast casts the fp32 table to bf16)
+        eb[:V] = (self.embed_f32 if self.tied_head else head.detach().to(device=device, dtype=F32)).to(BF16)   # autocast casts the fp32 table to bf16
         self.embed_bf16 = eb
         self.embed_bf16_t = eb.t().contiguous()
         self.final_norm_w = dev(sd["model.norm.weight"], F32)
@@ -225,6 +227,8 @@ class PackedLM:
         if getattr(self, "wgrad_flat", None) is not None:
             return
         assert self.lora_pad == 0, "LoRA adapters and an unfrozen LM are mutually exclusive"
+        if not self.tied_head:
+            raise L.TinyAudioB200Error("unfrozen decoder with an untied lm_head is not supported (Qwen3-0.6B ties it to embed_tokens)")
         d = self.dims
         Lyr, D, F = d.lm_layers, d.lm_dim, d.lm_ffn
         shapes = {"qkv": (Lyr, self.QKV, D), "o": (Lyr, D, self.QD), "gu": (Lyr, 2 * F, D), "d": (Lyr, D, F), "ln1": (Lyr, D),
@@ -399,6 +403,40 @@ def label_rows_and_targets(labels_cpu: torch.Tensor):
 class HotPath:
     """One GPU's replica of the frozen towers + the per-step driver."""
 
+    def label_rows(self, labels: Optional[torch.Tensor]):
+        """(rows int32 [n], targets int32 [n], n) of the positions that carry a label after the shift-by-one
+        (HF:loss/loss_utils.py:56-59).  Host labels: built on the host, copied asynchronously (no device sync).  Device labels
+        (what HF Trainer hands over): compacted on the device by ta_label_rows; only the 4-byte count is read back (it sizes
+        the lm_head product) -- no labels.cpu(), no host-side nonzero()."""
+        if labels is None:
+            e = torch.empty(0, dtype=torch.int32, device=self.device)
+            return e, e, 0
+        if not labels.is_cuda:
+            rows, targets = label_rows_and_targets(labels)
+            return rows.to(self.device, non_blocking=True), targets.to(self.device, non_blocking=True), int(rows.numel())
+        B, S = labels.shape
+        lab = labels.to(device=self.device, dtype=torch.int64).contiguous()
+        rows = self.ws.typed("label_rows", (B * S,), torch.int32)
+        targets = self.ws.typed("label_targets", (B * S,), torch.int32)
+        count = self.ws.typed("label_count", (1,), torch.int32)
+        L.check(self.lib.ta_label_rows(L.ptr(lab), B, S, L.ptr(rows), L.ptr(targets), L.ptr(count), L.stream_ptr()))
+        n = int(count.item())
+        return rows[:n], targets[:n], n
+
+    def apply_frame_dropout(self, enc: torch.Tensor, keep_prob: Optional[float] = None, keep_mask: Optional[torch.Tensor] = None):
+        """audio_token_dropout (asr_modeling.py:458-479): whole-frame Bernoulli(keep_prob) zero mask on the encoder output, no
+        rescale.  The mask is drawn with torch's generator exactly as the reference draws it (same shape, fp32, same device), so
+        `torch.manual_seed` reproduces the reference's CUDA mask; `keep_mask` ([B, S_e], 1 = keep) injects a given draw (parity
+        tests replay the mask the reference drew).  Applied in place by ta_frame_keep_mask."""
+        if keep_mask is None:
+            if keep_prob is None or keep_prob >= 1.0:
+                return enc
+            keep_mask = torch.bernoulli(torch.full(enc.shape[:-1], float(keep_prob), device=self.device, dtype=F32))
+        keep = keep_mask.to(device=self.device, dtype=F32).contiguous()
+        assert tuple(keep.shape) == tuple(enc.shape[:-1]), f"keep mask {tuple(keep.shape)} vs encoder frames {tuple(enc.shape[:-1])}"
+        L.check(self.lib.ta_frame_keep_mask(L.ptr(enc), L.ptr(keep), keep.numel(), enc.shape[-1], L.stream_ptr()))
+        return enc
+
     def __init__(self, dims: PathDims, enc_sd, lm_sd, device="cuda", lora: bool = False):
         self.lib = L.load()
         self.dims = dims
@@ -515,8 +553,11 @@ class HotPath:
 
     # ------------------------------------------------------------------ decoder + loss (+ backward to inputs_embeds)
     def lm_step(self, emb: torch.Tensor, B: int, S: int, rows: torch.Tensor, targets: torch.Tensor, inv_items: float,
-                with_backward: bool, want_row_loss: bool = False, train_lm: bool = False, input_ids: Optional[torch.Tensor] = None):
-        """train_lm (unfrozen LM): the backward also fills self.lm.wgrad (PackedLM.enable_weight_grads) -- needs input_ids."""
+                with_backward: bool, want_row_loss: bool = False, train_lm: bool = False, input_ids: Optional[torch.Tensor] = None,
+                want_hidden: bool = False):
+        """train_lm (unfrozen LM): the backward also fills self.lm.wgrad (PackedLM.enable_weight_grads) -- needs input_ids.
+        want_hidden: also keep the last layer's output (before the final norm) in the `final_hidden` workspace, from which
+        logits of arbitrary positions can be produced afterwards (HotPath.logits_all)."""
         d = self.dims
         nl = int(rows.numel())
         n = C.c_longlong()
@@ -529,8 +570,9 @@ class HotPath:
         loss = torch.zeros(1, device=self.device, dtype=F32)
         demb = self.ws.typed("d_inputs_embeds", (B * S, d.lm_dim), F32) if with_backward else None
         row_loss = torch.empty(nl, device=self.device, dtype=F32) if want_row_loss else None
+        hid = self.ws.typed("final_hidden", (B * S, d.lm_dim), F32) if want_hidden else None
         args = L.LmStepArgs(B, S, nl, int(with_backward), L.ptr(emb), L.ptr(rows), L.ptr(targets), inv_items, L.ptr(loss),
-                            L.ptr(row_loss), L.ptr(demb), L.ptr(ws), n.value, None,
+                            L.ptr(row_loss), L.ptr(demb), L.ptr(ws), n.value, L.ptr(hid),
                             C.cast(self.lm.grad_table, C.POINTER(L.P)) if (with_backward and self.lm.grad_table is not None) else None,
                             None, None, 0,
                             C.cast(self.lm.wgrad_table, C.POINTER(L.P)) if train_lm else None,
@@ -607,6 +649,22 @@ class HotPath:
         L.check(self.lib.ta_lm_hidden_to_logits(C.byref(self.lm.c), L.ptr(hidden), L.ptr(rows), nr, L.ptr(normed), L.ptr(logits),
                                                 L.stream_ptr()))
         return logits[:, : d.vocab]
+
+    def logits_all(self, B: int, S: int, hidden: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """bf16 logits [B, S, vocab] of every position from the kept final hidden states (lm_step(want_hidden=True) or lm_hidden):
+        what the reference's forward returns as `outputs.logits` (asr_modeling.py:517-533; bf16 under the autocast recipe)."""
+        hid = hidden if hidden is not None else self.ws.typed("final_hidden", (B * S, self.dims.lm_dim), F32)
+        rows = torch.arange(B * S, device=self.device, dtype=torch.int32)
+        return self.logits_rows(hid, rows).view(B, S, self.dims.vocab)
+
+    def text_embeds(self, input_ids: torch.Tensor) -> torch.Tensor:
+        """fp32 embedding lookup [B*S, dim] for a batch without audio (the <audio> scatter has nothing to place)."""
+        B, S = input_ids.shape
+        ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
+        zero = torch.zeros(B, dtype=torch.int64, device=self.device)
+        dummy = self.ws.typed("no_audio", (1, self.dims.lm_dim), F32)
+        emb, _ = self.embed_scatter(ids, zero, dummy, 1)
+        return emb
 
     @torch.no_grad()
     def audio_embeds(self, *, waveform=None, input_features=None, proj_params=None):
@@ -701,55 +759,68 @@ class HotPath:
                 break
         return torch.stack(out, dim=1)
 
-    def lm_loss_and_audio_grad(self, *, input_ids, labels_cpu, audio, n_a, audio_token_counts=None, num_items_in_batch=None,
-                               with_backward=True):
-        """<audio> scatter -> Qwen3 -> CE (-> backward to the audio embeddings).  `audio` fp32 [B*n_a, lm_dim].
-        Returns (loss [1], d_audio [B*n_a, lm_dim] or None).  Projector-agnostic: any module that produces the audio
-        embeddings can sit in front of it (ASRModel uses it for every projector except the fused MLP path)."""
+    def lm_loss_and_audio_grad(self, *, input_ids=None, audio=None, n_a=0, inputs_embeds=None, labels=None, labels_cpu=None,
+                               audio_token_counts=None, num_items_in_batch=None, with_backward=True, lm_backward=None, train_lm=False,
+                               want_hidden=False):
+        """<audio> scatter -> Qwen3 -> CE (-> backward to the audio embeddings).  `audio` fp32 [B*n_a, lm_dim], or None for a batch
+        without audio (plain embedding lookup); `inputs_embeds` fp32 [B, S, lm_dim] bypasses the lookup altogether.
+        Returns (loss [1], d_audio [B*n_a, lm_dim] or None).  Projector-agnostic: any module that produces the audio embeddings
+        can sit in front of it (ASRModel uses it for every projector except the fused MLP path).  lm_backward / train_lm: the
+        decoder's own trainable tensors (LoRA A / B, or all Qwen3 weights) get their gradients in the same pass."""
         d = self.dims
-        B, S = input_ids.shape
-        if audio_token_counts is None:
-            audio_token_counts = (input_ids == d.audio_token_id).sum(-1)
-        counts = audio_token_counts.to(device=self.device, dtype=torch.int64).contiguous()
-        ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
-        emb, src = self.embed_scatter(ids, counts, audio, n_a)
-        if labels_cpu is not None:
-            rows, targets = label_rows_and_targets(labels_cpu)
-            n_items = float(rows.numel()) if num_items_in_batch is None else float(num_items_in_batch)
-            rows_d, tg_d = rows.to(self.device, non_blocking=True), targets.to(self.device, non_blocking=True)
+        src = None
+        if inputs_embeds is not None:
+            B, S = int(inputs_embeds.shape[0]), int(inputs_embeds.shape[1])
+            emb = inputs_embeds.detach().to(device=self.device, dtype=F32).contiguous().view(B * S, d.lm_dim)
+            # no token ids: the embedding table receives no input-side gradient (every position counts as a placeholder)
+            ids = (input_ids.to(device=self.device, dtype=torch.int64).contiguous() if input_ids is not None
+                   else torch.full((B, S), d.audio_token_id, dtype=torch.int64, device=self.device))
         else:
-            rows_d = torch.empty(0, dtype=torch.int32, device=self.device)
-            tg_d, n_items = rows_d, 1.0
-        loss, demb, _ = self.lm_step(emb, B, S, rows_d, tg_d, 1.0 / max(n_items, 1.0), with_backward)
+            B, S = input_ids.shape
+            ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
+            if audio is None:
+                emb = self.text_embeds(ids)
+            else:
+                if audio_token_counts is None:
+                    audio_token_counts = (ids == d.audio_token_id).sum(-1)
+                counts = audio_token_counts.to(device=self.device, dtype=torch.int64).contiguous()
+                emb, src = self.embed_scatter(ids, counts, audio, n_a)
+        rows_d, tg_d, n_lab = self.label_rows(labels if labels is not None else labels_cpu)
+        n_items = float(n_lab) if num_items_in_batch is None else float(num_items_in_batch)
+        want_audio_grad = bool(with_backward and src is not None)
+        lm_bwd = bool(want_audio_grad or lm_backward or train_lm)   # LoRA / unfrozen decoder need the LM backward even for a frozen projector
+        loss, demb, _ = self.lm_step(emb, B, S, rows_d, tg_d, 1.0 / max(n_items, 1.0), lm_bwd, train_lm=train_lm, input_ids=ids,
+                                     want_hidden=want_hidden)
         d_audio = None
-        if with_backward:
+        if want_audio_grad:
             d_audio = self.ws.typed("d_audio", (B * n_a, d.lm_dim), F32)
             d_audio.zero_()
             L.check(self.lib.ta_audio_grad_gather(L.ptr(src), L.ptr(demb), L.ptr(d_audio), B * S, d.lm_dim, L.stream_ptr()))
         return loss, d_audio
 
     @torch.no_grad()
-    def encode_audio(self, *, waveform=None, input_features=None, frame_keep_prob=None):
+    def encode_audio(self, *, waveform=None, input_features=None, frame_keep_prob=None, frame_keep_mask=None):
         """log-mel (if needed) + frozen encoder (+ audio-token dropout) -> bf16 [B, S_e, enc_dim]."""
         B = (waveform if waveform is not None else input_features).shape[0]
         if waveform is not None:
             im2, _, T = self.logmel(waveform)
         else:
             im2, T = self.mel_to_im2col(input_features)
-        enc = self.encode(im2, B, T)
-        if frame_keep_prob is not None and frame_keep_prob < 1.0:
-            keep = torch.bernoulli(torch.full(enc.shape[:-1], float(frame_keep_prob), device=self.device, dtype=F32))
-            enc.mul_(keep.unsqueeze(-1).to(enc.dtype))
-        return enc
+        return self.apply_frame_dropout(self.encode(im2, B, T), frame_keep_prob, frame_keep_mask)
 
     # ------------------------------------------------------------------ the whole step
-    def forward_backward(self, *, input_ids: torch.Tensor, labels_cpu: Optional[torch.Tensor], proj_params,
+    def forward_backward(self, *, input_ids: torch.Tensor, proj_params, labels: Optional[torch.Tensor] = None,
+                         labels_cpu: Optional[torch.Tensor] = None,
                          waveform: Optional[torch.Tensor] = None, input_features: Optional[torch.Tensor] = None,
                          audio_token_counts: Optional[torch.Tensor] = None, num_items_in_batch: Optional[float] = None,
                          grads: Optional[Dict[str, torch.Tensor]] = None, return_parts: bool = False,
-                         frame_keep_prob: Optional[float] = None, lm_backward: Optional[bool] = None, train_lm: bool = False):
+                         frame_keep_prob: Optional[float] = None, frame_keep_mask: Optional[torch.Tensor] = None,
+                         lm_backward: Optional[bool] = None, train_lm: bool = False, want_hidden: bool = False):
         """Returns (loss [1] fp32 device tensor, parts).  When `grads` is given (fp32 tensors shaped like the projector
-        params) the backward runs and fills them with d(loss)/d(param)."""
+        params) the backward runs and fills them with d(loss)/d(param).  `labels` may live on the host or on the device
+        (`labels_cpu` is the older name of the same argument)."""
+        if labels is None:
+            labels = labels_cpu
         d = self.dims
         B, S = input_ids.shape
         parts = {}
@@ -759,12 +830,7 @@ class HotPath:
                 parts["mel"] = mel_f32
         else:
             im2, T = self.mel_to_im2col(input_features)
-        enc = self.encode(im2, B, T)
-        if frame_keep_prob is not None and frame_keep_prob < 1.0:
-            # audio_token_dropout (asr_modeling.py:458-479): whole-frame Bernoulli zero mask, no rescale.  The mask is
-            # drawn with torch's generator exactly as the reference does; parity runs use p = 0.
-            keep = torch.bernoulli(torch.full(enc.shape[:-1], float(frame_keep_prob), device=self.device, dtype=F32))
-            enc.mul_(keep.unsqueeze(-1).to(enc.dtype))
+        enc = self.apply_frame_dropout(self.encode(im2, B, T), frame_keep_prob, frame_keep_mask)
         xs, n_a = self.frame_stack(enc)
         with_bwd = grads is not None                           # projector gradients wanted
         lm_bwd = with_bwd if lm_backward is None else (lm_backward or with_bwd)   # LoRA-only training still needs the LM backward
@@ -775,17 +841,10 @@ class HotPath:
         counts = audio_token_counts.to(device=self.device, dtype=torch.int64).contiguous()
         ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
         emb, src = self.embed_scatter(ids, counts, audio, n_a)
-        if labels_cpu is not None:
-            rows, targets = label_rows_and_targets(labels_cpu)
-            n_items = float(rows.numel()) if num_items_in_batch is None else float(num_items_in_batch)
-            rows_d = rows.to(self.device, non_blocking=True)
-            tg_d = targets.to(self.device, non_blocking=True)
-        else:
-            rows_d = torch.empty(0, dtype=torch.int32, device=self.device)
-            tg_d = rows_d
-            n_items = 1.0
+        rows_d, tg_d, n_lab = self.label_rows(labels)
+        n_items = float(n_lab) if num_items_in_batch is None else float(num_items_in_batch)
         inv = 1.0 / max(n_items, 1.0)
-        loss, demb, _ = self.lm_step(emb, B, S, rows_d, tg_d, inv, lm_bwd, train_lm=train_lm, input_ids=ids)
+        loss, demb, _ = self.lm_step(emb, B, S, rows_d, tg_d, inv, lm_bwd, train_lm=train_lm, input_ids=ids, want_hidden=want_hidden)
         if with_bwd:
             d_audio = self.ws.typed("d_audio", (B * n_a, d.lm_dim), F32)
             d_audio.zero_()

@@ -10,6 +10,19 @@ flat fp32 buffer (`param.grad` are views of it), so a step is:
 The loss is normalised by the GLOBAL number of label tokens (num_items_in_batch), so SUM over ranks yields the
 gradient of the global token-mean CE -- the same quantity HF Trainer produces with
 average_tokens_across_devices (HF:trainer.py:2141-2143, 2013-2018).
+
+Who reduces the gradients is explicit (`allreduce`):
+  * allreduce=True  -- this optimiser does the one SUM all-reduce (bench.py, plain torchrun loops: the model is NOT wrapped
+    in DistributedDataParallel and the loss is NOT multiplied by the world size);
+  * allreduce=False -- somebody else already reduced them: under HF Trainer / accelerate the model is DDP-wrapped (bucketed
+    MEAN all-reduce during backward) and Trainer multiplies the loss by the number of processes, which together give the
+    same SUM; reducing again here would scale the gradient by the world size before the clip;
+  * allreduce=None (default) -- True iff a process group with more than one rank exists AND `ddp_wrapped` was not declared.
+    Pass `ddp_wrapped=True` (or allreduce=False) whenever the model goes through DistributedDataParallel.
+
+Optimiser state lives in flat buffers but is exposed through `self.state` in torch.optim.AdamW's layout (`step`, `exp_avg`,
+`exp_avg_sq` per parameter), so `state_dict()` / `load_state_dict()` -- what HF Trainer writes to / reads from optimizer.pt --
+round-trip the moments and the step count, and interchange with the reference's `adamw_torch_fused` checkpoints.
 """
 from __future__ import annotations
 
@@ -22,7 +35,8 @@ from . import lib as L
 
 class ClipAdamW(torch.optim.Optimizer):
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, max_grad_norm: float = 1.0, process_group=None):
+                 weight_decay: float = 0.0, max_grad_norm: float = 1.0, process_group=None, allreduce=None,
+                 ddp_wrapped: bool = False):
         params = list(params)
         if params and isinstance(params[0], dict):      # torch-style parameter groups (decoder lr / weight decay: train.py:384-437)
             groups = [dict(g, params=[p for p in g["params"] if p.requires_grad]) for g in params]
@@ -35,6 +49,7 @@ class ClipAdamW(torch.optim.Optimizer):
         self.lib = L.load()
         self.max_grad_norm = max_grad_norm
         self.process_group = process_group
+        self.allreduce = (not ddp_wrapped) if allreduce is None else bool(allreduce)
         self._params = params
         self._index = {id(p): i for i, p in enumerate(params)}
         for p in params:
@@ -54,6 +69,35 @@ class ClipAdamW(torch.optim.Optimizer):
             p.grad = self.flat_grad[off: off + k].view_as(p)      # autograd accumulates in place into the flat buffer
             self._slices.append((off, k))
             off += k
+        self._bind_state()
+
+    # ------------------------------------------------------------------ torch.optim.AdamW-compatible state
+    def _bind_state(self):
+        """self.state[p] = views of the flat moment buffers + the (global) step count, in torch.optim.AdamW's layout."""
+        for p, (off, k) in zip(self._params, self._slices):
+            self.state[p] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.m[off: off + k].view_as(p),
+                             "exp_avg_sq": self.v[off: off + k].view_as(p)}
+
+    def state_dict(self):
+        for p in self._params:
+            self.state[p]["step"] = torch.tensor(float(self.step_count))
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)          # fills self.state[p] with (copies of) the saved tensors
+        steps = set()
+        for p, (off, k) in zip(self._params, self._slices):
+            st = self.state.get(p)
+            if not st:
+                continue
+            self.m[off: off + k].copy_(st["exp_avg"].reshape(-1))
+            self.v[off: off + k].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"ClipAdamW keeps one step count for all parameters; the checkpoint holds {sorted(steps)}")
+        self.step_count = steps.pop() if steps else 0
+        self._bind_state()
+        self.zero_grad()                             # re-bind the .grad views
 
     def zero_grad(self, set_to_none: bool = False):
         self.flat_grad.zero_()
@@ -66,10 +110,12 @@ class ClipAdamW(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
-        for p, (off, k) in zip(self._params, self._slices):       # a fresh .grad tensor (not our view) is folded in
-            if p.grad is not None and p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
-                self.flat_grad[off: off + k].copy_(p.grad.reshape(-1))
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and \
+        for p, (off, k) in zip(self._params, self._slices):
+            if p.grad is None:                                     # no gradient this step (zero_grad(set_to_none=True) + unused):
+                self.flat_grad[off: off + k].zero_()               # the slice must not keep the previous step's values
+            elif p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                self.flat_grad[off: off + k].copy_(p.grad.reshape(-1))      # a fresh .grad tensor (not our view) is folded in
+        if self.allreduce and torch.distributed.is_available() and torch.distributed.is_initialized() and \
                 torch.distributed.get_world_size(self.process_group) > 1:
             torch.distributed.all_reduce(self.flat_grad, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
         st = L.stream_ptr()
