@@ -782,7 +782,14 @@ def test_generic_projector_routes_decoder_gradients(cuda):
         assert ad.lora_A[t].grad is not None and ad.lora_B[t].grad is not None, t
         ea, eb = rel(ad.lora_A[t].grad, res["lora_grads"]["A"][t]), rel(ad.lora_B[t].grad, res["lora_grads"]["B"][t])
         assert ea < 6e-2 and eb < 6e-2, (t, ea, eb)
-    worst = max(rel(p.grad, res["grads"][k]) for k, p in model.projector.named_parameters())
+    gmax = max(float(g.norm()) for g in res["grads"].values())
+    worst = 0.0
+    for k, p in model.projector.named_parameters():
+        ref = res["grads"][k]
+        if float(ref.norm()) < 1e-5 * gmax:      # zero in exact arithmetic (key biases under softmax): absolute check
+            assert float(p.grad.float().norm()) < 1e-3 * gmax, k
+            continue
+        worst = max(worst, rel(p.grad, ref))
     print(f"[qformer + lora] loss {float(loss):.5f} oracle {float(res['loss']):.5f}; worst projector grad rel err {worst:.3e}")
     assert worst < 8e-2
     del model

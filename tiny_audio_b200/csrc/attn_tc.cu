@@ -877,6 +877,319 @@ int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant 6 (encoder shape, head_dim 64, non-causal): persistent CTA, two query tiles in ping-pong.
+//
+// ncu of variant 2 (profiles/r02_c01_ncu_attn_tc_fwd1.txt): the SFU pipe is 61 % busy and the tensor pipe 30 % -- the two resident
+// CTAs drift INTO phase (both softmax warps of an SM sub-partition sit in their exp2 phase together, sharing the 4 MUFU lanes, and
+// then both wait for their S / PV products together: 25 % of a softmax warp's samples are s_full / pv_done waits), and every CTA
+// pays its own prologue (TMEM allocation, Q and first K tile from HBM) 52 times per SM.
+//
+// Here ONE CTA per SM stays resident and walks work items (batch, head, pair of 128-query tiles):
+//   * warps 0-3 = softmax group A (query rows 0..127 of the pair), warps 4-7 = group B (rows 128..255); warp i and warp i+4 sit on
+//     the same SM sub-partition and take STRICT TURNS in the exp2 phase (mbarrier token per sub-partition): while A's warp runs its
+//     128 MUFU.EX2 per row, B's warp loads its next S row from TMEM, takes the row max, and waits for its PV product -- the SFUs see
+//     one warp at a time, back to back;
+//   * both groups share every K / V tile (one TMA load, one shared-memory copy for two S and two PV products);
+//   * warp 8 = TMA producer (Q double-buffered: the next item's Q and first K/V tiles land while the current item finishes),
+//     warp 9 = MMA issuer; TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384);
+//   * the O / l epilogue of an item runs in the slack the other group's exp2 phase leaves.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int ATT3_THREADS = 320;
+
+struct Att3Cfg {
+    static constexpr int KV_SLOTS = 4;
+    static constexpr int Q_ITEM = 2 * TILE16;                       // Q of one work item: tile A + tile B (128 x 64 bf16 each)
+    static constexpr int KV_OFF = 2 * Q_ITEM;                       // two Q buffers
+    static constexpr int P_OFF = KV_OFF + KV_SLOTS * TILE16;
+    static constexpr int BAR_OFF = P_OFF + 2 * (2 * TILE16);        // P_A, P_B: 128 x 128 bf16 each
+    static constexpr int SMEM = BAR_OFF + 512;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr uint32_t S_COL0 = 0, O_COL0 = 256;
+};
+
+template <int POLY>
+__global__ void __launch_bounds__(ATT3_THREADS, 1)
+attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int Hq, int Hkv,
+                    long long o_rs, float scale_log2, int n_items, int n_qpairs) {
+    TA_PDL_ENTRY();
+    constexpr int HD = 64;
+    using C = Att3Cfg;
+    extern __shared__ __align__(1024) uint8_t smem_al[];
+    uint8_t* smem = smem_al;
+    if (smem_u32(smem) & 1023u) __trap();                 // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* sQ = smem;
+    uint8_t* sKV = smem + C::KV_OFF;
+    uint8_t* sP = smem + C::P_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+    uint64_t* q_full = bars;                  // [2]
+    uint64_t* q_empty = bars + 2;             // [2]
+    uint64_t* kv_full = bars + 4;             // [4]
+    uint64_t* kv_empty = bars + 8;            // [4]
+    uint64_t* s_full = bars + 12;             // [2] per group
+    uint64_t* s_empty = bars + 14;            // [2]
+    uint64_t* p_full = bars + 16;             // [2]
+    uint64_t* pv_done = bars + 18;            // [2]
+    uint64_t* o_free = bars + 20;             // [2]
+    uint64_t* turn = bars + 22;               // [2][4]: turn[g * 4 + q] completes when the OTHER group's warp q has finished an exp2 phase
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_kv = (S + BKV - 1) / BKV;
+    const int n_mine = (n_items > (int)blockIdx.x) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total = n_mine * n_kv;          // (item, kv tile) steps of this CTA
+
+    if (warp == 8) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&q_full[i], 1);
+                mbar_init(&q_empty[i], 1);
+                mbar_init(&s_full[i], 1);
+                mbar_init(&s_empty[i], 4);
+                mbar_init(&p_full[i], 4);
+                mbar_init(&pv_done[i], 1);
+                mbar_init(&o_free[i], 4);
+            }
+            for (int s = 0; s < C::KV_SLOTS; ++s) {
+                mbar_init(&kv_full[s], 1);
+                mbar_init(&kv_empty[s], 1);
+            }
+            for (int i = 0; i < 8; ++i) mbar_init(&turn[i], 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ------------------------------------------------ TMA producer ------------------------------------------------
+        if (lane == 0) {
+            int ld = 0;                                    // K / V tile loads issued so far (ring position)
+            for (int it = 0; it < n_mine; ++it) {
+                const int w = (int)blockIdx.x + it * (int)gridDim.x;
+                const int qp = w % n_qpairs, bh = w / n_qpairs, h = bh % Hq, b = bh / Hq;
+                const int hk = h / (Hq / Hkv), row_base = b * S, q0 = qp * 2 * BQ;
+                const int buf = it & 1;
+                mbar_wait(&q_empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&q_full[buf], C::Q_ITEM);
+                tma_load_2d(sQ + buf * C::Q_ITEM, &tmQ, &q_full[buf], h * HD, row_base + q0);
+                tma_load_2d(sQ + buf * C::Q_ITEM + TILE16, &tmQ, &q_full[buf], h * HD, row_base + q0 + BQ);
+                for (int i = 0; i < 2 * n_kv; ++i, ++ld) {
+                    const int slot = ld % C::KV_SLOTS;
+                    mbar_wait(&kv_empty[slot], (((uint32_t)ld / C::KV_SLOTS) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&kv_full[slot], TILE16);
+                    tma_load_2d(sKV + slot * TILE16, (i & 1) ? &tmV : &tmK, &kv_full[slot], hk * HD, row_base + (i >> 1) * BKV);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ------------------------------------------------ MMA issuer ------------------------------------------------
+        if (lane == 0 && total > 0) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
+            constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
+            auto issue_s = [&](int g, int t) {             // S_g(t) = Q_g K(t)^T
+                const int it = t / n_kv, j = t - it * n_kv, buf = it & 1;
+                const int ld = 2 * t, slot = ld % C::KV_SLOTS;
+                if (j == 0) mbar_wait(&q_full[buf], ((uint32_t)it >> 1) & 1u);
+                mbar_wait(&kv_full[slot], ((uint32_t)ld / C::KV_SLOTS) & 1u);
+                mbar_wait(&s_empty[g], ((uint32_t)t & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(sQ + buf * C::Q_ITEM + g * TILE16), k_addr = smem_u32(sKV + slot * TILE16);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_f16(tmem_base + C::S_COL0 + g * 128, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(k_addr + k * 32),
+                             idesc_s, k != 0 ? 1u : 0u);
+                umma_commit(&s_full[g]);
+                if (g == 1) {
+                    umma_commit(&kv_empty[slot]);
+                    if (j == n_kv - 1) umma_commit(&q_empty[buf]);
+                }
+            };
+            auto issue_pv = [&](int g, int t) {            // O_g (+)= P_g(t) V(t)
+                const int it = t / n_kv, j = t - it * n_kv;
+                const int ld = 2 * t + 1, slot = ld % C::KV_SLOTS;
+                mbar_wait(&p_full[g], (uint32_t)t & 1u);
+                mbar_wait(&kv_full[slot], ((uint32_t)ld / C::KV_SLOTS) & 1u);
+                if (j == 0 && it > 0) mbar_wait(&o_free[g], ((uint32_t)(it - 1)) & 1u);   // the previous item's O has been read out
+                tc_fence_after();
+                const uint32_t p_addr = smem_u32(sP + g * 2 * TILE16), v_addr = smem_u32(sKV + slot * TILE16);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    const uint32_t pa = p_addr + (k >> 2) * TILE16 + (k & 3) * 32;
+                    umma_f16(tmem_base + C::O_COL0 + g * HD, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16),
+                             idesc_o, (j | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&pv_done[g]);
+                if (g == 1) umma_commit(&kv_empty[slot]);
+            };
+            issue_s(0, 0);
+            issue_s(1, 0);
+            for (int t = 0; t < total; ++t) {
+                if (t + 1 < total) issue_s(0, t + 1);
+                issue_pv(0, t);
+                if (t + 1 < total) issue_s(1, t + 1);
+                issue_pv(1, t);
+            }
+        }
+    } else {
+        // ------------------------------------------------ softmax groups ------------------------------------------------
+        const int g = warp >> 2, q = warp & 3;
+        const int r = q * 32 + lane;                        // query row of my tile = TMEM lane
+        const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + C::S_COL0 + (uint32_t)g * 128;
+        const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + C::O_COL0 + (uint32_t)g * HD;
+        uint8_t* p_row = sP + g * 2 * TILE16 + r * 128;
+        uint64_t* my_turn = &turn[g * 4 + q];
+        uint64_t* other_turn = &turn[(g ^ 1) * 4 + q];
+        int t = 0;
+        for (int it = 0; it < n_mine; ++it) {
+            const int w = (int)blockIdx.x + it * (int)gridDim.x;
+            const int qp = w % n_qpairs, bh = w / n_qpairs, h = bh % Hq, b = bh / Hq;
+            const int row_base = b * S, q0 = qp * 2 * BQ + g * BQ;
+            float m_ref = -INFINITY, l_sum = 0.f;
+            for (int j = 0; j < n_kv; ++j, ++t) {
+                mbar_wait(&s_full[g], (uint32_t)t & 1u);
+                tc_fence_after();
+                const int lim = min(S - j * BKV - 1, 127);  // my columns e = 0..127 are real (unmasked) keys iff e <= lim
+                uint32_t v[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, v[c]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[g]);    // S is in registers: the MMA warp may issue my next S product now
+                if (lim < 127) {                            // last tile of the sequence only: warp-uniform
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i > lim) v[c][i] = 0xff800000u;      // -inf
+                }
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[c][i]));
+                const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
+                const bool grow = mx > m_ref + 8.0f;
+                const float m_new = grow ? mx : m_ref;
+                const float alpha = (grow && j > 0) ? ex2_approx(m_ref - m_new) : 1.0f;
+                m_ref = m_new;
+                if (j > 0) {
+                    mbar_wait(&pv_done[g], (uint32_t)(t - 1) & 1u);     // PV of my previous tile has consumed P and updated O
+                    tc_fence_after();
+                }
+                // ---- my turn on this sub-partition's SFUs (group A starts; then strictly alternating with warp q of the other group) ----
+                mbar_wait(my_turn, g == 0 ? (((uint32_t)t & 1u) ^ 1u) : ((uint32_t)t & 1u));
+                float l4[4] = {0.f, 0.f, 0.f, 0.f};
+                const float neg_m = -m_ref;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        float e[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float x = fmaf(__uint_as_float(v[c][8 * qd + u]), scale_log2, neg_m);
+                            if (POLY > 0 && (u % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) e[u] = ex2_poly(x);
+                            else e[u] = ex2_approx(x);                    // exp2(-inf) = 0 for masked columns
+                            l4[u & 3] += e[u];
+                        }
+                        uint4 pk;
+                        pk.x = pack_bf16x2(e[0], e[1]);
+                        pk.y = pack_bf16x2(e[2], e[3]);
+                        pk.z = pack_bf16x2(e[4], e[5]);
+                        pk.w = pack_bf16x2(e[6], e[7]);
+                        const int k16 = c * 4 + qd;                       // 16-byte chunk of the 256-byte P row
+                        *reinterpret_cast<uint4*>(p_row + (k16 >> 3) * TILE16 + (((k16 & 7) ^ (r & 7)) << 4)) = pk;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(other_turn);                   // hand the SFUs to the other group's warp
+                if (j > 0 && __any_sync(0xffffffffu, grow)) {             // lazy rescale of O (rare)
+#pragma unroll 1
+                    for (int c = 0; c < HD / 32; ++c) {
+                        uint32_t o[32];
+                        tmem_ld_32x32(t_o + c * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x32(t_o + c * 32, o);
+                    }
+                    tmem_st_wait();
+                    l_sum *= alpha;
+                }
+                l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[g]);
+            }
+            // ---- item epilogue: O / l -> bf16 (runs while the other group has the SFUs) ----
+            mbar_wait(&pv_done[g], (uint32_t)(t - 1) & 1u);
+            tc_fence_after();
+            const int row = q0 + r;
+            const float inv = 1.0f / l_sum;
+            bf16* orow = O + ((long long)row_base + row) * o_rs + (long long)h * HD;
+#pragma unroll 1
+            for (int c = 0; c < HD / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld_32x32(t_o + c * 32, o);
+                tmem_ld_wait();
+                if (row < S) {
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        uint4 u;
+                        u.x = pack_bf16x2(__uint_as_float(o[8 * qd + 0]) * inv, __uint_as_float(o[8 * qd + 1]) * inv);
+                        u.y = pack_bf16x2(__uint_as_float(o[8 * qd + 2]) * inv, __uint_as_float(o[8 * qd + 3]) * inv);
+                        u.z = pack_bf16x2(__uint_as_float(o[8 * qd + 4]) * inv, __uint_as_float(o[8 * qd + 5]) * inv);
+                        u.w = pack_bf16x2(__uint_as_float(o[8 * qd + 6]) * inv, __uint_as_float(o[8 * qd + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + qd * 8) = u;
+                    }
+                }
+            }
+            if (LSE && row < S) LSE[((long long)b * Hq + h) * S + row] = (m_ref + log2f(l_sum)) * 0.69314718055994531f;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free[g]);                       // the MMA warp may overwrite O with the next item's first PV
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int POLY>
+int launch_attn_tc3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* o, float* lse, int B, int S, int Hq,
+                    int Hkv, long long o_rs, float scale, cudaStream_t st) {
+    using C = Att3Cfg;
+    auto kern = attn_tc_fwd3_kernel<POLY>;
+    static bool done = false;
+    static int n_sm = 0;
+    if (!done) {
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        int dev = 0;
+        TA_CHECK_CUDA(cudaGetDevice(&dev));
+        TA_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        done = true;
+    }
+    const int n_qpairs = ((S + BQ - 1) / BQ + 1) / 2;
+    const long long n_items = (long long)B * Hq * n_qpairs;
+    TA_REQUIRE(n_items < (1LL << 30), "attention: too many work items");
+    const int grid = (int)((n_items < n_sm) ? n_items : n_sm);
+    TA_KERNEL_LAUNCH(kern, grid, ATT3_THREADS, C::SMEM, st, tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f, (int)n_items,
+                     n_qpairs);
+    return 0;
+}
+
 // 0: mma.sync; 1: tcgen05, 2 threads per row everywhere; 2 (default): head_dim-64 non-causal runs the one-thread-per-row variant
 // (0.590 vs 0.632 ms per encoder layer at B=32, S=1500); 3 / 4: that variant with every 4th / 2nd exp2 on the FMA pipe -- slower
 // (0.68 / 0.75 ms): with two softmax warps per sub-partition the kernel is issue/latency-bound, not MUFU-bound (profiles/).
@@ -885,7 +1198,7 @@ int g_attn_tc = 2;
 }  // namespace
 
 TA_API int ta_attn_set_tc(int on) {
-    g_attn_tc = (on < 0 || on > 5) ? 2 : on;
+    g_attn_tc = (on < 0 || on > 7) ? 2 : on;
     return 0;
 }
 int k_attn_tc_enabled() { return g_attn_tc; }
@@ -909,6 +1222,8 @@ int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* l
     if (rc) return rc;
     *handled = 1;
     if (head_dim == 64 && !causal && g_attn_tc >= 2) {
+        if (g_attn_tc == 6) return launch_attn_tc3<0>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+        if (g_attn_tc == 7) return launch_attn_tc3<4>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 5) return launch_attn_tc2<64>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 2) return launch_attn_tc1<64, false, 0>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 3) return launch_attn_tc1<64, false, 4>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
