@@ -267,6 +267,11 @@ typedef struct ta_lm_step_args {
     float* d_final_norm;          /*   fp32 [dim], accumulated                                                                       */
     const long long* input_ids;   /*   [B*S]: which rows of the table the text positions read                                       */
     long long audio_token_id;
+    /* forward-only (generate() with ragged prompts, tiny_audio/asr_modeling.py:587-640 -> HF generate with attention_mask): LEFT-padded
+       prompts.  position_ids [B*S]: rotary position of every token (HF: cumsum(attention_mask) - 1); kv_start [B]: index of the first
+       real token of each sequence -- keys before it are never attended to by real tokens.  NULL: arange(S) / no padding. */
+    const int* position_ids;
+    const int* kv_start;
 } ta_lm_step_args;
 /* with_backward: 0 forward only; 1 backward to inputs_embeds (frozen LM, LoRA); 2 additionally the weight gradients (lm_grads) */
 int ta_lm_workspace_bytes(const ta_lm_weights* w, int B, int S, int n_labelled, int with_backward, long long* bytes);
@@ -291,7 +296,7 @@ int ta_lm_hidden_to_logits(const ta_lm_weights* w, const float* hidden_f32 /*[B*
  *     tiny_audio/asr_modeling.py:562-646; greedy defaults asr_config.py:103-111.  Prefill = ta_lm_forward_backward with
  *     k_cache / v_cache set; then one ta_lm_decode_step per new token:
  *       ids [B] int64 (the token fed at position *pos) -> embed -> 28 x [RMSNorm, qkv, head-norm + RoPE + cache append,
- *       single-query attention over cache rows [0, *pos], o + residual, RMSNorm, SwiGLU MLP + residual] -> final norm ->
+ *       single-query attention over cache rows [kv_start[b], *pos], o + residual, RMSNorm, SwiGLU MLP + residual] -> final norm ->
  *       tied lm_head -> logits bf16 [B, vocab_pad] -> next_ids [B] = argmax;  *pos += 1 (device side, graph-replayable).
  *     B <= 32 per call.  All linears are HBM-bound skinny products (csrc/decode.cu).
  * ---------------------------------------------------------------------------------------------- */
@@ -311,7 +316,9 @@ int ta_argmax_rows(const void* logits_bf16, long long ld, int rows, int V, long 
 int ta_lm_decode_workspace_bytes(const ta_lm_weights* w, int B, long long* bytes);
 int ta_lm_decode_step(const ta_lm_weights* w, const long long* ids, int* pos /*device*/, int pos_host /*validation only*/,
                       void* k_cache, void* v_cache, int cache_max_seq, int B, void* workspace, long long workspace_bytes,
-                      void* logits_bf16 /*[B, vocab_pad]*/, long long* next_ids /*[B]*/, void* stream);
+                      void* logits_bf16 /*[B, vocab_pad]*/, long long* next_ids /*[B]*/,
+                      const int* kv_start /*[B] or NULL: first real cache row of each (left-padded) sequence; rotary position = *pos - kv_start[b]*/,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -70,7 +70,7 @@ template <int HD, bool CAUSAL>
 __global__ void __launch_bounds__(ATT_THREADS, AttCfg<HD>::CTAS_PER_SM)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int Hq, int Hkv,
-                   long long o_rs, float scale_log2) {
+                   long long o_rs, float scale_log2, const int* __restrict__ kv_start) {
     TA_PDL_ENTRY();
     using C = AttCfg<HD>;
     extern __shared__ uint8_t smem_raw[];
@@ -186,14 +186,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         float m_ref = -INFINITY, l_sum = 0.f;
         uint8_t* p_row = sP + half * TILE16 + r * 128;
         const uint32_t bar_id = 1 + q;
+        // left-padded prompts (generate() with ragged prompts): keys before kv_start[b] are padding.  A real query row (>= kv_start)
+        // must not see them; a padding row keeps plain causal attention so that its (unused) output stays finite.
+        const int k_lo = (kv_start != nullptr && q0 + r >= kv_start[b]) ? kv_start[b] : 0;
         for (int j = 0; j < n_kv; ++j) {
             mbar_wait(s_full, (uint32_t)j & 1u);
             tc_fence_after();
-            // my columns e = 0..63 are real (unmasked) keys iff e <= lim
+            // my columns e = lo..lim are real (unmasked) keys
             int lim = S - j * BKV - half * 64 - 1;
             if (CAUSAL && j == qt) lim = min(lim, r - half * 64);
             lim = min(lim, 63);
-            const bool full_tile = __all_sync(0xffffffffu, lim >= 63);
+            const int lo = k_lo - j * BKV - half * 64;
+            const bool full_tile = __all_sync(0xffffffffu, lim >= 63 && lo <= 0);
             uint32_t v0[32], v1[32];
             tmem_ld_32x32(t_s, v0);
             tmem_ld_32x32(t_s + 32, v1);
@@ -212,8 +216,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    if (i > lim) v0[i] = 0xff800000u;          // -inf
-                    if (32 + i > lim) v1[i] = 0xff800000u;
+                    if (i > lim || i < lo) v0[i] = 0xff800000u;          // -inf
+                    if (32 + i > lim || 32 + i < lo) v1[i] = 0xff800000u;
                     m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v0[i]));
                     m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v1[i]));
                 }
@@ -225,7 +229,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]) * scale_log2;
             const bool grow = mx > m_ref + 8.0f;
             const float m_new = grow ? mx : m_ref;
-            const float alpha = (grow && j > 0) ? ex2_approx(m_ref - m_new) : 1.0f;
+            const float alpha = (grow && j > 0) ? ex2_approx(m_ref - m_new) : 1.0f;   // m_ref = -inf (all keys masked so far): 0, O and l are 0
             m_ref = m_new;
             if (j > 0) {
                 mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);     // PV_{j-1} has consumed sP and finished updating O
@@ -233,7 +237,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             // ---- P = exp2(S * scale - m_ref) -> bf16 -> swizzled smem (my 64 columns = sub-tile `half`) ----
             float l4[4] = {0.f, 0.f, 0.f, 0.f};
-            const float neg_m = -m_ref;
+            const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;     // a tile of padding keys only: exp2(-inf) = 0, never inf - inf
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
 #pragma unroll
@@ -312,7 +316,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 template <int HD, bool CAUSAL>
 int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* o, float* lse, int B, int S, int Hq,
-                   int Hkv, long long o_rs, float scale, cudaStream_t st) {
+                   int Hkv, long long o_rs, float scale, cudaStream_t st, const int* kv_start = nullptr) {
     using C = AttCfg<HD>;
     auto kern = attn_tc_fwd_kernel<HD, CAUSAL>;
     static bool done = false;
@@ -322,7 +326,7 @@ int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
         done = true;
     }
     dim3 grid((S + BQ - 1) / BQ, Hq, B);
-    TA_KERNEL_LAUNCH(kern, grid, ATT_THREADS, C::SMEM, st, tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f);
+    TA_KERNEL_LAUNCH(kern, grid, ATT_THREADS, C::SMEM, st, tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f, kv_start);
     return 0;
 }
 
@@ -897,25 +901,47 @@ int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int ATT3_THREADS = 320;
 
+template <bool P_TMEM>
 struct Att3Cfg {
-    static constexpr int KV_SLOTS = 4;
+    // P_TMEM: the probabilities go back into TENSOR MEMORY (bf16 pairs, 64 columns per group) and the PV product takes its A operand
+    // from there (tcgen05.mma with A in TMEM) -- no P store / P operand read through shared memory (64 KB of the 144 KB a tile moves
+    // through the 128 B/clk shared-memory port), and the freed 64 KB deepen the K / V ring to 8 tiles.
+    static constexpr int KV_SLOTS = P_TMEM ? 8 : 4;
     static constexpr int Q_ITEM = 2 * TILE16;                       // Q of one work item: tile A + tile B (128 x 64 bf16 each)
     static constexpr int KV_OFF = 2 * Q_ITEM;                       // two Q buffers
     static constexpr int P_OFF = KV_OFF + KV_SLOTS * TILE16;
-    static constexpr int BAR_OFF = P_OFF + 2 * (2 * TILE16);        // P_A, P_B: 128 x 128 bf16 each
+    static constexpr int BAR_OFF = P_OFF + (P_TMEM ? 0 : 2 * (2 * TILE16));   // P_A, P_B: 128 x 128 bf16 each (shared-memory variant)
     static constexpr int SMEM = BAR_OFF + 512;
     static constexpr int TMEM_COLS = 512;
-    static constexpr uint32_t S_COL0 = 0, O_COL0 = 256;
+    static constexpr uint32_t S_COL0 = 0, O_COL0 = 256, P_COL0 = 384;          // S_A S_B | O_A O_B | P_A P_B (64 columns each)
 };
 
-template <int POLY>
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (128 lanes x K, two bf16 per 32-bit column, even k in the low half) comes from
+// tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+template <int POLY, bool TURNS, bool P_TMEM>
 __global__ void __launch_bounds__(ATT3_THREADS, 1)
 attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int Hq, int Hkv,
                     long long o_rs, float scale_log2, int n_items, int n_qpairs) {
     TA_PDL_ENTRY();
     constexpr int HD = 64;
-    using C = Att3Cfg;
+    using C = Att3Cfg<P_TMEM>;
     extern __shared__ __align__(1024) uint8_t smem_al[];
     uint8_t* smem = smem_al;
     if (smem_u32(smem) & 1023u) __trap();                 // SWIZZLE_128B tiles need 1024-byte alignment
@@ -925,15 +951,15 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
     uint64_t* q_full = bars;                  // [2]
     uint64_t* q_empty = bars + 2;             // [2]
-    uint64_t* kv_full = bars + 4;             // [4]
-    uint64_t* kv_empty = bars + 8;            // [4]
-    uint64_t* s_full = bars + 12;             // [2] per group
-    uint64_t* s_empty = bars + 14;            // [2]
-    uint64_t* p_full = bars + 16;             // [2]
-    uint64_t* pv_done = bars + 18;            // [2]
-    uint64_t* o_free = bars + 20;             // [2]
-    uint64_t* turn = bars + 22;               // [2][4]: turn[g * 4 + q] completes when the OTHER group's warp q has finished an exp2 phase
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+    uint64_t* kv_full = bars + 4;             // [8]
+    uint64_t* kv_empty = bars + 12;           // [8]
+    uint64_t* s_full = bars + 20;             // [2] per group
+    uint64_t* s_empty = bars + 22;            // [2]
+    uint64_t* p_full = bars + 24;             // [2]
+    uint64_t* pv_done = bars + 26;            // [2]
+    uint64_t* o_free = bars + 28;             // [2]
+    uint64_t* turn = bars + 30;               // [2][4]: turn[g * 4 + q] completes when the OTHER group's warp q has finished an exp2 phase
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kv = (S + BKV - 1) / BKV;
@@ -1020,12 +1046,20 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 mbar_wait(&kv_full[slot], ((uint32_t)ld / C::KV_SLOTS) & 1u);
                 if (j == 0 && it > 0) mbar_wait(&o_free[g], ((uint32_t)(it - 1)) & 1u);   // the previous item's O has been read out
                 tc_fence_after();
-                const uint32_t p_addr = smem_u32(sP + g * 2 * TILE16), v_addr = smem_u32(sKV + slot * TILE16);
+                const uint32_t v_addr = smem_u32(sKV + slot * TILE16);
+                if constexpr (P_TMEM) {
 #pragma unroll
-                for (int k = 0; k < BKV / 16; ++k) {
-                    const uint32_t pa = p_addr + (k >> 2) * TILE16 + (k & 3) * 32;
-                    umma_f16(tmem_base + C::O_COL0 + g * HD, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16),
-                             idesc_o, (j | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BKV / 16; ++k)      // 16 keys = 8 columns of packed bf16 pairs
+                        umma_f16_ts(tmem_base + C::O_COL0 + g * HD, tmem_base + C::P_COL0 + g * 64 + k * 8,
+                                    umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16), idesc_o, (j | k) != 0 ? 1u : 0u);
+                } else {
+                    const uint32_t p_addr = smem_u32(sP + g * 2 * TILE16);
+#pragma unroll
+                    for (int k = 0; k < BKV / 16; ++k) {
+                        const uint32_t pa = p_addr + (k >> 2) * TILE16 + (k & 3) * 32;
+                        umma_f16(tmem_base + C::O_COL0 + g * HD, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16),
+                                 idesc_o, (j | k) != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(&pv_done[g]);
                 if (g == 1) umma_commit(&kv_empty[slot]);
@@ -1045,7 +1079,8 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int r = q * 32 + lane;                        // query row of my tile = TMEM lane
         const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + C::S_COL0 + (uint32_t)g * 128;
         const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + C::O_COL0 + (uint32_t)g * HD;
-        uint8_t* p_row = sP + g * 2 * TILE16 + r * 128;
+        uint8_t* p_row = sP + (P_TMEM ? 0 : g * 2 * TILE16 + r * 128);
+        const uint32_t t_p = tmem_base + ((uint32_t)(q * 32) << 16) + C::P_COL0 + (uint32_t)g * 64;
         uint64_t* my_turn = &turn[g * 4 + q];
         uint64_t* other_turn = &turn[(g ^ 1) * 4 + q];
         int t = 0;
@@ -1086,8 +1121,8 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     mbar_wait(&pv_done[g], (uint32_t)(t - 1) & 1u);     // PV of my previous tile has consumed P and updated O
                     tc_fence_after();
                 }
-                // ---- my turn on this sub-partition's SFUs (group A starts; then strictly alternating with warp q of the other group) ----
-                mbar_wait(my_turn, g == 0 ? (((uint32_t)t & 1u) ^ 1u) : ((uint32_t)t & 1u));
+                // ---- TURNS: my turn on this sub-partition's SFUs (group A starts; then strictly alternating with warp q of the other group) ----
+                if constexpr (TURNS) mbar_wait(my_turn, g == 0 ? (((uint32_t)t & 1u) ^ 1u) : ((uint32_t)t & 1u));
                 float l4[4] = {0.f, 0.f, 0.f, 0.f};
                 const float neg_m = -m_ref;
 #pragma unroll
@@ -1108,11 +1143,23 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         pk.z = pack_bf16x2(e[4], e[5]);
                         pk.w = pack_bf16x2(e[6], e[7]);
                         const int k16 = c * 4 + qd;                       // 16-byte chunk of the 256-byte P row
-                        *reinterpret_cast<uint4*>(p_row + (k16 >> 3) * TILE16 + (((k16 & 7) ^ (r & 7)) << 4)) = pk;
+                        if constexpr (P_TMEM) {
+                            // keep the packed pairs in the (dead) S registers: columns [4 k16, +4) of my P row, stored 8 columns at a time
+                            v[c][8 * qd + 0] = pk.x; v[c][8 * qd + 1] = pk.y; v[c][8 * qd + 2] = pk.z; v[c][8 * qd + 3] = pk.w;
+                            if (qd & 1) {
+                                const uint32_t w8[8] = {v[c][8 * (qd - 1) + 0], v[c][8 * (qd - 1) + 1], v[c][8 * (qd - 1) + 2], v[c][8 * (qd - 1) + 3],
+                                                        pk.x, pk.y, pk.z, pk.w};
+                                tmem_st_32x8(t_p + (k16 - 1) * 4, w8);
+                            }
+                        } else {
+                            *reinterpret_cast<uint4*>(p_row + (k16 >> 3) * TILE16 + (((k16 & 7) ^ (r & 7)) << 4)) = pk;
+                        }
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(other_turn);                   // hand the SFUs to the other group's warp
+                if constexpr (TURNS) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(other_turn);               // hand the SFUs to the other group's warp
+                }
                 if (j > 0 && __any_sync(0xffffffffu, grow)) {             // lazy rescale of O (rare)
 #pragma unroll 1
                     for (int c = 0; c < HD / 32; ++c) {
@@ -1127,8 +1174,9 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     l_sum *= alpha;
                 }
                 l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+                if constexpr (P_TMEM) tmem_st_wait();
                 tc_fence_before();
-                fence_proxy_async_smem();
+                if constexpr (!P_TMEM) fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[g]);
             }
@@ -1167,11 +1215,11 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (warp == 8) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-template <int POLY>
+template <int POLY, bool TURNS, bool P_TMEM>
 int launch_attn_tc3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* o, float* lse, int B, int S, int Hq,
                     int Hkv, long long o_rs, float scale, cudaStream_t st) {
-    using C = Att3Cfg;
-    auto kern = attn_tc_fwd3_kernel<POLY>;
+    using C = Att3Cfg<P_TMEM>;
+    auto kern = attn_tc_fwd3_kernel<POLY, TURNS, P_TMEM>;
     static bool done = false;
     static int n_sm = 0;
     if (!done) {
@@ -1198,7 +1246,7 @@ int g_attn_tc = 2;
 }  // namespace
 
 TA_API int ta_attn_set_tc(int on) {
-    g_attn_tc = (on < 0 || on > 7) ? 2 : on;
+    g_attn_tc = (on < 0 || on > 10) ? 2 : on;
     return 0;
 }
 int k_attn_tc_enabled() { return g_attn_tc; }
@@ -1206,8 +1254,12 @@ int k_attn_tc_enabled() { return g_attn_tc; }
 // internal: *handled = 1 if this shape runs on the tcgen05 kernel (and was launched), 0 if the caller should use mma.sync
 int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* lse, int B, int S, int Hq, int Hkv, int head_dim,
                   long long q_rs, long long k_rs, long long v_rs, long long o_rs, int causal, float scale, cudaStream_t st,
-                  int* handled) {
+                  int* handled, const int* kv_start) {
     *handled = 0;
+    if (kv_start != nullptr && !(g_attn_tc && head_dim == 128 && causal)) {
+        ta_set_error("attention with left-padded keys (kv_start) runs on the tcgen05 causal head_dim-128 kernel only");
+        return -1;
+    }
     if (!g_attn_tc || (head_dim != 64 && head_dim != 128) || S < 1 || Hq % Hkv != 0) return 0;
     if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
          reinterpret_cast<uintptr_t>(o)) & 15)
@@ -1222,8 +1274,13 @@ int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* l
     if (rc) return rc;
     *handled = 1;
     if (head_dim == 64 && !causal && g_attn_tc >= 2) {
-        if (g_attn_tc == 6) return launch_attn_tc3<0>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
-        if (g_attn_tc == 7) return launch_attn_tc3<4>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+        // persistent two-tile kernel: 6 = strict SFU turns, P through shared memory; 7 = free-running groups, P through shared memory;
+        // 8 = free-running, P in tensor memory; 9 = turns + P in tensor memory; 10 = 8 with every 4th exp2 on the FMA pipe
+        if (g_attn_tc == 6) return launch_attn_tc3<0, true, false>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+        if (g_attn_tc == 7) return launch_attn_tc3<0, false, false>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+        if (g_attn_tc == 8) return launch_attn_tc3<0, false, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+        if (g_attn_tc == 9) return launch_attn_tc3<0, true, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+        if (g_attn_tc == 10) return launch_attn_tc3<4, false, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 5) return launch_attn_tc2<64>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 2) return launch_attn_tc1<64, false, 0>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 3) return launch_attn_tc1<64, false, 4>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
@@ -1233,6 +1290,6 @@ int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* l
         if (causal) return launch_attn_tc<64, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         return launch_attn_tc<64, false>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
     }
-    if (causal) return launch_attn_tc<128, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+    if (causal) return launch_attn_tc<128, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st, kv_start);
     return launch_attn_tc<128, false>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
 }

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32)
 decode_attn_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ q_ready, bf16* k_cache, bf16* v_cache,
                    bf16* __restrict__ out, long long ld_out, const float* __restrict__ qw, const float* __restrict__ kw,
                    const float* __restrict__ cosT, const float* __restrict__ sinT, const int* __restrict__ pos_ptr, int Hq, int Hkv,
-                   int max_seq, float eps, float scale_log2) {
+                   int max_seq, float eps, float scale_log2, const int* __restrict__ kv_start) {
     const int HD = 128;
     __shared__ float s_acc[DA_SLOTS][G][HD];
     __shared__ float s_m[DA_SLOTS][G], s_l[DA_SLOTS][G];
@@ -314,8 +314,12 @@ decode_attn_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ q_read
     const int KD = Hkv * HD;
     pdl_launch_dependents();
     pdl_wait();
-    const int pos = *pos_ptr;
-    const int n_keys = pos + 1;
+    const int pos = *pos_ptr;                          // cache row the new token is appended to (same for every sequence)
+    // left-padded prompts (generate() with ragged prompts): sequence b's real tokens start at cache row ks; its rotary position
+    // is counted from there (HF: position_ids = cumsum(attention_mask) - 1) and the padding rows are never attended to
+    const int ks = kv_start ? kv_start[b] : 0;
+    const int rpos = pos - ks;
+    const int n_keys = rpos + 1;
     bf16* kb_w = k_cache + (long long)b * max_seq * KD + (long long)kvh * HD;
     bf16* vb_w = v_cache + (long long)b * max_seq * KD + (long long)kvh * HD;
 
@@ -339,8 +343,8 @@ decode_attn_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ q_read
                 // normed value is cast back to bf16 before the gain is applied (Qwen3RMSNorm)
                 const float n0 = bf16_round(a.x * rstd) * w[2 * lane], n1 = bf16_round(a.y * rstd) * w[2 * lane + 1];
                 const float n2 = bf16_round(bb.x * rstd) * w[64 + 2 * lane], n3 = bf16_round(bb.y * rstd) * w[64 + 2 * lane + 1];
-                const float c0 = cosT[pos * 64 + 2 * lane], c1 = cosT[pos * 64 + 2 * lane + 1];
-                const float s0 = sinT[pos * 64 + 2 * lane], s1 = sinT[pos * 64 + 2 * lane + 1];
+                const float c0 = cosT[rpos * 64 + 2 * lane], c1 = cosT[rpos * 64 + 2 * lane + 1];
+                const float s0 = sinT[rpos * 64 + 2 * lane], s1 = sinT[rpos * 64 + 2 * lane + 1];
                 const uint32_t lo = pack_bf16x2(n0 * c0 - n2 * s0, n1 * c1 - n3 * s1);
                 const uint32_t hi = pack_bf16x2(n2 * c0 + n0 * s0, n3 * c1 + n1 * s1);
                 if (warp == G) {
@@ -375,8 +379,8 @@ decode_attn_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ q_read
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[gq][i] = 0.f;
     }
-    const bf16* kb = kb_w + l8 * 16;
-    const bf16* vb = vb_w + l8 * 16;
+    const bf16* kb = kb_w + (long long)ks * KD + l8 * 16;       // keys / values of the real tokens: cache rows [ks, pos]
+    const bf16* vb = vb_w + (long long)ks * KD + l8 * 16;
     uint4 nk[KPI][2], nv[KPI][2];
     auto load_kv = [&](int key0) {
 #pragma unroll
@@ -549,7 +553,7 @@ int k_kv_cache_store(const bf16* k_src, long long k_ld, const bf16* v_src, long 
 
 int k_decode_attn(const bf16* qkv, const bf16* q_ready, bf16* k_cache, bf16* v_cache, bf16* out, long long ld_out, const float* qw,
                   const float* kw, const float* cosT, const float* sinT, const int* pos, int B, int Hq, int Hkv, int max_seq, float eps,
-                  float scale, cudaStream_t st) {
+                  float scale, cudaStream_t st, const int* kv_start) {
     const float sl2 = scale * 1.4426950408889634f;
     dim3 grid(Hkv, B);
     const int G = Hq / Hkv;
@@ -558,7 +562,7 @@ int k_decode_attn(const bf16* qkv, const bf16* q_ready, bf16* k_cache, bf16* v_c
     const bool deep = (long long)B * Hkv <= 148;
 #define TA_DA_LAUNCH(GG, KK)                                                                                                     \
     TA_CHECK_CUDA(launch_pdl(decode_attn_kernel<GG, KK>, grid, DA_WARPS * 32, 0, st, qkv, q_ready, k_cache, v_cache, out, ld_out, qw, kw, \
-                             cosT, sinT, pos, Hq, Hkv, max_seq, eps, sl2))
+                             cosT, sinT, pos, Hq, Hkv, max_seq, eps, sl2, kv_start))
     if (G == 1) {
         if (deep) TA_DA_LAUNCH(1, 2); else TA_DA_LAUNCH(1, 1);
     } else {

@@ -219,7 +219,8 @@ __global__ void enc_rope_kernel(bf16* __restrict__ qkv, const float* __restrict_
 // =============================================================================================================
 __global__ void lm_qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ qk, const float* __restrict__ qw,
                                           const float* __restrict__ kw, const float* __restrict__ cosT,
-                                          const float* __restrict__ sinT, long long M, int S, int Hq, int Hkv, float eps) {
+                                          const float* __restrict__ sinT, long long M, int S, int Hq, int Hkv, float eps,
+                                          const int* __restrict__ pos_ids) {
     TA_PDL_ENTRY();
     // 8 lanes per (row, head): lane l8 owns dims [8 l8, +8) and [64 + 8 l8, +8) -- the RoPE pairs (d, d + 64) stay in one thread and every
     // access is a 16-byte vector (a warp covers 4 consecutive heads = 1 KB contiguous); 4-byte accesses ran at 40 % of the HBM rate
@@ -231,7 +232,8 @@ __global__ void lm_qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, bf16* __
     const long long it = live ? item : 0;
     const int h = (int)(it % heads);
     const long long row = it / heads;
-    const int pos = (int)(row % S);
+    // position ids are arange(S) (HF:qwen3:397-400) unless the caller supplies them (left-padded prompts in generate())
+    const int pos = pos_ids ? pos_ids[row] : (int)(row % S);
     const bf16* src = qkv + row * (long long)((Hq + 2 * Hkv) * HD) + (long long)h * HD + 8 * l8;
     const float* w = ((h < Hq) ? qw : kw) + 8 * l8;
     float a[8], b[8];
@@ -814,10 +816,11 @@ int k_enc_rope(bf16* qkv, const float* cosT, const float* sinT, long long rows, 
 }
 
 int k_lm_qknorm_rope_fwd(const bf16* qkv, bf16* qk, const float* qw, const float* kw, const float* cosT, const float* sinT,
-                         long long M, int S, int Hq, int Hkv, float eps, cudaStream_t st) {
+                         long long M, int S, int Hq, int Hkv, float eps, cudaStream_t st, const int* pos_ids) {
     const long long threads = M * (Hq + Hkv) * 8;      // 8 lanes per (row, head)
     if (threads == 0) return 0;
-    TA_KERNEL_LAUNCH(lm_qknorm_rope_fwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, qkv, qk, qw, kw, cosT, sinT, M, S, Hq, Hkv, eps);
+    TA_KERNEL_LAUNCH(lm_qknorm_rope_fwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, qkv, qk, qw, kw, cosT, sinT, M, S, Hq, Hkv, eps,
+                     pos_ids);
     return 0;
 }
 
@@ -961,7 +964,7 @@ TA_API int ta_enc_rope(void* qkv, const float* cosT, const float* sinT, long lon
 }
 TA_API int ta_lm_qknorm_rope_fwd(const void* qkv, void* qk, const float* qw, const float* kw, const float* cosT, const float* sinT,
                                  long long M, int S, int Hq, int Hkv, float eps, void* stream) {
-    return k_lm_qknorm_rope_fwd((const bf16*)qkv, (bf16*)qk, qw, kw, cosT, sinT, M, S, Hq, Hkv, eps, ST(stream));
+    return k_lm_qknorm_rope_fwd((const bf16*)qkv, (bf16*)qk, qw, kw, cosT, sinT, M, S, Hq, Hkv, eps, ST(stream), nullptr);
 }
 TA_API int ta_lm_qknorm_rope_bwd(const void* qkv, const float* dq, const void* dk, const void* dv, void* dqkv, const float* qw,
                                  const float* kw, const float* cosT, const float* sinT, long long M, int S, int Hq, int Hkv,

@@ -331,6 +331,7 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
     TA_REQUIRE(!(P && a->with_backward) || a->lora_grads, "LoRA backward needs the gradient pointer table");
     TA_REQUIRE(!a->k_cache || (a->v_cache && a->S <= a->cache_max_seq), "prefill: v_cache missing or S %d > cache_max_seq %d", a->S,
                a->cache_max_seq);
+    TA_REQUIRE(!(a->position_ids || a->kv_start) || !a->with_backward, "position_ids / kv_start (left-padded prompts) are forward-only");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int B = a->B, S = a->S, nl = a->n_labelled;
     const long long M = (long long)B * S;
@@ -370,13 +371,19 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
         }
         RUN(gemm(b.xn, ldX, Lw[TA_LM_WQKV], ldX, M, QKV, D + P, TA_EPI_BF16, qkv, QKV, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
         RUN(k_lm_qknorm_rope_fwd(qkv, qk, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W], w->rope_cos, w->rope_sin,
-                                 M, S, Hq, Hkv, w->eps, st));
+                                 M, S, Hq, Hkv, w->eps, st, a->position_ids));
         if (a->k_cache) {   // prefill of generate(): keep the prompt's roped keys and values for the decode steps
             const long long per_layer = (long long)B * a->cache_max_seq * KD;
             RUN(k_kv_cache_store(qk + QD, QK, qkv + QK, QKV, reinterpret_cast<bf16*>(a->k_cache) + l * per_layer,
                                  reinterpret_cast<bf16*>(a->v_cache) + l * per_layer, B, S, KD, a->cache_max_seq, st));
         }
-        RUN(ta_attn_fwd(qk, qk + QD, qkv + QK, att, lse, B, S, Hq, Hkv, hd, QK, QK, QKV, ldAtt, 1, scale, st));
+        if (a->kv_start) {   // left-padded prompts: the tcgen05 kernel masks the padding keys per sequence
+            int handled = 0;
+            RUN(k_attn_tc_fwd(qk, qk + QD, qkv + QK, att, lse, B, S, Hq, Hkv, hd, QK, QK, QKV, ldAtt, 1, scale, st, &handled, a->kv_start));
+            TA_REQUIRE(handled, "left-padded attention: shape not supported by the tcgen05 kernel");
+        } else {
+            RUN(ta_attn_fwd(qk, qk + QD, qkv + QK, att, lse, B, S, Hq, Hkv, hd, QK, QK, QKV, ldAtt, 1, scale, st));
+        }
         if (P) RUN(plain(att, ldAtt, Lw[TA_LM_LORA_A_O], QD, M, P, QD, att + QD, ldAtt, st));
         RUN(gemm(att, ldAtt, Lw[TA_LM_WO], ldAtt, M, D, QD + P, TA_EPI_F32_RESID, x_mid, D, nullptr, x_in, nullptr, 0, nullptr, 0, st));
         RUN(k_rmsnorm_f32(x_mid, (const float*)Lw[TA_LM_LN2_W], b.xn, nullptr, M, D, w->eps, st, ldX));
@@ -544,7 +551,7 @@ TA_API int ta_lm_decode_workspace_bytes(const ta_lm_weights* w, int B, long long
 
 TA_API int ta_lm_decode_step(const ta_lm_weights* w, const long long* ids, int* pos, int pos_host, void* k_cache, void* v_cache,
                              int cache_max_seq, int B, void* workspace, long long workspace_bytes, void* logits, long long* next_ids,
-                             void* stream) {
+                             const int* kv_start, void* stream) {
     TA_REQUIRE(w && ids && pos && k_cache && v_cache && workspace && logits && next_ids, "ta_lm_decode_step: null pointer");
     TA_REQUIRE(w->head_dim == 128, "Qwen3 path: head_dim must be 128");
     TA_REQUIRE(B >= 1 && B <= 32, "decode step: batch %d not in [1, 32]", B);
@@ -574,7 +581,7 @@ TA_API int ta_lm_decode_step(const ta_lm_weights* w, const long long* ids, int* 
         if (P) RUN(k_skinny_gemm(b.xn, ldX, (const bf16*)Lw[TA_LM_LORA_A_QKV], D, B, P, D, TA_SKINNY_BF16, b.xn + D, ldX, nullptr, st));
         RUN(k_skinny_gemm(b.xn, ldX, (const bf16*)Lw[TA_LM_WQKV], ldX, B, QKV, D + P, TA_SKINNY_BF16, b.qkv, QKV, nullptr, st));
         RUN(k_decode_attn(b.qkv, nullptr, kc, vc, b.att, ldAtt, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W], w->rope_cos,
-                          w->rope_sin, pos, B, Hq, Hkv, cache_max_seq, w->eps, scale, st));
+                          w->rope_sin, pos, B, Hq, Hkv, cache_max_seq, w->eps, scale, st, kv_start));
         if (P) RUN(k_skinny_gemm(b.att, ldAtt, (const bf16*)Lw[TA_LM_LORA_A_O], QD, B, P, QD, TA_SKINNY_BF16, b.att + QD, ldAtt, nullptr, st));
         // o_proj / down_proj have only dim / 16 = 64 row tiles: split K so that the whole GPU streams; the partial sums are
         // reduced (fixed order), rounded to bf16 and added to the residual by the RMSNorm kernel that follows anyway

@@ -10,7 +10,7 @@ int k_rmsnorm_f32_bwd(const bf16* dy, const float* x, const float* w, float* dx,
                       float eps, int accumulate, cudaStream_t st, bf16* dx_bf16 = nullptr, long long ld_b = 0);
 int k_enc_rope(bf16* qkv, const float* cosT, const float* sinT, long long rows, int S, int H, int hd, int rd, cudaStream_t st);
 int k_lm_qknorm_rope_fwd(const bf16* qkv, bf16* qk, const float* qw, const float* kw, const float* cosT, const float* sinT,
-                         long long M, int S, int Hq, int Hkv, float eps, cudaStream_t st);
+                         long long M, int S, int Hq, int Hkv, float eps, cudaStream_t st, const int* pos_ids = nullptr);
 int k_lm_qknorm_rope_bwd(const bf16* qkv, const float* dq, const bf16* dk, const bf16* dv, bf16* dqkv, const float* qw,
                          const float* kw, const float* cosT, const float* sinT, long long M, int S, int Hq, int Hkv, float eps,
                          cudaStream_t st, long long ld_out = 0);
@@ -46,7 +46,7 @@ int k_kv_cache_store(const bf16* k_src, long long k_ld, const bf16* v_src, long 
                      int KD, int max_seq, cudaStream_t st);
 int k_decode_attn(const bf16* qkv, const bf16* q_ready, bf16* k_cache, bf16* v_cache, bf16* out, long long ld_out, const float* qw,
                   const float* kw, const float* cosT, const float* sinT, const int* pos, int B, int Hq, int Hkv, int max_seq, float eps,
-                  float scale, cudaStream_t st);
+                  float scale, cudaStream_t st, const int* kv_start = nullptr);
 int k_decode_resid_rmsnorm(const float* x_in, const float* partial, int n_splits, int rows, float* x_out, const float* w, bf16* y, int D,
                            float eps, long long ldy, cudaStream_t st);
 int k_embed_rows(const long long* ids, const float* table, float* out, int B, int D, long long vocab, cudaStream_t st);
@@ -58,7 +58,7 @@ int k_make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long
 // tcgen05 attention forward (attn_tc.cu): *handled = 1 when the shape is supported and the kernel was launched
 int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* lse, int B, int S, int Hq, int Hkv, int head_dim,
                   long long q_rs, long long k_rs, long long v_rs, long long o_rs, int causal, float scale, cudaStream_t st,
-                  int* handled);
+                  int* handled, const int* kv_start = nullptr);
 int k_attn_tc_enabled();
 int k_attn_tc_bwd(const bf16* q, const bf16* k, const bf16* v, const bf16* d_o, const float* lse, const float* dsum, float* dq_acc,
                   bf16* dk, bf16* dv, int B, int S, int Hq, int Hkv, int head_dim, long long q_rs, long long k_rs, long long v_rs,

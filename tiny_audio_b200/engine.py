@@ -577,13 +577,16 @@ class HotPath:
                             None, None, 0,
                             C.cast(self.lm.wgrad_table, C.POINTER(L.P)) if train_lm else None,
                             L.ptr(self.lm.wgrad["embed"]) if train_lm else None, L.ptr(self.lm.wgrad["fnorm"]) if train_lm else None,
-                            L.ptr(input_ids) if train_lm else None, d.audio_token_id)
+                            L.ptr(input_ids) if train_lm else None, d.audio_token_id, None, None)
         L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
         return loss, demb, row_loss
 
-    def lm_hidden(self, emb: torch.Tensor, B: int, S: int, kv_cache=None) -> torch.Tensor:
+    def lm_hidden(self, emb: torch.Tensor, B: int, S: int, kv_cache=None, position_ids: Optional[torch.Tensor] = None,
+                  kv_start: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Forward-only decoder pass; returns the last layer's output before the final norm, fp32 [B*S, dim].
-        `kv_cache` = (k, v, max_seq): the prompt's roped keys / values of every layer are stored in rows [0, S) (prefill)."""
+        `kv_cache` = (k, v, max_seq): the prompt's roped keys / values of every layer are stored in rows [0, S) (prefill).
+        `position_ids` int32 [B, S] / `kv_start` int32 [B]: left-padded prompts (rotary positions counted from each sequence's first
+        real token; padding keys masked)."""
         d = self.dims
         n = C.c_longlong()
         L.check(self.lib.ta_lm_workspace_bytes(C.byref(self.lm.c), B, S, 0, 0, C.byref(n)))
@@ -592,7 +595,7 @@ class HotPath:
         hid = self.ws.typed("final_hidden", (B * S, d.lm_dim), F32)
         kc, vc, ms = kv_cache if kv_cache is not None else (None, None, 0)
         args = L.LmStepArgs(B, S, 0, 0, L.ptr(emb), None, None, 1.0, L.ptr(loss), None, None, L.ptr(ws), n.value, L.ptr(hid), None,
-                            L.ptr(kc), L.ptr(vc), ms, None, None, None, None, 0)
+                            L.ptr(kc), L.ptr(vc), ms, None, None, None, None, 0, L.ptr(position_ids), L.ptr(kv_start))
         L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
         return hid
 
@@ -602,10 +605,10 @@ class HotPath:
         shape = (d.lm_layers, B, max_seq, d.lm_kv_heads * d.lm_head_dim)
         return (torch.empty(shape, device=self.device, dtype=BF16), torch.empty(shape, device=self.device, dtype=BF16), max_seq)
 
-    def _decode_graph(self, fed, nxt_buf, pos_dev, cache, logits, pos_host: int):
+    def _decode_graph(self, fed, nxt_buf, pos_dev, cache, logits, pos_host: int, kv_start=None):
         """CUDA graph of one decode step over the given (persistent, workspace-owned) buffers; cached per pointer set."""
         key = (int(fed.numel()), cache[2], fed.data_ptr(), nxt_buf.data_ptr(), pos_dev.data_ptr(), cache[0].data_ptr(),
-               cache[1].data_ptr(), logits.data_ptr())
+               cache[1].data_ptr(), logits.data_ptr(), kv_start.data_ptr() if kv_start is not None else 0)
         graphs = self.__dict__.setdefault("_decode_graphs", {})
         g = graphs.get(key)
         if g is None:
@@ -613,14 +616,14 @@ class HotPath:
             L.check(self.lib.ta_lm_decode_workspace_bytes(C.byref(self.lm.c), int(fed.numel()), C.byref(n)))
             self.ws.get("lm_decode", n.value)                  # allocate outside the capture
             keep = pos_dev.clone()
-            self.decode_step(fed, pos_dev, pos_host, cache, logits, nxt_buf)      # eager warm-up (module load) before the capture;
+            self.decode_step(fed, pos_dev, pos_host, cache, logits, nxt_buf, kv_start)      # eager warm-up (module load) before the capture;
             pos_dev.copy_(keep)                                                   # its cache row is rewritten by the real step
             g = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 with torch.cuda.graph(g, stream=side):
-                    self.decode_step(fed, pos_dev, pos_host, cache, logits, nxt_buf)
+                    self.decode_step(fed, pos_dev, pos_host, cache, logits, nxt_buf, kv_start)
             torch.cuda.current_stream().wait_stream(side)
             pos_dev.copy_(keep)
             graphs.clear()                                     # one live graph per HotPath is enough
@@ -628,16 +631,17 @@ class HotPath:
         return g
 
     def decode_step(self, ids: torch.Tensor, pos_dev: torch.Tensor, pos_host: int, kv_cache, logits: torch.Tensor,
-                    next_ids: torch.Tensor):
-        """One KV-cache decode step (ta_lm_decode_step): feeds ids [B] at position *pos_dev, writes the bf16 logits
-        [B, vocab_pad] and next_ids [B] = argmax, and advances *pos_dev on the device."""
+                    next_ids: torch.Tensor, kv_start: Optional[torch.Tensor] = None):
+        """One KV-cache decode step (ta_lm_decode_step): feeds ids [B] at cache row *pos_dev, writes the bf16 logits
+        [B, vocab_pad] and next_ids [B] = argmax, and advances *pos_dev on the device.  kv_start int32 [B]: first real cache row
+        of each left-padded sequence."""
         B = int(ids.numel())
         kc, vc, ms = kv_cache
         n = C.c_longlong()
         L.check(self.lib.ta_lm_decode_workspace_bytes(C.byref(self.lm.c), B, C.byref(n)))
         ws = self.ws.get("lm_decode", n.value)
         L.check(self.lib.ta_lm_decode_step(C.byref(self.lm.c), L.ptr(ids), L.ptr(pos_dev), int(pos_host), L.ptr(kc), L.ptr(vc), ms, B,
-                                           L.ptr(ws), n.value, L.ptr(logits), L.ptr(next_ids), L.stream_ptr()))
+                                           L.ptr(ws), n.value, L.ptr(logits), L.ptr(next_ids), L.ptr(kv_start), L.stream_ptr()))
 
     def logits_rows(self, hidden: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
         """final norm + tied lm_head on the given flat token rows -> bf16 logits [n_rows, vocab] (padding sliced off)."""
@@ -680,7 +684,7 @@ class HotPath:
 
     @torch.no_grad()
     def greedy_generate(self, *, input_ids: torch.Tensor, proj_params=None, waveform=None, input_features=None, audio_embeds=None,
-                        audio_token_counts=None, max_new_tokens: int = 16, eos_token_ids=(), pad_token_id: int = 0,
+                        audio_token_counts=None, attention_mask=None, max_new_tokens: int = 16, eos_token_ids=(), pad_token_id: int = 0,
                         use_cache: bool = True, sync_every: int = 8, use_graph: bool = False):
         """Greedy decoding (num_beams=1, do_sample=False: the reference's generation defaults, asr_config.py:103-111).
         use_cache=True (default, like HF generate): one prefill pass that also fills the KV cache, then one
@@ -688,7 +692,11 @@ class HotPath:
         over the whole sequence for every new token (kept as the A/B reference of the cache path).  use_graph: the decode
         step (~200 PDL launches, position counter on the device) is captured once per buffer set in a CUDA graph and replayed
         (-5 % per token; off by default because the capture costs more than it saves on short transcripts).
-        All prompts in the batch have the same length (equal-length clips); batches larger than 32 sequences fall back to use_cache=False."""
+
+        Ragged prompts (asr_modeling.py:587-640 -> HF generate with attention_mask): `attention_mask` [B, S0] marks LEFT-padded
+        prompts; rotary positions are counted from each sequence's first real token (HF: cumsum(mask) - 1), padding keys are never
+        attended to, and per-sample `audio_token_counts` place each clip's own number of audio embeddings.  Batches larger than
+        32 sequences (the decode kernels' row limit) are decoded in chunks of 32."""
         d = self.dims
         ids = input_ids.to(device=self.device, dtype=torch.int64).contiguous()
         B = ids.shape[0]
@@ -701,10 +709,31 @@ class HotPath:
         if audio_token_counts is None:
             audio_token_counts = (ids == d.audio_token_id).sum(-1)
         counts = audio_token_counts.to(device=self.device, dtype=torch.int64).contiguous()
+        kv_start = pos_ids = None
+        if attention_mask is not None:
+            am = attention_mask.to("cpu", torch.int64)
+            if tuple(am.shape) != tuple(ids.shape):
+                raise L.TinyAudioB200Error(f"attention_mask {tuple(am.shape)} does not match input_ids {tuple(ids.shape)}")
+            if bool((am[:, 1:] < am[:, :-1]).any()):
+                raise L.TinyAudioB200Error("generate(): prompts must be LEFT-padded (attention_mask 0...01...1), as HF generate requires "
+                                           "for decoder-only models; right-padded prompts would continue after the padding")
+            if bool((am == 0).any()):
+                kv_start = (am == 0).sum(-1).to(torch.int32).to(self.device)
+                pos_ids = (am.cumsum(-1) - 1).clamp_(min=0).to(torch.int32).to(self.device).contiguous()
+        if B > 32 and use_cache and max_new_tokens > 0:      # the skinny decode kernels hold <= 32 rows: decode in chunks
+            outs = []
+            for lo in range(0, B, 32):
+                sl = slice(lo, min(B, lo + 32))
+                outs.append(self.greedy_generate(input_ids=ids[sl], audio_embeds=audio.view(B, n_a, d.lm_dim)[sl], audio_token_counts=counts[sl],
+                                                 attention_mask=(attention_mask[sl] if attention_mask is not None else None),
+                                                 max_new_tokens=max_new_tokens, eos_token_ids=eos_token_ids, pad_token_id=pad_token_id,
+                                                 use_cache=True, sync_every=sync_every, use_graph=use_graph))
+            T = max(o.shape[1] for o in outs)      # a chunk that finished early is padded: same as running on after every eos
+            return torch.cat([torch.nn.functional.pad(o, (0, T - o.shape[1]), value=pad_token_id) for o in outs], 0)
         eos = torch.tensor(list(eos_token_ids), device=self.device, dtype=torch.int64)
         done = torch.zeros(B, dtype=torch.bool, device=self.device)
         out = []
-        if use_cache and B <= 32 and max_new_tokens > 0:
+        if use_cache and max_new_tokens > 0:
             S0 = ids.shape[1]
             if S0 + max_new_tokens > d.lm_max_pos:
                 raise L.TinyAudioB200Error(f"prompt {S0} + {max_new_tokens} new tokens exceed the rotary table ({d.lm_max_pos})")
@@ -712,7 +741,7 @@ class HotPath:
             kv_shape = (d.lm_layers, B, max_seq, d.lm_kv_heads * d.lm_head_dim)
             cache = (self.ws.typed("kv_cache_k", kv_shape, BF16), self.ws.typed("kv_cache_v", kv_shape, BF16), max_seq)
             emb, _ = self.embed_scatter(ids, counts, audio, n_a)
-            hid = self.lm_hidden(emb, B, S0, kv_cache=cache)
+            hid = self.lm_hidden(emb, B, S0, kv_cache=cache, position_ids=pos_ids, kv_start=kv_start)
             last = torch.arange(B, device=self.device, dtype=torch.int32) * S0 + (S0 - 1)
             nxt = self.logits_rows(hid, last).float().argmax(-1)
             pos_dev = self.ws.typed("decode_pos", (1,), torch.int32)
@@ -720,7 +749,7 @@ class HotPath:
             logits = self.ws.typed("decode_logits", (B, self.lm.vocab_pad), BF16)
             fed = self.ws.typed("decode_ids_in", (B,), torch.int64)
             nxt_buf = self.ws.typed("decode_ids_out", (B,), torch.int64)
-            step = self._decode_graph(fed, nxt_buf, pos_dev, cache, logits, S0) if (use_graph and max_new_tokens >= 8) else None
+            step = self._decode_graph(fed, nxt_buf, pos_dev, cache, logits, S0, kv_start) if (use_graph and max_new_tokens >= 8) else None
             flags = []                                                      # per step: have all sequences finished?
             for t in range(max_new_tokens):
                 nxt = torch.where(done, torch.full_like(nxt, pad_token_id), nxt)
@@ -736,7 +765,7 @@ class HotPath:
                 if step is not None:
                     step.replay()
                 else:
-                    self.decode_step(fed, pos_dev, S0 + t, cache, logits, nxt_buf)
+                    self.decode_step(fed, pos_dev, S0 + t, cache, logits, nxt_buf, kv_start)
                 nxt = nxt_buf.clone()
             res = torch.stack(out, dim=1)
             if flags:      # stop exactly where the token-by-token loop would have: the first step after which all are done
@@ -747,7 +776,7 @@ class HotPath:
         for _ in range(max_new_tokens):
             S = ids.shape[1]
             emb, _ = self.embed_scatter(ids, counts, audio, n_a)
-            hid = self.lm_hidden(emb, B, S)
+            hid = self.lm_hidden(emb, B, S, position_ids=pos_ids, kv_start=kv_start)
             last = torch.arange(B, device=self.device, dtype=torch.int32) * S + (S - 1)
             nxt = self.logits_rows(hid, last).float().argmax(-1)
             nxt = torch.where(done, torch.full_like(nxt, pad_token_id), nxt)
@@ -755,6 +784,8 @@ class HotPath:
             if eos.numel():
                 done = done | (nxt[:, None] == eos[None, :]).any(-1)
             ids = torch.cat([ids, nxt[:, None]], dim=1).contiguous()
+            if pos_ids is not None:
+                pos_ids = torch.cat([pos_ids, pos_ids[:, -1:] + 1], dim=1).contiguous()
             if bool(done.all()):
                 break
         return torch.stack(out, dim=1)

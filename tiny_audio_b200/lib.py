@@ -62,7 +62,8 @@ class LmStepArgs(C.Structure):
                 ("inputs_embeds", P), ("label_rows", P), ("label_targets", P), ("inv_num_items", c_float),
                 ("loss", P), ("row_loss", P), ("d_inputs_embeds", P), ("workspace", P), ("workspace_bytes", c_ll),
                 ("final_hidden", P), ("lora_grads", C.POINTER(P)), ("k_cache", P), ("v_cache", P), ("cache_max_seq", c_int),
-                ("lm_grads", C.POINTER(P)), ("d_embed", P), ("d_final_norm", P), ("input_ids", P), ("audio_token_id", c_ll)]
+                ("lm_grads", C.POINTER(P)), ("d_embed", P), ("d_final_norm", P), ("input_ids", P), ("audio_token_id", c_ll),
+                ("position_ids", P), ("kv_start", P)]
 
 
 _SIGS = {
@@ -123,7 +124,7 @@ _SIGS = {
     "ta_decode_attn": ([P, P, P, P, c_ll, P, c_int, c_int, c_int, c_int, c_float, P], c_int),
     "ta_argmax_rows": ([P, c_ll, c_int, c_int, P, P], c_int),
     "ta_lm_decode_workspace_bytes": ([C.POINTER(LmWeights), c_int, C.POINTER(c_ll)], c_int),
-    "ta_lm_decode_step": ([C.POINTER(LmWeights), P, P, c_int, P, P, c_int, c_int, P, c_ll, P, P, P], c_int),
+    "ta_lm_decode_step": ([C.POINTER(LmWeights), P, P, c_int, P, P, c_int, c_int, P, c_ll, P, P, P, P], c_int),
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["ta_last_error_string"])
