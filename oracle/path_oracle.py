@@ -551,9 +551,12 @@ def init_lora_weights(cfg: PathConfig, seed: int = 55, rank: int = 8, alpha: flo
 
 
 def lm_forward(w: Dict[str, Tensor], inputs_embeds: Tensor, cfg: PathConfig = FULL,
-               attention_mask: Optional[Tensor] = None, lora=None) -> Tensor:
+               attention_mask: Optional[Tensor] = None, lora=None, position_ids: Optional[Tensor] = None) -> Tensor:
     """inputs_embeds (B, S, D) -> final-norm hidden states (B, S, D).  `lora`: adapters of init_lora_weights
-    (peft semantics: y = W x + alpha/r * B(A(x)), dropout 0; tiny_audio/asr_modeling.py:289-301)."""
+    (peft semantics: y = W x + alpha/r * B(A(x)), dropout 0; tiny_audio/asr_modeling.py:289-301).
+    `position_ids` (B, S): rotary positions (HF generate with a left-padded attention_mask: cumsum(mask) - 1); default arange(S).
+    A query row whose keys are ALL masked (a left-padding row) keeps plain causal attention, so that it stays finite -- its output
+    is never used (HF's sdpa path un-masks such rows for the same reason)."""
     def lin(x, name, layer, proj):
         y = F.linear(x, w[name])
         if lora is not None and proj in lora["A"]:
@@ -563,11 +566,17 @@ def lm_forward(w: Dict[str, Tensor], inputs_embeds: Tensor, cfg: PathConfig = FU
     x = inputs_embeds
     B, S, D = x.shape
     Hq, Hkv, hd = cfg.lm_heads, cfg.lm_kv_heads, cfg.lm_head_dim
-    cos, sin = _rope_tables(S, hd, cfg.lm_rope_theta)
+    if position_ids is None:
+        cos, sin = _rope_tables(S, hd, cfg.lm_rope_theta)
+    else:
+        tc, ts = _rope_tables(int(position_ids.max()) + 1, hd, cfg.lm_rope_theta)
+        cos, sin = tc[position_ids][:, None], ts[position_ids][:, None]          # (B, 1, S, hd)
     causal = torch.ones(S, S, dtype=torch.bool).tril()
     mask = causal[None, None]
     if attention_mask is not None:
         mask = mask & attention_mask.bool()[:, None, None, :]
+        dead = ~mask.any(-1, keepdim=True)                                        # padding query rows
+        mask = mask | (dead & causal[None, None])
     for i in range(cfg.lm_layers):
         p = f"model.layers.{i}."
         h = rms_norm(x, w[p + "input_layernorm.weight"], cfg.lm_eps)
@@ -653,10 +662,12 @@ def model_forward(W, batch: Dict[str, Tensor], cfg: PathConfig = FULL, num_items
 
 
 @torch.no_grad()
-def greedy_generate(W, batch, cfg: PathConfig = FULL, max_new_tokens: int = 8):
+def greedy_generate(W, batch, cfg: PathConfig = FULL, max_new_tokens: int = 8, attention_mask: Optional[Tensor] = None):
     """Greedy ids by re-running the whole forward per token (reference: asr_modeling.py:562-646, greedy defaults).
-    Returns (ids [B, T_new], top-1 minus top-2 logit margin [B, T_new])."""
+    Returns (ids [B, T_new], top-1 minus top-2 logit margin [B, T_new]).  `attention_mask` (B, S0): LEFT-padded prompts (ragged
+    batches) -- HF generate masks the padding keys and counts rotary positions from each sequence's first real token."""
     ids = batch["input_ids"].clone()
+    am = attention_mask.clone() if attention_mask is not None else None
     counts = batch["audio_token_counts"]
     mel = batch["input_features"].float() if "input_features" in batch else log_mel(batch["waveform"], cfg)
     audio = projector_forward(W["projector"], encoder_forward(W["encoder"], mel, cfg), cfg)
@@ -665,13 +676,16 @@ def greedy_generate(W, batch, cfg: PathConfig = FULL, max_new_tokens: int = 8):
     for _ in range(max_new_tokens):
         emb = F.embedding(ids, W["lm"]["model.embed_tokens.weight"])
         emb = scatter_audio(emb, ids, packed, cfg.audio_token_id)
-        hid = lm_forward(W["lm"], emb, cfg)[:, -1]
+        pos = (am.cumsum(-1) - 1).clamp(min=0) if am is not None else None
+        hid = lm_forward(W["lm"], emb, cfg, attention_mask=am, position_ids=pos)[:, -1]
         logits = F.linear(hid, W["lm"]["lm_head.weight"])
         top = logits.topk(2, -1).values
         nxt = logits.argmax(-1)
         out.append(nxt)
         margins.append(top[:, 0] - top[:, 1])
         ids = torch.cat([ids, nxt[:, None]], 1)
+        if am is not None:
+            am = torch.cat([am, torch.ones_like(am[:, :1])], 1)
     return torch.stack(out, 1), torch.stack(margins, 1)
 
 

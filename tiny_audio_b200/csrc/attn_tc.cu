@@ -36,6 +36,20 @@ struct AttCfg {
     static constexpr int CTAS_PER_SM = (HD == 64) ? 2 : 1;
 };
 
+// fp32 pair -> packed bf16 pair on the INTEGER pipes (round half up: differs from cvt.rn only on exact ties).  The cvt instruction
+// (F2FP.BF16.F32.PACK_AB) executes on the XU pipe at 4 lanes per clock and SM sub-partition -- the same pipe MUFU.EX2 uses: ncu on
+// the encoder attention shows that pipe 85 % busy (sm__inst_executed_pipe_xu_realtime) with 128 EX2 + 64 F2FP per row and key tile,
+// i.e. the conversions take a third of the bottleneck resource.  Two adds and a byte permute cost three issue slots on idle pipes.
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+    const uint32_t a = __float_as_uint(lo) + 0x8000u, b = __float_as_uint(hi) + 0x8000u;
+    return __byte_perm(a, b, 0x7632);       // (b & 0xffff0000) | (a >> 16)
+}
+#ifndef TA_ATTN_PACK_XU
+#define PACK_P pack_bf16x2_alu
+#else
+#define PACK_P pack_bf16x2
+#endif
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -250,10 +264,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         l4[t & 3] += e[t];
                     }
                     uint4 u;
-                    u.x = pack_bf16x2(e[0], e[1]);
-                    u.y = pack_bf16x2(e[2], e[3]);
-                    u.z = pack_bf16x2(e[4], e[5]);
-                    u.w = pack_bf16x2(e[6], e[7]);
+                    u.x = PACK_P(e[0], e[1]);
+                    u.y = PACK_P(e[2], e[3]);
+                    u.z = PACK_P(e[4], e[5]);
+                    u.w = PACK_P(e[6], e[7]);
                     const int k16 = c * 4 + qd;
                     *reinterpret_cast<uint4*>(p_row + ((k16 ^ (r & 7)) << 4)) = u;
                 }
@@ -533,10 +547,10 @@ attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             l4[t & 3] += e[t];
                         }
                         uint4 u;
-                        u.x = pack_bf16x2(e[0], e[1]);
-                        u.y = pack_bf16x2(e[2], e[3]);
-                        u.z = pack_bf16x2(e[4], e[5]);
-                        u.w = pack_bf16x2(e[6], e[7]);
+                        u.x = PACK_P(e[0], e[1]);
+                        u.y = PACK_P(e[2], e[3]);
+                        u.z = PACK_P(e[4], e[5]);
+                        u.w = PACK_P(e[6], e[7]);
                         const int k16 = c * 4 + qd;                       // 16-byte chunk of the 256-byte P row
                         *reinterpret_cast<uint4*>(p_row + (k16 >> 3) * TILE16 + (((k16 & 7) ^ (r & 7)) << 4)) = u;
                     }
@@ -780,10 +794,10 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         l4[t & 3] += e[t];
                     }
                     uint4 u;
-                    u.x = pack_bf16x2(e[0], e[1]);
-                    u.y = pack_bf16x2(e[2], e[3]);
-                    u.z = pack_bf16x2(e[4], e[5]);
-                    u.w = pack_bf16x2(e[6], e[7]);
+                    u.x = PACK_P(e[0], e[1]);
+                    u.y = PACK_P(e[2], e[3]);
+                    u.z = PACK_P(e[4], e[5]);
+                    u.w = PACK_P(e[6], e[7]);
                     const int k16 = c * 4 + qd;                           // 16-byte chunk of my 128-byte half row
                     *reinterpret_cast<uint4*>(p_row + ((k16 ^ (r & 7)) << 4)) = u;
                 }
@@ -1138,10 +1152,10 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             l4[u & 3] += e[u];
                         }
                         uint4 pk;
-                        pk.x = pack_bf16x2(e[0], e[1]);
-                        pk.y = pack_bf16x2(e[2], e[3]);
-                        pk.z = pack_bf16x2(e[4], e[5]);
-                        pk.w = pack_bf16x2(e[6], e[7]);
+                        pk.x = PACK_P(e[0], e[1]);
+                        pk.y = PACK_P(e[2], e[3]);
+                        pk.z = PACK_P(e[4], e[5]);
+                        pk.w = PACK_P(e[6], e[7]);
                         const int k16 = c * 4 + qd;                       // 16-byte chunk of the 256-byte P row
                         if constexpr (P_TMEM) {
                             // keep the packed pairs in the (dead) S registers: columns [4 k16, +4) of my P row, stored 8 columns at a time
@@ -1246,7 +1260,7 @@ int g_attn_tc = 2;
 }  // namespace
 
 TA_API int ta_attn_set_tc(int on) {
-    g_attn_tc = (on < 0 || on > 10) ? 2 : on;
+    g_attn_tc = (on < 0 || on > 13) ? 2 : on;
     return 0;
 }
 int k_attn_tc_enabled() { return g_attn_tc; }
@@ -1281,6 +1295,9 @@ int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* l
         if (g_attn_tc == 8) return launch_attn_tc3<0, false, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 9) return launch_attn_tc3<0, true, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 10) return launch_attn_tc3<4, false, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+        if (g_attn_tc == 11) return launch_attn_tc1<64, false, 8>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);   // mode 2 + every 8th exp2 on the FMA pipe
+        if (g_attn_tc == 12) return launch_attn_tc3<8, false, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
+        if (g_attn_tc == 13) return launch_attn_tc3<8, false, false>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 5) return launch_attn_tc2<64>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 2) return launch_attn_tc1<64, false, 0>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         if (g_attn_tc == 3) return launch_attn_tc1<64, false, 4>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
