@@ -102,6 +102,8 @@ int ta_debug_set(int key, int value); /* profiling experiments only; never chang
 int ta_attn_set_tc(int mode); /* 0: mma.sync kernels; 1: tcgen05, two threads per query row; 2 (default): tcgen05, head_dim-64 forward with one
                                  thread per row (attn_tc.cu); 3 / 4: mode 2 with every 4th / 2nd exp2 evaluated on the FMA pipe (experiment);
                                  5: head_dim-64 forward as two independent 64-key streams per row (split-KV inside the CTA, 8 softmax warps) */
+/* diagnostic timeline of the persistent encoder-attention kernel (tools/attn_trace.py): buf int64 [3][steps][8] device memory, NULL = off */
+int ta_attn_set_trace(void* buf, int steps);
 int ta_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                 float* dsum_ws, float* dq_acc, void* dk, void* dv, int B, int S, int Hq, int Hkv, int head_dim,
                 long long q_rs, long long k_rs, long long v_rs, long long o_rs, long long do_rs, long long dq_rs,

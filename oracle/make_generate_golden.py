@@ -67,15 +67,18 @@ def to_bf16_bits(x: torch.Tensor) -> np.ndarray:
 
 
 @torch.no_grad()
-def last_hidden(W, cfg, ids, packed):
+def last_hidden(W, cfg, ids, packed, am=None):
     emb = F.embedding(ids, W["lm"]["model.embed_tokens.weight"])
     emb = po.scatter_audio(emb, ids, packed, cfg.audio_token_id)
-    return po.lm_forward(W["lm"], emb, cfg)[:, -1]
+    pos = (am.cumsum(-1) - 1).clamp(min=0) if am is not None else None
+    return po.lm_forward(W["lm"], emb, cfg, attention_mask=am, position_ids=pos)[:, -1]
 
 
 @torch.no_grad()
-def plant(cfg, W, batch, prompt):
-    c = CASE
+def plant(cfg, W, batch, prompt, case=None, attention_mask=None, lo_id=2000, hi_id=150000):
+    """`attention_mask`: left-padded prompts (ragged batches, oracle/make_ragged_generate_golden.py)."""
+    c = case or CASE
+    am = attention_mask.clone() if attention_mask is not None else None
     E = W["lm"]["model.embed_tokens.weight"]
     mel = po.log_mel(batch["waveform"], cfg)
     audio = po.projector_forward(W["projector"], po.encoder_forward(W["encoder"], mel, cfg), cfg)
@@ -88,12 +91,12 @@ def plant(cfg, W, batch, prompt):
     B = ids.shape[0]
     for t in range(c["new_tokens"]):
         t0 = time.time()
-        hid = last_hidden(W, cfg, ids, packed).double()            # [B, D]
+        hid = last_hidden(W, cfg, ids, packed, am).double()        # [B, D]
         for b in range(B):
             logits = (E.double() @ hid[b])
             top2 = logits.topk(2)
             while True:
-                r = int(rng.integers(2000, 150000))
+                r = int(rng.integers(lo_id, hi_id))
                 if r not in used:
                     break
             used.add(r)
@@ -116,6 +119,8 @@ def plant(cfg, W, batch, prompt):
         nxt = logits.argmax(-1)
         past.extend(hid[b] for b in range(B))
         ids = torch.cat([ids, nxt[:, None]], 1)
+        if am is not None:
+            am = torch.cat([am, torch.ones_like(am[:, :1])], 1)
         st = stats[-B:]
         print(f"step {t}: ids {nxt.tolist()}  alpha {min(a for a, _, _ in st):.2f}..{max(a for a, _, _ in st):.2f}  |row| "
               f"{max(n for _, n, _ in st):.3f}  inflation {max(i for _, _, i in st):.2f}  ({time.time() - t0:.1f}s)", flush=True)

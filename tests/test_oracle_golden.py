@@ -166,6 +166,25 @@ def test_oracle_reproduces_full_size_reference_generate_ids():
     assert bool(fx["ids_bf16_autocast_equal"])          # the reference's own bf16-autocast run produced the same ids
 
 
+def test_oracle_reproduces_ragged_reference_generate_ids():
+    """tests/golden/generate_ragged.npz: four clips of 1 / 2 / 1.5 / 2 s in one batch, LEFT-padded prompts, ids from the unmodified
+    reference's ASRModel.generate -> HF generate (oracle/make_ragged_generate_golden.py).  The oracle's restatement of HF's left-padding
+    semantics (rotary positions = cumsum(mask) - 1, padding keys masked) reproduces them, free-running."""
+    from oracle.make_generate_golden import apply_planted
+    from oracle.make_ragged_generate_golden import NEW_TOKENS, case_inputs
+    fx = np.load(os.path.join(GOLD, "generate_ragged.npz"))
+    cfg, W, batch = case_inputs(int(fx["seed"]))
+    assert np.array_equal(batch["input_ids"].numpy(), fx["input_ids"]) and np.array_equal(batch["attention_mask"].numpy(), fx["attention_mask"])
+    assert np.array_equal(batch["audio_token_counts"].numpy(), fx["audio_token_counts"]) and len(set(fx["audio_token_counts"].tolist())) >= 3
+    assert (fx["attention_mask"] == 0).any() and not (np.diff(fx["attention_mask"], axis=1) < 0).any()      # ragged, left-padded
+    apply_planted(W, fx["planted_tokens"], fx["planted_rows_bf16"])
+    ids, margins = po.greedy_generate(W, batch, cfg, max_new_tokens=NEW_TOKENS, attention_mask=batch["attention_mask"])
+    assert np.array_equal(ids.numpy(), fx["ids"]) and float(margins.min()) >= 0.5 and bool(fx["ids_bf16_autocast_equal"])
+    # without the mask / position handling the padded sequences decode differently: the fixture really exercises it
+    wrong, _ = po.greedy_generate(W, batch, cfg, max_new_tokens=2)
+    assert not np.array_equal(wrong.numpy(), fx["ids"][:, :2])
+
+
 def test_oracle_equals_recorded_reference_on_the_bench_parity_sample():
     """bench.py's CE-loss parity sample (full-size model, seed-1 weights, 1 x 30 s clip): the oracle's fp32 loss against the value the
     unmodified reference produced (tests/golden/reference_precision_gap.json), which also records the reference's own bf16-autocast

@@ -489,7 +489,9 @@ class ASRModel(PreTrainedModel, GenerationMixin):
         """Greedy transcription ids (reference: asr_modeling.py:562-646 with num_beams=1, do_sample=False).  Returns only the
         newly generated tokens, like the reference (it strips the prompt, :644-646).  `input_ids` holds the prompt with its <audio>
         placeholders; when it is None the prompt is built from the tokenizer's chat template exactly as the reference does
-        (:588-617; needs `audio_attention_mask` to size the placeholder run)."""
+        (:588-617; needs `audio_attention_mask` to size the placeholder run).  Ragged batches: `audio_attention_mask` gives every clip
+        its own audio token count and `attention_mask` marks LEFT-padded prompts (rotary positions start at each sequence's first real
+        token, padding keys are masked) -- ids equal to the reference's HF generate (tests/golden/generate_ragged.npz)."""
         if input_features is None:
             raise ValueError("input_features required for generation")
         if input_ids is None:
@@ -544,6 +546,12 @@ class ASRModel(PreTrainedModel, GenerationMixin):
         _prepare_decoder(self, hot, self._decoder_tensors())      # current LoRA operands / re-packed decoder after optimiser steps
         use_cache = kwargs.get("use_cache")
         kw["use_cache"] = bool(getattr(self.config, "use_cache", True) if use_cache is None else use_cache)
+        if audio_token_counts is None and audio_attention_mask is not None:
+            # per-sample audio token counts from the frame mask, as the reference derives them (asr_modeling.py:587-589): clips of
+            # different lengths in one batch place different numbers of audio embeddings
+            enc_len = self._compute_encoder_output_lengths(audio_attention_mask)
+            audio_token_counts = self.projector.get_output_length(enc_len).to(torch.long)
+        kw["attention_mask"] = attention_mask      # left-padded prompts of a ragged batch (HF generate semantics)
         return hot.greedy_generate(input_ids=input_ids, proj_params=params, audio_token_counts=audio_token_counts,
                                    max_new_tokens=int(max_new_tokens or gc.max_new_tokens or 128),
                                    eos_token_ids=[e for e in eos if e is not None], pad_token_id=int(gc.pad_token_id or 0), **kw)

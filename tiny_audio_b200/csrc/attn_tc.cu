@@ -913,7 +913,7 @@ int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
 //     warp 9 = MMA issuer; TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384);
 //   * the O / l epilogue of an item runs in the slack the other group's exp2 phase leaves.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int ATT3_THREADS = 320;
+constexpr int ATT3_THREADS = 352;      // 8 softmax warps, TMA producer, one MMA-issuing warp per query group
 
 template <bool P_TMEM>
 struct Att3Cfg {
@@ -952,10 +952,17 @@ template <int POLY, bool TURNS, bool P_TMEM>
 __global__ void __launch_bounds__(ATT3_THREADS, 1)
 attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int Hq, int Hkv,
-                    long long o_rs, float scale_log2, int n_items, int n_qpairs) {
+                    long long o_rs, float scale_log2, int n_items, int n_qpairs, long long* __restrict__ trace, int trace_steps) {
     TA_PDL_ENTRY();
     constexpr int HD = 64;
     using C = Att3Cfg<P_TMEM>;
+    // optional timeline of CTA 0 (ta_attn_set_trace): SM clock at the pipeline events of softmax warps 0 (group A) and 4 (group B) and
+    // of the MMA thread, 8 slots per (kv tile) step -- tools/attn_trace.py turns it into per-phase durations
+    const bool tr_on = trace != nullptr && blockIdx.x == 0;
+#define TR(slot, step, ev)                                                                   \
+    do {                                                                                     \
+        if (tr_on && (threadIdx.x & 31) == 0 && (step) < trace_steps) trace[((slot) * trace_steps + (step)) * 8 + (ev)] = clock64(); \
+    } while (0)
     extern __shared__ __align__(1024) uint8_t smem_al[];
     uint8_t* smem = smem_al;
     if (smem_u32(smem) & 1023u) __trap();                 // SWIZZLE_128B tiles need 1024-byte alignment
@@ -987,7 +994,7 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tma_prefetch_desc(&tmV);
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&q_full[i], 1);
-                mbar_init(&q_empty[i], 1);
+                mbar_init(&q_empty[i], 2);                 // both groups' MMA threads are done with the item's Q
                 mbar_init(&s_full[i], 1);
                 mbar_init(&s_empty[i], 4);
                 mbar_init(&p_full[i], 4);
@@ -996,7 +1003,7 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             for (int s = 0; s < C::KV_SLOTS; ++s) {
                 mbar_init(&kv_full[s], 1);
-                mbar_init(&kv_empty[s], 1);
+                mbar_init(&kv_empty[s], 2);                // both groups have consumed the tile
             }
             for (int i = 0; i < 8; ++i) mbar_init(&turn[i], 1);
             mbar_fence_init();
@@ -1030,12 +1037,17 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
             }
         }
-    } else if (warp == 9) {
-        // ------------------------------------------------ MMA issuer ------------------------------------------------
+    } else if (warp >= 9) {
+        // ------------------------------------------------ MMA issuers ------------------------------------------------
+        // one issuing thread PER GROUP (warp 9: group A, warp 10: group B).  A single in-order thread serving both groups
+        // (S_A, PV_A, S_B, PV_B, ...) couples them: the timeline (tools/attn_trace.py) showed PV_A issued 1 700 clk after A's P was
+        // ready because the thread was parked on B's barrier, and every softmax warp waiting ~700 clk for an S product that takes
+        // 120 clk once issued.
+        const int g = warp - 9;
         if (lane == 0 && total > 0) {
             constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
             constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
-            auto issue_s = [&](int g, int t) {             // S_g(t) = Q_g K(t)^T
+            auto issue_s = [&](int t) {                    // S_g(t) = Q_g K(t)^T
                 const int it = t / n_kv, j = t - it * n_kv, buf = it & 1;
                 const int ld = 2 * t, slot = ld % C::KV_SLOTS;
                 if (j == 0) mbar_wait(&q_full[buf], ((uint32_t)it >> 1) & 1u);
@@ -1048,12 +1060,10 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     umma_f16(tmem_base + C::S_COL0 + g * 128, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(k_addr + k * 32),
                              idesc_s, k != 0 ? 1u : 0u);
                 umma_commit(&s_full[g]);
-                if (g == 1) {
-                    umma_commit(&kv_empty[slot]);
-                    if (j == n_kv - 1) umma_commit(&q_empty[buf]);
-                }
+                umma_commit(&kv_empty[slot]);
+                if (j == n_kv - 1) umma_commit(&q_empty[buf]);
             };
-            auto issue_pv = [&](int g, int t) {            // O_g (+)= P_g(t) V(t)
+            auto issue_pv = [&](int t) {                   // O_g (+)= P_g(t) V(t)
                 const int it = t / n_kv, j = t - it * n_kv;
                 const int ld = 2 * t + 1, slot = ld % C::KV_SLOTS;
                 mbar_wait(&p_full[g], (uint32_t)t & 1u);
@@ -1076,15 +1086,15 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     }
                 }
                 umma_commit(&pv_done[g]);
-                if (g == 1) umma_commit(&kv_empty[slot]);
+                umma_commit(&kv_empty[slot]);
             };
-            issue_s(0, 0);
-            issue_s(1, 0);
+            issue_s(0);
             for (int t = 0; t < total; ++t) {
-                if (t + 1 < total) issue_s(0, t + 1);
-                issue_pv(0, t);
-                if (t + 1 < total) issue_s(1, t + 1);
-                issue_pv(1, t);
+                if (g == 0) TR(2, t, 0);
+                if (t + 1 < total) issue_s(t + 1);
+                if (g == 0) TR(2, t, 1);
+                issue_pv(t);
+                if (g == 0) TR(2, t, 2);
             }
         }
     } else {
@@ -1104,13 +1114,16 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int row_base = b * S, q0 = qp * 2 * BQ + g * BQ;
             float m_ref = -INFINITY, l_sum = 0.f;
             for (int j = 0; j < n_kv; ++j, ++t) {
+                if (q == 0) TR(g, t, 0);
                 mbar_wait(&s_full[g], (uint32_t)t & 1u);
                 tc_fence_after();
+                if (q == 0) TR(g, t, 1);
                 const int lim = min(S - j * BKV - 1, 127);  // my columns e = 0..127 are real (unmasked) keys iff e <= lim
                 uint32_t v[4][32];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, v[c]);
                 tmem_ld_wait();
+                if (q == 0) TR(g, t, 2);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_empty[g]);    // S is in registers: the MMA warp may issue my next S product now
@@ -1131,12 +1144,15 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const float m_new = grow ? mx : m_ref;
                 const float alpha = (grow && j > 0) ? ex2_approx(m_ref - m_new) : 1.0f;
                 m_ref = m_new;
+                if (q == 0) TR(g, t, 3);
                 if (j > 0) {
                     mbar_wait(&pv_done[g], (uint32_t)(t - 1) & 1u);     // PV of my previous tile has consumed P and updated O
                     tc_fence_after();
                 }
+                if (q == 0) TR(g, t, 4);
                 // ---- TURNS: my turn on this sub-partition's SFUs (group A starts; then strictly alternating with warp q of the other group) ----
                 if constexpr (TURNS) mbar_wait(my_turn, g == 0 ? (((uint32_t)t & 1u) ^ 1u) : ((uint32_t)t & 1u));
+                if (q == 0) TR(g, t, 5);
                 float l4[4] = {0.f, 0.f, 0.f, 0.f};
                 const float neg_m = -m_ref;
 #pragma unroll
@@ -1189,6 +1205,7 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
                 l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
                 if constexpr (P_TMEM) tmem_st_wait();
+                if (q == 0) TR(g, t, 6);
                 tc_fence_before();
                 if constexpr (!P_TMEM) fence_proxy_async_smem();
                 __syncwarp();
@@ -1224,10 +1241,14 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
     }
 
+#undef TR
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
+
+long long* g_attn_trace = nullptr;
+int g_attn_trace_steps = 0;
 
 template <int POLY, bool TURNS, bool P_TMEM>
 int launch_attn_tc3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* o, float* lse, int B, int S, int Hq,
@@ -1248,7 +1269,7 @@ int launch_attn_tc3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
     TA_REQUIRE(n_items < (1LL << 30), "attention: too many work items");
     const int grid = (int)((n_items < n_sm) ? n_items : n_sm);
     TA_KERNEL_LAUNCH(kern, grid, ATT3_THREADS, C::SMEM, st, tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f, (int)n_items,
-                     n_qpairs);
+                     n_qpairs, g_attn_trace, g_attn_trace_steps);
     return 0;
 }
 
@@ -1258,6 +1279,14 @@ int launch_attn_tc3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
 int g_attn_tc = 2;
 
 }  // namespace
+
+// diagnostic: the persistent encoder-attention kernel (modes 6+) records the SM clock at its pipeline events for CTA 0 into
+// buf [3 slots (softmax A, softmax B, MMA thread)][steps][8] (int64, device memory; NULL switches it off)
+TA_API int ta_attn_set_trace(void* buf, int steps) {
+    g_attn_trace = reinterpret_cast<long long*>(buf);
+    g_attn_trace_steps = buf ? steps : 0;
+    return 0;
+}
 
 TA_API int ta_attn_set_tc(int on) {
     g_attn_tc = (on < 0 || on > 13) ? 2 : on;

@@ -81,6 +81,7 @@ _SIGS = {
     "ta_mel_to_conv1_im2col": ([P, c_int, c_int, P, P], c_int),
     "ta_attn_fwd": ([P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_int, c_float, P], c_int),
     "ta_attn_set_tc": ([c_int], c_int),
+    "ta_attn_set_trace": ([P, c_int], c_int),
     "ta_debug_set": ([c_int, c_int], c_int),
     "ta_attn_bwd": ([P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
                      c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_int, c_float, P], c_int),
