@@ -146,7 +146,7 @@ def ref_attn(q, k, v, causal, scale):
     return (torch.softmax(s, -1) @ vf).transpose(1, 2), lse
 
 
-@pytest.mark.parametrize("tc", [1, 0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13])
+@pytest.mark.parametrize("tc", [1, 0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16])
 @pytest.mark.parametrize("B,S,Hq,Hkv,hd,causal", [(2, 200, 4, 4, 64, False), (1, 1500, 20, 20, 64, False), (3, 128, 2, 2, 64, False),
                                                    (5, 50, 3, 3, 64, False), (9, 700, 20, 20, 64, False),
                                                    (2, 77, 4, 2, 128, True), (3, 464, 16, 8, 128, True), (2, 300, 4, 4, 64, True),

@@ -36,15 +36,15 @@ struct AttCfg {
     static constexpr int CTAS_PER_SM = (HD == 64) ? 2 : 1;
 };
 
-// fp32 pair -> packed bf16 pair on the INTEGER pipes (round half up: differs from cvt.rn only on exact ties).  The cvt instruction
-// (F2FP.BF16.F32.PACK_AB) executes on the XU pipe at 4 lanes per clock and SM sub-partition -- the same pipe MUFU.EX2 uses: ncu on
-// the encoder attention shows that pipe 85 % busy (sm__inst_executed_pipe_xu_realtime) with 128 EX2 + 64 F2FP per row and key tile,
-// i.e. the conversions take a third of the bottleneck resource.  Two adds and a byte permute cost three issue slots on idle pipes.
+// fp32 pair -> packed bf16 pair on the integer pipes (round half up).  Experiment (-DTA_ATTN_PACK_ALU): ncu's
+// sm__inst_executed_pipe_xu_realtime (85 %) suggested that cvt.rn.bf16x2.f32 (F2FP) shares the XU pipe with MUFU.EX2; the
+// micro-benchmark tools/ubench/sfu4.cu says otherwise -- EX2 issues once per 8.0 clk and sub-partition with or without one F2FP per
+// two EX2 -- and the kernel got SLOWER with the integer pack (0.589 -> 0.621 ms: three issue slots instead of one).  Default: cvt.
 __device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
     const uint32_t a = __float_as_uint(lo) + 0x8000u, b = __float_as_uint(hi) + 0x8000u;
     return __byte_perm(a, b, 0x7632);       // (b & 0xffff0000) | (a >> 16)
 }
-#ifndef TA_ATTN_PACK_XU
+#ifdef TA_ATTN_PACK_ALU
 #define PACK_P pack_bf16x2_alu
 #else
 #define PACK_P pack_bf16x2
@@ -1273,6 +1273,269 @@ int launch_attn_tc3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant "64-key tiles, three CTAs per SM" (encoder shape, head_dim 64, non-causal).
+//
+// What the measurements of this round say (tools/ubench/sfu4.cu, tools/attn_trace.py, ncu):
+//   * MUFU.EX2 issues once per 8.0 clk and SM sub-partition = 16 exp2 / clk / SM, and that is the kernel's floor: 1024 clk per
+//     128 x 128 score tile;  cvt.rn.bf16x2 is free next to it;
+//   * one softmax warp alone runs its exp2 phase at ~11.7 clk per EX2, two warps of a sub-partition together at ~8.8 (91 % of the
+//     pipe) -- but every warp also spends ~1 100 clk per tile NOT issuing exp2 (TMEM load, row max, waiting for its S / PV products
+//     and for the barrier wake-ups), and with two softmax warps per sub-partition nothing fills the SFUs meanwhile: 8.2 of 16
+//     exp2 / clk / SM, whatever the arrangement (two CTAs, one persistent CTA with two query tiles, strict turns, P in TMEM).
+// So: THREE softmax warps per sub-partition.  Tensor memory (512 columns) and registers (64 K) do not allow a third 128-column S
+// tile, hence 64-key tiles: S 64 + O 64 columns and 64 fp32 scores per thread -> 112 registers, 64 KB of shared memory
+// (Q 16 K, four 8 KB K / V tiles, P 16 K) and 128 TMEM columns per CTA, three CTAs per SM.
+//   warps 0-3 softmax (thread = query row = TMEM lane), warp 4 TMA producer + TMEM allocator, warp 5 MMA issuer.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int BKV5 = 64;
+constexpr int TILE8 = BKV5 * 64 * 2;       // one K or V tile: 64 keys x 64 bf16
+struct Att5Cfg {
+    static constexpr int KV_SLOTS = 4;
+    static constexpr int KV_OFF = TILE16;                            // after Q (128 x 64 bf16)
+    static constexpr int P_OFF = KV_OFF + KV_SLOTS * TILE8;
+    static constexpr int BAR_OFF = P_OFF + TILE16;                   // P: 128 x 64 bf16 = one SWIZZLE_128B tile
+    static constexpr int SMEM = BAR_OFF + 128;
+    static constexpr int TMEM_COLS = 128;
+};
+
+template <int POLY>
+__global__ void __launch_bounds__(ATT1_THREADS, 3)
+attn_tc_fwd5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int Hq, int Hkv,
+                    long long o_rs, float scale_log2) {
+    TA_PDL_ENTRY();
+    constexpr int HD = 64;
+    using C = Att5Cfg;
+    extern __shared__ __align__(1024) uint8_t smem_al[];
+    uint8_t* smem = smem_al;
+    if (smem_u32(smem) & 1023u) __trap();                 // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* sQ = smem;
+    uint8_t* sKV = smem + C::KV_OFF;
+    uint8_t* sP = smem + C::P_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = bars + 1 + C::KV_SLOTS;
+    uint64_t* s_full = bars + 1 + 2 * C::KV_SLOTS;
+    uint64_t* s_empty = s_full + 1;
+    uint64_t* p_full = s_full + 2;
+    uint64_t* pv_done = s_full + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int hk = h / (Hq / Hkv);
+    const int q0 = qt * BQ;
+    const int n_kv = (S + BKV5 - 1) / BKV5;
+    const int row_base = b * S;
+    constexpr uint32_t S5_COL = 0, O5_COL = 64;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+            mbar_init(q_full, 1);
+            for (int s = 0; s < C::KV_SLOTS; ++s) {
+                mbar_init(&kv_full[s], 1);
+                mbar_init(&kv_empty[s], 1);
+            }
+            mbar_init(s_full, 1);
+            mbar_init(s_empty, 4);
+            mbar_init(p_full, 4);
+            mbar_init(pv_done, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, TILE16);
+            tma_load_2d(sQ, &tmQ, q_full, h * HD, row_base + q0);
+            for (int i = 0; i < 2 * n_kv; ++i) {
+                const int slot = i % C::KV_SLOTS;
+                mbar_wait(&kv_empty[slot], (((uint32_t)i / C::KV_SLOTS) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&kv_full[slot], TILE8);
+                tma_load_2d(sKV + slot * TILE8, (i & 1) ? &tmV : &tmK, &kv_full[slot], hk * HD, row_base + (i >> 1) * BKV5);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV5);
+            constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
+            const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+            auto issue_s = [&](int j) {
+                const int i = 2 * j, slot = i % C::KV_SLOTS;
+                mbar_wait(&kv_full[slot], ((uint32_t)i / C::KV_SLOTS) & 1u);
+                mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sKV + slot * TILE8);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_f16(tmem_base + S5_COL, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s,
+                             k != 0 ? 1u : 0u);
+                umma_commit(s_full);
+                umma_commit(&kv_empty[slot]);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) issue_s(j + 1);
+                const int i = 2 * j + 1, slot = i % C::KV_SLOTS;
+                mbar_wait(p_full, (uint32_t)j & 1u);
+                mbar_wait(&kv_full[slot], ((uint32_t)i / C::KV_SLOTS) & 1u);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(sKV + slot * TILE8);
+#pragma unroll
+                for (int k = 0; k < BKV5 / 16; ++k)
+                    umma_f16(tmem_base + O5_COL, umma_desc_sw128_kmajor(p_addr + k * 32), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE8), idesc_o,
+                             (j | k) != 0 ? 1u : 0u);
+                umma_commit(pv_done);
+                umma_commit(&kv_empty[slot]);
+            }
+        }
+    } else {
+        const int r = warp * 32 + lane;                     // query row of the tile = TMEM lane
+        const uint32_t t_s = tmem_base + ((uint32_t)(warp * 32) << 16) + S5_COL;
+        const uint32_t t_o = tmem_base + ((uint32_t)(warp * 32) << 16) + O5_COL;
+        float m_ref = -INFINITY, l_sum = 0.f;
+        uint8_t* p_row = sP + r * 128;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(s_full, (uint32_t)j & 1u);
+            tc_fence_after();
+            const int lim = min(S - j * BKV5 - 1, BKV5 - 1);      // my columns e = 0..63 are real (unmasked) keys iff e <= lim
+            uint32_t v[2][32];
+            tmem_ld_32x32(t_s, v[0]);
+            tmem_ld_32x32(t_s + 32, v[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);            // S_j is in registers: the MMA warp may issue S_{j+1} now
+            if (lim < BKV5 - 1) {                           // last tile only: warp-uniform
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i > lim) v[c][i] = 0xff800000u;      // -inf
+            }
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[c][i]));
+            const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
+            const bool grow = mx > m_ref + 8.0f;
+            const float m_new = grow ? mx : m_ref;
+            const float alpha = (grow && j > 0) ? ex2_approx(m_ref - m_new) : 1.0f;
+            m_ref = m_new;
+            if (j > 0) {
+                mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);     // PV_{j-1} has consumed sP and finished updating O
+                tc_fence_after();
+            }
+            float l4[4] = {0.f, 0.f, 0.f, 0.f};
+            const float neg_m = -m_ref;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    float e[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float x = fmaf(__uint_as_float(v[c][8 * qd + u]), scale_log2, neg_m);
+                        if (POLY > 0 && (u % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) e[u] = ex2_poly(x);
+                        else e[u] = ex2_approx(x);                    // exp2(-inf) = 0 for masked columns
+                        l4[u & 3] += e[u];
+                    }
+                    uint4 pk;
+                    pk.x = PACK_P(e[0], e[1]);
+                    pk.y = PACK_P(e[2], e[3]);
+                    pk.z = PACK_P(e[4], e[5]);
+                    pk.w = PACK_P(e[6], e[7]);
+                    const int k16 = c * 4 + qd;                       // 16-byte chunk of the 128-byte P row
+                    *reinterpret_cast<uint4*>(p_row + ((k16 ^ (r & 7)) << 4)) = pk;
+                }
+            }
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {             // lazy rescale of O (rare)
+#pragma unroll 1
+                for (int c = 0; c < HD / 32; ++c) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(t_o + c * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st_32x32(t_o + c * 32, o);
+                }
+                tmem_st_wait();
+                l_sum *= alpha;
+            }
+            l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(pv_done, (uint32_t)(n_kv - 1) & 1u);
+        tc_fence_after();
+        const int row = q0 + r;
+        const float inv = 1.0f / l_sum;
+        bf16* orow = O + ((long long)row_base + row) * o_rs + (long long)h * HD;
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_o + c * 32, o);
+            tmem_ld_wait();
+            if (row < S) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(o[8 * qd + 0]) * inv, __uint_as_float(o[8 * qd + 1]) * inv);
+                    u.y = pack_bf16x2(__uint_as_float(o[8 * qd + 2]) * inv, __uint_as_float(o[8 * qd + 3]) * inv);
+                    u.z = pack_bf16x2(__uint_as_float(o[8 * qd + 4]) * inv, __uint_as_float(o[8 * qd + 5]) * inv);
+                    u.w = pack_bf16x2(__uint_as_float(o[8 * qd + 6]) * inv, __uint_as_float(o[8 * qd + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + qd * 8) = u;
+                }
+            }
+        }
+        if (LSE && row < S) LSE[((long long)b * Hq + h) * S + row] = (m_ref + log2f(l_sum)) * 0.69314718055994531f;
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int POLY>
+int launch_attn_tc5(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* lse, int B, int S, int Hq, int Hkv, long long q_rs,
+                    long long k_rs, long long v_rs, long long o_rs, float scale, cudaStream_t st) {
+    using C = Att5Cfg;
+    auto kern = attn_tc_fwd5_kernel<POLY>;
+    static bool done = false;
+    if (!done) {
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        done = true;
+    }
+    CUtensorMap tq, tk, tv;                                  // K / V boxes hold 64 rows here
+    const long long rows = (long long)B * S;
+    int rc = k_make_tensor_map_2d(&tq, q, rows, (long long)Hq * 64, q_rs, BQ);
+    if (rc) return rc;
+    rc = k_make_tensor_map_2d(&tk, k, rows, (long long)Hkv * 64, k_rs, BKV5);
+    if (rc) return rc;
+    rc = k_make_tensor_map_2d(&tv, v, rows, (long long)Hkv * 64, v_rs, BKV5);
+    if (rc) return rc;
+    dim3 grid((S + BQ - 1) / BQ, Hq, B);
+    TA_KERNEL_LAUNCH(kern, grid, ATT1_THREADS, C::SMEM, st, tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f);
+    return 0;
+}
+
 // 0: mma.sync; 1: tcgen05, 2 threads per row everywhere; 2 (default): head_dim-64 non-causal runs the one-thread-per-row variant
 // (0.590 vs 0.632 ms per encoder layer at B=32, S=1500); 3 / 4: that variant with every 4th / 2nd exp2 on the FMA pipe -- slower
 // (0.68 / 0.75 ms): with two softmax warps per sub-partition the kernel is issue/latency-bound, not MUFU-bound (profiles/).
@@ -1289,7 +1552,7 @@ TA_API int ta_attn_set_trace(void* buf, int steps) {
 }
 
 TA_API int ta_attn_set_tc(int on) {
-    g_attn_tc = (on < 0 || on > 13) ? 2 : on;
+    g_attn_tc = (on < 0 || on > 16) ? 2 : on;
     return 0;
 }
 int k_attn_tc_enabled() { return g_attn_tc; }
@@ -1316,6 +1579,11 @@ int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* l
     rc = k_make_tensor_map_2d(&tv, v, rows, (long long)Hkv * head_dim, v_rs, BKV);
     if (rc) return rc;
     *handled = 1;
+    if (head_dim == 64 && !causal && (g_attn_tc == 14 || g_attn_tc == 15 || g_attn_tc == 16)) {      // 64-key tiles, three CTAs per SM
+        if (g_attn_tc == 14) return launch_attn_tc5<0>(q, k, v, o, lse, B, S, Hq, Hkv, q_rs, k_rs, v_rs, o_rs, scale, st);
+        if (g_attn_tc == 15) return launch_attn_tc5<8>(q, k, v, o, lse, B, S, Hq, Hkv, q_rs, k_rs, v_rs, o_rs, scale, st);
+        return launch_attn_tc5<4>(q, k, v, o, lse, B, S, Hq, Hkv, q_rs, k_rs, v_rs, o_rs, scale, st);
+    }
     if (head_dim == 64 && !causal && g_attn_tc >= 2) {
         // persistent two-tile kernel: 6 = strict SFU turns, P through shared memory; 7 = free-running groups, P through shared memory;
         // 8 = free-running, P in tensor memory; 9 = turns + P in tensor memory; 10 = 8 with every 4th exp2 on the FMA pipe
