@@ -194,13 +194,22 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait with a suspend-time hint: the waiting thread is parked by the hardware (and woken when the phase completes) instead of
-// spinning through SYNCS / BRA / YIELD, which would steal issue slots from the compute warps of the same SM sub-partition
-// (ncu on the encoder attention: 30 % of all executed warp instructions were such spins without the hint).
+// Waiting on an mbarrier.  TA_MBAR_WAIT_MODE (compile time; A/B builds through `make VARIANT=... EXTRA=-DTA_MBAR_WAIT_MODE=n`):
+//   0: try_wait with a suspend-time hint -- the waiting thread is parked by the hardware instead of spinning through SYNCS / BRA,
+//      which would steal issue slots from the compute warps of the same SM sub-partition (ncu on the encoder attention, round 1:
+//      30 % of all executed warp instructions were such spins without the hint);
+//   1: try_wait without a hint (the system-dependent default time limit, then the loop re-issues it);
+//   2: test_wait in a tight loop (never parks).
+// Round 2's kernel timeline (tools/attn_trace.py) measured ~1 000 clk between an arrive and the parked waiter's next instruction
+// in mode 0 -- on the critical path of every (softmax -> MMA -> softmax) hand-over.
 #ifndef TA_MBAR_SUSPEND_HINT
 #define TA_MBAR_SUSPEND_HINT 0x989680
 #endif
+#ifndef TA_MBAR_WAIT_MODE
+#define TA_MBAR_WAIT_MODE 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if TA_MBAR_WAIT_MODE == 0
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -212,6 +221,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity), "r"(TA_MBAR_SUSPEND_HINT)
         : "memory");
+#elif TA_MBAR_WAIT_MODE == 1
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+#else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+#endif
 }
 
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
