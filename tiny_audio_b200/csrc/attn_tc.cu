@@ -1043,10 +1043,14 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // (S_A, PV_A, S_B, PV_B, ...) couples them: the timeline (tools/attn_trace.py) showed PV_A issued 1 700 clk after A's P was
         // ready because the thread was parked on B's barrier, and every softmax warp waiting ~700 clk for an S product that takes
         // 120 clk once issued.
-        const int g = warp - 9;
-        if (lane == 0 && total > 0) {
+        const int g = __shfl_sync(0xffffffffu, warp - 9, 0);
+        if (total > 0) {
+            // whole warp, warp-uniform operands, one elected lane issues (see the 64-key kernel below: ~95 clk per MMA issue otherwise)
             constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
             constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const bool leader = elect_one();
+            const uint64_t p_desc = umma_desc_sw128_kmajor(smem_u32(sP + g * 2 * TILE16));
             auto issue_s = [&](int t) {                    // S_g(t) = Q_g K(t)^T
                 const int it = t / n_kv, j = t - it * n_kv, buf = it & 1;
                 const int ld = 2 * t, slot = ld % C::KV_SLOTS;
@@ -1054,47 +1058,52 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 mbar_wait(&kv_full[slot], ((uint32_t)ld / C::KV_SLOTS) & 1u);
                 mbar_wait(&s_empty[g], ((uint32_t)t & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t q_addr = smem_u32(sQ + buf * C::Q_ITEM + g * TILE16), k_addr = smem_u32(sKV + slot * TILE16);
+                const uint64_t q_desc = umma_desc_sw128_kmajor(smem_u32(sQ + buf * C::Q_ITEM + g * TILE16));
+                const uint64_t k_desc = umma_desc_sw128_kmajor(smem_u32(sKV + slot * TILE16));
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    umma_f16(tmem_base + C::S_COL0 + g * 128, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(k_addr + k * 32),
-                             idesc_s, k != 0 ? 1u : 0u);
-                umma_commit(&s_full[g]);
-                umma_commit(&kv_empty[slot]);
-                if (j == n_kv - 1) umma_commit(&q_empty[buf]);
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_f16(tb + C::S_COL0 + g * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                    umma_commit(&s_full[g]);
+                    umma_commit(&kv_empty[slot]);
+                    if (j == n_kv - 1) umma_commit(&q_empty[buf]);
+                }
+                __syncwarp();
             };
             auto issue_pv = [&](int t) {                   // O_g (+)= P_g(t) V(t)
                 const int it = t / n_kv, j = t - it * n_kv;
                 const int ld = 2 * t + 1, slot = ld % C::KV_SLOTS;
                 mbar_wait(&p_full[g], (uint32_t)t & 1u);
+                TR(8 + g, t, 3);
                 mbar_wait(&kv_full[slot], ((uint32_t)ld / C::KV_SLOTS) & 1u);
                 if (j == 0 && it > 0) mbar_wait(&o_free[g], ((uint32_t)(it - 1)) & 1u);   // the previous item's O has been read out
+                TR(8 + g, t, 4);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(sKV + slot * TILE16);
-                if constexpr (P_TMEM) {
+                const uint64_t v_desc = umma_desc_sw128_mnmajor(smem_u32(sKV + slot * TILE16), TILE16);
+                if (leader) {
+                    if constexpr (P_TMEM) {
 #pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k)      // 16 keys = 8 columns of packed bf16 pairs
-                        umma_f16_ts(tmem_base + C::O_COL0 + g * HD, tmem_base + C::P_COL0 + g * 64 + k * 8,
-                                    umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16), idesc_o, (j | k) != 0 ? 1u : 0u);
-                } else {
-                    const uint32_t p_addr = smem_u32(sP + g * 2 * TILE16);
+                        for (int k = 0; k < BKV / 16; ++k)      // 16 keys = 8 columns of packed bf16 pairs
+                            umma_f16_ts(tb + C::O_COL0 + g * HD, tb + C::P_COL0 + g * 64 + k * 8, v_desc + 128 * k, idesc_o,
+                                        (j | k) != 0 ? 1u : 0u);
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k) {
-                        const uint32_t pa = p_addr + (k >> 2) * TILE16 + (k & 3) * 32;
-                        umma_f16(tmem_base + C::O_COL0 + g * HD, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16),
-                                 idesc_o, (j | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BKV / 16; ++k)      // P tile = two 64-key SWIZZLE_128B sub-tiles, 32 bytes per 16 keys inside each
+                            umma_f16(tb + C::O_COL0 + g * HD, p_desc + (k >> 2) * (TILE16 >> 4) + (k & 3) * 2, v_desc + 128 * k, idesc_o,
+                                     (j | k) != 0 ? 1u : 0u);
                     }
+                    umma_commit(&pv_done[g]);
+                    umma_commit(&kv_empty[slot]);
                 }
-                umma_commit(&pv_done[g]);
-                umma_commit(&kv_empty[slot]);
+                __syncwarp();
             };
             issue_s(0);
             for (int t = 0; t < total; ++t) {
-                if (g == 0) TR(2, t, 0);
+                TR(8 + g, t, 0);
                 if (t + 1 < total) issue_s(t + 1);
-                if (g == 0) TR(2, t, 1);
+                TR(8 + g, t, 1);
                 issue_pv(t);
-                if (g == 0) TR(2, t, 2);
+                TR(8 + g, t, 2);
             }
         }
     } else {
@@ -1114,16 +1123,16 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int row_base = b * S, q0 = qp * 2 * BQ + g * BQ;
             float m_ref = -INFINITY, l_sum = 0.f;
             for (int j = 0; j < n_kv; ++j, ++t) {
-                if (q == 0) TR(g, t, 0);
+                TR(warp, t, 0);
                 mbar_wait(&s_full[g], (uint32_t)t & 1u);
                 tc_fence_after();
-                if (q == 0) TR(g, t, 1);
+                TR(warp, t, 1);
                 const int lim = min(S - j * BKV - 1, 127);  // my columns e = 0..127 are real (unmasked) keys iff e <= lim
                 uint32_t v[4][32];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, v[c]);
                 tmem_ld_wait();
-                if (q == 0) TR(g, t, 2);
+                TR(warp, t, 2);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_empty[g]);    // S is in registers: the MMA warp may issue my next S product now
@@ -1144,15 +1153,15 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const float m_new = grow ? mx : m_ref;
                 const float alpha = (grow && j > 0) ? ex2_approx(m_ref - m_new) : 1.0f;
                 m_ref = m_new;
-                if (q == 0) TR(g, t, 3);
+                TR(warp, t, 3);
                 if (j > 0) {
                     mbar_wait(&pv_done[g], (uint32_t)(t - 1) & 1u);     // PV of my previous tile has consumed P and updated O
                     tc_fence_after();
                 }
-                if (q == 0) TR(g, t, 4);
+                TR(warp, t, 4);
                 // ---- TURNS: my turn on this sub-partition's SFUs (group A starts; then strictly alternating with warp q of the other group) ----
                 if constexpr (TURNS) mbar_wait(my_turn, g == 0 ? (((uint32_t)t & 1u) ^ 1u) : ((uint32_t)t & 1u));
-                if (q == 0) TR(g, t, 5);
+                TR(warp, t, 5);
                 float l4[4] = {0.f, 0.f, 0.f, 0.f};
                 const float neg_m = -m_ref;
 #pragma unroll
@@ -1205,7 +1214,7 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
                 l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
                 if constexpr (P_TMEM) tmem_st_wait();
-                if (q == 0) TR(g, t, 6);
+                TR(warp, t, 6);
                 tc_fence_before();
                 if constexpr (!P_TMEM) fence_proxy_async_smem();
                 __syncwarp();
@@ -1367,39 +1376,47 @@ attn_tc_fwd5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV5);
-            constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
-            const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-            auto issue_s = [&](int j) {
-                const int i = 2 * j, slot = i % C::KV_SLOTS;
-                mbar_wait(&kv_full[slot], ((uint32_t)i / C::KV_SLOTS) & 1u);
-                mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t k_addr = smem_u32(sKV + slot * TILE8);
+        // The WHOLE warp walks the issue loop (warp-uniform control flow and operands); one elected lane executes the tcgen05
+        // instructions.  Inside an `if (lane == 0)` region ptxas cannot keep the descriptors in uniform registers and wraps every
+        // UTCHMMA into an ELECT / 4 x R2UR.BROADCAST / BRA.U.ANY loop: the kernel timeline (tools/attn_trace.py) showed ~95 clk per
+        // MMA *issue* -- 760 clk per key tile on the softmax -> PV -> softmax critical path, while an M128 N64 K16 MMA executes in 32.
+        constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV5);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const bool leader = elect_one();
+        const uint64_t q_desc = umma_desc_sw128_kmajor(smem_u32(sQ)), p_desc = umma_desc_sw128_kmajor(smem_u32(sP));
+        auto issue_s = [&](int j) {
+            const int i = 2 * j, slot = i % C::KV_SLOTS;
+            mbar_wait(&kv_full[slot], ((uint32_t)i / C::KV_SLOTS) & 1u);
+            mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
+            tc_fence_after();
+            const uint64_t k_desc = umma_desc_sw128_kmajor(smem_u32(sKV + slot * TILE8));
+            if (leader) {
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    umma_f16(tmem_base + S5_COL, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s,
-                             k != 0 ? 1u : 0u);
+                for (int k = 0; k < HD / 16; ++k)      // + 32 bytes (>> 4 = 2) per 16-wide k step
+                    umma_f16(tb + S5_COL, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
                 umma_commit(s_full);
                 umma_commit(&kv_empty[slot]);
-            };
-            mbar_wait(q_full, 0);
-            issue_s(0);
-            for (int j = 0; j < n_kv; ++j) {
-                if (j + 1 < n_kv) issue_s(j + 1);
-                const int i = 2 * j + 1, slot = i % C::KV_SLOTS;
-                mbar_wait(p_full, (uint32_t)j & 1u);
-                mbar_wait(&kv_full[slot], ((uint32_t)i / C::KV_SLOTS) & 1u);
-                tc_fence_after();
-                const uint32_t v_addr = smem_u32(sKV + slot * TILE8);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_s(0);
+        for (int j = 0; j < n_kv; ++j) {
+            if (j + 1 < n_kv) issue_s(j + 1);
+            const int i = 2 * j + 1, slot = i % C::KV_SLOTS;
+            mbar_wait(p_full, (uint32_t)j & 1u);
+            mbar_wait(&kv_full[slot], ((uint32_t)i / C::KV_SLOTS) & 1u);
+            tc_fence_after();
+            const uint64_t v_desc = umma_desc_sw128_mnmajor(smem_u32(sKV + slot * TILE8), TILE8);
+            if (leader) {
 #pragma unroll
-                for (int k = 0; k < BKV5 / 16; ++k)
-                    umma_f16(tmem_base + O5_COL, umma_desc_sw128_kmajor(p_addr + k * 32), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE8), idesc_o,
-                             (j | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < BKV5 / 16; ++k)    // P: + 32 bytes per 16 keys; V: + 16 rows x 128 B = 2048 bytes (>> 4 = 128)
+                    umma_f16(tb + O5_COL, p_desc + 2 * k, v_desc + 128 * k, idesc_o, (j | k) != 0 ? 1u : 0u);
                 umma_commit(pv_done);
                 umma_commit(&kv_empty[slot]);
             }
+            __syncwarp();
         }
     } else {
         const int r = warp * 32 + lane;                     // query row of the tile = TMEM lane
@@ -1544,7 +1561,7 @@ int g_attn_tc = 2;
 }  // namespace
 
 // diagnostic: the persistent encoder-attention kernel (modes 6+) records the SM clock at its pipeline events for CTA 0 into
-// buf [3 slots (softmax A, softmax B, MMA thread)][steps][8] (int64, device memory; NULL switches it off)
+// buf [10 slots: softmax warps 0-7 (group A = 0-3, B = 4-7), MMA threads of A and B][steps][8] (int64, device memory; NULL switches it off)
 TA_API int ta_attn_set_trace(void* buf, int steps) {
     g_attn_trace = reinterpret_cast<long long*>(buf);
     g_attn_trace_steps = buf ? steps : 0;
