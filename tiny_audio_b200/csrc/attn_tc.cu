@@ -151,9 +151,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     tma_load_2d(sKV + slot * C::TILE_BYTES + u * TILE16, (i & 1) ? &tmV : &tmK, &kv_full[slot], hk * HD + u * 64,
                                 row_base + j * BKV);
             }
-        } else if (warp == 1 && lane == 0) {
+        } else if (warp == 1) {
+            // whole warp, warp-uniform operands, one elected lane issues the tcgen05 instructions (an `if (lane == 0)` region costs
+            // ~100 clk of ELECT / R2UR.BROADCAST plumbing per UTCHMMA: tools/attn_trace.py)
             constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
             constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const bool issuer = elect_one();
             const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
             auto issue_s = [&](int j) {
                 const int i = 2 * j, slot = i % C::KV_SLOTS;
@@ -161,14 +165,17 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(sKV + slot * C::TILE_BYTES);
+                if (issuer) {
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) {
-                    const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
-                    umma_f16(tmem_base + S_COL, umma_desc_sw128_kmajor(q_addr + off), umma_desc_sw128_kmajor(k_addr + off), idesc_s,
-                             k != 0 ? 1u : 0u);
+                    for (int k = 0; k < HD / 16; ++k) {
+                        const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
+                        umma_f16(tb + S_COL, umma_desc_sw128_kmajor(q_addr + off), umma_desc_sw128_kmajor(k_addr + off), idesc_s,
+                                 k != 0 ? 1u : 0u);
+                    }
+                    umma_commit(s_full);
+                    umma_commit(&kv_empty[slot]);
                 }
-                umma_commit(s_full);
-                umma_commit(&kv_empty[slot]);
+                __syncwarp();
             };
             mbar_wait(q_full, 0);
             issue_s(0);
@@ -179,14 +186,17 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_wait(&kv_full[slot], (uint32_t)(i / C::KV_SLOTS) & 1u);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(sKV + slot * C::TILE_BYTES);
+                if (issuer) {
 #pragma unroll
-                for (int k = 0; k < BKV / 16; ++k) {
-                    const uint32_t pa = p_addr + (k >> 2) * TILE16 + (k & 3) * 32;
-                    umma_f16(tmem_base + O_COL, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16), idesc_o,
-                             (j | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BKV / 16; ++k) {
+                        const uint32_t pa = p_addr + (k >> 2) * TILE16 + (k & 3) * 32;
+                        umma_f16(tb + O_COL, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16), idesc_o,
+                                 (j | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(pv_done);
+                    umma_commit(&kv_empty[slot]);
                 }
-                umma_commit(pv_done);
-                umma_commit(&kv_empty[slot]);
+                __syncwarp();
             }
         }
     } else {
@@ -451,9 +461,11 @@ attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        {   // whole warp, warp-uniform operands, one elected lane issues (see attn_tc_fwd_kernel)
             constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
             constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const bool issuer = elect_one();
             const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
             auto issue_s = [&](int j) {
                 const int i = 2 * j, slot = i % C::KV_SLOTS;
@@ -461,14 +473,17 @@ attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(sKV + slot * C::TILE_BYTES);
+                if (issuer) {
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) {
-                    const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
-                    umma_f16(tmem_base + S_COL, umma_desc_sw128_kmajor(q_addr + off), umma_desc_sw128_kmajor(k_addr + off), idesc_s,
-                             k != 0 ? 1u : 0u);
+                    for (int k = 0; k < HD / 16; ++k) {
+                        const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
+                        umma_f16(tb + S_COL, umma_desc_sw128_kmajor(q_addr + off), umma_desc_sw128_kmajor(k_addr + off), idesc_s,
+                                 k != 0 ? 1u : 0u);
+                    }
+                    umma_commit(s_full);
+                    umma_commit(&kv_empty[slot]);
                 }
-                umma_commit(s_full);
-                umma_commit(&kv_empty[slot]);
+                __syncwarp();
             };
             mbar_wait(q_full, 0);
             issue_s(0);
@@ -479,14 +494,17 @@ attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 mbar_wait(&kv_full[slot], (uint32_t)(i / C::KV_SLOTS) & 1u);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(sKV + slot * C::TILE_BYTES);
+                if (issuer) {
 #pragma unroll
-                for (int k = 0; k < BKV / 16; ++k) {
-                    const uint32_t pa = p_addr + (k >> 2) * TILE16 + (k & 3) * 32;
-                    umma_f16(tmem_base + O_COL, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16), idesc_o,
-                             (j | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BKV / 16; ++k) {
+                        const uint32_t pa = p_addr + (k >> 2) * TILE16 + (k & 3) * 32;
+                        umma_f16(tb + O_COL, umma_desc_sw128_kmajor(pa), umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE16), idesc_o,
+                                 (j | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(pv_done);
+                    umma_commit(&kv_empty[slot]);
                 }
-                umma_commit(pv_done);
-                umma_commit(&kv_empty[slot]);
+                __syncwarp();
             }
         }
     } else {

@@ -123,10 +123,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp, warp-uniform operands, one elected lane issues: inside an `if (lane == 0)` region every UTCHMMA is wrapped into
+            // an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~100 clk of single-thread latency per MMA, tools/attn_trace.py) -- 40 MMAs per
+            // (query tile, key tile) here, against 64 clk of tensor-pipe time each
             constexpr uint32_t id_kk = umma_idesc_bf16(BT, BT);                              // A, B K-major
             constexpr uint32_t id_kmn = umma_idesc_bf16(BT, HD) | (1u << 16);                // B MN-major
             constexpr uint32_t id_mnmn = umma_idesc_bf16(BT, HD) | (1u << 15) | (1u << 16);  // A and B MN-major
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const bool issuer = elect_one();
             const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO), aP = smem_u32(sP),
                            adS = smem_u32(sdS);
             mbar_wait(kv_full, 0);
@@ -135,34 +139,40 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_wait(qdo_full, ph);
                 mbar_wait(dq_empty, ph ^ 1u);          // previous dQ tile has been read out of TMEM[0,128)
                 tc_fence_after();
+                if (issuer) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
-                    umma_f16(tmem_base + ST_COL, desc_k(aK + off), desc_k(aQ + off), id_kk, k != 0 ? 1u : 0u);
-                }
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
+                        umma_f16(tb + ST_COL, desc_k(aK + off), desc_k(aQ + off), id_kk, k != 0 ? 1u : 0u);
+                    }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
-                    umma_f16(tmem_base + DP_COL, desc_k(aV + off), desc_k(adO + off), id_kk, k != 0 ? 1u : 0u);
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t off = (k >> 2) * TILE16 + (k & 3) * 32;
+                        umma_f16(tb + DP_COL, desc_k(aV + off), desc_k(adO + off), id_kk, k != 0 ? 1u : 0u);
+                    }
+                    umma_commit(s_full);
                 }
-                umma_commit(s_full);
+                __syncwarp();
                 mbar_wait(pds_full, ph);
                 tc_fence_after();
+                if (issuer) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {      // contraction over the 128 queries, 16 per step
-                    const uint32_t offk = (k >> 2) * TILE16 + (k & 3) * 32;
-                    umma_f16(tmem_base + DV_COL, desc_k(aP + offk), desc_mn(adO + k * 2048), id_kmn, (it | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < 8; ++k) {      // contraction over the 128 queries, 16 per step
+                        const uint32_t offk = (k >> 2) * TILE16 + (k & 3) * 32;
+                        umma_f16(tb + DV_COL, desc_k(aP + offk), desc_mn(adO + k * 2048), id_kmn, (it | k) != 0 ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t offk = (k >> 2) * TILE16 + (k & 3) * 32;
+                        umma_f16(tb + DK_COL, desc_k(adS + offk), desc_mn(aQ + k * 2048), id_kmn, (it | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(qdo_empty);            // Q / dO tiles may be overwritten by the next iteration's TMA
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)        // contraction over the 128 keys
+                        umma_f16(tb + ST_COL, desc_mn(adS + k * 2048), desc_mn(aK + k * 2048), id_mnmn, k != 0 ? 1u : 0u);
+                    umma_commit(dq_full);
                 }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t offk = (k >> 2) * TILE16 + (k & 3) * 32;
-                    umma_f16(tmem_base + DK_COL, desc_k(adS + offk), desc_mn(aQ + k * 2048), id_kmn, (it | k) != 0 ? 1u : 0u);
-                }
-                umma_commit(qdo_empty);            // Q / dO tiles may be overwritten by the next iteration's TMA
-#pragma unroll
-                for (int k = 0; k < 8; ++k)        // contraction over the 128 keys
-                    umma_f16(tmem_base + ST_COL, desc_mn(adS + k * 2048), desc_mn(aK + k * 2048), id_mnmn, k != 0 ? 1u : 0u);
-                umma_commit(dq_full);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {

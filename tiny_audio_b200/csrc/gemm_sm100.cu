@@ -352,8 +352,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // whole warp, warp-uniform operands, one elected lane issues (see gemm2_kernel: an `if (lane == 0)` region costs ~100 clk of
+        // ELECT / R2UR.BROADCAST plumbing per UTCHMMA)
+        {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const bool issuer = elect_one();
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -361,22 +365,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                const uint32_t d_tmem = tb + (uint32_t)(as * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(smA + stage * C::A_BYTES);
-                    const uint32_t b0 = smem_u32(smB + stage * C::B_BYTES);
+                    const uint64_t ad0 = umma_desc_sw128_kmajor(smem_u32(smA + stage * C::A_BYTES));
+                    const uint64_t bd0 = umma_desc_sw128_kmajor(smem_u32(smB + stage * C::B_BYTES));
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t ad = umma_desc_sw128_kmajor(a0 + k * UMMA_K * 2);
-                        const uint64_t bd = umma_desc_sw128_kmajor(b0 + k * UMMA_K * 2);
-                        umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k)      // + 32 bytes (>> 4 = 2) per 16-wide k step
+                            umma_f16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit(&empty[stage]);
                     }
-                    umma_commit(&empty[stage]);
+                    __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[as]);
+                if (issuer) umma_commit(&tfull[as]);
+                __syncwarp();
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
             }
@@ -848,8 +853,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (leader && lane == 0) {
+        // The WHOLE warp walks the loop with warp-uniform operands and one elected lane executes the tcgen05 instructions: inside an
+        // `if (lane == 0)` region ptxas cannot keep the descriptors in uniform registers and wraps every UTCHMMA into an
+        // ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY loop (~20 instructions, ~100 clk of one thread's latency per MMA, measured on the
+        // attention kernels with tools/attn_trace.py) -- next to 128 clk of tensor-pipe time per 256 x 256 x 16 MMA that leaves the
+        // issuing thread, not the tensor pipe, as the pacing resource (ncu: tensor pipe 74.5 % active on the largest GEMM).
+        if (leader) {
             constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN) | (TN ? ((1u << 15) | (1u << 16)) : 0u);
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const bool issuer = elect_one();
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -859,22 +871,27 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const int kb1 = SPLITK ? min(num_kb, kb0 + kb_per) : num_kb;
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                const uint32_t d_tmem = tb + (uint32_t)(as * BN);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(smA + stage * C::A_BYTES);
                     const uint32_t b0 = smem_u32(smB + stage * C::B_BYTES);
+                    // descriptor of the first 16-wide k step; later steps add their byte offset >> 4 to the start-address field
+                    const uint64_t ad0 = TN ? umma_desc_sw128_mnmajor_g(a0, 8192) : umma_desc_sw128_kmajor(a0);
+                    const uint64_t bd0 = TN ? umma_desc_sw128_mnmajor_g(b0, 8192) : umma_desc_sw128_kmajor(b0);
+                    constexpr uint32_t kstep = (TN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t ad = TN ? umma_desc_sw128_mnmajor_g(a0 + k * UMMA_K * 128, 8192) : umma_desc_sw128_kmajor(a0 + k * UMMA_K * 2);
-                        const uint64_t bd = TN ? umma_desc_sw128_mnmajor_g(b0 + k * UMMA_K * 128, 8192) : umma_desc_sw128_kmajor(b0 + k * UMMA_K * 2);
-                        umma_f16_2sm(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_f16_2sm(d_tmem, ad0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(k * kstep), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+                        umma_commit_2sm(&empty[stage]);
                     }
-                    umma_commit_2sm(&empty[stage]);
+                    __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_2sm(&tfull[as]);
+                if (issuer) umma_commit_2sm(&tfull[as]);
+                __syncwarp();
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
             }
