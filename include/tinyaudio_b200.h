@@ -99,9 +99,11 @@ int ta_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
                 int head_dim, long long q_rs, long long k_rs, long long v_rs, long long o_rs, int causal, float scale,
                 void* stream);
 int ta_debug_set(int key, int value); /* profiling experiments only; never changes results when left at 0 */
-int ta_attn_set_tc(int mode); /* 0: mma.sync kernels; 1: tcgen05, two threads per query row; 2 (default): tcgen05, head_dim-64 forward with one
-                                 thread per row (attn_tc.cu); 3 / 4: mode 2 with every 4th / 2nd exp2 evaluated on the FMA pipe (experiment);
-                                 5: head_dim-64 forward as two independent 64-key streams per row (split-KV inside the CTA, 8 softmax warps) */
+int ta_attn_set_tc(int mode); /* forward-kernel selection.  0: mma.sync reference kernels (the ONLY way to reach them: with any other mode a shape
+                                 the tcgen05 kernels do not cover is an error, not a fallback); 1: tcgen05, two threads per query row;
+                                 14 (default): tcgen05, encoder shape (head_dim 64, non-causal) on 64-key tiles with three CTAs per SM, other
+                                 shapes as mode 1; 2-13, 15, 16: earlier / experimental encoder-shape kernels kept as A/B references
+                                 (csrc/attn_tc.cu lists them with their measured times) */
 /* diagnostic timeline of the persistent encoder-attention kernel (tools/attn_trace.py): buf int64 [3][steps][8] device memory, NULL = off */
 int ta_attn_set_trace(void* buf, int steps);
 int ta_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
@@ -156,6 +158,12 @@ int ta_frame_keep_mask(void* x /*bf16 [rows,D], in place*/, const float* keep /*
 /* a9. HF:loss/loss_utils.py:56-59 (shift labels by one, ignore_index -100) as device-side bookkeeping: ascending flat positions
  * p = b*S + s with labels[b, s+1] != -100, their targets, and the count -- replaces a labels.cpu() + nonzero() on the host when
  * the Trainer hands device-resident labels; the caller reads back the 4-byte count to size the lm_head product. */
+/* f2. GPU-side collation (scripts/train.py:324-348 assembles these on the CPU dataloader workers): row b = prefix | <audio> x counts[b] |
+ * middle | response_b | suffix | pad; labels = -100 except the response and the first suffix token; attention_mask marks the real tokens. */
+int ta_assemble_prompts(const long long* counts /*[B]*/, const long long* resp /*packed*/, const long long* resp_off /*[B+1]*/,
+                        const long long* prefix, int n_prefix, const long long* middle, int n_middle, const long long* suffix, int n_suffix,
+                        long long audio_id, long long pad_id, int B, int S, long long* ids /*[B,S]*/, long long* labels, long long* mask,
+                        void* stream);
 int ta_label_rows(const long long* labels /*[B,S]*/, int B, int S, int* rows /*[B*S]*/, int* targets /*[B*S]*/, int* count /*[1]*/,
                   void* stream);
 

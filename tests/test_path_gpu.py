@@ -755,6 +755,58 @@ def test_forward_surface_logits_text_only_inputs_embeds_and_device_labels(cuda):
         model()
 
 
+def test_device_prompt_assembly_matches_host_collation(cuda):
+    """f2 (GPU-side collation): ta_assemble_prompts builds input_ids / labels / attention_mask on the device from the per-clip audio
+    token counts and the packed response ids -- bit-exact against the host-side construction (tiny_audio_b200.synthetic.synthetic_batch:
+    the chat-template layout scripts/train.py:324-348 + trl's ChatML collator produce), equal-length and ragged; the per-clip counts are
+    the reference's integer arithmetic evaluated on the device; a train step on the device-built batch equals the host-built one."""
+    from tiny_audio_b200 import synthetic as syn
+    from tiny_audio_b200.asr_processing import DevicePromptAssembler
+    from tiny_audio_b200.synthetic import build_offline_model
+    cfg = po.small_config(enc_layers=1, lm_layers=1)
+    dims = PathDims.from_any(cfg.to_dict())
+    W = po.init_weights(cfg, seed=81)
+    model = build_offline_model(dims, device="cuda", enc_state=W["encoder"], lm_state=W["lm"], proj_state=W["projector"])
+    V = dims.vocab
+    tid = lambda t: t if t < V - 1 else t % (V - 1)
+    prefix = [tid(t) for t in (syn.IM_START, syn.USER, syn.NL)]
+    middle = [tid(t) for t in syn.PROMPT_TAIL + [syn.IM_END, syn.NL, syn.IM_START, syn.ASSISTANT, syn.NL] + syn.THINK_EMPTY]
+    suffix = [tid(t) for t in (syn.IM_END, syn.NL)]
+    pad = model.tokenizer.pad_token_id
+    asm = DevicePromptAssembler(prefix, middle, suffix, dims.audio_token_id, pad, projector=model.projector,
+                                encoder_conv_layers=model.config.encoder_conv_layers)
+    # counts: device arithmetic == host arithmetic for many clip lengths
+    lens = torch.tensor([16000, 16001, 31999, 32000, 40000, 159999, 160000, 479999, 480000, 1, 159, 160, 161, 640, 3199])
+    want = torch.tensor([syn.num_audio_tokens(int(n) if int(n) % 160 == 0 else (int(n) // 160 + 1) * 160, dims.hop, dims.proj_k) for n in lens])
+    assert torch.equal(asm.audio_token_counts(lens.cuda()).cpu(), want)
+    # equal-length batch: identical to the host collation
+    host = syn.synthetic_batch(dims, 3, 2.0, seed=4, response_len=9)
+    resp = [host["labels"][b][host["labels"][b] != -100][:-1].tolist() for b in range(3)]
+    dev = asm(host["audio_token_counts"].cuda(), resp)
+    for k in ("input_ids", "labels", "attention_mask"):
+        assert torch.equal(dev[k].cpu(), host[k]), k
+    # ragged: different audio token counts and response lengths, right padding
+    counts = torch.tensor([25, 12, 18, 25])
+    rag = [[tid(1000 + 7 * i + j) for j in range(n)] for i, n in enumerate((9, 3, 14, 1))]
+    out = asm(counts.cuda(), rag)
+    S = out["input_ids"].shape[1]
+    for b in range(4):
+        row = prefix + [dims.audio_token_id] * int(counts[b]) + middle + rag[b] + suffix
+        lab = [-100] * (len(row) - len(rag[b]) - len(suffix)) + rag[b] + [suffix[0]] + [-100] * (len(suffix) - 1)
+        n = len(row)
+        assert out["input_ids"][b, :n].tolist() == row and (out["input_ids"][b, n:] == pad).all()
+        assert out["labels"][b, :n].tolist() == lab and (out["labels"][b, n:] == -100).all()
+        assert int(out["attention_mask"][b].sum()) == n and bool((out["attention_mask"][b, :n] == 1).all())
+    assert S == max(len(prefix) + int(c) + len(middle) + len(r) + len(suffix) for c, r in zip(counts, rag))
+    # a train step on the device-built batch == on the host-built batch
+    model.train()
+    n_items = int((host["labels"] != -100).sum())
+    kw = dict(input_features=host["input_features"].cuda(), num_items_in_batch=n_items)
+    l_host = model(input_ids=host["input_ids"].cuda(), labels=host["labels"].cuda(), audio_token_counts=host["audio_token_counts"].cuda(), **kw).loss
+    l_dev = model(input_ids=dev["input_ids"], labels=dev["labels"], attention_mask=dev["attention_mask"], audio_token_counts=dev["audio_token_counts"], **kw).loss
+    assert abs(float(l_host) - float(l_dev)) < 1e-6 * abs(float(l_host))
+
+
 def test_generic_projector_routes_decoder_gradients(cuda):
     """a non-MLP projector (qformer) combined with LoRA adapters or an unfrozen decoder must still hand the decoder's
     trainable tensors their gradients (before: grad None -> the decoder silently never learned).  Loss and gradients vs the oracle."""

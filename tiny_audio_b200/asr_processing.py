@@ -134,3 +134,61 @@ try:
     transformers.AutoProcessor.register(ASRConfig, ASRProcessor, exist_ok=True)
 except Exception:
     pass
+
+
+class DevicePromptAssembler:
+    """GPU-side collation.  The reference's DataCollator (scripts/train.py:324-348) builds the chat prompt
+    of every sample on the CPU dataloader workers: `<audio>` x N_b placeholders inside the user turn, the transcript as the assistant
+    turn, labels masked outside the answer.  With the log-mel already on the GPU (WaveformFeatureExtractor), this moves the rest:
+    the per-clip audio token counts (conv-length formula + projector.get_output_length, integer arithmetic on the device) and the
+    assembly of input_ids / labels / attention_mask from the tokenised template pieces and the packed response ids
+    (ta_assemble_prompts), so a training batch needs only (waveforms, sample lengths, response ids) from the host.
+
+    Template pieces are token-id lists of the chat template around the audio placeholders and the answer, e.g. for Qwen3:
+    prefix = <|im_start|> user \n ; middle = " Transcribe the speech to text" <|im_end|> \n <|im_start|> assistant \n (+ empty think block);
+    suffix = <|im_end|> \n  (the first suffix token is part of the labels, as the reference's collator produces it)."""
+
+    def __init__(self, prefix_ids, middle_ids, suffix_ids, audio_token_id: int, pad_token_id: int, projector=None,
+                 encoder_conv_layers=None, hop_length: int = 160, device="cuda"):
+        from . import lib as L
+        self.L = L
+        self.lib = L.load()
+        self.device = torch.device(device)
+        t = lambda x: torch.tensor(list(x), dtype=torch.int64, device=self.device)
+        self.prefix, self.middle, self.suffix = t(prefix_ids), t(middle_ids), t(suffix_ids)
+        self.audio_token_id, self.pad_token_id = int(audio_token_id), int(pad_token_id)
+        self.projector, self.hop = projector, hop_length
+        self.conv_layers = encoder_conv_layers or DEFAULT_ENCODER_CONV_LAYERS
+
+    def audio_token_counts(self, sample_lengths: torch.Tensor) -> torch.Tensor:
+        """samples per clip [B] (device) -> `<audio>` placeholders per clip, the reference's arithmetic (asr_config.py:9-19,
+        projectors.py:52-55) on the device: mel frames = ceil(len / hop) clipped by the extractor's frame mask rule."""
+        n = sample_lengths.to(self.device, torch.int64)
+        mel = (n + self.hop - 1) // self.hop                      # frame mask = every hop-th sample of the sample mask
+        enc = compute_encoder_output_length(mel, self.conv_layers)
+        return self.projector.get_output_length(enc).to(torch.int64)
+
+    def __call__(self, counts: torch.Tensor, response_ids, seq_len: int = None):
+        """counts int64 [B] (device); response_ids: list of per-sample id lists (host) or (packed int64 tensor, offsets [B+1]).
+        Returns dict(input_ids, labels, attention_mask) [B, S] on the device."""
+        L = self.L
+        counts = counts.to(self.device, torch.int64).contiguous()
+        B = int(counts.numel())
+        if isinstance(response_ids, (list, tuple)) and not torch.is_tensor(response_ids[0]):
+            lens = [len(r) for r in response_ids]
+            off = torch.tensor([0] + list(__import__("itertools").accumulate(lens)), dtype=torch.int64)
+            packed = torch.tensor([t for r in response_ids for t in r], dtype=torch.int64)
+        else:
+            packed, off = response_ids
+            lens = (off[1:] - off[:-1]).tolist()
+        packed, off = packed.to(self.device).contiguous(), off.to(self.device).contiguous()
+        if seq_len is None:          # the one host-side quantity: row length (counts are known to the host that cut the clips)
+            seq_len = int(counts.max()) + max(lens) + self.prefix.numel() + self.middle.numel() + self.suffix.numel()
+        ids = torch.empty(B, seq_len, dtype=torch.int64, device=self.device)
+        labels, mask = torch.empty_like(ids), torch.empty_like(ids)
+        dummy = packed if packed.numel() else torch.zeros(1, dtype=torch.int64, device=self.device)
+        L.check(self.lib.ta_assemble_prompts(L.ptr(counts), L.ptr(dummy), L.ptr(off), L.ptr(self.prefix), int(self.prefix.numel()),
+                                             L.ptr(self.middle), int(self.middle.numel()), L.ptr(self.suffix), int(self.suffix.numel()),
+                                             self.audio_token_id, self.pad_token_id, B, seq_len, L.ptr(ids), L.ptr(labels), L.ptr(mask),
+                                             L.stream_ptr()))
+        return {"input_ids": ids, "labels": labels, "attention_mask": mask, "audio_token_counts": counts}

@@ -471,6 +471,10 @@ TA_API int ta_attn_fwd(const void* q, const void* k, const void* v, void* o, flo
         const int rc = k_attn_tc_fwd(Q, K, V, O, lse, B, S, Hq, Hkv, head_dim, q_rs, k_rs, v_rs, o_rs, causal, scale, st, &handled);
         if (rc) return rc;
         if (handled) return 0;
+        // no silent second backend: with the tcgen05 path selected (the default) a shape it does not cover is an error; the mma.sync
+        // kernels below run only when they are asked for explicitly (ta_attn_set_tc(0): parity / A-B reference)
+        TA_REQUIRE(!k_attn_tc_enabled(), "ta_attn_fwd: shape not covered by the tcgen05 kernels (head_dim %d, 16-byte aligned q/k/v/o "
+                   "required); ta_attn_set_tc(0) selects the mma.sync reference kernels", head_dim);
     }
     if (head_dim == 64 && !causal) return launch_fwd<64, false>(Q, K, V, O, lse, B, S, Hq, Hkv, q_rs, k_rs, v_rs, o_rs, scale, st);
     if (head_dim == 64 && causal) return launch_fwd<64, true>(Q, K, V, O, lse, B, S, Hq, Hkv, q_rs, k_rs, v_rs, o_rs, scale, st);
@@ -503,6 +507,8 @@ TA_API int ta_attn_bwd(const void* q, const void* k, const void* v, const void* 
                                      &handled);
         if (rc) return rc;
         if (handled) return 0;
+        TA_REQUIRE(false, "ta_attn_bwd: shape not covered by the tcgen05 kernel (causal, head_dim 128); ta_attn_set_tc(0) selects the "
+                   "mma.sync reference kernel");
     }
     const int smem = 4 * TILE * HD * 2 + TILE * TILE * 2 + 2 * TILE * 4;
     dim3 grid((S + TILE - 1) / TILE, Hkv, B);

@@ -1571,10 +1571,15 @@ int launch_attn_tc5(const bf16* q, const bf16* k, const bf16* v, bf16* o, float*
     return 0;
 }
 
-// 0: mma.sync; 1: tcgen05, 2 threads per row everywhere; 2 (default): head_dim-64 non-causal runs the one-thread-per-row variant
-// (0.590 vs 0.632 ms per encoder layer at B=32, S=1500); 3 / 4: that variant with every 4th / 2nd exp2 on the FMA pipe -- slower
-// (0.68 / 0.75 ms): with two softmax warps per sub-partition the kernel is issue/latency-bound, not MUFU-bound (profiles/).
-int g_attn_tc = 2;
+// Forward-kernel selection (ta_attn_set_tc).  0: mma.sync; 1: tcgen05, two threads per query row, every shape; the other modes choose
+// the encoder-shape kernel (head_dim 64, non-causal) and leave the rest on mode 1's kernel:
+//   2: one thread per row, 128-key tiles, two CTAs per SM (round-1 default: 0.590 ms per encoder layer at B = 32, S = 1500);
+//      3 / 4 / 11: the same with every 4th / 2nd / 8th exp2 on the FMA pipe;  5: two 64-key streams per row;
+//   6-10, 12, 13: persistent CTA with two query tiles (turns / free-running, P through shared or tensor memory; 0.58-0.64 ms);
+//   14 (default): 64-key tiles, three CTAs per SM -- three softmax warps per SM sub-partition keep the SFUs busier: 0.527 ms;
+//      15 / 16: the same with every 8th / 4th exp2 on the FMA pipe (0.521 / slower).
+// Measurements: profiles/r02_attention_*.txt.
+int g_attn_tc = 14;
 
 }  // namespace
 
@@ -1587,7 +1592,7 @@ TA_API int ta_attn_set_trace(void* buf, int steps) {
 }
 
 TA_API int ta_attn_set_tc(int on) {
-    g_attn_tc = (on < 0 || on > 16) ? 2 : on;
+    g_attn_tc = (on < 0 || on > 16) ? 14 : on;
     return 0;
 }
 int k_attn_tc_enabled() { return g_attn_tc; }

@@ -723,6 +723,31 @@ label_rows_kernel(const long long* __restrict__ labels, int B, int S, int* __res
     if (tid == 0) *count = s_carry;
 }
 
+// GPU-side collation (scripts/train.py:324-348 builds these on the CPU workers): chat-template prompt assembly on the
+// device.  Row b of the batch is   prefix | <audio> x counts[b] | middle | response_b | suffix | pad ...
+// with labels = -100 except the response tokens and the first suffix token (<|im_end|>), attention_mask = 1 on the real tokens.
+// One thread per (b, s) position.
+__global__ void assemble_prompts_kernel(const long long* __restrict__ counts, const long long* __restrict__ resp, const long long* __restrict__ resp_off,
+                                        const long long* __restrict__ prefix, int n_prefix, const long long* __restrict__ middle, int n_middle,
+                                        const long long* __restrict__ suffix, int n_suffix, long long audio_id, long long pad_id, int B, int S,
+                                        long long* __restrict__ ids, long long* __restrict__ labels, long long* __restrict__ mask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * S) return;
+    const int b = (int)(i / S);
+    int s = (int)(i % S);
+    const int n_a = (int)counts[b], n_r = (int)(resp_off[b + 1] - resp_off[b]);
+    long long id = pad_id, lab = -100, m = 1;
+    if (s < n_prefix) id = prefix[s];
+    else if ((s -= n_prefix) < n_a) id = audio_id;
+    else if ((s -= n_a) < n_middle) id = middle[s];
+    else if ((s -= n_middle) < n_r) { id = resp[resp_off[b] + s]; lab = id; }
+    else if ((s -= n_r) < n_suffix) { id = suffix[s]; if (s == 0) lab = id; }
+    else m = 0;
+    ids[i] = id;
+    labels[i] = lab;
+    mask[i] = m;
+}
+
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
     __shared__ float red[40];
     float s = 0.f;
@@ -1019,6 +1044,21 @@ TA_API int ta_label_rows(const long long* labels, int B, int S, int* rows, int* 
     TA_REQUIRE(labels && rows && targets && count, "ta_label_rows: null pointer");
     TA_REQUIRE(B >= 0 && S >= 1 && (long long)B * S < (1LL << 31), "ta_label_rows: bad shape B=%d S=%d", B, S);
     label_rows_kernel<<<1, 1024, 0, ST(stream)>>>(labels, B, S, rows, targets, count);
+    TA_LAUNCH_CHECK();
+    return 0;
+}
+
+// GPU-side prompt assembly: counts [B] (audio tokens per clip), resp (packed response ids) + resp_off [B+1], template pieces as device
+// arrays -> input_ids / labels / attention_mask [B, S] (all int64).  S is chosen by the caller (>= the longest row; longer rows are an error
+// the caller rules out on the host, where the lengths come from).
+TA_API int ta_assemble_prompts(const long long* counts, const long long* resp, const long long* resp_off, const long long* prefix, int n_prefix,
+                               const long long* middle, int n_middle, const long long* suffix, int n_suffix, long long audio_id, long long pad_id,
+                               int B, int S, long long* ids, long long* labels, long long* mask, void* stream) {
+    TA_REQUIRE(counts && resp_off && ids && labels && mask, "ta_assemble_prompts: null pointer");
+    TA_REQUIRE((n_prefix == 0 || prefix) && (n_middle == 0 || middle) && (n_suffix == 0 || suffix), "ta_assemble_prompts: template piece missing");
+    if (B == 0 || S == 0) return 0;
+    assemble_prompts_kernel<<<grid_for((long long)B * S, 256), 256, 0, ST(stream)>>>(counts, resp, resp_off, prefix, n_prefix, middle, n_middle,
+                                                                                     suffix, n_suffix, audio_id, pad_id, B, S, ids, labels, mask);
     TA_LAUNCH_CHECK();
     return 0;
 }

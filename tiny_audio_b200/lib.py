@@ -103,6 +103,7 @@ _SIGS = {
     "ta_frame_stack": ([P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
     "ta_frame_keep_mask": ([P, P, c_ll, c_int, P], c_int),
     "ta_label_rows": ([P, c_int, c_int, P, P, P, P], c_int),
+    "ta_assemble_prompts": ([P, P, P, P, c_int, P, c_int, P, c_int, c_ll, c_ll, c_int, c_int, P, P, P, P], c_int),
     "ta_window_attn_fwd": ([P, P, P, P, P, c_ll, c_int, c_int, c_int, c_int, c_float, P], c_int),
     "ta_window_attn_bwd": ([P, P, P, P, P, P, P, P, c_ll, c_int, c_int, c_int, c_int, c_float, P], c_int),
     "ta_window_attn_set_variant": ([c_int], c_int),

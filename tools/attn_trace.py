@@ -53,4 +53,4 @@ for mode in [int(a) for a in sys.argv[1:]] or [8]:
               f"{med(m[:, 3] - p_done.max(0)):.0f} clk after the LAST warp wrote P; V/O-free wait {med(m[:, 4] - m[:, 3]):.0f}; PV issue {med(m[:, 2] - m[:, 4]):.0f}")
         nxt_pv = t[ws, lo + 1:hi + 1, 4]   # pv_done seen by the softmax warps in the next step
         print(f"     pv_done seen by the softmax warps {med(nxt_pv.min(0) - m[:, 2]):.0f} .. {med(nxt_pv.max(0) - m[:, 2]):.0f} clk after the PV issue")
-lib.ta_attn_set_tc(2)
+lib.ta_attn_set_tc(14)

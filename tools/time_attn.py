@@ -32,4 +32,4 @@ for tc in modes:
     t = e0.elapsed_time(e1) / 20
     print(f"enc attention fwd mode={tc}: {t:.3f} ms  {4.0 * B * H * S * S * hd / t / 1e9:.0f} TF/s  "
           f"{B * H * S * S / t / 1e6 / 148:.2f} Gexp/s/SM", flush=True)
-lib.ta_attn_set_tc(2)
+lib.ta_attn_set_tc(14)
