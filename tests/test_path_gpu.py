@@ -797,7 +797,11 @@ def test_device_prompt_assembly_matches_host_collation(cuda):
         assert out["input_ids"][b, :n].tolist() == row and (out["input_ids"][b, n:] == pad).all()
         assert out["labels"][b, :n].tolist() == lab and (out["labels"][b, n:] == -100).all()
         assert int(out["attention_mask"][b].sum()) == n and bool((out["attention_mask"][b, :n] == 1).all())
-    assert S == max(len(prefix) + int(c) + len(middle) + len(r) + len(suffix) for c, r in zip(counts, rag))
+    # default row length = a bound the host knows without looking at the pairing (max count + max response); an explicit one is honoured
+    assert S == len(prefix) + int(counts.max()) + len(middle) + max(len(r) for r in rag) + len(suffix)
+    longest = max(len(prefix) + int(c) + len(middle) + len(r) + len(suffix) for c, r in zip(counts, rag))
+    tight = asm(counts.cuda(), rag, seq_len=longest)
+    assert tight["input_ids"].shape[1] == longest and torch.equal(tight["input_ids"], out["input_ids"][:, :longest])
     # a train step on the device-built batch == on the host-built batch
     model.train()
     n_items = int((host["labels"] != -100).sum())
