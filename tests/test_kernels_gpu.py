@@ -487,6 +487,34 @@ def test_skinny_gemm_plain_and_resid(cuda, M, N, K):
         assert rel_err(y2, resid * torch.rsqrt(resid.pow(2).mean(-1, keepdim=True) + 1e-6) * gw) < 5e-3
 
 
+@pytest.mark.parametrize("M,Fd,D2", [(300, 512, 128), (5000, 3072, 256), (14848 // 4 + 77, 1024, 1024)])
+def test_gemm_swiglu_bwd_tma_epilogue_equals_per_thread_epilogue(cuda, M, Fd, D2):
+    """The in-place TMA epilogue of SwiGLU-backward (stash in / gradients out through the same shared-memory boxes, agent warps) and
+    the per-thread-load epilogue run the same arithmetic: bit-identical gradients, including the clipped M tail and several waves of
+    tiles per CTA pair (more chunks than the two buffer sets, so every barrier phase wraps)."""
+    lib = L.load()
+    gu = rnd(M, 2 * Fd, seed=11, scale=1.5)
+    dy = rnd(M, D2, seed=12)
+    wd_t = rnd(Fd, D2, seed=13, scale=0.1)
+    out = {}
+    try:
+        for mode in (0, 1):
+            L.check(lib.ta_gemm_set_swiglu_bwd_tma(mode))
+            dgu = torch.full((M, 2 * Fd), float("nan"), device="cuda", dtype=BF16)
+            L.gemm(dy, wd_t, epi=L.EPI_SWIGLU_BWD, aux=gu, out=dgu)
+            out[mode] = dgu
+    finally:
+        L.check(lib.ta_gemm_set_swiglu_bwd_tma(1))
+    assert torch.isfinite(out[1].float()).all()
+    assert torch.equal(out[0], out[1])
+    dh = (dy.float() @ wd_t.float().t()).to(BF16).float()
+    g = gu.view(M, Fd // 64, 2, 64)[:, :, 0].reshape(M, Fd).float().requires_grad_(True)
+    u = gu.view(M, Fd // 64, 2, 64)[:, :, 1].reshape(M, Fd).float().requires_grad_(True)
+    (F.silu(g) * u * dh).sum().backward()
+    v = out[1].view(M, Fd // 64, 2, 64)
+    assert rel_err(v[:, :, 0].reshape(M, Fd), g.grad) < 1e-2 and rel_err(v[:, :, 1].reshape(M, Fd), u.grad) < 1e-2
+
+
 @pytest.mark.parametrize("M", [3, 32])
 def test_skinny_gemm_swiglu(cuda, M):
     lib = L.load()

@@ -76,6 +76,7 @@ struct EpiArgs {
     int rope_seq;
     int rope_cols;
     int k_splits;            // SPLITK instantiations only: the contraction is cut into k_splits ranges whose partial tiles are reduce-added
+    int aux_tma;             // SWIGLU_BWD (pair kernel): the (gate, up) stash comes in by TMA and the gradients leave from the same buffer
 };
 
 __device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32]) {
@@ -676,6 +677,66 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// SwiGLU-backward epilogue, in place through shared memory (pair kernel, ep.aux_tma).
+//   A "chunk" is 32 h columns of this CTA's 128 accumulator rows.  Its (gate, up) stash values -- two [128 x 32] bf16 boxes, 8 KB each,
+//   SWIZZLE_64B -- are brought in by TMA two chunks ahead by the group's agent warp (warp 2 + grp); every epilogue thread reads ITS
+//   row of both boxes, overwrites it with (d gate, d up) and the agent stores the two boxes to the interleaved [M, 2F] gradient,
+//   which has the stash's layout.  No global loads in the epilogue threads, no store-drain on their path: they only wait on
+//   ld_full[set] (TMA landed) and signal st_ready[set] (row rewritten).  Replaces the per-thread 128-bit global loads + staged stores
+//   that left the kernel at 613 TFLOP/s (tensor pipe 33 % active, profiles/r02_c01_ncu_lm_gemm.txt).
+// ----------------------------------------------------------------------------------------------
+constexpr int SWB_SET_BYTES = 2 * 8192;    // gate box + up box
+
+template <int BN>
+__device__ __forceinline__ void epilogue_swiglu_bwd_inplace(uint32_t taddr, int grp, int r, int lane, uint8_t* gbuf, uint64_t* ldf,
+                                                            uint64_t* str, uint32_t& n) {
+    constexpr int CPT = BN / 64;               // chunks per tile and group
+    const int sw = (r >> 1) & 3;               // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
+#pragma unroll 1
+    for (int i = 0; i < CPT; ++i, ++n) {
+        const uint32_t set = n & 1u;
+        uint32_t rr[32];
+        tmem_ld_32x32(taddr + (uint32_t)((grp * CPT + i) * 32), rr);
+        mbar_wait(&ldf[set], (n >> 1) & 1u);
+        uint8_t* gp = gbuf + set * SWB_SET_BYTES + r * 64;
+        uint8_t* up = gp + 8192;
+        uint4 g4[4], u4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            g4[k] = *reinterpret_cast<const uint4*>(gp + ((k ^ sw) << 4));
+            u4[k] = *reinterpret_cast<const uint4*>(up + ((k ^ sw) << 4));
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t gw[4] = {g4[k].x, g4[k].y, g4[k].z, g4[k].w};
+            const uint32_t uw[4] = {u4[k].x, u4[k].y, u4[k].z, u4[k].w};
+            uint32_t og[4], ou[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 g2 = unpack_bf16x2(gw[t]), u2 = unpack_bf16x2(uw[t]);
+                const float gq[2] = {g2.x, g2.y}, uq[2] = {u2.x, u2.y};
+                float dg[2], du[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float dh = bf16_round(__uint_as_float(rr[8 * k + 2 * t + e]));
+                    const float sgm = sigmoidf_(gq[e]);
+                    du[e] = dh * bf16_round(gq[e] * sgm);
+                    dg[e] = dh * uq[e] * (sgm * (1.0f + gq[e] * (1.0f - sgm)));
+                }
+                og[t] = pack_bf16x2(dg[0], dg[1]);
+                ou[t] = pack_bf16x2(du[0], du[1]);
+            }
+            *reinterpret_cast<uint4*>(gp + ((k ^ sw) << 4)) = make_uint4(og[0], og[1], og[2], og[3]);
+            *reinterpret_cast<uint4*>(up + ((k ^ sw) << 4)) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&str[set]);
+    }
+}
+
 // =============================================================================================================
 // 2-CTA variant (cta_group::2): a CTA pair (cluster 2x1x1, two SMs of one TPC) owns a 256 x BN tile.
 //   CTA r holds A rows [m0 + 128 r, +128) and the B rows [n0 + r BN/2, + BN/2) of every stage; the leader (rank 0)
@@ -781,6 +842,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint64_t* tfull = bars + 2 * C::STAGES;
     uint64_t* tempty = bars + 2 * C::STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    uint64_t* swb_ld_full = bars + 20;       // [group][set]: in-place SwiGLU-backward epilogue (ep.aux_tma)
+    uint64_t* swb_st_ready = bars + 24;
+    static_assert(2 * C::STAGES + 5 <= 20, "barrier area layout");
     float* s_bias_all = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);   // [2][BN]
 
     const int warp = threadIdx.x >> 5;
@@ -810,6 +874,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], 16);
+        }
+        if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
+            for (int s = 0; s < 4; ++s) {
+                mbar_init(&swb_ld_full[s], 1);
+                mbar_init(&swb_st_ready[s], 4);
+            }
         }
         mbar_fence_init();
     }
@@ -896,6 +966,56 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (as == 0) aphase ^= 1;
             }
         }
+    } else if (EPI == TA_EPI_SWIGLU_BWD && (warp == 2 || warp == 3)) {
+        // ===================== SwiGLU-backward stash agent of epilogue group (warp - 2) =====================
+        if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
+            if (ep.aux_tma) {
+                constexpr int CPT = BN / 64;
+                const int grp = warp - 2;
+                uint8_t* gbuf = smStage + grp * 2 * STG_BYTES;
+                uint64_t* ldf = swb_ld_full + 2 * grp;
+                uint64_t* str = swb_st_ready + 2 * grp;
+                const bool issuer = elect_one();
+                const int my_tiles = pair < num_work ? (num_work - pair + n_pairs - 1) / n_pairs : 0;
+                const uint32_t total = (uint32_t)(my_tiles * CPT);
+                auto coords = [&](uint32_t n, int& x, int& y) {
+                    const int tile = pair + (int)(n / CPT) * n_pairs;
+                    const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
+                    const int col = n_blk * BN + (grp * CPT + (int)(n % CPT)) * 32;       // first h column of the chunk
+                    x = (col >> 6) * 128 + (col & 63);                                     // its gate columns in the [M, 2F] layout
+                    y = m_blk * 2 * BM + (int)rank * BM;
+                };
+                auto load = [&](uint32_t n) {
+                    int x, y;
+                    coords(n, x, y);
+                    uint8_t* dst = gbuf + (n & 1u) * SWB_SET_BYTES;
+                    if (issuer) {
+                        mbar_arrive_expect_tx(&ldf[n & 1u], SWB_SET_BYTES);
+                        tma_load_2d(dst, &tmC2, &ldf[n & 1u], x, y);
+                        tma_load_2d(dst + 8192, &tmC2, &ldf[n & 1u], x + 64, y);
+                    }
+                    __syncwarp();
+                };
+                if (total > 0) load(0);
+                if (total > 1) load(1);
+                for (uint32_t n = 0; n < total; ++n) {
+                    mbar_wait(&str[n & 1u], (n >> 1) & 1u);
+                    int x, y;
+                    coords(n, x, y);
+                    const uint8_t* src = gbuf + (n & 1u) * SWB_SET_BYTES;
+                    if (issuer) {
+                        tma_store_2d(&tmC, src, x, y);
+                        tma_store_2d(&tmC, src + 8192, x + 64, y);
+                        tma_store_commit();
+                        if (n + 2 < total) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    __syncwarp();
+                    if (n + 2 < total) load(n + 2);
+                }
+                if (issuer) tma_store_wait_all();
+                __syncwarp();
+            }
+        }
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs, their own 128 rows) =====================
         const int q = warp & 3;
@@ -909,6 +1029,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         int tile_iter = 0;
         int as = 0;
         uint32_t aphase = 0;
+        uint32_t swb_n = 0;      // chunks this group has processed (in-place SwiGLU-backward)
         for (int work = pair; work < num_work; work += n_pairs) {
             const int tile = SPLITK ? work % num_tiles : work;
             const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
@@ -925,8 +1046,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const long long row = (long long)m_blk * 2 * BM + (long long)rank * BM + q * 32 + lane;
             const bool row_ok = row < M;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            epilogue_tile_tma<BN, EPI, SPLITK>(taddr, row, row_ok, m_blk * 2 * BM + (int)rank * BM, (long long)n_blk * BN, ep, grp, s_bias,
-                                               sg, &tmC, &tmC2);
+            bool done = false;
+            if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
+                if (ep.aux_tma) {
+                    epilogue_swiglu_bwd_inplace<BN>(taddr, grp, sg.r, lane, sg.buf, swb_ld_full + 2 * grp, swb_st_ready + 2 * grp, swb_n);
+                    done = true;
+                }
+            }
+            if (!done)
+                epilogue_tile_tma<BN, EPI, SPLITK>(taddr, row, row_ok, m_blk * 2 * BM + (int)rank * BM, (long long)n_blk * BN, ep, grp,
+                                                   s_bias, sg, &tmC, &tmC2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty[as]);
@@ -965,24 +1094,27 @@ struct MapKey {
     const void* ptr;
     long long rows, cols, ld;
     int box_rows;   // negative: fp32 elements (box = 32 x |box_rows|)
+    int box_cols;   // 0: the default 128-byte inner extent
     bool operator==(const MapKey& o) const {
-        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         size_t h = std::hash<const void*>()(k.ptr);
         h ^= std::hash<long long>()(k.rows * 1315423911LL + k.cols) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
-        h ^= std::hash<long long>()(k.ld * 31 + k.box_rows) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+        h ^= std::hash<long long>()(k.ld * 31 + k.box_rows + 7919LL * k.box_cols) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
         return h;
     }
 };
 std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// 2-D bf16 row-major [rows, cols] (ld elements), box = {64 cols, box_rows}, SWIZZLE_128B, zero fill out of bounds
-int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows, bool f32 = false) {
-    MapKey key{ptr, rows, cols, ld, f32 ? -box_rows : box_rows};
+// 2-D bf16 row-major [rows, cols] (ld elements), box = {64 cols, box_rows}, SWIZZLE_128B, zero fill out of bounds.
+// box_cols = 32 (bf16): 64-byte inner extent with SWIZZLE_64B (the in-place SwiGLU-backward epilogue's (gate, up) chunks)
+int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows, bool f32 = false,
+             int box_cols = 0) {
+    MapKey key{ptr, rows, cols, ld, f32 ? -box_rows : box_rows, box_cols};
     {
         std::lock_guard<std::mutex> g(g_map_mu);
         auto it = g_maps.find(key);
@@ -998,10 +1130,11 @@ int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, 
     TA_REQUIRE((ld * esz) % 16 == 0, "GEMM operand leading dimension must be a multiple of 16 bytes (got %lld elements)", ld);
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
-    cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : BK), (cuuint32_t)box_rows};   // 128-byte inner extent either way
+    TA_REQUIRE(box_cols == 0 || (!f32 && box_cols == 32), "tensor map: unsupported box width %d", box_cols);
+    cuuint32_t box[2] = {(cuuint32_t)(box_cols ? box_cols : (f32 ? 32 : BK)), (cuuint32_t)box_rows};   // 128-byte inner extent by default
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows,
                cols, ld);
@@ -1100,6 +1233,7 @@ int g_force_bn = 0;
 int g_tail_split = 0; // 1: split off a poorly filled last wave into 256 x 128 tiles (ta_gemm_set_tail_split).  Off by default: on the
                       // power-capped B200 the step did not get faster (130.4 vs 129.3 ms) -- SMs idling in a short last wave hand their
                       // power budget to the busy ones, which then clock higher, so the quantisation loss is mostly virtual here.
+int g_swiglu_bwd_tma = 1;   // 1 (default): in-place TMA epilogue for SwiGLU-backward (ta_gemm_set_swiglu_bwd_tma); 0: per-thread loads
 int g_cta_pair = 1;   // 1 (default): CTA-pair kernel (cta_group::2, 256 x N tiles); 0: 1-CTA kernel (cta_group::1)
 
 }  // namespace
@@ -1123,6 +1257,11 @@ TA_API int ta_gemm_set_tail_split(int on) {
 int g_tn_splitk = 1;
 TA_API int ta_gemm_set_tn_splitk(int on) {
     g_tn_splitk = on ? 1 : 0;
+    return 0;
+}
+
+TA_API int ta_gemm_set_swiglu_bwd_tma(int on) {
+    g_swiglu_bwd_tma = on ? 1 : 0;
     return 0;
 }
 
@@ -1150,6 +1289,7 @@ TA_API int ta_gemm_bf16_tn(const void* At, long long ldat, const void* Bt, long 
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     ep.k_splits = 1;
+    ep.aux_tma = 0;
     if (g_tn_splitk) {
         // few output tiles, deep contraction (rank-8 LoRA gradients: 4 ... 24 tiles x 230 k-blocks): cut K so that every CTA pair
         // gets a work item, each at least 8 k-blocks long; partial tiles are reduce-added into the zeroed output
@@ -1182,6 +1322,7 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
     if (N % bn != 0) bn = 128;
     EpiArgs ep;
     ep.k_splits = 1;
+    ep.aux_tma = 0;
     ep.out = e->out; ep.ldo = e->ldo; ep.bias = e->bias; ep.resid = e->resid; ep.ldr = e->ldr ? e->ldr : e->ldo;
     ep.out2 = e->out2; ep.ldo2 = e->ldo2; ep.aux = reinterpret_cast<const bf16*>(e->aux); ep.ldaux = e->ldaux;
     ep.alpha = e->alpha == 0.0f ? 1.0f : e->alpha;
@@ -1218,9 +1359,15 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
             r2 = make_map(&mb, B, N, K, ldb, bnp / 2);     // each CTA of the pair loads half of the B tile
             if (r2) return r2;
             // output maps for the TMA-store epilogue: [rows, width] with 128-byte wide sub-tiles
-            r2 = make_map(&tc, e2.out, rows, out_cols, e->ldo, BM, f32out);
+            const bool swb_tma = (epi == TA_EPI_SWIGLU_BWD) && g_swiglu_bwd_tma;
+            e2.aux_tma = swb_tma ? 1 : 0;
+            r2 = make_map(&tc, e2.out, rows, out_cols, e->ldo, BM, f32out, swb_tma ? 32 : 0);
             if (r2) return r2;
             tc2 = tc;
+            if (swb_tma) {
+                r2 = make_map(&tc2, e2.aux, rows, 2LL * N, e->ldaux, BM, false, 32);
+                if (r2) return r2;
+            }
             if (epi == TA_EPI_SWIGLU && e->out2) {
                 r2 = make_map(&tc2, e2.out2, rows, N, e->ldo2, BM, false);
                 if (r2) return r2;

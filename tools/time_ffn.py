@@ -42,6 +42,20 @@ rows = [("gate_up plain bf16 out [M,6144]", lambda: L.gemm(x, wgu, epi=L.EPI_BF1
         ("down + fp32 residual", lambda: L.gemm(h, wd, epi=L.EPI_F32_RESID, resid=resid, out=y), fl_d),
         ("d(h) SwiGLU-backward -> (d gate, d up)", lambda: L.gemm(dy, wd_t, epi=L.EPI_SWIGLU_BWD, aux=gu, out=dgu), fl_d),
         ("cuBLAS gate_up", lambda: torch.matmul(x, wgu.t()), fl_gu), ("cuBLAS down", lambda: torch.matmul(h, wd.t()), fl_d)]
-for name, fn, fl in rows:
-    t = timeit(fn)
-    print(f"{name:42s} {t * 1e3:7.1f} us  {fl / t / 1e9:6.0f} TFLOP/s", flush=True)
+def report(rows):
+    for name, fn, fl in rows:
+        t = timeit(fn)
+        print(f"{name:42s} {t * 1e3:7.1f} us  {fl / t / 1e9:6.0f} TFLOP/s", flush=True)
+
+
+report(rows)
+# A/B switches
+lib.ta_gemm_set_swiglu_bwd_tma(0)
+report([("d(h) SwiGLU-backward, per-thread stash loads", rows[4][1], fl_d)])
+lib.ta_gemm_set_swiglu_bwd_tma(1)
+lib.ta_gemm_set_tail_split(1)
+report([("down + fp32 residual, tail split 256x128", rows[3][1], fl_d)])
+lib.ta_gemm_set_tail_split(0)
+lib.ta_gemm_set_tile_n(128)
+report([("down + fp32 residual, 256x128 tiles", rows[3][1], fl_d)])
+lib.ta_gemm_set_tile_n(0)
