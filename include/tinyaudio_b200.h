@@ -151,6 +151,24 @@ int ta_window_attn_bwd(const void* q, const void* k, const void* v, const float*
 /* A/B switch: 1 = lanes over head_dim (any head_dim), 2 = key per lane with 16-byte accesses (head_dim % 8 == 0, else falls back
  * to 1); returns the previous setting */
 int ta_window_attn_set_variant(int variant);
+/* a6 (QFormer projector glue; tiny_audio/projectors.py:359-475 = HF:models/blip_2/modeling_blip_2.py Blip2QFormerSelfOutput :637-648,
+ * Blip2QFormerOutput :693-704, Blip2QFormerIntermediate :677-689, query LayerNorm + dropout :985-986):
+ *   y = LayerNorm(bf16(o) * mask + resid[row % resid_rows]) * post_mask[row % post_rows]   (o / mask / resid / post_mask optional; masks are
+ *   the 0 or 1/(1-p) dropout multipliers), fp32 out + optional bf16 copy for the next GEMM; stats [rows, 2] = (mean, rstd) for the backward.
+ *   Backward: dy = g32 + g16 (either optional) -> d_o bf16 (masked), d_resid fp32 (atomically reduced when resid is row-broadcast), dw, db. */
+int ta_add_layernorm_fwd(const void* o, const float* mask, const float* resid, long long resid_rows, const float* w, const float* b,
+                         const float* post_mask, long long post_rows, float* y32, void* y16, float* stats, long long rows, int H, float eps,
+                         void* stream);
+int ta_add_layernorm_bwd(const float* g32, const void* g16, const void* o, const float* mask, const float* resid, long long resid_rows,
+                         const float* w, const float* post_mask, long long post_rows, const float* stats, void* d_o, float* d_resid, float* dw,
+                         float* db, float* partial /* ta_add_layernorm_bwd_partial_floats(H) floats of scratch: per-block dw / db partial
+                         sums, reduced in a fixed order (deterministic) */, long long rows, int H, void* stream);
+long long ta_add_layernorm_bwd_partial_floats(int H);
+/* exact-erf GELU on bf16 storage and its backward dx = dy (Phi(x) + x phi(x)); n elements, multiple of 8 */
+int ta_gelu_fwd_bf16(const void* x, void* y, long long n, void* stream);
+int ta_gelu_bwd_bf16(const void* x, const void* dy, void* dx, long long n, void* stream);
+/* out[j] = sum_r x[r, j] (bias gradients of the tcgen05 linears); out is zeroed inside */
+int ta_colsum_bf16(const void* x, long long ld, float* out, long long rows, int cols, void* stream);
 /* tiny_audio/projectors.py:79-87 (_frame_stack): row j <- frames k*j .. k*j+k-1, feature-major per frame */
 int ta_frame_stack(const void* x /*bf16 [B,S,D]*/, void* out /*bf16 [B,n,k*D]*/, int B, int S, int n, int k, int D, void* stream);
 /* a4. tiny_audio/asr_modeling.py:458-479 (_maybe_drop_audio_tokens): whole encoder frames zeroed by a {0,1} keep mask, no rescale.

@@ -364,7 +364,15 @@ def qformer_output_length(enc_len):
     return ((enc_len + QF_WINDOW - 1) // QF_WINDOW) * (QF_WINDOW // QF_DOWNSAMPLE)
 
 
-def qformer_projector_forward(w: Dict[str, Tensor], enc_out: Tensor, cfg: PathConfig = FULL) -> Tensor:
+def qformer_projector_forward(w: Dict[str, Tensor], enc_out: Tensor, cfg: PathConfig = FULL, drop_masks=None) -> Tensor:
+    """`drop_masks`: optional iterable of hidden-dropout multiplier tensors (0 or 1/(1-p), [windows * queries, H]) in the order the
+    reference draws them -- after the query LayerNorm (HF:models/blip_2/modeling_blip_2.py:985-986), then per layer after the
+    self-attention, cross-attention and FFN output projections (:644-648, :700-704); None = eval mode.  (Attention-probability
+    dropout, :622, is not injectable here.)"""
+    masks = iter(drop_masks) if drop_masks is not None else None
+
+    def drop(t):
+        return t if masks is None else t * next(masks).reshape(t.shape).to(t.dtype)
     B, S, H = enc_out.shape
     nb = -(-S // QF_WINDOW)
     x_enc = F.pad(enc_out.float(), (0, 0, 0, nb * QF_WINDOW - S)).reshape(B * nb, QF_WINDOW, H)
@@ -376,16 +384,16 @@ def qformer_projector_forward(w: Dict[str, Tensor], enc_out: Tensor, cfg: PathCo
         k = F.linear(src, w[p + "attention.key.weight"], w[p + "attention.key.bias"]).view(Wn, -1, QF_HEADS, hd).transpose(1, 2)
         v = F.linear(src, w[p + "attention.value.weight"], w[p + "attention.value.bias"]).view(Wn, -1, QF_HEADS, hd).transpose(1, 2)
         ctx = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1) @ v).transpose(1, 2).reshape(Wn, -1, H)
-        o = F.linear(ctx, w[p + "output.dense.weight"], w[p + "output.dense.bias"])
+        o = drop(F.linear(ctx, w[p + "output.dense.weight"], w[p + "output.dense.bias"]))
         return F.layer_norm(o + x, (H,), w[p + "output.LayerNorm.weight"], w[p + "output.LayerNorm.bias"], QF_EPS)
 
-    x = F.layer_norm(w["query"], (H,), w["qformer.layernorm.weight"], w["qformer.layernorm.bias"], QF_EPS).expand(B * nb, -1, -1)
+    x = drop(F.layer_norm(w["query"], (H,), w["qformer.layernorm.weight"], w["qformer.layernorm.bias"], QF_EPS).expand(B * nb, -1, -1))
     for i in range(QF_LAYERS):
         p = f"qformer.encoder.layer.{i}."
         x = attend(p + "attention.", x, x)
         x = attend(p + "crossattention.", x, x_enc)
         h = F.gelu(F.linear(x, w[p + "intermediate_query.dense.weight"], w[p + "intermediate_query.dense.bias"]))
-        f = F.linear(h, w[p + "output_query.dense.weight"], w[p + "output_query.dense.bias"])
+        f = drop(F.linear(h, w[p + "output_query.dense.weight"], w[p + "output_query.dense.bias"]))
         x = F.layer_norm(f + x, (H,), w[p + "output_query.LayerNorm.weight"], w[p + "output_query.LayerNorm.bias"], QF_EPS)
     return F.linear(x.reshape(B, nb * (QF_WINDOW // QF_DOWNSAMPLE), H), w["linear.weight"], w["linear.bias"])
 

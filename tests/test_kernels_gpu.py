@@ -756,3 +756,73 @@ def test_window_attention_rejects_unsupported_shapes(cuda):
     t = rnd(2, 5, 128, seed=1)
     rc = lib.ta_window_attn_fwd(L.ptr(t), L.ptr(t), L.ptr(t), None, L.ptr(torch.empty_like(t)), 2, 5, 5, 2, 64, 0.125, L.stream_ptr())
     assert rc != 0 and b"queries per window" in lib.ta_last_error_string()
+
+
+# ------------------------------------------------------------------ QFormer glue (csrc/qformer_glue.cu)
+@pytest.mark.parametrize("R,H,rr,with_o,with_mask,post", [(9600, 1280, 9600, True, True, False), (777, 256, 777, True, False, False),
+                                                        (600, 1280, 3, False, False, True), (50, 2048, 50, True, True, True),
+                                                        (45, 128, 3, True, False, False)])
+def test_add_layernorm_fwd_bwd(cuda, R, H, rr, with_o, with_mask, post):
+    """LayerNorm(dropout(o) + residual) * post-dropout in one kernel each way against fp32 torch autograd on the same operands:
+    both outputs (fp32 + bf16 copy), d(o), d(residual) -- also when the residual is row-broadcast (the 3 learnable queries) --
+    and the LayerNorm weight / bias gradients, with cotangents arriving on either or both outputs."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(R + H)
+    o = (torch.randn(R, H, generator=g) * 0.7).to(BF16).cuda() if with_o else None
+    mask = (torch.bernoulli(torch.full((R, H), 0.9), generator=g) / 0.9).cuda() if with_mask else None
+    resid = torch.randn(rr, H, generator=g).cuda()
+    w = (1.0 + 0.2 * torch.randn(H, generator=g)).cuda()
+    b = (0.1 * torch.randn(H, generator=g)).cuda()
+    pm = (torch.bernoulli(torch.full((R, H), 0.9), generator=g) / 0.9).cuda() if post else None
+    y32 = torch.empty(R, H, device="cuda")
+    y16 = torch.empty(R, H, device="cuda", dtype=BF16)
+    stats = torch.empty(R, 2, device="cuda")
+    L.check(lib.ta_add_layernorm_fwd(L.ptr(o), L.ptr(mask), L.ptr(resid), rr, L.ptr(w), L.ptr(b), L.ptr(pm), R if post else 0, L.ptr(y32),
+                                     L.ptr(y16), L.ptr(stats), R, H, 1e-12, L.stream_ptr()))
+    of = o.float().requires_grad_(True) if with_o else None
+    rf, wf, bf = resid.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    z = rf.repeat(R // rr, 1) if rr != R else rf
+    if with_o:
+        z = z + (of * mask if with_mask else of)
+    ref = F.layer_norm(z, (H,), wf, bf, 1e-12)
+    if post:
+        ref = ref * pm
+    assert rel_err(y32, ref) < 1e-5 and torch.equal(y16, y32.to(BF16))
+    g32 = torch.randn(R, H, generator=g).cuda()
+    g16 = torch.randn(R, H, generator=g).to(BF16).cuda()
+    for use32, use16 in ((True, True), (True, False), (False, True)):
+        gsum = (g32 if use32 else 0) + (g16.float() if use16 else 0)
+        grads = torch.autograd.grad(ref, [t for t in (of, rf, wf, bf) if t is not None], gsum, retain_graph=True)
+        if with_o:
+            d_o_ref, grads = grads[0], grads[1:]
+        d_o = torch.empty(R, H, device="cuda", dtype=BF16) if with_o else None
+        d_r = torch.full((rr, H), float("nan"), device="cuda")
+        dw, db = torch.empty(H, device="cuda"), torch.empty(H, device="cuda")
+        scratch = torch.empty(lib.ta_add_layernorm_bwd_partial_floats(H), device="cuda")
+        L.check(lib.ta_add_layernorm_bwd(L.ptr(g32) if use32 else None, L.ptr(g16) if use16 else None, L.ptr(o), L.ptr(mask), L.ptr(resid), rr,
+                                         L.ptr(w), L.ptr(pm), R if post else 0, L.ptr(stats), L.ptr(d_o), L.ptr(d_r), L.ptr(dw), L.ptr(db),
+                                         L.ptr(scratch), R, H, L.stream_ptr()))
+        if with_o:
+            assert rel_err(d_o, d_o_ref) < 4e-3            # bf16 output
+        assert rel_err(d_r, grads[0]) < 2e-5 and rel_err(dw, grads[1]) < 2e-5 and rel_err(db, grads[2]) < 2e-5
+
+
+def test_gelu_and_colsum_kernels(cuda):
+    lib = L.load()
+    x = rnd(1000, 5120, seed=3, scale=2.0)
+    y = torch.empty_like(x)
+    L.check(lib.ta_gelu_fwd_bf16(L.ptr(x), L.ptr(y), x.numel(), L.stream_ptr()))
+    assert torch.equal(y, F.gelu(x.float()).to(BF16))
+    dy = rnd(1000, 5120, seed=4)
+    dx = torch.empty_like(x)
+    L.check(lib.ta_gelu_bwd_bf16(L.ptr(x), L.ptr(dy), L.ptr(dx), x.numel(), L.stream_ptr()))
+    xf = x.float().requires_grad_(True)
+    (F.gelu(xf) * dy.float()).sum().backward()
+    assert rel_err(dx, xf.grad) < 3e-3
+    out = torch.empty(5120, device="cuda")
+    L.check(lib.ta_colsum_bf16(L.ptr(dy), 5120, L.ptr(out), 1000, 5120, L.stream_ptr()))
+    assert rel_err(out, dy.float().sum(0)) < 1e-5
+    sub = dy[:333, :1280]                                 # strided view: ld != cols, rows not a multiple of the 128-row chunk
+    out2 = torch.empty(1280, device="cuda")
+    L.check(lib.ta_colsum_bf16(L.ptr(sub), 5120, L.ptr(out2), 333, 1280, L.stream_ptr()))
+    assert rel_err(out2, sub.float().sum(0)) < 1e-5

@@ -407,6 +407,56 @@ def test_qformer_projector_path(cuda):
     print(f"[qformer] worst projector-grad rel err {worst:.3e} over {len(res['grads'])} tensors")
 
 
+def test_qformer_projector_hidden_dropout_with_recorded_masks(cuda):
+    """QFormerAudioProjector in TRAIN mode (hidden dropout 0.1 on; attention-probability dropout off, it has no injection point in
+    the oracle): the masks the module draws are recorded and replayed in the oracle (reference order: after the query LayerNorm on
+    the EXPANDED queries, projectors.py:461 + HF:models/blip_2/modeling_blip_2.py:985-986, then after each output projection).
+    Output and every parameter gradient must match -- this is the fused dropout + residual + LayerNorm kernel in situ."""
+    from tiny_audio_b200.projectors import PROJECTOR_CLASSES
+    cfg = po.small_config()
+
+    class Cfg:
+        encoder_dim, llm_dim, qformer_window_size, downsample_rate = cfg.enc_dim, cfg.lm_dim, po.QF_WINDOW, po.QF_DOWNSAMPLE
+        qformer_hidden_size, qformer_num_layers, qformer_num_heads, qformer_intermediate_size = None, po.QF_LAYERS, po.QF_HEADS, None
+    w = po.init_qformer_weights(cfg, seed=77)
+    m = PROJECTOR_CLASSES["qformer"](Cfg()).cuda()
+    m.load_state_dict(w, strict=True)
+    m.train()
+    m.p_attn = 0.0
+    recorded = []
+    orig = m._drop_mask
+
+    def recording(rows, H, p, device):
+        t = orig(rows, H, p, device)
+        assert t is not None and p == 0.1
+        recorded.append(t.detach().cpu())
+        return t
+    m._drop_mask = recording
+    torch.manual_seed(5)
+    x = torch.randn(2, 47, cfg.enc_dim, generator=torch.Generator().manual_seed(9)).bfloat16()
+    y = m(x.cuda())
+    assert len(recorded) == 1 + 3 * po.QF_LAYERS and all(0.85 < float((t > 0).float().mean()) < 0.95 for t in recorded)
+    wr = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    ref = po.qformer_projector_forward(wr, x.float(), cfg, drop_masks=recorded)
+    assert y.shape == ref.shape
+    e_out = rel(y, ref)
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6))
+    (ref * g).sum().backward()
+    (y * g.cuda()).sum().backward()
+    worst = 0.0
+    gmax = max(float(t.grad.norm()) for t in wr.values() if t.grad is not None)
+    for k, p in m.named_parameters():
+        r = wr[k].grad
+        if r is None or float(r.norm()) < 1e-5 * gmax:
+            assert p.grad is None or float(p.grad.float().norm()) < 1e-3 * gmax, k
+            continue
+        e = rel(p.grad, r)
+        worst = max(worst, e)
+        assert e < 6e-2, f"{k}: {e}"
+    print(f"[qformer dropout] out rel err {e_out:.3e}, worst grad rel err {worst:.3e}")
+    assert e_out < 2e-2
+
+
 @pytest.mark.parametrize("kind", ["mosa", "moe"])
 def test_mixture_projector_modules_vs_oracle(cuda, kind):
     """MOSAProjector / MoEAudioProjector in isolation on diverse (random) encoder frames, so that every expert is selected by

@@ -259,6 +259,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
         "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// warm L2 with the box at {c0, c1} (no shared-memory destination, nothing to wait on)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)

@@ -996,9 +996,24 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                     __syncwarp();
                 };
+                // the stash streams from HBM (it was written a whole forward pass ago): warm L2 two tiles ahead so that the loads below,
+                // of which only two per group can be in flight, see L2 latency
+                constexpr uint32_t PF = 2 * CPT;
+                auto prefetch = [&](uint32_t n) {
+                    if (n >= total) return;
+                    int x, y;
+                    coords(n, x, y);
+                    if (issuer) {
+                        tma_prefetch_l2_2d(&tmC2, x, y);
+                        tma_prefetch_l2_2d(&tmC2, x + 64, y);
+                    }
+                };
                 if (total > 0) load(0);
                 if (total > 1) load(1);
+                for (uint32_t n = 2; n < PF; ++n) prefetch(n);
                 for (uint32_t n = 0; n < total; ++n) {
+                    prefetch(n + PF);
+                    __syncwarp();
                     mbar_wait(&str[n & 1u], (n >> 1) & 1u);
                     int x, y;
                     coords(n, x, y);

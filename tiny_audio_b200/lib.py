@@ -103,6 +103,12 @@ _SIGS = {
     "ta_cast_f32_bf16": ([P, P, c_ll, P], c_int),
     "ta_frame_stack": ([P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
     "ta_frame_keep_mask": ([P, P, c_ll, c_int, P], c_int),
+    "ta_add_layernorm_fwd": ([P, P, P, c_ll, P, P, P, c_ll, P, P, P, c_ll, c_int, c_float, P], c_int),
+    "ta_add_layernorm_bwd": ([P, P, P, P, P, c_ll, P, P, c_ll, P, P, P, P, P, P, c_ll, c_int, P], c_int),
+    "ta_add_layernorm_bwd_partial_floats": ([c_int], c_ll),
+    "ta_gelu_fwd_bf16": ([P, P, c_ll, P], c_int),
+    "ta_gelu_bwd_bf16": ([P, P, P, c_ll, P], c_int),
+    "ta_colsum_bf16": ([P, c_ll, P, c_ll, c_int, P], c_int),
     "ta_label_rows": ([P, c_int, c_int, P, P, P, P], c_int),
     "ta_assemble_prompts": ([P, P, P, P, c_int, P, c_int, P, c_int, c_ll, c_ll, c_int, c_int, P, P, P, P], c_int),
     "ta_window_attn_fwd": ([P, P, P, P, P, c_ll, c_int, c_int, c_int, c_int, c_float, P], c_int),

@@ -134,6 +134,18 @@ class MLPAudioProjector(nn.Module):
                                      self.k, self.norm.variance_epsilon)
 
 
+def _bf16_weight(w: torch.Tensor) -> torch.Tensor:
+    """bf16 GEMM operand of a (usually fp32 master) weight: the library's cast kernel, no ATen copy."""
+    w = w.detach()
+    if w.dtype == torch.bfloat16:
+        return w.contiguous()
+    if w.dtype == torch.float32 and w.is_contiguous() and w.is_cuda:
+        out = torch.empty(w.shape, device=w.device, dtype=torch.bfloat16)
+        L.check(L.load().ta_cast_f32_bf16(L.ptr(w), L.ptr(out), w.numel(), L.stream_ptr()))
+        return out
+    return w.to(torch.bfloat16).contiguous()
+
+
 class _TcLinearFn(torch.autograd.Function):
     """y = x W^T + b on the tcgen05 GEMM (bf16 operands, fp32 accumulate), with dgrad and wgrad on the same kernel:
     dx = dy W,  dW = dy^T x (fp32 out; the TN form of the GEMM reads both row-major activations as MN-major operands, no
@@ -145,7 +157,7 @@ class _TcLinearFn(torch.autograd.Function):
         L.require_cuda(x, w)
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1]).to(BF16).contiguous()
-        wb = w.detach().to(BF16).contiguous()
+        wb = _bf16_weight(w)
         bias = b.detach().float().contiguous() if b is not None else None
         out = L.gemm(x2, wb, epi=L.EPI_BF16, bias=bias)
         ctx.save_for_backward(x2, wb)
@@ -182,7 +194,9 @@ class _TcLinearFn(torch.autograd.Function):
                 L.check(lib.ta_transpose_bf16(L.ptr(x2), L.ptr(xt), M, K, K, Mp, st))
                 dw = L.gemm(dyt, xt, epi=L.EPI_F32, k=M).to(wdt)
         if bdt is not None and ctx.needs_input_grad[2]:
-            db = dy2.float().sum(0).to(bdt)
+            db32 = torch.empty(N, device=dy2.device, dtype=F32)
+            L.check(lib.ta_colsum_bf16(L.ptr(dy2), N, L.ptr(db32), M, N, st))
+            db = db32.to(bdt)
         return dx, dw, db
 
 
@@ -236,13 +250,87 @@ def window_attention(q, k, v, heads: int, dropout_p: float = 0.0, training: bool
     return _WindowAttnFn.apply(q, k, v, mask, heads)
 
 
+class _AddLayerNormFn(torch.autograd.Function):
+    """(y fp32, y bf16) = LayerNorm(bf16(o) * mask + resid[row % resid_rows]) * post_mask   in one kernel, and its backward in one
+    kernel (csrc/qformer_glue.cu): Blip2QFormerSelfOutput / Blip2QFormerOutput (HF:models/blip_2/modeling_blip_2.py:637-648,693-704)
+    and the query LayerNorm + dropout (:985-986).  `mask` / `post_mask` are dropout multipliers (0 or 1/(1-p)) or None.  The bf16 copy
+    feeds the next tcgen05 linear without a cast kernel; its gradient arrives as a second (bf16) cotangent."""
+
+    @staticmethod
+    def forward(ctx, o, mask, resid, w, b, post_mask, rows, eps):
+        from .engine import BF16, F32
+        lib = L.load()
+        L.require_cuda(resid, w, b)
+        ctx.set_materialize_grads(False)       # an unused output (the last block's fp32 copy) arrives as None, not as a zero tensor
+        H = w.shape[0]
+        dev = w.device
+        o2 = o.reshape(rows, H).contiguous() if o is not None else None
+        r2 = resid.reshape(-1, H).float().contiguous()
+        w32, b32 = w.detach().float().contiguous(), b.detach().float().contiguous()
+        m2 = mask.reshape(rows, H).contiguous() if mask is not None else None
+        pm2 = post_mask.reshape(-1, H).contiguous() if post_mask is not None else None
+        y32 = torch.empty(rows, H, device=dev, dtype=F32)
+        y16 = torch.empty(rows, H, device=dev, dtype=BF16)
+        stats = torch.empty(rows, 2, device=dev, dtype=F32)
+        L.check(lib.ta_add_layernorm_fwd(L.ptr(o2), L.ptr(m2), L.ptr(r2), r2.shape[0], L.ptr(w32), L.ptr(b32), L.ptr(pm2),
+                                         pm2.shape[0] if pm2 is not None else 0, L.ptr(y32), L.ptr(y16), L.ptr(stats), rows, H, eps,
+                                         L.stream_ptr()))
+        ctx.save_for_backward(o2, m2, r2, w32, pm2, stats)
+        ctx.meta = (rows, H, o.shape if o is not None else None, resid.shape, w.dtype, b.dtype, resid.dtype)
+        return y32, y16
+
+    @staticmethod
+    def backward(ctx, g32, g16):
+        from .engine import BF16, F32
+        lib = L.load()
+        if g32 is None and g16 is None:
+            return (None,) * 8
+        o2, m2, r2, w32, pm2, stats = ctx.saved_tensors
+        rows, H, o_shape, r_shape, wdt, bdt, rdt = ctx.meta
+        dev = w32.device
+        g32c = g32.reshape(rows, H).float().contiguous() if g32 is not None else None
+        g16c = g16.reshape(rows, H).contiguous() if g16 is not None else None
+        d_o = torch.empty(rows, H, device=dev, dtype=BF16) if (o2 is not None and ctx.needs_input_grad[0]) else None
+        d_r = torch.empty(r2.shape, device=dev, dtype=F32) if ctx.needs_input_grad[2] else None
+        dw = torch.empty(H, device=dev, dtype=F32)
+        db = torch.empty(H, device=dev, dtype=F32)
+        scratch = torch.empty(lib.ta_add_layernorm_bwd_partial_floats(H), device=dev, dtype=F32)
+        L.check(lib.ta_add_layernorm_bwd(L.ptr(g32c), L.ptr(g16c), L.ptr(o2), L.ptr(m2), L.ptr(r2), r2.shape[0], L.ptr(w32), L.ptr(pm2),
+                                         pm2.shape[0] if pm2 is not None else 0, L.ptr(stats), L.ptr(d_o), L.ptr(d_r), L.ptr(dw), L.ptr(db),
+                                         L.ptr(scratch), rows, H, L.stream_ptr()))
+        return (d_o.view(o_shape) if d_o is not None else None, None, d_r.view(r_shape).to(rdt) if d_r is not None else None, dw.to(wdt),
+                db.to(bdt), None, None, None)
+
+
+class _GeluFn(torch.autograd.Function):
+    """Exact-erf GELU on bf16 storage (Blip2QFormerIntermediate, hidden_act = "gelu"; HF:models/blip_2/modeling_blip_2.py:677-689)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        L.require_cuda(x)
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        L.check(L.load().ta_gelu_fwd_bf16(L.ptr(xc), L.ptr(y), xc.numel(), L.stream_ptr()))
+        ctx.save_for_backward(xc)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        gc = g.to(torch.bfloat16).contiguous()
+        dx = torch.empty_like(xc)
+        L.check(L.load().ta_gelu_bwd_bf16(L.ptr(xc), L.ptr(gc), L.ptr(dx), xc.numel(), L.stream_ptr()))
+        return dx
+
+
 class QFormerAudioProjector(nn.Module):
     """BLIP-2 QFormer projector with learnable queries (reference: tiny_audio/projectors.py:359-475; arithmetic of
     HF:models/blip_2/modeling_blip_2.py:537-1042).  Parameter names and initialisation are the reference's (the HF
     `Blip2QFormerModel` is instantiated as the owner of the weights, exactly as the reference does), so checkpoints
     interchange.  Every linear -- q/k/v/o of self- and cross-attention, the FFN, the final projection; forward, dgrad and
     wgrad -- runs on the tcgen05 GEMM; the 3x3 / 3x15 softmax attention is one warp per (window, head) in csrc/window_attn.cu
-    (forward and backward); LayerNorm, GELU and the residual adds are PyTorch glue."""
+    (forward and backward); dropout + residual + LayerNorm is one kernel each way and the exact GELU another (csrc/qformer_glue.cu);
+    PyTorch supplies only the dropout masks (its Philox stream, so seeding behaves like nn.Dropout)."""
 
     def __init__(self, config):
         super().__init__()
@@ -273,26 +361,33 @@ class QFormerAudioProjector(nn.Module):
         nblocks = (input_length + self.window_size - 1) // self.window_size
         return nblocks * self.num_queries
 
-    def _attend(self, att, x, kv_src):
-        """Blip2QFormerMultiHeadAttention + SelfOutput: x [W, q, H] queries, kv_src [W, n, H] keys/values."""
-        F_ = torch.nn.functional
-        Wn, nq, H = x.shape
+    def _drop_mask(self, rows: int, H: int, p: float, device):
+        """[rows, H] fp32 multipliers 0 or 1/(1-p) from torch's RNG, or None when dropout is off."""
+        if not self.training or p <= 0.0:
+            return None
+        return torch.nn.functional.dropout(torch.ones(rows, H, device=device, dtype=torch.float32), p, True)
+
+    def _attend(self, att, x32, x16, kv16):
+        """Blip2QFormerMultiHeadAttention + SelfOutput: x [W, q, H] queries (fp32 residual + its bf16 copy), kv16 [W, n, H] keys/values."""
+        Wn, nq, H = x16.shape
         hd = H // self.num_heads
-        q = tc_linear(x, att.attention.query.weight, att.attention.query.bias)
-        k = tc_linear(kv_src, att.attention.key.weight, att.attention.key.bias)
-        v = tc_linear(kv_src, att.attention.value.weight, att.attention.value.bias)
+        q = tc_linear(x16, att.attention.query.weight, att.attention.query.bias)
+        k = tc_linear(kv16, att.attention.key.weight, att.attention.key.bias)
+        v = tc_linear(kv16, att.attention.value.weight, att.attention.value.bias)
         if self.fused_attention:
             ctx = window_attention(q, k, v, self.num_heads, self.p_attn, self.training)
         else:       # PyTorch glue (A/B reference for the kernel)
+            F_ = torch.nn.functional
             q = q.view(Wn, nq, self.num_heads, hd).transpose(1, 2).float()
             k = k.view(Wn, -1, self.num_heads, hd).transpose(1, 2).float()
             v = v.view(Wn, -1, self.num_heads, hd).transpose(1, 2).float()
             probs = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
             probs = F_.dropout(probs, self.p_attn, self.training)
-            ctx = (probs @ v).transpose(1, 2).reshape(Wn, nq, H)
-        o = tc_linear(ctx, att.output.dense.weight, att.output.dense.bias).float()
-        o = F_.dropout(o, self.p_hidden, self.training)
-        return F_.layer_norm(o + x.float(), (H,), att.output.LayerNorm.weight.float(), att.output.LayerNorm.bias.float(), self.ln_eps)
+            ctx = (probs @ v).transpose(1, 2).reshape(Wn, nq, H).to(torch.bfloat16)
+        o = tc_linear(ctx, att.output.dense.weight, att.output.dense.bias)
+        y32, y16 = _AddLayerNormFn.apply(o, self._drop_mask(Wn * nq, H, self.p_hidden, o.device), x32, att.output.LayerNorm.weight,
+                                         att.output.LayerNorm.bias, None, Wn * nq, self.ln_eps)
+        return y32.view(Wn, nq, H), y16.view(Wn, nq, H)
 
     def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
         if not hidden_states.is_cuda:
@@ -307,21 +402,24 @@ class QFormerAudioProjector(nn.Module):
         if pad > 0:
             x_enc = F_.pad(x_enc, (0, 0, 0, pad))
         Wn = B * nblocks
-        x_enc = x_enc.reshape(Wn, self.window_size, -1)
+        x_enc = x_enc.reshape(Wn, self.window_size, -1).to(torch.bfloat16)
         qf = self.qformer
-        H = self.query.shape[-1]
-        x = F_.layer_norm(self.query.float(), (H,), qf.layernorm.weight.float(), qf.layernorm.bias.float(), self.ln_eps)
-        x = F_.dropout(x, self.p_hidden, self.training).expand(Wn, -1, -1)
+        nq, H = self.num_queries, self.query.shape[-1]
+        # the reference expands the query to every window BEFORE layernorm + dropout (projectors.py:461, HF :985-986): one LayerNorm row per
+        # (window, query) with its own dropout mask; the kernel reads the 3 query rows through the row-broadcast residual slot
+        x32, x16 = _AddLayerNormFn.apply(None, None, self.query.reshape(nq, H), qf.layernorm.weight, qf.layernorm.bias,
+                                         self._drop_mask(Wn * nq, H, self.p_hidden, x_enc.device), Wn * nq, self.ln_eps)
+        x32, x16 = x32.view(Wn, nq, H), x16.view(Wn, nq, H)
         for layer in qf.encoder.layer:
-            x = self._attend(layer.attention, x, x)
-            x = self._attend(layer.crossattention, x, x_enc)
-            h = tc_linear(x, layer.intermediate_query.dense.weight, layer.intermediate_query.dense.bias)
-            h = F_.gelu(h)
-            f = tc_linear(h, layer.output_query.dense.weight, layer.output_query.dense.bias).float()
-            f = F_.dropout(f, self.p_hidden, self.training)
-            x = F_.layer_norm(f + x, (H,), layer.output_query.LayerNorm.weight.float(), layer.output_query.LayerNorm.bias.float(),
-                              self.ln_eps)
-        out = tc_linear(x.reshape(B, nblocks * self.num_queries, H), self.linear.weight, self.linear.bias)
+            x32, x16 = self._attend(layer.attention, x32, x16, x16)
+            x32, x16 = self._attend(layer.crossattention, x32, x16, x_enc)
+            h = tc_linear(x16, layer.intermediate_query.dense.weight, layer.intermediate_query.dense.bias)
+            h = _GeluFn.apply(h)
+            f = tc_linear(h, layer.output_query.dense.weight, layer.output_query.dense.bias)
+            y32, y16 = _AddLayerNormFn.apply(f, self._drop_mask(Wn * nq, H, self.p_hidden, f.device), x32, layer.output_query.LayerNorm.weight,
+                                             layer.output_query.LayerNorm.bias, None, Wn * nq, self.ln_eps)
+            x32, x16 = y32.view(Wn, nq, H), y16.view(Wn, nq, H)
+        out = tc_linear(x16.reshape(B, nblocks * nq, H), self.linear.weight, self.linear.bias)
         return out
 
 

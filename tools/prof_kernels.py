@@ -25,6 +25,26 @@ if "gemm" in which:
     gu = torch.empty(M, N, device=dev, dtype=BF16)
     for _ in range(3):
         L.gemm(a2, w2, epi=L.EPI_SWIGLU, out2=gu)
+if "swiglu_bwd" in which:
+    M, D, Fd = 14848, 1024, 3072
+    gu = torch.randn(M, 2 * Fd, device=dev, dtype=BF16)
+    dy = torch.randn(M, D, device=dev, dtype=BF16)
+    wd_t = torch.randn(Fd, D, device=dev, dtype=BF16) * 0.03
+    dgu = torch.empty(M, 2 * Fd, device=dev, dtype=BF16)
+    for _ in range(3):
+        L.gemm(dy, wd_t, epi=L.EPI_SWIGLU_BWD, aux=gu, out=dgu)
+    torch.cuda.synchronize()
+if "gemm_cmp" in which:
+    # this library's pair GEMM next to cuBLAS on the encoder fc1 shape and on 8192^3 (what tile / cluster shape does the library pick?)
+    for (M, N, K) in ((48000, 5120, 1280), (8192, 8192, 8192)):
+        a = torch.randn(M, K, device=dev, dtype=BF16)
+        w = torch.randn(N, K, device=dev, dtype=BF16) * 0.03
+        out = torch.empty(M, N, device=dev, dtype=BF16)
+        for _ in range(2):
+            L.gemm(a, w, epi=L.EPI_BF16, out=out)
+            torch.matmul(a, w.t(), out=out)
+        torch.cuda.synchronize()
+        del a, w, out
 if "attn_enc" in which:
     B, S, H, hd = 32, 1500, 20, 64
     qkv = torch.randn(B, S, 3 * H * hd, device=dev, dtype=BF16)
