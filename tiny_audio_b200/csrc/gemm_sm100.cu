@@ -679,33 +679,36 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
 
 // ----------------------------------------------------------------------------------------------
 // SwiGLU-backward epilogue, in place through shared memory (pair kernel, ep.aux_tma).
-//   A "chunk" is 32 h columns of this CTA's 128 accumulator rows.  Its (gate, up) stash values -- two [128 x 32] bf16 boxes, 8 KB each,
-//   SWIZZLE_64B -- are brought in by TMA two chunks ahead by the group's agent warp (warp 2 + grp); every epilogue thread reads ITS
-//   row of both boxes, overwrites it with (d gate, d up) and the agent stores the two boxes to the interleaved [M, 2F] gradient,
-//   which has the stash's layout.  No global loads in the epilogue threads, no store-drain on their path: they only wait on
-//   ld_full[set] (TMA landed) and signal st_ready[set] (row rewritten).  Replaces the per-thread 128-bit global loads + staged stores
-//   that left the kernel at 613 TFLOP/s (tensor pipe 33 % active, profiles/r02_c01_ncu_lm_gemm.txt).
+//   A "chunk" is 64 h columns of this CTA's 128 accumulator rows.  Its (gate, up) stash values -- two [128 x 64] bf16 boxes, 16 KB
+//   each, SWIZZLE_128B, i.e. whole 128-byte lines of the interleaved [M, 2F] layout -- are brought in by TMA by the agent warp
+//   (warp 2), two chunks ahead; BOTH epilogue groups work on the same chunk (group g owns columns [32 g, 32 g + 32) of it = 16-byte
+//   pieces 4g..4g+3 of every 128-byte row): each thread reads ITS row of both boxes, overwrites it with (d gate, d up), and the agent
+//   stores the two boxes to the gradient tensor, which has the stash's layout.  No global loads in the epilogue threads and no
+//   store-drain on their path: they wait on ld_full[set] (TMA landed) and signal st_ready[set] (rows rewritten).
+//   History: per-thread 128-bit global loads + staged stores ran at 600 TFLOP/s (tensor pipe 33 % active, profiles/
+//   r02_c01_ncu_lm_gemm.txt); 32-column in-place boxes (64-byte rows) reached 840 but wrote half lines, which cost 145 MB of DRAM
+//   fill reads per launch (profiles/r02_c19_ncu_swiglu_bwd_tma.txt).
 // ----------------------------------------------------------------------------------------------
-constexpr int SWB_SET_BYTES = 2 * 8192;    // gate box + up box
+constexpr int SWB_SET_BYTES = 2 * 16384;    // gate box + up box
 
 template <int BN>
-__device__ __forceinline__ void epilogue_swiglu_bwd_inplace(uint32_t taddr, int grp, int r, int lane, uint8_t* gbuf, uint64_t* ldf,
+__device__ __forceinline__ void epilogue_swiglu_bwd_inplace(uint32_t taddr, int grp, int r, int lane, uint8_t* sbuf, uint64_t* ldf,
                                                             uint64_t* str, uint32_t& n) {
-    constexpr int CPT = BN / 64;               // chunks per tile and group
-    const int sw = (r >> 1) & 3;               // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
+    constexpr int CPT = BN / 64;               // chunks per tile
+    const int sw = r & 7;                      // SWIZZLE_128B: 16-byte piece index ^= row & 7
 #pragma unroll 1
     for (int i = 0; i < CPT; ++i, ++n) {
         const uint32_t set = n & 1u;
         uint32_t rr[32];
-        tmem_ld_32x32(taddr + (uint32_t)((grp * CPT + i) * 32), rr);
+        tmem_ld_32x32(taddr + (uint32_t)(i * 64 + grp * 32), rr);
         mbar_wait(&ldf[set], (n >> 1) & 1u);
-        uint8_t* gp = gbuf + set * SWB_SET_BYTES + r * 64;
-        uint8_t* up = gp + 8192;
+        uint8_t* gp = sbuf + set * SWB_SET_BYTES + r * 128;
+        uint8_t* up = gp + 16384;
         uint4 g4[4], u4[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            g4[k] = *reinterpret_cast<const uint4*>(gp + ((k ^ sw) << 4));
-            u4[k] = *reinterpret_cast<const uint4*>(up + ((k ^ sw) << 4));
+            g4[k] = *reinterpret_cast<const uint4*>(gp + (((4 * grp + k) ^ sw) << 4));
+            u4[k] = *reinterpret_cast<const uint4*>(up + (((4 * grp + k) ^ sw) << 4));
         }
         tmem_ld_wait();
 #pragma unroll
@@ -728,8 +731,8 @@ __device__ __forceinline__ void epilogue_swiglu_bwd_inplace(uint32_t taddr, int 
                 og[t] = pack_bf16x2(dg[0], dg[1]);
                 ou[t] = pack_bf16x2(du[0], du[1]);
             }
-            *reinterpret_cast<uint4*>(gp + ((k ^ sw) << 4)) = make_uint4(og[0], og[1], og[2], og[3]);
-            *reinterpret_cast<uint4*>(up + ((k ^ sw) << 4)) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+            *reinterpret_cast<uint4*>(gp + (((4 * grp + k) ^ sw) << 4)) = make_uint4(og[0], og[1], og[2], og[3]);
+            *reinterpret_cast<uint4*>(up + (((4 * grp + k) ^ sw) << 4)) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -782,8 +785,16 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                  "h"((uint16_t)3)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on rank 0's copy of `bar`
+// arrive on rank 0's copy of `bar`.  Used for "this warp has read its accumulator quadrant out of TMEM" (tempty): the reads were
+// completed by tcgen05.wait::ld and ordered by tcgen05.fence::before_thread_sync, no memory written by this thread has to become
+// visible to the MMA issuer, so the arrive is RELAXED -- .release.cluster compiles to MEMBAR.ALL.CTA + ERRBAR, which was 14 % of the
+// epilogue warps' stall samples on the SwiGLU-backward GEMM (profiles/r02_c19_ncu_swiglu_bwd_tma.txt)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+#ifdef TA_TEMPTY_RELEASE
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+#else
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+#endif
 }
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst) {
@@ -842,7 +853,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint64_t* tfull = bars + 2 * C::STAGES;
     uint64_t* tempty = bars + 2 * C::STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-    uint64_t* swb_ld_full = bars + 20;       // [group][set]: in-place SwiGLU-backward epilogue (ep.aux_tma)
+    uint64_t* swb_ld_full = bars + 20;       // [set]: in-place SwiGLU-backward epilogue (ep.aux_tma)
     uint64_t* swb_st_ready = bars + 24;
     static_assert(2 * C::STAGES + 5 <= 20, "barrier area layout");
     float* s_bias_all = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);   // [2][BN]
@@ -876,9 +887,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_init(&tempty[s], 16);
         }
         if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
-            for (int s = 0; s < 4; ++s) {
+            for (int s = 0; s < 2; ++s) {
                 mbar_init(&swb_ld_full[s], 1);
-                mbar_init(&swb_st_ready[s], 4);
+                mbar_init(&swb_st_ready[s], 8);      // one arrive per epilogue warp of both groups
             }
         }
         mbar_fence_init();
@@ -966,38 +977,36 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (as == 0) aphase ^= 1;
             }
         }
-    } else if (EPI == TA_EPI_SWIGLU_BWD && (warp == 2 || warp == 3)) {
-        // ===================== SwiGLU-backward stash agent of epilogue group (warp - 2) =====================
+    } else if (EPI == TA_EPI_SWIGLU_BWD && warp == 2) {
+        // ===================== SwiGLU-backward stash agent =====================
         if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
             if (ep.aux_tma) {
                 constexpr int CPT = BN / 64;
-                const int grp = warp - 2;
-                uint8_t* gbuf = smStage + grp * 2 * STG_BYTES;
-                uint64_t* ldf = swb_ld_full + 2 * grp;
-                uint64_t* str = swb_st_ready + 2 * grp;
+                uint64_t* ldf = swb_ld_full;
+                uint64_t* str = swb_st_ready;
                 const bool issuer = elect_one();
                 const int my_tiles = pair < num_work ? (num_work - pair + n_pairs - 1) / n_pairs : 0;
                 const uint32_t total = (uint32_t)(my_tiles * CPT);
                 auto coords = [&](uint32_t n, int& x, int& y) {
                     const int tile = pair + (int)(n / CPT) * n_pairs;
                     const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
-                    const int col = n_blk * BN + (grp * CPT + (int)(n % CPT)) * 32;       // first h column of the chunk
-                    x = (col >> 6) * 128 + (col & 63);                                     // its gate columns in the [M, 2F] layout
+                    const int col = n_blk * BN + (int)(n % CPT) * 64;      // first h column of the chunk
+                    x = 2 * col;                                            // its gate columns in the interleaved [M, 2F] layout
                     y = m_blk * 2 * BM + (int)rank * BM;
                 };
                 auto load = [&](uint32_t n) {
                     int x, y;
                     coords(n, x, y);
-                    uint8_t* dst = gbuf + (n & 1u) * SWB_SET_BYTES;
+                    uint8_t* dst = smStage + (n & 1u) * SWB_SET_BYTES;
                     if (issuer) {
                         mbar_arrive_expect_tx(&ldf[n & 1u], SWB_SET_BYTES);
                         tma_load_2d(dst, &tmC2, &ldf[n & 1u], x, y);
-                        tma_load_2d(dst + 8192, &tmC2, &ldf[n & 1u], x + 64, y);
+                        tma_load_2d(dst + 16384, &tmC2, &ldf[n & 1u], x + 64, y);
                     }
                     __syncwarp();
                 };
                 // the stash streams from HBM (it was written a whole forward pass ago): warm L2 two tiles ahead so that the loads below,
-                // of which only two per group can be in flight, see L2 latency
+                // of which only two can be in flight, see L2 latency
                 constexpr uint32_t PF = 2 * CPT;
                 auto prefetch = [&](uint32_t n) {
                     if (n >= total) return;
@@ -1017,10 +1026,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     mbar_wait(&str[n & 1u], (n >> 1) & 1u);
                     int x, y;
                     coords(n, x, y);
-                    const uint8_t* src = gbuf + (n & 1u) * SWB_SET_BYTES;
+                    const uint8_t* src = smStage + (n & 1u) * SWB_SET_BYTES;
                     if (issuer) {
                         tma_store_2d(&tmC, src, x, y);
-                        tma_store_2d(&tmC, src + 8192, x + 64, y);
+                        tma_store_2d(&tmC, src + 16384, x + 64, y);
                         tma_store_commit();
                         if (n + 2 < total) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
@@ -1064,7 +1073,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             bool done = false;
             if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
                 if (ep.aux_tma) {
-                    epilogue_swiglu_bwd_inplace<BN>(taddr, grp, sg.r, lane, sg.buf, swb_ld_full + 2 * grp, swb_st_ready + 2 * grp, swb_n);
+                    epilogue_swiglu_bwd_inplace<BN>(taddr, grp, sg.r, lane, smStage, swb_ld_full, swb_st_ready, swb_n);
                     done = true;
                 }
             }
@@ -1376,11 +1385,11 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
             // output maps for the TMA-store epilogue: [rows, width] with 128-byte wide sub-tiles
             const bool swb_tma = (epi == TA_EPI_SWIGLU_BWD) && g_swiglu_bwd_tma;
             e2.aux_tma = swb_tma ? 1 : 0;
-            r2 = make_map(&tc, e2.out, rows, out_cols, e->ldo, BM, f32out, swb_tma ? 32 : 0);
+            r2 = make_map(&tc, e2.out, rows, out_cols, e->ldo, BM, f32out);
             if (r2) return r2;
             tc2 = tc;
             if (swb_tma) {
-                r2 = make_map(&tc2, e2.aux, rows, 2LL * N, e->ldaux, BM, false, 32);
+                r2 = make_map(&tc2, e2.aux, rows, 2LL * N, e->ldaux, BM, false);
                 if (r2) return r2;
             }
             if (epi == TA_EPI_SWIGLU && e->out2) {
