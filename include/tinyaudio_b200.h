@@ -116,6 +116,7 @@ int ta_attn_bwd(const void* q, const void* k, const void* v, const void* o, cons
  * HBM-bound building blocks (exported for unit parity tests; the engines below call them internally)
  * ---------------------------------------------------------------------------------------------- */
 int ta_im2col_k3(const void* x /*bf16 [B,T,C]*/, void* out /*bf16 [B*T2, 3C]*/, int B, int T, int C, int stride, void* stream);
+int ta_layernorm_set_reverse(int on); /* 1 (default): rows are processed last-to-first (the tail of the producer's output is still in L2) */
 int ta_layernorm_bf16(const void* x, const float* w, const float* b, void* y, long long rows, int D, float eps, void* stream);
 int ta_rmsnorm_f32(const float* x, const float* w, void* y_bf16, const int* row_index, long long rows, int D, float eps, void* stream);
 int ta_rmsnorm_f32_bwd(const void* dy_bf16, const float* x, const float* w, float* dx, const int* row_index, long long rows,

@@ -52,10 +52,15 @@ __global__ void im2col_k3_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
 template <int MAXV>   // MAXV = max 8-element vectors per lane
 __global__ void __launch_bounds__(256)
 layernorm_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                      bf16* __restrict__ y, long long rows, int D, float eps) {
+                      bf16* __restrict__ y, long long rows, int D, float eps, int reverse) {
     TA_PDL_ENTRY();
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
+    // reverse: walk the rows from the end.  The producing GEMM wrote x in ascending row order, so its LAST rows are the ones still in the
+    // 126 MB L2 (x alone is 123 MB at 48 000 x 1280); and the consuming GEMM reads y from row 0, which this order writes last.
+    // Same-box A/B: step 122.4 / 123.1 -> 121.8 / 121.8 ms (profiles/r02_c21_*).  (A persistent variant that prefetches the next row
+    // into registers was NOT faster: 3.65 vs 3.53 ms per step for the 65 launches, call 22.)
+    if (reverse) row = rows - 1 - row;
     const int lane = threadIdx.x & 31;
     const int nv = D / 256;   // vectors per lane
     // the row stays PACKED (bf16) in registers between the three passes: 4 instead of 8 registers per vector, so twice as many
@@ -798,12 +803,13 @@ int k_im2col_k3(const bf16* x, bf16* out, int B, int T, int C, int stride, cudaS
     return 0;
 }
 
+int g_ln_reverse = 1;   // ta_layernorm_set_reverse: A/B switch for the row order of the encoder LayerNorm (L2 reuse, see the kernel)
 int k_layernorm_bf16(const bf16* x, const float* w, const float* b, bf16* y, long long rows, int D, float eps, cudaStream_t st) {
     TA_REQUIRE(D % 256 == 0 && D <= 2048, "layernorm: D=%d must be a multiple of 256 and <= 2048", D);
     const int wpb = 8;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    if (D <= 1280) TA_KERNEL_LAUNCH(layernorm_bf16_kernel<5>, grid, wpb * 32, 0, st, x, w, b, y, rows, D, eps);
-    else TA_KERNEL_LAUNCH(layernorm_bf16_kernel<8>, grid, wpb * 32, 0, st, x, w, b, y, rows, D, eps);
+    if (D <= 1280) TA_KERNEL_LAUNCH(layernorm_bf16_kernel<5>, grid, wpb * 32, 0, st, x, w, b, y, rows, D, eps, g_ln_reverse);
+    else TA_KERNEL_LAUNCH(layernorm_bf16_kernel<8>, grid, wpb * 32, 0, st, x, w, b, y, rows, D, eps, g_ln_reverse);
     return 0;
 }
 
@@ -973,6 +979,10 @@ int k_sumsq(const float* g, long long n, float* out, cudaStream_t st) {
 
 TA_API int ta_im2col_k3(const void* x, void* out, int B, int T, int C, int stride, void* stream) {
     return k_im2col_k3((const bf16*)x, (bf16*)out, B, T, C, stride, ST(stream));
+}
+TA_API int ta_layernorm_set_reverse(int on) {
+    g_ln_reverse = on ? 1 : 0;
+    return 0;
 }
 TA_API int ta_layernorm_bf16(const void* x, const float* w, const float* b, void* y, long long rows, int D, float eps, void* stream) {
     return k_layernorm_bf16((const bf16*)x, w, b, (bf16*)y, rows, D, eps, ST(stream));

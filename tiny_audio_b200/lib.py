@@ -87,6 +87,7 @@ _SIGS = {
     "ta_attn_bwd": ([P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
                      c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_int, c_float, P], c_int),
     "ta_im2col_k3": ([P, P, c_int, c_int, c_int, c_int, P], c_int),
+    "ta_layernorm_set_reverse": ([c_int], c_int),
     "ta_layernorm_bf16": ([P, P, P, P, c_ll, c_int, c_float, P], c_int),
     "ta_rmsnorm_f32": ([P, P, P, P, c_ll, c_int, c_float, P], c_int),
     "ta_rmsnorm_f32_bwd": ([P, P, P, P, P, c_ll, c_int, c_float, c_int, P], c_int),
@@ -168,6 +169,8 @@ def load() -> C.CDLL:
         lib.ta_gemm_set_tn_splitk(int(os.environ["TA_GEMM_TN_SPLITK"]))
     if os.environ.get("TA_GEMM_SWIGLU_BWD_TMA") is not None:
         lib.ta_gemm_set_swiglu_bwd_tma(int(os.environ["TA_GEMM_SWIGLU_BWD_TMA"]))
+    if os.environ.get("TA_LN_REVERSE") is not None:
+        lib.ta_layernorm_set_reverse(int(os.environ["TA_LN_REVERSE"]))
     if os.environ.get("TA_GEMM_TAIL_SPLIT") is not None:
         lib.ta_gemm_set_tail_split(int(os.environ["TA_GEMM_TAIL_SPLIT"]))
     if os.environ.get("TA_PDL") is not None:          # effective only in a `make PDL=1` build of the library
