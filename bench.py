@@ -564,8 +564,14 @@ def run_ours(args):
                                                           B, S_e, Hh, Hh, hd_e, 3 * dims.enc_dim, 3 * dims.enc_dim, 3 * dims.enc_dim, dims.enc_dim, 0,
                                                           hd_e ** -0.5, L.stream_ptr())), reps=10)
         f_at = 4.0 * S_e * S_e * hd_e * Hh * B
+        pa = ncu_metric("attn_tc_fwd5_kernel", "")
         roof["encoder_attention"] = {"shape": f"B={B} S={S_e} H={Hh} hd={hd_e}", "us": t_at * 1e6, "tflops": f_at / t_at / 1e12,
-                                     "frac": f_at / t_at / 1e12 / peak,
+                                     "frac": f_at / t_at / 1e12 / peak, "bound": "sfu",
+                                     "gexp2_per_s_per_sm": B * Hh * S_e * ((S_e + 63) // 64 * 64) / t_at / 148.0 / 1e9,
+                                     "mufu_ceiling": "16 exp2 per clk and SM (tools/ubench/sfu4.cu): 31.4 Gexp2/s/SM at 1.965 GHz",
+                                     "tensor_pipe_active_pct_ncu": pa["tensor_pipe_active_pct"] if pa else None,
+                                     "xu_pipe_pct_ncu": pa["xu_pipe_pct"] if pa else None,
+                                     "ncu_source": ({"file": pa["source"], "git_sha": pa["git_sha"]} if pa else None),
                                      "note": "bound by exp2 on the SFUs, not by the tensor pipe (256 FLOP per exponential at head_dim 64)"}
         del a, wt, out, qkv, ao
 

@@ -25,6 +25,15 @@ if "gemm" in which:
     gu = torch.empty(M, N, device=dev, dtype=BF16)
     for _ in range(3):
         L.gemm(a2, w2, epi=L.EPI_SWIGLU, out2=gu)
+if "down" in which:
+    M, D, Fd = 14848, 1024, 3072
+    hh = torch.randn(M, Fd, device=dev, dtype=BF16)
+    wd = torch.randn(D, Fd, device=dev, dtype=BF16) * 0.03
+    resid = torch.zeros(M, D, device=dev, dtype=F32)
+    yy = torch.empty(M, D, device=dev, dtype=F32)
+    for _ in range(3):
+        L.gemm(hh, wd, epi=L.EPI_F32_RESID, resid=resid, out=yy)
+    torch.cuda.synchronize()
 if "swiglu_bwd" in which:
     M, D, Fd = 14848, 1024, 3072
     gu = torch.randn(M, 2 * Fd, device=dev, dtype=BF16)
