@@ -105,8 +105,11 @@ int ta_attn_set_tc(int mode); /* forward-kernel selection.  0: mma.sync referenc
                                  14 (default): tcgen05, encoder shape (head_dim 64, non-causal) on 64-key tiles with three CTAs per SM, other
                                  shapes as mode 1; 2-13, 15, 16: earlier / experimental encoder-shape kernels kept as A/B references
                                  (csrc/attn_tc.cu lists them with their measured times) */
+int ta_attn_set_tc_lm(int variant); /* decoder-shape forward (head_dim 128, causal): 1 (default) = 64-key tiles, two CTAs per SM, K/V ring of 4 slots (3 / 4 / 6 / 8 select the depth; 6 and 8 leave room for one CTA per SM only); 0 = 128-key tiles, one CTA per SM */
+int ta_attn_tc_lm_ring_slots(void);  /* the ring depth in use */
 /* diagnostic timeline of the persistent encoder-attention kernel (tools/attn_trace.py): buf int64 [3][steps][8] device memory, NULL = off */
 int ta_attn_set_trace(void* buf, int steps);
+int ta_attn_set_bwd_variant(int variant); /* decoder attention backward: 2 (default) = 64-query sub-tiles, software-pipelined, dQ^T with its own TMEM buffers; 1 = 128-query serial kernel */
 int ta_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                 float* dsum_ws, float* dq_acc, void* dk, void* dv, int B, int S, int Hq, int Hkv, int head_dim,
                 long long q_rs, long long k_rs, long long v_rs, long long o_rs, long long do_rs, long long dq_rs,

@@ -139,6 +139,9 @@ CASES = {
     "small_b3_ragged": (dict(enc_layers=1, lm_layers=1), 3, 1.5, None, 8, 13),
     "h2048_b2_2s":   (dict(proj_hidden=2048, enc_layers=1, lm_layers=1), 2, 2.0, None, 8, 14),
     "full_b1_4s":    ("full", 1, 4.0, None, 32, 21),
+    # 260 labelled tokens instead of 33: the bf16-vs-fp32 loss noise of ANY two kernels of equal accuracy is ~1e-3 on a 33-token mean
+    # (two attention kernels of this repo differ by 8e-4 there); the 1e-3 parity bound is asserted on this larger sample
+    "full_b4_10s":   ("full", 4, 10.0, None, 64, 22),
     # config 4: QFormer projector (reference in eval mode: its dropout 0.1 has no bit-parity definition)
     "qformer_b2_2s": (dict(enc_layers=1, lm_layers=1, _projector="qformer"), 2, 2.0, None, 8, 15),
     # full decoder fine-tuning (configs/experiments/embedded.yaml:19-33, freeze_language_model: false): LM weight gradients

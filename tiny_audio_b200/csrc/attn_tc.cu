@@ -1571,6 +1571,299 @@ int launch_attn_tc5(const bf16* q, const bf16* k, const bf16* v, bf16* o, float*
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant 6: variant 5's structure (64-key tiles, one thread per query row, warps 0-3 softmax, warp 4 TMA + TMEM, warp 5 MMA issuer)
+// for head_dim 128, causal, GQA, left-padded keys (kv_start) -- the decoder's attention.  Q 32 KB + 4 x 16 KB K/V ring + P 16 KB =
+// 112 KB, TMEM 64 (S) + 128 (O) columns: TWO CTAs per SM.  The decoder's problems are short (S = 464: a query tile sees 2-8 key tiles),
+// so a CTA's prologue / first-load latency / epilogue are as long as its main loop; with one 192 KB CTA per SM (attn_tc_fwd_kernel<128>)
+// nothing ran under them and ncu showed no unit above 24 % (profiles/r02_c23_ncu_top_kernels_summary.txt: 115.6 us, tensor pipe 19 %).
+// Heavy query tiles are scheduled first (qt = gridDim.x - 1 - blockIdx.x).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int HD, int SLOTS>
+struct Att6Cfg {
+    static constexpr int NSUB = HD / 64;
+    static constexpr int Q_BYTES = NSUB * TILE16;                    // 128 rows x HD
+    static constexpr int KV_BYTES = NSUB * TILE8;                    // 64 keys x HD
+    static constexpr int KV_SLOTS = SLOTS;
+    static constexpr int KV_OFF = Q_BYTES;
+    static constexpr int P_OFF = KV_OFF + KV_SLOTS * KV_BYTES;
+    static constexpr int BAR_OFF = P_OFF + TILE16;
+    static constexpr int SMEM = BAR_OFF + (SLOTS <= 4 ? 128 : 256);  // 5 + 2 SLOTS barriers + the TMEM slot
+    static constexpr int TMEM_COLS = (HD == 64) ? 128 : 256;         // S: 64 columns, O: HD columns
+    static constexpr int CTAS = (HD == 64) ? 3 : (SLOTS <= 4 ? 2 : 1);
+};
+
+template <int HD, bool CAUSAL, int SLOTS>
+__global__ void __launch_bounds__(ATT1_THREADS, Att6Cfg<HD, SLOTS>::CTAS)
+attn_tc_fwd6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ O, float* __restrict__ LSE, int S, int Hq, int Hkv,
+                    long long o_rs, float scale_log2, const int* __restrict__ kv_start) {
+    TA_PDL_ENTRY();
+    using C = Att6Cfg<HD, SLOTS>;
+    extern __shared__ __align__(1024) uint8_t smem_al[];
+    uint8_t* smem = smem_al;
+    if (smem_u32(smem) & 1023u) __trap();                 // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* sQ = smem;
+    uint8_t* sKV = smem + C::KV_OFF;
+    uint8_t* sP = smem + C::P_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = bars + 1 + C::KV_SLOTS;
+    uint64_t* s_full = bars + 1 + 2 * C::KV_SLOTS;
+    uint64_t* s_empty = s_full + 1;
+    uint64_t* p_full = s_full + 2;
+    uint64_t* pv_done = s_full + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = (int)gridDim.x - 1 - (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int hk = h / (Hq / Hkv);
+    const int q0 = qt * BQ;
+    const int n_all = (S + BKV5 - 1) / BKV5;
+    const int n_kv = CAUSAL ? min(n_all, 2 * qt + 2) : n_all;       // keys <= q0 + 127
+    const int row_base = b * S;
+    constexpr uint32_t S6_COL = 0, O6_COL = 64;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+            mbar_init(q_full, 1);
+            for (int s = 0; s < C::KV_SLOTS; ++s) {
+                mbar_init(&kv_full[s], 1);
+                mbar_init(&kv_empty[s], 1);
+            }
+            mbar_init(s_full, 1);
+            mbar_init(s_empty, 4);
+            mbar_init(p_full, 4);
+            mbar_init(pv_done, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, C::Q_BYTES);
+#pragma unroll
+            for (int u = 0; u < C::NSUB; ++u) tma_load_2d(sQ + u * TILE16, &tmQ, q_full, h * HD + u * 64, row_base + q0);
+            for (int i = 0; i < 2 * n_kv; ++i) {
+                const int slot = i % C::KV_SLOTS;
+                mbar_wait(&kv_empty[slot], (((uint32_t)i / C::KV_SLOTS) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&kv_full[slot], C::KV_BYTES);
+#pragma unroll
+                for (int u = 0; u < C::NSUB; ++u)
+                    tma_load_2d(sKV + slot * C::KV_BYTES + u * TILE8, (i & 1) ? &tmV : &tmK, &kv_full[slot], hk * HD + u * 64,
+                                row_base + (i >> 1) * BKV5);
+            }
+        }
+    } else if (warp == 5) {
+        // whole warp, warp-uniform operands, one elected lane issues (see variant 5)
+        constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV5);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD) | (1u << 16);   // B operand (V) is MN-major
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const bool leader = elect_one();
+        const uint32_t q_addr = smem_u32(sQ);
+        const uint64_t p_desc = umma_desc_sw128_kmajor(smem_u32(sP));
+        auto issue_s = [&](int j) {
+            const int i = 2 * j, slot = i % C::KV_SLOTS;
+            mbar_wait(&kv_full[slot], ((uint32_t)i / C::KV_SLOTS) & 1u);
+            mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t k_addr = smem_u32(sKV + slot * C::KV_BYTES);
+            if (leader) {
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)      // 64-wide sub-tile (k >> 2), + 32 bytes per 16-wide k step inside it
+                    umma_f16(tb + S6_COL, umma_desc_sw128_kmajor(q_addr + (k >> 2) * TILE16 + (k & 3) * 32),
+                             umma_desc_sw128_kmajor(k_addr + (k >> 2) * TILE8 + (k & 3) * 32), idesc_s, k != 0 ? 1u : 0u);
+                umma_commit(s_full);
+                umma_commit(&kv_empty[slot]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_s(0);
+        for (int j = 0; j < n_kv; ++j) {
+            if (j + 1 < n_kv) issue_s(j + 1);
+            const int i = 2 * j + 1, slot = i % C::KV_SLOTS;
+            mbar_wait(p_full, (uint32_t)j & 1u);
+            mbar_wait(&kv_full[slot], ((uint32_t)i / C::KV_SLOTS) & 1u);
+            tc_fence_after();
+            const uint32_t v_addr = smem_u32(sKV + slot * C::KV_BYTES);
+            if (leader) {
+#pragma unroll
+                for (int k = 0; k < BKV5 / 16; ++k)    // P: + 32 bytes per 16 keys; V: + 16 rows x 128 B; 64-wide head-dim atoms TILE8 apart
+                    umma_f16(tb + O6_COL, p_desc + 2 * k, umma_desc_sw128_mnmajor(v_addr + k * 2048, TILE8), idesc_o, (j | k) != 0 ? 1u : 0u);
+                umma_commit(pv_done);
+                umma_commit(&kv_empty[slot]);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int r = warp * 32 + lane;                     // query row of the tile = TMEM lane
+        const uint32_t t_s = tmem_base + ((uint32_t)(warp * 32) << 16) + S6_COL;
+        const uint32_t t_o = tmem_base + ((uint32_t)(warp * 32) << 16) + O6_COL;
+        float m_ref = -INFINITY, l_sum = 0.f;
+        uint8_t* p_row = sP + r * 128;
+        // left-padded prompts: keys before kv_start[b] are padding.  A real query row (>= kv_start) must not see them; a padding row
+        // keeps plain causal attention so that its (unused) output stays finite.
+        const int k_lo = (kv_start != nullptr && q0 + r >= kv_start[b]) ? kv_start[b] : 0;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(s_full, (uint32_t)j & 1u);
+            tc_fence_after();
+            // my columns e = lo..lim of this tile are real (unmasked) keys
+            int lim = S - j * BKV5 - 1;
+            if (CAUSAL) lim = min(lim, q0 + r - j * BKV5);
+            lim = min(lim, BKV5 - 1);
+            const int lo = k_lo - j * BKV5;
+            const bool full_tile = __all_sync(0xffffffffu, lim >= BKV5 - 1 && lo <= 0);
+            uint32_t v[2][32];
+            tmem_ld_32x32(t_s, v[0]);
+            tmem_ld_32x32(t_s + 32, v[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);            // S_j is in registers: the MMA warp may issue S_{j+1} now
+            if (!full_tile) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i > lim || c * 32 + i < lo) v[c][i] = 0xff800000u;      // -inf
+            }
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[c][i]));
+            const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
+            const bool grow = mx > m_ref + 8.0f;
+            const float m_new = grow ? mx : m_ref;
+            const float alpha = (grow && j > 0) ? ex2_approx(m_ref - m_new) : 1.0f;   // m_ref = -inf (all keys masked so far): 0, O and l are 0
+            m_ref = m_new;
+            if (j > 0) {
+                mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);     // PV_{j-1} has consumed sP and finished updating O
+                tc_fence_after();
+            }
+            float l4[4] = {0.f, 0.f, 0.f, 0.f};
+            const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;     // a tile of masked keys only: exp2(-inf) = 0, never inf - inf
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    float e[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        e[u] = ex2_approx(fmaf(__uint_as_float(v[c][8 * qd + u]), scale_log2, neg_m));     // exp2(-inf) = 0 for masked columns
+                        l4[u & 3] += e[u];
+                    }
+                    uint4 pk;
+                    pk.x = PACK_P(e[0], e[1]);
+                    pk.y = PACK_P(e[2], e[3]);
+                    pk.z = PACK_P(e[4], e[5]);
+                    pk.w = PACK_P(e[6], e[7]);
+                    const int k16 = c * 4 + qd;                       // 16-byte chunk of the 128-byte P row
+                    *reinterpret_cast<uint4*>(p_row + ((k16 ^ (r & 7)) << 4)) = pk;
+                }
+            }
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {             // lazy rescale of O (rare)
+#pragma unroll 1
+                for (int c = 0; c < HD / 32; ++c) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(t_o + c * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st_32x32(t_o + c * 32, o);
+                }
+                tmem_st_wait();
+                l_sum *= alpha;
+            }
+            l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(pv_done, (uint32_t)(n_kv - 1) & 1u);
+        tc_fence_after();
+        const int row = q0 + r;
+        const float inv = 1.0f / l_sum;
+        bf16* orow = O + ((long long)row_base + row) * o_rs + (long long)h * HD;
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_o + c * 32, o);
+            tmem_ld_wait();
+            if (row < S) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(o[8 * qd + 0]) * inv, __uint_as_float(o[8 * qd + 1]) * inv);
+                    u.y = pack_bf16x2(__uint_as_float(o[8 * qd + 2]) * inv, __uint_as_float(o[8 * qd + 3]) * inv);
+                    u.z = pack_bf16x2(__uint_as_float(o[8 * qd + 4]) * inv, __uint_as_float(o[8 * qd + 5]) * inv);
+                    u.w = pack_bf16x2(__uint_as_float(o[8 * qd + 6]) * inv, __uint_as_float(o[8 * qd + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + qd * 8) = u;
+                }
+            }
+        }
+        if (LSE && row < S) LSE[((long long)b * Hq + h) * S + row] = (m_ref + log2f(l_sum)) * 0.69314718055994531f;
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int HD, bool CAUSAL, int SLOTS>
+int launch_attn_tc6s(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* o, float* lse, int B, int S, int Hq, int Hkv,
+                     long long o_rs, float scale, cudaStream_t st, const int* kv_start) {
+    using C = Att6Cfg<HD, SLOTS>;
+    auto kern = attn_tc_fwd6_kernel<HD, CAUSAL, SLOTS>;
+    static bool done = false;
+    if (!done) {
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        done = true;
+    }
+    dim3 grid((S + BQ - 1) / BQ, Hq, B);
+    TA_KERNEL_LAUNCH(kern, grid, ATT1_THREADS, C::SMEM, st, tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f, kv_start);
+    return 0;
+}
+
+// K/V ring depth.  Measured at B = 32, S = 464 (profiles/r02_c26_time_lm_attention.log): 4 slots 80.4 us, 3 slots 87.6 us (K_{j+1} cannot be
+// requested before PV_{j-1} has released its slot), 6 / 8 slots with one CTA per SM 119 us, the 128-key-tile kernel 113.7 us.
+// (cudaOccupancyMaxActiveBlocksPerMultiprocessor reports ONE resident CTA for every depth, 3 included; the timings say two are
+// resident for 3 and 4 -- it is not used for the choice.)
+int g_attn6_slots = 4;
+
+template <int HD, bool CAUSAL>
+int launch_attn_tc6(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* lse, int B, int S, int Hq, int Hkv, long long q_rs,
+                    long long k_rs, long long v_rs, long long o_rs, float scale, cudaStream_t st, const int* kv_start) {
+    CUtensorMap tq, tk, tv;                                  // K / V boxes hold 64 rows here
+    const long long rows = (long long)B * S;
+    int rc = k_make_tensor_map_2d(&tq, q, rows, (long long)Hq * HD, q_rs, BQ);
+    if (rc) return rc;
+    rc = k_make_tensor_map_2d(&tk, k, rows, (long long)Hkv * HD, k_rs, BKV5);
+    if (rc) return rc;
+    rc = k_make_tensor_map_2d(&tv, v, rows, (long long)Hkv * HD, v_rs, BKV5);
+    if (rc) return rc;
+    if (g_attn6_slots == 4) return launch_attn_tc6s<HD, CAUSAL, 4>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st, kv_start);
+    if (g_attn6_slots == 6) return launch_attn_tc6s<HD, CAUSAL, 6>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st, kv_start);
+    if (g_attn6_slots == 8) return launch_attn_tc6s<HD, CAUSAL, 8>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st, kv_start);
+    return launch_attn_tc6s<HD, CAUSAL, 3>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st, kv_start);
+}
+
+int g_attn_tc_lm = 1;   // 1 (default): decoder shape (head_dim 128, causal) on variant 6; 0: on attn_tc_fwd_kernel<128, true> (ta_attn_set_tc_lm)
+
 // Forward-kernel selection (ta_attn_set_tc).  0: mma.sync; 1: tcgen05, two threads per query row, every shape; the other modes choose
 // the encoder-shape kernel (head_dim 64, non-causal) and leave the rest on mode 1's kernel:
 //   2: one thread per row, 128-key tiles, two CTAs per SM (round-1 default: 0.590 ms per encoder layer at B = 32, S = 1500);
@@ -1591,6 +1884,12 @@ TA_API int ta_attn_set_trace(void* buf, int steps) {
     return 0;
 }
 
+TA_API int ta_attn_set_tc_lm(int variant) {      // 0: 128-key tiles; 1: 64-key tiles, 4-slot ring (default); 3 / 4 / 6 / 8: that ring depth
+    g_attn_tc_lm = variant ? 1 : 0;
+    g_attn6_slots = (variant == 3 || variant == 6 || variant == 8) ? variant : 4;
+    return 0;
+}
+TA_API int ta_attn_tc_lm_ring_slots(void) { return g_attn6_slots; }
 TA_API int ta_attn_set_tc(int on) {
     g_attn_tc = (on < 0 || on > 16) ? 14 : on;
     return 0;
@@ -1644,6 +1943,7 @@ int k_attn_tc_fwd(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* l
         if (causal) return launch_attn_tc<64, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
         return launch_attn_tc<64, false>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
     }
+    if (causal && g_attn_tc_lm) return launch_attn_tc6<128, true>(q, k, v, o, lse, B, S, Hq, Hkv, q_rs, k_rs, v_rs, o_rs, scale, st, kv_start);
     if (causal) return launch_attn_tc<128, true>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st, kv_start);
     return launch_attn_tc<128, false>(tq, tk, tv, o, lse, B, S, Hq, Hkv, o_rs, scale, st);
 }

@@ -81,6 +81,9 @@ _SIGS = {
     "ta_logmel_fwd": ([P, c_ll, c_int, c_int, P, P, P, P], c_int),
     "ta_mel_to_conv1_im2col": ([P, c_int, c_int, P, P], c_int),
     "ta_attn_fwd": ([P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_int, c_float, P], c_int),
+    "ta_attn_set_bwd_variant": ([c_int], c_int),
+    "ta_attn_set_tc_lm": ([c_int], c_int),
+    "ta_attn_tc_lm_ring_slots": ([], c_int),
     "ta_attn_set_tc": ([c_int], c_int),
     "ta_attn_set_trace": ([P, c_int], c_int),
     "ta_debug_set": ([c_int, c_int], c_int),
@@ -178,6 +181,10 @@ def load() -> C.CDLL:
             raise TinyAudioB200Error("TA_PDL=1 requested but libtinyaudio_b200.so was built without PDL (make -C tiny_audio_b200/csrc PDL=1)")
     if os.environ.get("TA_WINDOW_ATTN_VARIANT") is not None:
         lib.ta_window_attn_set_variant(int(os.environ["TA_WINDOW_ATTN_VARIANT"]))
+    if os.environ.get("TA_ATTN_BWD_VARIANT") is not None:
+        lib.ta_attn_set_bwd_variant(int(os.environ["TA_ATTN_BWD_VARIANT"]))
+    if os.environ.get("TA_ATTN_TC_LM") is not None:
+        lib.ta_attn_set_tc_lm(int(os.environ["TA_ATTN_TC_LM"]))
     if os.environ.get("TA_ATTN_TC") is not None:
         lib.ta_attn_set_tc(int(os.environ["TA_ATTN_TC"]))
     _lib = lib

@@ -45,9 +45,15 @@ def timeit(fn, reps=20):
 
 
 fl = 2.0 * B * Hq * S * S * hd          # causal: half of 4 S^2 hd
-print(f"forward                         {timeit(fwd):7.1f} us  ({fl / timeit(fwd) / 1e6:.0f} TFLOP/s)")
-t = timeit(bwd)
-print(f"backward (prep + memset + main) {t:7.1f} us  ({2.5 * fl / t / 1e6:.0f} TFLOP/s)")
-lib.ta_debug_set(1, 1)
-print(f"backward, dQ atomics OFF        {timeit(bwd):7.1f} us")
-lib.ta_debug_set(1, 0)
+for variant, name in ((0, "128-key tiles, 1 CTA/SM"), (3, "64-key tiles, 2 CTAs/SM, 3-slot ring"), (4, "64-key tiles, 4-slot ring"), (6, "64-key tiles, 1 CTA/SM, 6-slot ring"), (8, "64-key tiles, 1 CTA/SM, 8-slot ring"), (1, "default")):
+    lib.ta_attn_set_tc_lm(variant)
+    t = timeit(fwd)
+    print(f"forward [{name:38s}] {t:7.1f} us  ({fl / t / 1e6:.0f} TFLOP/s)  ring slots {lib.ta_attn_tc_lm_ring_slots()}")
+for variant, name in ((1, "128-query serial kernel"), (2, "64-query pipelined kernel (default)")):
+    lib.ta_attn_set_bwd_variant(variant)
+    t = timeit(bwd)
+    print(f"backward [{name:36s}] (prep + memset + main) {t:7.1f} us  ({2.5 * fl / t / 1e6:.0f} TFLOP/s)")
+    lib.ta_debug_set(1, 1)
+    print(f"backward [{name:36s}] dQ atomics OFF         {timeit(bwd):7.1f} us")
+    lib.ta_debug_set(1, 0)
+lib.ta_attn_set_bwd_variant(2)
