@@ -1577,7 +1577,7 @@ int launch_attn_tc5(const bf16* q, const bf16* k, const bf16* v, bf16* o, float*
 // 112 KB, TMEM 64 (S) + 128 (O) columns: TWO CTAs per SM.  The decoder's problems are short (S = 464: a query tile sees 2-8 key tiles),
 // so a CTA's prologue / first-load latency / epilogue are as long as its main loop; with one 192 KB CTA per SM (attn_tc_fwd_kernel<128>)
 // nothing ran under them and ncu showed no unit above 24 % (profiles/r02_c23_ncu_top_kernels_summary.txt: 115.6 us, tensor pipe 19 %).
-// Heavy query tiles are scheduled first (qt = gridDim.x - 1 - blockIdx.x).
+// Heavy query tiles are scheduled first (linear grid ordered by query tile, last tile first).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int HD, int SLOTS>
 struct Att6Cfg {
@@ -1617,7 +1617,10 @@ attn_tc_fwd6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = (int)gridDim.x - 1 - (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    // linear grid, longest work first (causal: the last query tile sees every key tile)
+    const int n_qt = (S + BQ - 1) / BQ, per_qt = (int)gridDim.x / n_qt;      // per_qt = Hq * B
+    const int qt = CAUSAL ? n_qt - 1 - (int)blockIdx.x / per_qt : (int)blockIdx.x / per_qt;
+    const int h = ((int)blockIdx.x % per_qt) % Hq, b = ((int)blockIdx.x % per_qt) / Hq;
     const int hk = h / (Hq / Hkv);
     const int q0 = qt * BQ;
     const int n_all = (S + BKV5 - 1) / BKV5;
@@ -1834,7 +1837,7 @@ int launch_attn_tc6s(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
         TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         done = true;
     }
-    dim3 grid((S + BQ - 1) / BQ, Hq, B);
+    const unsigned grid = (unsigned)(((S + BQ - 1) / BQ) * Hq * B);
     TA_KERNEL_LAUNCH(kern, grid, ATT1_THREADS, C::SMEM, st, tq, tk, tv, o, lse, S, Hq, Hkv, o_rs, scale * 1.4426950408889634f, kv_start);
     return 0;
 }

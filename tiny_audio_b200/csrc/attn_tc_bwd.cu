@@ -342,7 +342,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                     const float* __restrict__ LSE, const float* __restrict__ Dsum, float* __restrict__ dQacc,
                     bf16* __restrict__ dK, bf16* __restrict__ dV, int S, int Hq, int Hkv, long long dq_rs, long long dk_rs,
-                    long long dv_rs, float scale, float scale_log2, int dbg) {
+                    long long dv_rs, float scale, float scale_log2, int dbg, int n_kt) {
     TA_PDL_ENTRY();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -366,7 +366,9 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float* sVec = reinterpret_cast<float*>(smem + B2_BAR + 256);   // [2 buffers][lse*log2e (64) | D (64)]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+    // linear grid, longest work first: key tile 0 sees every query sub-tile of the sequence, the last key tile only the last few
+    const int per_kt = (int)gridDim.x / n_kt;        // = Hkv * B
+    const int kt = (int)blockIdx.x / per_kt, hk = ((int)blockIdx.x % per_kt) % Hkv, b = ((int)blockIdx.x % per_kt) / Hkv;
     const int G = Hq / Hkv;
     const int kv0 = kt * BT;
     const int n_qs = (S + BQ2 - 1) / BQ2;            // 64-query sub-tiles of the sequence
@@ -655,8 +657,9 @@ int k_attn_tc_bwd(const bf16* q, const bf16* k, const bf16* v, const bf16* d_o, 
         if (rc) return rc;
         rc = k_make_tensor_map_2d(&tdo2, d_o, rows, (long long)Hq * HD, do_rs, BQ2);
         if (rc) return rc;
-        TA_KERNEL_LAUNCH(attn_tc_bwd2_kernel, grid, BWD_THREADS, SMEM_BWD2, st, tq2, tk, tv, tdo2, lse, dsum, dq_acc, dk, dv, S, Hq, Hkv, dq_rs,
-                         dk_rs, dv_rs, scale, scale * 1.4426950408889634f, g_bwd_dbg);
+        const int n_kt = (S + BT - 1) / BT;
+        TA_KERNEL_LAUNCH(attn_tc_bwd2_kernel, (unsigned)(n_kt * Hkv * B), BWD_THREADS, SMEM_BWD2, st, tq2, tk, tv, tdo2, lse, dsum, dq_acc, dk, dv, S,
+                         Hq, Hkv, dq_rs, dk_rs, dv_rs, scale, scale * 1.4426950408889634f, g_bwd_dbg, n_kt);
         *handled = 1;
         return 0;
     }
