@@ -39,7 +39,9 @@ enum {
     TA_EPI_F32 = 4,        /* out f32  = alpha * acc                                             */
     TA_EPI_SWIGLU = 5,     /* B rows interleaved [64 gate | 64 up]: out bf16 [M,N/2] = silu(g)*u; out2 = (g,u) stash */
     TA_EPI_SWIGLU_BWD = 6, /* acc = d(h) [M,N]; aux = (g,u) stash [M,2N]; out bf16 [M,2N] = (d gate | d up)          */
-    TA_EPI_BF16_ROPE = 7   /* out bf16 = rope(acc + bias): GLM-ASR partial rotary on columns < rope_cols (64-wide heads, 32 dims) */
+    TA_EPI_BF16_ROPE = 7,  /* out bf16 = rope(acc + bias): GLM-ASR partial rotary on columns < rope_cols (64-wide heads, 32 dims) */
+    TA_EPI_BF16_ROWDOT = 8 /* out bf16 = acc, and out2 fp32 [B, N/128, S] (S = rope_seq, row = b S + s) = sum over each 128-wide head of out * aux:
+                              the attention backward's D = rowsum(dO o O) computed where dO is produced (HF sdpa backward).  N % 256 == 0 */
 };
 
 typedef struct ta_gemm_epilogue {
@@ -307,6 +309,7 @@ typedef struct ta_lm_step_args {
     const int* kv_start;
 } ta_lm_step_args;
 /* with_backward: 0 forward only; 1 backward to inputs_embeds (frozen LM, LoRA); 2 additionally the weight gradients (lm_grads) */
+int ta_lm_set_fused_attn_dsum(int on); /* 1 (default): the attention backward's D = rowsum(dO o O) comes out of the o-projection dgrad GEMM's epilogue (TA_EPI_BF16_ROWDOT); 0: separate preparation kernel */
 int ta_lm_workspace_bytes(const ta_lm_weights* w, int B, int S, int n_labelled, int with_backward, long long* bytes);
 /* building blocks of the unfrozen recipe (exported for unit parity tests and the host-side operand refresh) */
 int ta_rmsnorm_dw(const void* dy_bf16, const float* x, const int* row_index, long long rows, int D, float eps, float* dw /*accumulated*/,

@@ -132,6 +132,21 @@ def test_gemm_rope_epilogue(cuda, pair):
     assert torch.equal(out, ref)
 
 
+def test_gemm_rowdot_epilogue(cuda):
+    """TA_EPI_BF16_ROWDOT: the plain bf16 GEMM output plus, per 128-wide head, the row sums of out * aux in [B, heads, S] layout -- the
+    attention backward's D = rowsum(dO o O) fused into the o-projection dgrad (row tail, several waves, K with a remainder block)."""
+    B, S, H = 3, 217, 4
+    M, N, K = B * S, H * 128, 1000
+    x, w = rnd(M, K, seed=21), rnd(N, K, seed=22, scale=0.05)
+    aux = rnd(M, N + 64, seed=23)[:, :N]                      # strided view: ldaux != N
+    d = torch.full((B, H, S), float("nan"), device="cuda", dtype=F32)
+    out = L.gemm(x, w, epi=L.EPI_BF16_ROWDOT, aux=aux, out2=d, seq=S)
+    ref = L.gemm(x, w, epi=L.EPI_BF16)
+    assert torch.equal(out, ref)
+    dref = (ref.float() * aux.float()).view(B, S, H, 128).sum(-1).permute(0, 2, 1)
+    assert torch.isfinite(d).all() and rel_err(d, dref) < 1e-5
+
+
 # ------------------------------------------------------------------ attention
 def ref_attn(q, k, v, causal, scale):
     B, S, Hq, hd = q.shape

@@ -484,17 +484,17 @@ TA_API int ta_attn_fwd(const void* q, const void* k, const void* v, void* o, flo
     return -1;
 }
 
-TA_API int ta_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
-                       float* dsum_ws, float* dq_acc, void* dk, void* dv, int B, int S, int Hq, int Hkv, int head_dim,
-                       long long q_rs, long long k_rs, long long v_rs, long long o_rs, long long do_rs, long long dq_rs,
-                       long long dk_rs, long long dv_rs, int causal, float scale, void* stream) {
-    TA_REQUIRE(q && k && v && o && d_o && lse && dsum_ws && dq_acc && dk && dv, "ta_attn_bwd: null pointer");
+// dsum_ready != 0: dsum_ws already holds D = rowsum(dO o O) (the o-projection dgrad GEMM's ROWDOT epilogue wrote it), `o` is not read
+int k_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse, float* dsum_ws, float* dq_acc,
+               void* dk, void* dv, int B, int S, int Hq, int Hkv, int head_dim, long long q_rs, long long k_rs, long long v_rs, long long o_rs,
+               long long do_rs, long long dq_rs, long long dk_rs, long long dv_rs, int causal, float scale, void* stream, int dsum_ready) {
+    TA_REQUIRE(q && k && v && (o || dsum_ready) && d_o && lse && dsum_ws && dq_acc && dk && dv, "ta_attn_bwd: null pointer");
     TA_REQUIRE(head_dim == 128, "ta_attn_bwd: only head_dim 128 (Qwen3) is on the path, got %d", head_dim);
     TA_REQUIRE(Hq % Hkv == 0, "ta_attn_bwd: Hq must be a multiple of Hkv");
     if (B == 0 || S == 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int HD = 128;
-    {
+    if (!dsum_ready) {
         const long long threads = (long long)B * S * Hq * (HD / 8);
         TA_KERNEL_LAUNCH(attn_bwd_prep_kernel<HD>, (unsigned)((threads + 255) / 256), 256, 0, st, (const bf16*)o, (const bf16*)d_o, dsum_ws, B,
                          S, Hq, o_rs, do_rs);
@@ -528,4 +528,12 @@ TA_API int ta_attn_bwd(const void* q, const void* k, const void* v, const void* 
     }
     TA_LAUNCH_CHECK();
     return 0;
+}
+
+TA_API int ta_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                       float* dsum_ws, float* dq_acc, void* dk, void* dv, int B, int S, int Hq, int Hkv, int head_dim,
+                       long long q_rs, long long k_rs, long long v_rs, long long o_rs, long long do_rs, long long dq_rs,
+                       long long dk_rs, long long dv_rs, int causal, float scale, void* stream) {
+    return k_attn_bwd(q, k, v, o, d_o, lse, dsum_ws, dq_acc, dk, dv, B, S, Hq, Hkv, head_dim, q_rs, k_rs, v_rs, o_rs, do_rs, dq_rs, dk_rs,
+                      dv_rs, causal, scale, stream, 0);
 }

@@ -6,6 +6,7 @@
 #include "tinyaudio_b200.h"
 
 extern int g_wgrad_transposed;   // attn_tc_bwd.cu (ta_debug_set key 2)
+int g_fuse_attn_dsum = 1;         // ta_lm_set_fused_attn_dsum: D = rowsum(dO o O) in the o-projection dgrad epilogue (1, default) or its own kernel (0)
 
 namespace {
 
@@ -312,6 +313,11 @@ int full_wgrad(const LmBufs& b, long long M, const bf16* dy, long long ld_dy, in
 }
 }  // namespace
 
+TA_API int ta_lm_set_fused_attn_dsum(int on) {
+    g_fuse_attn_dsum = on ? 1 : 0;
+    return 0;
+}
+
 TA_API int ta_lm_workspace_bytes(const ta_lm_weights* w, int B, int S, int n_labelled, int with_backward, long long* bytes) {
     TA_REQUIRE(w && bytes, "null");
     LmBufs b;
@@ -479,9 +485,18 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
             RUN(lora_wgrad(b, M, P, b.dxb, ldX, D, att + QD, ldAtt, b.dxb + D, ldX, att, ldAtt, QD, Lg[TA_LM_LORA_DA_O],
                            Lg[TA_LM_LORA_DB_O], st));
         }
-        RUN(gemm(b.dxb, ldX, Lw[TA_LM_WO_T], ldX, M, QD, D + P, TA_EPI_BF16, b.datt, QD, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
-        RUN(ta_attn_bwd(qk, qk + QD, qkv + QK, att, b.datt, lse, b.dsum, b.dq, b.dk, b.dv, B, S, Hq, Hkv, hd, QK, QK, QKV, ldAtt, QD, QD,
-                        KD, KD, 1, scale, st));
+        // d(att) = d(x) Wo, and in the same epilogue D = rowsum(d(att) o att) per head (one epilogue thread owns a row's 128-wide head):
+        // the attention backward's preparation pass (a 122 MB read per layer) is gone
+        const bool rowdot = g_fuse_attn_dsum && QD % 256 == 0;
+        if (rowdot) {
+            ta_gemm_epilogue e{};
+            e.out = b.datt; e.ldo = QD; e.aux = att; e.ldaux = ldAtt; e.out2 = b.dsum; e.rope_seq = S;
+            RUN(ta_gemm_bf16(b.dxb, ldX, Lw[TA_LM_WO_T], ldX, (int)M, QD, D + P, TA_EPI_BF16_ROWDOT, &e, st));
+        } else {
+            RUN(gemm(b.dxb, ldX, Lw[TA_LM_WO_T], ldX, M, QD, D + P, TA_EPI_BF16, b.datt, QD, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
+        }
+        RUN(k_attn_bwd(qk, qk + QD, qkv + QK, att, b.datt, lse, b.dsum, b.dq, b.dk, b.dv, B, S, Hq, Hkv, hd, QK, QK, QKV, ldAtt, QD, QD,
+                       KD, KD, 1, scale, st, rowdot ? 1 : 0));
         RUN(k_lm_qknorm_rope_bwd(qkv, b.dq, b.dk, b.dv, b.big, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W],
                                  w->rope_cos, w->rope_sin, M, S, Hq, Hkv, w->eps, st, ldBig));
         if (Gl) {

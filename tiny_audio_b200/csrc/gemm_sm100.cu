@@ -528,13 +528,17 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
         }
     } else {
         constexpr bool F32OUT = (EPI == TA_EPI_F32 || EPI == TA_EPI_F32_RESID);
-        constexpr int NRAW = (EPI == TA_EPI_F32_RESID || EPI == TA_EPI_SWIGLU_BWD) ? 8 : (EPI == TA_EPI_BF16_RESID) ? 4 : 1;
+        constexpr int NRAW = (EPI == TA_EPI_F32_RESID || EPI == TA_EPI_SWIGLU_BWD) ? 8 : (EPI == TA_EPI_BF16_RESID || EPI == TA_EPI_BF16_ROWDOT) ? 4 : 1;
         uint4 cur[NRAW], nxt[NRAW];
         auto prefetch = [&](int c, uint4 (&dst)[NRAW]) {
-            if constexpr (EPI == TA_EPI_BF16_RESID || EPI == TA_EPI_F32_RESID || EPI == TA_EPI_SWIGLU_BWD) {
+            if constexpr (EPI == TA_EPI_BF16_RESID || EPI == TA_EPI_F32_RESID || EPI == TA_EPI_SWIGLU_BWD || EPI == TA_EPI_BF16_ROWDOT) {
                 if (!row_ok) return;
                 const long long col = tile_col0 + c * 32;
-                if constexpr (EPI == TA_EPI_BF16_RESID) {
+                if constexpr (EPI == TA_EPI_BF16_ROWDOT) {
+                    const uint4* p = reinterpret_cast<const uint4*>(ep.aux + row * ep.ldaux + col);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = p[i];
+                } else if constexpr (EPI == TA_EPI_BF16_RESID) {
                     const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.resid) + row * ep.ldr + col);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) dst[i] = p[i];
@@ -552,6 +556,7 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
         const int c_lo = grp * (BN / 64), c_hi = (grp + 1) * (BN / 64);
         prefetch(c_lo, cur);
         uint8_t* srow = nullptr;
+        float rowdot = 0.f;       // ROWDOT: sum over this group's 128 columns (one head) of out * aux
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
             const long long col = tile_col0 + c * 32;
@@ -618,6 +623,17 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
             } else if constexpr (EPI == TA_EPI_F32) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] *= ep.alpha;
+            } else if constexpr (EPI == TA_EPI_BF16_ROWDOT) {
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 a = unpack_bf16x2(cur[i].x), b = unpack_bf16x2(cur[i].y), cc = unpack_bf16x2(cur[i].z),
+                                     d = unpack_bf16x2(cur[i].w);
+                        rowdot += bf16_round(v[8 * i + 0]) * a.x + bf16_round(v[8 * i + 1]) * a.y + bf16_round(v[8 * i + 2]) * b.x +
+                                  bf16_round(v[8 * i + 3]) * b.y + bf16_round(v[8 * i + 4]) * cc.x + bf16_round(v[8 * i + 5]) * cc.y +
+                                  bf16_round(v[8 * i + 6]) * d.x + bf16_round(v[8 * i + 7]) * d.y;
+                    }
+                }
             }
             if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
                 // v = d(h) for h columns [col, col+32) -> (d gate, d up) chunks of the interleaved [M, 2F] gradient
@@ -672,6 +688,14 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
             if (c + 1 < c_hi) {
 #pragma unroll
                 for (int i = 0; i < NRAW; ++i) cur[i] = nxt[i];
+            }
+        }
+        if constexpr (EPI == TA_EPI_BF16_ROWDOT) {
+            static_assert(EPI != TA_EPI_BF16_ROWDOT || BN == 256, "ROWDOT: one epilogue group = one 128-wide head needs 256-wide tiles");
+            if (row_ok) {
+                const long long head = (tile_col0 >> 7) + grp, n_heads = ep.ldo2;            // ldo2 carries N / 128
+                const long long bb = row / ep.rope_seq, ss = row % ep.rope_seq;
+                reinterpret_cast<float*>(ep.out2)[(bb * n_heads + head) * ep.rope_seq + ss] = rowdot;
             }
         }
     }
@@ -1216,6 +1240,7 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, i
         case TA_EPI_SWIGLU: return launch<BN, TA_EPI_SWIGLU>(ta, tb, M, N, K, ep, st);
         case TA_EPI_SWIGLU_BWD: return launch<BN, TA_EPI_SWIGLU_BWD>(ta, tb, M, N, K, ep, st);
         case TA_EPI_BF16_ROPE: return launch<BN, TA_EPI_BF16_ROPE>(ta, tb, M, N, K, ep, st);
+        case TA_EPI_BF16_ROWDOT: ta_set_error("the ROWDOT epilogue exists in the CTA-pair kernel only"); return -1;
         default: ta_set_error("unknown epilogue mode %d", epi); return -1;
     }
 }
@@ -1249,6 +1274,10 @@ int dispatch_epi2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const C
         case TA_EPI_SWIGLU: return launch2<BN, TA_EPI_SWIGLU>(ta, tb, tc, tc2, M, N, K, ep, st);
         case TA_EPI_SWIGLU_BWD: return launch2<BN, TA_EPI_SWIGLU_BWD>(ta, tb, tc, tc2, M, N, K, ep, st);
         case TA_EPI_BF16_ROPE: return launch2<BN, TA_EPI_BF16_ROPE>(ta, tb, tc, tc2, M, N, K, ep, st);
+        case TA_EPI_BF16_ROWDOT:
+            if constexpr (BN == 256) return launch2<256, TA_EPI_BF16_ROWDOT>(ta, tb, tc, tc2, M, N, K, ep, st);
+            ta_set_error("the ROWDOT epilogue needs 256-wide tiles");
+            return -1;
         default: ta_set_error("unknown epilogue mode %d", epi); return -1;
     }
 }
@@ -1342,8 +1371,12 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
     TA_REQUIRE(N % 128 == 0, "ta_gemm_bf16: N=%d must be a multiple of 128", N);
     if (epi == TA_EPI_BF16_RESID || epi == TA_EPI_F32_RESID) TA_REQUIRE(e->resid, "residual epilogue needs resid");
     if (epi == TA_EPI_SWIGLU_BWD) TA_REQUIRE(e->aux && N % 64 == 0, "swiglu-bwd epilogue needs aux stash");
+    if (epi == TA_EPI_BF16_ROWDOT)
+        TA_REQUIRE(e->aux && e->out2 && e->rope_seq > 0 && N % 256 == 0 && M % e->rope_seq == 0,
+                   "rowdot epilogue needs aux, out2, the sequence length in rope_seq (dividing M) and N %% 256 == 0");
     int bn = g_force_bn ? g_force_bn : ((N % 256 == 0) ? 256 : 128);
     if (N % bn != 0) bn = 128;
+    if (epi == TA_EPI_BF16_ROWDOT) bn = 256;
     EpiArgs ep;
     ep.k_splits = 1;
     ep.aux_tma = 0;
@@ -1356,8 +1389,8 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
     int rc = make_map(&ta, A, M, K, lda, BM);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    bool use_pair = g_cta_pair != 0;
-    if (use_pair && !g_force_bn) {
+    bool use_pair = g_cta_pair != 0 || epi == TA_EPI_BF16_ROWDOT;
+    if (use_pair && !g_force_bn && epi != TA_EPI_BF16_ROWDOT) {
         // few, deep tiles (the d(lm_head) product: M = labelled rows, N = dim, K = vocabulary): 256 x 256 pair tiles would leave
         // most SMs idle; 128 x 128 single-CTA tiles give 4 x as many work items (measured 0.60 vs 0.85 ms on 2080 x 1024 x 151936)
         const long long pair_tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * (N / bn);
@@ -1375,7 +1408,8 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
             EpiArgs e2 = ep;
             e2.out = reinterpret_cast<uint8_t*>(ep.out) + row0 * ep.ldo * (f32out ? 4 : 2);
             if (ep.resid) e2.resid = reinterpret_cast<const uint8_t*>(ep.resid) + row0 * ep.ldr * (epi == TA_EPI_F32_RESID ? 4 : 2);
-            if (ep.out2) e2.out2 = reinterpret_cast<uint8_t*>(ep.out2) + row0 * ep.ldo2 * 2;
+            if (ep.out2 && epi != TA_EPI_BF16_ROWDOT) e2.out2 = reinterpret_cast<uint8_t*>(ep.out2) + row0 * ep.ldo2 * 2;
+            if (epi == TA_EPI_BF16_ROWDOT) e2.ldo2 = N / 128;      // heads per row of the D output
             if (ep.aux) e2.aux = ep.aux + row0 * ep.ldaux;
             CUtensorMap ma, mb, tc, tc2;
             int r2 = make_map(&ma, reinterpret_cast<const bf16*>(A) + row0 * lda, rows, K, lda, BM);
@@ -1402,7 +1436,7 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
         // Wave quantisation: the persistent kernel runs ceil(tiles / 74 CTA pairs) waves of 256 x 256 tiles.  When the last wave
         // would be mostly empty (the decoder's N = 1024 products: 232 tiles = 3.14 waves -> 4), the trailing row blocks are
         // issued as a second launch with 256 x 128 tiles, which fills the SMs with half-cost tiles (3 + ~0.55 instead of 4).
-        if (bn == 256 && !g_force_bn && g_tail_split && epi != TA_EPI_BF16_ROPE) {
+        if (bn == 256 && !g_force_bn && g_tail_split && epi != TA_EPI_BF16_ROPE && epi != TA_EPI_BF16_ROWDOT) {
             const int pairs = num_sms() / 2;
             const int tm = (M + 2 * BM - 1) / (2 * BM), tn = N / 256;
             const long long tiles = (long long)tm * tn;

@@ -64,3 +64,7 @@ int k_attn_tc_bwd(const bf16* q, const bf16* k, const bf16* v, const bf16* d_o, 
                   bf16* dk, bf16* dv, int B, int S, int Hq, int Hkv, int head_dim, long long q_rs, long long k_rs, long long v_rs,
                   long long do_rs, long long dq_rs, long long dk_rs, long long dv_rs, int causal, float scale, cudaStream_t st,
                   int* handled);
+// attention backward with an optional precomputed D = rowsum(dO o O) (attn_mma.cu)
+int k_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse, float* dsum_ws, float* dq_acc,
+               void* dk, void* dv, int B, int S, int Hq, int Hkv, int head_dim, long long q_rs, long long k_rs, long long v_rs, long long o_rs,
+               long long do_rs, long long dq_rs, long long dk_rs, long long dv_rs, int causal, float scale, void* stream, int dsum_ready);

@@ -21,7 +21,7 @@ P = c_void_p
 
 # epilogue modes (enum in the header)
 SKINNY_BF16, SKINNY_F32_RESID, SKINNY_SWIGLU, SKINNY_PARTIAL = range(4)
-EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESID, EPI_F32_RESID, EPI_F32, EPI_SWIGLU, EPI_SWIGLU_BWD, EPI_BF16_ROPE = range(8)
+EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESID, EPI_F32_RESID, EPI_F32, EPI_SWIGLU, EPI_SWIGLU_BWD, EPI_BF16_ROPE, EPI_BF16_ROWDOT = range(9)
 ENC_PTRS_PER_LAYER = 12
 LM_PTRS_PER_LAYER = 20
 LM_LORA_GRADS_PER_LAYER = 8
@@ -82,6 +82,7 @@ _SIGS = {
     "ta_mel_to_conv1_im2col": ([P, c_int, c_int, P, P], c_int),
     "ta_attn_fwd": ([P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_int, c_float, P], c_int),
     "ta_attn_set_bwd_variant": ([c_int], c_int),
+    "ta_lm_set_fused_attn_dsum": ([c_int], c_int),
     "ta_attn_set_tc_lm": ([c_int], c_int),
     "ta_attn_tc_lm_ring_slots": ([], c_int),
     "ta_attn_set_tc": ([c_int], c_int),
@@ -181,6 +182,8 @@ def load() -> C.CDLL:
             raise TinyAudioB200Error("TA_PDL=1 requested but libtinyaudio_b200.so was built without PDL (make -C tiny_audio_b200/csrc PDL=1)")
     if os.environ.get("TA_WINDOW_ATTN_VARIANT") is not None:
         lib.ta_window_attn_set_variant(int(os.environ["TA_WINDOW_ATTN_VARIANT"]))
+    if os.environ.get("TA_LM_FUSED_ATTN_DSUM") is not None:
+        lib.ta_lm_set_fused_attn_dsum(int(os.environ["TA_LM_FUSED_ATTN_DSUM"]))
     if os.environ.get("TA_ATTN_BWD_VARIANT") is not None:
         lib.ta_attn_set_bwd_variant(int(os.environ["TA_ATTN_BWD_VARIANT"]))
     if os.environ.get("TA_ATTN_TC_LM") is not None:
@@ -219,7 +222,7 @@ def require_cuda(*tensors: torch.Tensor) -> None:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, epi: int = EPI_BF16, out: Optional[torch.Tensor] = None,
          bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, alpha: float = 1.0, k: Optional[int] = None,
-         rope: Optional[tuple] = None) -> torch.Tensor:
+         rope: Optional[tuple] = None, seq: int = 0) -> torch.Tensor:
     """out = epilogue(a @ b.T);  a [M,K] bf16, b [N,K] bf16 (both row-major, K contiguous)."""
     lib = load()
     require_cuda(a, b)
@@ -237,9 +240,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, epi: int = EPI_BF16, out: Optional
         else:
             out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
     e = GemmEpilogue(ptr(out), out.stride(0), ptr(bias), ptr(resid), resid.stride(0) if resid is not None else 0,
-                     ptr(out2), out2.stride(0) if out2 is not None else 0, ptr(aux),
+                     ptr(out2), out2.stride(0) if (out2 is not None and out2.dim() == 2) else 0, ptr(aux),
                      aux.stride(0) if aux is not None else 0, alpha,
-                     ptr(rope[0]) if rope else None, ptr(rope[1]) if rope else None, rope[2] if rope else 0, rope[3] if rope else 0)
+                     ptr(rope[0]) if rope else None, ptr(rope[1]) if rope else None, rope[2] if rope else seq, rope[3] if rope else 0)
     check(lib.ta_gemm_bf16(ptr(a), a.stride(0), ptr(b), b.stride(0), M, N, K, epi, C.byref(e), stream_ptr()))
     return out
 
