@@ -41,7 +41,7 @@ enum {
     TA_EPI_SWIGLU_BWD = 6, /* acc = d(h) [M,N]; aux = (g,u) stash [M,2N]; out bf16 [M,2N] = (d gate | d up)          */
     TA_EPI_BF16_ROPE = 7,  /* out bf16 = rope(acc + bias): GLM-ASR partial rotary on columns < rope_cols (64-wide heads, 32 dims) */
     TA_EPI_BF16_ROWDOT = 8 /* out bf16 = acc, and out2 fp32 [B, N/128, S] (S = rope_seq, row = b S + s) = sum over each 128-wide head of out * aux:
-                              the attention backward's D = rowsum(dO o O) computed where dO is produced (HF sdpa backward).  N % 256 == 0 */
+                              the attention backward's D = rowsum(dO o O) computed where dO is produced (HF sdpa backward).  N % 256 == 0; optional zero_f32 */
 };
 
 typedef struct ta_gemm_epilogue {
@@ -59,6 +59,9 @@ typedef struct ta_gemm_epilogue {
     const float* rope_sin;
     int rope_seq;       /* position = row % rope_seq */
     int rope_cols;      /* rotate output columns [0, rope_cols) (the q and k blocks of a fused qkv projection) */
+    void* zero_f32;     /* BF16_ROWDOT: optional fp32 [M, N] buffer (ld_zero elements per row) that the epilogue fills with ZEROS next to its
+                           output -- the attention backward's dQ accumulator, cleared by a tensor-bound kernel's idle store bandwidth */
+    long long ld_zero;
 } ta_gemm_epilogue;
 
 int ta_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epilogue_mode,

@@ -143,6 +143,12 @@ def test_gemm_rowdot_epilogue(cuda):
     out = L.gemm(x, w, epi=L.EPI_BF16_ROWDOT, aux=aux, out2=d, seq=S)
     ref = L.gemm(x, w, epi=L.EPI_BF16)
     assert torch.equal(out, ref)
+    # + zero-fill of an fp32 [M, N] buffer (the dQ accumulator) from the same epilogue; rows beyond M of a padded buffer stay untouched
+    zbuf = torch.full((M + 5, N), 7.0, device="cuda", dtype=F32)
+    d2 = torch.empty_like(d)
+    out2 = L.gemm(x, w, epi=L.EPI_BF16_ROWDOT, aux=aux, out2=d2, seq=S, zero=zbuf[:M])
+    assert torch.equal(out2, ref) and torch.equal(d2, d)
+    assert float(zbuf[:M].abs().max()) == 0.0 and float((zbuf[M:] - 7.0).abs().max()) == 0.0
     dref = (ref.float() * aux.float()).view(B, S, H, 128).sum(-1).permute(0, 2, 1)
     assert torch.isfinite(d).all() and rel_err(d, dref) < 1e-5
 

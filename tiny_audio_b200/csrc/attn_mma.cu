@@ -484,22 +484,23 @@ TA_API int ta_attn_fwd(const void* q, const void* k, const void* v, void* o, flo
     return -1;
 }
 
-// dsum_ready != 0: dsum_ws already holds D = rowsum(dO o O) (the o-projection dgrad GEMM's ROWDOT epilogue wrote it), `o` is not read
+// dsum_ready bit 0: dsum_ws already holds D = rowsum(dO o O) (the o-projection dgrad GEMM's ROWDOT epilogue wrote it), `o` is not read;
+// bit 1: dq_acc is already zero (same epilogue)
 int k_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse, float* dsum_ws, float* dq_acc,
                void* dk, void* dv, int B, int S, int Hq, int Hkv, int head_dim, long long q_rs, long long k_rs, long long v_rs, long long o_rs,
                long long do_rs, long long dq_rs, long long dk_rs, long long dv_rs, int causal, float scale, void* stream, int dsum_ready) {
-    TA_REQUIRE(q && k && v && (o || dsum_ready) && d_o && lse && dsum_ws && dq_acc && dk && dv, "ta_attn_bwd: null pointer");
+    TA_REQUIRE(q && k && v && (o || (dsum_ready & 1)) && d_o && lse && dsum_ws && dq_acc && dk && dv, "ta_attn_bwd: null pointer");
     TA_REQUIRE(head_dim == 128, "ta_attn_bwd: only head_dim 128 (Qwen3) is on the path, got %d", head_dim);
     TA_REQUIRE(Hq % Hkv == 0, "ta_attn_bwd: Hq must be a multiple of Hkv");
     if (B == 0 || S == 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int HD = 128;
-    if (!dsum_ready) {
+    if (!(dsum_ready & 1)) {
         const long long threads = (long long)B * S * Hq * (HD / 8);
         TA_KERNEL_LAUNCH(attn_bwd_prep_kernel<HD>, (unsigned)((threads + 255) / 256), 256, 0, st, (const bf16*)o, (const bf16*)d_o, dsum_ws, B,
                          S, Hq, o_rs, do_rs);
     }
-    TA_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)B * S * dq_rs, st));
+    if (!(dsum_ready & 2)) TA_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)B * S * dq_rs, st));
     if (k_attn_tc_enabled()) {   // tcgen05 kernel (attn_tc_bwd.cu); the mma.sync kernel below stays as A/B reference
         int handled = 0;
         const int rc = k_attn_tc_bwd((const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)d_o, lse, dsum_ws, dq_acc, (bf16*)dk,

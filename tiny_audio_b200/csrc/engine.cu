@@ -491,12 +491,13 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
         if (rowdot) {
             ta_gemm_epilogue e{};
             e.out = b.datt; e.ldo = QD; e.aux = att; e.ldaux = ldAtt; e.out2 = b.dsum; e.rope_seq = S;
+            e.zero_f32 = b.dq; e.ld_zero = QD;       // the dQ accumulator is cleared here too: no separate 122 MB memset per layer
             RUN(ta_gemm_bf16(b.dxb, ldX, Lw[TA_LM_WO_T], ldX, (int)M, QD, D + P, TA_EPI_BF16_ROWDOT, &e, st));
         } else {
             RUN(gemm(b.dxb, ldX, Lw[TA_LM_WO_T], ldX, M, QD, D + P, TA_EPI_BF16, b.datt, QD, nullptr, nullptr, nullptr, 0, nullptr, 0, st));
         }
         RUN(k_attn_bwd(qk, qk + QD, qkv + QK, att, b.datt, lse, b.dsum, b.dq, b.dk, b.dv, B, S, Hq, Hkv, hd, QK, QK, QKV, ldAtt, QD, QD,
-                       KD, KD, 1, scale, st, rowdot ? 1 : 0));
+                       KD, KD, 1, scale, st, rowdot ? 3 : 0));
         RUN(k_lm_qknorm_rope_bwd(qkv, b.dq, b.dk, b.dv, b.big, (const float*)Lw[TA_LM_QNORM_W], (const float*)Lw[TA_LM_KNORM_W],
                                  w->rope_cos, w->rope_sin, M, S, Hq, Hkv, w->eps, st, ldBig));
         if (Gl) {

@@ -77,6 +77,7 @@ struct EpiArgs {
     int rope_cols;
     int k_splits;            // SPLITK instantiations only: the contraction is cut into k_splits ranges whose partial tiles are reduce-added
     int aux_tma;             // SWIGLU_BWD (pair kernel): the (gate, up) stash comes in by TMA and the gradients leave from the same buffer
+    int zero_fill;           // BF16_ROWDOT (pair kernel): tmC2 maps an fp32 [M, N] buffer that the epilogue fills with zeros next to its output
 };
 
 __device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32]) {
@@ -440,6 +441,7 @@ struct Stager {
     int r;              // my row (0..127)
     int n;              // sub-tiles issued so far
     bool leader;
+    const uint8_t* zbuf = nullptr;   // ROWDOT: 16 KB of zeros in shared memory (source of the zero-fill stores), or nullptr
 
     __device__ __forceinline__ uint8_t* begin() {
         if (leader && n >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -453,6 +455,20 @@ struct Stager {
         if (leader) {
             if constexpr (REDUCE) tma_reduce_add_2d(map, buf + (n & 1) * STG_BYTES, col0, row0);
             else tma_store_2d(map, buf + (n & 1) * STG_BYTES, col0, row0);
+            tma_store_commit();
+        }
+        ++n;
+    }
+    // bf16 sub-tile (64 columns) as end(), plus -- in the same bulk group -- zeros for the same rows x columns of an fp32 tensor
+    __device__ __forceinline__ void end_with_zero(const CUtensorMap* map, const CUtensorMap* zmap, int col0, int row0) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (leader) {
+            tma_store_2d(map, buf + (n & 1) * STG_BYTES, col0, row0);
+            if (zbuf) {
+                tma_store_2d(zmap, zbuf, col0, row0);
+                tma_store_2d(zmap, zbuf, col0 + 32, row0);
+            }
             tma_store_commit();
         }
         ++n;
@@ -683,7 +699,10 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
             } else {
                 const int which = (c - c_lo) & 1;
                 stage_bf16x32(srow, r, which, v);
-                if (which == 1) sg.end(tmC, (int)(col - 32), tile_row0);
+                if (which == 1) {
+                    if constexpr (EPI == TA_EPI_BF16_ROWDOT) sg.end_with_zero(tmC, tmC2, (int)(col - 32), tile_row0);
+                    else sg.end(tmC, (int)(col - 32), tile_row0);
+                }
             }
             if (c + 1 < c_hi) {
 #pragma unroll
@@ -840,6 +859,8 @@ struct Cfg2 {
     static constexpr int STG_OFF = STAGES * STAGE_BYTES;                   // 2 groups x 2 staging buffers x 16 KB (1024-aligned)
     static constexpr int BAR_OFF = STG_OFF + 4 * STG_BYTES;
     static constexpr int SMEM_BYTES = BAR_OFF + 256 + 2 * BN * 4 + 1024;
+    static constexpr int ZERO_OFF = (BAR_OFF + 256 + 2 * BN * 4 + 1023) / 1024 * 1024;   // ROWDOT: 16 KB of zeros behind everything else
+    static constexpr int SMEM_BYTES_ZERO = ZERO_OFF + STG_BYTES + 1024;
 };
 
 // MN-major SWIZZLE_128B operand tile (TN variant below): rows = K index (128 B = 64 bf16 of the M / N index per row), 8-row groups
@@ -1074,6 +1095,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         sg.r = q * 32 + lane;
         sg.n = 0;
         sg.leader = (q == 0 && lane == 0);
+        if constexpr (EPI == TA_EPI_BF16_ROWDOT) {
+            if (ep.zero_fill) {          // the launch reserved SMEM_BYTES_ZERO
+                uint8_t* z = smem + C::ZERO_OFF;
+                const int e_tid = (warp - 4) * 32 + lane;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(z)[e_tid * 4 + i] = make_uint4(0u, 0u, 0u, 0u);
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                sg.zbuf = z;
+            }
+        }
         int tile_iter = 0;
         int as = 0;
         uint32_t aphase = 0;
@@ -1250,15 +1282,16 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
             const EpiArgs& ep, cudaStream_t st) {
     using C = Cfg2<BN>;
     auto kern = gemm2_kernel<BN, EPI, TN, SPLITK>;
+    constexpr int smem_bytes = (EPI == TA_EPI_BF16_ROWDOT) ? C::SMEM_BYTES_ZERO : C::SMEM_BYTES;
     static bool attr_done = false;
     if (!attr_done) {
-        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        TA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_done = true;
     }
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN) * (SPLITK ? ep.k_splits : 1);
     int pairs = num_sms() / 2;
     if (tiles < pairs) pairs = tiles;
-    TA_KERNEL_LAUNCH(kern, 2 * pairs, GEMM_THREADS, C::SMEM_BYTES, st, ta, tb, tc, tc2, M, N, K, ep);
+    TA_KERNEL_LAUNCH(kern, 2 * pairs, GEMM_THREADS, smem_bytes, st, ta, tb, tc, tc2, M, N, K, ep);
     return 0;
 }
 
@@ -1343,6 +1376,7 @@ TA_API int ta_gemm_bf16_tn(const void* At, long long ldat, const void* Bt, long 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     ep.k_splits = 1;
     ep.aux_tma = 0;
+    ep.zero_fill = 0;
     if (g_tn_splitk) {
         // few output tiles, deep contraction (rank-8 LoRA gradients: 4 ... 24 tiles x 230 k-blocks): cut K so that every CTA pair
         // gets a work item, each at least 8 k-blocks long; partial tiles are reduce-added into the zeroed output
@@ -1380,6 +1414,7 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
     EpiArgs ep;
     ep.k_splits = 1;
     ep.aux_tma = 0;
+    ep.zero_fill = 0;
     ep.out = e->out; ep.ldo = e->ldo; ep.bias = e->bias; ep.resid = e->resid; ep.ldr = e->ldr ? e->ldr : e->ldo;
     ep.out2 = e->out2; ep.ldo2 = e->ldo2; ep.aux = reinterpret_cast<const bf16*>(e->aux); ep.ldaux = e->ldaux;
     ep.alpha = e->alpha == 0.0f ? 1.0f : e->alpha;
@@ -1425,6 +1460,11 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
             if (swb_tma) {
                 r2 = make_map(&tc2, e2.aux, rows, 2LL * N, e->ldaux, BM, false);
                 if (r2) return r2;
+            }
+            if (epi == TA_EPI_BF16_ROWDOT && e->zero_f32) {      // fp32 [rows, N] buffer to be zero-filled alongside the output
+                r2 = make_map(&tc2, reinterpret_cast<uint8_t*>(e->zero_f32) + row0 * e->ld_zero * 4, rows, N, e->ld_zero, BM, true);
+                if (r2) return r2;
+                e2.zero_fill = 1;
             }
             if (epi == TA_EPI_SWIGLU && e->out2) {
                 r2 = make_map(&tc2, e2.out2, rows, N, e->ldo2, BM, false);

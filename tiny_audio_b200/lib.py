@@ -35,7 +35,7 @@ LM_GRADS_PER_LAYER = 8
 class GemmEpilogue(C.Structure):
     _fields_ = [("out", P), ("ldo", c_ll), ("bias", P), ("resid", P), ("ldr", c_ll), ("out2", P), ("ldo2", c_ll),
                 ("aux", P), ("ldaux", c_ll), ("alpha", c_float), ("rope_cos", P), ("rope_sin", P), ("rope_seq", c_int),
-                ("rope_cols", c_int)]
+                ("rope_cols", c_int), ("zero_f32", P), ("ld_zero", c_ll)]
 
 
 class EncoderWeights(C.Structure):
@@ -222,7 +222,7 @@ def require_cuda(*tensors: torch.Tensor) -> None:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, epi: int = EPI_BF16, out: Optional[torch.Tensor] = None,
          bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, alpha: float = 1.0, k: Optional[int] = None,
-         rope: Optional[tuple] = None, seq: int = 0) -> torch.Tensor:
+         rope: Optional[tuple] = None, seq: int = 0, zero: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epilogue(a @ b.T);  a [M,K] bf16, b [N,K] bf16 (both row-major, K contiguous)."""
     lib = load()
     require_cuda(a, b)
@@ -242,7 +242,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, epi: int = EPI_BF16, out: Optional
     e = GemmEpilogue(ptr(out), out.stride(0), ptr(bias), ptr(resid), resid.stride(0) if resid is not None else 0,
                      ptr(out2), out2.stride(0) if (out2 is not None and out2.dim() == 2) else 0, ptr(aux),
                      aux.stride(0) if aux is not None else 0, alpha,
-                     ptr(rope[0]) if rope else None, ptr(rope[1]) if rope else None, rope[2] if rope else seq, rope[3] if rope else 0)
+                     ptr(rope[0]) if rope else None, ptr(rope[1]) if rope else None, rope[2] if rope else seq, rope[3] if rope else 0,
+                     ptr(zero), zero.stride(0) if zero is not None else 0)
     check(lib.ta_gemm_bf16(ptr(a), a.stride(0), ptr(b), b.stride(0), M, N, K, epi, C.byref(e), stream_ptr()))
     return out
 
