@@ -226,6 +226,7 @@ def trace_kernels(step, path, header):
             step()
             torch.cuda.synchronize()
         tot, cnt = collections.defaultdict(float), collections.Counter()
+        spans = []
         for ev in prof.events():
             if getattr(ev, "device_type", None) is None or "cuda" not in str(ev.device_type).lower():
                 continue
@@ -235,10 +236,26 @@ def trace_kernels(step, path, header):
             name = ev.name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("(")[0].replace("void ", "")
             tot[name] += us
             cnt[name] += 1
+            tr = getattr(ev, "time_range", None)
+            if tr is not None:
+                spans.append((float(tr.start), float(tr.end), name))
         T = sum(tot.values())
         lines = [header, f"total {T / 1000.0:.3f} ms of kernel time over {sum(cnt.values())} device activities (one step, in situ)"]
         lines += [f"{v / 1000.0:9.3f} ms {100.0 * v / max(T, 1e-9):5.1f}%  n={cnt[k]:4d}  {k[:140]}"
                   for k, v in sorted(tot.items(), key=lambda kv: -kv[1])]
+        # idle time between consecutive device activities, charged to the activity that FOLLOWS the gap (its launch latency / the
+        # predecessor's drain); measured under the profiler, so somewhat larger than in the timed run
+        if len(spans) > 1:
+            spans.sort()
+            gap, gcnt = collections.defaultdict(float), collections.Counter()
+            for (s0, e0, _), (s1, _, n1) in zip(spans[:-1], spans[1:]):
+                g = max(0.0, s1 - e0)
+                gap[n1] += g
+                gcnt[n1] += 1
+            G = sum(gap.values())
+            lines.append(f"gaps: {G / 1000.0:.3f} ms idle between {len(spans)} activities (span {(spans[-1][1] - spans[0][0]) / 1000.0:.3f} ms); by the kernel that follows the gap:")
+            lines += [f"{v / 1000.0:9.3f} ms  avg {v / max(gcnt[k], 1):6.2f} us  n={gcnt[k]:4d}  {k[:120]}"
+                      for k, v in sorted(gap.items(), key=lambda kv: -kv[1])[:14]]
     except Exception as e:          # a diagnostic must never cost the bench line
         lines = [header, f"trace failed: {type(e).__name__}: {e}"]
     with open(path, "w") as f:
