@@ -610,6 +610,7 @@ int g_bwd_variant = 2;   // ta_attn_set_bwd_variant: 2 (default) = 64-query pipe
 int g_bwd_dbg = 0;
 }  // namespace
 
+extern int g_norm_wpb;        // elementwise.cu
 int g_wgrad_transposed = 0;   // key 2: 1 = weight-gradient GEMMs through transposed operand copies (A/B reference of the TN kernel)
 TA_API int ta_attn_set_bwd_variant(int v) {
     g_bwd_variant = (v == 1) ? 1 : 2;
@@ -618,6 +619,7 @@ TA_API int ta_attn_set_bwd_variant(int v) {
 TA_API int ta_debug_set(int key, int value) {   // experiments only (key 1: attention-backward switches)
     if (key == 1) g_bwd_dbg = value;
     if (key == 2) g_wgrad_transposed = value;
+    if (key == 3 && value >= 1 && value <= 8) g_norm_wpb = value;
     return 0;
 }
 

@@ -803,10 +803,11 @@ int k_im2col_k3(const bf16* x, bf16* out, int B, int T, int C, int stride, cudaS
     return 0;
 }
 
+int g_norm_wpb = 8;     // warps (= rows) per block of the LayerNorm / RMSNorm kernels; ta_debug_set(3, n) for experiments (1..8)
 int g_ln_reverse = 1;   // ta_layernorm_set_reverse: A/B switch for the row order of the encoder LayerNorm (L2 reuse, see the kernel)
 int k_layernorm_bf16(const bf16* x, const float* w, const float* b, bf16* y, long long rows, int D, float eps, cudaStream_t st) {
     TA_REQUIRE(D % 256 == 0 && D <= 2048, "layernorm: D=%d must be a multiple of 256 and <= 2048", D);
-    const int wpb = 8;
+    const int wpb = g_norm_wpb;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
     if (D <= 1280) TA_KERNEL_LAUNCH(layernorm_bf16_kernel<5>, grid, wpb * 32, 0, st, x, w, b, y, rows, D, eps, g_ln_reverse);
     else TA_KERNEL_LAUNCH(layernorm_bf16_kernel<8>, grid, wpb * 32, 0, st, x, w, b, y, rows, D, eps, g_ln_reverse);
@@ -818,7 +819,7 @@ int k_rmsnorm_f32(const float* x, const float* w, bf16* y, const int* row_index,
     if (ldy == 0) ldy = D;
     TA_REQUIRE(D % 256 == 0 && D <= 2048, "rmsnorm: D=%d must be a multiple of 256 and <= 2048", D);
     if (rows == 0) return 0;
-    const int wpb = 8;
+    const int wpb = g_norm_wpb;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
     if (D <= 1024) TA_KERNEL_LAUNCH(rmsnorm_f32_kernel<4>, grid, wpb * 32, 0, st, x, w, y, row_index, rows, D, eps, ldy);
     else TA_KERNEL_LAUNCH(rmsnorm_f32_kernel<8>, grid, wpb * 32, 0, st, x, w, y, row_index, rows, D, eps, ldy);
@@ -830,7 +831,7 @@ int k_rmsnorm_f32_bwd(const bf16* dy, const float* x, const float* w, float* dx,
     if (ld_b == 0) ld_b = D;
     TA_REQUIRE(D % 256 == 0 && D <= 2048, "rmsnorm bwd: D=%d must be a multiple of 256 and <= 2048", D);
     if (rows == 0) return 0;
-    const int wpb = 8;
+    const int wpb = g_norm_wpb;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
     if (D <= 1024)
         TA_KERNEL_LAUNCH(rmsnorm_f32_bwd_kernel<4>, grid, wpb * 32, 0, st, dy, x, w, dx, row_index, rows, D, eps, accumulate, dx_bf16, ld_b);
