@@ -12,7 +12,8 @@ Full-size architecture, random-initialised weights (no checkpoints offline), bf1
 accumulation = the reference's production recipe (fp32 masters + bf16 autocast).
 
 `value`  : device-resident inputs, HotPath driver.            `e2e`: public API (ASRModel(**batch) -> loss.backward()
--> optimizer.step()) with pinned HOST buffers, H2D of the waveform / ids and D2H of the loss inside the timed region.
+-> optimizer.step()) with pinned HOST buffers, H2D of every step's waveform / ids (DevicePrefetcher: the copy of batch i+1 runs on a
+side stream under step i) and D2H of the loss inside the timed region.
 """
 from __future__ import annotations
 
@@ -310,6 +311,7 @@ class Workload:
             self.opt = ClipAdamW(self.params, lr=1e-3, max_grad_norm=1.0, allreduce=True)
         self.pmap = {n: p.data for n, p in zip(self.names, self.params)}
         self.gmap = {n: p.grad for n, p in zip(self.names, self.params)}
+        self._prefetch = None
 
     def set_batch(self, B, clip_seconds, seed=None):
         from tiny_audio_b200.synthetic import synthetic_batch
@@ -322,6 +324,7 @@ class Workload:
         self.d_wave = self.host["input_features"].to(self.dev)
         self.d_ids = self.host["input_ids"].to(self.dev)
         self.d_cnt = self.host["audio_token_counts"].to(self.dev)
+        self._prefetch = None
         return self
 
     def step_resident(self):
@@ -338,10 +341,17 @@ class Workload:
         return loss
 
     def step_e2e(self):
-        h = self.host
+        # the public path a training loop takes: pinned host batches -> DevicePrefetcher (every step's batch is copied host -> device inside
+        # the timed region, on the prefetcher's stream, under the previous step's compute) -> ASRModel(**batch) -> backward -> ClipAdamW
+        if self._prefetch is None:
+            from tiny_audio_b200.prefetch import DevicePrefetcher
+            import itertools
+            h = self.host
+            keys = ("input_ids", "input_features", "labels", "attention_mask", "audio_token_counts")
+            self._prefetch = DevicePrefetcher(itertools.repeat({k: h[k] for k in keys}), self.dev)
+        b = next(self._prefetch)
         self.opt.zero_grad()
-        out = self.model(input_ids=h["input_ids"], input_features=h["input_features"], labels=h["labels"], attention_mask=h["attention_mask"],
-                         audio_token_counts=h["audio_token_counts"], num_items_in_batch=self.n_items_global)
+        out = self.model(**b, num_items_in_batch=self.n_items_global)
         out.loss.backward()
         self.opt.step()
         return float(out.loss.detach())   # device -> host read of the step's loss
@@ -350,7 +360,7 @@ class Workload:
         return sum(self.host[k].numel() * self.host[k].element_size() for k in ("input_features", "input_ids", "audio_token_counts"))
 
     def free(self):
-        self.model = self.hot = self.opt = self.pmap = self.gmap = self.params = None
+        self.model = self.hot = self.opt = self.pmap = self.gmap = self.params = self._prefetch = None
         import gc
         gc.collect()
         torch.cuda.empty_cache()

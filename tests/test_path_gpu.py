@@ -805,6 +805,39 @@ def test_forward_surface_logits_text_only_inputs_embeds_and_device_labels(cuda):
         model()
 
 
+def test_device_prefetcher_stages_batches_on_a_side_stream(cuda):
+    """DevicePrefetcher: batches come back on the device with the host values (also when shapes change between batches and when a slot is
+    re-used), labels stay on the host, and a model step on a prefetched batch gives the loss of the same batch passed from the host."""
+    from tiny_audio_b200.prefetch import DevicePrefetcher
+    g = torch.Generator().manual_seed(0)
+    batches = []
+    for i in range(5):
+        n = 1000 + 37 * (i % 2)
+        batches.append({"input_features": torch.randn(2, n, generator=g).pin_memory(), "input_ids": torch.randint(0, 100, (2, 9 + i), generator=g),
+                        "labels": torch.randint(0, 100, (2, 9 + i), generator=g), "audio_token_counts": torch.tensor([3, 4]), "note": "x"})
+    got = []
+    for b in DevicePrefetcher(batches, "cuda"):
+        assert b["input_features"].is_cuda and b["input_ids"].is_cuda and b["audio_token_counts"].is_cuda
+        assert not b["labels"].is_cuda and b["note"] == "x"
+        got.append({k: (v.cpu().clone() if torch.is_tensor(v) else v) for k, v in b.items()})     # sync read before the slot is restaged
+    assert len(got) == 5
+    for a, b in zip(got, batches):
+        for k in ("input_features", "input_ids", "labels", "audio_token_counts"):
+            assert torch.equal(a[k], b[k]), k
+    # through the model: same loss as the host batch
+    from tiny_audio_b200.synthetic import build_offline_model, synthetic_batch
+    cfg = po.small_config(enc_layers=1, lm_layers=1)
+    dims = PathDims.from_any(cfg.to_dict())
+    m = build_offline_model(dims, device="cuda", seed=3)
+    m.train()
+    hb = synthetic_batch(dims, 2, 1.0, seed=5, response_len=6, pin=True)
+    keys = ("input_ids", "input_features", "labels", "attention_mask", "audio_token_counts")
+    n_items = int((hb["labels"] != -100).sum())
+    l_host = float(m(**{k: hb[k] for k in keys}, num_items_in_batch=n_items).loss)
+    for b in DevicePrefetcher([{k: hb[k] for k in keys}] * 3, "cuda"):
+        assert abs(float(m(**b, num_items_in_batch=n_items).loss) - l_host) < 1e-6 * abs(l_host)
+
+
 def test_device_prompt_assembly_matches_host_collation(cuda):
     """f2 (GPU-side collation): ta_assemble_prompts builds input_ids / labels / attention_mask on the device from the per-clip audio
     token counts and the packed response ids -- bit-exact against the host-side construction (tiny_audio_b200.synthetic.synthetic_batch:
