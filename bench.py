@@ -389,15 +389,31 @@ def dp_parity(w: Workload, global_batch: int, clip_seconds: float):
                                          audio_token_counts=b["audio_token_counts"].to(dev), num_items_in_batch=n_global, grads=grads)
         return loss.clone(), torch.cat([grads[n].reshape(-1) for n in w.names])
 
+    # replicas must hold bit-identical parameters after the timed steps (same all-reduced gradients, same update on every rank)
+    pflat = torch.cat([w.pmap[n].reshape(-1) for n in w.names]).float()
+    p_drift = 0.0
+    if world > 1:
+        ref = pflat.clone()
+        dist.broadcast(ref, src=0)
+        dmax = (pflat - ref).abs().max().reshape(1)
+        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+        p_drift = float(dmax)
     loss_r, flat = run(mine)
+    loss_mine = float(loss_r)
     dp.allreduce_flat_(flat)
     if world > 1:
         dist.all_reduce(loss_r, op=dist.ReduceOp.SUM)
     out = {"global_batch": global_batch, "clip_seconds": clip_seconds, "n_ranks": world, "batch_seed": 4242, "num_items_global": int(n_global),
-           "loss_dp": float(loss_r), "grad_checksum_dp": {"sum": float(flat.double().sum()), "l2": float(flat.double().norm())}}
+           "loss_dp": float(loss_r), "loss_rank0_shard": loss_mine if rank == 0 else None, "param_max_abs_diff_across_ranks": p_drift,
+           "grad_checksum_dp": {"sum": float(flat.double().sum()), "l2": float(flat.double().norm())}}
     if rank == 0:
         if world > 1:
             loss_1, flat_1 = run({k: gb[k] for k in keys})
+            # rank 0's own shard inside the whole batch: must reproduce its sharded loss (the forward is batch-invariant bit for bit,
+            # tools/batch_invariance.py); anything left in dp_loss_delta then comes from the other ranks' replicas
+            n0 = global_batch // world
+            l0_again, _ = run({k: gb[k][:n0] for k in keys})
+            out["loss_rank0_shard_again"] = float(l0_again)
         else:
             loss_1, flat_1 = loss_r, flat
         out.update({"loss_single_gpu": float(loss_1), "dp_loss_delta": abs(float(loss_r) - float(loss_1)),

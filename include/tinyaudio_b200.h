@@ -144,7 +144,9 @@ int ta_audio_index(const long long* input_ids, const long long* token_counts, in
 int ta_embed_scatter(const long long* input_ids, const int* src_row, const float* embed_table, const float* audio_embeds,
                      float* inputs_embeds, long long n_tok, int D, long long vocab, void* stream);
 int ta_audio_grad_gather(const int* src_row, const float* d_inputs_embeds, float* d_audio_embeds, long long n_tok, int D, void* stream);
-/* HF:loss/loss_utils.py:28-67 on the labelled rows only; loss_sum += sum_rows(CE) * inv_items; logits <- d(logits) */
+/* HF:loss/loss_utils.py:28-67 on the labelled rows only; loss_sum += sum_rows(CE) * inv_items; logits <- d(logits).
+ * With a row_loss buffer [rows] the sum is taken afterwards in a fixed order in double precision (reproducible, independent of the
+ * batch sharding); with row_loss = NULL every row adds itself with a float atomic. */
 int ta_ce_fwd_bwd(void* logits_bf16, long long ld, const int* targets, long long rows, int V, int Vpad, float inv_items,
                   float* loss_sum, float* row_loss, int write_grad, void* stream);
 int ta_transpose_bf16(const void* in, void* out, int R, int C, long long ld_in, long long ld_out, void* stream);

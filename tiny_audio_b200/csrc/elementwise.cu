@@ -533,6 +533,21 @@ __global__ void audio_grad_gather_kernel(const int* __restrict__ src_row, const 
 }
 
 // =============================================================================================================
+// *loss_sum += inv_items * sum(row_loss), one block, fixed summation order, double accumulation
+__global__ void __launch_bounds__(1024) ce_loss_reduce_kernel(const float* __restrict__ row_loss, long long rows, float inv_items,
+                                                              float* __restrict__ loss_sum) {
+    __shared__ double part[1024];
+    double a = 0.0;
+    for (long long i = threadIdx.x; i < rows; i += blockDim.x) a += (double)row_loss[i];
+    part[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss_sum += (float)(part[0] * (double)inv_items);
+}
+
 // cross entropy on bf16 logits of the labelled rows (HF:loss/loss_utils.py:28-67): fp32 upcast, sum / num_items
 // one block per row; writes d(logits) in place (bf16) and accumulates the loss
 // =============================================================================================================
@@ -570,8 +585,11 @@ ce_fwd_bwd_kernel(bf16* __restrict__ logits, long long ld, const int* __restrict
     if (threadIdx.x == 0) {
         const float lt = __bfloat162float(lr[tgt]);
         const float l = lse - lt;
+        // with a row-loss buffer the batch loss is summed afterwards in a fixed order and in double precision (ce_loss_reduce_kernel):
+        // reproducible and independent of how the batch is sharded.  A float atomicAdd per row drifts by ~1e-5 over 4 000 rows of ~12
+        // (measured: the same 64 clips on 1 vs 2 GPUs differed by 1.6e-5)
         if (row_loss) row_loss[row] = l;
-        atomicAdd(loss_sum, l * inv_items);
+        else atomicAdd(loss_sum, l * inv_items);
     }
     if (!write_grad) return;
     __syncthreads();
@@ -753,12 +771,31 @@ __global__ void assemble_prompts_kernel(const long long* __restrict__ counts, co
     mask[i] = m;
 }
 
+// *out += sum(g^2), DETERMINISTIC: block partials go to a scratch array and the last block to finish adds them up in index order (in
+// double).  With a float atomicAdd per block the clip norm differed in its last bit between data-parallel replicas holding the same
+// all-reduced gradient, and their parameters drifted apart by an ulp per step (bench.py parity.dp.param_max_abs_diff_across_ranks).
+constexpr int SUMSQ_MAX_BLOCKS = 148 * 4;
+__device__ float g_sumsq_partial[SUMSQ_MAX_BLOCKS];
+__device__ unsigned int g_sumsq_done = 0;          // one grad-norm reduction at a time per device (they are issued on one stream)
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
     __shared__ float red[40];
+    __shared__ bool last;
     float s = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += g[i] * g[i];
     s = block_sum(s, red);
-    if (threadIdx.x == 0) atomicAdd(out, s);
+    if (threadIdx.x == 0) {
+        g_sumsq_partial[blockIdx.x] = s;
+        __threadfence();
+        last = (atomicAdd(&g_sumsq_done, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += (double)reinterpret_cast<volatile float*>(g_sumsq_partial)[b];
+        *out += (float)t;
+        g_sumsq_done = 0;
+    }
 }
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -924,6 +961,10 @@ int k_ce_fwd_bwd(bf16* logits, long long ld, const int* targets, long long rows,
     if (rows == 0) return 0;
     ce_fwd_bwd_kernel<<<(unsigned)rows, 1024, 0, st>>>(logits, ld, targets, V, Vpad, inv_items, loss_sum, row_loss, write_grad);
     TA_LAUNCH_CHECK();
+    if (row_loss) {
+        ce_loss_reduce_kernel<<<1, 1024, 0, st>>>(row_loss, rows, inv_items, loss_sum);
+        TA_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -968,7 +1009,7 @@ int k_frame_stack(const bf16* x, bf16* out, int B, int S, int n, int k, int D, c
 
 int k_sumsq(const float* g, long long n, float* out, cudaStream_t st) {
     if (n == 0) return 0;
-    sumsq_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(g, n, out);
+    sumsq_kernel<<<grid_for(n, 256, SUMSQ_MAX_BLOCKS), 256, 0, st>>>(g, n, out);
     TA_LAUNCH_CHECK();
     return 0;
 }

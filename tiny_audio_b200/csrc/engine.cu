@@ -215,6 +215,7 @@ struct LmBufs {
     bf16* hl;          // [n_lab, D]
     bf16* logits;      // [n_lab, Vpad]
     bf16* dhl;         // [n_lab, D]
+    float* row_loss;   // [n_lab] per-row CE losses (reduced in a fixed order)
     bf16* dxb;         // [M, D + P]
     bf16* big;         // [M, max(2F, QKV) + P]
     bf16* dxn;         // [M, D]
@@ -252,6 +253,7 @@ long long lm_carve(const ta_lm_weights* w, int B, int S, int n_lab, int with_bwd
     b->hl = c.take<bf16>((long long)n_lab * D);
     b->logits = c.take<bf16>((long long)n_lab * w->vocab_pad);
     b->dhl = c.take<bf16>((long long)n_lab * D);
+    b->row_loss = c.take<float>((long long)n_lab);
     if (with_bwd) {
         b->dxb = c.take<bf16>(M * (D + P));
         const long long bigw = (2 * F > QKV) ? 2 * F : QKV;
@@ -414,8 +416,9 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
         RUN(k_rmsnorm_f32(x_final, w->final_norm_w, b.hl, a->label_rows, nl, D, w->eps, st));
         RUN(gemm(b.hl, D, w->embed_bf16, D, nl, (int)w->vocab_pad, D, TA_EPI_BF16, b.logits, w->vocab_pad, nullptr, nullptr, nullptr,
                  0, nullptr, 0, st));
+        // per-row losses always go through a buffer: the batch loss is then reduced in a fixed order in double precision
         RUN(k_ce_fwd_bwd(b.logits, w->vocab_pad, a->label_targets, nl, (int)w->vocab, (int)w->vocab_pad, a->inv_num_items, a->loss,
-                         a->row_loss, a->with_backward, st));
+                         a->row_loss ? a->row_loss : b.row_loss, a->with_backward, st));
     }
     if (!a->with_backward) return 0;
 
