@@ -879,3 +879,33 @@ def test_gelu_and_colsum_kernels(cuda):
     out2 = torch.empty(1280, device="cuda")
     L.check(lib.ta_colsum_bf16(L.ptr(sub), 5120, L.ptr(out2), 333, 1280, L.stream_ptr()))
     assert rel_err(out2, sub.float().sum(0)) < 1e-5
+
+
+def test_grad_sumsq_and_ce_loss_are_deterministic(cuda):
+    """The clip norm and the batch loss are reduced in a fixed order: repeated calls give the same bits (data-parallel replicas that
+    hold the same all-reduced gradient must compute the same clip coefficient, or their parameters drift apart), and both agree with
+    a double-precision reference."""
+    lib = L.load()
+    g = torch.randn(12_600_000, generator=torch.Generator().manual_seed(1)).cuda()
+    outs = []
+    for _ in range(4):
+        o = torch.zeros(1, device="cuda")
+        L.check(lib.ta_grad_sumsq(L.ptr(g), g.numel(), L.ptr(o), L.stream_ptr()))
+        L.check(lib.ta_grad_sumsq(L.ptr(g[:1000]), 1000, L.ptr(o), L.stream_ptr()))        # accumulates over several tensors
+        outs.append(o.clone())
+    assert all(torch.equal(outs[0], x) for x in outs[1:])
+    ref = float(g.double().pow(2).sum() + g[:1000].double().pow(2).sum())
+    assert abs(float(outs[0]) - ref) < 2e-7 * ref
+    R, V, Vp = 517, 1000, 1024
+    logits = rnd(R, Vp, seed=3, scale=3.0)
+    tg = torch.randint(0, V, (R,), generator=torch.Generator().manual_seed(4)).int().cuda()
+    losses = []
+    for _ in range(3):
+        lg = logits.clone()
+        loss = torch.zeros(1, device="cuda")
+        rows = torch.empty(R, device="cuda")
+        L.check(lib.ta_ce_fwd_bwd(L.ptr(lg), Vp, L.ptr(tg), R, V, Vp, 1.0 / R, L.ptr(loss), L.ptr(rows), 1, L.stream_ptr()))
+        losses.append(loss.clone())
+    assert all(torch.equal(losses[0], x) for x in losses[1:])
+    ref = float(F.cross_entropy(logits[:, :V].double(), tg.long(), reduction="sum") / R)
+    assert abs(float(losses[0]) - ref) < 2e-6 * abs(ref)
