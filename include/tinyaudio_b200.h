@@ -312,6 +312,8 @@ typedef struct ta_lm_step_args {
        real token of each sequence -- keys before it are never attended to by real tokens.  NULL: arange(S) / no padding. */
     const int* position_ids;
     const int* kv_start;
+    int lora_grads_zeroed;        /* != 0: the caller cleared every buffer in lora_grads before the call (one memset per stacked tensor
+                                     instead of one in front of each of the 8 split-K gradient products per layer) */
 } ta_lm_step_args;
 /* with_backward: 0 forward only; 1 backward to inputs_embeds (frozen LM, LoRA); 2 additionally the weight gradients (lm_grads) */
 int ta_lm_set_fused_attn_dsum(int on); /* 1 (default): the attention backward's D = rowsum(dO o O) comes out of the o-projection dgrad GEMM's epilogue (TA_EPI_BF16_ROWDOT); 0: separate preparation kernel */

@@ -216,6 +216,8 @@ struct LmBufs {
     bf16* logits;      // [n_lab, Vpad]
     bf16* dhl;         // [n_lab, D]
     float* row_loss;   // [n_lab] per-row CE losses (reduced in a fixed order)
+    int h_layers;      // 1: h is kept per layer (LoRA / unfrozen decoder with backward)
+    int lora_zeroed;   // the caller cleared every LoRA gradient buffer before the step (ta_lm_step_args.lora_grads_zeroed)
     bf16* dxb;         // [M, D + P]
     bf16* big;         // [M, max(2F, QKV) + P]
     bf16* dxn;         // [M, D]
@@ -249,7 +251,10 @@ long long lm_carve(const ta_lm_weights* w, int B, int S, int n_lab, int with_bwd
     b->gu = c.take<bf16>(L * M * 2 * F);
     b->lt = c.take<bf16>(P ? L * 3 * M * P : 0);
     b->xn = c.take<bf16>(M * (D + P));
-    b->h = c.take<bf16>(M * (F + P));
+    // h = silu(gate) * up is the input of down_proj: recipes that need its weight / adapter gradients keep it per layer (2.7 GB at the
+    // headline shape) instead of recomputing it from the (gate, up) stash in the backward (1.5 ms per step)
+    b->h_layers = (with_bwd && (P || train_lm)) ? 1 : 0;
+    b->h = c.take<bf16>((b->h_layers ? (long long)w->n_layers : 1) * M * (F + P));
     b->hl = c.take<bf16>((long long)n_lab * D);
     b->logits = c.take<bf16>((long long)n_lab * w->vocab_pad);
     b->dhl = c.take<bf16>((long long)n_lab * D);
@@ -289,8 +294,8 @@ inline int plain(const void* A, long long lda, const void* Bm, long long ldb, lo
 int lora_wgrad(const LmBufs& b, long long M, int P, const bf16* dy, long long ld_dy, int n_out, const bf16* t, long long ld_t,
                const bf16* u, long long ld_u, const bf16* x, long long ld_x, int k_in, float* dA, float* dBs, cudaStream_t st) {
     if (!g_wgrad_transposed) {
-        RUN(ta_gemm_bf16_tn(dy, ld_dy, t, ld_t, n_out, P, (int)M, dBs, P, 1.0f, st));
-        RUN(ta_gemm_bf16_tn(u, ld_u, x, ld_x, P, k_in, (int)M, dA, k_in, 1.0f, st));
+        RUN(k_gemm_bf16_tn(dy, ld_dy, t, ld_t, n_out, P, (int)M, dBs, P, 1.0f, st, b.lora_zeroed));
+        RUN(k_gemm_bf16_tn(u, ld_u, x, ld_x, P, k_in, (int)M, dA, k_in, 1.0f, st, b.lora_zeroed));
         return 0;
     }
     const long long Mp = (M + 7) / 8 * 8;
@@ -353,6 +358,7 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
     TA_REQUIRE(!(G_all && P), "LoRA adapters and an unfrozen LM are mutually exclusive (asr_modeling.py:251-301)");
     TA_REQUIRE(!G_all || (a->d_embed && a->d_final_norm && a->input_ids), "unfrozen LM: d_embed / d_final_norm / input_ids missing");
     const long long need = lm_carve(w, B, S, nl, a->with_backward != 0, a->workspace, a->workspace_bytes, &b, G_all != nullptr);
+    b.lora_zeroed = a->lora_grads_zeroed;
     TA_REQUIRE(need <= a->workspace_bytes, "LM workspace too small: need %lld, have %lld", need, a->workspace_bytes);
     if (M == 0) return 0;
     const long long sl = b.stride_layers;
@@ -399,12 +405,13 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
             RUN(plain(b.xn, ldX, Lw[TA_LM_LORA_A_GU], D, M, P, D, b.xn + D, ldX, st));
             TA_CHECK_CUDA(cudaMemcpy2DAsync(lt + M * P, P * 2, b.xn + D, ldX * 2, P * 2, M, cudaMemcpyDeviceToDevice, st));
         }
-        RUN(gemm(b.xn, ldX, Lw[TA_LM_WGU], ldX, M, 2 * F, D + P, TA_EPI_SWIGLU, b.h, ldH, nullptr, nullptr, gu, 2 * F, nullptr, 0, st));
+        bf16* h_l = b.h + (b.h_layers ? (long long)l * M * ldH : 0);
+        RUN(gemm(b.xn, ldX, Lw[TA_LM_WGU], ldX, M, 2 * F, D + P, TA_EPI_SWIGLU, h_l, ldH, nullptr, nullptr, gu, 2 * F, nullptr, 0, st));
         if (P) {
-            RUN(plain(b.h, ldH, Lw[TA_LM_LORA_A_D], F, M, P, F, b.h + F, ldH, st));
-            TA_CHECK_CUDA(cudaMemcpy2DAsync(lt + 2 * M * P, P * 2, b.h + F, ldH * 2, P * 2, M, cudaMemcpyDeviceToDevice, st));
+            RUN(plain(h_l, ldH, Lw[TA_LM_LORA_A_D], F, M, P, F, h_l + F, ldH, st));
+            TA_CHECK_CUDA(cudaMemcpy2DAsync(lt + 2 * M * P, P * 2, h_l + F, ldH * 2, P * 2, M, cudaMemcpyDeviceToDevice, st));
         }
-        RUN(gemm(b.h, ldH, Lw[TA_LM_WD], ldH, M, D, F + P, TA_EPI_F32_RESID, x_out, D, nullptr, x_mid, nullptr, 0, nullptr, 0, st));
+        RUN(gemm(h_l, ldH, Lw[TA_LM_WD], ldH, M, D, F + P, TA_EPI_F32_RESID, x_out, D, nullptr, x_mid, nullptr, 0, nullptr, 0, st));
         x_in = x_out;
     }
     const float* x_final = x_in;
@@ -454,16 +461,17 @@ TA_API int ta_lm_forward_backward(const ta_lm_weights* w, const ta_lm_step_args*
         const float* x_l = (l == 0) ? a->inputs_embeds : (b.resid + (long long)l * M * D);
 
         // ---- MLP branch: b.dxb = bf16(d x_out) ----
+        bf16* h_b = b.h + (b.h_layers ? (long long)l * M * ldH : 0);
         if (P) {
             RUN(plain(b.dxb, ldX, Lw[TA_LM_LORA_BT_D], D, M, P, D, b.dxb + D, ldX, st));          // u_d = dy (s B_d)
-            RUN(k_swiglu_h(gu, b.h, M, F, ldH, st));                                               // x of down_proj
-            RUN(lora_wgrad(b, M, P, b.dxb, ldX, D, lt + 2 * M * P, P, b.dxb + D, ldX, b.h, ldH, F, Lg[TA_LM_LORA_DA_D],
+            if (!b.h_layers) RUN(k_swiglu_h(gu, h_b, M, F, ldH, st));                              // x of down_proj (kept per layer otherwise)
+            RUN(lora_wgrad(b, M, P, b.dxb, ldX, D, lt + 2 * M * P, P, b.dxb + D, ldX, h_b, ldH, F, Lg[TA_LM_LORA_DA_D],
                            Lg[TA_LM_LORA_DB_D], st));
         }
         float* const* Gl = G_all ? G_all + (long long)l * TA_LM_GRADS_PER_LAYER : nullptr;
-        if (Gl) {   // down_proj: x = h = silu(gate) * up recomputed from the stash
-            RUN(k_swiglu_h(gu, b.h, M, F, ldH, st));
-            RUN(full_wgrad(b, M, b.dxb, ldX, D, b.h, ldH, F, Gl[TA_LM_G_WD], st));
+        if (Gl) {   // down_proj: x = h = silu(gate) * up, kept per layer by the forward
+            if (!b.h_layers) RUN(k_swiglu_h(gu, h_b, M, F, ldH, st));
+            RUN(full_wgrad(b, M, b.dxb, ldX, D, h_b, ldH, F, Gl[TA_LM_G_WD], st));
         }
         RUN(gemm(b.dxb, ldX, Lw[TA_LM_WD_T], ldX, M, F, D + P, TA_EPI_SWIGLU_BWD, b.big, ldBig, nullptr, nullptr, nullptr, 0, gu, 2 * F,
                  st));

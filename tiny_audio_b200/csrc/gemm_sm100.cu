@@ -1357,8 +1357,17 @@ TA_API int ta_gemm_set_cta_pair(int on) {
 }
 
 // C fp32 [M, N] = alpha * At^T . Bt,  At bf16 [K, M] (ld ldat), Bt bf16 [K, N] (ld ldbt): weight gradients dW = dY^T X
+int k_gemm_bf16_tn(const void* At, long long ldat, const void* Bt, long long ldbt, int M, int N, int K, float* out, long long ldo, float alpha,
+                   void* stream, int out_zeroed);
 TA_API int ta_gemm_bf16_tn(const void* At, long long ldat, const void* Bt, long long ldbt, int M, int N, int K, float* out, long long ldo,
                            float alpha, void* stream) {
+    return k_gemm_bf16_tn(At, ldat, Bt, ldbt, M, N, K, out, ldo, alpha, stream, 0);
+}
+
+// out_zeroed != 0: the caller has already cleared `out` (the LoRA engine clears all adapters' gradient buffers with a handful of
+// memsets per step instead of one per split-K product: 224 of them)
+int k_gemm_bf16_tn(const void* At, long long ldat, const void* Bt, long long ldbt, int M, int N, int K, float* out, long long ldo, float alpha,
+                   void* stream, int out_zeroed) {
     TA_REQUIRE(At && Bt && out, "ta_gemm_bf16_tn: null pointer");
     TA_REQUIRE(M > 0 && N > 0 && K > 0, "ta_gemm_bf16_tn: empty problem M=%d N=%d K=%d", M, N, K);
     TA_REQUIRE(N % 128 == 0, "ta_gemm_bf16_tn: N=%d must be a multiple of 128", N);
@@ -1389,7 +1398,8 @@ TA_API int ta_gemm_bf16_tn(const void* At, long long ldat, const void* Bt, long 
             const int kb_per = (num_kb + splits - 1) / splits;
             splits = (num_kb + kb_per - 1) / kb_per;          // no empty k range
             ep.k_splits = splits;
-            TA_CHECK_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+            if (!out_zeroed)
+                TA_CHECK_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
             if (bn == 256) return launch2<256, TA_EPI_F32, true, true>(ta, tb, tc, tc, M, N, K, ep, st);
             return launch2<128, TA_EPI_F32, true, true>(ta, tb, tc, tc, M, N, K, ep, st);
         }

@@ -571,13 +571,19 @@ class HotPath:
         demb = self.ws.typed("d_inputs_embeds", (B * S, d.lm_dim), F32) if with_backward else None
         row_loss = torch.empty(nl, device=self.device, dtype=F32) if want_row_loss else None
         hid = self.ws.typed("final_hidden", (B * S, d.lm_dim), F32) if want_hidden else None
+        lora_zeroed = 0
+        if with_backward and self.lm.grad_table is not None:        # LoRA: clear the 8 stacked gradient tensors once, not per product
+            for g in self.lm.lora_da:
+                self.lm.lora_da[g].zero_()
+                self.lm.lora_db[g].zero_()
+            lora_zeroed = 1
         args = L.LmStepArgs(B, S, nl, int(with_backward), L.ptr(emb), L.ptr(rows), L.ptr(targets), inv_items, L.ptr(loss),
                             L.ptr(row_loss), L.ptr(demb), L.ptr(ws), n.value, L.ptr(hid),
                             C.cast(self.lm.grad_table, C.POINTER(L.P)) if (with_backward and self.lm.grad_table is not None) else None,
                             None, None, 0,
                             C.cast(self.lm.wgrad_table, C.POINTER(L.P)) if train_lm else None,
                             L.ptr(self.lm.wgrad["embed"]) if train_lm else None, L.ptr(self.lm.wgrad["fnorm"]) if train_lm else None,
-                            L.ptr(input_ids) if train_lm else None, d.audio_token_id, None, None)
+                            L.ptr(input_ids) if train_lm else None, d.audio_token_id, None, None, lora_zeroed)
         L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
         return loss, demb, row_loss
 
@@ -595,7 +601,7 @@ class HotPath:
         hid = self.ws.typed("final_hidden", (B * S, d.lm_dim), F32)
         kc, vc, ms = kv_cache if kv_cache is not None else (None, None, 0)
         args = L.LmStepArgs(B, S, 0, 0, L.ptr(emb), None, None, 1.0, L.ptr(loss), None, None, L.ptr(ws), n.value, L.ptr(hid), None,
-                            L.ptr(kc), L.ptr(vc), ms, None, None, None, None, 0, L.ptr(position_ids), L.ptr(kv_start))
+                            L.ptr(kc), L.ptr(vc), ms, None, None, None, None, 0, L.ptr(position_ids), L.ptr(kv_start), 0)
         L.check(self.lib.ta_lm_forward_backward(C.byref(self.lm.c), C.byref(args), L.stream_ptr()))
         return hid
 

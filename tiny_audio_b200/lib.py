@@ -63,7 +63,7 @@ class LmStepArgs(C.Structure):
                 ("loss", P), ("row_loss", P), ("d_inputs_embeds", P), ("workspace", P), ("workspace_bytes", c_ll),
                 ("final_hidden", P), ("lora_grads", C.POINTER(P)), ("k_cache", P), ("v_cache", P), ("cache_max_seq", c_int),
                 ("lm_grads", C.POINTER(P)), ("d_embed", P), ("d_final_norm", P), ("input_ids", P), ("audio_token_id", c_ll),
-                ("position_ids", P), ("kv_start", P)]
+                ("position_ids", P), ("kv_start", P), ("lora_grads_zeroed", c_int)]
 
 
 _SIGS = {
