@@ -129,6 +129,22 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi);
+// Round two floats to bf16 precision through ONE packed conversion (F2FP.BF16.F32.PACK_AB) + two integer ops.  A scalar
+// __float2bfloat16_rn is an F2F.BF16.F32, which issues on the XU pipe next to MUFU (16 / clk / SM): the SwiGLU-backward epilogue spent
+// as much XU time on its two roundings per element as on the sigmoid's ex2 + rcp (ncu: XU pipe 50 % of the kernel, F2F on the hot list).
+__device__ __forceinline__ void bf16_round_pair(float& a, float& b) {
+    const uint32_t p = pack_bf16x2(a, b);
+    a = __uint_as_float(p << 16);
+    b = __uint_as_float(p & 0xffff0000u);
+}
+template <int N>
+__device__ __forceinline__ void bf16_round_all(float (&v)[N]) {
+    static_assert(N % 2 == 0, "pairs");
+#pragma unroll
+    for (int i = 0; i < N; i += 2) bf16_round_pair(v[i], v[i + 1]);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

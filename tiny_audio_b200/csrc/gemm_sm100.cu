@@ -515,12 +515,19 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
                 tmem_ld_32x32(taddr + sb * 128 + c * 32, rg);
                 tmem_ld_32x32(taddr + sb * 128 + 64 + c * 32, ru);
                 tmem_ld_wait();
-                float h[32];
+                float h[32], gg[32], uu[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float g = bf16_round(__uint_as_float(rg[i])), u = bf16_round(__uint_as_float(ru[i]));
-                    h[i] = bf16_round(g * sigmoidf_(g)) * u;
+                    gg[i] = __uint_as_float(rg[i]);
+                    uu[i] = __uint_as_float(ru[i]);
                 }
+                bf16_round_all(gg);
+                bf16_round_all(uu);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) h[i] = gg[i] * sigmoidf_(gg[i]);
+                bf16_round_all(h);                      // act_fn output is bf16 under autocast
+#pragma unroll
+                for (int i = 0; i < 32; ++i) h[i] *= uu[i];
                 stage_bf16x32(hrow, r, c, h);
             }
             sg.end(tmC, (int)((tile_col0 + sb * 128) / 2), tile_row0);
@@ -596,6 +603,11 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
                     }
                 }
             }
+            // the linear layer's output is bf16 under autocast: round it ONCE here, in pairs (bf16_round_pair), for every epilogue that
+            // continues to compute with it
+            if constexpr (EPI == TA_EPI_BF16_ROPE || EPI == TA_EPI_BF16_GELU || EPI == TA_EPI_BF16_RESID || EPI == TA_EPI_F32_RESID ||
+                          EPI == TA_EPI_BF16_ROWDOT || EPI == TA_EPI_SWIGLU_BWD)
+                bf16_round_all(v);
             if constexpr (EPI == TA_EPI_BF16_ROPE) {
                 if (col < ep.rope_cols && (col & 63) == 0) {
                     const int pos = (int)(row % ep.rope_seq);
@@ -610,31 +622,31 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float x1 = bf16_round(v[i]), x2 = bf16_round(v[i + 16]);
+                        const float x1 = v[i], x2 = v[i + 16];
                         v[i] = x1 * cs[i] - x2 * sn[i];
                         v[i + 16] = x2 * cs[i] + x1 * sn[i];
                     }
                 }
             } else if constexpr (EPI == TA_EPI_BF16_GELU) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(bf16_round(v[i]));
+                for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
             } else if constexpr (EPI == TA_EPI_BF16_RESID) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float2 a = unpack_bf16x2(cur[i].x), b = unpack_bf16x2(cur[i].y), cc = unpack_bf16x2(cur[i].z),
                                  d = unpack_bf16x2(cur[i].w);
-                    v[8 * i + 0] = a.x + bf16_round(v[8 * i + 0]); v[8 * i + 1] = a.y + bf16_round(v[8 * i + 1]);
-                    v[8 * i + 2] = b.x + bf16_round(v[8 * i + 2]); v[8 * i + 3] = b.y + bf16_round(v[8 * i + 3]);
-                    v[8 * i + 4] = cc.x + bf16_round(v[8 * i + 4]); v[8 * i + 5] = cc.y + bf16_round(v[8 * i + 5]);
-                    v[8 * i + 6] = d.x + bf16_round(v[8 * i + 6]); v[8 * i + 7] = d.y + bf16_round(v[8 * i + 7]);
+                    v[8 * i + 0] = a.x + v[8 * i + 0]; v[8 * i + 1] = a.y + v[8 * i + 1];
+                    v[8 * i + 2] = b.x + v[8 * i + 2]; v[8 * i + 3] = b.y + v[8 * i + 3];
+                    v[8 * i + 4] = cc.x + v[8 * i + 4]; v[8 * i + 5] = cc.y + v[8 * i + 5];
+                    v[8 * i + 6] = d.x + v[8 * i + 6]; v[8 * i + 7] = d.y + v[8 * i + 7];
                 }
             } else if constexpr (EPI == TA_EPI_F32_RESID) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    v[4 * i + 0] = __uint_as_float(cur[i].x) + bf16_round(v[4 * i + 0]);
-                    v[4 * i + 1] = __uint_as_float(cur[i].y) + bf16_round(v[4 * i + 1]);
-                    v[4 * i + 2] = __uint_as_float(cur[i].z) + bf16_round(v[4 * i + 2]);
-                    v[4 * i + 3] = __uint_as_float(cur[i].w) + bf16_round(v[4 * i + 3]);
+                    v[4 * i + 0] = __uint_as_float(cur[i].x) + v[4 * i + 0];
+                    v[4 * i + 1] = __uint_as_float(cur[i].y) + v[4 * i + 1];
+                    v[4 * i + 2] = __uint_as_float(cur[i].z) + v[4 * i + 2];
+                    v[4 * i + 3] = __uint_as_float(cur[i].w) + v[4 * i + 3];
                 }
             } else if constexpr (EPI == TA_EPI_F32) {
 #pragma unroll
@@ -645,9 +657,9 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
                     for (int i = 0; i < 4; ++i) {
                         const float2 a = unpack_bf16x2(cur[i].x), b = unpack_bf16x2(cur[i].y), cc = unpack_bf16x2(cur[i].z),
                                      d = unpack_bf16x2(cur[i].w);
-                        rowdot += bf16_round(v[8 * i + 0]) * a.x + bf16_round(v[8 * i + 1]) * a.y + bf16_round(v[8 * i + 2]) * b.x +
-                                  bf16_round(v[8 * i + 3]) * b.y + bf16_round(v[8 * i + 4]) * cc.x + bf16_round(v[8 * i + 5]) * cc.y +
-                                  bf16_round(v[8 * i + 6]) * d.x + bf16_round(v[8 * i + 7]) * d.y;
+                        rowdot += v[8 * i + 0] * a.x + v[8 * i + 1] * a.y + v[8 * i + 2] * b.x +
+                                  v[8 * i + 3] * b.y + v[8 * i + 4] * cc.x + v[8 * i + 5] * cc.y +
+                                  v[8 * i + 6] * d.x + v[8 * i + 7] * d.y;
                     }
                 }
             }
@@ -665,7 +677,7 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int k = 8 * i + 2 * t + e;
-                            const float dh = bf16_round(v[k]);
+                            const float dh = v[k];
                             const float sgm = sigmoidf_(gq[e]);
                             du[k] = dh * bf16_round(gq[e] * sgm);
                             dg[k] = dh * uq[e] * (sgm * (1.0f + gq[e] * (1.0f - sgm)));
@@ -764,12 +776,15 @@ __device__ __forceinline__ void epilogue_swiglu_bwd_inplace(uint32_t taddr, int 
                 const float2 g2 = unpack_bf16x2(gw[t]), u2 = unpack_bf16x2(uw[t]);
                 const float gq[2] = {g2.x, g2.y}, uq[2] = {u2.x, u2.y};
                 float dg[2], du[2];
+                float dh[2] = {__uint_as_float(rr[8 * k + 2 * t]), __uint_as_float(rr[8 * k + 2 * t + 1])};
+                bf16_round_pair(dh[0], dh[1]);
+                const float sgm[2] = {sigmoidf_(gq[0]), sigmoidf_(gq[1])};
+                float silu[2] = {gq[0] * sgm[0], gq[1] * sgm[1]};
+                bf16_round_pair(silu[0], silu[1]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const float dh = bf16_round(__uint_as_float(rr[8 * k + 2 * t + e]));
-                    const float sgm = sigmoidf_(gq[e]);
-                    du[e] = dh * bf16_round(gq[e] * sgm);
-                    dg[e] = dh * uq[e] * (sgm * (1.0f + gq[e] * (1.0f - sgm)));
+                    du[e] = dh[e] * silu[e];
+                    dg[e] = dh[e] * uq[e] * (sgm[e] * (1.0f + gq[e] * (1.0f - sgm[e])));
                 }
                 og[t] = pack_bf16x2(dg[0], dg[1]);
                 ou[t] = pack_bf16x2(du[0], du[1]);
