@@ -746,17 +746,17 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
 // ----------------------------------------------------------------------------------------------
 constexpr int SWB_SET_BYTES = 2 * 16384;    // gate box + up box
 
-template <int BN>
+template <int BN, int NSET>
 __device__ __forceinline__ void epilogue_swiglu_bwd_inplace(uint32_t taddr, int grp, int r, int lane, uint8_t* sbuf, uint64_t* ldf,
                                                             uint64_t* str, uint32_t& n) {
     constexpr int CPT = BN / 64;               // chunks per tile
     const int sw = r & 7;                      // SWIZZLE_128B: 16-byte piece index ^= row & 7
 #pragma unroll 1
     for (int i = 0; i < CPT; ++i, ++n) {
-        const uint32_t set = n & 1u;
+        const uint32_t set = n % NSET;
         uint32_t rr[32];
         tmem_ld_32x32(taddr + (uint32_t)(i * 64 + grp * 32), rr);
-        mbar_wait(&ldf[set], (n >> 1) & 1u);
+        mbar_wait(&ldf[set], (n / NSET) & 1u);
         uint8_t* gp = sbuf + set * SWB_SET_BYTES + r * 128;
         uint8_t* up = gp + 16384;
         uint4 g4[4], u4[4];
@@ -901,12 +901,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int M, int N, int K, EpiArgs ep) {
     using C = Cfg2<BN>;
+    // SwiGLU-backward in place: NSET box sets next to an NSTAGE-deep operand ring.  Tried 3 sets + a 3-stage ring (same 192 KB): the
+    // third set does not pay for the shallower ring -- 117.6 us vs 107.6 us with 2 sets + 4 stages at 14848 x 3072 x 1024 (call 45)
+    constexpr int NSTAGE = C::STAGES;
+    constexpr int NSET = 2;
+    static_assert(EPI != TA_EPI_SWIGLU_BWD || NSTAGE * C::STAGE_BYTES + NSET * SWB_SET_BYTES <= C::BAR_OFF, "in-place sets do not fit");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* smA = smem;
-    uint8_t* smB = smem + C::STAGES * C::A_BYTES;
-    uint8_t* smStage = smem + C::STG_OFF;
+    uint8_t* smB = smem + NSTAGE * C::A_BYTES;
+    uint8_t* smStage = smem + NSTAGE * C::STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
     uint64_t* full = bars;
     uint64_t* empty = bars + C::STAGES;
@@ -938,7 +943,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tma_prefetch_desc(&tmC2);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < C::STAGES; ++s) {
+        for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -947,7 +952,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_init(&tempty[s], 16);
         }
         if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < NSET; ++s) {
                 mbar_init(&swb_ld_full[s], 1);
                 mbar_init(&swb_st_ready[s], 8);      // one arrive per epilogue warp of both groups
             }
@@ -988,7 +993,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         tma_load_2d_2sm(smA + stage * C::A_BYTES, &tmA, &full[stage], kb * BK, row0);
                         tma_load_2d_2sm(smB + stage * C::B_BYTES, &tmB, &full[stage], kb * BK, nrow0);
                     }
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -1029,7 +1034,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         umma_commit_2sm(&empty[stage]);
                     }
                     __syncwarp();
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
                 if (issuer) umma_commit_2sm(&tfull[as]);
                 __syncwarp();
@@ -1057,11 +1062,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 auto load = [&](uint32_t n) {
                     int x, y;
                     coords(n, x, y);
-                    uint8_t* dst = smStage + (n & 1u) * SWB_SET_BYTES;
+                    uint8_t* dst = smStage + (n % NSET) * SWB_SET_BYTES;
                     if (issuer) {
-                        mbar_arrive_expect_tx(&ldf[n & 1u], SWB_SET_BYTES);
-                        tma_load_2d(dst, &tmC2, &ldf[n & 1u], x, y);
-                        tma_load_2d(dst + 16384, &tmC2, &ldf[n & 1u], x + 64, y);
+                        mbar_arrive_expect_tx(&ldf[n % NSET], SWB_SET_BYTES);
+                        tma_load_2d(dst, &tmC2, &ldf[n % NSET], x, y);
+                        tma_load_2d(dst + 16384, &tmC2, &ldf[n % NSET], x + 64, y);
                     }
                     __syncwarp();
                 };
@@ -1077,24 +1082,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         tma_prefetch_l2_2d(&tmC2, x + 64, y);
                     }
                 };
-                if (total > 0) load(0);
-                if (total > 1) load(1);
-                for (uint32_t n = 2; n < PF; ++n) prefetch(n);
+                for (uint32_t n = 0; n < (uint32_t)NSET && n < total; ++n) load(n);
+                for (uint32_t n = NSET; n < PF; ++n) prefetch(n);
                 for (uint32_t n = 0; n < total; ++n) {
                     prefetch(n + PF);
                     __syncwarp();
-                    mbar_wait(&str[n & 1u], (n >> 1) & 1u);
+                    mbar_wait(&str[n % NSET], (n / NSET) & 1u);
                     int x, y;
                     coords(n, x, y);
-                    const uint8_t* src = smStage + (n & 1u) * SWB_SET_BYTES;
+                    const uint8_t* src = smStage + (n % NSET) * SWB_SET_BYTES;
                     if (issuer) {
                         tma_store_2d(&tmC, src, x, y);
                         tma_store_2d(&tmC, src + 16384, x + 64, y);
                         tma_store_commit();
-                        if (n + 2 < total) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        if (n + NSET < total) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
                     __syncwarp();
-                    if (n + 2 < total) load(n + 2);
+                    if (n + NSET < total) load(n + NSET);
                 }
                 if (issuer) tma_store_wait_all();
                 __syncwarp();
@@ -1144,7 +1148,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             bool done = false;
             if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
                 if (ep.aux_tma) {
-                    epilogue_swiglu_bwd_inplace<BN>(taddr, grp, sg.r, lane, smStage, swb_ld_full, swb_st_ready, swb_n);
+                    epilogue_swiglu_bwd_inplace<BN, NSET>(taddr, grp, sg.r, lane, smStage, swb_ld_full, swb_st_ready, swb_n);
                     done = true;
                 }
             }
