@@ -840,7 +840,8 @@ int k_im2col_k3(const bf16* x, bf16* out, int B, int T, int C, int stride, cudaS
     return 0;
 }
 
-int g_norm_wpb = 8;     // warps (= rows) per block of the LayerNorm / RMSNorm kernels; ta_debug_set(3, n) for experiments (1..8)
+int g_norm_wpb = 4;     // warps (= rows) per block of the LayerNorm / RMSNorm kernels (ta_debug_set(3, n): 1..8).  tools/sweep_norms.py at the
+                        // production shapes: 4 is 2-5 % faster than 8 on all three kernels (profiles/r02_c31_sweep_norms.log)
 int g_ln_reverse = 1;   // ta_layernorm_set_reverse: A/B switch for the row order of the encoder LayerNorm (L2 reuse, see the kernel)
 int k_layernorm_bf16(const bf16* x, const float* w, const float* b, bf16* y, long long rows, int D, float eps, cudaStream_t st) {
     TA_REQUIRE(D % 256 == 0 && D <= 2048, "layernorm: D=%d must be a multiple of 256 and <= 2048", D);
