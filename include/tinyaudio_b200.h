@@ -76,6 +76,7 @@ int ta_gemm_set_tail_split(int on);
  * reduce-added into the (zeroed) fp32 output by TMA.  0 = off (default).  Experimental, not yet run on hardware. */
 int ta_gemm_set_tn_splitk(int on); /* 1: a mostly empty last wave of 256 x 256 tiles is issued as a second launch of 256 x 128 tiles (default 0:
                                        no gain under the 1 kW power cap, see gemm_sm100.cu) */
+int ta_gemm_set_resid_tma(int on); /* bf16-residual epilogue (encoder o-projection / fc2): 1 = residual sub-tiles in by TMA, sum out of the same shared-memory buffer; 0 = per-thread global loads */
 int ta_gemm_set_swiglu_bwd_tma(int on); /* 1 (default): SwiGLU-backward epilogue moves the (gate, up) stash and the gradients by TMA, in place in shared memory; 0: per-thread global loads */
 int ta_gemm_set_cta_pair(int on); /* 1: CTA-pair kernel (tcgen05 cta_group::2, 256 x N tiles); 0: 1-CTA kernel */
 

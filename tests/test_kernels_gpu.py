@@ -132,6 +132,31 @@ def test_gemm_rope_epilogue(cuda, pair):
     assert torch.equal(out, ref)
 
 
+@pytest.mark.parametrize("M,N,K,with_bias", [(300, 512, 192, True), (5000, 1280, 1280, True), (48000 // 8 + 33, 1280, 640, False), (128, 256, 64, True)])
+def test_gemm_resid_tma_epilogue_equals_per_thread_epilogue(cuda, M, N, K, with_bias):
+    """bf16-residual GEMM (encoder o-projection / fc2): the in-place TMA epilogue (residual sub-tiles in by TMA, sums out of the same
+    shared-memory buffers, one agent warp per epilogue group) gives the bits of the per-thread-load epilogue, also IN PLACE (out = resid,
+    as the encoder runs it), with a clipped M tail and several tiles per CTA pair."""
+    lib = L.load()
+    x, w = rnd(M, K, seed=31), rnd(N, K, seed=32, scale=0.05)
+    bias = rnd(N, dtype=F32, seed=33) if with_bias else None
+    r0 = rnd(M, N, seed=34)
+    out = {}
+    try:
+        for mode in (0, 1):
+            L.check(lib.ta_gemm_set_resid_tma(mode))
+            sep = L.gemm(x, w, epi=L.EPI_BF16_RESID, bias=bias, resid=r0)
+            inplace = r0.clone()
+            L.gemm(x, w, epi=L.EPI_BF16_RESID, bias=bias, resid=inplace, out=inplace)
+            assert torch.equal(sep, inplace)
+            out[mode] = sep
+    finally:
+        L.check(lib.ta_gemm_set_resid_tma(0))
+    assert torch.equal(out[0], out[1])
+    acc = x.float() @ w.float().t() + (bias if with_bias else 0.0)
+    assert rel_err(out[1], r0.float() + acc.to(BF16).float()) < 5e-3
+
+
 def test_gemm_rowdot_epilogue(cuda):
     """TA_EPI_BF16_ROWDOT: the plain bf16 GEMM output plus, per 128-wide head, the row sums of out * aux in [B, heads, S] layout -- the
     attention backward's D = rowsum(dO o O) fused into the o-projection dgrad (row tail, several waves, K with a remainder block)."""

@@ -733,6 +733,60 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t taddr, long long row,
 }
 
 // ----------------------------------------------------------------------------------------------
+// bf16 residual epilogue, in place through shared memory (pair kernel, ep.aux_tma): the agent warp of each epilogue group (warp 2 + grp)
+// TMA-loads the residual sub-tile [128 rows x 64 columns] into the group's staging buffer two sub-tiles ahead, every thread adds its
+// accumulator row into it, the agent stores the buffer.  No per-thread global loads (whose latency the short K = 1280 o-projection of
+// the encoder could not hide: 1 013 TFLOP/s against 1 260 for the other K = 1280 products).
+// ----------------------------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void epilogue_resid_bf16_inplace(uint32_t taddr, int grp, int r, int lane, uint8_t* gbuf, uint64_t* ldf,
+                                                            uint64_t* str, uint32_t& n, const float* s_bias, bool has_bias) {
+    constexpr int SPT = BN / 128;              // 64-column sub-tiles per tile and group
+    const int sw = r & 7;
+#pragma unroll 1
+    for (int sub = 0; sub < SPT; ++sub, ++n) {
+        const uint32_t set = n & 1u;
+        uint8_t* row_ptr = gbuf + set * STG_BYTES + r * 128;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            const int col_in_tile = (grp * SPT + sub) * 64 + c * 32;
+            uint32_t rr[32];
+            tmem_ld_32x32(taddr + (uint32_t)col_in_tile, rr);
+            if (c == 0) mbar_wait(&ldf[set], (n >> 1) & 1u);
+            uint4 x4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x4[k] = *reinterpret_cast<const uint4*>(row_ptr + (((c * 4 + k) ^ sw) << 4));
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+            if (has_bias) {
+                const float4* b4 = reinterpret_cast<const float4*>(s_bias + col_in_tile);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b = b4[i];
+                    v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                }
+            }
+            bf16_round_all(v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 a = unpack_bf16x2(x4[k].x), b = unpack_bf16x2(x4[k].y), cc = unpack_bf16x2(x4[k].z), d = unpack_bf16x2(x4[k].w);
+                uint4 o;
+                o.x = pack_bf16x2(a.x + v[8 * k + 0], a.y + v[8 * k + 1]);
+                o.y = pack_bf16x2(b.x + v[8 * k + 2], b.y + v[8 * k + 3]);
+                o.z = pack_bf16x2(cc.x + v[8 * k + 4], cc.y + v[8 * k + 5]);
+                o.w = pack_bf16x2(d.x + v[8 * k + 6], d.y + v[8 * k + 7]);
+                *reinterpret_cast<uint4*>(row_ptr + (((c * 4 + k) ^ sw) << 4)) = o;
+            }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&str[set]);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // SwiGLU-backward epilogue, in place through shared memory (pair kernel, ep.aux_tma).
 //   A "chunk" is 64 h columns of this CTA's 128 accumulator rows.  Its (gate, up) stash values -- two [128 x 64] bf16 boxes, 16 KB
 //   each, SWIZZLE_128B, i.e. whole 128-byte lines of the interleaved [M, 2F] layout -- are brought in by TMA by the agent warp
@@ -951,6 +1005,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], 16);
         }
+        if constexpr (EPI == TA_EPI_BF16_RESID) {      // [group][set]
+            for (int s = 0; s < 4; ++s) {
+                mbar_init(&swb_ld_full[s], 1);
+                mbar_init(&swb_st_ready[s], 4);      // one arrive per warp of the group
+            }
+        }
         if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
             for (int s = 0; s < NSET; ++s) {
                 mbar_init(&swb_ld_full[s], 1);
@@ -1040,6 +1100,51 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 __syncwarp();
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
+            }
+        }
+    } else if (EPI == TA_EPI_BF16_RESID && (warp == 2 || warp == 3)) {
+        // ===================== residual agent of epilogue group (warp - 2) =====================
+        if constexpr (EPI == TA_EPI_BF16_RESID) {
+            if (ep.aux_tma) {
+                constexpr int SPT = BN / 128;
+                const int grp = warp - 2;
+                uint8_t* gbuf = smStage + grp * 2 * STG_BYTES;
+                uint64_t* ldf = swb_ld_full + 2 * grp;
+                uint64_t* str = swb_st_ready + 2 * grp;
+                const bool issuer = elect_one();
+                const int my_tiles = pair < num_work ? (num_work - pair + n_pairs - 1) / n_pairs : 0;
+                const uint32_t total = (uint32_t)(my_tiles * SPT);
+                auto coords = [&](uint32_t n, int& x, int& y) {
+                    const int tile = pair + (int)(n / SPT) * n_pairs;
+                    const int n_blk = tile % tiles_n, m_blk = tile / tiles_n;
+                    x = n_blk * BN + (grp * SPT + (int)(n % SPT)) * 64;
+                    y = m_blk * 2 * BM + (int)rank * BM;
+                };
+                auto load = [&](uint32_t n) {
+                    int x, y;
+                    coords(n, x, y);
+                    if (issuer) {
+                        mbar_arrive_expect_tx(&ldf[n & 1u], STG_BYTES);
+                        tma_load_2d(gbuf + (n & 1u) * STG_BYTES, &tmC2, &ldf[n & 1u], x, y);
+                    }
+                    __syncwarp();
+                };
+                if (total > 0) load(0);
+                if (total > 1) load(1);
+                for (uint32_t n = 0; n < total; ++n) {
+                    mbar_wait(&str[n & 1u], (n >> 1) & 1u);
+                    int x, y;
+                    coords(n, x, y);
+                    if (issuer) {
+                        tma_store_2d(&tmC, gbuf + (n & 1u) * STG_BYTES, x, y);
+                        tma_store_commit();
+                        if (n + 2 < total) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    __syncwarp();
+                    if (n + 2 < total) load(n + 2);
+                }
+                if (issuer) tma_store_wait_all();
+                __syncwarp();
             }
         }
     } else if (EPI == TA_EPI_SWIGLU_BWD && warp == 2) {
@@ -1146,6 +1251,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const bool row_ok = row < M;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
             bool done = false;
+            if constexpr (EPI == TA_EPI_BF16_RESID) {
+                if (ep.aux_tma) {
+                    epilogue_resid_bf16_inplace<BN>(taddr, grp, sg.r, lane, sg.buf, swb_ld_full + 2 * grp, swb_st_ready + 2 * grp, swb_n, s_bias,
+                                                    ep.bias != nullptr);
+                    done = true;
+                }
+            }
             if constexpr (EPI == TA_EPI_SWIGLU_BWD) {
                 if (ep.aux_tma) {
                     epilogue_swiglu_bwd_inplace<BN, NSET>(taddr, grp, sg.r, lane, smStage, swb_ld_full, swb_st_ready, swb_n);
@@ -1338,6 +1450,7 @@ int g_force_bn = 0;
 int g_tail_split = 0; // 1: split off a poorly filled last wave into 256 x 128 tiles (ta_gemm_set_tail_split).  Off by default: on the
                       // power-capped B200 the step did not get faster (130.4 vs 129.3 ms) -- SMs idling in a short last wave hand their
                       // power budget to the busy ones, which then clock higher, so the quantisation loss is mostly virtual here.
+int g_resid_tma = 0;        // 1: in-place TMA epilogue for the bf16 residual GEMMs (ta_gemm_set_resid_tma); 0: per-thread residual loads
 int g_swiglu_bwd_tma = 1;   // 1 (default): in-place TMA epilogue for SwiGLU-backward (ta_gemm_set_swiglu_bwd_tma); 0: per-thread loads
 int g_cta_pair = 1;   // 1 (default): CTA-pair kernel (cta_group::2, 256 x N tiles); 0: 1-CTA kernel (cta_group::1)
 
@@ -1362,6 +1475,11 @@ TA_API int ta_gemm_set_tail_split(int on) {
 int g_tn_splitk = 1;
 TA_API int ta_gemm_set_tn_splitk(int on) {
     g_tn_splitk = on ? 1 : 0;
+    return 0;
+}
+
+TA_API int ta_gemm_set_resid_tma(int on) {
+    g_resid_tma = on ? 1 : 0;
     return 0;
 }
 
@@ -1489,6 +1607,11 @@ TA_API int ta_gemm_bf16(const void* A, long long lda, const void* B, long long l
             if (swb_tma) {
                 r2 = make_map(&tc2, e2.aux, rows, 2LL * N, e->ldaux, BM, false);
                 if (r2) return r2;
+            }
+            if (epi == TA_EPI_BF16_RESID && g_resid_tma && bnp == 256) {      // residual sub-tiles come in by TMA, the sum leaves from the same buffer
+                r2 = make_map(&tc2, e2.resid, rows, N, ep.ldr, BM, false);
+                if (r2) return r2;
+                e2.aux_tma = 1;
             }
             if (epi == TA_EPI_BF16_ROWDOT && e->zero_f32) {      // fp32 [rows, N] buffer to be zero-filled alongside the output
                 r2 = make_map(&tc2, reinterpret_cast<uint8_t*>(e->zero_f32) + row0 * e->ld_zero * 4, rows, N, e->ld_zero, BM, true);

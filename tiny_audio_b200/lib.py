@@ -73,6 +73,7 @@ _SIGS = {
     "ta_gemm_bf16": ([P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, C.POINTER(GemmEpilogue), P], c_int),
     "ta_gemm_bf16_tn": ([P, c_ll, P, c_ll, c_int, c_int, c_int, P, c_ll, c_float, P], c_int),
     "ta_gemm_set_tile_n": ([c_int], c_int),
+    "ta_gemm_set_resid_tma": ([c_int], c_int),
     "ta_gemm_set_swiglu_bwd_tma": ([c_int], c_int),
     "ta_gemm_set_cta_pair": ([c_int], c_int),
     "ta_gemm_set_tail_split": ([c_int], c_int),
@@ -171,6 +172,8 @@ def load() -> C.CDLL:
         lib.ta_gemm_set_cta_pair(int(os.environ["TA_GEMM_CTA_PAIR"]))
     if os.environ.get("TA_GEMM_TN_SPLITK") is not None:
         lib.ta_gemm_set_tn_splitk(int(os.environ["TA_GEMM_TN_SPLITK"]))
+    if os.environ.get("TA_GEMM_RESID_TMA") is not None:
+        lib.ta_gemm_set_resid_tma(int(os.environ["TA_GEMM_RESID_TMA"]))
     if os.environ.get("TA_GEMM_SWIGLU_BWD_TMA") is not None:
         lib.ta_gemm_set_swiglu_bwd_tma(int(os.environ["TA_GEMM_SWIGLU_BWD_TMA"]))
     if os.environ.get("TA_LN_REVERSE") is not None:

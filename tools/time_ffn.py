@@ -59,3 +59,15 @@ lib.ta_gemm_set_tail_split(0)
 lib.ta_gemm_set_tile_n(128)
 report([("down + fp32 residual, 256x128 tiles", rows[3][1], fl_d)])
 lib.ta_gemm_set_tile_n(0)
+
+# encoder bf16-residual GEMMs: per-thread residual loads vs the in-place TMA epilogue
+Me = 48000
+for name, N_, K_ in (("enc o + residual 48000x1280x1280", 1280, 1280), ("enc fc2 + residual 48000x1280x5120", 1280, 5120)):
+    xe = torch.randn(Me, K_, device=dev, dtype=BF16)
+    we = torch.randn(N_, K_, device=dev, dtype=BF16) * 0.03
+    be = torch.zeros(N_, device=dev, dtype=F32)
+    re_ = torch.zeros(Me, N_, device=dev, dtype=BF16)
+    for mode in (0, 1):
+        lib.ta_gemm_set_resid_tma(mode)
+        report([(f"{name} [resid_tma={mode}]", lambda: L.gemm(xe, we, epi=L.EPI_BF16_RESID, bias=be, resid=re_, out=re_), 2.0 * Me * N_ * K_)])
+lib.ta_gemm_set_resid_tma(0)
