@@ -420,3 +420,12 @@ def test_generate_rejects_settings_it_would_otherwise_ignore():
     m.generation_config.repetition_penalty = 1.1            # set through the config, not the call
     with pytest.raises(NotImplementedError, match="repetition_penalty"):
         m.generate(input_ids=ids, input_features=x)
+
+
+def test_device_prefetcher_refuses_cpu_targets_and_imports_without_cuda():
+    """tiny_audio_b200.prefetch has no CPU mode (like the rest of the package it stages onto a CUDA device or raises)."""
+    import pytest as _pytest
+    from tiny_audio_b200.prefetch import DEVICE_KEYS, DevicePrefetcher
+    assert "input_features" in DEVICE_KEYS and "labels" not in DEVICE_KEYS       # labels stay on the host: no device sync for the row list
+    with _pytest.raises(ValueError):
+        DevicePrefetcher([], device="cpu")
